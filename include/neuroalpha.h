@@ -1,0 +1,153 @@
+/*
+ * neuroalpha.h -- C ABI of libneuroalpha_b200.so (sm_100a).
+ *
+ * This is the drop-in boundary for the NeuroAlpha decoder hot path
+ * (aa217/Neural-Speech-Decoding).  The reference has no FFI / plugin layer: its only
+ * interface for this path is the Python class `EEG_LSTM` and its callers
+ *     Neuro-Alpha-App/Utilities/lstm_eeg_model.py:13-39   EEG_LSTM.__init__/forward
+ *     Neuro-Alpha-App/Utilities/lstm_eeg_model.py:86-101  SimplePredictor.predict
+ *     Neuro-Alpha-App/Utilities/tester.py:54,89,97        run_trials probability averaging
+ *     Neuro-Alpha-App/Frontend/app.py:166-170             normalize_eeg (z-score)
+ * Each entry point below names the reference lines whose arithmetic it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer on the current CUDA device, contiguous and
+ *     16-byte aligned, allocated and owned by the caller.  Kernels never allocate.
+ *   - Launches are asynchronous on `stream` (a cudaStream_t passed as void*); there
+ *     is no hidden synchronisation and no global mutable state except a thread-local
+ *     error string.
+ *   - Return value: 0 = ok; >0 = cudaError_t of a failed launch; <0 = NA_E* below.
+ *     No exception crosses the ABI; na_last_error() gives the message.
+ *   - "time-major padded" (TMP) layout: [T][Bp][F] fp32, Bp = batch rounded up to a
+ *     multiple of NA_BATCH_ALIGN; rows b >= B are padding and hold finite values.
+ *   - Gate order everywhere is torch's [i, f, g, o] (lstm_eeg_model.py:16-22 -> nn.LSTM).
+ */
+#ifndef NEUROALPHA_H_
+#define NEUROALPHA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NA_VERSION 100          /* 0.1.0 */
+#define NA_BATCH_ALIGN 32       /* Bp granularity of the TMP layout */
+#define NA_FC_HIDDEN 32         /* lstm_eeg_model.py:26 -- fc hidden width is fixed at 32 */
+#define NA_MAX_CLASSES 16
+
+enum {
+    NA_OK = 0,
+    NA_EINVAL = -1,        /* bad shape / null pointer */
+    NA_EALIGN = -2,        /* pointer not 16-byte aligned */
+    NA_EUNSUPPORTED = -3,  /* size outside what the kernels implement */
+    NA_EDEVICE = -4        /* not an sm_100 device */
+};
+
+enum { NA_F32 = 0, NA_BF16 = 1 };
+
+typedef void* na_stream_t;      /* cudaStream_t */
+
+int na_version(void);
+const char* na_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t na_launch_count(void);
+
+/* ---- K1: windowing + optional per-window per-channel z-score -------------------------
+ * Replaces Frontend/app.py:166-170 (normalize_eeg: (x-mean)/(std+1e-6), population std,
+ * over the time axis) and the "latest int(window_seconds*sr) samples" windowing of
+ * Utilities/streaming_process.py:35,55.
+ *   x      [n_samples, C] fp32 stream; window w covers samples [w*hop, w*hop+T)
+ *          (a [B,T,C] batch is the case hop == T)
+ *   y      normalize ? z-scored : copied windows, fp32 or bf16 (out_dtype), in
+ *          out_tmp ? TMP layout [T][Bp][C] (rows >= B zero-filled) : [B][T][C]
+ */
+int na_window_zscore(const float* x, void* y, int64_t B, int64_t T, int64_t C, int64_t hop,
+                     int normalize, int out_tmp, int64_t Bp, int out_dtype, na_stream_t stream);
+
+/* ---- weight packing ---------------------------------------------------------------------
+ * nn.LSTM parameters of one layer (lstm_eeg_model.py:16-22; shapes SURVEY 8a):
+ *   w_ih [4H,K], w_hh [4H,H], b_ih [4H], b_hh [4H]  ->
+ *   wt   [(K+H)][4H]  k-major concatenation [W_ih | W_hh]^T,   bias [4H] = b_ih + b_hh
+ */
+int na_pack_lstm_layer(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                       float* wt, float* bias, int64_t K, int64_t H, na_stream_t stream);
+
+/* ---- K3: one LSTM layer, all timesteps, h0 = c0 = 0 -------------------------------------
+ * Replaces `self.lstm(x)` (lstm_eeg_model.py:34), one layer per call.
+ *   in    TMP [T][Bp][K]       hout TMP [T][Bp][H]
+ *   cout  TMP [T][Bp][H]  or NULL   (cell state, saved for backward)
+ *   gates TMP [T][Bp][4H] or NULL   (activated i,f,g,o, saved for backward)
+ *   drop_mask TMP [T][Bp][H] of 0/1 + hout_drop TMP [T][Bp][H], both or neither: inter-layer
+ *          dropout (lstm_eeg_model.py:21).  hout_drop = hout * mask * drop_scale
+ *          (drop_scale = 1/(1-p)) is what the next layer consumes; hout stays the raw h
+ *          (the recurrence and dW_hh need it).
+ */
+int na_lstm_layer_fwd_f32(const float* in, const float* wt, const float* bias,
+                          float* hout, float* cout, float* gates,
+                          const float* drop_mask, float drop_scale, float* hout_drop,
+                          int64_t T, int64_t Bp, int64_t K, int64_t H, na_stream_t stream);
+
+/* Fused BPTT of one layer.  dh_out TMP [T][Bp][H] is dLoss/d(hout).  Produces dgates TMP
+ * [T][Bp][4H] (pre-activation gate gradients) and, if din != NULL, din TMP [T][Bp][K] =
+ * dLoss/d(in); when in_drop_mask != NULL (the mask that produced this layer's input in the
+ * forward) din is multiplied by mask*drop_scale so it is directly the lower layer's dh_out.
+ * Weight gradients follow from dgates with na_lstm_layer_wgrad_f32.  w_ih [4H,K] / w_hh
+ * [4H,H] are the unpacked nn.LSTM tensors.
+ */
+int na_lstm_layer_bwd_f32(const float* dh_out, const float* gates, const float* cstate,
+                          const float* w_ih, const float* w_hh,
+                          float* dgates, float* din, const float* in_drop_mask, float drop_scale,
+                          int64_t T, int64_t Bp, int64_t K, int64_t H, na_stream_t stream);
+
+/* dW_ih [4H,K] = sum_rows dgates^T in ; dW_hh [4H,H] = sum_{t>=1} dgates_t^T h_{t-1} ;
+ * db [4H] = column sums (gradient of both b_ih and b_hh).  Deterministic two-stage
+ * reduction; `partials` is caller scratch of na_wgrad_partial_floats(K,H) floats.
+ */
+int64_t na_wgrad_partial_floats(int64_t K, int64_t H);
+int na_lstm_layer_wgrad_f32(const float* dgates, const float* in, const float* h,
+                            float* dw_ih, float* dw_hh, float* db, float* partials,
+                            int64_t T, int64_t Bp, int64_t K, int64_t H, na_stream_t stream);
+
+/* ---- K4: attention pool + LayerNorm + MLP head (+ softmax) -------------------------------
+ * Replaces lstm_eeg_model.py:35-39 and, when probs != NULL, F.softmax at :97.
+ *   h TMP [T][Bp][H];  attn_w [H], attn_b [1], ln_w [H], ln_b [H],
+ *   fc0_w [32,H], fc0_b [32], fc3_w [NC,32], fc3_b [NC]
+ *   rrelu_slope [B,32] or NULL (eval: (1/8+1/3)/2), drop_mask [B,32] 0/1 or NULL, drop_scale
+ *   logits [B,NC]; probs [B,NC] or NULL
+ *   saved (training, may be NULL): stats [B][2] = softmax-over-time (max, sum),
+ *   zpool [B,H] (pre-LN pooled vector)
+ */
+int na_head_fwd_f32(const float* h, const float* attn_w, const float* attn_b,
+                    const float* ln_w, const float* ln_b,
+                    const float* fc0_w, const float* fc0_b, const float* fc3_w, const float* fc3_b,
+                    const float* rrelu_slope, const float* drop_mask, float drop_scale,
+                    float* logits, float* probs, float* stats, float* zpool,
+                    int64_t T, int64_t B, int64_t Bp, int64_t H, int64_t NC, na_stream_t stream);
+
+/* Backward of na_head_fwd_f32.  dlogits [B,NC] -> dh TMP [T][Bp][H] (padding rows zeroed)
+ * and the 8 head parameter gradients, packed in `dparams` as
+ * [attn_w H | attn_b 1 | ln_w H | ln_b H | fc0_w 32H | fc0_b 32 | fc3_w 32NC | fc3_b NC].
+ * `partials` is scratch of na_head_partial_floats(B,H,NC) floats.
+ */
+int64_t na_head_param_floats(int64_t H, int64_t NC);
+int64_t na_head_partial_floats(int64_t B, int64_t H, int64_t NC);
+int na_head_bwd_f32(const float* dlogits, const float* h, const float* stats, const float* zpool,
+                    const float* attn_w, const float* attn_b, const float* ln_w, const float* ln_b,
+                    const float* fc0_w, const float* fc0_b, const float* fc3_w, const float* fc3_b,
+                    const float* rrelu_slope, const float* drop_mask, float drop_scale,
+                    float* dh, float* dparams, float* partials,
+                    int64_t T, int64_t B, int64_t Bp, int64_t H, int64_t NC, na_stream_t stream);
+
+/* ---- K5: trial averaging -----------------------------------------------------------------
+ * Replaces tester.py:54,89,97 (and :90,98 for the chunk): fp32 zeros, += in trial order
+ * r = 0..R-1, then one IEEE division by R.   in [R][N] -> out [N].
+ */
+int na_trial_mean_f32(const float* in, float* out, int64_t R, int64_t N, na_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUROALPHA_H_ */

@@ -1,0 +1,99 @@
+// C-ABI plumbing: version, thread-local error string, launch counter, K5 trial mean, and the
+// dispatch of na_lstm_layer_{fwd,bwd}_f32 between the specialised and the generic tier.
+#include "na_common.cuh"
+
+namespace na {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+char* err_buf() { return g_err; }
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return NA_OK;
+    snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+    return (int)e;
+}
+
+int lstm_layer_fwd_generic(const float* in, const float* wt, const float* bias, float* hout, float* cout,
+                           float* gates, const float* drop_mask, float drop_scale, float* hout_drop,
+                           int64_t T, int64_t Bp, int64_t K, int64_t H, cudaStream_t st);
+int lstm_layer_bwd_generic(const float* dh_out, const float* gates, const float* cstate, const float* w_ih,
+                           const float* w_hh, float* dgates, float* din, const float* in_drop_mask,
+                           float drop_scale, int64_t T, int64_t Bp, int64_t K, int64_t H, cudaStream_t st);
+
+// K5.  fp32 zeros, += in trial order, one IEEE division: bit-identical to tester.py:54,89,97.
+__global__ void trial_mean_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int64_t N) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float acc = 0.f;
+    for (int r = 0; r < R; ++r) acc = __fadd_rn(acc, in[(int64_t)r * N + i]);
+    out[i] = __fdiv_rn(acc, (float)R);
+}
+
+}  // namespace na
+
+extern "C" int na_version(void) { return NA_VERSION; }
+extern "C" const char* na_last_error(void) { return na::err_buf(); }
+extern "C" int64_t na_launch_count(void) { return na::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int na_trial_mean_f32(const float* in, float* out, int64_t R, int64_t N, na_stream_t stream) {
+    using namespace na;
+    NA_REQUIRE(R >= 1 && R <= (1 << 24) && N >= 0, NA_EINVAL, "na_trial_mean_f32: bad shape R=%lld N=%lld",
+               (long long)R, (long long)N);
+    if (N == 0) return NA_OK;
+    NA_REQUIRE_PTR(in);
+    NA_REQUIRE_PTR(out);
+    trial_mean_kernel<<<(unsigned)((N + 255) / 256), 256, 0, as_stream(stream)>>>(in, out, (int)R, N);
+    count_launch();
+    return check_launch("na_trial_mean_f32");
+}
+
+static int check_lstm_shape(const char* fn, int64_t T, int64_t Bp, int64_t K, int64_t H) {
+    using namespace na;
+    NA_REQUIRE(T >= 1 && Bp >= NA_BATCH_ALIGN && Bp % NA_BATCH_ALIGN == 0, NA_EINVAL,
+               "%s: bad shape T=%lld Bp=%lld (Bp must be a positive multiple of %d)", fn, (long long)T,
+               (long long)Bp, NA_BATCH_ALIGN);
+    NA_REQUIRE(K >= 1 && H >= 1 && H <= 1024 && K <= 4096, NA_EUNSUPPORTED, "%s: unsupported K=%lld H=%lld", fn,
+               (long long)K, (long long)H);
+    NA_REQUIRE(T <= INT32_MAX && T * Bp * 4 * H < ((int64_t)1 << 40), NA_EUNSUPPORTED, "%s: problem too large", fn);
+    return NA_OK;
+}
+
+extern "C" int na_lstm_layer_fwd_f32(const float* in, const float* wt, const float* bias, float* hout,
+                                     float* cout, float* gates, const float* drop_mask, float drop_scale,
+                                     float* hout_drop, int64_t T, int64_t Bp, int64_t K, int64_t H,
+                                     na_stream_t stream) {
+    using namespace na;
+    if (int rc = check_lstm_shape("na_lstm_layer_fwd_f32", T, Bp, K, H)) return rc;
+    NA_REQUIRE_PTR(in); NA_REQUIRE_PTR(wt); NA_REQUIRE_PTR(bias); NA_REQUIRE_PTR(hout);
+    NA_OPTIONAL_PTR(cout); NA_OPTIONAL_PTR(gates); NA_OPTIONAL_PTR(drop_mask); NA_OPTIONAL_PTR(hout_drop);
+    NA_REQUIRE((drop_mask == nullptr) == (hout_drop == nullptr), NA_EINVAL,
+               "na_lstm_layer_fwd_f32: drop_mask and hout_drop must be given together");
+    return lstm_layer_fwd_generic(in, wt, bias, hout, cout, gates, drop_mask, drop_scale, hout_drop, T, Bp, K, H,
+                                  as_stream(stream));
+}
+
+extern "C" int na_lstm_layer_bwd_f32(const float* dh_out, const float* gates, const float* cstate,
+                                     const float* w_ih, const float* w_hh, float* dgates, float* din,
+                                     const float* in_drop_mask, float drop_scale, int64_t T, int64_t Bp,
+                                     int64_t K, int64_t H, na_stream_t stream) {
+    using namespace na;
+    if (int rc = check_lstm_shape("na_lstm_layer_bwd_f32", T, Bp, K, H)) return rc;
+    NA_REQUIRE_PTR(dh_out); NA_REQUIRE_PTR(gates); NA_REQUIRE_PTR(cstate); NA_REQUIRE_PTR(w_ih);
+    NA_REQUIRE_PTR(w_hh); NA_REQUIRE_PTR(dgates);
+    NA_OPTIONAL_PTR(din); NA_OPTIONAL_PTR(in_drop_mask);
+    return lstm_layer_bwd_generic(dh_out, gates, cstate, w_ih, w_hh, dgates, din, in_drop_mask, drop_scale, T, Bp,
+                                  K, H, as_stream(stream));
+}

@@ -1,0 +1,159 @@
+// Time-parallel gradient reductions: out[M][N] = sum_r G[r][m] * A[r][n] over a very tall
+// row range (rows = T*Bp), tiny outputs.  Split over row chunks, partials reduced in a fixed
+// order -> bit-reproducible run to run (no float atomics).
+#include "na_common.cuh"
+
+namespace na {
+
+constexpr int kTnTile = 64;     // output tile 64 x 64
+constexpr int kTnRows = 16;     // rows staged per iteration
+constexpr int kTnThreads = 256; // 16 x 16 threads, 4 x 4 outputs each
+
+__global__ void __launch_bounds__(kTnThreads)
+gemm_tn_partial_kernel(const float* __restrict__ G, int64_t ldg, const float* __restrict__ A, int64_t lda,
+                       int64_t R, int M, int N, float* __restrict__ partial, int64_t rows_per_chunk) {
+    __shared__ float Gs[kTnRows][kTnTile + 4];
+    __shared__ float As[kTnRows][kTnTile + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * kTnTile, n0 = blockIdx.z * kTnTile;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_chunk;
+    const int64_t r_end = min(R, r_begin + rows_per_chunk);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) acc[i][jn] = 0.f;
+
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += kTnRows) {
+#pragma unroll
+        for (int e = 0; e < (kTnRows * kTnTile) / kTnThreads; ++e) {
+            const int idx = tid + e * kTnThreads;
+            const int rr = idx / kTnTile, cc = idx % kTnTile;
+            const int64_t r = r0 + rr;
+            Gs[rr][cc] = (r < r_end && m0 + cc < M) ? G[r * ldg + m0 + cc] : 0.f;
+            As[rr][cc] = (r < r_end && n0 + cc < N) ? A[r * lda + n0 + cc] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < kTnRows; ++rr) {
+            const float4 g = *reinterpret_cast<const float4*>(&Gs[rr][ty * 4]);
+            const float4 a = *reinterpret_cast<const float4*>(&As[rr][tx * 4]);
+            const float gv[4] = {g.x, g.y, g.z, g.w}, av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jn = 0; jn < 4; ++jn) acc[i][jn] = fmaf(gv[i], av[jn], acc[i][jn]);
+        }
+        __syncthreads();
+    }
+    float* out = partial + (size_t)blockIdx.x * M * N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) {
+            const int n = n0 + tx * 4 + jn;
+            if (m < M && n < N) out[(size_t)m * N + n] = acc[i][jn];
+        }
+    }
+}
+
+__global__ void colsum_partial_kernel(const float* __restrict__ G, int64_t ldg, int64_t R, int M,
+                                      float* __restrict__ partial, int64_t rows_per_chunk) {
+    const int m = blockIdx.y * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_chunk;
+    const int64_t r_end = min(R, r_begin + rows_per_chunk);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int64_t r = r_begin;
+    for (; r + 3 < r_end; r += 4) {
+        s0 += G[r * ldg + m];
+        s1 += G[(r + 1) * ldg + m];
+        s2 += G[(r + 2) * ldg + m];
+        s3 += G[(r + 3) * ldg + m];
+    }
+    for (; r < r_end; ++r) s0 += G[r * ldg + m];
+    partial[(size_t)blockIdx.x * M + m] = (s0 + s1) + (s2 + s3);
+}
+
+// out[i] = sum_c partial[c][i], c ascending (fixed order).
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                       int nchunks, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int c = 0; c < nchunks; ++c) s += partial[(size_t)c * n + i];
+    out[i] = s;
+}
+
+int wgrad_nchunks(int64_t M, int64_t N, int64_t R) {
+    const int64_t tiles = ((M + kTnTile - 1) / kTnTile) * ((N + kTnTile - 1) / kTnTile);
+    int64_t n = 592 / (tiles > 0 ? tiles : 1);
+    if (n < 4) n = 4;
+    if (n > 296) n = 296;
+    const int64_t max_by_rows = (R + kTnRows - 1) / kTnRows;
+    if (n > max_by_rows) n = max_by_rows > 0 ? max_by_rows : 1;
+    return (int)n;
+}
+
+// out[M][N] = G^T A over R rows.  `partial` must hold wgrad_nchunks(M,N,R)*M*N floats.
+int gemm_tn(const float* G, int64_t ldg, const float* A, int64_t lda, int64_t R, int64_t M, int64_t N,
+            float* out, float* partial, cudaStream_t st) {
+    const int nch = wgrad_nchunks(M, N, R);
+    int64_t rpc = (R + nch - 1) / nch;
+    rpc = (rpc + kTnRows - 1) / kTnRows * kTnRows;
+    const dim3 grid(nch, (unsigned)((M + kTnTile - 1) / kTnTile), (unsigned)((N + kTnTile - 1) / kTnTile));
+    gemm_tn_partial_kernel<<<grid, kTnThreads, 0, st>>>(G, ldg, A, lda, R, (int)M, (int)N, partial, rpc);
+    const int64_t n = M * N;
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, out, nch, n);
+    count_launch(2);
+    return check_launch("gemm_tn");
+}
+
+int reduce_partials(const float* partial, float* out, int nchunks, int64_t n, cudaStream_t st) {
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, out, nchunks, n);
+    count_launch();
+    return check_launch("reduce_partials");
+}
+
+int colsum(const float* G, int64_t ldg, int64_t R, int64_t M, float* out, float* partial, cudaStream_t st) {
+    const int nch = wgrad_nchunks(M, 1, R);
+    const int64_t rpc = (R + nch - 1) / nch;
+    const dim3 grid(nch, (unsigned)((M + 127) / 128));
+    colsum_partial_kernel<<<grid, 128, 0, st>>>(G, ldg, R, (int)M, partial, rpc);
+    reduce_partials_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(partial, out, nch, M);
+    count_launch(2);
+    return check_launch("colsum");
+}
+
+}  // namespace na
+
+extern "C" int64_t na_wgrad_partial_floats(int64_t K, int64_t H) {
+    // worst case over the three reductions of one layer (row count unbounded)
+    const int64_t M = 4 * H, big = (int64_t)1 << 40;
+    const int64_t a = (int64_t)na::wgrad_nchunks(M, K, big) * M * K;
+    const int64_t b = (int64_t)na::wgrad_nchunks(M, H, big) * M * H;
+    const int64_t c = (int64_t)na::wgrad_nchunks(M, 1, big) * M;
+    return (a > b ? (a > c ? a : c) : (b > c ? b : c)) + 64;
+}
+
+extern "C" int na_lstm_layer_wgrad_f32(const float* dgates, const float* in, const float* h, float* dw_ih,
+                                       float* dw_hh, float* db, float* partials, int64_t T, int64_t Bp,
+                                       int64_t K, int64_t H, na_stream_t stream) {
+    using namespace na;
+    NA_REQUIRE(T >= 1 && Bp >= 1 && K >= 1 && H >= 1, NA_EINVAL, "na_lstm_layer_wgrad_f32: bad shape");
+    NA_REQUIRE_PTR(dgates); NA_REQUIRE_PTR(in); NA_REQUIRE_PTR(h);
+    NA_REQUIRE_PTR(dw_ih); NA_REQUIRE_PTR(dw_hh); NA_REQUIRE_PTR(db); NA_REQUIRE_PTR(partials);
+    cudaStream_t st = as_stream(stream);
+    const int64_t R = T * Bp, G = 4 * H;
+    int rc = gemm_tn(dgates, G, in, K, R, G, K, dw_ih, partials, st);
+    if (rc) return rc;
+    if (T > 1) {
+        // rows (t, b), t >= 1, pair with h_{t-1} = h rows shifted down by Bp
+        rc = gemm_tn(dgates + Bp * G, G, h, H, R - Bp, G, H, dw_hh, partials, st);
+    } else {
+        rc = (int)cudaMemsetAsync(dw_hh, 0, sizeof(float) * G * H, st);
+    }
+    if (rc) return rc;
+    return colsum(dgates, G, R, G, db, partials, st);
+}

@@ -1,0 +1,372 @@
+"""Torch-facing operators over the C ABI: ``torch.ops.neuroalpha.*`` custom ops (CUDA only) and
+the explicit autograd function of the whole decoder.
+
+PyTorch is plumbing here -- device memory, streams, autograd bookkeeping.  Every arithmetic
+step of the hot path runs in libneuroalpha_b200.so.  Calling an op with a CPU tensor raises:
+there is deliberately no CPU implementation.
+
+Internal activation layout is "time-major padded" (TMP): ``[T, Bp, F]`` with ``Bp`` the batch
+rounded up to a multiple of 32 (see include/neuroalpha.h).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+BATCH_ALIGN = 32
+FC_HIDDEN = 32
+NA_F32, NA_BF16 = 0, 1
+
+HEAD_KEYS = ("attn.weight", "attn.bias", "ln.weight", "ln.bias",
+             "fc.0.weight", "fc.0.bias", "fc.3.weight", "fc.3.bias")
+
+
+def padded_batch(b: int) -> int:
+    return max(BATCH_ALIGN, (b + BATCH_ALIGN - 1) // BATCH_ALIGN * BATCH_ALIGN)
+
+
+def _require_cuda(*tensors: Optional[Tensor]) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "neural_speech_decoding_b200: tensor on %s -- the decoder runs only on CUDA (sm_100a); "
+                "there is no CPU fallback" % t.device)
+
+
+def compute_device(io_device: torch.device) -> torch.device:
+    """Device the kernels run on for a caller that names ``io_device`` (reference callers pass
+    "cpu", tester.py:83): the named CUDA device, else the current one.  Raises without a GPU."""
+    if io_device.type == "cuda":
+        return io_device
+    if not torch.cuda.is_available():
+        raise RuntimeError("neural_speech_decoding_b200: no CUDA device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def all_custom_ops():
+    return [window_zscore, pack_lstm_layer, lstm_layer_fwd, lstm_layer_bwd, lstm_layer_wgrad, head_fwd,
+            head_bwd, trial_mean]
+
+
+def launch_count() -> int:
+    return _lib.query("na_launch_count")
+
+
+# ------------------------------------------------------------------------------------------
+# custom ops (kernel granularity)
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op("neuroalpha::window_zscore", mutates_args=(), device_types="cuda")
+def window_zscore(x: Tensor, T: int, hop: int, normalize: bool, time_major: bool, bf16: bool) -> Tensor:
+    """K1.  x: [B,T,C] batch or [n_samples,C] stream (then windows start every ``hop`` samples).
+
+    Returns the windows ([B,T,C], or TMP [T,Bp,C] when ``time_major``), z-scored per window and
+    channel when ``normalize`` (Frontend/app.py:166-170)."""
+    _require_cuda(x)
+    x = _f32c(x)
+    if x.dim() == 3:
+        B, T_, C = x.shape
+        if T_ != T:
+            raise RuntimeError(f"window_zscore: x has T={T_}, expected {T}")
+        hop = T
+    elif x.dim() == 2:
+        n, C = x.shape
+        B = 0 if n < T else (n - T) // hop + 1
+    else:
+        raise RuntimeError("window_zscore: x must be [B,T,C] or [n_samples,C]")
+    Bp = padded_batch(B) if time_major else B
+    dt = torch.bfloat16 if bf16 else torch.float32
+    y = torch.empty((T, Bp, C) if time_major else (B, T, C), dtype=dt, device=x.device)
+    if y.numel():
+        _lib.call("na_window_zscore", x.data_ptr(), y.data_ptr(), B, T, C, hop, int(normalize),
+                  int(time_major), Bp, NA_BF16 if bf16 else NA_F32, _stream())
+    return y
+
+
+@window_zscore.register_fake
+def _(x, T, hop, normalize, time_major, bf16):
+    if x.dim() == 3:
+        B, C = x.shape[0], x.shape[2]
+    else:
+        n, C = x.shape
+        B = 0 if n < T else (n - T) // hop + 1
+    dt = torch.bfloat16 if bf16 else torch.float32
+    return x.new_empty((T, padded_batch(B), C) if time_major else (B, T, C), dtype=dt)
+
+
+@torch.library.custom_op("neuroalpha::pack_lstm_layer", mutates_args=(), device_types="cuda")
+def pack_lstm_layer(w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh: Tensor) -> Tuple[Tensor, Tensor]:
+    _require_cuda(w_ih, w_hh, b_ih, b_hh)
+    w_ih, w_hh, b_ih, b_hh = map(_f32c, (w_ih, w_hh, b_ih, b_hh))
+    G, K = w_ih.shape
+    H = G // 4
+    wt = torch.empty((K + H, G), dtype=torch.float32, device=w_ih.device)
+    bias = torch.empty((G,), dtype=torch.float32, device=w_ih.device)
+    _lib.call("na_pack_lstm_layer", w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(),
+              wt.data_ptr(), bias.data_ptr(), K, H, _stream())
+    return wt, bias
+
+
+@pack_lstm_layer.register_fake
+def _(w_ih, w_hh, b_ih, b_hh):
+    G, K = w_ih.shape
+    return w_ih.new_empty((K + G // 4, G)), w_ih.new_empty((G,))
+
+
+@torch.library.custom_op("neuroalpha::lstm_layer_fwd", mutates_args=(), device_types="cuda")
+def lstm_layer_fwd(inp: Tensor, wt: Tensor, bias: Tensor, drop_mask: Optional[Tensor], drop_scale: float,
+                   save: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """K3 forward of one layer.  inp TMP [T,Bp,K] -> (h, c, gates, h_drop); c/gates are empty
+    unless ``save``; h_drop is empty unless ``drop_mask`` is given."""
+    _require_cuda(inp, wt, bias, drop_mask)
+    T, Bp, K = inp.shape
+    H = bias.numel() // 4
+    dev = inp.device
+    h = torch.empty((T, Bp, H), dtype=torch.float32, device=dev)
+    c = torch.empty((T, Bp, H) if save else (0,), dtype=torch.float32, device=dev)
+    gates = torch.empty((T, Bp, 4 * H) if save else (0,), dtype=torch.float32, device=dev)
+    h_drop = torch.empty((T, Bp, H) if drop_mask is not None else (0,), dtype=torch.float32, device=dev)
+    _lib.call("na_lstm_layer_fwd_f32", inp.data_ptr(), wt.data_ptr(), bias.data_ptr(), h.data_ptr(),
+              _ptr(c) if save else None, _ptr(gates) if save else None, _ptr(drop_mask), float(drop_scale),
+              _ptr(h_drop) if drop_mask is not None else None, T, Bp, K, H, _stream())
+    return h, c, gates, h_drop
+
+
+@lstm_layer_fwd.register_fake
+def _(inp, wt, bias, drop_mask, drop_scale, save):
+    T, Bp, K = inp.shape
+    H = bias.numel() // 4
+    e = inp.new_empty((0,))
+    return (inp.new_empty((T, Bp, H)), inp.new_empty((T, Bp, H)) if save else e,
+            inp.new_empty((T, Bp, 4 * H)) if save else inp.new_empty((0,)),
+            inp.new_empty((T, Bp, H)) if drop_mask is not None else inp.new_empty((0,)))
+
+
+@torch.library.custom_op("neuroalpha::lstm_layer_bwd", mutates_args=(), device_types="cuda")
+def lstm_layer_bwd(dh: Tensor, gates: Tensor, c: Tensor, w_ih: Tensor, w_hh: Tensor,
+                   in_drop_mask: Optional[Tensor], drop_scale: float, need_din: bool) -> Tuple[Tensor, Tensor]:
+    """Fused BPTT of one layer: (dgates TMP [T,Bp,4H], din TMP [T,Bp,K] or empty)."""
+    _require_cuda(dh, gates, c, w_ih, w_hh, in_drop_mask)
+    T, Bp, H = dh.shape
+    K = w_ih.shape[1]
+    dgates = torch.empty((T, Bp, 4 * H), dtype=torch.float32, device=dh.device)
+    din = torch.empty((T, Bp, K) if need_din else (0,), dtype=torch.float32, device=dh.device)
+    _lib.call("na_lstm_layer_bwd_f32", dh.data_ptr(), gates.data_ptr(), c.data_ptr(), w_ih.data_ptr(),
+              w_hh.data_ptr(), dgates.data_ptr(), _ptr(din) if need_din else None, _ptr(in_drop_mask),
+              float(drop_scale), T, Bp, K, H, _stream())
+    return dgates, din
+
+
+@lstm_layer_bwd.register_fake
+def _(dh, gates, c, w_ih, w_hh, in_drop_mask, drop_scale, need_din):
+    T, Bp, H = dh.shape
+    return dh.new_empty((T, Bp, 4 * H)), dh.new_empty((T, Bp, w_ih.shape[1]) if need_din else (0,))
+
+
+@torch.library.custom_op("neuroalpha::lstm_layer_wgrad", mutates_args=(), device_types="cuda")
+def lstm_layer_wgrad(dgates: Tensor, inp: Tensor, h: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """(dW_ih [4H,K], dW_hh [4H,H], db [4H]) from dgates -- deterministic two-stage reduction."""
+    _require_cuda(dgates, inp, h)
+    T, Bp, G = dgates.shape
+    K, H = inp.shape[2], h.shape[2]
+    dev = dgates.device
+    dw_ih = torch.empty((G, K), dtype=torch.float32, device=dev)
+    dw_hh = torch.empty((G, H), dtype=torch.float32, device=dev)
+    db = torch.empty((G,), dtype=torch.float32, device=dev)
+    partials = torch.empty((_lib.query("na_wgrad_partial_floats", K, H),), dtype=torch.float32, device=dev)
+    _lib.call("na_lstm_layer_wgrad_f32", dgates.data_ptr(), inp.data_ptr(), h.data_ptr(), dw_ih.data_ptr(),
+              dw_hh.data_ptr(), db.data_ptr(), partials.data_ptr(), T, Bp, K, H, _stream())
+    return dw_ih, dw_hh, db
+
+
+@lstm_layer_wgrad.register_fake
+def _(dgates, inp, h):
+    G = dgates.shape[2]
+    return dgates.new_empty((G, inp.shape[2])), dgates.new_empty((G, h.shape[2])), dgates.new_empty((G,))
+
+
+@torch.library.custom_op("neuroalpha::head_fwd", mutates_args=(), device_types="cuda")
+def head_fwd(h: Tensor, B: int, params: Sequence[Tensor], rrelu_slope: Optional[Tensor],
+             drop_mask: Optional[Tensor], drop_scale: float, want_probs: bool,
+             save: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """K4.  h TMP [T,Bp,H]; params in HEAD_KEYS order -> (logits [B,NC], probs, stats, zpool)."""
+    _require_cuda(h, rrelu_slope, drop_mask, *params)
+    T, Bp, H = h.shape
+    NC = params[6].shape[0]
+    dev = h.device
+    logits = torch.empty((B, NC), dtype=torch.float32, device=dev)
+    probs = torch.empty((B, NC) if want_probs else (0,), dtype=torch.float32, device=dev)
+    stats = torch.empty((B, 2) if save else (0,), dtype=torch.float32, device=dev)
+    zpool = torch.empty((B, H) if save else (0,), dtype=torch.float32, device=dev)
+    _lib.call("na_head_fwd_f32", h.data_ptr(), *[p.data_ptr() for p in params], _ptr(rrelu_slope),
+              _ptr(drop_mask), float(drop_scale), logits.data_ptr(), _ptr(probs) if want_probs else None,
+              _ptr(stats) if save else None, _ptr(zpool) if save else None, T, B, Bp, H, NC, _stream())
+    return logits, probs, stats, zpool
+
+
+@head_fwd.register_fake
+def _(h, B, params, rrelu_slope, drop_mask, drop_scale, want_probs, save):
+    NC, H = params[6].shape[0], h.shape[2]
+    return (h.new_empty((B, NC)), h.new_empty((B, NC) if want_probs else (0,)),
+            h.new_empty((B, 2) if save else (0,)), h.new_empty((B, H) if save else (0,)))
+
+
+@torch.library.custom_op("neuroalpha::head_bwd", mutates_args=(), device_types="cuda")
+def head_bwd(dlogits: Tensor, h: Tensor, stats: Tensor, zpool: Tensor, params: Sequence[Tensor],
+             rrelu_slope: Optional[Tensor], drop_mask: Optional[Tensor], drop_scale: float) -> Tuple[Tensor, Tensor]:
+    """Backward of K4: (dh TMP [T,Bp,H], dparams packed in HEAD_KEYS order)."""
+    _require_cuda(dlogits, h, stats, zpool, rrelu_slope, drop_mask, *params)
+    T, Bp, H = h.shape
+    B, NC = dlogits.shape
+    dev = h.device
+    dlogits = _f32c(dlogits)
+    dh = torch.empty((T, Bp, H), dtype=torch.float32, device=dev)
+    dparams = torch.empty((_lib.query("na_head_param_floats", H, NC),), dtype=torch.float32, device=dev)
+    partials = torch.empty((_lib.query("na_head_partial_floats", B, H, NC),), dtype=torch.float32, device=dev)
+    _lib.call("na_head_bwd_f32", dlogits.data_ptr(), h.data_ptr(), stats.data_ptr(), zpool.data_ptr(),
+              *[p.data_ptr() for p in params], _ptr(rrelu_slope), _ptr(drop_mask), float(drop_scale),
+              dh.data_ptr(), dparams.data_ptr(), partials.data_ptr(), T, B, Bp, H, NC, _stream())
+    return dh, dparams
+
+
+@head_bwd.register_fake
+def _(dlogits, h, stats, zpool, params, rrelu_slope, drop_mask, drop_scale):
+    H, NC = h.shape[2], dlogits.shape[1]
+    n = H + 1 + 2 * H + FC_HIDDEN * H + FC_HIDDEN + FC_HIDDEN * NC + NC
+    return h.new_empty(h.shape), h.new_empty((n,))
+
+
+@torch.library.custom_op("neuroalpha::trial_mean", mutates_args=(), device_types="cuda")
+def trial_mean(x: Tensor) -> Tensor:
+    """K5.  x [R, ...] fp32 -> mean over the leading (trial) axis with run_trials' exact rounding
+    (tester.py:54,89,97)."""
+    _require_cuda(x)
+    x = _f32c(x)
+    R = x.shape[0]
+    out = torch.empty(x.shape[1:], dtype=torch.float32, device=x.device)
+    _lib.call("na_trial_mean_f32", x.data_ptr(), out.data_ptr(), R, out.numel(), _stream())
+    return out
+
+
+@trial_mean.register_fake
+def _(x):
+    return x.new_empty(x.shape[1:])
+
+
+# ------------------------------------------------------------------------------------------
+# decoder-level forward / explicit autograd
+# ------------------------------------------------------------------------------------------
+def split_head_grads(dparams: Tensor, H: int, NC: int) -> List[Tensor]:
+    """Unpack na_head_bwd_f32's dparams into tensors shaped like HEAD_KEYS."""
+    sizes = [H, 1, H, H, FC_HIDDEN * H, FC_HIDDEN, FC_HIDDEN * NC, NC]
+    shapes = [(1, H), (1,), (H,), (H,), (FC_HIDDEN, H), (FC_HIDDEN,), (NC, FC_HIDDEN), (NC,)]
+    return [p.reshape(s) for p, s in zip(dparams.split(sizes), shapes)]
+
+
+def decoder_infer(x: Tensor, lstm_params: Sequence[Sequence[Tensor]], head_params: Sequence[Tensor],
+                  want_probs: bool = False, zscore: bool = False,
+                  packed: Optional[Sequence[Tuple[Tensor, Tensor]]] = None) -> Tuple[Tensor, Tensor]:
+    """Eval-mode forward, nothing saved.  x [B,T,C] -> (logits [B,NC], probs or empty)."""
+    _require_cuda(x)
+    B, T, C = x.shape
+    cur = window_zscore(x, T, T, zscore, True, False)
+    for l, (w_ih, w_hh, b_ih, b_hh) in enumerate(lstm_params):
+        wt, bias = packed[l] if packed is not None else pack_lstm_layer(w_ih, w_hh, b_ih, b_hh)
+        cur = lstm_layer_fwd(cur, wt, bias, None, 1.0, False)[0]
+    logits, probs, _, _ = head_fwd(cur, B, list(head_params), None, None, 1.0, want_probs, False)
+    return logits, probs
+
+
+class DecoderFunction(torch.autograd.Function):
+    """x, 4*L LSTM tensors, 8 head tensors -> logits, with the backward written out by hand
+    (fused BPTT + time-parallel weight-gradient reductions).  Noise tensors are inputs, so the
+    function itself is deterministic."""
+
+    @staticmethod
+    def forward(ctx, x, num_layers, p, zscore, drop1_masks, rrelu_slope, drop2_mask, *params):
+        _require_cuda(x, *params)
+        B, T, C = x.shape
+        lstm_flat, head = params[:4 * num_layers], [_f32c(t) for t in params[4 * num_layers:]]
+        scale = 1.0 / (1.0 - p) if p < 1.0 else 0.0
+        cur = window_zscore(x.detach(), T, T, zscore, True, False)
+        saved, layer_in = [], cur
+        for l in range(num_layers):
+            w_ih, w_hh, b_ih, b_hh = (_f32c(t.detach()) for t in lstm_flat[4 * l:4 * l + 4])
+            wt, bias = pack_lstm_layer(w_ih, w_hh, b_ih, b_hh)
+            mask = drop1_masks[l] if (drop1_masks is not None and l < num_layers - 1) else None
+            h, c, gates, h_drop = lstm_layer_fwd(layer_in, wt, bias, mask, scale, True)
+            saved += [layer_in, h, c, gates, w_ih, w_hh]
+            layer_in = h_drop if mask is not None else h
+        logits, _, stats, zpool = head_fwd(layer_in, B, head, rrelu_slope, drop2_mask, scale, False, True)
+        ctx.save_for_backward(*saved, stats, zpool, *head,
+                              *([m for m in drop1_masks] if drop1_masks is not None else []),
+                              *([rrelu_slope] if rrelu_slope is not None else []),
+                              *([drop2_mask] if drop2_mask is not None else []))
+        ctx.meta = (num_layers, scale, B, x.shape, zscore, drop1_masks is not None,
+                    rrelu_slope is not None, drop2_mask is not None)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        num_layers, scale, B, xshape, zscore, has_d1, has_rr, has_d2 = ctx.meta
+        sv = list(ctx.saved_tensors)
+        layers = [sv[6 * l:6 * l + 6] for l in range(num_layers)]
+        pos = 6 * num_layers
+        stats, zpool = sv[pos], sv[pos + 1]
+        head = sv[pos + 2:pos + 10]
+        pos += 10
+        d1 = sv[pos:pos + num_layers - 1] if has_d1 else None
+        pos += (num_layers - 1) if has_d1 else 0
+        rr = sv[pos] if has_rr else None
+        pos += 1 if has_rr else 0
+        d2 = sv[pos] if has_d2 else None
+
+        top_in = layers[-1][1]
+        if has_d1 and num_layers > 1:
+            # the head consumed the raw h of the last layer (dropout is never applied after it)
+            pass
+        H = top_in.shape[2]
+        NC = dlogits.shape[1]
+        dh, dparams = head_bwd(dlogits.contiguous(), top_in, stats, zpool, head, rr, d2, scale)
+        head_grads = split_head_grads(dparams, H, NC)
+
+        need_dx = ctx.needs_input_grad[0]
+        lstm_grads: List[Tensor] = [None] * (4 * num_layers)
+        dx = None
+        for l in range(num_layers - 1, -1, -1):
+            layer_in, h, c, gates, w_ih, w_hh = layers[l]
+            in_mask = d1[l - 1] if (has_d1 and l > 0) else None
+            need_din = l > 0 or need_dx
+            dgates, din = lstm_layer_bwd(dh, gates, c, w_ih, w_hh, in_mask, scale, need_din)
+            dw_ih, dw_hh, db = lstm_layer_wgrad(dgates, layer_in, h)
+            lstm_grads[4 * l:4 * l + 4] = [dw_ih, dw_hh, db, db.clone()]
+            dh = din
+        if need_dx:
+            if zscore:
+                raise RuntimeError("gradient w.r.t. x through the z-score front stage is not implemented")
+            dx = dh[:, :B].permute(1, 0, 2).contiguous().reshape(xshape)
+        return (dx, None, None, None, None, None, None, *lstm_grads, *head_grads)
+
+
+def decoder_train_forward(x: Tensor, lstm_params, head_params, p: float, zscore: bool = False,
+                          drop1_masks=None, rrelu_slope=None, drop2_mask=None) -> Tensor:
+    flat = [t for layer in lstm_params for t in layer]
+    return DecoderFunction.apply(x, len(lstm_params), p, zscore, drop1_masks, rrelu_slope, drop2_mask,
+                                 *flat, *head_params)

@@ -1,0 +1,345 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference's golden
+vectors.  Run on the GPU box:  python -m pytest tests -m gpu -x -q
+
+Tolerances (BASELINE.json north_star): fp32 logits and gradients within 1e-5 relative
+(max|d| / max|ref| per tensor), argmax bit-exact on the repo's EEG windows.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import numpy_oracle as no
+from oracle.torch_ref import RefEEGLSTM, explicit_forward
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+
+
+def rel(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from neural_speech_decoding_b200 import _lib
+    _lib.load()          # fail loudly if the CUDA library is missing
+    return torch.device("cuda:0")
+
+
+def make_model(dev, sd=None, **kw):
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    m = EEG_LSTM(**kw)
+    if sd is not None:
+        m.load_state_dict(sd, strict=True)
+    return m.to(dev)
+
+
+# ---------------------------------------------------------------------------------------------
+# K1 / K5
+# ---------------------------------------------------------------------------------------------
+def test_zscore_golden_and_synthetic(dev, windows, golden_dir):
+    from neural_speech_decoding_b200 import ops
+    X = torch.from_numpy(windows["X"]).to(dev)
+    z = ops.window_zscore(X, 625, 625, True, False, False).cpu().numpy()
+    want = no.zscore_window(windows["X"])
+    assert rel(z, want) < FP32_TOL
+    g = np.load(golden_dir / "ref_zscore.npz")
+    assert rel(z[g["idx"]], g["z"]) < FP32_TOL
+    # time-major padded layout + bf16 output + copy-only mode
+    tm = ops.window_zscore(X[:37], 625, 625, True, True, False)
+    assert tm.shape == (625, 64, 8)
+    assert torch.equal(tm[:, :37].permute(1, 0, 2).cpu(), torch.from_numpy(z[:37]))
+    assert tm[:, 37:].abs().sum().item() == 0
+    cp = ops.window_zscore(X[:5], 625, 625, False, False, False)
+    assert torch.equal(cp, X[:5])
+    zb = ops.window_zscore(X[:16], 625, 625, True, False, True)
+    assert zb.dtype == torch.bfloat16
+    assert torch.equal(zb.cpu(), torch.from_numpy(z[:16]).to(torch.bfloat16))
+    # stream windowing (hop != T), long windows, odd channel counts (generic kernel)
+    gen = torch.Generator().manual_seed(0)
+    s = torch.randn(5000, 8, generator=gen) * 2.73
+    w = ops.window_zscore(s.to(dev), 625, 125, True, False, False).cpu().numpy()
+    ref = no.zscore_window(np.stack([s.numpy()[i * 125:i * 125 + 625] for i in range(w.shape[0])]))
+    assert w.shape[0] == 36 and rel(w, ref) < FP32_TOL
+    for (T, C) in [(2500, 8), (100, 5), (625, 16), (33, 4)]:
+        x = torch.randn(9, T, C, generator=gen) * 3 + 1
+        got = ops.window_zscore(x.to(dev), T, T, True, False, False).cpu().numpy()
+        assert rel(got, no.zscore_window(x.numpy())) < FP32_TOL, (T, C)
+
+
+def test_trial_mean_bit_exact(dev, golden_dir, windows):
+    from neural_speech_decoding_b200 import ops
+    t = np.load(golden_dir / "ref_run_trials.npz")
+    got = ops.trial_mean(torch.from_numpy(t["per_trial_probs"]).to(dev)).cpu().numpy()
+    assert np.array_equal(got, t["avg_probs"])
+    chunks = windows["X"][t["trial_idx"]]
+    got = ops.trial_mean(torch.from_numpy(chunks).to(dev)).cpu().numpy()
+    assert np.array_equal(got, t["avg_chunk"])
+    gen = torch.Generator().manual_seed(1)
+    p = torch.rand(10, 4096, 3, generator=gen)
+    got = ops.trial_mean(p.to(dev)).cpu().numpy()
+    assert np.array_equal(got, no.trial_mean(p.numpy()))
+    assert ops.trial_mean(torch.empty(10, 0, 3, device=dev)).shape == (0, 3)
+
+
+# ---------------------------------------------------------------------------------------------
+# decoder forward (K3 + K4)
+# ---------------------------------------------------------------------------------------------
+def test_logits_all_324_windows_fp32_and_argmax(dev, checkpoint, windows, golden_dir):
+    ref = np.load(golden_dir / "ref_outputs_3class.npz")
+    m = make_model(dev, checkpoint).eval()
+    with torch.inference_mode():
+        got = m(torch.from_numpy(windows["X"]).to(dev)).cpu().numpy()
+    want = ref["logits_raw_b1"]
+    assert got.shape == (324, 3)
+    assert rel(got, want) < FP32_TOL
+    assert np.array_equal(got.argmax(1), want.argmax(1))
+    # B=1 path (what SimplePredictor does), and a ragged batch
+    with torch.inference_mode():
+        one = m(torch.from_numpy(windows["X"][7:8]).to(dev)).cpu().numpy()
+        rag = m(torch.from_numpy(windows["X"][:33]).to(dev)).cpu().numpy()
+    assert rel(one, want[7:8]) < FP32_TOL and rel(rag, want[:33]) < FP32_TOL
+    assert np.array_equal(rag, got[:33])                # batch-size invariant bit for bit
+
+
+def test_filtered_windows_and_predictor(dev, checkpoint, golden_dir, tmp_path, windows):
+    from neural_speech_decoding_b200.lstm_eeg_model import SimplePredictor
+    ref = np.load(golden_dir / "ref_outputs_3class.npz")
+    pth = tmp_path / "ck.pth"
+    torch.save({"state_dict": dict(checkpoint)}, pth)        # {"state_dict": ...} form
+
+    class Lookup:                                             # MindsAI filter stays CPU/out of scope
+        def __init__(self, table):
+            self.table = table
+
+        def transform(self, chunk):
+            return self.table[chunk.tobytes()]
+
+    sub = ref["filtered_subset_idx"]
+    table = {windows["X"][i].tobytes(): ref["filtered_subset"][k] for k, i in enumerate(sub)}
+    pred = SimplePredictor(str(pth), sr=125, device="cpu", preprocessor=Lookup(table))
+    for k, i in enumerate(sub):
+        probs, label = pred.predict(windows["X"][i])
+        assert probs.dtype == np.float32 and probs.shape == (3,)
+        assert np.abs(probs - ref["predict_probs_subset"][k]).max() < 2e-6
+        assert label == str(ref["predict_labels_subset"][k])
+    pb = pred.predict_batch(windows["X"][sub])
+    assert np.abs(pb - ref["predict_probs_subset"]).max() < 2e-6
+    assert np.array_equal(pb.argmax(1), ref["logits_filtered_b1"][sub].argmax(1))
+
+
+def test_run_trials_drop_in(dev, checkpoint, windows, golden_dir, tmp_path):
+    """run_trials with a fake producer feeding CSV windows == the reference's run_trials output."""
+    import threading
+    import types
+    from neural_speech_decoding_b200 import tester
+    g = np.load(golden_dir / "ref_run_trials.npz")
+    pth = tmp_path / "ck.pth"
+    torch.save(dict(checkpoint), pth)
+    table = {windows["X"][i].tobytes(): g["filtered"][k] for k, i in enumerate(g["trial_idx"])}
+
+    class Pre:
+        def __init__(self, sr, tailoring_lambda):
+            assert sr == 125 and tailoring_lambda == 1.25e-29
+
+        def transform(self, chunk):
+            return table[chunk.tobytes()]
+
+    class FakeProducer:
+        def __init__(self, serial_port, num_channels, window_seconds, out_queue):
+            self.q, self.recording_flag, self._alive = out_queue, types.SimpleNamespace(value=False), True
+
+        def start(self):
+            def run():
+                for i in g["trial_idx"]:
+                    self.q.put({"sr": 125, "channels": list(range(1, 9)), "data": windows["X"][i], "t_emit": 0.0})
+            threading.Thread(target=run, daemon=True).start()
+
+        def is_alive(self):
+            return self._alive
+
+        def stop(self):
+            self._alive = False
+
+        def join(self, timeout=None):
+            pass
+
+    from neural_speech_decoding_b200 import lstm_eeg_model
+    old = lstm_eeg_model._resolve_preprocessor
+    lstm_eeg_model._resolve_preprocessor = lambda: Pre
+    tester.StreamingProcess = FakeProducer
+    try:
+        res = tester.run_trials(trials=10, model_path=str(pth), verbose=False)
+    finally:
+        lstm_eeg_model._resolve_preprocessor = old
+        tester.StreamingProcess = None
+    assert res.trials == 10
+    assert np.abs(res.avg_probs - g["avg_probs"]).max() < 2e-6
+    assert np.array_equal(res.avg_chunk, g["avg_chunk"])
+    assert res.avg_probs.dtype == np.float32
+
+
+def test_run_trials_batched_host_and_device(dev, checkpoint, windows):
+    from neural_speech_decoding_b200.tester import run_trials_batched
+    m = make_model(dev, checkpoint).eval()
+    R, B = 10, 7
+    w = windows["X"][:R * B].reshape(R, B, 625, 8)
+    sdn = {k: v.numpy() for k, v in checkpoint.items()}
+    want = no.trial_mean(no.softmax(no.decoder_forward(w.reshape(R * B, 625, 8), sdn)).reshape(R, B, 3))
+    host = run_trials_batched(w, m)
+    pinned = run_trials_batched(torch.from_numpy(w).pin_memory(), m)
+    device = run_trials_batched(torch.from_numpy(w).to(dev), m)
+    assert np.abs(host - want).max() < 2e-6
+    assert np.array_equal(host, pinned) and np.array_equal(host, device)
+
+
+def test_synthetic_batch_parity_512(dev, checkpoint):
+    """SURVEY 8(d) config 2 parity slice: 512 synthetic windows N(0, 2.73^2), seed 0."""
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(512, 625, 8, generator=gen) * 2.73
+    ref = RefEEGLSTM().eval()
+    ref.load_state_dict(checkpoint, strict=True)
+    with torch.inference_mode():
+        want = ref(x).numpy()
+    m = make_model(dev, checkpoint).eval()
+    with torch.inference_mode():
+        got = m(x.to(dev)).cpu().numpy()
+    assert rel(got, want) < FP32_TOL
+    assert np.array_equal(got.argmax(1), want.argmax(1))
+
+
+# ---------------------------------------------------------------------------------------------
+# gradients
+# ---------------------------------------------------------------------------------------------
+def check_grads(model, ref_grads, tol=FP32_TOL):
+    worst = {}
+    aw = np.abs(ref_grads["attn.weight"]).max()
+    for k, p in model.named_parameters():
+        r = ref_grads[k]
+        scale = aw if k == "attn.bias" else np.abs(r).max()     # attn.bias grad is analytically 0
+        worst[k] = np.abs(p.grad.cpu().numpy() - r).max() / scale
+    bad = {k: v for k, v in worst.items() if not v < tol}
+    assert not bad, bad
+    return worst
+
+
+def test_gradients_eval_mode_vs_reference(dev, checkpoint, windows, golden_dir):
+    g = np.load(golden_dir / "ref_grads_3class_eval_b16.npz")
+    m = make_model(dev, checkpoint).eval()
+    x = torch.from_numpy(windows["X"][g["sel"]]).to(dev)
+    logits = m(x)
+    assert rel(logits.detach().cpu().numpy(), g["logits"]) < FP32_TOL
+    loss = torch.nn.functional.cross_entropy(logits, torch.from_numpy(g["y"]).to(dev))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    check_grads(m, g)
+    # run-to-run reproducibility (deterministic reductions)
+    g1 = [p.grad.clone() for p in m.parameters()]
+    m.zero_grad()
+    torch.nn.functional.cross_entropy(m(x), torch.from_numpy(g["y"]).to(dev)).backward()
+    for a, p in zip(g1, m.parameters()):
+        assert torch.equal(a, p.grad)
+
+
+def test_gradients_train_mode_injected_noise(dev, checkpoint):
+    torch.manual_seed(11)
+    B, T, H = 6, 40, 48
+    x = torch.randn(B, T, 8) * 2.73
+    y = torch.tensor([0, 1, 2, 2, 1, 0])
+    d1 = (torch.rand(1, B, T, H) >= 0.6).float()
+    rr = torch.empty(B, 32).uniform_(1 / 8, 1 / 3)
+    d2 = (torch.rand(B, 32) >= 0.6).float()
+    sd = {k: v.double().requires_grad_(True) for k, v in checkpoint.items()}
+    xr = x.double().requires_grad_(True)
+    lr = torch.nn.functional.cross_entropy(explicit_forward(xr, sd, 2, 0.6, d1[0].double(), rr.double(), d2.double()), y)
+    lr.backward()
+    m = make_model(dev, checkpoint).train()
+    m.inject_noise(drop1=d1, rrelu_slope=rr, drop2=d2)
+    xg = x.to(dev).requires_grad_(True)
+    loss = torch.nn.functional.cross_entropy(m(xg), y.to(dev))
+    loss.backward()
+    assert abs(loss.item() - lr.item()) < 1e-5
+    check_grads(m, {k: v.grad.numpy() for k, v in sd.items()})
+    assert rel(xg.grad.cpu().numpy(), xr.grad.numpy()) < FP32_TOL
+
+
+def test_train_mode_noise_statistics(dev, checkpoint):
+    m = make_model(dev, checkpoint).train()
+    d1, rr, d2 = m._draw_noise(4096, 8, dev)
+    assert abs(d1[0].mean().item() - 0.4) < 0.01 and abs(d2.mean().item() - 0.4) < 0.02
+    assert rr.min().item() >= 0.125 and rr.max().item() <= 1 / 3 and abs(rr.mean().item() - 0.2292) < 0.005
+    x = torch.randn(64, 50, 8, device=dev)
+    a, b = m(x), m(x)
+    assert not torch.equal(a, b)                      # stochastic in train mode
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m(x), m(x))
+
+
+def test_five_class_variant(dev, windows, golden_dir):
+    f = np.load(golden_dir / "ref_5class.npz")
+    sd = {k[3:]: torch.from_numpy(f[k]) for k in f.files if k.startswith("sd.")}
+    m = make_model(dev, sd, num_classes=5).eval()
+    x = torch.from_numpy(windows["X"][f["sel"]]).to(dev)
+    with torch.inference_mode():
+        got = m(x).cpu().numpy()
+    assert got.shape == (32, 5) and rel(got, f["logits"]) < FP32_TOL
+    assert np.array_equal(got.argmax(1), f["logits"].argmax(1))
+    loss = torch.nn.functional.cross_entropy(m(x[:16]), torch.from_numpy(f["y"][:16]).to(dev))
+    loss.backward()
+    assert abs(loss.item() - float(f["loss"])) < 1e-5
+    check_grads(m, {k[5:]: f[k] for k in f.files if k.startswith("grad.")})
+
+
+def test_stress_shape_h192(dev, golden_dir):
+    f = np.load(golden_dir / "ref_stress_h192.npz")
+    sd = {k[3:]: torch.from_numpy(f[k]) for k in f.files if k.startswith("sd.")}
+    m = make_model(dev, sd, hidden_size=192).eval()
+    x = torch.from_numpy(f["x"]).to(dev)
+    logits = m(x)
+    assert rel(logits.detach().cpu().numpy(), f["logits"]) < FP32_TOL
+    loss = torch.nn.functional.cross_entropy(logits, torch.from_numpy(f["y"]).to(dev))
+    loss.backward()
+    assert abs(loss.item() - float(f["loss"])) < 1e-5
+    check_grads(m, {k[5:]: f[k] for k in f.files if k.startswith("grad.")}, tol=2e-5)
+
+
+def test_odd_sizes_against_port(dev):
+    torch.manual_seed(5)
+    for kw, (B, T) in [(dict(input_size=4, hidden_size=20, num_layers=3, num_classes=5, dropout=0.25), (7, 11)),
+                       (dict(input_size=8, hidden_size=48, num_layers=1, num_classes=2), (3, 1)),
+                       (dict(input_size=3, hidden_size=70, num_layers=2, num_classes=16), (40, 9))]:
+        ref = RefEEGLSTM(**kw).eval()
+        m = make_model(dev, ref.state_dict(), **kw).eval()
+        x = torch.randn(B, T, kw["input_size"])
+        y = torch.randint(0, kw["num_classes"], (B,))
+        torch.nn.functional.cross_entropy(ref(x), y).backward()
+        out = m(x.to(dev))
+        torch.nn.functional.cross_entropy(out, y.to(dev)).backward()
+        assert rel(out.detach().cpu().numpy(), ref(x).detach().numpy()) < FP32_TOL, kw
+        check_grads(m, {k: p.grad.numpy() for k, p in ref.named_parameters()}, tol=2e-5)
+
+
+def test_state_dict_roundtrip_on_device(dev, checkpoint, tmp_path):
+    m = make_model(dev, checkpoint)
+    torch.save(m.state_dict(), tmp_path / "out.pth")
+    back = torch.load(tmp_path / "out.pth", map_location="cpu")
+    assert list(back.keys()) == list(checkpoint.keys())
+    ref = RefEEGLSTM()
+    ref.load_state_dict(back, strict=True)               # loadable by the reference architecture
+    for k in back:
+        assert torch.equal(back[k], checkpoint[k])
+
+
+def test_errors_surface_as_exceptions(dev, checkpoint):
+    from neural_speech_decoding_b200 import ops
+    m = make_model(dev, checkpoint)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 5, 8))                           # CPU tensor
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 5, 7, device=dev))               # wrong channel count
+    assert m(torch.zeros(0, 5, 8, device=dev)).shape == (0, 3)
+    assert ops.launch_count() > 0

@@ -1,0 +1,90 @@
+"""The oracle against the golden vectors produced by the REAL reference (oracle/make_golden.py)."""
+import numpy as np
+import torch
+
+from oracle import numpy_oracle as no
+from oracle.torch_ref import RefEEGLSTM, explicit_forward
+
+
+def _sd(checkpoint):
+    return {k: v.numpy() for k, v in checkpoint.items()}
+
+
+def test_numpy_oracle_matches_reference_logits(checkpoint, windows, golden_dir):
+    ref = np.load(golden_dir / "ref_outputs_3class.npz")
+    idx = np.arange(0, 324, 6)
+    got = no.decoder_forward(windows["X"][idx], _sd(checkpoint), np.float32)
+    want = ref["logits_raw_b1"][idx]
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-6
+    assert np.array_equal(got.argmax(1), want.argmax(1))
+    # histogram recorded in SURVEY 8(c)
+    assert np.bincount(ref["logits_raw_b1"].argmax(1), minlength=3).tolist() == [23, 288, 13]
+    assert np.bincount(ref["logits_filtered_b1"].argmax(1), minlength=3).tolist() == [117, 141, 66]
+
+
+def test_numpy_oracle_filtered_subset(checkpoint, golden_dir):
+    ref = np.load(golden_dir / "ref_outputs_3class.npz")
+    sub = ref["filtered_subset_idx"]
+    got = no.decoder_forward(ref["filtered_subset"], _sd(checkpoint), np.float32)
+    want = ref["logits_filtered_b1"][sub]
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-6
+    probs = no.softmax(got)
+    np.testing.assert_allclose(probs, ref["predict_probs_subset"], atol=2e-6)
+
+
+def test_torch_port_matches_reference(checkpoint, windows, golden_dir):
+    ref = np.load(golden_dir / "ref_outputs_3class.npz")
+    m = RefEEGLSTM().eval()
+    m.load_state_dict(checkpoint, strict=True)
+    x = torch.from_numpy(windows["X"][:24].copy())
+    with torch.inference_mode():
+        got = torch.cat([m(x[i:i + 1]) for i in range(24)]).numpy()
+    np.testing.assert_allclose(got, ref["logits_raw_b1"][:24], atol=1e-5)
+
+
+def test_torch_port_gradients_match_reference(checkpoint, windows, golden_dir):
+    g = np.load(golden_dir / "ref_grads_3class_eval_b16.npz")
+    m = RefEEGLSTM().eval()
+    m.load_state_dict(checkpoint, strict=True)
+    x = torch.from_numpy(windows["X"][g["sel"]].copy())
+    loss = torch.nn.functional.cross_entropy(m(x), torch.from_numpy(g["y"]))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    for k, p in m.named_parameters():
+        scale = max(np.abs(g[k]).max(), np.abs(g["attn.weight"]).max() if k == "attn.bias" else 0)
+        assert np.abs(p.grad.numpy() - g[k]).max() / scale < 2e-5, k
+
+
+def test_explicit_forward_matches_port(checkpoint, windows):
+    m = RefEEGLSTM().eval()
+    m.load_state_dict(checkpoint, strict=True)
+    x = torch.from_numpy(windows["X"][:4, :100].copy())
+    with torch.no_grad():
+        a = m(x)
+        b = explicit_forward(x, checkpoint)
+    np.testing.assert_allclose(a.numpy(), b.numpy(), atol=1e-5)
+
+
+def test_five_class_fixture(golden_dir, windows):
+    f = np.load(golden_dir / "ref_5class.npz")
+    sd = {k[3:]: f[k] for k in f.files if k.startswith("sd.")}
+    got = no.decoder_forward(windows["X"][f["sel"]][:8], sd, np.float32)
+    assert got.shape == (8, 5)
+    assert np.abs(got - f["logits"][:8]).max() / np.abs(f["logits"]).max() < 1e-5
+
+
+def test_stress_fixture(golden_dir):
+    f = np.load(golden_dir / "ref_stress_h192.npz")
+    sd = {k[3:]: f[k] for k in f.files if k.startswith("sd.")}
+    got = no.decoder_forward(f["x"], sd, np.float32)
+    assert np.abs(got - f["logits"]).max() / np.abs(f["logits"]).max() < 1e-5
+
+
+def test_trial_mean_and_zscore(golden_dir, windows):
+    t = np.load(golden_dir / "ref_run_trials.npz")
+    assert int(t["trials"]) == 10
+    assert np.array_equal(no.trial_mean(t["per_trial_probs"]), t["avg_probs"])
+    assert np.array_equal(no.trial_mean(windows["X"][t["trial_idx"]]), t["avg_chunk"])
+    z = np.load(golden_dir / "ref_zscore.npz")
+    assert np.array_equal(no.zscore_window(windows["X"][z["idx"]]), z["z"])
+    assert np.array_equal(no.zscore_window(t["avg_chunk"]), z["z_avg_chunk"])
