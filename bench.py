@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Headline benchmark of the NeuroAlpha decoder hot path (BASELINE.json: "EEG windows/sec").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic EEG: BASELINE.json configs[1],
+i.e. R=10 trials x B=4096 sessions of [625,8] windows per GPU (40,960 windows), decoder forward +
+class softmax + run_trials' 10-trial probability averaging, fp32, shipped 3-class weights.
+
+  value : windows/s with the windows already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same through the public host API (run_trials_batched on PINNED HOST windows):
+          H2D of every trial + D2H of the averaged probabilities inside the timed region
+  roofline / cpu_baseline / clocks / gpu_launches / train : see DESIGN.md "Measurement"
+
+Multi-GPU (torchrun, one rank per GPU): inference shards by batch with no data-path collective
+(weak scaling: every rank decodes its own 40,960 windows); the "train" leg is data-parallel with
+one flat NCCL gradient all-reduce.
+
+--impl reference times the reference's CPU implementation of the same path on the host cores
+(oracle/torch_ref.py RefEEGLSTM -- the reference module restated from the same torch building
+blocks; the reference itself is Python and /root/reference does not exist on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+T, C, H, NC = 625, 8, 48, 3
+R_TRIALS, B_SESSIONS = 10, 4096
+FWD_FLOPS_PER_WINDOW = 36_603_264            # SURVEY 8(a), base K=3
+FWDBWD_FLOPS_PER_WINDOW = 107_889_792
+L1_KERNEL_FLOPS_PER_WINDOW = 2 * (48 + 48) * 192 * T      # layer-1 recurrence kernel: [x_t|h] . W, K=96
+L0_KERNEL_FLOPS_PER_WINDOW = 2 * (8 + 48) * 192 * T
+INPUT_SIGMA = 2.73                            # matches the CSV corpus
+
+
+def load_checkpoint():
+    ck = np.load(ROOT / "tests" / "golden" / "checkpoint_3class.npz")
+    return {str(k): torch.from_numpy(ck[str(k)].copy()) for k in ck["__order__"]}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [s.strip() for s in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_windows(n, seed, pin=False):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.empty((n, T, C), dtype=torch.float32, pin_memory=pin)
+    chunk = 4096
+    for i in range(0, n, chunk):
+        x[i:i + chunk] = torch.randn((min(chunk, n - i), T, C), generator=g) * INPUT_SIGMA
+    return x
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference)
+# ---------------------------------------------------------------------------------------------
+def cpu_decode_pass(model, x_rb, R, B):
+    """One bounded sample of the workload on the host: R x B windows, chunks of 512, softmax,
+    10-trial mean (tester.py:89,97 semantics)."""
+    from oracle import trial_mean
+    probs = []
+    with torch.inference_mode():
+        for i in range(0, x_rb.shape[0], 512):
+            probs.append(torch.softmax(model(x_rb[i:i + 512]), dim=-1))
+    p = torch.cat(probs).numpy().reshape(R, B, NC)
+    return trial_mean(p)
+
+
+def cpu_arm(steps, warmup, R=10, B=256):
+    from oracle.torch_ref import RefEEGLSTM
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = RefEEGLSTM().eval()
+    m.load_state_dict(load_checkpoint(), strict=True)
+    x = synth_windows(R * B, seed=0)
+    for _ in range(warmup):
+        cpu_decode_pass(m, x, R, B)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_decode_pass(m, x, R, B)
+        times.append(time.perf_counter() - t0)
+    return {"windows_per_s": R * B / statistics.median(times), "ms_per_step": 1e3 * statistics.median(times),
+            "cores": torch.get_num_threads(), "sample": f"{R} trials x {B} sessions = {R * B} windows [625,8] per step, "
+            f"chunks of 512, fp32, median of {steps} after {warmup} warm-up", "times": times}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_arm(max(1, args.steps), max(1, args.warmup))
+    line = {
+        "impl": "reference", "metric": "EEG windows/sec (decoder fwd + softmax + 10-trial mean)",
+        "value": r["windows_per_s"], "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 3-class decoder inference + 10-trial averaging, bounded CPU sample",
+                   "trials": 10, "sessions": 256, "T": T, "C": C},
+        "cpu_baseline": {"value": r["windows_per_s"], "unit": "windows/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["windows_per_s"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(v, world, dev):
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return v
+
+
+def time_steps(fn, steps, warmup, world, dev):
+    for _ in range(warmup):
+        fn()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1), world, dev)      # ms, max over ranks
+
+
+def run_gpu_arm(args):
+    from neural_speech_decoding_b200 import _lib, ops
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    from neural_speech_decoding_b200.tester import run_trials_batched
+    _lib.load()                                     # fail loudly without the CUDA library
+    world, rank, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    peaks = measured_peaks()
+
+    model = EEG_LSTM().to(dev).eval()
+    model.load_state_dict(load_checkpoint(), strict=True)
+    R, B = R_TRIALS, B_SESSIONS
+    n_win = R * B
+    host = synth_windows(n_win, seed=1000 + rank, pin=True).reshape(R, B, T, C)
+    x_dev = host.to(dev)                            # 819 MB per rank: larger than the 126 MB L2
+
+    L = model.lstm.num_layers
+    lstm_params = [model.lstm.layer(l) for l in range(L)]
+    head = model._head_params()
+    with torch.inference_mode():
+        packed = [model._packed(l) for l in range(L)]
+
+    def step_device():
+        with torch.inference_mode():
+            _, p = ops.decoder_infer(x_dev.reshape(n_win, T, C), lstm_params, head, True, False, packed)
+            return ops.trial_mean(p.reshape(R, B, NC))
+
+    def step_e2e():
+        return run_trials_batched(host, model)      # pinned host in, numpy out
+
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    l0 = ops.launch_count()
+    ms = time_steps(step_device, args.steps, args.warmup, world, dev)
+    launches = ops.launch_count() - l0 - 0
+    clocks = sampler.stop() if sampler else None
+    launches_timed = launches * args.steps // (args.steps + args.warmup)
+    value = world * n_win * args.steps / (ms * 1e-3)
+
+    ms_e2e = time_steps(step_e2e, max(1, args.steps), 1, world, dev)
+    e2e_value = world * n_win * max(1, args.steps) / (ms_e2e * 1e-3)
+
+    # ---- dominant kernel alone: layer-1 recurrence (K3), CUDA events on the launching stream ----
+    with torch.inference_mode():
+        xt = ops.window_zscore(x_dev.reshape(n_win, T, C), T, T, False, True, False)
+        h0 = ops.lstm_layer_fwd(xt, packed[0][0], packed[0][1], None, 1.0, False)[0]
+        del xt
+
+        def k_l1():
+            return ops.lstm_layer_fwd(h0, packed[1][0], packed[1][1], None, 1.0, False)[0]
+        reps = max(3, args.steps)
+        ms_l1 = time_steps(k_l1, reps, 2, 1, dev) / reps
+        del h0
+    l1_tflops = L1_KERNEL_FLOPS_PER_WINDOW * n_win / (ms_l1 * 1e-3) / 1e12
+
+    # ---- measured CUDA-core fp32 peak (FFMA probe) -------------------------------------------
+    out = torch.zeros(4, device=dev)
+    blocks, iters = 148 * 8, 1 << 16
+    def probe():
+        _lib.call("na_ffma_probe", out.data_ptr(), blocks, iters, torch.cuda.current_stream().cuda_stream)
+    ms_probe = time_steps(probe, 3, 2, 1, dev) / 3
+    ffma_peak = blocks * 256 * 2 * 16 * iters / (ms_probe * 1e-3) / 1e12
+
+    # ---- train leg (fwd + bwd + all-reduce + Adam), per-GPU micro-batch --------------------------
+    train = None
+    if not args.no_train:
+        train = train_leg(args, world, rank, dev)
+
+    if rank != 0:
+        return
+    cpu = cpu_arm(3, 1) if world == 1 and not args.no_cpu else None
+    line = {
+        "metric": "EEG windows/sec (decoder fwd + softmax + 10-trial mean)", "value": value, "unit": "windows/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 3-class decoder (T=625,C=8,H=48,L=2) batched inference + run_trials "
+                               "10-trial probability averaging, shipped .pth weights",
+                   "trials": R, "sessions_per_gpu": B, "windows_per_step_per_gpu": n_win,
+                   "l2_policy": "inputs larger than L2 (819 MB per step per GPU)", "parallelism": f"batch-shard x{world}"},
+        "e2e": {"value": e2e_value, "unit": "windows/s", "ms_per_step": ms_e2e / max(1, args.steps),
+                "h2d_bytes_per_step": n_win * T * C * 4, "d2h_bytes_per_step": B * NC * 4,
+                "api": "neural_speech_decoding_b200.tester.run_trials_batched(pinned host [R,B,T,C]) -> numpy [B,K]"},
+        "gpu_launches": launches_timed,
+        "clocks": clocks,
+        "roofline": {
+            "kernel": "lstm_fwd_h48_kernel<KIN=48> (layer-1 recurrence, exact fp32 FFMA)",
+            "bound": "tensor", "achieved": l1_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+            "frac": l1_tflops / peaks["bf16_tflops_sustained"], "peak_source": peaks["source"] + " bf16 sustained",
+            "traffic": None,
+            "note": "exact-fp32 path runs on CUDA cores, so the binding roof is FFMA issue, not the tensor pipe: "
+                    "see cuda_core_fp32",
+            "cuda_core_fp32": {"achieved": l1_tflops, "peak": ffma_peak, "unit": "TFLOP/s",
+                               "frac": l1_tflops / ffma_peak, "peak_source": "na_ffma_probe measured in this run"},
+            "ms_per_launch": ms_l1,
+            "per_timestep_latency_us": ms_l1 * 1e3 / T,
+            "whole_decoder_fwd": {"achieved": FWD_FLOPS_PER_WINDOW * value / world / 1e12, "unit": "TFLOP/s",
+                                  "frac_of_bf16_sustained": FWD_FLOPS_PER_WINDOW * value / world / 1e12 / peaks["bf16_tflops_sustained"],
+                                  "frac_of_ffma": FWD_FLOPS_PER_WINDOW * value / world / 1e12 / ffma_peak},
+        },
+    }
+    if cpu:
+        line["cpu_baseline"] = {"value": cpu["windows_per_s"], "unit": "windows/s", "cores": cpu["cores"],
+                                "kind": "port", "sample": cpu["sample"]}
+    if train:
+        line["train"] = train
+    print(json.dumps(line), flush=True)
+
+
+def train_leg(args, world, rank, dev):
+    """Data-parallel training step: per-GPU micro-batches, one flat NCCL all-reduce, Adam."""
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    from neural_speech_decoding_b200.dp import DataParallelTrainer
+    torch.manual_seed(0)
+    model = EEG_LSTM().to(dev)
+    model.load_state_dict(load_checkpoint(), strict=True)
+    model.train()
+    per_gpu = args.train_batch
+    micro = min(per_gpu, args.train_micro)
+    x = synth_windows(micro, seed=2000 + rank).to(dev)
+    g = torch.Generator(device="cpu").manual_seed(1 + rank)
+    y = torch.randint(0, NC, (micro,), generator=g).to(dev)
+    trainer = DataParallelTrainer(model, torch.optim.Adam(model.parameters(), lr=1e-3), world_size=world)
+    n_micro = per_gpu // micro
+
+    def step():
+        trainer.step([(x, y)] * n_micro, global_batch=per_gpu * world)
+
+    steps = max(1, min(args.steps, 3))
+    ms = time_steps(step, steps, 1, world, dev)
+    wps = world * per_gpu * steps / (ms * 1e-3)
+    return {"value": wps, "unit": "windows/s", "ms_per_step": ms / steps, "global_batch": per_gpu * world,
+            "per_gpu_batch": per_gpu, "micro_batch": micro, "optimizer": "Adam lr=1e-3 (torch)",
+            "allreduce": "one flat fp32 bucket, NCCL" if world > 1 else "none (1 GPU)",
+            "achieved_tflops_per_gpu": FWDBWD_FLOPS_PER_WINDOW * wps / world / 1e12}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=8192, help="per-GPU batch of the train leg")
+    ap.add_argument("--train-micro", type=int, default=4096)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    run_gpu_arm(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

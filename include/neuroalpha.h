@@ -55,6 +55,17 @@ const char* na_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t na_launch_count(void);
 
+/* Tuning / test knobs (process-global, not thread-safe; set before launching work):
+ *   "lstm_tier"  0 = auto (specialised H=48 kernels when the shape allows), 1 = generic tier only
+ *   "h48_groups" 0 = auto, 1..4 = groups (32-window tiles) resident per CTA in the H=48 kernels
+ */
+int na_set_tuning(const char* key, int64_t value);
+
+/* Measurement aid: launches `blocks` CTAs of 256 threads, each thread running 16 independent
+ * fp32 FMA chains for `iters` iterations (2*16*iters flops per thread).  bench.py times it to
+ * obtain the CUDA-core fp32 peak the exact-fp32 recurrence is bounded by. */
+int na_ffma_probe(float* out, int64_t blocks, int64_t iters, na_stream_t stream);
+
 /* ---- K1: windowing + optional per-window per-channel z-score -------------------------
  * Replaces Frontend/app.py:166-170 (normalize_eeg: (x-mean)/(std+1e-6), population std,
  * over the time axis) and the "latest int(window_seconds*sr) samples" windowing of

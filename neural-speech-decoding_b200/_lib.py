@@ -19,6 +19,8 @@ SIGNATURES = {
     "na_version": (c_int, []),
     "na_last_error": (c_char_p, []),
     "na_launch_count": (c_int64, []),
+    "na_set_tuning": (c_int, [c_char_p, I64]),
+    "na_ffma_probe": (c_int, [P, I64, I64, P]),
     "na_window_zscore": (c_int, [P, P, I64, I64, I64, I64, I32, I32, I64, I32, P]),
     "na_pack_lstm_layer": (c_int, [P, P, P, P, P, P, I64, I64, P]),
     "na_lstm_layer_fwd_f32": (c_int, [P, P, P, P, P, P, P, F32, P, I64, I64, I64, I64, P]),

@@ -1,6 +1,7 @@
 // C-ABI plumbing: version, thread-local error string, launch counter, K5 trial mean, and the
 // dispatch of na_lstm_layer_{fwd,bwd}_f32 between the specialised and the generic tier.
 #include "na_common.cuh"
+#include <string.h>
 
 namespace na {
 
@@ -32,6 +33,14 @@ int lstm_layer_fwd_generic(const float* in, const float* wt, const float* bias, 
 int lstm_layer_bwd_generic(const float* dh_out, const float* gates, const float* cstate, const float* w_ih,
                            const float* w_hh, float* dgates, float* din, const float* in_drop_mask,
                            float drop_scale, int64_t T, int64_t Bp, int64_t K, int64_t H, cudaStream_t st);
+
+bool lstm_h48_supported(int64_t K, int64_t H, bool save_c, bool save_g);
+int lstm_layer_fwd_h48(const float* in, const float* wt, const float* bias, float* hout, float* cout,
+                       float* gates, int64_t T, int64_t Bp, int64_t K, cudaStream_t st);
+void set_h48_groups(int ng);
+int mask_scale(const float* h, const float* mask, float scale, float* out, int64_t n, cudaStream_t st);
+
+static int g_lstm_tier = 0;   // 0 = auto (specialised when available), 1 = generic only
 
 // K5.  fp32 zeros, += in trial order, one IEEE division: bit-identical to tester.py:54,89,97.
 __global__ void trial_mean_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int64_t N) {
@@ -81,8 +90,49 @@ extern "C" int na_lstm_layer_fwd_f32(const float* in, const float* wt, const flo
     NA_OPTIONAL_PTR(cout); NA_OPTIONAL_PTR(gates); NA_OPTIONAL_PTR(drop_mask); NA_OPTIONAL_PTR(hout_drop);
     NA_REQUIRE((drop_mask == nullptr) == (hout_drop == nullptr), NA_EINVAL,
                "na_lstm_layer_fwd_f32: drop_mask and hout_drop must be given together");
+    if (g_lstm_tier == 0 && lstm_h48_supported(K, H, cout != nullptr, gates != nullptr)) {
+        if (int rc = lstm_layer_fwd_h48(in, wt, bias, hout, cout, gates, T, Bp, K, as_stream(stream))) return rc;
+        if (drop_mask) return mask_scale(hout, drop_mask, drop_scale, hout_drop, T * Bp * H, as_stream(stream));
+        return NA_OK;
+    }
     return lstm_layer_fwd_generic(in, wt, bias, hout, cout, gates, drop_mask, drop_scale, hout_drop, T, Bp, K, H,
                                   as_stream(stream));
+}
+
+extern "C" int na_set_tuning(const char* key, int64_t value) {
+    using namespace na;
+    NA_REQUIRE(key != nullptr, NA_EINVAL, "na_set_tuning: null key");
+    if (!strcmp(key, "lstm_tier")) { g_lstm_tier = (int)value; return NA_OK; }
+    if (!strcmp(key, "h48_groups")) { set_h48_groups((int)value); return NA_OK; }
+    return fail(NA_EINVAL, "na_set_tuning: unknown key '%s'", key);
+}
+
+namespace na {
+// FFMA issue-rate probe: 16 independent fp32 FMA chains per thread.  Used by bench.py to MEASURE
+// the CUDA-core fp32 peak that bounds the exact-fp32 recurrence (there is no such number in
+// MEASURED_PEAKS.json).  2 * 16 * iters flops per thread.
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float* out, int iters, float a, float b) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    if (s == 12345.678f) out[0] = s;   // never true; keeps the chains alive
+}
+}  // namespace na
+
+extern "C" int na_ffma_probe(float* out, int64_t blocks, int64_t iters, na_stream_t stream) {
+    using namespace na;
+    NA_REQUIRE(blocks >= 1 && iters >= 1 && iters <= (1 << 30), NA_EINVAL, "na_ffma_probe: bad arguments");
+    NA_REQUIRE_PTR(out);
+    ffma_probe_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(out, (int)iters, 0.999f, 0.001f);
+    count_launch();
+    return check_launch("na_ffma_probe");
 }
 
 extern "C" int na_lstm_layer_bwd_f32(const float* dh_out, const float* gates, const float* cstate,

@@ -17,7 +17,7 @@ def pytest_configure(config):
 
 def load_checkpoint(name="checkpoint_3class.npz"):
     ck = np.load(GOLDEN / name)
-    return {k: torch.from_numpy(ck[k].copy()) for k in ck["__order__"]}
+    return {str(k): torch.from_numpy(ck[str(k)].copy()) for k in ck["__order__"]}
 
 
 @pytest.fixture(scope="session")

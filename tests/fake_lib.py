@@ -235,16 +235,15 @@ class FakeLib:
         m1 = dxh.mean(axis=1, keepdims=True)
         m2 = (dxh * xhat).mean(axis=1, keepdims=True)
         dz = rstd * (dxh - m1 - xhat * m2)
-        dzz = (dz * zp).sum(axis=1)
         s = hh @ P["aw"] + P["ab"]
         alpha = np.exp(s - st[:, 0]) / st[:, 1]                      # [T,B]
-        g = np.einsum("tbh,bh->tb", hh, dz)
-        ds = alpha * (g - dzz)
+        hc = hh - zp[None]                                           # centred form, as in na_head.cu
+        ds = alpha * np.einsum("tbh,bh->tb", hc, dz)
         dho = _arr(dh, (T, Bp, H))
         dho[...] = 0.0
         dho[:, :B] = alpha[..., None] * dz[None] + ds[..., None] * P["aw"]
         out = _arr(dparams, (self.na_head_param_floats(H, NC),))
-        parts = [np.einsum("tb,tbh->h", ds, hh), [ds.sum()], (dzn * xhat).sum(0), dzn.sum(0),
+        parts = [np.einsum("tb,tbh->h", ds, hc), [ds.sum()], (dzn * xhat).sum(0), dzn.sum(0),
                  (da_pre.T @ zn).ravel(), da_pre.sum(0), (dl.T @ a_post).ravel(), dl.sum(0)]
         out[...] = np.concatenate([np.asarray(p, np.float64).ravel() for p in parts])
         self.launches += 14
@@ -261,3 +260,17 @@ class FakeLib:
         _arr(out, (N,))[...] = acc / np.float32(R)
         self.launches += 1
         return 0
+
+
+def install():
+    """Process-wide installation (for spawned worker processes of the gloo DP test)."""
+    import torch
+    from neural_speech_decoding_b200 import _lib, ops
+    fake = FakeLib()
+    _lib.load = lambda path=None: fake
+    ops._require_cuda = lambda *t: None
+    ops._stream = lambda: None
+    ops.compute_device = lambda d: torch.device("cpu")
+    for op in ops.all_custom_ops():
+        op.register_kernel("cpu")(op._init_fn)
+    return fake

@@ -217,12 +217,17 @@ def test_synthetic_batch_parity_512(dev, checkpoint):
 def check_grads(model, ref_grads, tol=FP32_TOL):
     worst = {}
     aw = np.abs(ref_grads["attn.weight"]).max()
+    names = [k for k, _ in model.named_parameters()]
+    gmax = max(float(np.abs(ref_grads[k]).max()) for k in names)
     for k, p in model.named_parameters():
         r = ref_grads[k]
         scale = aw if k == "attn.bias" else np.abs(r).max()     # attn.bias grad is analytically 0
-        worst[k] = np.abs(p.grad.cpu().numpy() - r).max() / scale
+        # tensors whose true gradient (nearly) vanishes -- T=1 makes dW_hh and d attn.weight zero, two
+        # classes make d fc.3.bias a cancelling pair -- are judged on the model's gradient scale
+        scale = max(float(scale), 0.05 * gmax)
+        worst[k] = float(np.abs(p.grad.cpu().numpy() - r).max() / scale)
     bad = {k: v for k, v in worst.items() if not v < tol}
-    assert not bad, bad
+    assert not bad, f"bad={bad} all={worst}"
     return worst
 
 
@@ -343,3 +348,36 @@ def test_errors_surface_as_exceptions(dev, checkpoint):
         m(torch.zeros(2, 5, 7, device=dev))               # wrong channel count
     assert m(torch.zeros(0, 5, 8, device=dev)).shape == (0, 3)
     assert ops.launch_count() > 0
+
+
+@pytest.mark.parametrize("groups", [1, 2, 3, 4])
+def test_h48_tier_vs_generic_tier(dev, checkpoint, groups):
+    """The specialised H=48 kernels (TMA bulk I/O, register-tiled FFMA) against the generic tier and
+    the oracle, for every groups-per-CTA setting, forward and saved tensors (through the gradients)."""
+    from neural_speech_decoding_b200 import _lib
+    gen = torch.Generator().manual_seed(100 + groups)
+    B, T = 70, 57                                       # ragged: 70 -> 96 padded, 3 tiles
+    x = torch.randn(B, T, 8, generator=gen) * 2.73
+    y = torch.randint(0, 3, (B,), generator=gen)
+    ref = RefEEGLSTM().eval()
+    ref.load_state_dict(checkpoint, strict=True)
+    lr = torch.nn.functional.cross_entropy(ref(x), y)
+    lr.backward()
+    want = ref(x).detach().numpy()
+    outs = {}
+    try:
+        for tier in (1, 0):
+            _lib.call("na_set_tuning", b"lstm_tier", tier)
+            _lib.call("na_set_tuning", b"h48_groups", groups)
+            m = make_model(dev, checkpoint).eval()
+            with torch.inference_mode():
+                outs[tier] = m(x.to(dev)).cpu().numpy()          # inference kernels (nothing saved)
+            assert rel(outs[tier], want) < FP32_TOL, tier
+            loss = torch.nn.functional.cross_entropy(m(x.to(dev)), y.to(dev))   # training kernels (saved c, gates)
+            loss.backward()
+            assert abs(loss.item() - lr.item()) < 1e-5
+            check_grads(m, {k: p.grad.numpy() for k, p in ref.named_parameters()})
+    finally:
+        _lib.call("na_set_tuning", b"lstm_tier", 0)
+        _lib.call("na_set_tuning", b"h48_groups", 0)
+    assert rel(outs[0], outs[1]) < FP32_TOL
