@@ -115,6 +115,15 @@ def main():
     np.savez(OUT / "ref_grads_3class_eval_b16.npz", sel=sel, y=y.numpy(), loss=loss.item(),
              logits=logits.detach().numpy(), **g)
 
+    # fp64 "truth" for the same 16 windows from the oracle's explicit restatement.  The reference's own
+    # fp32 autograd is up to 1.1e-5 away from it on attn.weight (softmax-over-time cancellation), so a
+    # 1e-5 parity test needs to know how much of a difference is the reference's own rounding.
+    from oracle.torch_ref import explicit_forward
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    l64 = torch.nn.functional.cross_entropy(explicit_forward(xt[sel].double(), sd64), y)
+    l64.backward()
+    np.savez(OUT / "fp64_grads_3class_eval_b16.npz", loss=l64.item(), **{k: v.grad.numpy() for k, v in sd64.items()})
+
     # Seeded default init: manual_seed(7); EEG_LSTM()  (same RNG draw order)
     torch.manual_seed(7)
     m7 = EEG_LSTM()

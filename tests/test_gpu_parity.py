@@ -240,7 +240,16 @@ def test_gradients_eval_mode_vs_reference(dev, checkpoint, windows, golden_dir):
     loss = torch.nn.functional.cross_entropy(logits, torch.from_numpy(g["y"]).to(dev))
     loss.backward()
     assert abs(loss.item() - float(g["loss"])) < 1e-5
-    check_grads(m, g)
+    # (1) within 1e-5 of the fp64 truth for every tensor; (2) within 1e-5 of the reference's fp32
+    # autograd, allowing for the reference's OWN distance from the truth (1.1e-5 on attn.weight, where
+    # the softmax-over-time backward cancels; every other tensor is < 6e-6)
+    truth = np.load(golden_dir / "fp64_grads_3class_eval_b16.npz")
+    check_grads(m, truth)
+    aw = np.abs(truth["attn.weight"]).max()
+    for k, p in m.named_parameters():
+        scale = aw if k == "attn.bias" else np.abs(truth[k]).max()
+        ref_err = np.abs(g[k] - truth[k]).max() / scale
+        assert np.abs(p.grad.cpu().numpy() - g[k]).max() / scale < FP32_TOL + ref_err, k
     # run-to-run reproducibility (deterministic reductions)
     g1 = [p.grad.clone() for p in m.parameters()]
     m.zero_grad()
