@@ -152,6 +152,29 @@ int na_head_bwd_f32(const float* dlogits, const float* h, const float* stats, co
                     float* dh, float* dparams, float* partials,
                     int64_t T, int64_t B, int64_t Bp, int64_t H, int64_t NC, na_stream_t stream);
 
+/* ---- tensor-core tier: whole decoder forward, bf16 operands / fp32 accumulate ----------------
+ * One persistent warp-specialised tcgen05 / TMEM / TMA kernel: K2 (input-gate contraction,
+ * fused as extra K-steps of the per-step MMA), K3 (2-layer recurrence, wavefronted), K4 (online
+ * attention pool + LayerNorm + MLP head) and the class softmax.  Replaces
+ * lstm_eeg_model.py:32-39 + :97 in eval mode for the flagship shape C=8, H=48, L=2.
+ * Contract (north_star): logits within 2e-2 (relative to max|logit|) of the fp32 reference,
+ * argmax identical on the repo's windows.
+ *   na_decoder_pack_bf16: the 8 nn.LSTM tensors of both layers -> `packed`
+ *       (na_decoder_packed_bf16_bytes() bytes): B operands [W_ih | bias hi,lo | W_hh] in the UMMA
+ *       K-major core-matrix layout, gate columns permuted to (unit/8, gate, unit%8).
+ *   na_decoder_infer_bf16: x TMP bf16 [T][Bp][8] (na_window_zscore with out_dtype = NA_BF16,
+ *       Bp a multiple of 128) -> logits [B,NC] fp32 (+ probs [B,NC] if not NULL).
+ */
+int64_t na_decoder_packed_bf16_bytes(void);
+int na_decoder_pack_bf16(const float* w_ih0, const float* w_hh0, const float* b_ih0, const float* b_hh0,
+                         const float* w_ih1, const float* w_hh1, const float* b_ih1, const float* b_hh1,
+                         void* packed, na_stream_t stream);
+int na_decoder_infer_bf16(const void* x_bf16_tmp, const void* packed,
+                          const float* attn_w, const float* attn_b, const float* ln_w, const float* ln_b,
+                          const float* fc0_w, const float* fc0_b, const float* fc3_w, const float* fc3_b,
+                          float* logits, float* probs,
+                          int64_t T, int64_t B, int64_t Bp, int64_t NC, na_stream_t stream);
+
 /* ---- K5: trial averaging -----------------------------------------------------------------
  * Replaces tester.py:54,89,97 (and :90,98 for the chunk): fp32 zeros, += in trial order
  * r = 0..R-1, then one IEEE division by R.   in [R][N] -> out [N].

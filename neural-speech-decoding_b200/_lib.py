@@ -31,6 +31,9 @@ SIGNATURES = {
     "na_head_param_floats": (c_int64, [I64, I64]),
     "na_head_partial_floats": (c_int64, [I64, I64, I64]),
     "na_head_bwd_f32": (c_int, [P] * 12 + [P, P, F32, P, P, P, I64, I64, I64, I64, I64, P]),
+    "na_decoder_packed_bf16_bytes": (c_int64, []),
+    "na_decoder_pack_bf16": (c_int, [P] * 9 + [P]),
+    "na_decoder_infer_bf16": (c_int, [P] * 12 + [I64, I64, I64, I64, P]),
     "na_trial_mean_f32": (c_int, [P, P, I64, I64, P]),
 }
 

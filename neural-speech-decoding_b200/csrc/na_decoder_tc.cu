@@ -1,0 +1,479 @@
+// Tensor-core tier (bf16 operands, fp32 accumulate/state): the WHOLE 2-layer decoder forward
+// (K2 input-gate contraction + K3 recurrence + K4 head + class softmax) as one persistent,
+// warp-specialised sm_100a kernel built on tcgen05.mma / TMEM / TMA.
+//
+//   * CTA = one tile of 128 windows (UMMA M = 128, cta_group::1), one CTA per SM, persistent
+//     over tiles.  Per layer and step ONE accumulator D[128 x 192] (all four gates of all 48
+//     units) lives in TMEM: D0 at columns [0,192), D1 at [192,384).
+//   * The time-parallel input contraction x_t.W_ih^T is not materialised (it would be HBM-write
+//     bound): it is fused as extra K-steps of the per-step MMA,
+//         layer 0:  A = [x_t (8) | 1 1 0.. (8) | h0_{t-1} (48)]            K = 64  (4 x K16)
+//         layer 1:  A = [h0_t (48) | h1_{t-1} (48) | 1 1 0.. (8) | 0 (8)]  K = 112 (7 x K16)
+//     and the bias rides on the constant-one columns as a bf16 hi+lo pair (fp32-accurate bias for
+//     free).  B = [W_ih | bias | W_hh] is staged once per CTA in shared memory, K-major -- which
+//     is exactly nn.LSTM's [4H, K] layout -- in the canonical no-swizzle core-matrix layout
+//     ([K/8][rows][8] bf16: 8 rows x 16 B = one 128-B core matrix).
+//   * A operands use the same layout, so (a) x_t of a tile is ONE contiguous 2 KB TMA bulk copy
+//     from the time-major bf16 input and (b) the epilogue thread of window r writes the 8 bf16 of
+//     a unit block with one conflict-free 16-B st.shared at row r.
+//   * Gate columns are permuted to n = (j/8)*32 + gate*8 + j%8, so one tcgen05.ld.32x32b.x32
+//     returns i,f,g,o of 8 units of the thread's window; c, the pooled sum and the softmax state
+//     never leave registers.
+//   * Warp roles (320 threads): warps 0-3 layer-0 epilogue, warps 4-7 layer-1 epilogue + attention
+//     pooling + head, warp 8 MMA issuer (one lane), warp 9 TMA producer + TMEM allocator.
+//     Layer 1 runs one step behind layer 0 (wavefront), so the two epilogue groups and the tensor
+//     pipe overlap; all hand-offs are mbarriers (tcgen05.commit for MMA completion).
+//   * Activations: tanh.approx.f32 (sigmoid = 0.5 tanh(x/2) + 0.5).  bf16 contract: logits within
+//     2e-2 of the fp32 reference, argmax identical on the repo's windows.
+#include "na_common.cuh"
+#include "na_sm100.cuh"
+
+namespace na {
+namespace tc {
+
+constexpr int kRows = 128;
+constexpr int kH = 48;
+constexpr int kN = 4 * kH;                   // 192
+constexpr int kAChunk = kRows * 16;          // bytes of one A K-chunk (8 bf16 per row)
+constexpr int kBChunk = kN * 16;             // bytes of one B K-chunk
+constexpr int kXStages = 4;
+constexpr int kK0Chunks = 8;                 // layer 0: x | ones | h0 x6
+constexpr int kK1Chunks = 14;                // layer 1: h0 x6 | h1 x6 | ones | zero
+constexpr int kThreads = 320;
+constexpr int kFc = NA_FC_HIDDEN;
+constexpr uint32_t kTmemCols = 512;
+
+struct HeadSmem {
+    float wa[kH], lnw[kH], lnb[kH];
+    float w0[kFc * kH];
+    float b0[kFc];
+    float w3[NA_MAX_CLASSES * kFc];
+    float b3[NA_MAX_CLASSES];
+    float ba;
+};
+
+struct Smem {
+    alignas(128) unsigned char b0[kK0Chunks * kBChunk];          // 24,576
+    alignas(128) unsigned char b1[kK1Chunks * kBChunk];          // 43,008
+    alignas(128) unsigned char x[kXStages][2 * kAChunk];         // [x chunk | ones chunk] per stage
+    alignas(128) unsigned char h0[2][6 * kAChunk];               // double-buffered h0_t
+    alignas(128) unsigned char h1[6 * kAChunk];
+    alignas(128) unsigned char onez[2 * kAChunk];                // [ones | zeros]
+    HeadSmem head;
+    alignas(8) uint64_t x_full[kXStages], x_empty[kXStages];
+    uint64_t d0_full, d1_full, h0_ready[2], h0_free[2], h1_ready;
+    uint32_t tmem_base;
+};
+
+// ---- tcgen05 wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // K-major, no swizzle: LBO = byte stride between the two 8-element K-chunks of one K16 step,
+    // SBO = byte stride between 8-row groups.  Bits: addr>>4 [0,14), LBO>>4 [16,30),
+    // SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64).
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+constexpr uint32_t kIdesc = (1u << 4)                      // D format f32
+                            | (1u << 7) | (1u << 10)       // A, B = bf16
+                            | ((uint32_t)(kN >> 3) << 17)  // N = 192
+                            | ((uint32_t)(kRows >> 4) << 24);   // M = 128   (A, B K-major: bits 15,16 = 0)
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float tanh_apx(float v) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float sigmoid_apx(float v) { return fmaf(0.5f, tanh_apx(0.5f * v), 0.5f); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
+
+__device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+
+// One LSTM cell update for the 8 units of a block; v = [i x8 | f x8 | g x8 | o x8] pre-activations.
+// Returns h packed as 4 x bf16x2.
+__device__ __forceinline__ void cell_block(const uint32_t (&v)[32], float* c, uint32_t (&hp)[4]) {
+    float h[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float gi = sigmoid_apx(__uint_as_float(v[u]));
+        const float gf = sigmoid_apx(__uint_as_float(v[8 + u]));
+        const float gg = tanh_apx(__uint_as_float(v[16 + u]));
+        const float go = sigmoid_apx(__uint_as_float(v[24 + u]));
+        c[u] = fmaf(gf, c[u], gi * gg);
+        h[u] = go * tanh_apx(c[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) hp[u] = pack_bf16(h[2 * u], h[2 * u + 1]);
+}
+
+// ---- weight packing ----------------------------------------------------------------------------
+// B0 [8 chunks][192][8] and B1 [14 chunks][192][8] bf16, row n = (j/8)*32 + gate*8 + j%8.
+__global__ void pack_decoder_bf16_kernel(const float* __restrict__ w_ih0, const float* __restrict__ w_hh0,
+                                         const float* __restrict__ b_ih0, const float* __restrict__ b_hh0,
+                                         const float* __restrict__ w_ih1, const float* __restrict__ w_hh1,
+                                         const float* __restrict__ b_ih1, const float* __restrict__ b_hh1,
+                                         __nv_bfloat16* __restrict__ out) {
+    const int total0 = kK0Chunks * 8 * kN, total1 = kK1Chunks * 8 * kN;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total0 + total1; idx += gridDim.x * blockDim.x) {
+        const bool l1 = idx >= total0;
+        const int e = l1 ? idx - total0 : idx;
+        const int k = (e / (kN * 8)) * 8 + (e % 8);       // K index
+        const int n = (e / 8) % kN;                       // permuted gate column
+        const int j = (n / 32) * 8 + (n % 8), q = (n % 32) / 8;
+        const int col = q * kH + j;                       // row of the torch weight tensors
+        float v = 0.f;
+        if (!l1) {
+            const float b = b_ih0[col] + b_hh0[col];
+            const float bh = __bfloat162float(__float2bfloat16_rn(b));
+            if (k < 8) v = w_ih0[col * 8 + k];
+            else if (k == 8) v = bh;
+            else if (k == 9) v = b - bh;
+            else if (k >= 16) v = w_hh0[col * kH + (k - 16)];
+        } else {
+            const float b = b_ih1[col] + b_hh1[col];
+            const float bh = __bfloat162float(__float2bfloat16_rn(b));
+            if (k < 48) v = w_ih1[col * kH + k];
+            else if (k < 96) v = w_hh1[col * kH + (k - 48)];
+            else if (k == 96) v = bh;
+            else if (k == 97) v = b - bh;
+        }
+        out[idx] = __float2bfloat16_rn(v);
+    }
+}
+
+// ---- the fused decoder kernel --------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][Bp][8] bf16
+                          const unsigned char* __restrict__ packed,   // B0 | B1 (pack_decoder_bf16_kernel)
+                          const float* __restrict__ attn_w, const float* __restrict__ attn_b,
+                          const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                          const float* __restrict__ fc0_w, const float* __restrict__ fc0_b,
+                          const float* __restrict__ fc3_w, const float* __restrict__ fc3_b,
+                          float* __restrict__ logits, float* __restrict__ probs,
+                          int T, int64_t B, int64_t Bp, int NC, int ntiles) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- one-time setup --------------------------------------------------------------------------
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(packed);
+        uint4* dst = reinterpret_cast<uint4*>(S.b0);     // b0 and b1 are contiguous in Smem
+        constexpr int n16 = (kK0Chunks + kK1Chunks) * kBChunk / 16;
+        for (int i = tid; i < n16; i += kThreads) dst[i] = src[i];
+        const uint4 ones = make_uint4(0x3F803F80u, 0u, 0u, 0u);     // bf16 {1,1,0,0,0,0,0,0}
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < kRows; i += kThreads) {
+#pragma unroll
+            for (int s = 0; s < kXStages; ++s) reinterpret_cast<uint4*>(S.x[s] + kAChunk)[i] = ones;
+            reinterpret_cast<uint4*>(S.onez)[i] = ones;
+            reinterpret_cast<uint4*>(S.onez + kAChunk)[i] = zero;
+        }
+        for (int i = tid; i < kH; i += kThreads) { S.head.wa[i] = attn_w[i]; S.head.lnw[i] = ln_w[i]; S.head.lnb[i] = ln_b[i]; }
+        for (int i = tid; i < kFc * kH; i += kThreads) S.head.w0[i] = fc0_w[i];
+        for (int i = tid; i < kFc; i += kThreads) S.head.b0[i] = fc0_b[i];
+        for (int i = tid; i < NC * kFc; i += kThreads) S.head.w3[i] = fc3_w[i];
+        for (int i = tid; i < NC; i += kThreads) S.head.b3[i] = fc3_b[i];
+        if (tid == 0) {
+            S.head.ba = attn_b[0];
+            for (int s = 0; s < kXStages; ++s) { mbar_init(&S.x_full[s], 1); mbar_init(&S.x_empty[s], 1); }
+            mbar_init(&S.d0_full, 1); mbar_init(&S.d1_full, 1);
+            mbar_init(&S.h0_ready[0], 128); mbar_init(&S.h0_ready[1], 128);
+            mbar_init(&S.h0_free[0], 1); mbar_init(&S.h0_free[1], 1);
+            mbar_init(&S.h1_ready, 128);
+            fence_mbar_init();
+        }
+        if (warp == 9) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
+                         "r"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncthreads();
+        tc_fence_after();
+    }
+    const uint32_t tmem = S.tmem_base;
+    const uint32_t tmem_d0 = tmem, tmem_d1 = tmem + kN;
+
+    int n0 = 0;                                            // running step index across tiles
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, n0 += T) {
+        const int64_t b0 = (int64_t)tile * kRows;
+        // ---- zero h0_{-1}, h1_{-1} of this tile ----------------------------------------------------
+        {
+            uint4* z0 = reinterpret_cast<uint4*>(S.h0[(n0 + 1) & 1]);      // buffer of step n0-1
+            uint4* z1 = reinterpret_cast<uint4*>(S.h1);
+            for (int i = tid; i < 6 * kAChunk / 16; i += kThreads) { z0[i] = make_uint4(0, 0, 0, 0); z1[i] = make_uint4(0, 0, 0, 0); }
+            fence_proxy_async_smem();
+            __syncthreads();
+        }
+
+        if (warp == 9) {
+            // ================= TMA producer ==========================================================
+            if (lane == 0) {
+                for (int t = 0; t < T; ++t) {
+                    const int n = n0 + t, s = n % kXStages, u = n / kXStages;
+                    mbar_wait(&S.x_empty[s], (u & 1) ^ 1);
+                    mbar_arrive_expect_tx(&S.x_full[s], kAChunk);
+                    bulk_load(S.x[s], x + ((int64_t)t * Bp + b0) * 8, kAChunk, &S.x_full[s]);
+                }
+            }
+        } else if (warp == 8) {
+            // ================= MMA issuer ============================================================
+            if (lane == 0) {
+                const uint32_t b0a = smem_u32(S.b0), b1a = smem_u32(S.b1);
+                for (int t = 0; t <= T; ++t) {
+                    if (t < T) {                                   // layer 0, step n
+                        const int n = n0 + t, s = n % kXStages, u = n / kXStages;
+                        mbar_wait(&S.x_full[s], u & 1);
+                        mbar_wait(&S.h0_ready[(n + 1) & 1], ((n - 1) >> 1) & 1);     // h0_{n-1} written, D0 drained
+                        tc_fence_after();
+                        const uint32_t hprev = smem_u32(S.h0[(n + 1) & 1]);
+                        umma_bf16(tmem_d0, umma_desc(smem_u32(S.x[s]), kAChunk, 128), umma_desc(b0a, kBChunk, 128), 0u);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+                            umma_bf16(tmem_d0, umma_desc(hprev + 2 * i * kAChunk, kAChunk, 128),
+                                      umma_desc(b0a + (2 + 2 * i) * kBChunk, kBChunk, 128), 1u);
+                        umma_commit(&S.x_empty[s]);
+                        umma_commit(&S.d0_full);
+                    }
+                    if (t >= 1) {                                  // layer 1, step m (one behind)
+                        const int m = n0 + t - 1;
+                        mbar_wait(&S.h0_ready[m & 1], (m >> 1) & 1);                 // h0_m written
+                        mbar_wait(&S.h1_ready, (m - 1) & 1);                         // h1_{m-1} written, D1 drained
+                        tc_fence_after();
+                        const uint32_t hin = smem_u32(S.h0[m & 1]), hrec = smem_u32(S.h1);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+                            umma_bf16(tmem_d1, umma_desc(hin + 2 * i * kAChunk, kAChunk, 128),
+                                      umma_desc(b1a + (2 * i) * kBChunk, kBChunk, 128), i == 0 ? 0u : 1u);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+                            umma_bf16(tmem_d1, umma_desc(hrec + 2 * i * kAChunk, kAChunk, 128),
+                                      umma_desc(b1a + (6 + 2 * i) * kBChunk, kBChunk, 128), 1u);
+                        umma_bf16(tmem_d1, umma_desc(smem_u32(S.onez), kAChunk, 128),
+                                  umma_desc(b1a + 12 * kBChunk, kBChunk, 128), 1u);
+                        umma_commit(&S.d1_full);
+                        umma_commit(&S.h0_free[m & 1]);
+                    }
+                }
+            }
+        } else if (warp < 4) {
+            // ================= layer-0 epilogue: gates -> c, h0 (bf16) ================================
+            const int row = warp * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+            float c[kH];
+#pragma unroll
+            for (int j = 0; j < kH; ++j) c[j] = 0.f;
+            for (int t = 0; t < T; ++t) {
+                const int n = n0 + t;
+                mbar_wait(&S.d0_full, n & 1);
+                mbar_wait(&S.h0_free[n & 1], ((n >> 1) & 1) ^ 1);       // layer-1 MMA of step n-2 has read this buffer
+                tc_fence_after();
+                unsigned char* dst = S.h0[n & 1] + row * 16;
+#pragma unroll
+                for (int blk = 0; blk < 6; ++blk) {
+                    uint32_t v[32], hp[4];
+                    tmem_ld32(tmem_d0 + lane_base + blk * 32, v);
+                    cell_block(v, c + blk * 8, hp);
+                    st_shared_v4(dst + blk * kAChunk, hp[0], hp[1], hp[2], hp[3]);
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(&S.h0_ready[n & 1]);
+            }
+        } else {
+            // ================= layer-1 epilogue: gates -> c, h1; attention pooling; head ================
+            const int q = warp - 4;
+            const int row = q * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+            float c[kH], z[kH];
+#pragma unroll
+            for (int j = 0; j < kH; ++j) { c[j] = 0.f; z[j] = 0.f; }
+            float mx = -INFINITY, l = 0.f;
+            const float ba = S.head.ba;
+            for (int t = 0; t < T; ++t) {
+                const int m = n0 + t;
+                mbar_wait(&S.d1_full, m & 1);
+                tc_fence_after();
+                unsigned char* dst = S.h1 + row * 16;
+                uint32_t hb[24];
+                float score = ba;
+#pragma unroll
+                for (int blk = 0; blk < 6; ++blk) {
+                    uint32_t v[32], hp[4];
+                    tmem_ld32(tmem_d1 + lane_base + blk * 32, v);
+                    cell_block(v, c + blk * 8, hp);
+                    st_shared_v4(dst + blk * kAChunk, hp[0], hp[1], hp[2], hp[3]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        hb[blk * 4 + u] = hp[u];
+                        score = fmaf(bf16_lo(hp[u]), S.head.wa[blk * 8 + 2 * u], score);
+                        score = fmaf(bf16_hi(hp[u]), S.head.wa[blk * 8 + 2 * u + 1], score);
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(&S.h1_ready);
+                // online softmax over time (lstm_eeg_model.py:35-37), lazy rescale
+                if (score > mx) {
+                    const float sc = __expf(mx - score);
+                    l *= sc;
+#pragma unroll
+                    for (int j = 0; j < kH; ++j) z[j] *= sc;
+                    mx = score;
+                }
+                const float e = __expf(score - mx);
+                l += e;
+#pragma unroll
+                for (int u = 0; u < 24; ++u) {
+                    z[2 * u] = fmaf(e, bf16_lo(hb[u]), z[2 * u]);
+                    z[2 * u + 1] = fmaf(e, bf16_hi(hb[u]), z[2 * u + 1]);
+                }
+            }
+            // ---- head for this thread's window: LN -> fc0 -> RReLU(eval) -> fc3 -> softmax ----------
+            const int64_t b = b0 + row;
+            const float inv_l = 1.0f / l;
+            float mean = 0.f;
+#pragma unroll
+            for (int j = 0; j < kH; ++j) { z[j] *= inv_l; mean += z[j]; }
+            mean *= (1.0f / kH);
+            float var = 0.f;
+#pragma unroll
+            for (int j = 0; j < kH; ++j) { const float d = z[j] - mean; var = fmaf(d, d, var); }
+            const float rstd = rsqrtf(var * (1.0f / kH) + kLnEps);
+#pragma unroll
+            for (int j = 0; j < kH; ++j) z[j] = fmaf((z[j] - mean) * rstd, S.head.lnw[j], S.head.lnb[j]);
+            float lg[NA_MAX_CLASSES];
+#pragma unroll
+            for (int k = 0; k < NA_MAX_CLASSES; ++k) lg[k] = (k < NC) ? S.head.b3[k] : -INFINITY;
+            for (int o = 0; o < kFc; ++o) {
+                float a = S.head.b0[o];
+#pragma unroll
+                for (int j = 0; j < kH; ++j) a = fmaf(S.head.w0[o * kH + j], z[j], a);
+                a = a >= 0.f ? a : a * kRReluEvalSlope;
+#pragma unroll
+                for (int k = 0; k < NA_MAX_CLASSES; ++k)
+                    if (k < NC) lg[k] = fmaf(S.head.w3[k * kFc + o], a, lg[k]);
+            }
+            if (b < B) {
+                float mxl = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < NA_MAX_CLASSES; ++k) mxl = fmaxf(mxl, lg[k]);
+                float den = 0.f, pe[NA_MAX_CLASSES];
+#pragma unroll
+                for (int k = 0; k < NA_MAX_CLASSES; ++k) { pe[k] = (k < NC) ? __expf(lg[k] - mxl) : 0.f; den += pe[k]; }
+#pragma unroll
+                for (int k = 0; k < NA_MAX_CLASSES; ++k)
+                    if (k < NC) {
+                        logits[b * NC + k] = lg[k];
+                        if (probs) probs[b * NC + k] = pe[k] / den;
+                    }
+            }
+        }
+        __syncthreads();       // tile done: every MMA has completed (layer-1 epilogue saw the last d1_full)
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    }
+}
+
+}  // namespace tc
+}  // namespace na
+
+extern "C" int64_t na_decoder_packed_bf16_bytes(void) {
+    return (int64_t)(na::tc::kK0Chunks + na::tc::kK1Chunks) * na::tc::kBChunk;
+}
+
+extern "C" int na_decoder_pack_bf16(const float* w_ih0, const float* w_hh0, const float* b_ih0, const float* b_hh0,
+                                    const float* w_ih1, const float* w_hh1, const float* b_ih1, const float* b_hh1,
+                                    void* packed, na_stream_t stream) {
+    using namespace na;
+    NA_REQUIRE_PTR(w_ih0); NA_REQUIRE_PTR(w_hh0); NA_REQUIRE_PTR(b_ih0); NA_REQUIRE_PTR(b_hh0);
+    NA_REQUIRE_PTR(w_ih1); NA_REQUIRE_PTR(w_hh1); NA_REQUIRE_PTR(b_ih1); NA_REQUIRE_PTR(b_hh1);
+    NA_REQUIRE_PTR(packed);
+    tc::pack_decoder_bf16_kernel<<<64, 256, 0, as_stream(stream)>>>(w_ih0, w_hh0, b_ih0, b_hh0, w_ih1, w_hh1, b_ih1, b_hh1,
+                                                                    reinterpret_cast<__nv_bfloat16*>(packed));
+    count_launch();
+    return check_launch("na_decoder_pack_bf16");
+}
+
+extern "C" int na_decoder_infer_bf16(const void* x_bf16_tmp, const void* packed, const float* attn_w,
+                                     const float* attn_b, const float* ln_w, const float* ln_b, const float* fc0_w,
+                                     const float* fc0_b, const float* fc3_w, const float* fc3_b, float* logits,
+                                     float* probs, int64_t T, int64_t B, int64_t Bp, int64_t NC, na_stream_t stream) {
+    using namespace na;
+    NA_REQUIRE(T >= 1 && T < (1 << 20) && B >= 1 && Bp >= B && Bp % tc::kRows == 0, NA_EINVAL,
+               "na_decoder_infer_bf16: bad shape T=%lld B=%lld Bp=%lld (Bp must be a multiple of %d)", (long long)T,
+               (long long)B, (long long)Bp, tc::kRows);
+    NA_REQUIRE(NC >= 1 && NC <= NA_MAX_CLASSES, NA_EUNSUPPORTED, "na_decoder_infer_bf16: num_classes=%lld", (long long)NC);
+    NA_REQUIRE_PTR(x_bf16_tmp); NA_REQUIRE_PTR(packed); NA_REQUIRE_PTR(logits);
+    NA_OPTIONAL_PTR(probs);
+    NA_REQUIRE(attn_w && attn_b && ln_w && ln_b && fc0_w && fc0_b && fc3_w && fc3_b, NA_EINVAL,
+               "na_decoder_infer_bf16: null parameter pointer");
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const size_t smem = sizeof(tc::Smem) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(tc::decoder_infer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
+    const int ntiles = (int)(Bp / tc::kRows);
+    const int grid = ntiles < sms ? ntiles : sms;
+    tc::decoder_infer_bf16_kernel<<<grid, tc::kThreads, smem, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x_bf16_tmp), reinterpret_cast<const unsigned char*>(packed), attn_w, attn_b,
+        ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, (int)T, B, Bp, (int)NC, ntiles);
+    count_launch();
+    return check_launch("na_decoder_infer_bf16");
+}

@@ -78,8 +78,12 @@ class EEG_LSTM(nn.Module):
         )
         self.dropout_p = float(dropout)
         self.zscore_input = False
+        # torch.float32: exact tier (FFMA, 1e-5 contract).  torch.bfloat16: tensor-core tier for eval
+        # forwards (tcgen05, bf16 operands / fp32 accumulate, 2e-2 contract); also selected by bf16
+        # inputs or a .bfloat16() module.  Training always runs the exact tier.
+        self.compute_dtype = torch.float32
         self._injected_noise: Optional[Dict[str, torch.Tensor]] = None
-        self._pack_cache: Dict[int, tuple] = {}
+        self._pack_cache: Dict[object, tuple] = {}
 
     # -- helpers ---------------------------------------------------------------------------
     def _head_params(self) -> List[torch.Tensor]:
@@ -95,6 +99,35 @@ class EEG_LSTM(nn.Module):
                 hit = (key, ops.pack_lstm_layer(*ps))
             self._pack_cache[l] = hit
         return hit[1]
+
+    def tc_supported(self) -> bool:
+        """Shape implemented by the tensor-core tier (the flagship decoder)."""
+        return (self.lstm.input_size == 8 and self.lstm.hidden_size == 48 and self.lstm.num_layers == 2
+                and self.fc[3].out_features <= 16)
+
+    def _packed_tc(self):
+        ps = self.lstm.layer(0) + self.lstm.layer(1)
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+        hit = self._pack_cache.get("tc")
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, ops.decoder_pack_bf16(ps))
+            self._pack_cache["tc"] = hit
+        return hit[1]
+
+    def decode(self, x: torch.Tensor, want_probs: bool = True):
+        """Eval-mode forward without autograd: x [B,T,C] on CUDA -> (logits fp32 [B,K], probs fp32 [B,K] or
+        empty).  Picks the tier from ``compute_dtype`` / the dtype of ``x`` / the parameters."""
+        ops._require_cuda(x)
+        bf16 = (self.compute_dtype == torch.bfloat16 or x.dtype == torch.bfloat16
+                or self.attn.weight.dtype == torch.bfloat16)
+        with torch.no_grad():
+            if bf16 and self.tc_supported():
+                return ops.decoder_infer_tc(x, self._packed_tc(), self._head_params(), want_probs, self.zscore_input)
+            L = self.lstm.num_layers
+            return ops.decoder_infer(x, [self.lstm.layer(l) for l in range(L)],
+                                     [ops._f32c(t) for t in self._head_params()], want_probs, self.zscore_input,
+                                     [self._packed(l) for l in range(L)])
 
     def inject_noise(self, drop1: Optional[torch.Tensor] = None, rrelu_slope: Optional[torch.Tensor] = None,
                      drop2: Optional[torch.Tensor] = None) -> None:
@@ -149,9 +182,7 @@ class EEG_LSTM(nn.Module):
         head = self._head_params()
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if not self.training and not needs_grad:
-            packed = [self._packed(l) for l in range(L)]
-            logits, _ = ops.decoder_infer(x, lstm_params, [ops._f32c(t) for t in head], False,
-                                          self.zscore_input, packed)
+            logits, _ = self.decode(x, want_probs=False)
         else:
             d1 = rr = d2 = None
             if self.training:
@@ -206,10 +237,7 @@ class SimplePredictor:
         x = self.pre.transform(chunk_TxC)
         x_t = torch.from_numpy(np.ascontiguousarray(x[None, ...])).float().to(self.compute_device)
         with self._no_grad():
-            m = self.model
-            _, probs = ops.decoder_infer(x_t, [m.lstm.layer(l) for l in range(m.lstm.num_layers)],
-                                         m._head_params(), True, m.zscore_input,
-                                         [m._packed(l) for l in range(m.lstm.num_layers)])
+            _, probs = self.model.decode(x_t, want_probs=True)
             probs = probs[0].detach().cpu().numpy().astype(np.float32)
         y_idx = int(np.argmax(probs))
         return probs, self.class_names[y_idx]
@@ -219,8 +247,5 @@ class SimplePredictor:
         x = np.stack([self.pre.transform(c) for c in chunks_BxTxC]) if preprocess else np.asarray(chunks_BxTxC)
         x_t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.compute_device)
         with self._no_grad():
-            m = self.model
-            _, probs = ops.decoder_infer(x_t, [m.lstm.layer(l) for l in range(m.lstm.num_layers)],
-                                         m._head_params(), True, m.zscore_input,
-                                         [m._packed(l) for l in range(m.lstm.num_layers)])
+            _, probs = self.model.decode(x_t, want_probs=True)
         return probs.cpu().numpy().astype(np.float32)

@@ -25,8 +25,8 @@ HEAD_KEYS = ("attn.weight", "attn.bias", "ln.weight", "ln.bias",
              "fc.0.weight", "fc.0.bias", "fc.3.weight", "fc.3.bias")
 
 
-def padded_batch(b: int) -> int:
-    return max(BATCH_ALIGN, (b + BATCH_ALIGN - 1) // BATCH_ALIGN * BATCH_ALIGN)
+def padded_batch(b: int, align: int = BATCH_ALIGN) -> int:
+    return max(align, (b + align - 1) // align * align)
 
 
 def _require_cuda(*tensors: Optional[Tensor]) -> None:
@@ -63,7 +63,7 @@ def _stream() -> int:
 
 def all_custom_ops():
     return [window_zscore, pack_lstm_layer, lstm_layer_fwd, lstm_layer_bwd, lstm_layer_wgrad, head_fwd,
-            head_bwd, trial_mean]
+            head_bwd, trial_mean, decoder_pack_bf16, decoder_infer_bf16]
 
 
 def launch_count() -> int:
@@ -74,7 +74,8 @@ def launch_count() -> int:
 # custom ops (kernel granularity)
 # ------------------------------------------------------------------------------------------
 @torch.library.custom_op("neuroalpha::window_zscore", mutates_args=(), device_types="cuda")
-def window_zscore(x: Tensor, T: int, hop: int, normalize: bool, time_major: bool, bf16: bool) -> Tensor:
+def window_zscore(x: Tensor, T: int, hop: int, normalize: bool, time_major: bool, bf16: bool,
+                  pad_to: int = BATCH_ALIGN) -> Tensor:
     """K1.  x: [B,T,C] batch or [n_samples,C] stream (then windows start every ``hop`` samples).
 
     Returns the windows ([B,T,C], or TMP [T,Bp,C] when ``time_major``), z-scored per window and
@@ -91,7 +92,7 @@ def window_zscore(x: Tensor, T: int, hop: int, normalize: bool, time_major: bool
         B = 0 if n < T else (n - T) // hop + 1
     else:
         raise RuntimeError("window_zscore: x must be [B,T,C] or [n_samples,C]")
-    Bp = padded_batch(B) if time_major else B
+    Bp = padded_batch(B, pad_to) if time_major else B
     dt = torch.bfloat16 if bf16 else torch.float32
     y = torch.empty((T, Bp, C) if time_major else (B, T, C), dtype=dt, device=x.device)
     if y.numel():
@@ -101,14 +102,14 @@ def window_zscore(x: Tensor, T: int, hop: int, normalize: bool, time_major: bool
 
 
 @window_zscore.register_fake
-def _(x, T, hop, normalize, time_major, bf16):
+def _(x, T, hop, normalize, time_major, bf16, pad_to=BATCH_ALIGN):
     if x.dim() == 3:
         B, C = x.shape[0], x.shape[2]
     else:
         n, C = x.shape
         B = 0 if n < T else (n - T) // hop + 1
     dt = torch.bfloat16 if bf16 else torch.float32
-    return x.new_empty((T, padded_batch(B), C) if time_major else (B, T, C), dtype=dt)
+    return x.new_empty((T, padded_batch(B, pad_to), C) if time_major else (B, T, C), dtype=dt)
 
 
 @torch.library.custom_op("neuroalpha::pack_lstm_layer", mutates_args=(), device_types="cuda")
@@ -268,6 +269,60 @@ def trial_mean(x: Tensor) -> Tensor:
 @trial_mean.register_fake
 def _(x):
     return x.new_empty(x.shape[1:])
+
+
+TC_TILE = 128      # windows per CTA tile of the tensor-core tier (UMMA M)
+
+
+@torch.library.custom_op("neuroalpha::decoder_pack_bf16", mutates_args=(), device_types="cuda")
+def decoder_pack_bf16(lstm_flat: Sequence[Tensor]) -> Tensor:
+    """The 8 nn.LSTM tensors (layer 0 then layer 1) -> UMMA B operands of the tensor-core tier."""
+    _require_cuda(*lstm_flat)
+    ts = [_f32c(t) for t in lstm_flat]
+    if len(ts) != 8 or tuple(ts[0].shape) != (192, 8) or tuple(ts[4].shape) != (192, 48):
+        raise RuntimeError("decoder_pack_bf16: the tensor-core tier implements input_size=8, hidden_size=48, num_layers=2")
+    packed = torch.empty((_lib.query("na_decoder_packed_bf16_bytes"),), dtype=torch.uint8, device=ts[0].device)
+    _lib.call("na_decoder_pack_bf16", *[t.data_ptr() for t in ts], packed.data_ptr(), _stream())
+    return packed
+
+
+@decoder_pack_bf16.register_fake
+def _(lstm_flat):
+    return lstm_flat[0].new_empty((22 * 3072,), dtype=torch.uint8)
+
+
+@torch.library.custom_op("neuroalpha::decoder_infer_bf16", mutates_args=(), device_types="cuda")
+def decoder_infer_bf16(x_tmp: Tensor, packed: Tensor, head: Sequence[Tensor], B: int,
+                       want_probs: bool) -> Tuple[Tensor, Tensor]:
+    """Whole decoder forward on tcgen05 (bf16 operands, fp32 accumulate).  x_tmp: TMP bf16 [T,Bp,8]
+    with Bp a multiple of 128 (window_zscore(..., time_major=True, bf16=True, pad_to=128))."""
+    _require_cuda(x_tmp, packed, *head)
+    T, Bp, C = x_tmp.shape
+    if x_tmp.dtype != torch.bfloat16 or C != 8 or Bp % TC_TILE:
+        raise RuntimeError("decoder_infer_bf16: x_tmp must be bf16 [T, Bp % 128 == 0, 8]")
+    head = [_f32c(t) for t in head]
+    NC = head[6].shape[0]
+    logits = torch.empty((B, NC), dtype=torch.float32, device=x_tmp.device)
+    probs = torch.empty((B, NC) if want_probs else (0,), dtype=torch.float32, device=x_tmp.device)
+    _lib.call("na_decoder_infer_bf16", x_tmp.data_ptr(), packed.data_ptr(), *[t.data_ptr() for t in head],
+              logits.data_ptr(), _ptr(probs) if want_probs else None, T, B, Bp, NC, _stream())
+    return logits, probs
+
+
+@decoder_infer_bf16.register_fake
+def _(x_tmp, packed, head, B, want_probs):
+    NC = head[6].shape[0]
+    return x_tmp.new_empty((B, NC), dtype=torch.float32), x_tmp.new_empty((B, NC) if want_probs else (0,), dtype=torch.float32)
+
+
+def decoder_infer_tc(x: Tensor, packed: Tensor, head_params: Sequence[Tensor], want_probs: bool = False,
+                     zscore: bool = False) -> Tuple[Tensor, Tensor]:
+    """Eval forward on the tensor-core tier.  x [B,T,8] fp32 (or bf16) -> (logits fp32, probs or empty).
+    K1 packs the windows time-major in bf16 (one read of x, one half-size write)."""
+    _require_cuda(x)
+    B, T, C = x.shape
+    xt = window_zscore(x, T, T, zscore, True, True, TC_TILE)
+    return decoder_infer_bf16(xt, packed, list(head_params), B, want_probs)
 
 
 # ------------------------------------------------------------------------------------------

@@ -121,16 +121,12 @@ def run_trials_batched(windows, model, return_device: bool = False, chunk_trials
     if dev.type != "cuda":
         raise RuntimeError("run_trials_batched: the model must live on a CUDA device (no CPU fallback)")
     m = model
-    L = m.lstm.num_layers
-    lstm_params = [m.lstm.layer(l) for l in range(L)]
-    head = m._head_params()
     with torch.inference_mode():
-        packed = [m._packed(l) for l in range(L)]
-        NC = head[6].shape[0]
+        NC = m.fc[3].out_features
         probs_all = torch.empty((R, B, NC), dtype=torch.float32, device=dev)
         if windows.is_cuda:
             flat = windows.reshape(R * B, T, C)
-            _, p = ops.decoder_infer(flat, lstm_params, head, True, m.zscore_input, packed)
+            _, p = m.decode(flat, want_probs=True)
             probs_all = p.reshape(R, B, NC)
         else:
             main = torch.cuda.current_stream(dev)
@@ -146,7 +142,7 @@ def run_trials_batched(windows, model, return_device: bool = False, chunk_trials
                     bufs[k].copy_(windows[r], non_blocking=True)
                     ready[k].record(side)
                 main.wait_event(ready[k])
-                _, p = ops.decoder_infer(bufs[k], lstm_params, head, True, m.zscore_input, packed)
+                _, p = m.decode(bufs[k], want_probs=True)
                 probs_all[r].copy_(p)
                 freed[k].record(main)
         avg = ops.trial_mean(probs_all)

@@ -1,0 +1,107 @@
+"""Tensor-core tier (tcgen05, bf16 operands / fp32 accumulate) against the fp32 reference.
+
+Contract (BASELINE.json north_star): logits within 2e-2 of the reference (max|d| / max|ref|),
+argmax class labels identical on the repo's EEG_data_collection windows.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import numpy_oracle as no
+from oracle.torch_ref import RefEEGLSTM
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 2e-2
+
+
+def rel(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from neural_speech_decoding_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def bf16_model(dev, sd, **kw):
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    m = EEG_LSTM(**kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).eval()
+    m.compute_dtype = torch.bfloat16
+    return m
+
+
+def test_bf16_logits_and_argmax_on_all_windows(dev, checkpoint, windows, golden_dir):
+    ref = np.load(golden_dir / "ref_outputs_3class.npz")["logits_raw_b1"]
+    m = bf16_model(dev, checkpoint)
+    with torch.inference_mode():
+        got = m(torch.from_numpy(windows["X"]).to(dev)).cpu().numpy()
+    assert got.shape == (324, 3) and np.isfinite(got).all()
+    assert rel(got, ref) < BF16_TOL, rel(got, ref)
+    assert np.array_equal(got.argmax(1), ref.argmax(1))
+    # probabilities + ragged sizes (1 window; 130 windows = 2 tiles, second one almost empty)
+    with torch.inference_mode():
+        lg1, p1 = m.decode(torch.from_numpy(windows["X"][5:6]).to(dev))
+        lg130, p130 = m.decode(torch.from_numpy(windows["X"][:130]).to(dev))
+    assert rel(lg1.cpu().numpy(), ref[5:6]) < BF16_TOL
+    assert np.array_equal(lg130.cpu().numpy(), got[:130])          # independent of batch / tile position
+    np.testing.assert_allclose(p130.cpu().numpy(), no.softmax(lg130.cpu().numpy()), atol=2e-6)
+    assert np.array_equal(lg1.cpu().numpy(), got[5:6])
+
+
+def test_bf16_synthetic_512_and_many_tiles(dev, checkpoint):
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(512, 625, 8, generator=gen) * 2.73
+    refm = RefEEGLSTM().eval()
+    refm.load_state_dict(checkpoint, strict=True)
+    with torch.inference_mode():
+        want = refm(x).numpy()
+    m = bf16_model(dev, checkpoint)
+    with torch.inference_mode():
+        got = m(x.to(dev)).cpu().numpy()
+    assert rel(got, want) < BF16_TOL, rel(got, want)
+    margin = np.sort(want, axis=1)
+    safe = (margin[:, -1] - margin[:, -2]) > 0.1                   # argmax is only defined up to the tolerance
+    assert np.array_equal(got.argmax(1)[safe], want.argmax(1)[safe])
+    # more tiles than SMs (persistent loop, tile-boundary state reset): 160 tiles x 128 short windows
+    xs = torch.randn(160 * 128, 12, 8, generator=gen) * 2.73
+    with torch.inference_mode():
+        a = m(xs.to(dev)).cpu().numpy()
+        m.compute_dtype = torch.float32
+        b = m(xs.to(dev)).cpu().numpy()                             # exact tier
+    assert rel(a, b) < BF16_TOL, rel(a, b)
+
+
+def test_bf16_input_tensor_selects_tier_and_keeps_dtype(dev, checkpoint, windows):
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    m = EEG_LSTM()
+    m.load_state_dict(checkpoint, strict=True)
+    m = m.to(dev).eval()
+    x = torch.from_numpy(windows["X"][:8]).to(dev)
+    with torch.inference_mode():
+        y32 = m(x)
+        y16 = m(x.bfloat16())
+    assert y32.dtype == torch.float32 and y16.dtype == torch.bfloat16
+    assert rel(y16.float().cpu().numpy(), y32.cpu().numpy()) < 3e-2
+
+
+def test_bf16_five_class_and_trial_mean(dev, windows, golden_dir):
+    from neural_speech_decoding_b200.tester import run_trials_batched
+    f = np.load(golden_dir / "ref_5class.npz")
+    sd = {k[3:]: torch.from_numpy(f[k]) for k in f.files if k.startswith("sd.")}
+    m = bf16_model(dev, sd, num_classes=5)
+    x = torch.from_numpy(windows["X"][f["sel"]]).to(dev)
+    with torch.inference_mode():
+        got = m(x).cpu().numpy()
+    assert got.shape == (32, 5) and rel(got, f["logits"]) < BF16_TOL
+    R, B = 10, 3
+    w = windows["X"][:R * B].reshape(R, B, 625, 8)
+    want = no.trial_mean(no.softmax(no.decoder_forward(w.reshape(R * B, 625, 8), {k: v.numpy() for k, v in sd.items()})).reshape(R, B, 5))
+    avg = run_trials_batched(w, m)
+    assert np.abs(avg - want).max() < 2e-2
