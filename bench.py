@@ -220,46 +220,55 @@ def run_gpu_arm(args):
     n_win = R * B
     host = synth_windows(n_win, seed=1000 + rank, pin=True).reshape(R, B, T, C)
     x_dev = host.to(dev)                            # 819 MB per rank: larger than the 126 MB L2
-
-    L = model.lstm.num_layers
-    lstm_params = [model.lstm.layer(l) for l in range(L)]
-    head = model._head_params()
-    with torch.inference_mode():
-        packed = [model._packed(l) for l in range(L)]
+    x_flat = x_dev.reshape(n_win, T, C)
 
     def step_device():
         with torch.inference_mode():
-            _, p = ops.decoder_infer(x_dev.reshape(n_win, T, C), lstm_params, head, True, False, packed)
+            _, p = model.decode(x_flat, want_probs=True)
             return ops.trial_mean(p.reshape(R, B, NC))
 
     def step_e2e():
         return run_trials_batched(host, model)      # pinned host in, numpy out
 
-    sampler = ClockSampler(local).start() if rank == 0 else None
-    l0 = ops.launch_count()
-    ms = time_steps(step_device, args.steps, args.warmup, world, dev)
-    launches = ops.launch_count() - l0 - 0
-    clocks = sampler.stop() if sampler else None
-    launches_timed = launches * args.steps // (args.steps + args.warmup)
-    value = world * n_win * args.steps / (ms * 1e-3)
+    def measure(dtype):
+        model.compute_dtype = dtype
+        sampler = ClockSampler(local).start() if rank == 0 else None
+        for _ in range(args.warmup):
+            step_device()
+        l0 = ops.launch_count()
+        ms = time_steps(step_device, args.steps, 0, world, dev)
+        launches = ops.launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        e_steps = max(1, min(args.steps, 10))
+        ms_e2e = time_steps(step_e2e, e_steps, 2, world, dev)
+        return {"value": world * n_win * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
+                "e2e_value": world * n_win * e_steps / (ms_e2e * 1e-3), "e2e_ms_per_step": ms_e2e / e_steps,
+                "launches": launches, "clocks": clocks}
 
-    ms_e2e = time_steps(step_e2e, max(1, args.steps), 1, world, dev)
-    e2e_value = world * n_win * max(1, args.steps) / (ms_e2e * 1e-3)
+    bf = measure(torch.bfloat16)                    # tensor-core tier (headline)
+    fp = measure(torch.float32)                     # exact tier
 
-    # ---- dominant kernel alone: layer-1 recurrence (K3), CUDA events on the launching stream ----
+    # ---- dominant kernels alone, CUDA events on the launching stream -------------------------------
+    reps = max(3, min(args.steps, 10))
     with torch.inference_mode():
-        xt = ops.window_zscore(x_dev.reshape(n_win, T, C), T, T, False, True, False)
+        model.compute_dtype = torch.bfloat16
+        xt16 = ops.window_zscore(x_flat, T, T, False, True, True, ops.TC_TILE)
+        packed_tc, head = model._packed_tc(), model._head_params()
+        ms_tc = time_steps(lambda: ops.decoder_infer_bf16(xt16, packed_tc, head, n_win, True), reps, 2, 1, dev) / reps
+        ms_pack16 = time_steps(lambda: ops.window_zscore(x_flat, T, T, False, True, True, ops.TC_TILE), reps, 2, 1, dev) / reps
+        ms_z = time_steps(lambda: ops.window_zscore(x_flat, T, T, True, False, False), reps, 2, 1, dev) / reps
+        del xt16
+        packed = [model._packed(l) for l in range(2)]
+        xt = ops.window_zscore(x_flat, T, T, False, True, False)
         h0 = ops.lstm_layer_fwd(xt, packed[0][0], packed[0][1], None, 1.0, False)[0]
         del xt
-
-        def k_l1():
-            return ops.lstm_layer_fwd(h0, packed[1][0], packed[1][1], None, 1.0, False)[0]
-        reps = max(3, args.steps)
-        ms_l1 = time_steps(k_l1, reps, 2, 1, dev) / reps
+        ms_l1 = time_steps(lambda: ops.lstm_layer_fwd(h0, packed[1][0], packed[1][1], None, 1.0, False)[0], reps, 2, 1, dev) / reps
         del h0
+    tc_tflops = FWD_FLOPS_PER_WINDOW * n_win / (ms_tc * 1e-3) / 1e12
     l1_tflops = L1_KERNEL_FLOPS_PER_WINDOW * n_win / (ms_l1 * 1e-3) / 1e12
+    tile_rounds = -(-(n_win // 128) // 148)
 
-    # ---- measured CUDA-core fp32 peak (FFMA probe) -------------------------------------------
+    # ---- measured CUDA-core fp32 peak (FFMA probe) -------------------------------------------------
     out = torch.zeros(4, device=dev)
     blocks, iters = 148 * 8, 1 << 16
     def probe():
@@ -267,7 +276,6 @@ def run_gpu_arm(args):
     ms_probe = time_steps(probe, 3, 2, 1, dev) / 3
     ffma_peak = blocks * 256 * 2 * 16 * iters / (ms_probe * 1e-3) / 1e12
 
-    # ---- train leg (fwd + bwd + all-reduce + Adam), per-GPU micro-batch --------------------------
     train = None
     if not args.no_train:
         train = train_leg(args, world, rank, dev)
@@ -275,33 +283,49 @@ def run_gpu_arm(args):
     if rank != 0:
         return
     cpu = cpu_arm(3, 1) if world == 1 and not args.no_cpu else None
+    peak = peaks["bf16_tflops"]     # the kernel is timed alone -> burst figure
     line = {
-        "metric": "EEG windows/sec (decoder fwd + softmax + 10-trial mean)", "value": value, "unit": "windows/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "metric": "EEG windows/sec (decoder fwd + softmax + 10-trial mean)", "value": bf["value"], "unit": "windows/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": bf["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 (tcgen05 operands; fp32 accumulate, cell state, pooling, head)", "data": "synthetic",
         "config": {"workload": "configs[1]: 3-class decoder (T=625,C=8,H=48,L=2) batched inference + run_trials "
                                "10-trial probability averaging, shipped .pth weights",
                    "trials": R, "sessions_per_gpu": B, "windows_per_step_per_gpu": n_win,
-                   "l2_policy": "inputs larger than L2 (819 MB per step per GPU)", "parallelism": f"batch-shard x{world}"},
-        "e2e": {"value": e2e_value, "unit": "windows/s", "ms_per_step": ms_e2e / max(1, args.steps),
+                   "l2_policy": "inputs larger than L2 (819 MB fp32 windows per step per GPU)",
+                   "parallelism": f"batch-shard x{world}, no collective",
+                   "parity": "tests/test_gpu_bf16.py: logits within 2e-2 of the fp32 reference, argmax identical on the 324 repo windows"},
+        "e2e": {"value": bf["e2e_value"], "unit": "windows/s", "ms_per_step": bf["e2e_ms_per_step"],
                 "h2d_bytes_per_step": n_win * T * C * 4, "d2h_bytes_per_step": B * NC * 4,
-                "api": "neural_speech_decoding_b200.tester.run_trials_batched(pinned host [R,B,T,C]) -> numpy [B,K]"},
-        "gpu_launches": launches_timed,
-        "clocks": clocks,
+                "api": "neural_speech_decoding_b200.tester.run_trials_batched(pinned host fp32 [R,B,T,C]) -> numpy [B,K]"},
+        "gpu_launches": bf["launches"],
+        "clocks": bf["clocks"],
         "roofline": {
-            "kernel": "lstm_fwd_h48_kernel<KIN=48> (layer-1 recurrence, exact fp32 FFMA)",
-            "bound": "tensor", "achieved": l1_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-            "frac": l1_tflops / peaks["bf16_tflops_sustained"], "peak_source": peaks["source"] + " bf16 sustained",
-            "traffic": None,
-            "note": "exact-fp32 path runs on CUDA cores, so the binding roof is FFMA issue, not the tensor pipe: "
-                    "see cuda_core_fp32",
-            "cuda_core_fp32": {"achieved": l1_tflops, "peak": ffma_peak, "unit": "TFLOP/s",
-                               "frac": l1_tflops / ffma_peak, "peak_source": "na_ffma_probe measured in this run"},
-            "ms_per_launch": ms_l1,
-            "per_timestep_latency_us": ms_l1 * 1e3 / T,
-            "whole_decoder_fwd": {"achieved": FWD_FLOPS_PER_WINDOW * value / world / 1e12, "unit": "TFLOP/s",
-                                  "frac_of_bf16_sustained": FWD_FLOPS_PER_WINDOW * value / world / 1e12 / peaks["bf16_tflops_sustained"],
-                                  "frac_of_ffma": FWD_FLOPS_PER_WINDOW * value / world / 1e12 / ffma_peak},
+            "kernel": "decoder_infer_bf16_kernel (tcgen05/TMEM/TMA: K2+K3+K4 fused, whole decoder forward)",
+            "bound": "tensor", "achieved": tc_tflops, "peak": peak, "unit": "TFLOP/s", "frac": tc_tflops / peak,
+            "peak_source": peaks["source"] + " cuBLAS bf16 (burst: kernel timed alone)", "traffic": None,
+            "algorithmic_flops_per_launch": FWD_FLOPS_PER_WINDOW * n_win,
+            "ms_per_launch": ms_tc,
+            "per_timestep_latency_us": ms_tc * 1e3 / (T * tile_rounds),
+            "note": "latency/MUFU-bound, not tensor-bound: 1250 dependent cell updates per window; each step needs "
+                    "5 MUFU (tanh) per hidden unit -> 3840 MUFU cycles per 128-window step for both layers",
+            "k1_window_pack": {"kernel": "window_zscore_vec_kernel (fp32 -> time-major bf16)", "bound": "hbm",
+                               "achieved": n_win * T * C * 6 / (ms_pack16 * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                               "unit": "GB/s", "frac": n_win * T * C * 6 / (ms_pack16 * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+            "k1_zscore_f32": {"kernel": "window_zscore_vec_kernel (z-score, fp32 in/out)", "bound": "hbm",
+                              "achieved": n_win * T * C * 8 / (ms_z * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                              "unit": "GB/s", "frac": n_win * T * C * 8 / (ms_z * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+        },
+        "fp32_exact": {
+            "value": fp["value"], "unit": "windows/s", "ms_per_step": fp["ms_per_step"],
+            "e2e": {"value": fp["e2e_value"], "unit": "windows/s", "ms_per_step": fp["e2e_ms_per_step"]},
+            "gpu_launches": fp["launches"], "clocks": fp["clocks"],
+            "parity": "tests/test_gpu_parity.py: logits and gradients within 1e-5, argmax identical",
+            "roofline": {"kernel": "lstm_fwd_h48_kernel<KIN=48> (layer-1 recurrence, exact fp32 FFMA)",
+                         "bound": "cuda-core fp32 (FFMA issue)", "achieved": l1_tflops, "peak": ffma_peak,
+                         "unit": "TFLOP/s", "frac": l1_tflops / ffma_peak,
+                         "peak_source": "na_ffma_probe measured in this run", "ms_per_launch": ms_l1,
+                         "per_timestep_latency_us": ms_l1 * 1e3 / T},
         },
     }
     if cpu:
@@ -343,7 +367,7 @@ def train_leg(args, world, rank, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-train", action="store_true")
