@@ -193,7 +193,7 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                           const float* __restrict__ fc0_w, const float* __restrict__ fc0_b,
                           const float* __restrict__ fc3_w, const float* __restrict__ fc3_b,
                           float* __restrict__ logits, float* __restrict__ probs,
-                          int T, int64_t B, int64_t Bp, int NC, int ntiles) {
+                          int T, int64_t B, int64_t Bp, int NC, int nquarters) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -240,9 +240,17 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
     const uint32_t tmem = S.tmem_base;
     const uint32_t tmem_d0 = tmem, tmem_d1 = tmem + kN;
 
+    // Work split: the batch is cut into 32-window quarters (one epilogue warp each); CTA i owns the
+    // contiguous range [i*Q/G, (i+1)*Q/G) and walks it in tiles of up to 4 quarters.  A short last tile
+    // keeps its idle epilogue warps out of the MUFU pipe, so the tail costs ~its share instead of a
+    // whole extra 128-window round.
+    const int q_begin = (int)(((int64_t)blockIdx.x * nquarters) / gridDim.x);
+    const int q_end = (int)(((int64_t)(blockIdx.x + 1) * nquarters) / gridDim.x);
     int n0 = 0;                                            // running step index across tiles
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, n0 += T) {
-        const int64_t b0 = (int64_t)tile * kRows;
+    for (int q0 = q_begin; q0 < q_end; q0 += 4, n0 += T) {
+        const int nq = min(4, q_end - q0);                 // active quarters of this tile
+        const uint32_t x_bytes = (uint32_t)nq * 32u * 16u;
+        const int64_t b0 = (int64_t)q0 * 32;
         // ---- zero h0_{-1}, h1_{-1} of this tile ----------------------------------------------------
         {
             uint4* z0 = reinterpret_cast<uint4*>(S.h0[(n0 + 1) & 1]);      // buffer of step n0-1
@@ -258,8 +266,8 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                 for (int t = 0; t < T; ++t) {
                     const int n = n0 + t, s = n % kXStages, u = n / kXStages;
                     mbar_wait(&S.x_empty[s], (u & 1) ^ 1);
-                    mbar_arrive_expect_tx(&S.x_full[s], kAChunk);
-                    bulk_load(S.x[s], x + ((int64_t)t * Bp + b0) * 8, kAChunk, &S.x_full[s]);
+                    mbar_arrive_expect_tx(&S.x_full[s], x_bytes);
+                    bulk_load(S.x[s], x + ((int64_t)t * Bp + b0) * 8, x_bytes, &S.x_full[s]);
                 }
             }
         } else if (warp == 8) {
@@ -309,6 +317,13 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
             float c[kH];
 #pragma unroll
             for (int j = 0; j < kH; ++j) c[j] = 0.f;
+            if (warp >= nq) {                              // idle quarter: keep the barrier protocol only
+                for (int t = 0; t < T; ++t) {
+                    const int n = n0 + t;
+                    mbar_wait(&S.d0_full, n & 1);
+                    mbar_arrive(&S.h0_ready[n & 1]);
+                }
+            } else
             for (int t = 0; t < T; ++t) {
                 const int n = n0 + t;
                 mbar_wait(&S.d0_full, n & 1);
@@ -336,6 +351,13 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
             for (int j = 0; j < kH; ++j) { c[j] = 0.f; z[j] = 0.f; }
             float mx = -INFINITY, l = 0.f;
             const float ba = S.head.ba;
+            if (q >= nq) {                                 // idle quarter
+                for (int t = 0; t < T; ++t) {
+                    const int m = n0 + t;
+                    mbar_wait(&S.d1_full, m & 1);
+                    mbar_arrive(&S.h1_ready);
+                }
+            } else {
             for (int t = 0; t < T; ++t) {
                 const int m = n0 + t;
                 mbar_wait(&S.d1_full, m & 1);
@@ -414,6 +436,7 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                         if (probs) probs[b * NC + k] = pe[k] / den;
                     }
             }
+            }
         }
         __syncthreads();       // tile done: every MMA has completed (layer-1 epilogue saw the last d1_full)
     }
@@ -469,11 +492,12 @@ extern "C" int na_decoder_infer_bf16(const void* x_bf16_tmp, const void* packed,
     const size_t smem = sizeof(tc::Smem) + 1024;
     cudaError_t e = cudaFuncSetAttribute(tc::decoder_infer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
-    const int ntiles = (int)(Bp / tc::kRows);
+    const int nquarters = (int)((B + 31) / 32);            // padding quarters beyond B are never scheduled
+    const int ntiles = (nquarters + 3) / 4;
     const int grid = ntiles < sms ? ntiles : sms;
     tc::decoder_infer_bf16_kernel<<<grid, tc::kThreads, smem, as_stream(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(x_bf16_tmp), reinterpret_cast<const unsigned char*>(packed), attn_w, attn_b,
-        ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, (int)T, B, Bp, (int)NC, ntiles);
+        ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, (int)T, B, Bp, (int)NC, nquarters);
     count_launch();
     return check_launch("na_decoder_infer_bf16");
 }
