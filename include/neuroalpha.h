@@ -46,7 +46,7 @@ enum {
     NA_EDEVICE = -4        /* not an sm_100 device */
 };
 
-enum { NA_F32 = 0, NA_BF16 = 1 };
+enum { NA_F32 = 0, NA_BF16 = 1, NA_F16 = 2 };
 
 typedef void* na_stream_t;      /* cudaStream_t */
 
@@ -174,6 +174,32 @@ int na_decoder_infer_bf16(const void* x_bf16_tmp, const void* packed,
                           const float* fc0_w, const float* fc0_b, const float* fc3_w, const float* fc3_b,
                           float* logits, float* probs,
                           int64_t T, int64_t B, int64_t Bp, int64_t NC, na_stream_t stream);
+
+/* ---- tensor-core tier, training (bf16 operands; fp32 accumulate, cell state, gradients) ------------
+ * Layouts: TMP fp32 [T][Bp][48]; TCL bf16 [T][Bp/128][F/8][128][8] (tile-chunk layout: a tile's
+ * step-t slab is contiguous and already in the UMMA core-matrix layout); mask u8 [T][Bp][48].
+ * Bp must be a multiple of 128.  Flagship shape only (C=8, H=48, L=2).
+ *
+ * na_lstm2_fwd_train_bf16: x (bf16 TMP, na_window_zscore) -> h0 (TCL), h0d = h0*mask*scale (TCL; NULL
+ *   together with mask when there is no dropout), c0 (TMP), h1 (TCL), h1f (TMP fp32, input of the head
+ *   kernels), c1 (TMP).  Replaces `self.lstm(x)` (lstm_eeg_model.py:34) in train mode.
+ * na_lstm_bwd_bf16: fused BPTT + weight gradients of one layer (layer = 0 | 1).  act_in = the layer's
+ *   input (x for layer 0, h0d/h0 for layer 1; TCL), h = its raw output (TCL), cstate / dh_out (TMP).
+ *   Gates are recomputed on the tensor cores; d(gates) never leave shared memory; dW_ih / dW_hh / db
+ *   accumulate in TMEM in fp32 and are reduced over CTAs in a fixed order.  Layer 1 also writes
+ *   din = d(act_in) * in_mask * drop_scale (TMP) = dh_out of layer 0.
+ *   packed_fwd = na_decoder_pack_bf16 output; zeros = >= 12,288 B of zeros; scratch =
+ *   36,864 + 4 * na_train_bf16_partial_floats() bytes.
+ */
+int64_t na_train_bf16_partial_floats(void);
+int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packed, const unsigned char* mask,
+                            float drop_scale, void* h0, void* h0d, float* c0, void* h1, float* h1f,
+                            float* c1, int64_t T, int64_t Bp, na_stream_t stream);
+int na_lstm_bwd_bf16(int64_t layer, const void* act_in, const void* h, const float* cstate,
+                     const float* dh_out, const void* packed_fwd, const float* w_ih, const float* w_hh,
+                     const void* zeros, const unsigned char* in_mask, float drop_scale, float* din,
+                     float* dw_ih, float* dw_hh, float* db, void* scratch,
+                     int64_t T, int64_t Bp, na_stream_t stream);
 
 /* ---- K5: trial averaging -----------------------------------------------------------------
  * Replaces tester.py:54,89,97 (and :90,98 for the chunk): fp32 zeros, += in trial order

@@ -25,23 +25,16 @@
 //     pipe overlap; all hand-offs are mbarriers (tcgen05.commit for MMA completion).
 //   * Activations: tanh.approx.f32 (sigmoid = 0.5 tanh(x/2) + 0.5).  bf16 contract: logits within
 //     2e-2 of the fp32 reference, argmax identical on the repo's windows.
-#include "na_common.cuh"
-#include "na_sm100.cuh"
+#include "na_tc_common.cuh"
 
 namespace na {
 namespace tc {
 
-constexpr int kRows = 128;
-constexpr int kH = 48;
-constexpr int kN = 4 * kH;                   // 192
-constexpr int kAChunk = kRows * 16;          // bytes of one A K-chunk (8 bf16 per row)
-constexpr int kBChunk = kN * 16;             // bytes of one B K-chunk
 constexpr int kXStages = 4;
 constexpr int kK0Chunks = 8;                 // layer 0: x | ones | h0 x6
 constexpr int kK1Chunks = 14;                // layer 1: h0 x6 | h1 x6 | ones | zero
 constexpr int kThreads = 320;
 constexpr int kFc = NA_FC_HIDDEN;
-constexpr uint32_t kTmemCols = 512;
 
 struct HeadSmem {
     float wa[kH], lnw[kH], lnb[kH];
@@ -65,90 +58,6 @@ struct Smem {
     uint32_t tmem_base;
 };
 
-// ---- tcgen05 wrappers ------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    // K-major, no swizzle: LBO = byte stride between the two 8-element K-chunks of one K16 step,
-    // SBO = byte stride between 8-row groups.  Bits: addr>>4 [0,14), LBO>>4 [16,30),
-    // SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64).
-    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-
-constexpr uint32_t kIdesc = (1u << 4)                      // D format f32
-                            | (1u << 7) | (1u << 10)       // A, B = bf16
-                            | ((uint32_t)(kN >> 3) << 17)  // N = 192
-                            | ((uint32_t)(kRows >> 4) << 24);   // M = 128   (A, B K-major: bits 15,16 = 0)
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ float tanh_apx(float v) {
-    float r;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-__device__ __forceinline__ float sigmoid_apx(float v) { return fmaf(0.5f, tanh_apx(0.5f * v), 0.5f); }
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&p);
-}
-__device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
-
-__device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d)
-                 : "memory");
-}
-
-// One LSTM cell update for the 8 units of a block; v = [i x8 | f x8 | g x8 | o x8] pre-activations.
-// Returns h packed as 4 x bf16x2.
-__device__ __forceinline__ void cell_block(const uint32_t (&v)[32], float* c, uint32_t (&hp)[4]) {
-    float h[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const float gi = sigmoid_apx(__uint_as_float(v[u]));
-        const float gf = sigmoid_apx(__uint_as_float(v[8 + u]));
-        const float gg = tanh_apx(__uint_as_float(v[16 + u]));
-        const float go = sigmoid_apx(__uint_as_float(v[24 + u]));
-        c[u] = fmaf(gf, c[u], gi * gg);
-        h[u] = go * tanh_apx(c[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) hp[u] = pack_bf16(h[2 * u], h[2 * u + 1]);
-}
-
 // ---- weight packing ----------------------------------------------------------------------------
 // B0 [8 chunks][192][8] and B1 [14 chunks][192][8] bf16, row n = (j/8)*32 + gate*8 + j%8.
 __global__ void pack_decoder_bf16_kernel(const float* __restrict__ w_ih0, const float* __restrict__ w_hh0,
@@ -167,20 +76,20 @@ __global__ void pack_decoder_bf16_kernel(const float* __restrict__ w_ih0, const 
         float v = 0.f;
         if (!l1) {
             const float b = b_ih0[col] + b_hh0[col];
-            const float bh = __bfloat162float(__float2bfloat16_rn(b));
+            const float bh = val16_to_float(val16(b));
             if (k < 8) v = w_ih0[col * 8 + k];
             else if (k == 8) v = bh;
             else if (k == 9) v = b - bh;
             else if (k >= 16) v = w_hh0[col * kH + (k - 16)];
         } else {
             const float b = b_ih1[col] + b_hh1[col];
-            const float bh = __bfloat162float(__float2bfloat16_rn(b));
+            const float bh = val16_to_float(val16(b));
             if (k < 48) v = w_ih1[col * kH + k];
             else if (k < 96) v = w_hh1[col * kH + (k - 48)];
             else if (k == 96) v = bh;
             else if (k == 97) v = b - bh;
         }
-        out[idx] = __float2bfloat16_rn(v);
+        reinterpret_cast<uint16_t*>(out)[idx] = val16(v);
     }
 }
 
@@ -204,7 +113,7 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
         uint4* dst = reinterpret_cast<uint4*>(S.b0);     // b0 and b1 are contiguous in Smem
         constexpr int n16 = (kK0Chunks + kK1Chunks) * kBChunk / 16;
         for (int i = tid; i < n16; i += kThreads) dst[i] = src[i];
-        const uint4 ones = make_uint4(0x3F803F80u, 0u, 0u, 0u);     // bf16 {1,1,0,0,0,0,0,0}
+        const uint4 ones = make_uint4(kValOnes2, 0u, 0u, 0u);     // bf16 {1,1,0,0,0,0,0,0}
         const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
         for (int i = tid; i < kRows; i += kThreads) {
 #pragma unroll
@@ -374,8 +283,8 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         hb[blk * 4 + u] = hp[u];
-                        score = fmaf(bf16_lo(hp[u]), S.head.wa[blk * 8 + 2 * u], score);
-                        score = fmaf(bf16_hi(hp[u]), S.head.wa[blk * 8 + 2 * u + 1], score);
+                        score = fmaf(val_lo(hp[u]), S.head.wa[blk * 8 + 2 * u], score);
+                        score = fmaf(val_hi(hp[u]), S.head.wa[blk * 8 + 2 * u + 1], score);
                     }
                 }
                 tc_fence_before();
@@ -393,8 +302,8 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                 l += e;
 #pragma unroll
                 for (int u = 0; u < 24; ++u) {
-                    z[2 * u] = fmaf(e, bf16_lo(hb[u]), z[2 * u]);
-                    z[2 * u + 1] = fmaf(e, bf16_hi(hb[u]), z[2 * u + 1]);
+                    z[2 * u] = fmaf(e, val_lo(hb[u]), z[2 * u]);
+                    z[2 * u + 1] = fmaf(e, val_hi(hb[u]), z[2 * u + 1]);
                 }
             }
             // ---- head for this thread's window: LN -> fc0 -> RReLU(eval) -> fc3 -> softmax ----------

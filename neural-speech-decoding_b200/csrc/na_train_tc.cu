@@ -1,0 +1,641 @@
+// Tensor-core tier, TRAINING: 2-layer LSTM forward that saves what the backward needs, and a
+// fused BPTT + weight-gradient kernel per layer, both on tcgen05 / TMEM / TMA (bf16 operands, fp32
+// accumulate / cell state / gradients of the cell state).
+//
+// Layouts
+//   TMP  fp32 [T][Bp][48]                      (c, fp32 copy of h1 for the head kernels, dh, din)
+//   TCL  bf16 [T][Bp/128][F/8][128][8]         "tile-chunk": the [128 x F] slab of a tile at step t is
+//        contiguous AND already in the UMMA core-matrix layout, so it is one TMA bulk copy into
+//        an operand buffer (x: F = 8, identical to TMP bf16; h0, h0-after-dropout, h1: F = 48)
+//   mask u8  [T][Bp][48]                        inter-layer dropout keep-mask (lstm_eeg_model.py:21)
+//
+// Backward of one layer, per step t (descending) and 128-window tile:
+//   G: gates = [in_t | 1 | h_{t-1}] . B            (recompute; same MMA as the forward)       D_G
+//   E: thread = window: activations, d(gates) from dh_t = dh_out_t + dh_rec, c_t, c_{t-1};
+//      d(gates) -> shared memory (bf16) in the A-operand layout                                 DG
+//   R: [din | dh_rec] = DG . [W_ih | W_hh]          (K = 192)                                   D_R
+//   W: dW += DG^T . [in_t | 1 | h_{t-1}]            (K = 128 windows; DG and the operand buffer are
+//      re-used as MN-major operands -- no transposes, no dgates round trip through HBM)          D_W
+//   dW (+ db via the ones column) accumulates in TMEM in fp32 over ALL steps and tiles of the CTA;
+//   per-CTA partials are reduced in a fixed order by a second tiny kernel (deterministic).
+#include "na_tc_common.cuh"
+
+namespace na {
+namespace tc {
+
+constexpr int kTrainThreads = 320;     // forward: 4 + 4 epilogue warps, MMA warp, TMA warp
+constexpr int kBwdThreads = 192;       // backward: 4 epilogue warps, MMA warp, TMA warp
+constexpr int kXStagesT = 4;
+
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+
+// cell update of 8 units; returns fp32 h and leaves c updated.
+__device__ __forceinline__ void cell_block_f(const uint32_t (&v)[32], float* c, float (&h)[8]) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float gi = sigmoid_apx(__uint_as_float(v[u]));
+        const float gf = sigmoid_apx(__uint_as_float(v[8 + u]));
+        const float gg = tanh_apx(__uint_as_float(v[16 + u]));
+        const float go = sigmoid_apx(__uint_as_float(v[24 + u]));
+        c[u] = fmaf(gf, c[u], gi * gg);
+        h[u] = go * tanh_apx(c[u]);
+    }
+}
+
+__device__ __forceinline__ void st_global_v4f(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+
+// =================================================================================================
+// forward (training): x -> h0, h0 after dropout, c0, h1 (bf16 + fp32), c1
+// =================================================================================================
+struct FwdSmem {
+    alignas(128) unsigned char b0[8 * kBChunk];
+    alignas(128) unsigned char b1[14 * kBChunk];
+    alignas(128) unsigned char x[kXStagesT][2 * kAChunk];     // [x | ones]
+    alignas(128) unsigned char h0[2][6 * kAChunk];            // raw h0_t        (layer-0 recurrence)
+    alignas(128) unsigned char h0d[2][6 * kAChunk];           // dropped h0_t    (layer-1 input)
+    alignas(128) unsigned char h1[6 * kAChunk];
+    alignas(128) unsigned char onez[2 * kAChunk];
+    alignas(8) uint64_t x_full[kXStagesT], x_empty[kXStagesT];
+    uint64_t d0_full, d1_full, h0_ready[2], h0_free[2], h1_ready;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kTrainThreads, 1)
+lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned char* __restrict__ packed,
+                            const unsigned char* __restrict__ mask, float drop_scale,
+                            __nv_bfloat16* __restrict__ h0_out, __nv_bfloat16* __restrict__ h0d_out,
+                            float* __restrict__ c0_out, __nv_bfloat16* __restrict__ h1_out,
+                            float* __restrict__ h1f_out, float* __restrict__ c1_out,
+                            int T, int64_t Bp, int ntiles) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    FwdSmem& S = *reinterpret_cast<FwdSmem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(packed);
+        uint4* dst = reinterpret_cast<uint4*>(S.b0);
+        for (int i = tid; i < 22 * kBChunk / 16; i += kTrainThreads) dst[i] = src[i];
+        const uint4 ones = make_uint4(kValOnes2, 0u, 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < kRows; i += kTrainThreads) {
+#pragma unroll
+            for (int s = 0; s < kXStagesT; ++s) reinterpret_cast<uint4*>(S.x[s] + kAChunk)[i] = ones;
+            reinterpret_cast<uint4*>(S.onez)[i] = ones;
+            reinterpret_cast<uint4*>(S.onez + kAChunk)[i] = zero;
+        }
+        if (tid == 0) {
+            for (int s = 0; s < kXStagesT; ++s) { mbar_init(&S.x_full[s], 1); mbar_init(&S.x_empty[s], 1); }
+            mbar_init(&S.d0_full, 1); mbar_init(&S.d1_full, 1);
+            mbar_init(&S.h0_ready[0], 128); mbar_init(&S.h0_ready[1], 128);
+            mbar_init(&S.h0_free[0], 1); mbar_init(&S.h0_free[1], 1);
+            mbar_init(&S.h1_ready, 128);
+            fence_mbar_init();
+        }
+        if (warp == 9) tmem_alloc_all(&S.tmem_base);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncthreads();
+        tc_fence_after();
+    }
+    const uint32_t tmem = S.tmem_base, tmem_d0 = tmem, tmem_d1 = tmem + kN;
+    const bool drop = mask != nullptr;
+
+    int n0 = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, n0 += T) {
+        const int64_t b0 = (int64_t)tile * kRows;
+        {
+            uint4* z0 = reinterpret_cast<uint4*>(S.h0[(n0 + 1) & 1]);
+            uint4* z1 = reinterpret_cast<uint4*>(S.h1);
+            for (int i = tid; i < 6 * kAChunk / 16; i += kTrainThreads) { z0[i] = make_uint4(0, 0, 0, 0); z1[i] = make_uint4(0, 0, 0, 0); }
+            fence_proxy_async_smem();
+            __syncthreads();
+        }
+        if (warp == 9) {
+            if (lane == 0)
+                for (int t = 0; t < T; ++t) {
+                    const int n = n0 + t, s = n % kXStagesT, u = n / kXStagesT;
+                    mbar_wait(&S.x_empty[s], (u & 1) ^ 1);
+                    mbar_arrive_expect_tx(&S.x_full[s], kAChunk);
+                    bulk_load(S.x[s], x + ((int64_t)t * Bp + b0) * 8, kAChunk, &S.x_full[s]);
+                }
+        } else if (warp == 8) {
+            if (lane == 0) {
+                const uint32_t b0a = smem_u32(S.b0), b1a = smem_u32(S.b1);
+                for (int t = 0; t <= T; ++t) {
+                    if (t < T) {
+                        const int n = n0 + t, s = n % kXStagesT, u = n / kXStagesT;
+                        mbar_wait(&S.x_full[s], u & 1);
+                        mbar_wait(&S.h0_ready[(n + 1) & 1], ((n - 1) >> 1) & 1);
+                        tc_fence_after();
+                        const uint32_t hprev = smem_u32(S.h0[(n + 1) & 1]);
+                        umma_bf16(tmem_d0, umma_desc(smem_u32(S.x[s]), kAChunk, 128), umma_desc(b0a, kBChunk, 128), 0u);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+                            umma_bf16(tmem_d0, umma_desc(hprev + 2 * i * kAChunk, kAChunk, 128),
+                                      umma_desc(b0a + (2 + 2 * i) * kBChunk, kBChunk, 128), 1u);
+                        umma_commit(&S.x_empty[s]);
+                        umma_commit(&S.d0_full);
+                    }
+                    if (t >= 1) {
+                        const int m = n0 + t - 1;
+                        mbar_wait(&S.h0_ready[m & 1], (m >> 1) & 1);
+                        mbar_wait(&S.h1_ready, (m - 1) & 1);
+                        tc_fence_after();
+                        const uint32_t hin = smem_u32(drop ? S.h0d[m & 1] : S.h0[m & 1]), hrec = smem_u32(S.h1);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+                            umma_bf16(tmem_d1, umma_desc(hin + 2 * i * kAChunk, kAChunk, 128),
+                                      umma_desc(b1a + (2 * i) * kBChunk, kBChunk, 128), i == 0 ? 0u : 1u);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+                            umma_bf16(tmem_d1, umma_desc(hrec + 2 * i * kAChunk, kAChunk, 128),
+                                      umma_desc(b1a + (6 + 2 * i) * kBChunk, kBChunk, 128), 1u);
+                        umma_bf16(tmem_d1, umma_desc(smem_u32(S.onez), kAChunk, 128),
+                                  umma_desc(b1a + 12 * kBChunk, kBChunk, 128), 1u);
+                        umma_commit(&S.d1_full);
+                        umma_commit(&S.h0_free[m & 1]);
+                    }
+                }
+            }
+        } else if (warp < 4) {
+            // ---- layer-0 epilogue --------------------------------------------------------------------
+            const int row = warp * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+            float c[kH];
+#pragma unroll
+            for (int j = 0; j < kH; ++j) c[j] = 0.f;
+            for (int t = 0; t < T; ++t) {
+                const int n = n0 + t;
+                const int64_t grow = (int64_t)t * Bp + b0 + row;                 // TMP row
+                const int64_t tcl = ((int64_t)t * ntiles + tile) * 6 * (kAChunk / 2) + row * 8;   // TCL element offset of chunk 0
+                uint2 mk[6];
+                if (drop) {
+#pragma unroll
+                    for (int blk = 0; blk < 6; ++blk) mk[blk] = *reinterpret_cast<const uint2*>(mask + grow * kH + blk * 8);
+                }
+                mbar_wait(&S.d0_full, n & 1);
+                mbar_wait(&S.h0_free[n & 1], ((n >> 1) & 1) ^ 1);
+                tc_fence_after();
+                unsigned char* dst = S.h0[n & 1] + row * 16;
+                unsigned char* dstd = S.h0d[n & 1] + row * 16;
+#pragma unroll
+                for (int blk = 0; blk < 6; ++blk) {
+                    uint32_t v[32];
+                    float h[8];
+                    tmem_ld32(tmem_d0 + lane_base + blk * 32, v);
+                    cell_block_f(v, c + blk * 8, h);
+                    const uint32_t p0 = pack_val(h[0], h[1]), p1 = pack_val(h[2], h[3]);
+                    const uint32_t p2 = pack_val(h[4], h[5]), p3 = pack_val(h[6], h[7]);
+                    st_shared_v4(dst + blk * kAChunk, p0, p1, p2, p3);
+                    *reinterpret_cast<uint4*>(h0_out + tcl + blk * (kAChunk / 2)) = make_uint4(p0, p1, p2, p3);
+                    st_global_v4f(c0_out + grow * kH + blk * 8, c[blk * 8], c[blk * 8 + 1], c[blk * 8 + 2], c[blk * 8 + 3]);
+                    st_global_v4f(c0_out + grow * kH + blk * 8 + 4, c[blk * 8 + 4], c[blk * 8 + 5], c[blk * 8 + 6], c[blk * 8 + 7]);
+                    if (drop) {
+                        const uint32_t mlo = mk[blk].x, mhi = mk[blk].y;
+                        float hd[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const uint32_t byte = ((u < 4 ? mlo : mhi) >> (8 * (u & 3))) & 0xFFu;
+                            hd[u] = byte ? h[u] * drop_scale : 0.f;
+                        }
+                        const uint32_t q0 = pack_val(hd[0], hd[1]), q1 = pack_val(hd[2], hd[3]);
+                        const uint32_t q2 = pack_val(hd[4], hd[5]), q3 = pack_val(hd[6], hd[7]);
+                        st_shared_v4(dstd + blk * kAChunk, q0, q1, q2, q3);
+                        *reinterpret_cast<uint4*>(h0d_out + tcl + blk * (kAChunk / 2)) = make_uint4(q0, q1, q2, q3);
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(&S.h0_ready[n & 1]);
+            }
+        } else {
+            // ---- layer-1 epilogue --------------------------------------------------------------------
+            const int q = warp - 4;
+            const int row = q * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+            float c[kH];
+#pragma unroll
+            for (int j = 0; j < kH; ++j) c[j] = 0.f;
+            for (int t = 0; t < T; ++t) {
+                const int m = n0 + t;
+                const int64_t grow = (int64_t)t * Bp + b0 + row;
+                const int64_t tcl = ((int64_t)t * ntiles + tile) * 6 * (kAChunk / 2) + row * 8;
+                mbar_wait(&S.d1_full, m & 1);
+                tc_fence_after();
+                unsigned char* dst = S.h1 + row * 16;
+#pragma unroll
+                for (int blk = 0; blk < 6; ++blk) {
+                    uint32_t v[32];
+                    float h[8];
+                    tmem_ld32(tmem_d1 + lane_base + blk * 32, v);
+                    cell_block_f(v, c + blk * 8, h);
+                    const uint32_t p0 = pack_val(h[0], h[1]), p1 = pack_val(h[2], h[3]);
+                    const uint32_t p2 = pack_val(h[4], h[5]), p3 = pack_val(h[6], h[7]);
+                    st_shared_v4(dst + blk * kAChunk, p0, p1, p2, p3);
+                    *reinterpret_cast<uint4*>(h1_out + tcl + blk * (kAChunk / 2)) = make_uint4(p0, p1, p2, p3);
+                    st_global_v4f(h1f_out + grow * kH + blk * 8, h[0], h[1], h[2], h[3]);
+                    st_global_v4f(h1f_out + grow * kH + blk * 8 + 4, h[4], h[5], h[6], h[7]);
+                    st_global_v4f(c1_out + grow * kH + blk * 8, c[blk * 8], c[blk * 8 + 1], c[blk * 8 + 2], c[blk * 8 + 3]);
+                    st_global_v4f(c1_out + grow * kH + blk * 8 + 4, c[blk * 8 + 4], c[blk * 8 + 5], c[blk * 8 + 6], c[blk * 8 + 7]);
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(&S.h1_ready);
+            }
+        }
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) { tc_fence_after(); tmem_free_all(tmem); }
+}
+
+// =================================================================================================
+// backward of one layer (KI = 8: layer 0, no din;  KI = 48: layer 1, din with the dropout mask)
+// =================================================================================================
+template <int KI>
+struct BwdCfg {
+    static constexpr int kInChunks = KI / 8;
+    static constexpr int kStageChunks = KI == 8 ? 8 : 14;       // L0: x|ones|h x6   L1: in x6|h x6|ones|zero
+    static constexpr int kHprevChunk = KI == 8 ? 2 : 6;         // first h_{t-1} chunk inside the stage
+    static constexpr int kOnesChunk = KI == 8 ? 1 : 12;
+    static constexpr int kNW = kStageChunks * 8;                // 64 / 112 features of the stage = dW columns
+    static constexpr int kNR = KI == 8 ? 48 : 96;               // columns of D_R: [din (KI) |] dh_rec (48)
+    static constexpr int kRecCol = KI == 8 ? 0 : 48;            // first dh_rec column of D_R
+    static constexpr int kColG = 0, kColR = 192, kColW1 = KI == 8 ? 256 : 288, kColW2 = kColW1 + kNW;
+    static_assert(kColW2 + kNW <= 512, "TMEM budget");
+};
+
+template <int KI>
+struct BwdSmem {
+    using C = BwdCfg<KI>;
+    alignas(128) unsigned char bg[C::kStageChunks * kBChunk];          // forward B operand (recompute)
+    alignas(128) unsigned char br[24 * C::kNR * 16];                   // [W_ih | W_hh]^T, K = 192 gate columns
+    alignas(128) unsigned char act[2][C::kStageChunks * kAChunk];      // [in_t | 1 | h_{t-1}] stages
+    alignas(128) unsigned char dg[24 * kAChunk];                       // d(gates) bf16, A operand of R and W
+    alignas(8) uint64_t act_full[2], act_free[2];
+    uint64_t g_full, dg_ready;
+    uint32_t tmem_base;
+};
+
+template <int KI>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT][KI/8][128][8]
+                     const __nv_bfloat16* __restrict__ h,          // TCL [T][NT][6][128][8]  (this layer's raw h)
+                     const float* __restrict__ cstate,             // TMP
+                     const float* __restrict__ dh_out,             // TMP
+                     const unsigned char* __restrict__ packed_g,   // forward B operand of this layer
+                     const unsigned char* __restrict__ packed_r,   // [24 chunks][kNR][8] bf16
+                     const __nv_bfloat16* __restrict__ zeros,      // >= 6*2048 B of zeros (h_{-1})
+                     const unsigned char* __restrict__ mask, float drop_scale,   // KI == 48: mask of this layer's input
+                     float* __restrict__ din,                      // TMP, KI == 48 only
+                     float* __restrict__ dw_partial,               // [grid][192][kNW]
+                     int T, int64_t Bp, int ntiles) {
+    using C = BwdCfg<KI>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    BwdSmem<KI>& S = *reinterpret_cast<BwdSmem<KI>*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {
+        const uint4* sg = reinterpret_cast<const uint4*>(packed_g);
+        uint4* dgp = reinterpret_cast<uint4*>(S.bg);
+        for (int i = tid; i < C::kStageChunks * kBChunk / 16; i += kBwdThreads) dgp[i] = sg[i];
+        const uint4* sr = reinterpret_cast<const uint4*>(packed_r);
+        uint4* drp = reinterpret_cast<uint4*>(S.br);
+        for (int i = tid; i < 24 * C::kNR; i += kBwdThreads) drp[i] = sr[i];
+        const uint4 ones = make_uint4(kValOnes2, 0u, 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < kRows; i += kBwdThreads)
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                reinterpret_cast<uint4*>(S.act[s] + C::kOnesChunk * kAChunk)[i] = ones;
+                if (KI == 48) reinterpret_cast<uint4*>(S.act[s] + 13 * kAChunk)[i] = zero;
+            }
+        if (tid == 0) {
+            for (int s = 0; s < 2; ++s) { mbar_init(&S.act_full[s], 1); mbar_init(&S.act_free[s], 1); }
+            mbar_init(&S.g_full, 1);
+            mbar_init(&S.dg_ready, 128);
+            fence_mbar_init();
+        }
+        if (warp == 5) tmem_alloc_all(&S.tmem_base);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncthreads();
+        tc_fence_after();
+    }
+    const uint32_t tmem = S.tmem_base;
+    const uint32_t tm_g = tmem + C::kColG, tm_r = tmem + C::kColR, tm_w1 = tmem + C::kColW1, tm_w2 = tmem + C::kColW2;
+    constexpr uint32_t kIdescR = make_idesc(C::kNR, kFmtGrad, kFmtVal);               // d(gates) x W^T, K-major x K-major
+    constexpr uint32_t kIdescW = make_idesc(C::kNW, kFmtGrad, kFmtVal, true, true);   // d(gates)^T x act^T, MN-major x MN-major
+    constexpr uint32_t kStageBytes = (C::kInChunks + 6) * kAChunk;
+
+    uint32_t k0 = 0;                              // running step counter (stage / phase bookkeeping)
+    uint32_t gphase = 0;                          // phases of g_full consumed / produced so far
+    bool first_w = true;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t b0 = (int64_t)tile * kRows;
+        if (warp == 5) {
+            // ================= TMA producer: [in_t | h_{t-1}] for t = T-1 .. 0 ==========================
+            if (lane == 0)
+                for (int i = 0; i < T; ++i) {
+                    const int t = T - 1 - i;
+                    const uint32_t k = k0 + i, s = k & 1, u = k >> 1;
+                    mbar_wait(&S.act_free[s], (u & 1) ^ 1);
+                    mbar_arrive_expect_tx(&S.act_full[s], kStageBytes);
+                    bulk_load(S.act[s], act_in + (((int64_t)t * ntiles + tile) * C::kInChunks) * (kAChunk / 2),
+                              C::kInChunks * kAChunk, &S.act_full[s]);
+                    const __nv_bfloat16* hsrc = t > 0 ? h + (((int64_t)(t - 1) * ntiles + tile) * 6) * (kAChunk / 2) : zeros;
+                    bulk_load(S.act[s] + C::kHprevChunk * kAChunk, hsrc, 6 * kAChunk, &S.act_full[s]);
+                }
+        } else if (warp == 4) {
+            // ================= MMA issuer ================================================================
+            if (lane == 0) {
+                const uint32_t bga = smem_u32(S.bg), bra = smem_u32(S.br), dga = smem_u32(S.dg);
+                uint32_t dgp = k0;                // dg_ready phases consumed
+                for (int i = 0; i <= T; ++i) {
+                    if (i >= 1) {
+                        // R and W of the previous step (its d(gates) are in shared memory)
+                        const uint32_t kp = k0 + i - 1, sp = kp & 1;
+                        mbar_wait(&S.dg_ready, dgp & 1);
+                        ++dgp;
+                        tc_fence_after();
+                        const uint32_t acta = smem_u32(S.act[sp]);
+#pragma unroll
+                        for (int ks = 0; ks < 12; ++ks)
+                            umma_bf16_i(tm_r, umma_desc(dga + 2 * ks * kAChunk, kAChunk, 128),
+                                        umma_desc(bra + 2 * ks * C::kNR * 16, C::kNR * 16, 128), kIdescR, ks == 0 ? 0u : 1u);
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+                            const uint32_t acc = (first_w && ks == 0) ? 0u : 1u;
+                            const uint64_t bdesc = umma_desc(acta + ks * 256, 128, kAChunk);
+                            umma_bf16_i(tm_w1, umma_desc(dga + ks * 256, 128, kAChunk), bdesc, kIdescW, acc);
+                            umma_bf16_i(tm_w2, umma_desc(dga + 8 * kAChunk + ks * 256, 128, kAChunk), bdesc, kIdescW, acc);
+                        }
+                        first_w = false;
+                        umma_commit(&S.act_free[sp]);
+                    }
+                    if (i < T) {
+                        const uint32_t k = k0 + i, s = k & 1, u = k >> 1;
+                        mbar_wait(&S.act_full[s], u & 1);
+                        tc_fence_after();
+                        const uint32_t acta = smem_u32(S.act[s]);
+#pragma unroll
+                        for (int ks = 0; ks < C::kStageChunks / 2; ++ks)
+                            umma_bf16(tm_g, umma_desc(acta + 2 * ks * kAChunk, kAChunk, 128),
+                                      umma_desc(bga + 2 * ks * kBChunk, kBChunk, 128), ks == 0 ? 0u : 1u);
+                    }
+                    umma_commit(&S.g_full);        // step i: G(t) done (and R, W of the step before); i == T: tail
+                }
+            }
+        } else if (warp < 4) {
+            // ================= epilogue: thread = window ==================================================
+            const int row = warp * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+            float dc[kH];
+#pragma unroll
+            for (int j = 0; j < kH; ++j) dc[j] = 0.f;
+            unsigned char* dgrow = S.dg + row * 16;
+            for (int i = 0; i <= T; ++i) {
+                const int t = T - 1 - i;                                  // step whose gates are in D_G (i < T)
+                mbar_wait(&S.g_full, gphase & 1);
+                ++gphase;
+                tc_fence_after();
+                if (KI == 48 && i >= 1) {
+                    // din of step t+1 = D_R[:, 0:48] * mask * scale  -> dh_out of the layer below
+                    const int64_t grow = (int64_t)(t + 1) * Bp + b0 + row;
+#pragma unroll
+                    for (int blk = 0; blk < 6; ++blk) {
+                        uint32_t r[8];
+                        tmem_ld8(tm_r + lane_base + blk * 8, r);
+                        float o[8];
+                        if (mask) {
+                            const uint2 mk = *reinterpret_cast<const uint2*>(mask + grow * kH + blk * 8);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const uint32_t byte = ((u < 4 ? mk.x : mk.y) >> (8 * (u & 3))) & 0xFFu;
+                                o[u] = byte ? __uint_as_float(r[u]) * drop_scale : 0.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) o[u] = __uint_as_float(r[u]);
+                        }
+                        st_global_v4f(din + grow * kH + blk * 8, o[0], o[1], o[2], o[3]);
+                        st_global_v4f(din + grow * kH + blk * 8 + 4, o[4], o[5], o[6], o[7]);
+                    }
+                }
+                if (i == T) break;                                        // tail: nothing left to differentiate
+                const int64_t grow = (int64_t)t * Bp + b0 + row;
+                const float* crow = cstate + grow * kH;
+                const float* cprow = cstate + (grow - Bp) * kH;           // c_{t-1} (t > 0)
+                const float* dhrow = dh_out + grow * kH;
+#pragma unroll
+                for (int blk = 0; blk < 6; ++blk) {
+                    float ct[8], cp[8], dh[8];
+                    {
+                        const float4 a = *reinterpret_cast<const float4*>(crow + blk * 8), b = *reinterpret_cast<const float4*>(crow + blk * 8 + 4);
+                        ct[0] = a.x; ct[1] = a.y; ct[2] = a.z; ct[3] = a.w; ct[4] = b.x; ct[5] = b.y; ct[6] = b.z; ct[7] = b.w;
+                        const float4 d = *reinterpret_cast<const float4*>(dhrow + blk * 8), e = *reinterpret_cast<const float4*>(dhrow + blk * 8 + 4);
+                        dh[0] = d.x; dh[1] = d.y; dh[2] = d.z; dh[3] = d.w; dh[4] = e.x; dh[5] = e.y; dh[6] = e.z; dh[7] = e.w;
+                        if (t > 0) {
+                            const float4 f = *reinterpret_cast<const float4*>(cprow + blk * 8), g = *reinterpret_cast<const float4*>(cprow + blk * 8 + 4);
+                            cp[0] = f.x; cp[1] = f.y; cp[2] = f.z; cp[3] = f.w; cp[4] = g.x; cp[5] = g.y; cp[6] = g.z; cp[7] = g.w;
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) cp[u] = 0.f;
+                        }
+                    }
+                    uint32_t v[32];
+                    tmem_ld32(tm_g + lane_base + blk * 32, v);
+                    if (i >= 1) {
+                        uint32_t r[8];
+                        tmem_ld8(tm_r + lane_base + C::kRecCol + blk * 8, r);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) dh[u] += __uint_as_float(r[u]);
+                    }
+                    float pi[8], pf[8], pg[8], po[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float gi = sigmoid_apx(__uint_as_float(v[u]));
+                        const float gf = sigmoid_apx(__uint_as_float(v[8 + u]));
+                        const float gg = tanh_apx(__uint_as_float(v[16 + u]));
+                        const float go = sigmoid_apx(__uint_as_float(v[24 + u]));
+                        const float tcv = tanh_apx(ct[u]);
+                        const float d_o = dh[u] * tcv;
+                        const float dct = fmaf(dh[u] * go, 1.0f - tcv * tcv, dc[blk * 8 + u]);
+                        dc[blk * 8 + u] = dct * gf;
+                        pi[u] = dct * gg * gi * (1.0f - gi);
+                        pf[u] = dct * cp[u] * gf * (1.0f - gf);
+                        pg[u] = dct * gi * (1.0f - gg * gg);
+                        po[u] = d_o * go * (1.0f - go);
+                    }
+                    unsigned char* d4 = dgrow + (blk * 4) * kAChunk;
+                    st_shared_v4(d4, pack_val(pi[0], pi[1]), pack_val(pi[2], pi[3]), pack_val(pi[4], pi[5]), pack_val(pi[6], pi[7]));
+                    st_shared_v4(d4 + kAChunk, pack_val(pf[0], pf[1]), pack_val(pf[2], pf[3]), pack_val(pf[4], pf[5]), pack_val(pf[6], pf[7]));
+                    st_shared_v4(d4 + 2 * kAChunk, pack_val(pg[0], pg[1]), pack_val(pg[2], pg[3]), pack_val(pg[4], pg[5]), pack_val(pg[6], pg[7]));
+                    st_shared_v4(d4 + 3 * kAChunk, pack_val(po[0], po[1]), pack_val(po[2], po[3]), pack_val(po[4], po[5]), pack_val(po[6], po[7]));
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(&S.dg_ready);
+            }
+        }
+        k0 += (uint32_t)T;       // every thread tracks the running step count; gphase / first_w are role-private
+        __syncthreads();
+    }
+
+    // ---- per-CTA weight-gradient partial: D_W1 rows = gate columns 0..127, D_W2 rows 64..127 = 128..191 ----
+    tc_fence_after();
+    if (warp < 4) {
+        const int row = warp * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        float* out1 = dw_partial + ((size_t)blockIdx.x * kN + row) * C::kNW;
+#pragma unroll 1
+        for (int cc = 0; cc < C::kNW; cc += 8) {
+            uint32_t r[8];
+            tmem_ld8(tm_w1 + lane_base + cc, r);
+            st_global_v4f(out1 + cc, __uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+            st_global_v4f(out1 + cc + 4, __uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+        }
+        if (warp >= 2) {
+            float* out2 = dw_partial + ((size_t)blockIdx.x * kN + 64 + row) * C::kNW;
+#pragma unroll 1
+            for (int cc = 0; cc < C::kNW; cc += 8) {
+                uint32_t r[8];
+                tmem_ld8(tm_w2 + lane_base + cc, r);
+                st_global_v4f(out2 + cc, __uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+                st_global_v4f(out2 + cc + 4, __uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) { tc_fence_after(); tmem_free_all(tmem); }
+}
+
+// [W_ih | W_hh]^T as the B operand of R: out[chunk = n/8][o][n%8], n = permuted gate column (K index),
+// o = output column (din columns first when KI == 48, then dh_rec).
+__global__ void pack_bwd_r_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, int KI,
+                                  __nv_bfloat16* __restrict__ out) {
+    const int NR = KI == 8 ? 48 : 96;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 24 * NR * 8; idx += gridDim.x * blockDim.x) {
+        const int n = (idx / (NR * 8)) * 8 + (idx % 8);
+        const int o = (idx / 8) % NR;
+        const int j = (n / 32) * 8 + (n % 8), q = (n % 32) / 8, col = q * kH + j;
+        float v;
+        if (KI == 8) v = w_hh[col * kH + o];
+        else v = o < 48 ? w_ih[col * kH + o] : w_hh[col * kH + (o - 48)];
+        reinterpret_cast<uint16_t*>(out)[idx] = val16(v);
+    }
+}
+
+// Sum the per-CTA partials in a fixed order and scatter to torch layouts.
+__global__ void reduce_dw_kernel(const float* __restrict__ partial, int nparts, int KI, float* __restrict__ dw_ih,
+                                 float* __restrict__ dw_hh, float* __restrict__ db) {
+    const int NW = KI == 8 ? 64 : 112;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kN * NW) return;
+    const int n = idx / NW, f = idx % NW;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * kN * NW + idx];
+    const int j = (n / 32) * 8 + (n % 8), q = (n % 32) / 8, col = q * kH + j;
+    if (KI == 8) {
+        if (f < 8) dw_ih[col * 8 + f] = s;
+        else if (f == 8) db[col] = s;
+        else if (f >= 16) dw_hh[col * kH + (f - 16)] = s;
+    } else {
+        if (f < 48) dw_ih[col * kH + f] = s;
+        else if (f < 96) dw_hh[col * kH + (f - 48)] = s;
+        else if (f == 96) db[col] = s;
+    }
+}
+
+static int tc_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+template <int KI>
+static int launch_bwd(const void* act_in, const void* h, const float* c, const float* dh_out, const void* packed_g,
+                      const void* packed_r, const void* zeros, const unsigned char* mask, float scale, float* din,
+                      float* partial, int64_t T, int64_t Bp, cudaStream_t st, int* grid_out) {
+    const size_t smem = sizeof(BwdSmem<KI>) + 1024;
+    auto kern = lstm_bwd_bf16_kernel<KI>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "lstm_bwd_bf16: shared memory opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e));
+    const int ntiles = (int)(Bp / kRows);
+    const int grid = ntiles < tc_sms() ? ntiles : tc_sms();
+    *grid_out = grid;
+    kern<<<grid, kBwdThreads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(act_in), reinterpret_cast<const __nv_bfloat16*>(h),
+                                          c, dh_out, reinterpret_cast<const unsigned char*>(packed_g),
+                                          reinterpret_cast<const unsigned char*>(packed_r),
+                                          reinterpret_cast<const __nv_bfloat16*>(zeros), mask, scale, din, partial, (int)T, Bp, ntiles);
+    count_launch();
+    return check_launch("na_lstm_bwd_bf16");
+}
+
+}  // namespace tc
+}  // namespace na
+
+// ---- C ABI ---------------------------------------------------------------------------------------
+extern "C" int64_t na_train_bf16_partial_floats(void) { return (int64_t)148 * 2 * na::tc::kN * 112; }
+
+extern "C" int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packed, const unsigned char* mask,
+                                       float drop_scale, void* h0, void* h0d, float* c0, void* h1, float* h1f,
+                                       float* c1, int64_t T, int64_t Bp, na_stream_t stream) {
+    using namespace na;
+    NA_REQUIRE(T >= 1 && T < (1 << 20) && Bp >= tc::kRows && Bp % tc::kRows == 0, NA_EINVAL,
+               "na_lstm2_fwd_train_bf16: bad shape T=%lld Bp=%lld (Bp must be a multiple of 128)", (long long)T, (long long)Bp);
+    NA_REQUIRE_PTR(x_bf16_tmp); NA_REQUIRE_PTR(packed); NA_REQUIRE_PTR(h0); NA_REQUIRE_PTR(c0);
+    NA_REQUIRE_PTR(h1); NA_REQUIRE_PTR(h1f); NA_REQUIRE_PTR(c1);
+    NA_OPTIONAL_PTR(mask); NA_OPTIONAL_PTR(h0d);
+    NA_REQUIRE((mask == nullptr) == (h0d == nullptr), NA_EINVAL, "na_lstm2_fwd_train_bf16: mask and h0d go together");
+    const size_t smem = sizeof(tc::FwdSmem) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(tc::lstm2_fwd_train_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "na_lstm2_fwd_train_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
+    const int ntiles = (int)(Bp / tc::kRows);
+    const int grid = ntiles < tc::tc_sms() ? ntiles : tc::tc_sms();
+    tc::lstm2_fwd_train_bf16_kernel<<<grid, tc::kTrainThreads, smem, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x_bf16_tmp), reinterpret_cast<const unsigned char*>(packed), mask, drop_scale,
+        reinterpret_cast<__nv_bfloat16*>(h0), reinterpret_cast<__nv_bfloat16*>(h0d), c0, reinterpret_cast<__nv_bfloat16*>(h1),
+        h1f, c1, (int)T, Bp, ntiles);
+    count_launch();
+    return check_launch("na_lstm2_fwd_train_bf16");
+}
+
+extern "C" int na_lstm_bwd_bf16(int64_t layer, const void* act_in, const void* h, const float* cstate, const float* dh_out,
+                                const void* packed_fwd, const float* w_ih, const float* w_hh, const void* zeros,
+                                const unsigned char* in_mask, float drop_scale, float* din, float* dw_ih, float* dw_hh,
+                                float* db, void* scratch, int64_t T, int64_t Bp, na_stream_t stream) {
+    using namespace na;
+    NA_REQUIRE(layer == 0 || layer == 1, NA_EINVAL, "na_lstm_bwd_bf16: layer must be 0 or 1");
+    NA_REQUIRE(T >= 1 && T < (1 << 20) && Bp >= tc::kRows && Bp % tc::kRows == 0, NA_EINVAL,
+               "na_lstm_bwd_bf16: bad shape T=%lld Bp=%lld", (long long)T, (long long)Bp);
+    NA_REQUIRE_PTR(act_in); NA_REQUIRE_PTR(h); NA_REQUIRE_PTR(cstate); NA_REQUIRE_PTR(dh_out); NA_REQUIRE_PTR(packed_fwd);
+    NA_REQUIRE_PTR(w_ih); NA_REQUIRE_PTR(w_hh); NA_REQUIRE_PTR(zeros); NA_REQUIRE_PTR(dw_ih); NA_REQUIRE_PTR(dw_hh);
+    NA_REQUIRE_PTR(db); NA_REQUIRE_PTR(scratch);
+    NA_OPTIONAL_PTR(in_mask); NA_OPTIONAL_PTR(din);
+    NA_REQUIRE(layer == 0 || din != nullptr, NA_EINVAL, "na_lstm_bwd_bf16: layer 1 needs din");
+    cudaStream_t st = as_stream(stream);
+    const int KI = layer == 0 ? 8 : 48;
+    // scratch: [packed_r bf16: 24*96*8*2 B = 36,864 B][partials fp32]
+    __nv_bfloat16* packed_r = reinterpret_cast<__nv_bfloat16*>(scratch);
+    float* partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 36864);
+    tc::pack_bwd_r_kernel<<<32, 256, 0, st>>>(w_ih, w_hh, KI, packed_r);
+    count_launch();
+    // the forward pack holds B0 (8 chunks) then B1 (14 chunks)
+    const unsigned char* pg = reinterpret_cast<const unsigned char*>(packed_fwd) + (layer == 0 ? 0 : 8 * tc::kBChunk);
+    int grid = 0, rc;
+    if (layer == 0)
+        rc = tc::launch_bwd<8>(act_in, h, cstate, dh_out, pg, packed_r, zeros, nullptr, 1.0f, nullptr, partial, T, Bp, st, &grid);
+    else
+        rc = tc::launch_bwd<48>(act_in, h, cstate, dh_out, pg, packed_r, zeros, in_mask, drop_scale, din, partial, T, Bp, st, &grid);
+    if (rc) return rc;
+    const int NW = layer == 0 ? 64 : 112;
+    tc::reduce_dw_kernel<<<(tc::kN * NW + 255) / 256, 256, 0, st>>>(partial, grid, KI, dw_ih, dw_hh, db);
+    count_launch();
+    return check_launch("na_lstm_bwd_bf16(reduce)");
+}

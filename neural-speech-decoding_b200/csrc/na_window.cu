@@ -1,6 +1,7 @@
 // K1: windowing + per-window per-channel z-score (Frontend/app.py:166-170 semantics),
 // HBM-bound: one read of the window, one write.  One CTA per window.
 #include "na_common.cuh"
+#include <cuda_fp16.h>
 
 namespace na {
 
@@ -9,6 +10,13 @@ constexpr int kWinThreads = 256;
 __device__ __forceinline__ void store_vec4(void* y, int64_t vec_idx, float4 v, int out_dtype) {
     if (out_dtype == NA_F32) {
         reinterpret_cast<float4*>(y)[vec_idx] = v;
+    } else if (out_dtype == NA_F16) {
+        __half2 lo = __floats2half2_rn(v.x, v.y);
+        __half2 hi = __floats2half2_rn(v.z, v.w);
+        uint2 p;
+        p.x = *reinterpret_cast<uint32_t*>(&lo);
+        p.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(y)[vec_idx] = p;
     } else {
         __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
         __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
@@ -158,6 +166,7 @@ window_zscore_generic_kernel(const float* __restrict__ x, void* __restrict__ y, 
         }
         const int64_t o = out_tmp ? ((r * Bp + b) * C + c) : ((b * T + r) * C + c);
         if (out_dtype == NA_F32) reinterpret_cast<float*>(y)[o] = v;
+        else if (out_dtype == NA_F16) reinterpret_cast<__half*>(y)[o] = __float2half_rn(v);
         else reinterpret_cast<__nv_bfloat16*>(y)[o] = __float2bfloat16_rn(v);
     }
 }
@@ -172,7 +181,7 @@ extern "C" int na_window_zscore(const float* x, void* y, int64_t B, int64_t T, i
                "na_window_zscore: bad shape B=%lld T=%lld C=%lld hop=%lld", (long long)B, (long long)T,
                (long long)C, (long long)hop);
     NA_REQUIRE(C <= kWinThreads, NA_EUNSUPPORTED, "na_window_zscore: C=%lld > %d", (long long)C, kWinThreads);
-    NA_REQUIRE(out_dtype == NA_F32 || out_dtype == NA_BF16, NA_EINVAL, "na_window_zscore: bad out_dtype");
+    NA_REQUIRE(out_dtype == NA_F32 || out_dtype == NA_BF16 || out_dtype == NA_F16, NA_EINVAL, "na_window_zscore: bad out_dtype");
     if (!out_tmp) Bp = B;
     NA_REQUIRE(Bp >= B, NA_EINVAL, "na_window_zscore: Bp < B");
     if (Bp == 0) return NA_OK;

@@ -139,21 +139,23 @@ class EEG_LSTM(nn.Module):
         else:
             self._injected_noise = {"drop1": drop1, "rrelu": rrelu_slope, "drop2": drop2}
 
-    def _draw_noise(self, B: int, T: int, device):
+    def _draw_noise(self, B: int, T: int, device, pad: int = ops.BATCH_ALIGN, mask_dtype=torch.float32):
+        """Train-mode noise as tensors (the kernels are deterministic functions of them): inter-layer
+        dropout keep-masks (time-major padded, one per layer gap), RReLU slopes, head dropout mask."""
         p, L, H = self.dropout_p, self.lstm.num_layers, self.lstm.hidden_size
-        Bp = ops.padded_batch(B)
+        Bp = ops.padded_batch(B, pad)
         inj = self._injected_noise or {}
         d1 = None
         if L > 1 and self.lstm.dropout > 0.0:
             if inj.get("drop1") is not None:
-                m = inj["drop1"].to(device=device, dtype=torch.float32)          # [L-1,B,T,H]
+                m = inj["drop1"].to(device=device, dtype=mask_dtype)             # [L-1,B,T,H]
                 d1 = []
                 for l in range(L - 1):
-                    t = torch.zeros((T, Bp, H), dtype=torch.float32, device=device)
+                    t = torch.zeros((T, Bp, H), dtype=mask_dtype, device=device)
                     t[:, :B] = m[l].permute(1, 0, 2)
                     d1.append(t)
             else:
-                d1 = [(torch.rand((T, Bp, H), device=device) >= p).float() for _ in range(L - 1)]
+                d1 = [(torch.rand((T, Bp, H), device=device) >= p).to(mask_dtype) for _ in range(L - 1)]
         if inj.get("rrelu") is not None:
             rr = inj["rrelu"].to(device=device, dtype=torch.float32).contiguous()
         else:
@@ -185,10 +187,19 @@ class EEG_LSTM(nn.Module):
             logits, _ = self.decode(x, want_probs=False)
         else:
             d1 = rr = d2 = None
-            if self.training:
-                d1, rr, d2 = self._draw_noise(B, T, x.device)
-            logits = ops.decoder_train_forward(x, lstm_params, head, self.dropout_p, self.zscore_input,
-                                               d1, rr, d2)
+            bf16 = (self.compute_dtype == torch.bfloat16 or x.dtype == torch.bfloat16
+                    or self.attn.weight.dtype == torch.bfloat16)
+            if bf16 and self.tc_supported() and not x.requires_grad:
+                # tensor-core tier: tcgen05 forward + fused BPTT (bf16 operands, 2e-2 contract)
+                if self.training:
+                    d1, rr, d2 = self._draw_noise(B, T, x.device, ops.TC_TILE, torch.uint8)
+                logits = ops.decoder_train_forward_tc(x, lstm_params, head, self.dropout_p, self.zscore_input,
+                                                      d1[0] if d1 is not None else None, rr, d2)
+            else:
+                if self.training:
+                    d1, rr, d2 = self._draw_noise(B, T, x.device)
+                logits = ops.decoder_train_forward(x, lstm_params, head, self.dropout_p, self.zscore_input,
+                                                   d1, rr, d2)
         return logits if logits.dtype == x.dtype or not x.is_floating_point() else logits.to(x.dtype)
 
 

@@ -63,7 +63,7 @@ def _stream() -> int:
 
 def all_custom_ops():
     return [window_zscore, pack_lstm_layer, lstm_layer_fwd, lstm_layer_bwd, lstm_layer_wgrad, head_fwd,
-            head_bwd, trial_mean, decoder_pack_bf16, decoder_infer_bf16]
+            head_bwd, trial_mean, decoder_pack_bf16, decoder_infer_bf16, lstm2_fwd_train_bf16, lstm_bwd_bf16]
 
 
 def launch_count() -> int:
@@ -74,7 +74,7 @@ def launch_count() -> int:
 # custom ops (kernel granularity)
 # ------------------------------------------------------------------------------------------
 @torch.library.custom_op("neuroalpha::window_zscore", mutates_args=(), device_types="cuda")
-def window_zscore(x: Tensor, T: int, hop: int, normalize: bool, time_major: bool, bf16: bool,
+def window_zscore(x: Tensor, T: int, hop: int, normalize: bool, time_major: bool, out16: int,
                   pad_to: int = BATCH_ALIGN) -> Tensor:
     """K1.  x: [B,T,C] batch or [n_samples,C] stream (then windows start every ``hop`` samples).
 
@@ -93,22 +93,22 @@ def window_zscore(x: Tensor, T: int, hop: int, normalize: bool, time_major: bool
     else:
         raise RuntimeError("window_zscore: x must be [B,T,C] or [n_samples,C]")
     Bp = padded_batch(B, pad_to) if time_major else B
-    dt = torch.bfloat16 if bf16 else torch.float32
+    dt = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16}[int(out16)]    # NA_F32 / NA_BF16 / NA_F16
     y = torch.empty((T, Bp, C) if time_major else (B, T, C), dtype=dt, device=x.device)
     if y.numel():
         _lib.call("na_window_zscore", x.data_ptr(), y.data_ptr(), B, T, C, hop, int(normalize),
-                  int(time_major), Bp, NA_BF16 if bf16 else NA_F32, _stream())
+                  int(time_major), Bp, int(out16), _stream())
     return y
 
 
 @window_zscore.register_fake
-def _(x, T, hop, normalize, time_major, bf16, pad_to=BATCH_ALIGN):
+def _(x, T, hop, normalize, time_major, out16, pad_to=BATCH_ALIGN):
     if x.dim() == 3:
         B, C = x.shape[0], x.shape[2]
     else:
         n, C = x.shape
         B = 0 if n < T else (n - T) // hop + 1
-    dt = torch.bfloat16 if bf16 else torch.float32
+    dt = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16}[int(out16)]
     return x.new_empty((T, padded_batch(B, pad_to), C) if time_major else (B, T, C), dtype=dt)
 
 
@@ -272,6 +272,10 @@ def _(x):
 
 
 TC_TILE = 128      # windows per CTA tile of the tensor-core tier (UMMA M)
+# 16-bit VALUE format of the tier (EEG samples, h, weights): IEEE fp16 -- bounded range, 3 more mantissa
+# bits than bf16 at the same tensor throughput.  Gradient operands (d gates) are bf16 inside the kernels.
+TC_VALUE_DTYPE = torch.float16
+NA_F16 = 2
 
 
 @torch.library.custom_op("neuroalpha::decoder_pack_bf16", mutates_args=(), device_types="cuda")
@@ -298,8 +302,8 @@ def decoder_infer_bf16(x_tmp: Tensor, packed: Tensor, head: Sequence[Tensor], B:
     with Bp a multiple of 128 (window_zscore(..., time_major=True, bf16=True, pad_to=128))."""
     _require_cuda(x_tmp, packed, *head)
     T, Bp, C = x_tmp.shape
-    if x_tmp.dtype != torch.bfloat16 or C != 8 or Bp % TC_TILE:
-        raise RuntimeError("decoder_infer_bf16: x_tmp must be bf16 [T, Bp % 128 == 0, 8]")
+    if x_tmp.dtype != TC_VALUE_DTYPE or C != 8 or Bp % TC_TILE:
+        raise RuntimeError("decoder_infer_bf16: x_tmp must be fp16 [T, Bp % 128 == 0, 8] (the tier's value format)")
     head = [_f32c(t) for t in head]
     NC = head[6].shape[0]
     logits = torch.empty((B, NC), dtype=torch.float32, device=x_tmp.device)
@@ -321,7 +325,7 @@ def decoder_infer_tc(x: Tensor, packed: Tensor, head_params: Sequence[Tensor], w
     K1 packs the windows time-major in bf16 (one read of x, one half-size write)."""
     _require_cuda(x)
     B, T, C = x.shape
-    xt = window_zscore(x, T, T, zscore, True, True, TC_TILE)
+    xt = window_zscore(x, T, T, zscore, True, NA_F16, TC_TILE)
     return decoder_infer_bf16(xt, packed, list(head_params), B, want_probs)
 
 
@@ -425,3 +429,113 @@ def decoder_train_forward(x: Tensor, lstm_params, head_params, p: float, zscore:
     flat = [t for layer in lstm_params for t in layer]
     return DecoderFunction.apply(x, len(lstm_params), p, zscore, drop1_masks, rrelu_slope, drop2_mask,
                                  *flat, *head_params)
+
+
+# ------------------------------------------------------------------------------------------
+# tensor-core tier, training
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op("neuroalpha::lstm2_fwd_train_bf16", mutates_args=(), device_types="cuda")
+def lstm2_fwd_train_bf16(x_tmp: Tensor, packed: Tensor, mask: Optional[Tensor],
+                         drop_scale: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Training forward of the 2-layer LSTM on tcgen05.  x_tmp bf16 TMP [T,Bp,8] (Bp % 128 == 0), mask u8
+    [T,Bp,48] or None -> (h0 TCL, h0d TCL or empty, c0 TMP, h1 TCL, h1f TMP, c1 TMP)."""
+    _require_cuda(x_tmp, packed, mask)
+    T, Bp, _ = x_tmp.shape
+    dev = x_tmp.device
+    tcl = lambda: torch.empty((T, Bp // TC_TILE, 6, TC_TILE, 8), dtype=TC_VALUE_DTYPE, device=dev)
+    tmp = lambda: torch.empty((T, Bp, 48), dtype=torch.float32, device=dev)
+    h0, h1, c0, h1f, c1 = tcl(), tcl(), tmp(), tmp(), tmp()
+    h0d = tcl() if mask is not None else torch.empty((0,), dtype=TC_VALUE_DTYPE, device=dev)
+    _lib.call("na_lstm2_fwd_train_bf16", x_tmp.data_ptr(), packed.data_ptr(), _ptr(mask), float(drop_scale),
+              h0.data_ptr(), _ptr(h0d) if mask is not None else None, c0.data_ptr(), h1.data_ptr(), h1f.data_ptr(),
+              c1.data_ptr(), T, Bp, _stream())
+    return h0, h0d, c0, h1, h1f, c1
+
+
+@lstm2_fwd_train_bf16.register_fake
+def _(x_tmp, packed, mask, drop_scale):
+    T, Bp, _ = x_tmp.shape
+    tcl = lambda: x_tmp.new_empty((T, Bp // TC_TILE, 6, TC_TILE, 8))
+    tmp = lambda: x_tmp.new_empty((T, Bp, 48), dtype=torch.float32)
+    return tcl(), (tcl() if mask is not None else x_tmp.new_empty((0,))), tmp(), tcl(), tmp(), tmp()
+
+
+@torch.library.custom_op("neuroalpha::lstm_bwd_bf16", mutates_args=(), device_types="cuda")
+def lstm_bwd_bf16(layer: int, act_in: Tensor, h: Tensor, c: Tensor, dh: Tensor, packed: Tensor, w_ih: Tensor,
+                  w_hh: Tensor, in_mask: Optional[Tensor], drop_scale: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Fused BPTT + weight gradients of one layer on tcgen05 -> (din TMP or empty, dW_ih, dW_hh, db)."""
+    _require_cuda(act_in, h, c, dh, packed, w_ih, w_hh, in_mask)
+    T, Bp, H = c.shape
+    dev = c.device
+    w_ih, w_hh = _f32c(w_ih), _f32c(w_hh)
+    din = torch.empty((T, Bp, H) if layer == 1 else (0,), dtype=torch.float32, device=dev)
+    dw_ih, dw_hh = torch.empty_like(w_ih), torch.empty_like(w_hh)
+    db = torch.empty((4 * H,), dtype=torch.float32, device=dev)
+    zeros = torch.zeros((12288,), dtype=torch.uint8, device=dev)
+    scratch = torch.empty((36864 + 4 * _lib.query("na_train_bf16_partial_floats"),), dtype=torch.uint8, device=dev)
+    _lib.call("na_lstm_bwd_bf16", int(layer), act_in.data_ptr(), h.data_ptr(), c.data_ptr(), _f32c(dh).data_ptr(),
+              packed.data_ptr(), w_ih.data_ptr(), w_hh.data_ptr(), zeros.data_ptr(), _ptr(in_mask), float(drop_scale),
+              _ptr(din) if layer == 1 else None, dw_ih.data_ptr(), dw_hh.data_ptr(), db.data_ptr(), scratch.data_ptr(),
+              T, Bp, _stream())
+    return din, dw_ih, dw_hh, db
+
+
+@lstm_bwd_bf16.register_fake
+def _(layer, act_in, h, c, dh, packed, w_ih, w_hh, in_mask, drop_scale):
+    return (c.new_empty(c.shape if layer == 1 else (0,)), w_ih.new_empty(w_ih.shape, dtype=torch.float32),
+            w_hh.new_empty(w_hh.shape, dtype=torch.float32), c.new_empty((4 * c.shape[2],)))
+
+
+class DecoderFunctionTC(torch.autograd.Function):
+    """Training step of the flagship decoder on the tensor-core tier: tcgen05 forward that saves h / c,
+    fp32 head kernels, tcgen05 BPTT with the weight gradients accumulated in TMEM.  bf16 contract
+    (logits and gradients within 2e-2 of the fp32 reference)."""
+
+    @staticmethod
+    def forward(ctx, x, p, zscore, drop1_mask_u8, rrelu_slope, drop2_mask, *params):
+        _require_cuda(x, *params)
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("the tensor-core training tier does not produce d/dx; use compute_dtype=float32")
+        B, T, C = x.shape
+        lstm_flat, head = [t.detach() for t in params[:8]], [_f32c(t.detach()) for t in params[8:]]
+        scale = 1.0 / (1.0 - p) if p < 1.0 else 0.0
+        xt = window_zscore(x.detach(), T, T, zscore, True, NA_F16, TC_TILE)
+        packed = decoder_pack_bf16(lstm_flat)
+        h0, h0d, c0, h1, h1f, c1 = lstm2_fwd_train_bf16(xt, packed, drop1_mask_u8, scale)
+        logits, _, stats, zpool = head_fwd(h1f, B, head, rrelu_slope, drop2_mask, scale, False, True)
+        w = [_f32c(t) for t in lstm_flat]
+        opt = [t for t in (drop1_mask_u8, rrelu_slope, drop2_mask) if t is not None]
+        ctx.save_for_backward(xt, h0, h0d, c0, h1, h1f, c1, packed, stats, zpool, w[0], w[1], w[4], w[5], *head, *opt)
+        ctx.meta = (scale, B, drop1_mask_u8 is not None, rrelu_slope is not None, drop2_mask is not None)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        scale, B, has_d1, has_rr, has_d2 = ctx.meta
+        sv = list(ctx.saved_tensors)
+        xt, h0, h0d, c0, h1, h1f, c1, packed, stats, zpool, w_ih0, w_hh0, w_ih1, w_hh1 = sv[:14]
+        head = sv[14:22]
+        rest = sv[22:]
+        d1 = rest.pop(0) if has_d1 else None
+        rr = rest.pop(0) if has_rr else None
+        d2 = rest.pop(0) if has_d2 else None
+        H, NC = 48, dlogits.shape[1]
+        # Gradient scaling: d(gates) travel through the tensor pipe as fp16, so the incoming gradient is
+        # scaled by a power of two (exact) that puts max|dlogits| at 2^11; every gradient is unscaled by the
+        # same power at the end.  All on the device, no host sync.
+        amax = dlogits.detach().abs().max().clamp_min(1e-30)
+        s = torch.exp2(11.0 - torch.ceil(torch.log2(amax)))
+        inv_s = 1.0 / s
+        dh1, dparams = head_bwd((dlogits * s).contiguous(), h1f, stats, zpool, head, rr, d2, scale)
+        head_grads = split_head_grads(dparams * inv_s, H, NC)
+        din1, dw_ih1, dw_hh1, db1 = lstm_bwd_bf16(1, h0d if has_d1 else h0, h1, c1, dh1, packed, w_ih1, w_hh1, d1, scale)
+        _, dw_ih0, dw_hh0, db0 = lstm_bwd_bf16(0, xt, h0, c0, din1, packed, w_ih0, w_hh0, None, 1.0)
+        db0, db1 = db0 * inv_s, db1 * inv_s
+        return (None, None, None, None, None, None, dw_ih0 * inv_s, dw_hh0 * inv_s, db0, db0.clone(),
+                dw_ih1 * inv_s, dw_hh1 * inv_s, db1, db1.clone(), *head_grads)
+
+
+def decoder_train_forward_tc(x: Tensor, lstm_params, head_params, p: float, zscore: bool = False,
+                             drop1_mask_u8=None, rrelu_slope=None, drop2_mask=None) -> Tensor:
+    flat = [t for layer in lstm_params for t in layer]
+    return DecoderFunctionTC.apply(x, p, zscore, drop1_mask_u8, rrelu_slope, drop2_mask, *flat, *head_params)

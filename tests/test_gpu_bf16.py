@@ -110,3 +110,59 @@ def test_bf16_five_class_and_trial_mean(dev, windows, golden_dir):
     want = no.trial_mean(no.softmax(no.decoder_forward(w.reshape(R * B, 625, 8), {k: v.numpy() for k, v in sd.items()})).reshape(R, B, 5))
     avg = run_trials_batched(w, m)
     assert np.abs(avg - want).max() < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------
+# training on the tensor-core tier (tcgen05 forward-with-save + fused BPTT/weight gradients)
+# ---------------------------------------------------------------------------------------------
+def grad_rel(model, ref_grads):
+    out = {}
+    aw = np.abs(ref_grads["attn.weight"]).max()
+    gmax = max(float(np.abs(ref_grads[k]).max()) for k, _ in model.named_parameters())
+    for k, p in model.named_parameters():
+        r = ref_grads[k]
+        scale = max(float(aw if k == "attn.bias" else np.abs(r).max()), 0.05 * gmax)
+        out[k] = float(np.abs(p.grad.float().cpu().numpy() - r).max() / scale)
+    return out
+
+
+def test_bf16_training_gradients_eval_mode(dev, checkpoint, windows, golden_dir):
+    g = np.load(golden_dir / "fp64_grads_3class_eval_b16.npz")
+    sel = np.load(golden_dir / "ref_grads_3class_eval_b16.npz")
+    m = bf16_model(dev, checkpoint)                       # eval mode: deterministic, autograd still works
+    x = torch.from_numpy(windows["X"][sel["sel"]]).to(dev)
+    y = torch.from_numpy(sel["y"]).to(dev)
+    logits = m(x)
+    assert rel(logits.detach().cpu().numpy(), sel["logits"]) < BF16_TOL
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 2e-2
+    worst = grad_rel(m, g)
+    assert max(worst.values()) < BF16_TOL, worst
+    # bit-reproducible (fixed-order reduction of the per-CTA TMEM partials)
+    g1 = [p.grad.clone() for p in m.parameters()]
+    m.zero_grad()
+    torch.nn.functional.cross_entropy(m(x), y).backward()
+    for a, p in zip(g1, m.parameters()):
+        assert torch.equal(a, p.grad)
+
+
+def test_bf16_training_with_injected_noise_and_many_tiles(dev, checkpoint):
+    from oracle.torch_ref import explicit_forward
+    torch.manual_seed(21)
+    B, T, H = 300, 30, 48                                  # 3 tiles (384 padded), ragged
+    x = torch.randn(B, T, 8) * 2.73
+    y = torch.randint(0, 3, (B,))
+    d1 = (torch.rand(1, B, T, H) >= 0.6).float()
+    rr = torch.empty(B, 32).uniform_(1 / 8, 1 / 3)
+    d2 = (torch.rand(B, 32) >= 0.6).float()
+    sd = {k: v.double().requires_grad_(True) for k, v in checkpoint.items()}
+    lr = torch.nn.functional.cross_entropy(explicit_forward(x.double(), sd, 2, 0.6, d1[0].double(), rr.double(), d2.double()), y)
+    lr.backward()
+    m = bf16_model(dev, checkpoint).train()
+    m.inject_noise(drop1=d1, rrelu_slope=rr, drop2=d2)
+    loss = torch.nn.functional.cross_entropy(m(x.to(dev)), y.to(dev))
+    loss.backward()
+    assert abs(loss.item() - lr.item()) < 2e-2
+    worst = grad_rel(m, {k: v.grad.numpy() for k, v in sd.items()})
+    assert max(worst.values()) < BF16_TOL, worst
