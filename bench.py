@@ -338,31 +338,48 @@ def run_gpu_arm(args):
 
 
 def train_leg(args, world, rank, dev):
-    """Data-parallel training step: per-GPU micro-batches, one flat NCCL all-reduce, Adam."""
+    """BASELINE configs[2]: data-parallel training of the 3-class decoder on synthetic EEG, GLOBAL batch
+    65,536 (fixed as N grows: per-GPU batch 65,536/N, micro-batched), train mode (inter-layer dropout,
+    RReLU noise, dropout), mean CE over the global batch, one flat NCCL all-reduce, Adam (torch).
+    Headline: tensor-core tier; the exact-fp32 tier is timed beside it on a bounded global batch."""
     from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
     from neural_speech_decoding_b200.dp import DataParallelTrainer
-    torch.manual_seed(0)
-    model = EEG_LSTM().to(dev)
-    model.load_state_dict(load_checkpoint(), strict=True)
-    model.train()
-    per_gpu = args.train_batch
-    micro = min(per_gpu, args.train_micro)
-    x = synth_windows(micro, seed=2000 + rank).to(dev)
-    g = torch.Generator(device="cpu").manual_seed(1 + rank)
-    y = torch.randint(0, NC, (micro,), generator=g).to(dev)
-    trainer = DataParallelTrainer(model, torch.optim.Adam(model.parameters(), lr=1e-3), world_size=world)
-    n_micro = per_gpu // micro
 
-    def step():
-        trainer.step([(x, y)] * n_micro, global_batch=per_gpu * world)
+    def run(dtype, global_batch, micro, steps):
+        torch.manual_seed(0)
+        model = EEG_LSTM().to(dev)
+        model.load_state_dict(load_checkpoint(), strict=True)
+        model.train()
+        model.compute_dtype = dtype
+        per_gpu = global_batch // world
+        micro = min(per_gpu, micro)
+        n_micro = max(1, per_gpu // micro)
+        per_gpu = n_micro * micro
+        x = synth_windows(micro, seed=2000 + rank).to(dev)
+        g = torch.Generator(device="cpu").manual_seed(1 + rank)
+        y = torch.randint(0, NC, (micro,), generator=g).to(dev)
+        trainer = DataParallelTrainer(model, torch.optim.Adam(model.parameters(), lr=1e-3), world_size=world)
+
+        def step():
+            trainer.step([(x, y)] * n_micro, global_batch=per_gpu * world)
+
+        ms = time_steps(step, steps, 1, world, dev)
+        wps = world * per_gpu * steps / (ms * 1e-3)
+        return {"value": wps, "unit": "windows/s", "ms_per_step": ms / steps, "global_batch": per_gpu * world,
+                "per_gpu_batch": per_gpu, "micro_batch": micro, "steps": steps,
+                "achieved_tflops_per_gpu": FWDBWD_FLOPS_PER_WINDOW * wps / world / 1e12}
 
     steps = max(1, min(args.steps, 3))
-    ms = time_steps(step, steps, 1, world, dev)
-    wps = world * per_gpu * steps / (ms * 1e-3)
-    return {"value": wps, "unit": "windows/s", "ms_per_step": ms / steps, "global_batch": per_gpu * world,
-            "per_gpu_batch": per_gpu, "micro_batch": micro, "optimizer": "Adam lr=1e-3 (torch)",
-            "allreduce": "one flat fp32 bucket, NCCL" if world > 1 else "none (1 GPU)",
-            "achieved_tflops_per_gpu": FWDBWD_FLOPS_PER_WINDOW * wps / world / 1e12}
+    tc = run(torch.bfloat16, args.train_batch, args.train_micro, steps)
+    tc.update({"dtype": "fp16 tensor-core operands (tcgen05), fp32 accumulate / cell state / weight gradients",
+               "optimizer": "Adam lr=1e-3 (torch)", "scaling": "strong (global batch fixed)",
+               "allreduce": "one flat fp32 bucket (127 KB), NCCL" if world > 1 else "none (1 GPU)",
+               "parity": "tests/test_gpu_bf16.py: gradients within 2e-2 of the fp64 oracle",
+               "frac_of_bf16_sustained_peak": tc["achieved_tflops_per_gpu"] / measured_peaks()["bf16_tflops_sustained"]})
+    fp = run(torch.float32, min(args.train_batch, 8192 * world), 4096, min(steps, 2))
+    tc["fp32_exact"] = {k: fp[k] for k in ("value", "unit", "ms_per_step", "global_batch", "micro_batch")}
+    tc["fp32_exact"]["parity"] = "tests/test_gpu_parity.py: gradients within 1e-5"
+    return tc
 
 
 def main():
@@ -373,8 +390,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--train-batch", type=int, default=8192, help="per-GPU batch of the train leg")
-    ap.add_argument("--train-micro", type=int, default=4096)
+    ap.add_argument("--train-batch", type=int, default=65536, help="GLOBAL batch of the train leg (configs[2])")
+    ap.add_argument("--train-micro", type=int, default=16384)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -191,13 +191,20 @@ int na_decoder_infer_bf16(const void* x_bf16_tmp, const void* packed,
  *   packed_fwd = na_decoder_pack_bf16 output; zeros = >= 12,288 B of zeros; scratch =
  *   36,864 + 4 * na_train_bf16_partial_floats() bytes.
  */
+/* Dropout of the tier: either an explicit keep-mask tensor (mask != NULL) or, with mask == NULL and
+ * thresh16 < 65536, a counter-based in-kernel generator: unit block (t*Bp + b, blk) keeps a unit with
+ * probability thresh16/65536 as a pure function of (seed, row, blk) -- the backward regenerates the
+ * forward's mask, no mask tensor exists.  thresh16 == 65536 and mask == NULL: no dropout.
+ * na_dropout_mask_u8 materialises that mask ([T][Bp][48] u8) for tests. */
+int na_dropout_mask_u8(uint64_t seed, int64_t thresh16, int64_t T, int64_t Bp, unsigned char* out, na_stream_t stream);
 int64_t na_train_bf16_partial_floats(void);
 int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packed, const unsigned char* mask,
-                            float drop_scale, void* h0, void* h0d, float* c0, void* h1, float* h1f,
+                            uint64_t seed, int64_t thresh16, float drop_scale, void* h0, void* h0d, float* c0, void* h1, float* h1f,
                             float* c1, int64_t T, int64_t Bp, na_stream_t stream);
 int na_lstm_bwd_bf16(int64_t layer, const void* act_in, const void* h, const float* cstate,
                      const float* dh_out, const void* packed_fwd, const float* w_ih, const float* w_hh,
-                     const void* zeros, const unsigned char* in_mask, float drop_scale, float* din,
+                     const void* zeros, const unsigned char* in_mask, uint64_t seed, int64_t thresh16,
+                     float drop_scale, float* din,
                      float* dw_ih, float* dw_hh, float* db, void* scratch,
                      int64_t T, int64_t Bp, na_stream_t stream);
 

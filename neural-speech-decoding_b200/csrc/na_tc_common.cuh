@@ -123,6 +123,34 @@ __device__ __forceinline__ void cell_block(const uint32_t (&v)[32], float* c, ui
 }
 
 
+// ---- inter-layer dropout (lstm_eeg_model.py:21) without a mask tensor ---------------------------------
+// Counter-based: the keep-bits of the 8 units of block `blk` of window-row `grow` (= t*Bp + b) are a pure
+// function of (seed, grow, blk), so the backward regenerates exactly the forward's mask.  16-bit
+// resolution: P(keep) = thresh16 / 65536.
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, int64_t grow, int blk, uint32_t thresh16) {
+    const uint64_t idx = (uint64_t)grow * 6u + (uint32_t)blk;
+    const uint32_t base = fmix32(((uint32_t)idx ^ (uint32_t)seed) * 0x9E3779B1u + ((uint32_t)(idx >> 32) ^ (uint32_t)(seed >> 32)));
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t w = fmix32(base + (uint32_t)(i + 1) * 0x9E3779B9u);
+        bits |= ((w & 0xFFFFu) < thresh16 ? 1u : 0u) << (2 * i);
+        bits |= ((w >> 16) < thresh16 ? 1u : 0u) << (2 * i + 1);
+    }
+    return bits;
+}
+// keep-bits from 8 mask bytes (explicit mask tensor)
+__device__ __forceinline__ uint32_t mask_keep8(uint2 mk) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) bits |= ((((u < 4 ? mk.x : mk.y) >> (8 * (u & 3))) & 0xFFu) ? 1u : 0u) << u;
+    return bits;
+}
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])

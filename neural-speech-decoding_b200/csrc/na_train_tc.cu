@@ -24,7 +24,7 @@ namespace na {
 namespace tc {
 
 constexpr int kTrainThreads = 320;     // forward: 4 + 4 epilogue warps, MMA warp, TMA warp
-constexpr int kBwdThreads = 192;       // backward: 4 epilogue warps, MMA warp, TMA warp
+constexpr int kBwdThreads = 320;       // backward: 8 epilogue warps (2 per TMEM lane quarter), MMA warp, TMA warp
 constexpr int kXStagesT = 4;
 
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
@@ -64,7 +64,7 @@ struct FwdSmem {
 
 __global__ void __launch_bounds__(kTrainThreads, 1)
 lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned char* __restrict__ packed,
-                            const unsigned char* __restrict__ mask, float drop_scale,
+                            const unsigned char* __restrict__ mask, uint64_t seed, uint32_t thresh16, float drop_scale,
                             __nv_bfloat16* __restrict__ h0_out, __nv_bfloat16* __restrict__ h0d_out,
                             float* __restrict__ c0_out, __nv_bfloat16* __restrict__ h1_out,
                             float* __restrict__ h1f_out, float* __restrict__ c1_out,
@@ -98,7 +98,7 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
         tc_fence_after();
     }
     const uint32_t tmem = S.tmem_base, tmem_d0 = tmem, tmem_d1 = tmem + kN;
-    const bool drop = mask != nullptr;
+    const bool drop = mask != nullptr || thresh16 < 65536u;      // explicit mask tensor, or in-kernel counter-based RNG
 
     int n0 = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, n0 += T) {
@@ -168,10 +168,12 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                 const int n = n0 + t;
                 const int64_t grow = (int64_t)t * Bp + b0 + row;                 // TMP row
                 const int64_t tcl = ((int64_t)t * ntiles + tile) * 6 * (kAChunk / 2) + row * 8;   // TCL element offset of chunk 0
-                uint2 mk[6];
+                uint32_t keep[6];
                 if (drop) {
 #pragma unroll
-                    for (int blk = 0; blk < 6; ++blk) mk[blk] = *reinterpret_cast<const uint2*>(mask + grow * kH + blk * 8);
+                    for (int blk = 0; blk < 6; ++blk)
+                        keep[blk] = mask ? mask_keep8(*reinterpret_cast<const uint2*>(mask + grow * kH + blk * 8))
+                                         : dropout_keep8(seed, grow, blk, thresh16);
                 }
                 mbar_wait(&S.d0_full, n & 1);
                 mbar_wait(&S.h0_free[n & 1], ((n >> 1) & 1) ^ 1);
@@ -191,13 +193,9 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                     st_global_v4f(c0_out + grow * kH + blk * 8, c[blk * 8], c[blk * 8 + 1], c[blk * 8 + 2], c[blk * 8 + 3]);
                     st_global_v4f(c0_out + grow * kH + blk * 8 + 4, c[blk * 8 + 4], c[blk * 8 + 5], c[blk * 8 + 6], c[blk * 8 + 7]);
                     if (drop) {
-                        const uint32_t mlo = mk[blk].x, mhi = mk[blk].y;
                         float hd[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const uint32_t byte = ((u < 4 ? mlo : mhi) >> (8 * (u & 3))) & 0xFFu;
-                            hd[u] = byte ? h[u] * drop_scale : 0.f;
-                        }
+                        for (int u = 0; u < 8; ++u) hd[u] = ((keep[blk] >> u) & 1u) ? h[u] * drop_scale : 0.f;
                         const uint32_t q0 = pack_val(hd[0], hd[1]), q1 = pack_val(hd[2], hd[3]);
                         const uint32_t q2 = pack_val(hd[4], hd[5]), q3 = pack_val(hd[6], hd[7]);
                         st_shared_v4(dstd + blk * kAChunk, q0, q1, q2, q3);
@@ -274,7 +272,7 @@ struct BwdSmem {
     alignas(128) unsigned char act[2][C::kStageChunks * kAChunk];      // [in_t | 1 | h_{t-1}] stages
     alignas(128) unsigned char dg[24 * kAChunk];                       // d(gates) bf16, A operand of R and W
     alignas(8) uint64_t act_full[2], act_free[2];
-    uint64_t g_full, dg_ready;
+    uint64_t g_full, dg_ready, w_done;
     uint32_t tmem_base;
 };
 
@@ -287,7 +285,8 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                      const unsigned char* __restrict__ packed_g,   // forward B operand of this layer
                      const unsigned char* __restrict__ packed_r,   // [24 chunks][kNR][8] bf16
                      const __nv_bfloat16* __restrict__ zeros,      // >= 6*2048 B of zeros (h_{-1})
-                     const unsigned char* __restrict__ mask, float drop_scale,   // KI == 48: mask of this layer's input
+                     const unsigned char* __restrict__ mask, uint64_t seed, uint32_t thresh16,
+                     float drop_scale,                             // KI == 48: dropout of this layer's input
                      float* __restrict__ din,                      // TMP, KI == 48 only
                      float* __restrict__ dw_partial,               // [grid][192][kNW]
                      int T, int64_t Bp, int ntiles) {
@@ -312,10 +311,11 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
         if (tid == 0) {
             for (int s = 0; s < 2; ++s) { mbar_init(&S.act_full[s], 1); mbar_init(&S.act_free[s], 1); }
             mbar_init(&S.g_full, 1);
-            mbar_init(&S.dg_ready, 128);
+            mbar_init(&S.w_done, 1);
+            mbar_init(&S.dg_ready, 256);
             fence_mbar_init();
         }
-        if (warp == 5) tmem_alloc_all(&S.tmem_base);
+        if (warp == 9) tmem_alloc_all(&S.tmem_base);
         tc_fence_before();
         fence_proxy_async_smem();
         __syncthreads();
@@ -328,11 +328,11 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
     constexpr uint32_t kStageBytes = (C::kInChunks + 6) * kAChunk;
 
     uint32_t k0 = 0;                              // running step counter (stage / phase bookkeeping)
-    uint32_t gphase = 0;                          // phases of g_full consumed / produced so far
+    uint32_t gphase = 0, wphase = 0;              // phases of g_full / w_done consumed so far (epilogue warps)
     bool first_w = true;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t b0 = (int64_t)tile * kRows;
-        if (warp == 5) {
+        if (warp == 9) {
             // ================= TMA producer: [in_t | h_{t-1}] for t = T-1 .. 0 ==========================
             if (lane == 0)
                 for (int i = 0; i < T; ++i) {
@@ -345,32 +345,24 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                     const __nv_bfloat16* hsrc = t > 0 ? h + (((int64_t)(t - 1) * ntiles + tile) * 6) * (kAChunk / 2) : zeros;
                     bulk_load(S.act[s] + C::kHprevChunk * kAChunk, hsrc, 6 * kAChunk, &S.act_full[s]);
                 }
-        } else if (warp == 4) {
+        } else if (warp == 8) {
             // ================= MMA issuer ================================================================
+            // per iteration: R(prev) -> G(cur) -> commit g_full -> W(prev) -> commit act_free, w_done.
+            // The epilogue only needs R and G; W (dW accumulation) trails behind and is fenced by w_done
+            // before the epilogue overwrites d(gates).
             if (lane == 0) {
                 const uint32_t bga = smem_u32(S.bg), bra = smem_u32(S.br), dga = smem_u32(S.dg);
                 uint32_t dgp = k0;                // dg_ready phases consumed
                 for (int i = 0; i <= T; ++i) {
+                    const uint32_t sp = (k0 + i - 1) & 1;
                     if (i >= 1) {
-                        // R and W of the previous step (its d(gates) are in shared memory)
-                        const uint32_t kp = k0 + i - 1, sp = kp & 1;
                         mbar_wait(&S.dg_ready, dgp & 1);
                         ++dgp;
                         tc_fence_after();
-                        const uint32_t acta = smem_u32(S.act[sp]);
 #pragma unroll
                         for (int ks = 0; ks < 12; ++ks)
                             umma_bf16_i(tm_r, umma_desc(dga + 2 * ks * kAChunk, kAChunk, 128),
                                         umma_desc(bra + 2 * ks * C::kNR * 16, C::kNR * 16, 128), kIdescR, ks == 0 ? 0u : 1u);
-#pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {
-                            const uint32_t acc = (first_w && ks == 0) ? 0u : 1u;
-                            const uint64_t bdesc = umma_desc(acta + ks * 256, 128, kAChunk);
-                            umma_bf16_i(tm_w1, umma_desc(dga + ks * 256, 128, kAChunk), bdesc, kIdescW, acc);
-                            umma_bf16_i(tm_w2, umma_desc(dga + 8 * kAChunk + ks * 256, 128, kAChunk), bdesc, kIdescW, acc);
-                        }
-                        first_w = false;
-                        umma_commit(&S.act_free[sp]);
                     }
                     if (i < T) {
                         const uint32_t k = k0 + i, s = k & 1, u = k >> 1;
@@ -382,19 +374,56 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                             umma_bf16(tm_g, umma_desc(acta + 2 * ks * kAChunk, kAChunk, 128),
                                       umma_desc(bga + 2 * ks * kBChunk, kBChunk, 128), ks == 0 ? 0u : 1u);
                     }
-                    umma_commit(&S.g_full);        // step i: G(t) done (and R, W of the step before); i == T: tail
+                    umma_commit(&S.g_full);        // R(prev) and G(cur) done; i == T: tail (R only)
+                    if (i >= 1) {
+                        const uint32_t acta = smem_u32(S.act[sp]);
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+                            const uint32_t acc = (first_w && ks == 0) ? 0u : 1u;
+                            const uint64_t bdesc = umma_desc(acta + ks * 256, 128, kAChunk);
+                            umma_bf16_i(tm_w1, umma_desc(dga + ks * 256, 128, kAChunk), bdesc, kIdescW, acc);
+                            umma_bf16_i(tm_w2, umma_desc(dga + 8 * kAChunk + ks * 256, 128, kAChunk), bdesc, kIdescW, acc);
+                        }
+                        first_w = false;
+                        umma_commit(&S.act_free[sp]);
+                        umma_commit(&S.w_done);
+                    }
                 }
             }
-        } else if (warp < 4) {
-            // ================= epilogue: thread = window ==================================================
-            const int row = warp * 32 + lane;
-            const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-            float dc[kH];
+        } else if (warp < 8) {
+            // ================= epilogue: thread = window x half of the units (3 blocks of 8) ================
+            const int q = warp & 3, hf = warp >> 2;
+            const int row = q * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+            float dc[24], ccur[24];
 #pragma unroll
-            for (int j = 0; j < kH; ++j) dc[j] = 0.f;
+            for (int j = 0; j < 24; ++j) dc[j] = 0.f;
+            {   // c_{T-1} of this tile (afterwards c_t is carried over from the previous iteration's c_{t-1})
+                const float* crow = cstate + ((int64_t)(T - 1) * Bp + b0 + row) * kH + hf * 24;
+#pragma unroll
+                for (int j = 0; j < 24; j += 4) {
+                    const float4 a = *reinterpret_cast<const float4*>(crow + j);
+                    ccur[j] = a.x; ccur[j + 1] = a.y; ccur[j + 2] = a.z; ccur[j + 3] = a.w;
+                }
+            }
             unsigned char* dgrow = S.dg + row * 16;
             for (int i = 0; i <= T; ++i) {
                 const int t = T - 1 - i;                                  // step whose gates are in D_G (i < T)
+                // ---- prefetch this step's c_{t-1} and dh_out BEFORE waiting for the tensor pipe -----------
+                float cp[24], dh[24];
+                if (i < T) {
+                    const int64_t grow = (int64_t)t * Bp + b0 + row;
+                    const float* dhrow = dh_out + grow * kH + hf * 24;
+                    const float* cprow = cstate + (grow - Bp) * kH + hf * 24;
+#pragma unroll
+                    for (int j = 0; j < 24; j += 4) {
+                        const float4 d = *reinterpret_cast<const float4*>(dhrow + j);
+                        dh[j] = d.x; dh[j + 1] = d.y; dh[j + 2] = d.z; dh[j + 3] = d.w;
+                        float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (t > 0) c4 = *reinterpret_cast<const float4*>(cprow + j);
+                        cp[j] = c4.x; cp[j + 1] = c4.y; cp[j + 2] = c4.z; cp[j + 3] = c4.w;
+                    }
+                }
                 mbar_wait(&S.g_full, gphase & 1);
                 ++gphase;
                 tc_fence_after();
@@ -402,17 +431,16 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                     // din of step t+1 = D_R[:, 0:48] * mask * scale  -> dh_out of the layer below
                     const int64_t grow = (int64_t)(t + 1) * Bp + b0 + row;
 #pragma unroll
-                    for (int blk = 0; blk < 6; ++blk) {
+                    for (int bb = 0; bb < 3; ++bb) {
+                        const int blk = hf * 3 + bb;
                         uint32_t r[8];
                         tmem_ld8(tm_r + lane_base + blk * 8, r);
                         float o[8];
-                        if (mask) {
-                            const uint2 mk = *reinterpret_cast<const uint2*>(mask + grow * kH + blk * 8);
+                        if (mask || thresh16 < 65536u) {
+                            const uint32_t keep = mask ? mask_keep8(*reinterpret_cast<const uint2*>(mask + grow * kH + blk * 8))
+                                                       : dropout_keep8(seed, grow, blk, thresh16);
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const uint32_t byte = ((u < 4 ? mk.x : mk.y) >> (8 * (u & 3))) & 0xFFu;
-                                o[u] = byte ? __uint_as_float(r[u]) * drop_scale : 0.f;
-                            }
+                            for (int u = 0; u < 8; ++u) o[u] = ((keep >> u) & 1u) ? __uint_as_float(r[u]) * drop_scale : 0.f;
                         } else {
 #pragma unroll
                             for (int u = 0; u < 8; ++u) o[u] = __uint_as_float(r[u]);
@@ -421,50 +449,43 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                         st_global_v4f(din + grow * kH + blk * 8 + 4, o[4], o[5], o[6], o[7]);
                     }
                 }
-                if (i == T) break;                                        // tail: nothing left to differentiate
-                const int64_t grow = (int64_t)t * Bp + b0 + row;
-                const float* crow = cstate + grow * kH;
-                const float* cprow = cstate + (grow - Bp) * kH;           // c_{t-1} (t > 0)
-                const float* dhrow = dh_out + grow * kH;
+                if (i == T) {                                             // tail: all W of this tile must be done
+                    mbar_wait(&S.w_done, wphase & 1);
+                    ++wphase;
+                    break;
+                }
 #pragma unroll
-                for (int blk = 0; blk < 6; ++blk) {
-                    float ct[8], cp[8], dh[8];
-                    {
-                        const float4 a = *reinterpret_cast<const float4*>(crow + blk * 8), b = *reinterpret_cast<const float4*>(crow + blk * 8 + 4);
-                        ct[0] = a.x; ct[1] = a.y; ct[2] = a.z; ct[3] = a.w; ct[4] = b.x; ct[5] = b.y; ct[6] = b.z; ct[7] = b.w;
-                        const float4 d = *reinterpret_cast<const float4*>(dhrow + blk * 8), e = *reinterpret_cast<const float4*>(dhrow + blk * 8 + 4);
-                        dh[0] = d.x; dh[1] = d.y; dh[2] = d.z; dh[3] = d.w; dh[4] = e.x; dh[5] = e.y; dh[6] = e.z; dh[7] = e.w;
-                        if (t > 0) {
-                            const float4 f = *reinterpret_cast<const float4*>(cprow + blk * 8), g = *reinterpret_cast<const float4*>(cprow + blk * 8 + 4);
-                            cp[0] = f.x; cp[1] = f.y; cp[2] = f.z; cp[3] = f.w; cp[4] = g.x; cp[5] = g.y; cp[6] = g.z; cp[7] = g.w;
-                        } else {
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) cp[u] = 0.f;
-                        }
-                    }
+                for (int bb = 0; bb < 3; ++bb) {
+                    const int blk = hf * 3 + bb;
                     uint32_t v[32];
                     tmem_ld32(tm_g + lane_base + blk * 32, v);
                     if (i >= 1) {
                         uint32_t r[8];
                         tmem_ld8(tm_r + lane_base + C::kRecCol + blk * 8, r);
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) dh[u] += __uint_as_float(r[u]);
+                        for (int u = 0; u < 8; ++u) dh[bb * 8 + u] += __uint_as_float(r[u]);
                     }
                     float pi[8], pf[8], pg[8], po[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
+                        const int j = bb * 8 + u;
                         const float gi = sigmoid_apx(__uint_as_float(v[u]));
                         const float gf = sigmoid_apx(__uint_as_float(v[8 + u]));
                         const float gg = tanh_apx(__uint_as_float(v[16 + u]));
                         const float go = sigmoid_apx(__uint_as_float(v[24 + u]));
-                        const float tcv = tanh_apx(ct[u]);
-                        const float d_o = dh[u] * tcv;
-                        const float dct = fmaf(dh[u] * go, 1.0f - tcv * tcv, dc[blk * 8 + u]);
-                        dc[blk * 8 + u] = dct * gf;
+                        const float tcv = tanh_apx(ccur[j]);
+                        const float d_o = dh[j] * tcv;
+                        const float dct = fmaf(dh[j] * go, 1.0f - tcv * tcv, dc[j]);
+                        dc[j] = dct * gf;
                         pi[u] = dct * gg * gi * (1.0f - gi);
-                        pf[u] = dct * cp[u] * gf * (1.0f - gf);
+                        pf[u] = dct * cp[j] * gf * (1.0f - gf);
                         pg[u] = dct * gi * (1.0f - gg * gg);
                         po[u] = d_o * go * (1.0f - go);
+                        ccur[j] = cp[j];                                  // c_{t-1} is next iteration's c_t
+                    }
+                    if (bb == 0 && i >= 1) {                              // W of the previous step still reads d(gates)
+                        mbar_wait(&S.w_done, wphase & 1);
+                        ++wphase;
                     }
                     unsigned char* d4 = dgrow + (blk * 4) * kAChunk;
                     st_shared_v4(d4, pack_val(pi[0], pi[1]), pack_val(pi[2], pi[3]), pack_val(pi[4], pi[5]), pack_val(pi[6], pi[7]));
@@ -507,7 +528,7 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) { tc_fence_after(); tmem_free_all(tmem); }
+    if (warp == 9) { tc_fence_after(); tmem_free_all(tmem); }
 }
 
 // [W_ih | W_hh]^T as the B operand of R: out[chunk = n/8][o][n%8], n = permuted gate column (K index),
@@ -547,6 +568,17 @@ __global__ void reduce_dw_kernel(const float* __restrict__ partial, int nparts, 
     }
 }
 
+// Materialise the counter-based dropout mask (tests: the RNG mode must equal the mask-tensor mode bit for bit).
+__global__ void dropout_mask_kernel(uint64_t seed, uint32_t thresh16, int64_t rows, unsigned char* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;       // one (row, block) per thread
+    if (i >= rows * 6) return;
+    const uint32_t keep = dropout_keep8(seed, i / 6, (int)(i % 6), thresh16);
+    uint2 v;
+    v.x = ((keep >> 0) & 1u) | (((keep >> 1) & 1u) << 8) | (((keep >> 2) & 1u) << 16) | (((keep >> 3) & 1u) << 24);
+    v.y = ((keep >> 4) & 1u) | (((keep >> 5) & 1u) << 8) | (((keep >> 6) & 1u) << 16) | (((keep >> 7) & 1u) << 24);
+    reinterpret_cast<uint2*>(out)[i] = v;
+}
+
 static int tc_sms() {
     static int sms = 0;
     if (sms == 0) {
@@ -560,8 +592,8 @@ static int tc_sms() {
 
 template <int KI>
 static int launch_bwd(const void* act_in, const void* h, const float* c, const float* dh_out, const void* packed_g,
-                      const void* packed_r, const void* zeros, const unsigned char* mask, float scale, float* din,
-                      float* partial, int64_t T, int64_t Bp, cudaStream_t st, int* grid_out) {
+                      const void* packed_r, const void* zeros, const unsigned char* mask, uint64_t seed, uint32_t thresh16,
+                      float scale, float* din, float* partial, int64_t T, int64_t Bp, cudaStream_t st, int* grid_out) {
     const size_t smem = sizeof(BwdSmem<KI>) + 1024;
     auto kern = lstm_bwd_bf16_kernel<KI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -572,7 +604,8 @@ static int launch_bwd(const void* act_in, const void* h, const float* c, const f
     kern<<<grid, kBwdThreads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(act_in), reinterpret_cast<const __nv_bfloat16*>(h),
                                           c, dh_out, reinterpret_cast<const unsigned char*>(packed_g),
                                           reinterpret_cast<const unsigned char*>(packed_r),
-                                          reinterpret_cast<const __nv_bfloat16*>(zeros), mask, scale, din, partial, (int)T, Bp, ntiles);
+                                          reinterpret_cast<const __nv_bfloat16*>(zeros), mask, seed, thresh16, scale, din, partial,
+                                          (int)T, Bp, ntiles);
     count_launch();
     return check_launch("na_lstm_bwd_bf16");
 }
@@ -584,7 +617,7 @@ static int launch_bwd(const void* act_in, const void* h, const float* c, const f
 extern "C" int64_t na_train_bf16_partial_floats(void) { return (int64_t)148 * 2 * na::tc::kN * 112; }
 
 extern "C" int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packed, const unsigned char* mask,
-                                       float drop_scale, void* h0, void* h0d, float* c0, void* h1, float* h1f,
+                                       uint64_t seed, int64_t thresh16, float drop_scale, void* h0, void* h0d, float* c0, void* h1, float* h1f,
                                        float* c1, int64_t T, int64_t Bp, na_stream_t stream) {
     using namespace na;
     NA_REQUIRE(T >= 1 && T < (1 << 20) && Bp >= tc::kRows && Bp % tc::kRows == 0, NA_EINVAL,
@@ -592,23 +625,37 @@ extern "C" int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packe
     NA_REQUIRE_PTR(x_bf16_tmp); NA_REQUIRE_PTR(packed); NA_REQUIRE_PTR(h0); NA_REQUIRE_PTR(c0);
     NA_REQUIRE_PTR(h1); NA_REQUIRE_PTR(h1f); NA_REQUIRE_PTR(c1);
     NA_OPTIONAL_PTR(mask); NA_OPTIONAL_PTR(h0d);
-    NA_REQUIRE((mask == nullptr) == (h0d == nullptr), NA_EINVAL, "na_lstm2_fwd_train_bf16: mask and h0d go together");
+    NA_REQUIRE(thresh16 >= 0 && thresh16 <= 65536, NA_EINVAL, "na_lstm2_fwd_train_bf16: thresh16 outside [0,65536]");
+    NA_REQUIRE((mask != nullptr || thresh16 < 65536) == (h0d != nullptr), NA_EINVAL,
+               "na_lstm2_fwd_train_bf16: h0d must be given exactly when dropout is on (mask tensor or thresh16 < 65536)");
     const size_t smem = sizeof(tc::FwdSmem) + 1024;
     cudaError_t e = cudaFuncSetAttribute(tc::lstm2_fwd_train_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "na_lstm2_fwd_train_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
     const int ntiles = (int)(Bp / tc::kRows);
     const int grid = ntiles < tc::tc_sms() ? ntiles : tc::tc_sms();
     tc::lstm2_fwd_train_bf16_kernel<<<grid, tc::kTrainThreads, smem, as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x_bf16_tmp), reinterpret_cast<const unsigned char*>(packed), mask, drop_scale,
+        reinterpret_cast<const __nv_bfloat16*>(x_bf16_tmp), reinterpret_cast<const unsigned char*>(packed), mask, seed,
+        (uint32_t)thresh16, drop_scale,
         reinterpret_cast<__nv_bfloat16*>(h0), reinterpret_cast<__nv_bfloat16*>(h0d), c0, reinterpret_cast<__nv_bfloat16*>(h1),
         h1f, c1, (int)T, Bp, ntiles);
     count_launch();
     return check_launch("na_lstm2_fwd_train_bf16");
 }
 
+extern "C" int na_dropout_mask_u8(uint64_t seed, int64_t thresh16, int64_t T, int64_t Bp, unsigned char* out, na_stream_t stream) {
+    using namespace na;
+    NA_REQUIRE(T >= 1 && Bp >= 1 && thresh16 >= 0 && thresh16 <= 65536, NA_EINVAL, "na_dropout_mask_u8: bad arguments");
+    NA_REQUIRE_PTR(out);
+    const int64_t n = T * Bp * 6;
+    tc::dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(seed, (uint32_t)thresh16, T * Bp, out);
+    count_launch();
+    return check_launch("na_dropout_mask_u8");
+}
+
 extern "C" int na_lstm_bwd_bf16(int64_t layer, const void* act_in, const void* h, const float* cstate, const float* dh_out,
                                 const void* packed_fwd, const float* w_ih, const float* w_hh, const void* zeros,
-                                const unsigned char* in_mask, float drop_scale, float* din, float* dw_ih, float* dw_hh,
+                                const unsigned char* in_mask, uint64_t seed, int64_t thresh16, float drop_scale,
+                                float* din, float* dw_ih, float* dw_hh,
                                 float* db, void* scratch, int64_t T, int64_t Bp, na_stream_t stream) {
     using namespace na;
     NA_REQUIRE(layer == 0 || layer == 1, NA_EINVAL, "na_lstm_bwd_bf16: layer must be 0 or 1");
@@ -619,6 +666,7 @@ extern "C" int na_lstm_bwd_bf16(int64_t layer, const void* act_in, const void* h
     NA_REQUIRE_PTR(db); NA_REQUIRE_PTR(scratch);
     NA_OPTIONAL_PTR(in_mask); NA_OPTIONAL_PTR(din);
     NA_REQUIRE(layer == 0 || din != nullptr, NA_EINVAL, "na_lstm_bwd_bf16: layer 1 needs din");
+    NA_REQUIRE(thresh16 >= 0 && thresh16 <= 65536, NA_EINVAL, "na_lstm_bwd_bf16: thresh16 outside [0,65536]");
     cudaStream_t st = as_stream(stream);
     const int KI = layer == 0 ? 8 : 48;
     // scratch: [packed_r bf16: 24*96*8*2 B = 36,864 B][partials fp32]
@@ -630,9 +678,11 @@ extern "C" int na_lstm_bwd_bf16(int64_t layer, const void* act_in, const void* h
     const unsigned char* pg = reinterpret_cast<const unsigned char*>(packed_fwd) + (layer == 0 ? 0 : 8 * tc::kBChunk);
     int grid = 0, rc;
     if (layer == 0)
-        rc = tc::launch_bwd<8>(act_in, h, cstate, dh_out, pg, packed_r, zeros, nullptr, 1.0f, nullptr, partial, T, Bp, st, &grid);
+        rc = tc::launch_bwd<8>(act_in, h, cstate, dh_out, pg, packed_r, zeros, nullptr, 0, 65536u, 1.0f, nullptr, partial, T, Bp,
+                               st, &grid);
     else
-        rc = tc::launch_bwd<48>(act_in, h, cstate, dh_out, pg, packed_r, zeros, in_mask, drop_scale, din, partial, T, Bp, st, &grid);
+        rc = tc::launch_bwd<48>(act_in, h, cstate, dh_out, pg, packed_r, zeros, in_mask, seed, (uint32_t)thresh16, drop_scale, din,
+                                partial, T, Bp, st, &grid);
     if (rc) return rc;
     const int NW = layer == 0 ? 64 : 112;
     tc::reduce_dw_kernel<<<(tc::kN * NW + 255) / 256, 256, 0, st>>>(partial, grid, KI, dw_ih, dw_hh, db);

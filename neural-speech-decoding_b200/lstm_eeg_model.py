@@ -139,14 +139,15 @@ class EEG_LSTM(nn.Module):
         else:
             self._injected_noise = {"drop1": drop1, "rrelu": rrelu_slope, "drop2": drop2}
 
-    def _draw_noise(self, B: int, T: int, device, pad: int = ops.BATCH_ALIGN, mask_dtype=torch.float32):
+    def _draw_noise(self, B: int, T: int, device, pad: int = ops.BATCH_ALIGN, mask_dtype=torch.float32,
+                    skip_drop1: bool = False):
         """Train-mode noise as tensors (the kernels are deterministic functions of them): inter-layer
         dropout keep-masks (time-major padded, one per layer gap), RReLU slopes, head dropout mask."""
         p, L, H = self.dropout_p, self.lstm.num_layers, self.lstm.hidden_size
         Bp = ops.padded_batch(B, pad)
         inj = self._injected_noise or {}
         d1 = None
-        if L > 1 and self.lstm.dropout > 0.0:
+        if L > 1 and self.lstm.dropout > 0.0 and not skip_drop1:
             if inj.get("drop1") is not None:
                 m = inj["drop1"].to(device=device, dtype=mask_dtype)             # [L-1,B,T,H]
                 d1 = []
@@ -191,10 +192,18 @@ class EEG_LSTM(nn.Module):
                     or self.attn.weight.dtype == torch.bfloat16)
             if bf16 and self.tc_supported() and not x.requires_grad:
                 # tensor-core tier: tcgen05 forward + fused BPTT (bf16 operands, 2e-2 contract)
+                drop1 = None
                 if self.training:
-                    d1, rr, d2 = self._draw_noise(B, T, x.device, ops.TC_TILE, torch.uint8)
+                    injected = (self._injected_noise or {}).get("drop1") is not None
+                    d1, rr, d2 = self._draw_noise(B, T, x.device, ops.TC_TILE, torch.uint8, skip_drop1=not injected)
+                    if injected:
+                        drop1 = d1[0]
+                    elif self.lstm.dropout > 0.0:
+                        # no mask tensor: the kernels generate (and the backward re-generates) the keep-bits from
+                        # a counter-based hash; the seed comes from torch's CPU generator (torch.manual_seed)
+                        drop1 = (int(torch.randint(0, 2 ** 62, (1,)).item()), int(round((1.0 - self.dropout_p) * 65536)))
                 logits = ops.decoder_train_forward_tc(x, lstm_params, head, self.dropout_p, self.zscore_input,
-                                                      d1[0] if d1 is not None else None, rr, d2)
+                                                      drop1, rr, d2)
             else:
                 if self.training:
                     d1, rr, d2 = self._draw_noise(B, T, x.device)

@@ -63,7 +63,8 @@ def _stream() -> int:
 
 def all_custom_ops():
     return [window_zscore, pack_lstm_layer, lstm_layer_fwd, lstm_layer_bwd, lstm_layer_wgrad, head_fwd,
-            head_bwd, trial_mean, decoder_pack_bf16, decoder_infer_bf16, lstm2_fwd_train_bf16, lstm_bwd_bf16]
+            head_bwd, trial_mean, decoder_pack_bf16, decoder_infer_bf16, lstm2_fwd_train_bf16, lstm_bwd_bf16,
+            dropout_mask_u8]
 
 
 def launch_count() -> int:
@@ -435,34 +436,53 @@ def decoder_train_forward(x: Tensor, lstm_params, head_params, p: float, zscore:
 # tensor-core tier, training
 # ------------------------------------------------------------------------------------------
 @torch.library.custom_op("neuroalpha::lstm2_fwd_train_bf16", mutates_args=(), device_types="cuda")
-def lstm2_fwd_train_bf16(x_tmp: Tensor, packed: Tensor, mask: Optional[Tensor],
+def lstm2_fwd_train_bf16(x_tmp: Tensor, packed: Tensor, mask: Optional[Tensor], seed: int, thresh16: int,
                          drop_scale: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """Training forward of the 2-layer LSTM on tcgen05.  x_tmp bf16 TMP [T,Bp,8] (Bp % 128 == 0), mask u8
-    [T,Bp,48] or None -> (h0 TCL, h0d TCL or empty, c0 TMP, h1 TCL, h1f TMP, c1 TMP)."""
+    """Training forward of the 2-layer LSTM on tcgen05.  x_tmp fp16 TMP [T,Bp,8] (Bp % 128 == 0).
+    Inter-layer dropout: explicit ``mask`` u8 [T,Bp,48], or (mask None, thresh16 < 65536) the in-kernel
+    counter-based generator keyed by ``seed`` (keep probability thresh16/65536), or none (thresh16 = 65536).
+    -> (h0 TCL, h0d TCL or empty, c0 TMP, h1 TCL, h1f TMP, c1 TMP)."""
     _require_cuda(x_tmp, packed, mask)
     T, Bp, _ = x_tmp.shape
     dev = x_tmp.device
+    has_drop = mask is not None or thresh16 < 65536
     tcl = lambda: torch.empty((T, Bp // TC_TILE, 6, TC_TILE, 8), dtype=TC_VALUE_DTYPE, device=dev)
     tmp = lambda: torch.empty((T, Bp, 48), dtype=torch.float32, device=dev)
     h0, h1, c0, h1f, c1 = tcl(), tcl(), tmp(), tmp(), tmp()
-    h0d = tcl() if mask is not None else torch.empty((0,), dtype=TC_VALUE_DTYPE, device=dev)
-    _lib.call("na_lstm2_fwd_train_bf16", x_tmp.data_ptr(), packed.data_ptr(), _ptr(mask), float(drop_scale),
-              h0.data_ptr(), _ptr(h0d) if mask is not None else None, c0.data_ptr(), h1.data_ptr(), h1f.data_ptr(),
-              c1.data_ptr(), T, Bp, _stream())
+    h0d = tcl() if has_drop else torch.empty((0,), dtype=TC_VALUE_DTYPE, device=dev)
+    _lib.call("na_lstm2_fwd_train_bf16", x_tmp.data_ptr(), packed.data_ptr(), _ptr(mask), int(seed), int(thresh16),
+              float(drop_scale), h0.data_ptr(), _ptr(h0d) if has_drop else None, c0.data_ptr(), h1.data_ptr(),
+              h1f.data_ptr(), c1.data_ptr(), T, Bp, _stream())
     return h0, h0d, c0, h1, h1f, c1
 
 
 @lstm2_fwd_train_bf16.register_fake
-def _(x_tmp, packed, mask, drop_scale):
+def _(x_tmp, packed, mask, seed, thresh16, drop_scale):
     T, Bp, _ = x_tmp.shape
     tcl = lambda: x_tmp.new_empty((T, Bp // TC_TILE, 6, TC_TILE, 8))
     tmp = lambda: x_tmp.new_empty((T, Bp, 48), dtype=torch.float32)
-    return tcl(), (tcl() if mask is not None else x_tmp.new_empty((0,))), tmp(), tcl(), tmp(), tmp()
+    has_drop = mask is not None or thresh16 < 65536
+    return tcl(), (tcl() if has_drop else x_tmp.new_empty((0,))), tmp(), tcl(), tmp(), tmp()
+
+
+@torch.library.custom_op("neuroalpha::dropout_mask_u8", mutates_args=(), device_types="cuda")
+def dropout_mask_u8(like: Tensor, seed: int, thresh16: int, T: int, Bp: int) -> Tensor:
+    """The keep-mask the in-kernel generator produces for (seed, thresh16): u8 [T,Bp,48] on like.device."""
+    _require_cuda(like)
+    out = torch.empty((T, Bp, 48), dtype=torch.uint8, device=like.device)
+    _lib.call("na_dropout_mask_u8", int(seed), int(thresh16), T, Bp, out.data_ptr(), _stream())
+    return out
+
+
+@dropout_mask_u8.register_fake
+def _(like, seed, thresh16, T, Bp):
+    return like.new_empty((T, Bp, 48), dtype=torch.uint8)
 
 
 @torch.library.custom_op("neuroalpha::lstm_bwd_bf16", mutates_args=(), device_types="cuda")
 def lstm_bwd_bf16(layer: int, act_in: Tensor, h: Tensor, c: Tensor, dh: Tensor, packed: Tensor, w_ih: Tensor,
-                  w_hh: Tensor, in_mask: Optional[Tensor], drop_scale: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+                  w_hh: Tensor, in_mask: Optional[Tensor], seed: int, thresh16: int,
+                  drop_scale: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Fused BPTT + weight gradients of one layer on tcgen05 -> (din TMP or empty, dW_ih, dW_hh, db)."""
     _require_cuda(act_in, h, c, dh, packed, w_ih, w_hh, in_mask)
     T, Bp, H = c.shape
@@ -474,14 +494,15 @@ def lstm_bwd_bf16(layer: int, act_in: Tensor, h: Tensor, c: Tensor, dh: Tensor, 
     zeros = torch.zeros((12288,), dtype=torch.uint8, device=dev)
     scratch = torch.empty((36864 + 4 * _lib.query("na_train_bf16_partial_floats"),), dtype=torch.uint8, device=dev)
     _lib.call("na_lstm_bwd_bf16", int(layer), act_in.data_ptr(), h.data_ptr(), c.data_ptr(), _f32c(dh).data_ptr(),
-              packed.data_ptr(), w_ih.data_ptr(), w_hh.data_ptr(), zeros.data_ptr(), _ptr(in_mask), float(drop_scale),
+              packed.data_ptr(), w_ih.data_ptr(), w_hh.data_ptr(), zeros.data_ptr(), _ptr(in_mask), int(seed), int(thresh16),
+              float(drop_scale),
               _ptr(din) if layer == 1 else None, dw_ih.data_ptr(), dw_hh.data_ptr(), db.data_ptr(), scratch.data_ptr(),
               T, Bp, _stream())
     return din, dw_ih, dw_hh, db
 
 
 @lstm_bwd_bf16.register_fake
-def _(layer, act_in, h, c, dh, packed, w_ih, w_hh, in_mask, drop_scale):
+def _(layer, act_in, h, c, dh, packed, w_ih, w_hh, in_mask, seed, thresh16, drop_scale):
     return (c.new_empty(c.shape if layer == 1 else (0,)), w_ih.new_empty(w_ih.shape, dtype=torch.float32),
             w_hh.new_empty(w_hh.shape, dtype=torch.float32), c.new_empty((4 * c.shape[2],)))
 
@@ -492,26 +513,35 @@ class DecoderFunctionTC(torch.autograd.Function):
     (logits and gradients within 2e-2 of the fp32 reference)."""
 
     @staticmethod
-    def forward(ctx, x, p, zscore, drop1_mask_u8, rrelu_slope, drop2_mask, *params):
+    def forward(ctx, x, p, zscore, drop1, rrelu_slope, drop2_mask, *params):
+        """``drop1``: None (no inter-layer dropout), a u8 keep-mask [T,Bp,48], or ``(seed, thresh16)`` for the
+        in-kernel counter-based generator (no mask tensor at all)."""
         _require_cuda(x, *params)
         if ctx.needs_input_grad[0]:
             raise RuntimeError("the tensor-core training tier does not produce d/dx; use compute_dtype=float32")
         B, T, C = x.shape
         lstm_flat, head = [t.detach() for t in params[:8]], [_f32c(t.detach()) for t in params[8:]]
-        scale = 1.0 / (1.0 - p) if p < 1.0 else 0.0
+        scale = 1.0 / (1.0 - p) if p < 1.0 else 0.0          # head dropout (and mask-tensor mode)
+        mask, seed, thresh16, scale1 = None, 0, 65536, 1.0
+        if isinstance(drop1, tuple):
+            seed, thresh16 = int(drop1[0]), int(drop1[1])
+            scale1 = 65536.0 / thresh16 if thresh16 > 0 else 0.0   # exactly unbiased for the quantised keep-rate
+        elif drop1 is not None:
+            mask, scale1 = drop1, scale
         xt = window_zscore(x.detach(), T, T, zscore, True, NA_F16, TC_TILE)
         packed = decoder_pack_bf16(lstm_flat)
-        h0, h0d, c0, h1, h1f, c1 = lstm2_fwd_train_bf16(xt, packed, drop1_mask_u8, scale)
+        h0, h0d, c0, h1, h1f, c1 = lstm2_fwd_train_bf16(xt, packed, mask, seed, thresh16, scale1)
         logits, _, stats, zpool = head_fwd(h1f, B, head, rrelu_slope, drop2_mask, scale, False, True)
         w = [_f32c(t) for t in lstm_flat]
-        opt = [t for t in (drop1_mask_u8, rrelu_slope, drop2_mask) if t is not None]
+        opt = [t for t in (mask, rrelu_slope, drop2_mask) if t is not None]
         ctx.save_for_backward(xt, h0, h0d, c0, h1, h1f, c1, packed, stats, zpool, w[0], w[1], w[4], w[5], *head, *opt)
-        ctx.meta = (scale, B, drop1_mask_u8 is not None, rrelu_slope is not None, drop2_mask is not None)
+        ctx.meta = (scale, B, mask is not None, rrelu_slope is not None, drop2_mask is not None, seed, thresh16, scale1)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        scale, B, has_d1, has_rr, has_d2 = ctx.meta
+        scale, B, has_d1, has_rr, has_d2, seed, thresh16, scale1 = ctx.meta
+        has_drop = has_d1 or thresh16 < 65536
         sv = list(ctx.saved_tensors)
         xt, h0, h0d, c0, h1, h1f, c1, packed, stats, zpool, w_ih0, w_hh0, w_ih1, w_hh1 = sv[:14]
         head = sv[14:22]
@@ -528,14 +558,15 @@ class DecoderFunctionTC(torch.autograd.Function):
         inv_s = 1.0 / s
         dh1, dparams = head_bwd((dlogits * s).contiguous(), h1f, stats, zpool, head, rr, d2, scale)
         head_grads = split_head_grads(dparams * inv_s, H, NC)
-        din1, dw_ih1, dw_hh1, db1 = lstm_bwd_bf16(1, h0d if has_d1 else h0, h1, c1, dh1, packed, w_ih1, w_hh1, d1, scale)
-        _, dw_ih0, dw_hh0, db0 = lstm_bwd_bf16(0, xt, h0, c0, din1, packed, w_ih0, w_hh0, None, 1.0)
+        din1, dw_ih1, dw_hh1, db1 = lstm_bwd_bf16(1, h0d if has_drop else h0, h1, c1, dh1, packed, w_ih1, w_hh1, d1, seed,
+                                                  thresh16, scale1)
+        _, dw_ih0, dw_hh0, db0 = lstm_bwd_bf16(0, xt, h0, c0, din1, packed, w_ih0, w_hh0, None, 0, 65536, 1.0)
         db0, db1 = db0 * inv_s, db1 * inv_s
         return (None, None, None, None, None, None, dw_ih0 * inv_s, dw_hh0 * inv_s, db0, db0.clone(),
                 dw_ih1 * inv_s, dw_hh1 * inv_s, db1, db1.clone(), *head_grads)
 
 
 def decoder_train_forward_tc(x: Tensor, lstm_params, head_params, p: float, zscore: bool = False,
-                             drop1_mask_u8=None, rrelu_slope=None, drop2_mask=None) -> Tensor:
+                             drop1=None, rrelu_slope=None, drop2_mask=None) -> Tensor:
     flat = [t for layer in lstm_params for t in layer]
-    return DecoderFunctionTC.apply(x, p, zscore, drop1_mask_u8, rrelu_slope, drop2_mask, *flat, *head_params)
+    return DecoderFunctionTC.apply(x, p, zscore, drop1, rrelu_slope, drop2_mask, *flat, *head_params)
