@@ -253,10 +253,10 @@ def run_gpu_arm(args):
     reps = max(3, min(args.steps, 10))
     with torch.inference_mode():
         model.compute_dtype = torch.bfloat16
-        xt16 = ops.window_zscore(x_flat, T, T, False, True, True, ops.TC_TILE)
+        xt16 = ops.window_zscore(x_flat, T, T, False, True, ops.NA_F16, ops.TC_TILE)
         packed_tc, head = model._packed_tc(), model._head_params()
         ms_tc = time_steps(lambda: ops.decoder_infer_bf16(xt16, packed_tc, head, n_win, True), reps, 2, 1, dev) / reps
-        ms_pack16 = time_steps(lambda: ops.window_zscore(x_flat, T, T, False, True, True, ops.TC_TILE), reps, 2, 1, dev) / reps
+        ms_pack16 = time_steps(lambda: ops.window_zscore(x_flat, T, T, False, True, ops.NA_F16, ops.TC_TILE), reps, 2, 1, dev) / reps
         ms_z = time_steps(lambda: ops.window_zscore(x_flat, T, T, True, False, False), reps, 2, 1, dev) / reps
         del xt16
         packed = [model._packed(l) for l in range(2)]

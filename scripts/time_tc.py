@@ -19,8 +19,8 @@ def t(fn, reps=5):
 with torch.inference_mode():
     ms = t(lambda: m.decode(x))
     print(f"bf16 decode {N} windows: {ms:.3f} ms -> {N/ms*1e3/1e6:.3f} M windows/s")
-    xt = ops.window_zscore(x, 625, 625, False, True, True, 128)
+    xt = ops.window_zscore(x, 625, 625, False, True, 2, 128)
     packed = m._packed_tc(); head = m._head_params()
     ms_k = t(lambda: ops.decoder_infer_bf16(xt, packed, head, N, True))
-    ms_p = t(lambda: ops.window_zscore(x, 625, 625, False, True, True, 128))
+    ms_p = t(lambda: ops.window_zscore(x, 625, 625, False, True, 2, 128))
     print(f"  tcgen05 kernel alone {ms_k:.3f} ms ({ms_k*1e3/625/((N+128*148-1)//(128*148)):.3f} us per step per tile-round), pack kernel {ms_p:.3f} ms")
