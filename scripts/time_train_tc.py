@@ -31,8 +31,8 @@ with torch.no_grad():
     res = {}
     res['noise'] = t(lambda: m._draw_noise(B, T, dev, 128, torch.uint8))
     res['pack_x'] = t(lambda: ops.window_zscore(x, T, T, False, True, 2, 128))
-    res['fwd_train'] = t(lambda: ops.lstm2_fwd_train_bf16(xt, packed, mask, 2.5))
-    h0, h0d, c0, h1, h1f, c1 = ops.lstm2_fwd_train_bf16(xt, packed, mask, 2.5)
+    res['fwd_train'] = t(lambda: ops.lstm2_fwd_train_bf16(xt, packed, None, 1234, 26214, 2.5))
+    h0, h0d, c0, h1, h1f, c1 = ops.lstm2_fwd_train_bf16(xt, packed, None, 1234, 26214, 2.5)
     head = [p.detach() for p in m._head_params()]
     res['head_fwd'] = t(lambda: ops.head_fwd(h1f, B, head, None, None, 2.5, False, True))
     lg, _, st, zp = ops.head_fwd(h1f, B, head, None, None, 2.5, False, True)
@@ -40,9 +40,9 @@ with torch.no_grad():
     res['head_bwd'] = t(lambda: ops.head_bwd(dl * 1000, h1f, st, zp, head, None, None, 2.5))
     dh, _ = ops.head_bwd(dl * 1000, h1f, st, zp, head, None, None, 2.5)
     w1 = [p.detach() for p in m.lstm.layer(1)]; w0 = [p.detach() for p in m.lstm.layer(0)]
-    res['bwd_l1'] = t(lambda: ops.lstm_bwd_bf16(1, h0d, h1, c1, dh, packed, w1[0], w1[1], mask, 2.5))
-    din1 = ops.lstm_bwd_bf16(1, h0d, h1, c1, dh, packed, w1[0], w1[1], mask, 2.5)[0]
-    res['bwd_l0'] = t(lambda: ops.lstm_bwd_bf16(0, xt, h0, c0, din1, packed, w0[0], w0[1], None, 1.0))
+    res['bwd_l1'] = t(lambda: ops.lstm_bwd_bf16(1, h0d, h1, c1, dh, packed, w1[0], w1[1], None, 1234, 26214, 2.5))
+    din1 = ops.lstm_bwd_bf16(1, h0d, h1, c1, dh, packed, w1[0], w1[1], None, 1234, 26214, 2.5)[0]
+    res['bwd_l0'] = t(lambda: ops.lstm_bwd_bf16(0, xt, h0, c0, din1, packed, w0[0], w0[1], None, 0, 65536, 1.0))
 tot = sum(res.values())
 for k, v in res.items(): print(f"  {k:12s} {v:8.3f} ms  {100*v/tot:5.1f}%")
 print(f"  sum {tot:.2f} ms")

@@ -77,6 +77,8 @@ class FakeLib:
             out = win
         if out_dtype == 0:
             _arr(y, out.shape)[...] = out
+        elif out_dtype == 2:
+            _arr(y, out.shape, np.uint16)[...] = out.astype(np.float16).view(np.uint16)
         else:
             _arr(y, out.shape, np.uint16)[...] = _bf16_bits(out)
         self.launches += 1
