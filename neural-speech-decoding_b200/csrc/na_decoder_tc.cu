@@ -33,7 +33,7 @@ namespace tc {
 constexpr int kXStages = 4;
 constexpr int kK0Chunks = 8;                 // layer 0: x | ones | h0 x6
 constexpr int kK1Chunks = 14;                // layer 1: h0 x6 | h1 x6 | ones | zero
-constexpr int kThreads = 320;
+constexpr int kThreads = 320;            // HS = 1; HS = 2 runs (16 + 2) warps = 576 threads
 constexpr int kFc = NA_FC_HIDDEN;
 
 struct HeadSmem {
@@ -56,6 +56,10 @@ struct Smem {
     alignas(8) uint64_t x_full[kXStages], x_empty[kXStages];
     uint64_t d0_full, d1_full, h0_ready[2], h0_free[2], h1_ready;
     uint32_t tmem_base;
+    // HS == 2 only: the two half-row warps of a quarter exchange their partial attention scores every
+    // step (double-buffered by step parity) and their pooled halves once per tile
+    float score_part[2][2][kRows];
+    float zx[kRows][kH / 2];
 };
 
 // ---- weight packing ----------------------------------------------------------------------------
@@ -94,7 +98,11 @@ __global__ void pack_decoder_bf16_kernel(const float* __restrict__ w_ih0, const 
 }
 
 // ---- the fused decoder kernel --------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
+// HS = number of epilogue warps per TMEM lane quarter and layer: each handles 6/HS unit blocks of its
+// 32 windows.  HS = 2 doubles the warps per scheduler (4 instead of 2), which hides the
+// tcgen05.ld / MUFU dependency latency that leaves the xu pipe at ~72 % with HS = 1.
+template <int HS>
+__global__ void __launch_bounds__((8 * HS + 2) * 32, 1)
 decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][Bp][8] bf16
                           const unsigned char* __restrict__ packed,   // B0 | B1 (pack_decoder_bf16_kernel)
                           const float* __restrict__ attn_w, const float* __restrict__ attn_b,
@@ -103,6 +111,8 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                           const float* __restrict__ fc3_w, const float* __restrict__ fc3_b,
                           float* __restrict__ logits, float* __restrict__ probs,
                           int T, int64_t B, int64_t Bp, int NC, int nquarters) {
+    constexpr int kThreads = (8 * HS + 2) * 32;       // shadows the namespace constant inside the kernel
+    constexpr int kMmaWarp = 8 * HS, kTmaWarp = 8 * HS + 1, kNB = 6 / HS;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -130,12 +140,12 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
             S.head.ba = attn_b[0];
             for (int s = 0; s < kXStages; ++s) { mbar_init(&S.x_full[s], 1); mbar_init(&S.x_empty[s], 1); }
             mbar_init(&S.d0_full, 1); mbar_init(&S.d1_full, 1);
-            mbar_init(&S.h0_ready[0], 128); mbar_init(&S.h0_ready[1], 128);
+            mbar_init(&S.h0_ready[0], 128 * HS); mbar_init(&S.h0_ready[1], 128 * HS);
             mbar_init(&S.h0_free[0], 1); mbar_init(&S.h0_free[1], 1);
-            mbar_init(&S.h1_ready, 128);
+            mbar_init(&S.h1_ready, 128 * HS);
             fence_mbar_init();
         }
-        if (warp == 9) {
+        if (warp == kTmaWarp) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
                          "r"(kTmemCols)
                          : "memory");
@@ -169,7 +179,7 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
             __syncthreads();
         }
 
-        if (warp == 9) {
+        if (warp == kTmaWarp) {
             // ================= TMA producer ==========================================================
             if (lane == 0) {
                 for (int t = 0; t < T; ++t) {
@@ -179,7 +189,7 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                     bulk_load(S.x[s], x + ((int64_t)t * Bp + b0) * 8, x_bytes, &S.x_full[s]);
                 }
             }
-        } else if (warp == 8) {
+        } else if (warp == kMmaWarp) {
             // ================= MMA issuer ============================================================
             if (lane == 0) {
                 const uint32_t b0a = smem_u32(S.b0), b1a = smem_u32(S.b1);
@@ -219,14 +229,15 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                     }
                 }
             }
-        } else if (warp < 4) {
-            // ================= layer-0 epilogue: gates -> c, h0 (bf16) ================================
-            const int row = warp * 32 + lane;
-            const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-            float c[kH];
+        } else if (warp < 4 * HS) {
+            // ================= layer-0 epilogue: gates -> c, h0 (fp16) ================================
+            const int q = warp & 3, hf = warp >> 2;
+            const int row = q * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+            float c[8 * kNB];
 #pragma unroll
-            for (int j = 0; j < kH; ++j) c[j] = 0.f;
-            if (warp >= nq) {                              // idle quarter: keep the barrier protocol only
+            for (int j = 0; j < 8 * kNB; ++j) c[j] = 0.f;
+            if (q >= nq) {                                 // idle quarter: keep the barrier protocol only
                 for (int t = 0; t < T; ++t) {
                     const int n = n0 + t;
                     mbar_wait(&S.d0_full, n & 1);
@@ -240,10 +251,11 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                 tc_fence_after();
                 unsigned char* dst = S.h0[n & 1] + row * 16;
 #pragma unroll
-                for (int blk = 0; blk < 6; ++blk) {
+                for (int bb = 0; bb < kNB; ++bb) {
+                    const int blk = hf * kNB + bb;
                     uint32_t v[32], hp[4];
                     tmem_ld32(tmem_d0 + lane_base + blk * 32, v);
-                    cell_block(v, c + blk * 8, hp);
+                    cell_block(v, c + bb * 8, hp);
                     st_shared_v4(dst + blk * kAChunk, hp[0], hp[1], hp[2], hp[3]);
                 }
                 tc_fence_before();
@@ -252,12 +264,13 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
             }
         } else {
             // ================= layer-1 epilogue: gates -> c, h1; attention pooling; head ================
-            const int q = warp - 4;
+            const int q = (warp - 4 * HS) & 3, hf = (warp - 4 * HS) >> 2;
             const int row = q * 32 + lane;
             const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-            float c[kH], z[kH];
+            constexpr int kU = 8 * kNB;                    // units owned by this thread
+            float c[kU], z[kU];
 #pragma unroll
-            for (int j = 0; j < kH; ++j) { c[j] = 0.f; z[j] = 0.f; }
+            for (int j = 0; j < kU; ++j) { c[j] = 0.f; z[j] = 0.f; }
             float mx = -INFINITY, l = 0.f;
             const float ba = S.head.ba;
             if (q >= nq) {                                 // idle quarter
@@ -272,17 +285,18 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                 mbar_wait(&S.d1_full, m & 1);
                 tc_fence_after();
                 unsigned char* dst = S.h1 + row * 16;
-                uint32_t hb[24];
-                float score = ba;
+                uint32_t hb[4 * kNB];
+                float score = 0.f;
 #pragma unroll
-                for (int blk = 0; blk < 6; ++blk) {
+                for (int bb = 0; bb < kNB; ++bb) {
+                    const int blk = hf * kNB + bb;
                     uint32_t v[32], hp[4];
                     tmem_ld32(tmem_d1 + lane_base + blk * 32, v);
-                    cell_block(v, c + blk * 8, hp);
+                    cell_block(v, c + bb * 8, hp);
                     st_shared_v4(dst + blk * kAChunk, hp[0], hp[1], hp[2], hp[3]);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        hb[blk * 4 + u] = hp[u];
+                        hb[bb * 4 + u] = hp[u];
                         score = fmaf(val_lo(hp[u]), S.head.wa[blk * 8 + 2 * u], score);
                         score = fmaf(val_hi(hp[u]), S.head.wa[blk * 8 + 2 * u + 1], score);
                     }
@@ -290,42 +304,62 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                 tc_fence_before();
                 fence_proxy_async_smem();
                 mbar_arrive(&S.h1_ready);
+                if (HS == 2) {                             // total score = half 0 + half 1 (fixed order)
+                    S.score_part[t & 1][hf][row] = score;
+                    named_bar_sync(1 + q, 64);
+                    score = S.score_part[t & 1][0][row] + S.score_part[t & 1][1][row];
+                }
+                score += ba;
                 // online softmax over time (lstm_eeg_model.py:35-37), lazy rescale
                 if (score > mx) {
                     const float sc = __expf(mx - score);
                     l *= sc;
 #pragma unroll
-                    for (int j = 0; j < kH; ++j) z[j] *= sc;
+                    for (int j = 0; j < kU; ++j) z[j] *= sc;
                     mx = score;
                 }
                 const float e = __expf(score - mx);
                 l += e;
 #pragma unroll
-                for (int u = 0; u < 24; ++u) {
+                for (int u = 0; u < 4 * kNB; ++u) {
                     z[2 * u] = fmaf(e, val_lo(hb[u]), z[2 * u]);
                     z[2 * u + 1] = fmaf(e, val_hi(hb[u]), z[2 * u + 1]);
                 }
             }
-            // ---- head for this thread's window: LN -> fc0 -> RReLU(eval) -> fc3 -> softmax ----------
+            // ---- head for this window: LN -> fc0 -> RReLU(eval) -> fc3 -> softmax -------------------------
+            float zf[kH];
+            if (HS == 2) {                                 // half 1 hands its pooled half to half 0
+                if (hf == 1) {
+#pragma unroll
+                    for (int j = 0; j < kU; ++j) S.zx[row][j] = z[j];
+                }
+                named_bar_sync(1 + q, 64);
+#pragma unroll
+                for (int j = 0; j < kU; ++j) { zf[j] = z[j]; zf[kU + j] = S.zx[row][j]; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kU; ++j) zf[j] = z[j];
+            }
+            if (hf == 0) {
             const int64_t b = b0 + row;
             const float inv_l = 1.0f / l;
             float mean = 0.f;
 #pragma unroll
-            for (int j = 0; j < kH; ++j) { z[j] *= inv_l; mean += z[j]; }
+            for (int j = 0; j < kH; ++j) { zf[j] *= inv_l; mean += zf[j]; }
             mean *= (1.0f / kH);
             float var = 0.f;
 #pragma unroll
-            for (int j = 0; j < kH; ++j) { const float d = z[j] - mean; var = fmaf(d, d, var); }
+            for (int j = 0; j < kH; ++j) { const float d = zf[j] - mean; var = fmaf(d, d, var); }
             const float rstd = rsqrtf(var * (1.0f / kH) + kLnEps);
 #pragma unroll
-            for (int j = 0; j < kH; ++j) z[j] = fmaf((z[j] - mean) * rstd, S.head.lnw[j], S.head.lnb[j]);
+            for (int j = 0; j < kH; ++j) zf[j] = fmaf((zf[j] - mean) * rstd, S.head.lnw[j], S.head.lnb[j]);
             float lg[NA_MAX_CLASSES];
 #pragma unroll
             for (int k = 0; k < NA_MAX_CLASSES; ++k) lg[k] = (k < NC) ? S.head.b3[k] : -INFINITY;
             for (int o = 0; o < kFc; ++o) {
                 float a = S.head.b0[o];
 #pragma unroll
-                for (int j = 0; j < kH; ++j) a = fmaf(S.head.w0[o * kH + j], z[j], a);
+                for (int j = 0; j < kH; ++j) a = fmaf(S.head.w0[o * kH + j], zf[j], a);
                 a = a >= 0.f ? a : a * kRReluEvalSlope;
 #pragma unroll
                 for (int k = 0; k < NA_MAX_CLASSES; ++k)
@@ -346,17 +380,21 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                     }
             }
             }
+            }
         }
         __syncthreads();       // tile done: every MMA has completed (layer-1 epilogue saw the last d1_full)
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == kTmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
     }
 }
+
+int g_infer_hs = 2;      // epilogue warps per quarter and layer (na_set_tuning("tc_infer_hs", 1|2))
+void set_infer_hs(int hs) { g_infer_hs = hs == 1 ? 1 : 2; }
 
 }  // namespace tc
 }  // namespace na
@@ -399,14 +437,21 @@ extern "C" int na_decoder_infer_bf16(const void* x_bf16_tmp, const void* packed,
         if (sms <= 0) sms = 148;
     }
     const size_t smem = sizeof(tc::Smem) + 1024;
-    cudaError_t e = cudaFuncSetAttribute(tc::decoder_infer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int hs = tc::g_infer_hs;
+    cudaError_t e = hs == 2 ? cudaFuncSetAttribute(tc::decoder_infer_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(tc::decoder_infer_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
     const int nquarters = (int)((B + 31) / 32);            // padding quarters beyond B are never scheduled
     const int ntiles = (nquarters + 3) / 4;
     const int grid = ntiles < sms ? ntiles : sms;
-    tc::decoder_infer_bf16_kernel<<<grid, tc::kThreads, smem, as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x_bf16_tmp), reinterpret_cast<const unsigned char*>(packed), attn_w, attn_b,
-        ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, (int)T, B, Bp, (int)NC, nquarters);
+    if (hs == 2)
+        tc::decoder_infer_bf16_kernel<2><<<grid, 18 * 32, smem, as_stream(stream)>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x_bf16_tmp), reinterpret_cast<const unsigned char*>(packed), attn_w, attn_b,
+            ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, (int)T, B, Bp, (int)NC, nquarters);
+    else
+        tc::decoder_infer_bf16_kernel<1><<<grid, 10 * 32, smem, as_stream(stream)>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x_bf16_tmp), reinterpret_cast<const unsigned char*>(packed), attn_w, attn_b,
+            ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, (int)T, B, Bp, (int)NC, nquarters);
     count_launch();
     return check_launch("na_decoder_infer_bf16");
 }
