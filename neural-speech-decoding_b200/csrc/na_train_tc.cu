@@ -23,7 +23,7 @@
 namespace na {
 namespace tc {
 
-constexpr int kTrainThreads = 320;     // forward: 4 + 4 epilogue warps, MMA warp, TMA warp
+constexpr int kTrainThreads = 576;     // forward: 8 + 8 epilogue warps (2 per TMEM quarter and layer), MMA warp, TMA warp
 constexpr int kBwdThreads = 320;       // backward: 8 epilogue warps (2 per TMEM lane quarter), MMA warp, TMA warp
 constexpr int kXStagesT = 4;
 
@@ -86,12 +86,12 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
         if (tid == 0) {
             for (int s = 0; s < kXStagesT; ++s) { mbar_init(&S.x_full[s], 1); mbar_init(&S.x_empty[s], 1); }
             mbar_init(&S.d0_full, 1); mbar_init(&S.d1_full, 1);
-            mbar_init(&S.h0_ready[0], 128); mbar_init(&S.h0_ready[1], 128);
+            mbar_init(&S.h0_ready[0], 256); mbar_init(&S.h0_ready[1], 256);
             mbar_init(&S.h0_free[0], 1); mbar_init(&S.h0_free[1], 1);
-            mbar_init(&S.h1_ready, 128);
+            mbar_init(&S.h1_ready, 256);
             fence_mbar_init();
         }
-        if (warp == 9) tmem_alloc_all(&S.tmem_base);
+        if (warp == 17) tmem_alloc_all(&S.tmem_base);
         tc_fence_before();
         fence_proxy_async_smem();
         __syncthreads();
@@ -110,7 +110,7 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
             fence_proxy_async_smem();
             __syncthreads();
         }
-        if (warp == 9) {
+        if (warp == 17) {
             if (lane == 0)
                 for (int t = 0; t < T; ++t) {
                     const int n = n0 + t, s = n % kXStagesT, u = n / kXStagesT;
@@ -118,7 +118,7 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                     mbar_arrive_expect_tx(&S.x_full[s], kAChunk);
                     bulk_load(S.x[s], x + ((int64_t)t * Bp + b0) * 8, kAChunk, &S.x_full[s]);
                 }
-        } else if (warp == 8) {
+        } else if (warp == 16) {
             if (lane == 0) {
                 const uint32_t b0a = smem_u32(S.b0), b1a = smem_u32(S.b1);
                 for (int t = 0; t <= T; ++t) {
@@ -157,23 +157,26 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                     }
                 }
             }
-        } else if (warp < 4) {
-            // ---- layer-0 epilogue --------------------------------------------------------------------
-            const int row = warp * 32 + lane;
-            const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-            float c[kH];
+        } else if (warp < 8) {
+            // ---- layer-0 epilogue: thread = window x half of the units (3 blocks of 8) -----------------
+            const int q = warp & 3, hf = warp >> 2;
+            const int row = q * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+            float c[24];
 #pragma unroll
-            for (int j = 0; j < kH; ++j) c[j] = 0.f;
+            for (int j = 0; j < 24; ++j) c[j] = 0.f;
             for (int t = 0; t < T; ++t) {
                 const int n = n0 + t;
                 const int64_t grow = (int64_t)t * Bp + b0 + row;                 // TMP row
                 const int64_t tcl = ((int64_t)t * ntiles + tile) * 6 * (kAChunk / 2) + row * 8;   // TCL element offset of chunk 0
-                uint32_t keep[6];
+                uint32_t keep[3];
                 if (drop) {
 #pragma unroll
-                    for (int blk = 0; blk < 6; ++blk)
-                        keep[blk] = mask ? mask_keep8(*reinterpret_cast<const uint2*>(mask + grow * kH + blk * 8))
-                                         : dropout_keep8(seed, grow, blk, thresh16);
+                    for (int bb = 0; bb < 3; ++bb) {
+                        const int blk = hf * 3 + bb;
+                        keep[bb] = mask ? mask_keep8(*reinterpret_cast<const uint2*>(mask + grow * kH + blk * 8))
+                                        : dropout_keep8(seed, grow, blk, thresh16);
+                    }
                 }
                 mbar_wait(&S.d0_full, n & 1);
                 mbar_wait(&S.h0_free[n & 1], ((n >> 1) & 1) ^ 1);
@@ -181,21 +184,22 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                 unsigned char* dst = S.h0[n & 1] + row * 16;
                 unsigned char* dstd = S.h0d[n & 1] + row * 16;
 #pragma unroll
-                for (int blk = 0; blk < 6; ++blk) {
+                for (int bb = 0; bb < 3; ++bb) {
+                    const int blk = hf * 3 + bb;
                     uint32_t v[32];
                     float h[8];
                     tmem_ld32(tmem_d0 + lane_base + blk * 32, v);
-                    cell_block_f(v, c + blk * 8, h);
+                    cell_block_f(v, c + bb * 8, h);
                     const uint32_t p0 = pack_val(h[0], h[1]), p1 = pack_val(h[2], h[3]);
                     const uint32_t p2 = pack_val(h[4], h[5]), p3 = pack_val(h[6], h[7]);
                     st_shared_v4(dst + blk * kAChunk, p0, p1, p2, p3);
                     *reinterpret_cast<uint4*>(h0_out + tcl + blk * (kAChunk / 2)) = make_uint4(p0, p1, p2, p3);
-                    st_global_v4f(c0_out + grow * kH + blk * 8, c[blk * 8], c[blk * 8 + 1], c[blk * 8 + 2], c[blk * 8 + 3]);
-                    st_global_v4f(c0_out + grow * kH + blk * 8 + 4, c[blk * 8 + 4], c[blk * 8 + 5], c[blk * 8 + 6], c[blk * 8 + 7]);
+                    st_global_v4f(c0_out + grow * kH + blk * 8, c[bb * 8], c[bb * 8 + 1], c[bb * 8 + 2], c[bb * 8 + 3]);
+                    st_global_v4f(c0_out + grow * kH + blk * 8 + 4, c[bb * 8 + 4], c[bb * 8 + 5], c[bb * 8 + 6], c[bb * 8 + 7]);
                     if (drop) {
                         float hd[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) hd[u] = ((keep[blk] >> u) & 1u) ? h[u] * drop_scale : 0.f;
+                        for (int u = 0; u < 8; ++u) hd[u] = ((keep[bb] >> u) & 1u) ? h[u] * drop_scale : 0.f;
                         const uint32_t q0 = pack_val(hd[0], hd[1]), q1 = pack_val(hd[2], hd[3]);
                         const uint32_t q2 = pack_val(hd[4], hd[5]), q3 = pack_val(hd[6], hd[7]);
                         st_shared_v4(dstd + blk * kAChunk, q0, q1, q2, q3);
@@ -208,12 +212,12 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
             }
         } else {
             // ---- layer-1 epilogue --------------------------------------------------------------------
-            const int q = warp - 4;
+            const int q = (warp - 8) & 3, hf = (warp - 8) >> 2;
             const int row = q * 32 + lane;
             const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-            float c[kH];
+            float c[24];
 #pragma unroll
-            for (int j = 0; j < kH; ++j) c[j] = 0.f;
+            for (int j = 0; j < 24; ++j) c[j] = 0.f;
             for (int t = 0; t < T; ++t) {
                 const int m = n0 + t;
                 const int64_t grow = (int64_t)t * Bp + b0 + row;
@@ -222,19 +226,20 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                 tc_fence_after();
                 unsigned char* dst = S.h1 + row * 16;
 #pragma unroll
-                for (int blk = 0; blk < 6; ++blk) {
+                for (int bb = 0; bb < 3; ++bb) {
+                    const int blk = hf * 3 + bb;
                     uint32_t v[32];
                     float h[8];
                     tmem_ld32(tmem_d1 + lane_base + blk * 32, v);
-                    cell_block_f(v, c + blk * 8, h);
+                    cell_block_f(v, c + bb * 8, h);
                     const uint32_t p0 = pack_val(h[0], h[1]), p1 = pack_val(h[2], h[3]);
                     const uint32_t p2 = pack_val(h[4], h[5]), p3 = pack_val(h[6], h[7]);
                     st_shared_v4(dst + blk * kAChunk, p0, p1, p2, p3);
                     *reinterpret_cast<uint4*>(h1_out + tcl + blk * (kAChunk / 2)) = make_uint4(p0, p1, p2, p3);
                     st_global_v4f(h1f_out + grow * kH + blk * 8, h[0], h[1], h[2], h[3]);
                     st_global_v4f(h1f_out + grow * kH + blk * 8 + 4, h[4], h[5], h[6], h[7]);
-                    st_global_v4f(c1_out + grow * kH + blk * 8, c[blk * 8], c[blk * 8 + 1], c[blk * 8 + 2], c[blk * 8 + 3]);
-                    st_global_v4f(c1_out + grow * kH + blk * 8 + 4, c[blk * 8 + 4], c[blk * 8 + 5], c[blk * 8 + 6], c[blk * 8 + 7]);
+                    st_global_v4f(c1_out + grow * kH + blk * 8, c[bb * 8], c[bb * 8 + 1], c[bb * 8 + 2], c[bb * 8 + 3]);
+                    st_global_v4f(c1_out + grow * kH + blk * 8 + 4, c[bb * 8 + 4], c[bb * 8 + 5], c[bb * 8 + 6], c[bb * 8 + 7]);
                 }
                 tc_fence_before();
                 fence_proxy_async_smem();
@@ -245,7 +250,7 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) { tc_fence_after(); tmem_free_all(tmem); }
+    if (warp == 17) { tc_fence_after(); tmem_free_all(tmem); }
 }
 
 // =================================================================================================
