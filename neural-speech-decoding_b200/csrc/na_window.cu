@@ -112,6 +112,87 @@ window_zscore_vec_kernel(const float* __restrict__ x, void* __restrict__ y, int6
     }
 }
 
+// 16-bit time-major (TMP) output for C = 8: the input format of the tensor-core tier.  One window-row is
+// only 16 B there, so a CTA-per-window kernel would scatter 16-B pieces Bp*16 B apart (half-filled
+// sectors; measured 0.39 of HBM peak).  Here a CTA takes 8 consecutive windows, transposes them through
+// shared memory and writes 128-B contiguous runs [t][b0..b0+7][8 x 16 bit].
+constexpr int kPackWin = 8;
+template <int VPT>
+__global__ void __launch_bounds__(kWinThreads)
+window_pack16_tmp_kernel(const float* __restrict__ x, void* __restrict__ y, int64_t B, int64_t T, int64_t hop,
+                         int normalize, int64_t Bp, int out_dtype) {
+    extern __shared__ uint2 tile[];                      // [T][kPackWin] : 4 x 16-bit per entry half ... see below
+    // tile layout: uint4 per (t, w) = 8 channels x 16 bit; stored as two uint2 halves (cq = 0, 1)
+    __shared__ float4 scratch[2][(kWinThreads / 32) * 2];
+    const int tid = threadIdx.x;
+    const int64_t b0 = (int64_t)blockIdx.x * kPackWin;
+    const int64_t nvec = T * 2;
+    for (int w = 0; w < kPackWin; ++w) {
+        const int64_t b = b0 + w;
+        float4 v[VPT];
+        if (b < B) {                                      // block-uniform
+            const float4* src = reinterpret_cast<const float4*>(x + b * hop * 8);
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) {
+                const int64_t i = tid + (int64_t)k * kWinThreads;
+                v[k] = (i < nvec) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (normalize) {
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) s = f4add(s, v[k]);
+                __syncthreads();                          // scratch re-use across windows
+                s = class_sum<2>(s, scratch[0]);
+                const float fT = (float)T;
+                const float4 mu = make_float4(s.x / fT, s.y / fT, s.z / fT, s.w / fT);
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) {
+                    const int64_t i = tid + (int64_t)k * kWinThreads;
+                    if (i < nvec) {
+                        v[k] = make_float4(v[k].x - mu.x, v[k].y - mu.y, v[k].z - mu.z, v[k].w - mu.w);
+                        q.x = fmaf(v[k].x, v[k].x, q.x); q.y = fmaf(v[k].y, v[k].y, q.y);
+                        q.z = fmaf(v[k].z, v[k].z, q.z); q.w = fmaf(v[k].w, v[k].w, q.w);
+                    }
+                }
+                q = class_sum<2>(q, scratch[1]);
+                const float4 sg = make_float4(sqrtf(q.x / fT) + 1e-6f, sqrtf(q.y / fT) + 1e-6f,
+                                              sqrtf(q.z / fT) + 1e-6f, sqrtf(q.w / fT) + 1e-6f);
+#pragma unroll
+                for (int k = 0; k < VPT; ++k)
+                    v[k] = make_float4(v[k].x / sg.x, v[k].y / sg.y, v[k].z / sg.z, v[k].w / sg.w);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+            const int64_t i = tid + (int64_t)k * kWinThreads;      // i = t*2 + cq
+            if (i < nvec) {
+                uint2 p;
+                if (out_dtype == NA_F16) {
+                    __half2 lo = __floats2half2_rn(v[k].x, v[k].y), hi = __floats2half2_rn(v[k].z, v[k].w);
+                    p.x = *reinterpret_cast<uint32_t*>(&lo); p.y = *reinterpret_cast<uint32_t*>(&hi);
+                } else {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(v[k].x, v[k].y), hi = __floats2bfloat162_rn(v[k].z, v[k].w);
+                    p.x = *reinterpret_cast<uint32_t*>(&lo); p.y = *reinterpret_cast<uint32_t*>(&hi);
+                }
+                const int64_t t = i >> 1, cq = i & 1;
+                tile[(t * kPackWin + w) * 2 + cq] = p;
+            }
+        }
+    }
+    __syncthreads();
+    // write-out: for each t, 8 windows x 16 B = 128 B contiguous in the TMP layout
+    const uint4* tile4 = reinterpret_cast<const uint4*>(tile);
+    uint4* out = reinterpret_cast<uint4*>(y);
+    for (int64_t idx = tid; idx < T * kPackWin; idx += kWinThreads) {
+        const int64_t t = idx / kPackWin, w = idx % kPackWin;
+        out[t * Bp + b0 + w] = tile4[idx];
+    }
+}
+
 // Generic path: any T, any C <= 256.  Three passes over the window (the re-reads hit L1/L2).
 __global__ void __launch_bounds__(kWinThreads)
 window_zscore_generic_kernel(const float* __restrict__ x, void* __restrict__ y, int64_t B, int64_t T,
@@ -191,7 +272,16 @@ extern "C" int na_window_zscore(const float* x, void* y, int64_t B, int64_t T, i
     const dim3 grid((unsigned)Bp), block(kWinThreads);
     const int64_t nvec = (C % 4 == 0) ? T * (C / 4) : 0;
     const bool hop_ok = ((hop * C) % 4) == 0;   // every window start stays 16-byte aligned
-    if (C == 8 && hop_ok && nvec <= 5 * kWinThreads) {
+    if (C == 8 && hop_ok && out_tmp && out_dtype != NA_F32 && Bp % kPackWin == 0 && nvec <= 5 * kWinThreads &&
+        (size_t)T * kPackWin * 16 <= 200 * 1024) {
+        const size_t smem = (size_t)T * kPackWin * 16;
+        static bool opted = false;
+        if (!opted) {
+            cudaFuncSetAttribute(window_pack16_tmp_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            opted = true;
+        }
+        window_pack16_tmp_kernel<5><<<(unsigned)(Bp / kPackWin), block, smem, st>>>(x, y, B, T, hop, normalize, Bp, out_dtype);
+    } else if (C == 8 && hop_ok && nvec <= 5 * kWinThreads) {
         window_zscore_vec_kernel<2, 5><<<grid, block, 0, st>>>(x, y, B, T, hop, normalize, out_tmp, Bp, out_dtype);
     } else if (C == 8 && hop_ok && nvec <= 20 * kWinThreads) {
         window_zscore_vec_kernel<2, 20><<<grid, block, 0, st>>>(x, y, B, T, hop, normalize, out_tmp, Bp, out_dtype);

@@ -390,3 +390,17 @@ def test_h48_tier_vs_generic_tier(dev, checkpoint, groups):
         _lib.call("na_set_tuning", b"lstm_tier", 0)
         _lib.call("na_set_tuning", b"h48_groups", 0)
     assert rel(outs[0], outs[1]) < FP32_TOL
+
+
+def test_pack16_time_major_matches_row_major(dev, windows):
+    """16-bit time-major pack (shared-memory transposed, input of the tensor-core tier) == the row-major
+    16-bit output of the plain kernel, for both 16-bit formats, with and without z-score, ragged B."""
+    from neural_speech_decoding_b200 import ops
+    X = torch.from_numpy(windows["X"][:77]).to(dev)
+    for fmt in (1, 2):
+        for norm in (False, True):
+            rm = ops.window_zscore(X, 625, 625, norm, False, fmt)                 # [B,T,C]
+            tm = ops.window_zscore(X, 625, 625, norm, True, fmt, 128)             # [T,Bp,C]
+            assert tm.shape == (625, 128, 8) and tm.dtype == rm.dtype
+            assert torch.equal(tm[:, :77].permute(1, 0, 2), rm)
+            assert tm[:, 77:].float().abs().sum().item() == 0
