@@ -554,7 +554,7 @@ class DecoderFunctionTC(torch.autograd.Function):
         # scaled by a power of two (exact) that puts max|dlogits| at 2^11; every gradient is unscaled by the
         # same power at the end.  All on the device, no host sync.
         amax = dlogits.detach().abs().max().clamp_min(1e-30)
-        s = torch.exp2(11.0 - torch.ceil(torch.log2(amax)))
+        s = torch.pow(2.0, 11.0 - torch.ceil(torch.log2(amax)))      # (torch.exp2 would JIT-compile via nvrtc)
         inv_s = 1.0 / s
         dh1, dparams = head_bwd((dlogits * s).contiguous(), h1f, stats, zpool, head, rr, d2, scale)
         head_grads = split_head_grads(dparams * inv_s, H, NC)
