@@ -46,6 +46,13 @@ __device__ __forceinline__ void st_global_v4f(float* p, float a, float b, float 
     *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
 
+// TCL32: fp32 tile-chunk layout [T][Bp/128][12][128][4] for per-window-row tensors the epilogue threads
+// (thread = window) read and write 16 bytes at a time: lanes of a warp touch 32 consecutive 16-B pieces
+// (fully coalesced) instead of 16 B out of every 192-B row.  Used for c0, c1 and din.
+__device__ __forceinline__ int64_t tcl32_off(int t, int ntiles, int tile, int chunk, int row) {
+    return (((((int64_t)t * ntiles + tile) * 12 + chunk) * kRows) + row) * 4;
+}
+
 // =================================================================================================
 // forward (training): x -> h0, h0 after dropout, c0, h1 (bf16 + fp32), c1
 // =================================================================================================
@@ -194,8 +201,8 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                     const uint32_t p2 = pack_val(h[4], h[5]), p3 = pack_val(h[6], h[7]);
                     st_shared_v4(dst + blk * kAChunk, p0, p1, p2, p3);
                     *reinterpret_cast<uint4*>(h0_out + tcl + blk * (kAChunk / 2)) = make_uint4(p0, p1, p2, p3);
-                    st_global_v4f(c0_out + grow * kH + blk * 8, c[bb * 8], c[bb * 8 + 1], c[bb * 8 + 2], c[bb * 8 + 3]);
-                    st_global_v4f(c0_out + grow * kH + blk * 8 + 4, c[bb * 8 + 4], c[bb * 8 + 5], c[bb * 8 + 6], c[bb * 8 + 7]);
+                    st_global_v4f(c0_out + tcl32_off(t, ntiles, tile, 2 * blk, row), c[bb * 8], c[bb * 8 + 1], c[bb * 8 + 2], c[bb * 8 + 3]);
+                    st_global_v4f(c0_out + tcl32_off(t, ntiles, tile, 2 * blk + 1, row), c[bb * 8 + 4], c[bb * 8 + 5], c[bb * 8 + 6], c[bb * 8 + 7]);
                     if (drop) {
                         float hd[8];
 #pragma unroll
@@ -238,8 +245,8 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                     *reinterpret_cast<uint4*>(h1_out + tcl + blk * (kAChunk / 2)) = make_uint4(p0, p1, p2, p3);
                     st_global_v4f(h1f_out + grow * kH + blk * 8, h[0], h[1], h[2], h[3]);
                     st_global_v4f(h1f_out + grow * kH + blk * 8 + 4, h[4], h[5], h[6], h[7]);
-                    st_global_v4f(c1_out + grow * kH + blk * 8, c[bb * 8], c[bb * 8 + 1], c[bb * 8 + 2], c[bb * 8 + 3]);
-                    st_global_v4f(c1_out + grow * kH + blk * 8 + 4, c[bb * 8 + 4], c[bb * 8 + 5], c[bb * 8 + 6], c[bb * 8 + 7]);
+                    st_global_v4f(c1_out + tcl32_off(t, ntiles, tile, 2 * blk, row), c[bb * 8], c[bb * 8 + 1], c[bb * 8 + 2], c[bb * 8 + 3]);
+                    st_global_v4f(c1_out + tcl32_off(t, ntiles, tile, 2 * blk + 1, row), c[bb * 8 + 4], c[bb * 8 + 5], c[bb * 8 + 6], c[bb * 8 + 7]);
                 }
                 tc_fence_before();
                 fence_proxy_async_smem();
@@ -294,6 +301,7 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                      float drop_scale,                             // KI == 48: dropout of this layer's input
                      float* __restrict__ din,                      // TMP, KI == 48 only
                      float* __restrict__ dw_partial,               // [grid][192][kNW]
+                     int dh_chunked,                               // dh_out layout: 1 = TCL32 (din of the layer above), 0 = TMP
                      int T, int64_t Bp, int ntiles) {
     using C = BwdCfg<KI>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -404,10 +412,9 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
 #pragma unroll
             for (int j = 0; j < 24; ++j) dc[j] = 0.f;
             {   // c_{T-1} of this tile (afterwards c_t is carried over from the previous iteration's c_{t-1})
-                const float* crow = cstate + ((int64_t)(T - 1) * Bp + b0 + row) * kH + hf * 24;
 #pragma unroll
                 for (int j = 0; j < 24; j += 4) {
-                    const float4 a = *reinterpret_cast<const float4*>(crow + j);
+                    const float4 a = *reinterpret_cast<const float4*>(cstate + tcl32_off(T - 1, ntiles, tile, hf * 6 + j / 4, row));
                     ccur[j] = a.x; ccur[j + 1] = a.y; ccur[j + 2] = a.z; ccur[j + 3] = a.w;
                 }
             }
@@ -418,14 +425,14 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                 float cp[24], dh[24];
                 if (i < T) {
                     const int64_t grow = (int64_t)t * Bp + b0 + row;
-                    const float* dhrow = dh_out + grow * kH + hf * 24;
-                    const float* cprow = cstate + (grow - Bp) * kH + hf * 24;
+                    const float* dhrow = dh_out + grow * kH + hf * 24;           // row-major TMP (head backward)
 #pragma unroll
                     for (int j = 0; j < 24; j += 4) {
-                        const float4 d = *reinterpret_cast<const float4*>(dhrow + j);
+                        const float4 d = dh_chunked ? *reinterpret_cast<const float4*>(dh_out + tcl32_off(t, ntiles, tile, hf * 6 + j / 4, row))
+                                                    : *reinterpret_cast<const float4*>(dhrow + j);
                         dh[j] = d.x; dh[j + 1] = d.y; dh[j + 2] = d.z; dh[j + 3] = d.w;
                         float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (t > 0) c4 = *reinterpret_cast<const float4*>(cprow + j);
+                        if (t > 0) c4 = *reinterpret_cast<const float4*>(cstate + tcl32_off(t - 1, ntiles, tile, hf * 6 + j / 4, row));
                         cp[j] = c4.x; cp[j + 1] = c4.y; cp[j + 2] = c4.z; cp[j + 3] = c4.w;
                     }
                 }
@@ -450,8 +457,8 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
 #pragma unroll
                             for (int u = 0; u < 8; ++u) o[u] = __uint_as_float(r[u]);
                         }
-                        st_global_v4f(din + grow * kH + blk * 8, o[0], o[1], o[2], o[3]);
-                        st_global_v4f(din + grow * kH + blk * 8 + 4, o[4], o[5], o[6], o[7]);
+                        st_global_v4f(din + tcl32_off(t + 1, ntiles, tile, 2 * blk, row), o[0], o[1], o[2], o[3]);
+                        st_global_v4f(din + tcl32_off(t + 1, ntiles, tile, 2 * blk + 1, row), o[4], o[5], o[6], o[7]);
                     }
                 }
                 if (i == T) {                                             // tail: all W of this tile must be done
@@ -610,7 +617,7 @@ static int launch_bwd(const void* act_in, const void* h, const float* c, const f
                                           c, dh_out, reinterpret_cast<const unsigned char*>(packed_g),
                                           reinterpret_cast<const unsigned char*>(packed_r),
                                           reinterpret_cast<const __nv_bfloat16*>(zeros), mask, seed, thresh16, scale, din, partial,
-                                          (int)T, Bp, ntiles);
+                                          KI == 8 ? 1 : 0, (int)T, Bp, ntiles);
     count_launch();
     return check_launch("na_lstm_bwd_bf16");
 }
