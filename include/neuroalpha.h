@@ -180,14 +180,17 @@ int na_decoder_infer_bf16(const void* x_bf16_tmp, const void* packed,
  * step-t slab is contiguous and already in the UMMA core-matrix layout); mask u8 [T][Bp][48].
  * Bp must be a multiple of 128.  Flagship shape only (C=8, H=48, L=2).
  *
- * na_lstm2_fwd_train_bf16: x (bf16 TMP, na_window_zscore) -> h0 (TCL), h0d = h0*mask*scale (TCL; NULL
- *   together with mask when there is no dropout), c0 (TMP), h1 (TCL), h1f (TMP fp32, input of the head
- *   kernels), c1 (TMP).  Replaces `self.lstm(x)` (lstm_eeg_model.py:34) in train mode.
+ * na_lstm2_fwd_train_bf16: x (16-bit TMP, na_window_zscore) -> h0 (TCL), h0d = h0*mask*scale (TCL; NULL
+ *   when there is no dropout), c0, c1 (TCL32: fp32 [T][Bp/128][12][128][4]), h1 (TCL).  Replaces
+ *   `self.lstm(x)` (lstm_eeg_model.py:34) in train mode.  The attention pool of lstm_eeg_model.py:35-37 is
+ *   either fused (zpool [B,48] + stats [B,2] = (max, sum) of the softmax over time; needs attn_w, attn_b, B)
+ *   or left to na_head_fwd_f32 (then h1f, a fp32 TMP copy of h1, is written instead).
  * na_lstm_bwd_bf16: fused BPTT + weight gradients of one layer (layer = 0 | 1).  act_in = the layer's
  *   input (x for layer 0, h0d/h0 for layer 1; TCL), h = its raw output (TCL), cstate / dh_out (TMP).
  *   Gates are recomputed on the tensor cores; d(gates) never leave shared memory; dW_ih / dW_hh / db
  *   accumulate in TMEM in fp32 and are reduced over CTAs in a fixed order.  Layer 1 also writes
- *   din = d(act_in) * in_mask * drop_scale (TMP) = dh_out of layer 0.
+ *   din = d(act_in) * in_mask * drop_scale (TCL32) = dh_out of layer 0.  Exactly one of dh_out (TMP for layer
+ *   1, TCL32 for layer 0) and dz (layer 1 only: fused head backward, see below) is given.
  *   packed_fwd = na_decoder_pack_bf16 output; zeros = >= 12,288 B of zeros; scratch =
  *   36,864 + 4 * na_train_bf16_partial_floats() bytes.
  */
@@ -200,13 +203,28 @@ int na_dropout_mask_u8(uint64_t seed, int64_t thresh16, int64_t T, int64_t Bp, u
 int64_t na_train_bf16_partial_floats(void);
 int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packed, const unsigned char* mask,
                             uint64_t seed, int64_t thresh16, float drop_scale, void* h0, void* h0d, float* c0, void* h1, float* h1f,
-                            float* c1, int64_t T, int64_t Bp, na_stream_t stream);
+                            float* c1, const float* attn_w, const float* attn_b, float* zpool, float* stats,
+                            int64_t B, int64_t T, int64_t Bp, na_stream_t stream);
 int na_lstm_bwd_bf16(int64_t layer, const void* act_in, const void* h, const float* cstate,
                      const float* dh_out, const void* packed_fwd, const float* w_ih, const float* w_hh,
                      const void* zeros, const unsigned char* in_mask, uint64_t seed, int64_t thresh16,
-                     float drop_scale, float* din,
-                     float* dw_ih, float* dw_hh, float* db, void* scratch,
+                     float drop_scale, float* din, float* dw_ih, float* dw_hh, float* db, void* scratch,
+                     const float* dz, const float* stats, const float* zpool, const float* attn_w,
+                     const float* attn_b, int64_t B, float* d_attn,
                      int64_t T, int64_t Bp, na_stream_t stream);
+
+/* Tail-only forms of K4 for the fused tier: na_lstm2_fwd_train_bf16 already pooled (zpool, stats), and
+ * na_lstm_bwd_bf16(layer 1, dz != NULL) rebuilds dh_t = alpha_t dz + ds_t w_a per step and owns d attn_w /
+ * d attn_b (d_attn [49]).  na_head_tail_bwd_f32 zeroes the attn slots of `dparams`. */
+int na_head_tail_fwd_f32(const float* zpool, const float* attn_w, const float* attn_b, const float* ln_w,
+                         const float* ln_b, const float* fc0_w, const float* fc0_b, const float* fc3_w,
+                         const float* fc3_b, const float* rrelu_slope, const float* drop_mask, float drop_scale,
+                         float* logits, float* probs, int64_t B, int64_t H, int64_t NC, na_stream_t stream);
+int na_head_tail_bwd_f32(const float* dlogits, const float* zpool, const float* attn_w, const float* attn_b,
+                         const float* ln_w, const float* ln_b, const float* fc0_w, const float* fc0_b,
+                         const float* fc3_w, const float* fc3_b, const float* rrelu_slope, const float* drop_mask,
+                         float drop_scale, float* dz, float* dparams, float* partials,
+                         int64_t B, int64_t H, int64_t NC, na_stream_t stream);
 
 /* ---- K5: trial averaging -----------------------------------------------------------------
  * Replaces tester.py:54,89,97 (and :90,98 for the chunk): fp32 zeros, += in trial order

@@ -36,8 +36,11 @@ SIGNATURES = {
     "na_decoder_infer_bf16": (c_int, [P] * 12 + [I64, I64, I64, I64, P]),
     "na_train_bf16_partial_floats": (c_int64, []),
     "na_dropout_mask_u8": (c_int, [ctypes.c_uint64, I64, I64, I64, P, P]),
-    "na_lstm2_fwd_train_bf16": (c_int, [P, P, P, ctypes.c_uint64, I64, F32, P, P, P, P, P, P, I64, I64, P]),
-    "na_lstm_bwd_bf16": (c_int, [I64, P, P, P, P, P, P, P, P, P, ctypes.c_uint64, I64, F32, P, P, P, P, P, I64, I64, P]),
+    "na_lstm2_fwd_train_bf16": (c_int, [P, P, P, ctypes.c_uint64, I64, F32, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, P]),
+    "na_lstm_bwd_bf16": (c_int, [I64, P, P, P, P, P, P, P, P, P, ctypes.c_uint64, I64, F32, P, P, P, P, P,
+                                 P, P, P, P, P, I64, P, I64, I64, P]),
+    "na_head_tail_fwd_f32": (c_int, [P] * 9 + [P, P, F32, P, P, I64, I64, I64, P]),
+    "na_head_tail_bwd_f32": (c_int, [P] * 10 + [P, P, F32, P, P, P, I64, I64, I64, P]),
     "na_trial_mean_f32": (c_int, [P, P, I64, I64, P]),
 }
 

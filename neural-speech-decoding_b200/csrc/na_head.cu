@@ -67,6 +67,7 @@ template <int JPL, int CH>
 __global__ void __launch_bounds__(kHeadWarps * 32)
 head_fwd_kernel(const float* __restrict__ h, HeadParams p, float* __restrict__ logits,
                 float* __restrict__ probs, float* __restrict__ stats, float* __restrict__ zpool,
+                const float* __restrict__ zpool_in,      // != NULL: tail only (pooling was done upstream)
                 int T, int64_t B, int64_t Bp, int H, int NC) {
     extern __shared__ float smem[];
     float* w0t = smem;                               // [H][33]  fc0_w transposed
@@ -89,6 +90,15 @@ head_fwd_kernel(const float* __restrict__ h, HeadParams p, float* __restrict__ l
     }
     const float ba = p.attn_b[0];
     float m = -INFINITY, l = 0.f;
+    if (zpool_in != nullptr) {
+        T = 0;                                    // skip the time loop below
+        l = 1.0f;
+#pragma unroll
+        for (int i = 0; i < JPL; ++i) {
+            const int j = lane + 32 * i;
+            z[i] = (j < H) ? zpool_in[b * H + j] : 0.f;
+        }
+    }
     for (int t0 = 0; t0 < T; t0 += CH) {
         float hv[CH][JPL];
 #pragma unroll
@@ -157,6 +167,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32)
 head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ h, const float* __restrict__ stats,
                 const float* __restrict__ zpool, HeadParams p, float* __restrict__ dh,
                 float* __restrict__ scratch, float* __restrict__ wa_partial,
+                float* __restrict__ dz_out,              // != NULL: tail only -> dz [B,H]; no time loop, dh untouched
                 int T, int64_t B, int64_t Bp, int H, int NC) {
     extern __shared__ float smem[];
     float* w0t = smem;                               // [H][33]
@@ -177,7 +188,7 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ h, 
     for (int i = 0; i < JPL; ++i) dwa[i] = 0.f;
 
     if (b >= B) {
-        if (b < Bp)
+        if (b < Bp && dz_out == nullptr)
             for (int t = 0; t < T; ++t) {
                 float* row = dh + ((int64_t)t * Bp + b) * H;
                 for (int j = lane; j < H; j += 32) row[j] = 0.f;
@@ -191,7 +202,7 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ h, 
             zp[i] = (j < H) ? zpool[b * H + j] : 0.f;
         }
         const float ba = p.attn_b[0];
-        const float m = stats[2 * b], l = stats[2 * b + 1];
+        const float m = dz_out ? 0.f : stats[2 * b], l = dz_out ? 1.f : stats[2 * b + 1];
         float rstd, a_pre, a_post, act_grad;
         head_tail<JPL>(zp, p, w0t, zs + warp * H, b, H, lane, xhat, rstd, a_pre, a_post, act_grad);
 
@@ -236,6 +247,14 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ h, 
             dz[i] = (j < H) ? rstd * (dxh[i] - m1 - xhat[i] * m2) : 0.f;
         }
         const float inv_l = 1.0f / l;
+        if (dz_out != nullptr) {
+            T = 0;                                // tail only: hand dz to the fused BPTT kernel
+#pragma unroll
+            for (int i = 0; i < JPL; ++i) {
+                const int j = lane + 32 * i;
+                if (j < H) dz_out[b * H + j] = dz[i];
+            }
+        }
         // Softmax-over-time backward in CENTRED form: with z = sum_t alpha_t h_t,
         //   ds_t = alpha_t (dz.h_t - dz.z) = alpha_t dz.(h_t - z),   sum_t ds_t = 0  =>
         //   d attn_w = sum_t ds_t h_t = sum_t ds_t (h_t - z).
@@ -299,12 +318,13 @@ head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ h, 
 
 template <int JPL, int CH>
 int launch_head_fwd(const float* h, const HeadParams& p, float* logits, float* probs, float* stats, float* zpool,
-                    int64_t T, int64_t B, int64_t Bp, int64_t H, int64_t NC, cudaStream_t st) {
+                    int64_t T, int64_t B, int64_t Bp, int64_t H, int64_t NC, cudaStream_t st,
+                    const float* zpool_in = nullptr) {
     const size_t smem = sizeof(float) * (H * (kFc + 1) + kHeadWarps * H);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(head_fwd_kernel<JPL, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned grid = (unsigned)((B + kHeadWarps - 1) / kHeadWarps);
-    head_fwd_kernel<JPL, CH><<<grid, kHeadWarps * 32, smem, st>>>(h, p, logits, probs, stats, zpool, (int)T, B, Bp,
+    head_fwd_kernel<JPL, CH><<<grid, kHeadWarps * 32, smem, st>>>(h, p, logits, probs, stats, zpool, zpool_in, (int)T, B, Bp,
                                                                 (int)H, (int)NC);
     count_launch();
     return check_launch("na_head_fwd_f32");
@@ -313,13 +333,13 @@ int launch_head_fwd(const float* h, const HeadParams& p, float* logits, float* p
 template <int JPL, int CH>
 int launch_head_bwd(const float* dlogits, const float* h, const float* stats, const float* zpool,
                     const HeadParams& p, float* dh, float* scratch, float* wa_partial, int64_t T, int64_t B,
-                    int64_t Bp, int64_t H, int64_t NC, cudaStream_t st) {
+                    int64_t Bp, int64_t H, int64_t NC, cudaStream_t st, float* dz_out = nullptr) {
     const size_t smem = sizeof(float) * (H * (kFc + 1) + kHeadWarps * H + kHeadWarps * (H + 1));
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(head_bwd_kernel<JPL, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned grid = (unsigned)(Bp / kHeadWarps);
     head_bwd_kernel<JPL, CH><<<grid, kHeadWarps * 32, smem, st>>>(dlogits, h, stats, zpool, p, dh, scratch,
-                                                                wa_partial, (int)T, B, Bp, (int)H, (int)NC);
+                                                                wa_partial, dz_out, (int)T, B, Bp, (int)H, (int)NC);
     count_launch();
     return check_launch("na_head_bwd_f32");
 }
@@ -401,6 +421,72 @@ extern "C" int na_head_bwd_f32(const float* dlogits, const float* h, const float
     float* d_fc3w = d_fc0b + kFc;
     float* d_fc3b = d_fc3w + kFc * NC;
     if ((rc = reduce_partials(wa_partial, d_attn, (int)nblk, H + 1, st))) return rc;
+    if ((rc = colsum(scratch + 2 * kFc + H, S, B, H, d_lnw, gpart, st))) return rc;
+    if ((rc = colsum(scratch + 2 * kFc + 2 * H, S, B, H, d_lnb, gpart, st))) return rc;
+    if ((rc = gemm_tn(scratch + kFc, S, scratch + 2 * kFc, S, B, kFc, H, d_fc0w, gpart, st))) return rc;
+    if ((rc = colsum(scratch + kFc, S, B, kFc, d_fc0b, gpart, st))) return rc;
+    if ((rc = gemm_tn(dlogits, NC, scratch, S, B, NC, kFc, d_fc3w, gpart, st))) return rc;
+    return colsum(dlogits, NC, B, NC, d_fc3b, gpart, st);
+}
+
+
+// ---- tail-only forms (pooling fused upstream / time loop fused downstream: tensor-core training tier) ----
+extern "C" int na_head_tail_fwd_f32(const float* zpool, const float* attn_w, const float* attn_b, const float* ln_w,
+                                    const float* ln_b, const float* fc0_w, const float* fc0_b, const float* fc3_w,
+                                    const float* fc3_b, const float* rrelu_slope, const float* drop_mask,
+                                    float drop_scale, float* logits, float* probs, int64_t B, int64_t H, int64_t NC,
+                                    na_stream_t stream) {
+    using namespace na;
+    const int64_t Bp = (B + NA_BATCH_ALIGN - 1) / NA_BATCH_ALIGN * NA_BATCH_ALIGN;
+    if (int rc = check_head_shape("na_head_tail_fwd_f32", 1, B, Bp, H, NC)) return rc;
+    NA_REQUIRE_PTR(zpool); NA_REQUIRE_PTR(logits);
+    NA_REQUIRE(attn_w && attn_b && ln_w && ln_b && fc0_w && fc0_b && fc3_w && fc3_b, NA_EINVAL,
+               "na_head_tail_fwd_f32: null parameter pointer");
+    HeadParams p{attn_w, attn_b, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, rrelu_slope, drop_mask, drop_scale};
+    cudaStream_t st = as_stream(stream);
+    if (H <= 64) return launch_head_fwd<2, 8>(nullptr, p, logits, probs, nullptr, nullptr, 1, B, Bp, H, NC, st, zpool);
+    if (H <= 128) return launch_head_fwd<4, 4>(nullptr, p, logits, probs, nullptr, nullptr, 1, B, Bp, H, NC, st, zpool);
+    if (H <= 256) return launch_head_fwd<8, 2>(nullptr, p, logits, probs, nullptr, nullptr, 1, B, Bp, H, NC, st, zpool);
+    if (H <= 512) return launch_head_fwd<16, 1>(nullptr, p, logits, probs, nullptr, nullptr, 1, B, Bp, H, NC, st, zpool);
+    return launch_head_fwd<32, 1>(nullptr, p, logits, probs, nullptr, nullptr, 1, B, Bp, H, NC, st, zpool);
+}
+
+// dlogits -> dz [B,H] (gradient w.r.t. the pooled vector) + the gradients of ln / fc0 / fc3 in `dparams`
+// (same packing as na_head_bwd_f32; the attn_w / attn_b slots are zeroed -- the fused BPTT kernel owns them).
+extern "C" int na_head_tail_bwd_f32(const float* dlogits, const float* zpool, const float* attn_w, const float* attn_b,
+                                    const float* ln_w, const float* ln_b, const float* fc0_w, const float* fc0_b,
+                                    const float* fc3_w, const float* fc3_b, const float* rrelu_slope,
+                                    const float* drop_mask, float drop_scale, float* dz, float* dparams, float* partials,
+                                    int64_t B, int64_t H, int64_t NC, na_stream_t stream) {
+    using namespace na;
+    const int64_t Bp = (B + NA_BATCH_ALIGN - 1) / NA_BATCH_ALIGN * NA_BATCH_ALIGN;
+    if (int rc = check_head_shape("na_head_tail_bwd_f32", 1, B, Bp, H, NC)) return rc;
+    NA_REQUIRE_PTR(dlogits); NA_REQUIRE_PTR(zpool); NA_REQUIRE_PTR(dz); NA_REQUIRE_PTR(dparams); NA_REQUIRE_PTR(partials);
+    NA_REQUIRE(attn_w && attn_b && ln_w && ln_b && fc0_w && fc0_b && fc3_w && fc3_b, NA_EINVAL,
+               "na_head_tail_bwd_f32: null parameter pointer");
+    HeadParams p{attn_w, attn_b, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, rrelu_slope, drop_mask, drop_scale};
+    cudaStream_t st = as_stream(stream);
+    const int64_t S = 2 * kFc + 3 * H;
+    const int64_t nblk = Bp / kHeadWarps;
+    float* scratch = partials;
+    float* wa_partial = scratch + B * S;
+    float* gpart = wa_partial + nblk * (H + 1);
+    gpart += (4 - ((gpart - partials) & 3)) & 3;
+    int rc;
+    if (H <= 64) rc = launch_head_bwd<2, 8>(dlogits, nullptr, nullptr, zpool, p, nullptr, scratch, wa_partial, 1, B, Bp, H, NC, st, dz);
+    else if (H <= 128) rc = launch_head_bwd<4, 4>(dlogits, nullptr, nullptr, zpool, p, nullptr, scratch, wa_partial, 1, B, Bp, H, NC, st, dz);
+    else if (H <= 256) rc = launch_head_bwd<8, 2>(dlogits, nullptr, nullptr, zpool, p, nullptr, scratch, wa_partial, 1, B, Bp, H, NC, st, dz);
+    else if (H <= 512) rc = launch_head_bwd<16, 1>(dlogits, nullptr, nullptr, zpool, p, nullptr, scratch, wa_partial, 1, B, Bp, H, NC, st, dz);
+    else rc = launch_head_bwd<32, 1>(dlogits, nullptr, nullptr, zpool, p, nullptr, scratch, wa_partial, 1, B, Bp, H, NC, st, dz);
+    if (rc) return rc;
+    float* d_attn = dparams;
+    float* d_lnw = d_attn + H + 1;
+    float* d_lnb = d_lnw + H;
+    float* d_fc0w = d_lnb + H;
+    float* d_fc0b = d_fc0w + kFc * H;
+    float* d_fc3w = d_fc0b + kFc;
+    float* d_fc3b = d_fc3w + kFc * NC;
+    if ((rc = (int)cudaMemsetAsync(d_attn, 0, sizeof(float) * (H + 1), st))) return fail(rc, "na_head_tail_bwd_f32: memset failed");
     if ((rc = colsum(scratch + 2 * kFc + H, S, B, H, d_lnw, gpart, st))) return rc;
     if ((rc = colsum(scratch + 2 * kFc + 2 * H, S, B, H, d_lnb, gpart, st))) return rc;
     if ((rc = gemm_tn(scratch + kFc, S, scratch + 2 * kFc, S, B, kFc, H, d_fc0w, gpart, st))) return rc;

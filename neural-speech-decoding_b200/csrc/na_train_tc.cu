@@ -21,6 +21,7 @@
 #include "na_tc_common.cuh"
 
 namespace na {
+int reduce_partials(const float* partial, float* out, int nchunks, int64_t n, cudaStream_t st);   // na_reduce.cu
 namespace tc {
 
 constexpr int kTrainThreads = 576;     // forward: 8 + 8 epilogue warps (2 per TMEM quarter and layer), MMA warp, TMA warp
@@ -67,6 +68,9 @@ struct FwdSmem {
     alignas(8) uint64_t x_full[kXStagesT], x_empty[kXStagesT];
     uint64_t d0_full, d1_full, h0_ready[2], h0_free[2], h1_ready;
     uint32_t tmem_base;
+    float wa[kH];                                             // attention weights (fused pooling)
+    float ba;
+    float score_part[2][2][kRows];                            // per-step partial scores of the two half-row warps
 };
 
 __global__ void __launch_bounds__(kTrainThreads, 1)
@@ -75,6 +79,8 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                             __nv_bfloat16* __restrict__ h0_out, __nv_bfloat16* __restrict__ h0d_out,
                             float* __restrict__ c0_out, __nv_bfloat16* __restrict__ h1_out,
                             float* __restrict__ h1f_out, float* __restrict__ c1_out,
+                            const float* __restrict__ attn_w, const float* __restrict__ attn_b,   // fused attention pooling
+                            float* __restrict__ zpool_out, float* __restrict__ stats_out, int64_t B,   // (all NULL: off)
                             int T, int64_t Bp, int ntiles) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     FwdSmem& S = *reinterpret_cast<FwdSmem*>(smem_raw);
@@ -98,6 +104,10 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
             mbar_init(&S.h1_ready, 256);
             fence_mbar_init();
         }
+        if (zpool_out != nullptr) {
+            for (int i = tid; i < kH; i += kTrainThreads) S.wa[i] = attn_w[i];
+            if (tid == 0) S.ba = attn_b[0];
+        }
         if (warp == 17) tmem_alloc_all(&S.tmem_base);
         tc_fence_before();
         fence_proxy_async_smem();
@@ -105,7 +115,8 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
         tc_fence_after();
     }
     const uint32_t tmem = S.tmem_base, tmem_d0 = tmem, tmem_d1 = tmem + kN;
-    const bool drop = mask != nullptr || thresh16 < 65536u;      // explicit mask tensor, or in-kernel counter-based RNG
+    const bool drop = mask != nullptr || thresh16 < 65536u;
+    const bool pool = zpool_out != nullptr;      // explicit mask tensor, or in-kernel counter-based RNG
 
     int n0 = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, n0 += T) {
@@ -222,9 +233,10 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
             const int q = (warp - 8) & 3, hf = (warp - 8) >> 2;
             const int row = q * 32 + lane;
             const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-            float c[24];
+            float c[24], z[24];
 #pragma unroll
-            for (int j = 0; j < 24; ++j) c[j] = 0.f;
+            for (int j = 0; j < 24; ++j) { c[j] = 0.f; z[j] = 0.f; }
+            float mx = -INFINITY, l = 0.f;
             for (int t = 0; t < T; ++t) {
                 const int m = n0 + t;
                 const int64_t grow = (int64_t)t * Bp + b0 + row;
@@ -232,6 +244,8 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                 mbar_wait(&S.d1_full, m & 1);
                 tc_fence_after();
                 unsigned char* dst = S.h1 + row * 16;
+                uint32_t hb[12];
+                float score = 0.f;
 #pragma unroll
                 for (int bb = 0; bb < 3; ++bb) {
                     const int blk = hf * 3 + bb;
@@ -243,14 +257,52 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                     const uint32_t p2 = pack_val(h[4], h[5]), p3 = pack_val(h[6], h[7]);
                     st_shared_v4(dst + blk * kAChunk, p0, p1, p2, p3);
                     *reinterpret_cast<uint4*>(h1_out + tcl + blk * (kAChunk / 2)) = make_uint4(p0, p1, p2, p3);
-                    st_global_v4f(h1f_out + grow * kH + blk * 8, h[0], h[1], h[2], h[3]);
-                    st_global_v4f(h1f_out + grow * kH + blk * 8 + 4, h[4], h[5], h[6], h[7]);
+                    if (pool) {       // attention score on the fp16-rounded h (what the backward re-reads)
+                        hb[bb * 4] = p0; hb[bb * 4 + 1] = p1; hb[bb * 4 + 2] = p2; hb[bb * 4 + 3] = p3;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            score = fmaf(val_lo(hb[bb * 4 + u]), S.wa[blk * 8 + 2 * u], score);
+                            score = fmaf(val_hi(hb[bb * 4 + u]), S.wa[blk * 8 + 2 * u + 1], score);
+                        }
+                    }
+                    if (h1f_out) {
+                        st_global_v4f(h1f_out + grow * kH + blk * 8, h[0], h[1], h[2], h[3]);
+                        st_global_v4f(h1f_out + grow * kH + blk * 8 + 4, h[4], h[5], h[6], h[7]);
+                    }
                     st_global_v4f(c1_out + tcl32_off(t, ntiles, tile, 2 * blk, row), c[bb * 8], c[bb * 8 + 1], c[bb * 8 + 2], c[bb * 8 + 3]);
                     st_global_v4f(c1_out + tcl32_off(t, ntiles, tile, 2 * blk + 1, row), c[bb * 8 + 4], c[bb * 8 + 5], c[bb * 8 + 6], c[bb * 8 + 7]);
                 }
                 tc_fence_before();
                 fence_proxy_async_smem();
                 mbar_arrive(&S.h1_ready);
+                if (pool) {
+                    // online softmax over time (lstm_eeg_model.py:35-37); the two half-row warps add their
+                    // partial scores in a fixed order, so both carry bit-identical (max, sum)
+                    S.score_part[t & 1][hf][row] = score;
+                    named_bar_sync(1 + q, 64);
+                    score = S.score_part[t & 1][0][row] + S.score_part[t & 1][1][row] + S.ba;
+                    if (score > mx) {
+                        const float sc = __expf(mx - score);
+                        l *= sc;
+#pragma unroll
+                        for (int j = 0; j < 24; ++j) z[j] *= sc;
+                        mx = score;
+                    }
+                    const float e = __expf(score - mx);
+                    l += e;
+#pragma unroll
+                    for (int u = 0; u < 12; ++u) {
+                        z[2 * u] = fmaf(e, val_lo(hb[u]), z[2 * u]);
+                        z[2 * u + 1] = fmaf(e, val_hi(hb[u]), z[2 * u + 1]);
+                    }
+                }
+            }
+            if (pool && b0 + row < B) {
+                const float inv_l = 1.0f / l;
+                float* zo = zpool_out + (b0 + row) * kH + hf * 24;
+#pragma unroll
+                for (int j = 0; j < 24; j += 4) st_global_v4f(zo + j, z[j] * inv_l, z[j + 1] * inv_l, z[j + 2] * inv_l, z[j + 3] * inv_l);
+                if (hf == 0) { stats_out[2 * (b0 + row)] = mx; stats_out[2 * (b0 + row) + 1] = l; }
             }
         }
         __syncthreads();
@@ -286,6 +338,13 @@ struct BwdSmem {
     alignas(8) uint64_t act_full[2], act_free[2];
     uint64_t g_full, dg_ready, w_done;
     uint32_t tmem_base;
+    // fused head backward (layer 1): attention weights, per-step exchange of the two half-row warps'
+    // partial (score, dz.h), the per-tile dz.z exchange, and the final d(attn) reduction
+    float wa[kH];
+    float ba;
+    float2 xch[2][2][kRows];
+    float xch0[2][kRows];
+    float red[8][kH / 2 + 1];
 };
 
 template <int KI>
@@ -302,6 +361,11 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                      float* __restrict__ din,                      // TMP, KI == 48 only
                      float* __restrict__ dw_partial,               // [grid][192][kNW]
                      int dh_chunked,                               // dh_out layout: 1 = TCL32 (din of the layer above), 0 = TMP
+                     // fused head backward (KI == 48, dz != NULL): dh_out is not read; dh_t = alpha_t dz + ds_t w_a is
+                     // rebuilt per step from dz [B,48], the softmax stats [B,2], the pooled z [B,48] and h (= h1)
+                     const float* __restrict__ dz, const float* __restrict__ stats, const float* __restrict__ zpool,
+                     const float* __restrict__ attn_w, const float* __restrict__ attn_b, int64_t B,
+                     float* __restrict__ attn_partial,             // [grid][49]: d attn_w | d attn_b
                      int T, int64_t Bp, int ntiles) {
     using C = BwdCfg<KI>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -328,12 +392,20 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
             mbar_init(&S.dg_ready, 256);
             fence_mbar_init();
         }
+        if (dz != nullptr) {
+            for (int i = tid; i < kH; i += kBwdThreads) S.wa[i] = attn_w[i];
+            if (tid == 0) S.ba = attn_b[0];
+        }
         if (warp == 9) tmem_alloc_all(&S.tmem_base);
         tc_fence_before();
         fence_proxy_async_smem();
         __syncthreads();
         tc_fence_after();
     }
+    const bool head = (KI == 48) && dz != nullptr;
+    float dwa[24], dba = 0.f;                     // d attn_w (this thread's 24 units), d attn_b; epilogue warps only
+#pragma unroll
+    for (int j = 0; j < 24; ++j) dwa[j] = 0.f;
     const uint32_t tmem = S.tmem_base;
     const uint32_t tm_g = tmem + C::kColG, tm_r = tmem + C::kColR, tm_w1 = tmem + C::kColW1, tm_w2 = tmem + C::kColW2;
     constexpr uint32_t kIdescR = make_idesc(C::kNR, kFmtGrad, kFmtVal);               // d(gates) x W^T, K-major x K-major
@@ -419,11 +491,58 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                 }
             }
             unsigned char* dgrow = S.dg + row * 16;
+            float dzr[24], dzz = 0.f, sm_m = 0.f, inv_l = 1.f;
+            if (head) {
+                const int64_t b = b0 + row;
+                float part = 0.f;
+#pragma unroll
+                for (int j = 0; j < 24; ++j) {
+                    dzr[j] = (b < B) ? dz[b * kH + hf * 24 + j] : 0.f;
+                    part = fmaf(dzr[j], (b < B) ? zpool[b * kH + hf * 24 + j] : 0.f, part);
+                }
+                if (b < B) { sm_m = stats[2 * b]; inv_l = 1.0f / stats[2 * b + 1]; }
+                S.xch0[hf][row] = part;
+                named_bar_sync(1 + q, 64);
+                dzz = S.xch0[0][row] + S.xch0[1][row];              // dz . z  (both halves, fixed order)
+            }
             for (int i = 0; i <= T; ++i) {
                 const int t = T - 1 - i;                                  // step whose gates are in D_G (i < T)
                 // ---- prefetch this step's c_{t-1} and dh_out BEFORE waiting for the tensor pipe -----------
                 float cp[24], dh[24];
-                if (i < T) {
+                if (i < T && head) {
+                    // head backward fused here: the loads and the exchange overlap the tensor pipe's R/G of this step
+                    uint4 hp[3];
+#pragma unroll
+                    for (int bb = 0; bb < 3; ++bb)
+                        hp[bb] = *reinterpret_cast<const uint4*>(h + ((((int64_t)t * ntiles + tile) * 6 + hf * 3 + bb) * kRows + row) * 8);
+#pragma unroll
+                    for (int j = 0; j < 24; j += 4) {
+                        float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (t > 0) c4 = *reinterpret_cast<const float4*>(cstate + tcl32_off(t - 1, ntiles, tile, hf * 6 + j / 4, row));
+                        cp[j] = c4.x; cp[j + 1] = c4.y; cp[j + 2] = c4.z; cp[j + 3] = c4.w;
+                    }
+                    float hv[24];
+#pragma unroll
+                    for (int bb = 0; bb < 3; ++bb) {
+                        const uint32_t w4[4] = {hp[bb].x, hp[bb].y, hp[bb].z, hp[bb].w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { hv[bb * 8 + 2 * u] = val_lo(w4[u]); hv[bb * 8 + 2 * u + 1] = val_hi(w4[u]); }
+                    }
+                    float sp = 0.f, gp = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 24; ++j) { sp = fmaf(S.wa[hf * 24 + j], hv[j], sp); gp = fmaf(dzr[j], hv[j], gp); }
+                    S.xch[i & 1][hf][row] = make_float2(sp, gp);
+                    named_bar_sync(1 + q, 64);
+                    const float2 x0 = S.xch[i & 1][0][row], x1 = S.xch[i & 1][1][row];
+                    const float alpha = __expf(x0.x + x1.x + S.ba - sm_m) * inv_l;
+                    const float ds = alpha * (x0.y + x1.y - dzz);
+#pragma unroll
+                    for (int j = 0; j < 24; ++j) {
+                        dh[j] = fmaf(alpha, dzr[j], ds * S.wa[hf * 24 + j]);
+                        dwa[j] = fmaf(ds, hv[j], dwa[j]);
+                    }
+                    dba += ds;
+                } else if (i < T) {
                     const int64_t grow = (int64_t)t * Bp + b0 + row;
                     const float* dhrow = dh_out + grow * kH + hf * 24;           // row-major TMP (head backward)
 #pragma unroll
@@ -514,6 +633,26 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
         __syncthreads();
     }
 
+    // ---- per-CTA partial of d attn_w / d attn_b (fused head backward) ----------------------------------------
+    if (head) {
+        if (warp < 8) {
+#pragma unroll
+            for (int j = 0; j < 24; ++j) {
+                const float v = warp_sum(dwa[j]);
+                if (lane == 0) S.red[warp][j] = v;
+            }
+            const float vb = warp_sum(dba);
+            if (lane == 0) S.red[warp][24] = vb;
+        }
+        __syncthreads();
+        if (tid < kH) {
+            const int hfj = tid / 24, j = tid % 24;
+            attn_partial[(size_t)blockIdx.x * (kH + 1) + tid] =
+                S.red[4 * hfj][j] + S.red[4 * hfj + 1][j] + S.red[4 * hfj + 2][j] + S.red[4 * hfj + 3][j];
+        } else if (tid == kH) {
+            attn_partial[(size_t)blockIdx.x * (kH + 1) + kH] = S.red[0][24] + S.red[1][24] + S.red[2][24] + S.red[3][24];
+        }
+    }
     // ---- per-CTA weight-gradient partial: D_W1 rows = gate columns 0..127, D_W2 rows 64..127 = 128..191 ----
     tc_fence_after();
     if (warp < 4) {
@@ -605,7 +744,9 @@ static int tc_sms() {
 template <int KI>
 static int launch_bwd(const void* act_in, const void* h, const float* c, const float* dh_out, const void* packed_g,
                       const void* packed_r, const void* zeros, const unsigned char* mask, uint64_t seed, uint32_t thresh16,
-                      float scale, float* din, float* partial, int64_t T, int64_t Bp, cudaStream_t st, int* grid_out) {
+                      float scale, float* din, float* partial, const float* dz, const float* stats, const float* zpool,
+                      const float* attn_w, const float* attn_b, int64_t B, float* attn_partial, int64_t T, int64_t Bp,
+                      cudaStream_t st, int* grid_out) {
     const size_t smem = sizeof(BwdSmem<KI>) + 1024;
     auto kern = lstm_bwd_bf16_kernel<KI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -617,7 +758,7 @@ static int launch_bwd(const void* act_in, const void* h, const float* c, const f
                                           c, dh_out, reinterpret_cast<const unsigned char*>(packed_g),
                                           reinterpret_cast<const unsigned char*>(packed_r),
                                           reinterpret_cast<const __nv_bfloat16*>(zeros), mask, seed, thresh16, scale, din, partial,
-                                          KI == 8 ? 1 : 0, (int)T, Bp, ntiles);
+                                          KI == 8 ? 1 : 0, dz, stats, zpool, attn_w, attn_b, B, attn_partial, (int)T, Bp, ntiles);
     count_launch();
     return check_launch("na_lstm_bwd_bf16");
 }
@@ -626,17 +767,21 @@ static int launch_bwd(const void* act_in, const void* h, const float* c, const f
 }  // namespace na
 
 // ---- C ABI ---------------------------------------------------------------------------------------
-extern "C" int64_t na_train_bf16_partial_floats(void) { return (int64_t)148 * 2 * na::tc::kN * 112; }
+extern "C" int64_t na_train_bf16_partial_floats(void) { return (int64_t)148 * 2 * na::tc::kN * 112 + 148 * 52; }
 
 extern "C" int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packed, const unsigned char* mask,
                                        uint64_t seed, int64_t thresh16, float drop_scale, void* h0, void* h0d, float* c0, void* h1, float* h1f,
-                                       float* c1, int64_t T, int64_t Bp, na_stream_t stream) {
+                                       float* c1, const float* attn_w, const float* attn_b, float* zpool, float* stats,
+                                       int64_t B, int64_t T, int64_t Bp, na_stream_t stream) {
     using namespace na;
     NA_REQUIRE(T >= 1 && T < (1 << 20) && Bp >= tc::kRows && Bp % tc::kRows == 0, NA_EINVAL,
                "na_lstm2_fwd_train_bf16: bad shape T=%lld Bp=%lld (Bp must be a multiple of 128)", (long long)T, (long long)Bp);
     NA_REQUIRE_PTR(x_bf16_tmp); NA_REQUIRE_PTR(packed); NA_REQUIRE_PTR(h0); NA_REQUIRE_PTR(c0);
-    NA_REQUIRE_PTR(h1); NA_REQUIRE_PTR(h1f); NA_REQUIRE_PTR(c1);
-    NA_OPTIONAL_PTR(mask); NA_OPTIONAL_PTR(h0d);
+    NA_REQUIRE_PTR(h1); NA_REQUIRE_PTR(c1);
+    NA_OPTIONAL_PTR(mask); NA_OPTIONAL_PTR(h0d); NA_OPTIONAL_PTR(h1f); NA_OPTIONAL_PTR(zpool);
+    NA_REQUIRE(zpool == nullptr || (attn_w && attn_b && stats && B >= 1 && B <= Bp), NA_EINVAL,
+               "na_lstm2_fwd_train_bf16: fused pooling needs attn_w, attn_b, stats and 1 <= B <= Bp");
+    NA_REQUIRE(zpool != nullptr || h1f != nullptr, NA_EINVAL, "na_lstm2_fwd_train_bf16: give h1f (separate head) or zpool (fused pooling)");
     NA_REQUIRE(thresh16 >= 0 && thresh16 <= 65536, NA_EINVAL, "na_lstm2_fwd_train_bf16: thresh16 outside [0,65536]");
     NA_REQUIRE((mask != nullptr || thresh16 < 65536) == (h0d != nullptr), NA_EINVAL,
                "na_lstm2_fwd_train_bf16: h0d must be given exactly when dropout is on (mask tensor or thresh16 < 65536)");
@@ -649,7 +794,7 @@ extern "C" int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packe
         reinterpret_cast<const __nv_bfloat16*>(x_bf16_tmp), reinterpret_cast<const unsigned char*>(packed), mask, seed,
         (uint32_t)thresh16, drop_scale,
         reinterpret_cast<__nv_bfloat16*>(h0), reinterpret_cast<__nv_bfloat16*>(h0d), c0, reinterpret_cast<__nv_bfloat16*>(h1),
-        h1f, c1, (int)T, Bp, ntiles);
+        h1f, c1, attn_w, attn_b, zpool, stats, B, (int)T, Bp, ntiles);
     count_launch();
     return check_launch("na_lstm2_fwd_train_bf16");
 }
@@ -668,12 +813,18 @@ extern "C" int na_lstm_bwd_bf16(int64_t layer, const void* act_in, const void* h
                                 const void* packed_fwd, const float* w_ih, const float* w_hh, const void* zeros,
                                 const unsigned char* in_mask, uint64_t seed, int64_t thresh16, float drop_scale,
                                 float* din, float* dw_ih, float* dw_hh,
-                                float* db, void* scratch, int64_t T, int64_t Bp, na_stream_t stream) {
+                                float* db, void* scratch, const float* dz, const float* stats, const float* zpool,
+                                const float* attn_w, const float* attn_b, int64_t B, float* d_attn,
+                                int64_t T, int64_t Bp, na_stream_t stream) {
     using namespace na;
     NA_REQUIRE(layer == 0 || layer == 1, NA_EINVAL, "na_lstm_bwd_bf16: layer must be 0 or 1");
     NA_REQUIRE(T >= 1 && T < (1 << 20) && Bp >= tc::kRows && Bp % tc::kRows == 0, NA_EINVAL,
                "na_lstm_bwd_bf16: bad shape T=%lld Bp=%lld", (long long)T, (long long)Bp);
-    NA_REQUIRE_PTR(act_in); NA_REQUIRE_PTR(h); NA_REQUIRE_PTR(cstate); NA_REQUIRE_PTR(dh_out); NA_REQUIRE_PTR(packed_fwd);
+    NA_REQUIRE_PTR(act_in); NA_REQUIRE_PTR(h); NA_REQUIRE_PTR(cstate); NA_REQUIRE_PTR(packed_fwd);
+    NA_OPTIONAL_PTR(dh_out); NA_OPTIONAL_PTR(dz);
+    NA_REQUIRE((dz != nullptr) != (dh_out != nullptr), NA_EINVAL, "na_lstm_bwd_bf16: give exactly one of dh_out and dz");
+    NA_REQUIRE(dz == nullptr || (layer == 1 && stats && zpool && attn_w && attn_b && d_attn && B >= 1 && B <= Bp), NA_EINVAL,
+               "na_lstm_bwd_bf16: the fused head backward is for layer 1 and needs stats, zpool, attn_w, attn_b, d_attn, B");
     NA_REQUIRE_PTR(w_ih); NA_REQUIRE_PTR(w_hh); NA_REQUIRE_PTR(zeros); NA_REQUIRE_PTR(dw_ih); NA_REQUIRE_PTR(dw_hh);
     NA_REQUIRE_PTR(db); NA_REQUIRE_PTR(scratch);
     NA_OPTIONAL_PTR(in_mask); NA_OPTIONAL_PTR(din);
@@ -683,19 +834,22 @@ extern "C" int na_lstm_bwd_bf16(int64_t layer, const void* act_in, const void* h
     const int KI = layer == 0 ? 8 : 48;
     // scratch: [packed_r bf16: 24*96*8*2 B = 36,864 B][partials fp32]
     __nv_bfloat16* packed_r = reinterpret_cast<__nv_bfloat16*>(scratch);
-    float* partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 36864);
+    float* attn_partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 36864);        // [148][49]
+    float* partial = attn_partial + 148 * 52;
     tc::pack_bwd_r_kernel<<<32, 256, 0, st>>>(w_ih, w_hh, KI, packed_r);
     count_launch();
     // the forward pack holds B0 (8 chunks) then B1 (14 chunks)
     const unsigned char* pg = reinterpret_cast<const unsigned char*>(packed_fwd) + (layer == 0 ? 0 : 8 * tc::kBChunk);
     int grid = 0, rc;
     if (layer == 0)
-        rc = tc::launch_bwd<8>(act_in, h, cstate, dh_out, pg, packed_r, zeros, nullptr, 0, 65536u, 1.0f, nullptr, partial, T, Bp,
-                               st, &grid);
+        rc = tc::launch_bwd<8>(act_in, h, cstate, dh_out, pg, packed_r, zeros, nullptr, 0, 65536u, 1.0f, nullptr, partial,
+                               nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, T, Bp, st, &grid);
     else
         rc = tc::launch_bwd<48>(act_in, h, cstate, dh_out, pg, packed_r, zeros, in_mask, seed, (uint32_t)thresh16, drop_scale, din,
-                                partial, T, Bp, st, &grid);
+                                partial, dz, stats, zpool, attn_w, attn_b, B, attn_partial, T, Bp, st, &grid);
     if (rc) return rc;
+    if (dz != nullptr)
+        if ((rc = reduce_partials(attn_partial, d_attn, grid, tc::kH + 1, st))) return rc;
     const int NW = layer == 0 ? 64 : 112;
     tc::reduce_dw_kernel<<<(tc::kN * NW + 255) / 256, 256, 0, st>>>(partial, grid, KI, dw_ih, dw_hh, db);
     count_launch();

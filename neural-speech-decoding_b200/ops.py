@@ -64,7 +64,7 @@ def _stream() -> int:
 def all_custom_ops():
     return [window_zscore, pack_lstm_layer, lstm_layer_fwd, lstm_layer_bwd, lstm_layer_wgrad, head_fwd,
             head_bwd, trial_mean, decoder_pack_bf16, decoder_infer_bf16, lstm2_fwd_train_bf16, lstm_bwd_bf16,
-            dropout_mask_u8]
+            dropout_mask_u8, head_tail_fwd, head_tail_bwd]
 
 
 def launch_count() -> int:
@@ -437,32 +437,83 @@ def decoder_train_forward(x: Tensor, lstm_params, head_params, p: float, zscore:
 # ------------------------------------------------------------------------------------------
 @torch.library.custom_op("neuroalpha::lstm2_fwd_train_bf16", mutates_args=(), device_types="cuda")
 def lstm2_fwd_train_bf16(x_tmp: Tensor, packed: Tensor, mask: Optional[Tensor], seed: int, thresh16: int,
-                         drop_scale: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """Training forward of the 2-layer LSTM on tcgen05.  x_tmp fp16 TMP [T,Bp,8] (Bp % 128 == 0).
-    Inter-layer dropout: explicit ``mask`` u8 [T,Bp,48], or (mask None, thresh16 < 65536) the in-kernel
-    counter-based generator keyed by ``seed`` (keep probability thresh16/65536), or none (thresh16 = 65536).
-    -> (h0 TCL, h0d TCL or empty, c0 TMP, h1 TCL, h1f TMP, c1 TMP)."""
-    _require_cuda(x_tmp, packed, mask)
+                         drop_scale: float, attn_w: Tensor, attn_b: Tensor,
+                         B: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Training forward of the 2-layer LSTM on tcgen05 with the attention pool fused.  x_tmp fp16 TMP
+    [T,Bp,8] (Bp % 128 == 0).  Inter-layer dropout: explicit ``mask`` u8 [T,Bp,48], or (mask None, thresh16 <
+    65536) the in-kernel counter-based generator keyed by ``seed``, or none (thresh16 = 65536).
+    -> (h0 TCL, h0d TCL or empty, c0 TCL32, h1 TCL, c1 TCL32, zpool [B,48], stats [B,2])."""
+    _require_cuda(x_tmp, packed, mask, attn_w, attn_b)
     T, Bp, _ = x_tmp.shape
     dev = x_tmp.device
     has_drop = mask is not None or thresh16 < 65536
     tcl = lambda: torch.empty((T, Bp // TC_TILE, 6, TC_TILE, 8), dtype=TC_VALUE_DTYPE, device=dev)
-    tmp = lambda: torch.empty((T, Bp, 48), dtype=torch.float32, device=dev)
-    h0, h1, c0, h1f, c1 = tcl(), tcl(), tmp(), tmp(), tmp()
+    tcl32 = lambda: torch.empty((T, Bp // TC_TILE, 12, TC_TILE, 4), dtype=torch.float32, device=dev)
+    h0, h1, c0, c1 = tcl(), tcl(), tcl32(), tcl32()
     h0d = tcl() if has_drop else torch.empty((0,), dtype=TC_VALUE_DTYPE, device=dev)
+    zpool = torch.empty((B, 48), dtype=torch.float32, device=dev)
+    stats = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    aw, ab = _f32c(attn_w), _f32c(attn_b)
     _lib.call("na_lstm2_fwd_train_bf16", x_tmp.data_ptr(), packed.data_ptr(), _ptr(mask), int(seed), int(thresh16),
-              float(drop_scale), h0.data_ptr(), _ptr(h0d) if has_drop else None, c0.data_ptr(), h1.data_ptr(),
-              h1f.data_ptr(), c1.data_ptr(), T, Bp, _stream())
-    return h0, h0d, c0, h1, h1f, c1
+              float(drop_scale), h0.data_ptr(), _ptr(h0d) if has_drop else None, c0.data_ptr(), h1.data_ptr(), None,
+              c1.data_ptr(), aw.data_ptr(), ab.data_ptr(), zpool.data_ptr(), stats.data_ptr(), B, T, Bp, _stream())
+    return h0, h0d, c0, h1, c1, zpool, stats
 
 
 @lstm2_fwd_train_bf16.register_fake
-def _(x_tmp, packed, mask, seed, thresh16, drop_scale):
+def _(x_tmp, packed, mask, seed, thresh16, drop_scale, attn_w, attn_b, B):
     T, Bp, _ = x_tmp.shape
     tcl = lambda: x_tmp.new_empty((T, Bp // TC_TILE, 6, TC_TILE, 8))
-    tmp = lambda: x_tmp.new_empty((T, Bp, 48), dtype=torch.float32)
+    tcl32 = lambda: x_tmp.new_empty((T, Bp // TC_TILE, 12, TC_TILE, 4), dtype=torch.float32)
     has_drop = mask is not None or thresh16 < 65536
-    return tcl(), (tcl() if has_drop else x_tmp.new_empty((0,))), tmp(), tcl(), tmp(), tmp()
+    return (tcl(), (tcl() if has_drop else x_tmp.new_empty((0,))), tcl32(), tcl(), tcl32(),
+            x_tmp.new_empty((B, 48), dtype=torch.float32), x_tmp.new_empty((B, 2), dtype=torch.float32))
+
+
+@torch.library.custom_op("neuroalpha::head_tail_fwd", mutates_args=(), device_types="cuda")
+def head_tail_fwd(zpool: Tensor, params: Sequence[Tensor], rrelu_slope: Optional[Tensor], drop_mask: Optional[Tensor],
+                  drop_scale: float, want_probs: bool) -> Tuple[Tensor, Tensor]:
+    """LayerNorm -> fc0 -> RReLU -> dropout -> fc3 (+softmax) on an already pooled z [B,H] (lstm_eeg_model.py:38-39)."""
+    _require_cuda(zpool, rrelu_slope, drop_mask, *params)
+    B, H = zpool.shape
+    NC = params[6].shape[0]
+    logits = torch.empty((B, NC), dtype=torch.float32, device=zpool.device)
+    probs = torch.empty((B, NC) if want_probs else (0,), dtype=torch.float32, device=zpool.device)
+    _lib.call("na_head_tail_fwd_f32", zpool.data_ptr(), *[p.data_ptr() for p in params], _ptr(rrelu_slope),
+              _ptr(drop_mask), float(drop_scale), logits.data_ptr(), _ptr(probs) if want_probs else None, B, H, NC,
+              _stream())
+    return logits, probs
+
+
+@head_tail_fwd.register_fake
+def _(zpool, params, rrelu_slope, drop_mask, drop_scale, want_probs):
+    B, NC = zpool.shape[0], params[6].shape[0]
+    return zpool.new_empty((B, NC)), zpool.new_empty((B, NC) if want_probs else (0,))
+
+
+@torch.library.custom_op("neuroalpha::head_tail_bwd", mutates_args=(), device_types="cuda")
+def head_tail_bwd(dlogits: Tensor, zpool: Tensor, params: Sequence[Tensor], rrelu_slope: Optional[Tensor],
+                  drop_mask: Optional[Tensor], drop_scale: float) -> Tuple[Tensor, Tensor]:
+    """Backward of head_tail_fwd: (dz [B,H], dparams packed like head_bwd with the attn slots zeroed)."""
+    _require_cuda(dlogits, zpool, rrelu_slope, drop_mask, *params)
+    B, H = zpool.shape
+    NC = dlogits.shape[1]
+    dev = zpool.device
+    dlogits = _f32c(dlogits)
+    dz = torch.empty((B, H), dtype=torch.float32, device=dev)
+    dparams = torch.empty((_lib.query("na_head_param_floats", H, NC),), dtype=torch.float32, device=dev)
+    partials = torch.empty((_lib.query("na_head_partial_floats", B, H, NC),), dtype=torch.float32, device=dev)
+    _lib.call("na_head_tail_bwd_f32", dlogits.data_ptr(), zpool.data_ptr(), *[p.data_ptr() for p in params],
+              _ptr(rrelu_slope), _ptr(drop_mask), float(drop_scale), dz.data_ptr(), dparams.data_ptr(),
+              partials.data_ptr(), B, H, NC, _stream())
+    return dz, dparams
+
+
+@head_tail_bwd.register_fake
+def _(dlogits, zpool, params, rrelu_slope, drop_mask, drop_scale):
+    H, NC = zpool.shape[1], dlogits.shape[1]
+    n = H + 1 + 2 * H + FC_HIDDEN * H + FC_HIDDEN + FC_HIDDEN * NC + NC
+    return zpool.new_empty(zpool.shape), zpool.new_empty((n,))
 
 
 @torch.library.custom_op("neuroalpha::dropout_mask_u8", mutates_args=(), device_types="cuda")
@@ -480,31 +531,39 @@ def _(like, seed, thresh16, T, Bp):
 
 
 @torch.library.custom_op("neuroalpha::lstm_bwd_bf16", mutates_args=(), device_types="cuda")
-def lstm_bwd_bf16(layer: int, act_in: Tensor, h: Tensor, c: Tensor, dh: Tensor, packed: Tensor, w_ih: Tensor,
-                  w_hh: Tensor, in_mask: Optional[Tensor], seed: int, thresh16: int,
-                  drop_scale: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """Fused BPTT + weight gradients of one layer on tcgen05 -> (din TMP or empty, dW_ih, dW_hh, db)."""
-    _require_cuda(act_in, h, c, dh, packed, w_ih, w_hh, in_mask)
-    T, Bp, H = c.shape
+def lstm_bwd_bf16(layer: int, act_in: Tensor, h: Tensor, c: Tensor, dh: Optional[Tensor], packed: Tensor, w_ih: Tensor,
+                  w_hh: Tensor, in_mask: Optional[Tensor], seed: int, thresh16: int, drop_scale: float,
+                  head: Sequence[Tensor], B: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Fused BPTT + weight gradients of one layer on tcgen05 -> (din TCL32 or empty, dW_ih, dW_hh, db, d_attn).
+    ``head`` = [] (dh given) or [dz, stats, zpool, attn_w, attn_b] for layer 1 with the head backward fused:
+    dh_t is rebuilt per step inside the kernel and d_attn [49] = (d attn_w | d attn_b) is returned."""
+    _require_cuda(act_in, h, c, dh, packed, w_ih, w_hh, in_mask, *head)
+    T, NT = c.shape[0], c.shape[1]
+    Bp, H = NT * TC_TILE, 48
     dev = c.device
     w_ih, w_hh = _f32c(w_ih), _f32c(w_hh)
-    din = torch.empty((T, Bp, H) if layer == 1 else (0,), dtype=torch.float32, device=dev)
+    din = torch.empty((T, NT, 12, TC_TILE, 4) if layer == 1 else (0,), dtype=torch.float32, device=dev)
     dw_ih, dw_hh = torch.empty_like(w_ih), torch.empty_like(w_hh)
     db = torch.empty((4 * H,), dtype=torch.float32, device=dev)
+    fused = len(head) > 0
+    d_attn = torch.empty((H + 1,) if fused else (0,), dtype=torch.float32, device=dev)
+    hp = [_f32c(t) for t in head]
     zeros = torch.zeros((12288,), dtype=torch.uint8, device=dev)
     scratch = torch.empty((36864 + 4 * _lib.query("na_train_bf16_partial_floats"),), dtype=torch.uint8, device=dev)
-    _lib.call("na_lstm_bwd_bf16", int(layer), act_in.data_ptr(), h.data_ptr(), c.data_ptr(), _f32c(dh).data_ptr(),
-              packed.data_ptr(), w_ih.data_ptr(), w_hh.data_ptr(), zeros.data_ptr(), _ptr(in_mask), int(seed), int(thresh16),
-              float(drop_scale),
+    _lib.call("na_lstm_bwd_bf16", int(layer), act_in.data_ptr(), h.data_ptr(), c.data_ptr(),
+              None if fused else _f32c(dh).data_ptr(), packed.data_ptr(), w_ih.data_ptr(), w_hh.data_ptr(),
+              zeros.data_ptr(), _ptr(in_mask), int(seed), int(thresh16), float(drop_scale),
               _ptr(din) if layer == 1 else None, dw_ih.data_ptr(), dw_hh.data_ptr(), db.data_ptr(), scratch.data_ptr(),
+              *([t.data_ptr() for t in hp] if fused else [None] * 5), int(B), _ptr(d_attn) if fused else None,
               T, Bp, _stream())
-    return din, dw_ih, dw_hh, db
+    return din, dw_ih, dw_hh, db, d_attn
 
 
 @lstm_bwd_bf16.register_fake
-def _(layer, act_in, h, c, dh, packed, w_ih, w_hh, in_mask, seed, thresh16, drop_scale):
+def _(layer, act_in, h, c, dh, packed, w_ih, w_hh, in_mask, seed, thresh16, drop_scale, head, B):
     return (c.new_empty(c.shape if layer == 1 else (0,)), w_ih.new_empty(w_ih.shape, dtype=torch.float32),
-            w_hh.new_empty(w_hh.shape, dtype=torch.float32), c.new_empty((4 * c.shape[2],)))
+            w_hh.new_empty(w_hh.shape, dtype=torch.float32), c.new_empty((192,)),
+            c.new_empty((49,) if len(head) else (0,)))
 
 
 class DecoderFunctionTC(torch.autograd.Function):
@@ -530,11 +589,11 @@ class DecoderFunctionTC(torch.autograd.Function):
             mask, scale1 = drop1, scale
         xt = window_zscore(x.detach(), T, T, zscore, True, NA_F16, TC_TILE)
         packed = decoder_pack_bf16(lstm_flat)
-        h0, h0d, c0, h1, h1f, c1 = lstm2_fwd_train_bf16(xt, packed, mask, seed, thresh16, scale1)
-        logits, _, stats, zpool = head_fwd(h1f, B, head, rrelu_slope, drop2_mask, scale, False, True)
+        h0, h0d, c0, h1, c1, zpool, stats = lstm2_fwd_train_bf16(xt, packed, mask, seed, thresh16, scale1, head[0], head[1], B)
+        logits, _ = head_tail_fwd(zpool, head, rrelu_slope, drop2_mask, scale, False)
         w = [_f32c(t) for t in lstm_flat]
         opt = [t for t in (mask, rrelu_slope, drop2_mask) if t is not None]
-        ctx.save_for_backward(xt, h0, h0d, c0, h1, h1f, c1, packed, stats, zpool, w[0], w[1], w[4], w[5], *head, *opt)
+        ctx.save_for_backward(xt, h0, h0d, c0, h1, c1, packed, stats, zpool, w[0], w[1], w[4], w[5], *head, *opt)
         ctx.meta = (scale, B, mask is not None, rrelu_slope is not None, drop2_mask is not None, seed, thresh16, scale1)
         return logits
 
@@ -543,9 +602,9 @@ class DecoderFunctionTC(torch.autograd.Function):
         scale, B, has_d1, has_rr, has_d2, seed, thresh16, scale1 = ctx.meta
         has_drop = has_d1 or thresh16 < 65536
         sv = list(ctx.saved_tensors)
-        xt, h0, h0d, c0, h1, h1f, c1, packed, stats, zpool, w_ih0, w_hh0, w_ih1, w_hh1 = sv[:14]
-        head = sv[14:22]
-        rest = sv[22:]
+        xt, h0, h0d, c0, h1, c1, packed, stats, zpool, w_ih0, w_hh0, w_ih1, w_hh1 = sv[:13]
+        head = sv[13:21]
+        rest = sv[21:]
         d1 = rest.pop(0) if has_d1 else None
         rr = rest.pop(0) if has_rr else None
         d2 = rest.pop(0) if has_d2 else None
@@ -556,11 +615,13 @@ class DecoderFunctionTC(torch.autograd.Function):
         amax = dlogits.detach().abs().max().clamp_min(1e-30)
         s = torch.pow(2.0, 11.0 - torch.ceil(torch.log2(amax)))      # (torch.exp2 would JIT-compile via nvrtc)
         inv_s = 1.0 / s
-        dh1, dparams = head_bwd((dlogits * s).contiguous(), h1f, stats, zpool, head, rr, d2, scale)
+        # head tail backward -> dz; the time loop of the head backward (dh_t, d attn) runs inside the layer-1 BPTT kernel
+        dz, dparams = head_tail_bwd((dlogits * s).contiguous(), zpool, head, rr, d2, scale)
+        din1, dw_ih1, dw_hh1, db1, d_attn = lstm_bwd_bf16(1, h0d if has_drop else h0, h1, c1, None, packed, w_ih1, w_hh1,
+                                                          d1, seed, thresh16, scale1, [dz, stats, zpool, head[0], head[1]], B)
+        dparams = torch.cat([d_attn, dparams[H + 1:]])
         head_grads = split_head_grads(dparams * inv_s, H, NC)
-        din1, dw_ih1, dw_hh1, db1 = lstm_bwd_bf16(1, h0d if has_drop else h0, h1, c1, dh1, packed, w_ih1, w_hh1, d1, seed,
-                                                  thresh16, scale1)
-        _, dw_ih0, dw_hh0, db0 = lstm_bwd_bf16(0, xt, h0, c0, din1, packed, w_ih0, w_hh0, None, 0, 65536, 1.0)
+        _, dw_ih0, dw_hh0, db0, _ = lstm_bwd_bf16(0, xt, h0, c0, din1, packed, w_ih0, w_hh0, None, 0, 65536, 1.0, [], B)
         db0, db1 = db0 * inv_s, db1 * inv_s
         return (None, None, None, None, None, None, dw_ih0 * inv_s, dw_hh0 * inv_s, db0, db0.clone(),
                 dw_ih1 * inv_s, dw_hh1 * inv_s, db1, db1.clone(), *head_grads)
