@@ -362,6 +362,7 @@ class DecoderFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, num_layers, p, zscore, drop1_masks, rrelu_slope, drop2_mask, *params):
         _require_cuda(x, *params)
+        ctx.param_dtypes = [t.dtype for t in params]
         B, T, C = x.shape
         lstm_flat, head = params[:4 * num_layers], [_f32c(t) for t in params[4 * num_layers:]]
         scale = 1.0 / (1.0 - p) if p < 1.0 else 0.0
@@ -422,7 +423,8 @@ class DecoderFunction(torch.autograd.Function):
             if zscore:
                 raise RuntimeError("gradient w.r.t. x through the z-score front stage is not implemented")
             dx = dh[:, :B].permute(1, 0, 2).contiguous().reshape(xshape)
-        return (dx, None, None, None, None, None, None, *lstm_grads, *head_grads)
+        grads = [g.to(dt) if g.dtype != dt else g for g, dt in zip([*lstm_grads, *head_grads], ctx.param_dtypes)]
+        return (dx, None, None, None, None, None, None, *grads)
 
 
 def decoder_train_forward(x: Tensor, lstm_params, head_params, p: float, zscore: bool = False,
@@ -576,6 +578,7 @@ class DecoderFunctionTC(torch.autograd.Function):
         """``drop1``: None (no inter-layer dropout), a u8 keep-mask [T,Bp,48], or ``(seed, thresh16)`` for the
         in-kernel counter-based generator (no mask tensor at all)."""
         _require_cuda(x, *params)
+        ctx.param_dtypes = [t.dtype for t in params]
         if ctx.needs_input_grad[0]:
             raise RuntimeError("the tensor-core training tier does not produce d/dx; use compute_dtype=float32")
         B, T, C = x.shape
@@ -623,8 +626,10 @@ class DecoderFunctionTC(torch.autograd.Function):
         head_grads = split_head_grads(dparams * inv_s, H, NC)
         _, dw_ih0, dw_hh0, db0, _ = lstm_bwd_bf16(0, xt, h0, c0, din1, packed, w_ih0, w_hh0, None, 0, 65536, 1.0, [], B)
         db0, db1 = db0 * inv_s, db1 * inv_s
-        return (None, None, None, None, None, None, dw_ih0 * inv_s, dw_hh0 * inv_s, db0, db0.clone(),
-                dw_ih1 * inv_s, dw_hh1 * inv_s, db1, db1.clone(), *head_grads)
+        grads = [dw_ih0 * inv_s, dw_hh0 * inv_s, db0, db0.clone(), dw_ih1 * inv_s, dw_hh1 * inv_s, db1, db1.clone(),
+                 *head_grads]
+        grads = [g.to(dt) if g.dtype != dt else g for g, dt in zip(grads, ctx.param_dtypes)]   # .bfloat16() modules
+        return (None, None, None, None, None, None, *grads)
 
 
 def decoder_train_forward_tc(x: Tensor, lstm_params, head_params, p: float, zscore: bool = False,

@@ -202,3 +202,42 @@ def test_in_kernel_dropout_equals_mask_tensor_mode(dev, checkpoint):
     assert torch.equal(a, b) and not torch.equal(a, c)
     for g in ga:
         assert torch.isfinite(g).all()
+
+
+def test_edge_shapes_and_bfloat16_module(dev, checkpoint, windows):
+    """T = 1 and T = 2 windows (wavefront start-up), the z-score front stage on the tensor-core tier, and a
+    module converted with .bfloat16() (bf16 parameters and inputs in, bf16 logits / gradients out)."""
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    gen = torch.Generator().manual_seed(9)
+    refm = RefEEGLSTM().eval()
+    refm.load_state_dict(checkpoint, strict=True)
+    m = bf16_model(dev, checkpoint)
+    for T in (1, 2, 3):
+        x = torch.randn(200, T, 8, generator=gen) * 2.73
+        with torch.inference_mode():
+            got = m(x.to(dev)).cpu().numpy()
+            want = refm(x).numpy()
+        assert rel(got, want) < BF16_TOL, T
+        y = torch.randint(0, 3, (200,), generator=gen)
+        m.zero_grad()
+        torch.nn.functional.cross_entropy(m(x.to(dev)), y.to(dev)).backward()      # T = 1: no recurrence at all
+        assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+    # z-score front stage (K1 normalises, then the same decoder)
+    m.zscore_input = True
+    X = torch.from_numpy(windows["X"][:40])
+    with torch.inference_mode():
+        got = m(X.to(dev)).cpu().numpy()
+        want = refm(torch.from_numpy(no.zscore_window(X.numpy()))).numpy()
+    assert rel(got, want) < BF16_TOL
+    m.zscore_input = False
+    # .bfloat16() module
+    mb = EEG_LSTM()
+    mb.load_state_dict(checkpoint, strict=True)
+    mb = mb.to(dev).bfloat16()
+    xb = X[:16].to(dev).bfloat16()
+    with torch.inference_mode():
+        out = mb.eval()(xb)
+    assert out.dtype == torch.bfloat16 and rel(out.float().cpu().numpy(), refm(X[:16]).detach().numpy()) < 5e-2
+    mb.train()
+    torch.nn.functional.cross_entropy(mb(xb).float(), torch.randint(0, 3, (16,)).to(dev)).backward()
+    assert all(p.grad is not None and p.grad.dtype == torch.bfloat16 for p in mb.parameters())
