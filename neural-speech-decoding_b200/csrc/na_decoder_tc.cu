@@ -192,19 +192,21 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
         } else if (warp == kMmaWarp) {
             // ================= MMA issuer ============================================================
             if (lane == 0) {
-                const uint32_t b0a = smem_u32(S.b0), b1a = smem_u32(S.b1);
+                const uint64_t d_b0 = umma_desc(smem_u32(S.b0), kBChunk, 128), d_b1 = umma_desc(smem_u32(S.b1), kBChunk, 128);
+                const uint64_t d_x0 = umma_desc(smem_u32(S.x[0]), kAChunk, 128);
+                const uint64_t d_h0[2] = {umma_desc(smem_u32(S.h0[0]), kAChunk, 128), umma_desc(smem_u32(S.h0[1]), kAChunk, 128)};
+                const uint64_t d_h1 = umma_desc(smem_u32(S.h1), kAChunk, 128), d_onez = umma_desc(smem_u32(S.onez), kAChunk, 128);
                 for (int t = 0; t <= T; ++t) {
                     if (t < T) {                                   // layer 0, step n
                         const int n = n0 + t, s = n % kXStages, u = n / kXStages;
                         mbar_wait(&S.x_full[s], u & 1);
                         mbar_wait(&S.h0_ready[(n + 1) & 1], ((n - 1) >> 1) & 1);     // h0_{n-1} written, D0 drained
                         tc_fence_after();
-                        const uint32_t hprev = smem_u32(S.h0[(n + 1) & 1]);
-                        umma_bf16(tmem_d0, umma_desc(smem_u32(S.x[s]), kAChunk, 128), umma_desc(b0a, kBChunk, 128), 0u);
+                        const uint64_t hprev = d_h0[(n + 1) & 1];
+                        umma_bf16(tmem_d0, desc_adv(d_x0, s * 2 * kAChunk), d_b0, 0u);
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
-                            umma_bf16(tmem_d0, umma_desc(hprev + 2 * i * kAChunk, kAChunk, 128),
-                                      umma_desc(b0a + (2 + 2 * i) * kBChunk, kBChunk, 128), 1u);
+                            umma_bf16(tmem_d0, desc_adv(hprev, 2 * i * kAChunk), desc_adv(d_b0, (2 + 2 * i) * kBChunk), 1u);
                         umma_commit(&S.x_empty[s]);
                         umma_commit(&S.d0_full);
                     }
@@ -213,17 +215,14 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                         mbar_wait(&S.h0_ready[m & 1], (m >> 1) & 1);                 // h0_m written
                         mbar_wait(&S.h1_ready, (m - 1) & 1);                         // h1_{m-1} written, D1 drained
                         tc_fence_after();
-                        const uint32_t hin = smem_u32(S.h0[m & 1]), hrec = smem_u32(S.h1);
+                        const uint64_t hin = d_h0[m & 1];
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
-                            umma_bf16(tmem_d1, umma_desc(hin + 2 * i * kAChunk, kAChunk, 128),
-                                      umma_desc(b1a + (2 * i) * kBChunk, kBChunk, 128), i == 0 ? 0u : 1u);
+                            umma_bf16(tmem_d1, desc_adv(hin, 2 * i * kAChunk), desc_adv(d_b1, 2 * i * kBChunk), i == 0 ? 0u : 1u);
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
-                            umma_bf16(tmem_d1, umma_desc(hrec + 2 * i * kAChunk, kAChunk, 128),
-                                      umma_desc(b1a + (6 + 2 * i) * kBChunk, kBChunk, 128), 1u);
-                        umma_bf16(tmem_d1, umma_desc(smem_u32(S.onez), kAChunk, 128),
-                                  umma_desc(b1a + 12 * kBChunk, kBChunk, 128), 1u);
+                            umma_bf16(tmem_d1, desc_adv(d_h1, 2 * i * kAChunk), desc_adv(d_b1, (6 + 2 * i) * kBChunk), 1u);
+                        umma_bf16(tmem_d1, d_onez, desc_adv(d_b1, 12 * kBChunk), 1u);
                         umma_commit(&S.d1_full);
                         umma_commit(&S.h0_free[m & 1]);
                     }

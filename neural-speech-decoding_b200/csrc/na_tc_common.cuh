@@ -26,6 +26,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
+// Advance a descriptor's start address by `bytes` (a multiple of 16; the 14-bit address field never carries
+// for shared-memory offsets).  The MMA-issuing thread builds each base descriptor ONCE and steps it with
+// one add per MMA: issuing 30+ MMAs per step with a full descriptor rebuild each (~16 instructions on the
+// uniform datapath) was the serial bottleneck of the BPTT kernel.
+__device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
 // 16-bit operand formats of the tier.  VALUE operands (EEG samples, h, weights, bias) have a bounded
 // range, so they are IEEE fp16: 3 more mantissa bits than bf16 at the same tensor throughput -- the
 // weight rounding is a FIXED perturbation applied at every one of the 1250 dependent steps, so those

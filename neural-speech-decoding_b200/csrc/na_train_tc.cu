@@ -138,19 +138,22 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                 }
         } else if (warp == 16) {
             if (lane == 0) {
-                const uint32_t b0a = smem_u32(S.b0), b1a = smem_u32(S.b1);
+                const uint64_t d_b0 = umma_desc(smem_u32(S.b0), kBChunk, 128), d_b1 = umma_desc(smem_u32(S.b1), kBChunk, 128);
+                const uint64_t d_x0 = umma_desc(smem_u32(S.x[0]), kAChunk, 128);
+                const uint64_t d_h0[2] = {umma_desc(smem_u32(S.h0[0]), kAChunk, 128), umma_desc(smem_u32(S.h0[1]), kAChunk, 128)};
+                const uint64_t d_h0d[2] = {umma_desc(smem_u32(S.h0d[0]), kAChunk, 128), umma_desc(smem_u32(S.h0d[1]), kAChunk, 128)};
+                const uint64_t d_h1 = umma_desc(smem_u32(S.h1), kAChunk, 128), d_onez = umma_desc(smem_u32(S.onez), kAChunk, 128);
                 for (int t = 0; t <= T; ++t) {
                     if (t < T) {
                         const int n = n0 + t, s = n % kXStagesT, u = n / kXStagesT;
                         mbar_wait(&S.x_full[s], u & 1);
                         mbar_wait(&S.h0_ready[(n + 1) & 1], ((n - 1) >> 1) & 1);
                         tc_fence_after();
-                        const uint32_t hprev = smem_u32(S.h0[(n + 1) & 1]);
-                        umma_bf16(tmem_d0, umma_desc(smem_u32(S.x[s]), kAChunk, 128), umma_desc(b0a, kBChunk, 128), 0u);
+                        const uint64_t hprev = d_h0[(n + 1) & 1];
+                        umma_bf16(tmem_d0, desc_adv(d_x0, s * 2 * kAChunk), d_b0, 0u);
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
-                            umma_bf16(tmem_d0, umma_desc(hprev + 2 * i * kAChunk, kAChunk, 128),
-                                      umma_desc(b0a + (2 + 2 * i) * kBChunk, kBChunk, 128), 1u);
+                            umma_bf16(tmem_d0, desc_adv(hprev, 2 * i * kAChunk), desc_adv(d_b0, (2 + 2 * i) * kBChunk), 1u);
                         umma_commit(&S.x_empty[s]);
                         umma_commit(&S.d0_full);
                     }
@@ -159,17 +162,14 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                         mbar_wait(&S.h0_ready[m & 1], (m >> 1) & 1);
                         mbar_wait(&S.h1_ready, (m - 1) & 1);
                         tc_fence_after();
-                        const uint32_t hin = smem_u32(drop ? S.h0d[m & 1] : S.h0[m & 1]), hrec = smem_u32(S.h1);
+                        const uint64_t hin = drop ? d_h0d[m & 1] : d_h0[m & 1];
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
-                            umma_bf16(tmem_d1, umma_desc(hin + 2 * i * kAChunk, kAChunk, 128),
-                                      umma_desc(b1a + (2 * i) * kBChunk, kBChunk, 128), i == 0 ? 0u : 1u);
+                            umma_bf16(tmem_d1, desc_adv(hin, 2 * i * kAChunk), desc_adv(d_b1, 2 * i * kBChunk), i == 0 ? 0u : 1u);
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
-                            umma_bf16(tmem_d1, umma_desc(hrec + 2 * i * kAChunk, kAChunk, 128),
-                                      umma_desc(b1a + (6 + 2 * i) * kBChunk, kBChunk, 128), 1u);
-                        umma_bf16(tmem_d1, umma_desc(smem_u32(S.onez), kAChunk, 128),
-                                  umma_desc(b1a + 12 * kBChunk, kBChunk, 128), 1u);
+                            umma_bf16(tmem_d1, desc_adv(d_h1, 2 * i * kAChunk), desc_adv(d_b1, (6 + 2 * i) * kBChunk), 1u);
+                        umma_bf16(tmem_d1, d_onez, desc_adv(d_b1, 12 * kBChunk), 1u);
                         umma_commit(&S.d1_full);
                         umma_commit(&S.h0_free[m & 1]);
                     }
@@ -436,7 +436,14 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
             // The epilogue only needs R and G; W (dW accumulation) trails behind and is fenced by w_done
             // before the epilogue overwrites d(gates).
             if (lane == 0) {
-                const uint32_t bga = smem_u32(S.bg), bra = smem_u32(S.br), dga = smem_u32(S.dg);
+                // base descriptors, built once (see desc_adv)
+                const uint64_t d_bg = umma_desc(smem_u32(S.bg), kBChunk, 128);                 // forward B, K-major
+                const uint64_t d_br = umma_desc(smem_u32(S.br), C::kNR * 16, 128);             // [W_ih|W_hh]^T, K-major
+                const uint64_t d_dgk = umma_desc(smem_u32(S.dg), kAChunk, 128);                // d(gates) as K-major A (R)
+                const uint64_t d_dgm1 = umma_desc(smem_u32(S.dg), 128, kAChunk);               // d(gates)^T, MN-major A (W, rows 0..127)
+                const uint64_t d_dgm2 = umma_desc(smem_u32(S.dg) + 8 * kAChunk, 128, kAChunk); // rows 64..191
+                const uint64_t d_actk[2] = {umma_desc(smem_u32(S.act[0]), kAChunk, 128), umma_desc(smem_u32(S.act[1]), kAChunk, 128)};
+                const uint64_t d_actm[2] = {umma_desc(smem_u32(S.act[0]), 128, kAChunk), umma_desc(smem_u32(S.act[1]), 128, kAChunk)};
                 uint32_t dgp = k0;                // dg_ready phases consumed
                 for (int i = 0; i <= T; ++i) {
                     const uint32_t sp = (k0 + i - 1) & 1;
@@ -446,28 +453,27 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                         tc_fence_after();
 #pragma unroll
                         for (int ks = 0; ks < 12; ++ks)
-                            umma_bf16_i(tm_r, umma_desc(dga + 2 * ks * kAChunk, kAChunk, 128),
-                                        umma_desc(bra + 2 * ks * C::kNR * 16, C::kNR * 16, 128), kIdescR, ks == 0 ? 0u : 1u);
+                            umma_bf16_i(tm_r, desc_adv(d_dgk, 2 * ks * kAChunk), desc_adv(d_br, 2 * ks * C::kNR * 16), kIdescR,
+                                        ks == 0 ? 0u : 1u);
                     }
                     if (i < T) {
                         const uint32_t k = k0 + i, s = k & 1, u = k >> 1;
                         mbar_wait(&S.act_full[s], u & 1);
                         tc_fence_after();
-                        const uint32_t acta = smem_u32(S.act[s]);
+                        const uint64_t da = d_actk[s];
 #pragma unroll
                         for (int ks = 0; ks < C::kStageChunks / 2; ++ks)
-                            umma_bf16(tm_g, umma_desc(acta + 2 * ks * kAChunk, kAChunk, 128),
-                                      umma_desc(bga + 2 * ks * kBChunk, kBChunk, 128), ks == 0 ? 0u : 1u);
+                            umma_bf16(tm_g, desc_adv(da, 2 * ks * kAChunk), desc_adv(d_bg, 2 * ks * kBChunk), ks == 0 ? 0u : 1u);
                     }
                     umma_commit(&S.g_full);        // R(prev) and G(cur) done; i == T: tail (R only)
                     if (i >= 1) {
-                        const uint32_t acta = smem_u32(S.act[sp]);
+                        const uint64_t db = d_actm[sp];
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks) {
                             const uint32_t acc = (first_w && ks == 0) ? 0u : 1u;
-                            const uint64_t bdesc = umma_desc(acta + ks * 256, 128, kAChunk);
-                            umma_bf16_i(tm_w1, umma_desc(dga + ks * 256, 128, kAChunk), bdesc, kIdescW, acc);
-                            umma_bf16_i(tm_w2, umma_desc(dga + 8 * kAChunk + ks * 256, 128, kAChunk), bdesc, kIdescW, acc);
+                            const uint64_t bdesc = desc_adv(db, ks * 256);
+                            umma_bf16_i(tm_w1, desc_adv(d_dgm1, ks * 256), bdesc, kIdescW, acc);
+                            umma_bf16_i(tm_w2, desc_adv(d_dgm2, ks * 256), bdesc, kIdescW, acc);
                         }
                         first_w = false;
                         umma_commit(&S.act_free[sp]);
