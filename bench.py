@@ -316,12 +316,17 @@ def run_gpu_arm(args):
         "roofline": {
             "kernel": "decoder_infer_bf16_kernel (tcgen05/TMEM/TMA: K2+K3+K4 fused, whole decoder forward)",
             "bound": "tensor", "achieved": tc_tflops, "peak": peak, "unit": "TFLOP/s", "frac": tc_tflops / peak,
-            "peak_source": peaks["source"] + " cuBLAS bf16 (burst: kernel timed alone)", "traffic": None,
+            "peak_source": peaks["source"] + " cuBLAS bf16 (burst: kernel timed alone)",
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+            # (profiles/r1_tc_infer_ncu_full.csv: 409.7 MB + 5.6 MB at 40,960 windows), scaled to this launch
+            "traffic": 415.36e6 * n_win / 40960, "traffic_source": "profiles/r1_tc_infer_ncu_full.csv",
+            "algorithmic_bytes_per_launch": n_win * (T * C * 2 + NC * 8),
             "algorithmic_flops_per_launch": FWD_FLOPS_PER_WINDOW * n_win,
             "ms_per_launch": ms_tc,
             "per_timestep_latency_us": ms_tc * 1e3 / (T * tile_rounds),
             "note": "latency/MUFU-bound, not tensor-bound: 1250 dependent cell updates per window; each step needs "
-                    "5 MUFU (tanh) per hidden unit -> 3840 MUFU cycles per 128-window step for both layers",
+                    "5 MUFU (tanh) per hidden unit -> 3840 MUFU cycles per 128-window step for both layers "
+                    "(xu pipe 72-80 % busy in ncu); 16-bit operands are fp16 (see DESIGN.md section 5)",
             "k1_window_pack": {"kernel": "window_zscore_vec_kernel (fp32 -> time-major bf16)", "bound": "hbm",
                                "achieved": n_win * T * C * 6 / (ms_pack16 * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                "unit": "GB/s", "frac": n_win * T * C * 6 / (ms_pack16 * 1e-3) / 1e9 / peaks["hbm_gbs"]},
