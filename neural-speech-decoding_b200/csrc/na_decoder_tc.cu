@@ -392,14 +392,23 @@ decoder_infer_bf16_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
     }
 }
 
-int g_infer_hs = 2;      // epilogue warps per quarter and layer (na_set_tuning("tc_infer_hs", 1|2))
-void set_infer_hs(int hs) { g_infer_hs = hs == 1 ? 1 : 2; }
+// Kernel selection (na_set_tuning("tc_infer_hs", v)): 3 = v2, the software-pipelined kernel of na_decoder_tc2.cu
+// (default); 1 | 2 = the v1 kernel above with that many epilogue warps per quarter and layer (kept for A/B timing).
+int g_infer_hs = 3;
+void set_infer_hs(int hs) { g_infer_hs = (hs >= 1 && hs <= 3) ? hs : 3; }
+
+// na_decoder_tc2.cu
+int launch_pack_v2(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*,
+                   void*, cudaStream_t);
+int launch_infer_v2(const void*, const unsigned char*, const float*, const float*, const float*, const float*, const float*,
+                    const float*, const float*, const float*, float*, float*, int, int64_t, int64_t, int, int, cudaStream_t);
+constexpr int64_t kPackedV1Bytes = (int64_t)(kK0Chunks + kK1Chunks) * kBChunk;
 
 }  // namespace tc
 }  // namespace na
 
 extern "C" int64_t na_decoder_packed_bf16_bytes(void) {
-    return (int64_t)(na::tc::kK0Chunks + na::tc::kK1Chunks) * na::tc::kBChunk;
+    return 2 * na::tc::kPackedV1Bytes;      // [v1 section (training kernels, v1 inference) | v2 section (pre-scaled)]
 }
 
 extern "C" int na_decoder_pack_bf16(const float* w_ih0, const float* w_hh0, const float* b_ih0, const float* b_hh0,
@@ -412,7 +421,9 @@ extern "C" int na_decoder_pack_bf16(const float* w_ih0, const float* w_hh0, cons
     tc::pack_decoder_bf16_kernel<<<64, 256, 0, as_stream(stream)>>>(w_ih0, w_hh0, b_ih0, b_hh0, w_ih1, w_hh1, b_ih1, b_hh1,
                                                                     reinterpret_cast<__nv_bfloat16*>(packed));
     count_launch();
-    return check_launch("na_decoder_pack_bf16");
+    if (int rc = check_launch("na_decoder_pack_bf16")) return rc;
+    return tc::launch_pack_v2(w_ih0, w_hh0, b_ih0, b_hh0, w_ih1, w_hh1, b_ih1, b_hh1,
+                              reinterpret_cast<unsigned char*>(packed) + tc::kPackedV1Bytes, as_stream(stream));
 }
 
 extern "C" int na_decoder_infer_bf16(const void* x_bf16_tmp, const void* packed, const float* attn_w,
@@ -435,8 +446,12 @@ extern "C" int na_decoder_infer_bf16(const void* x_bf16_tmp, const void* packed,
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
-    const size_t smem = sizeof(tc::Smem) + 1024;
     const int hs = tc::g_infer_hs;
+    if (hs == 3)
+        return tc::launch_infer_v2(x_bf16_tmp, reinterpret_cast<const unsigned char*>(packed) + tc::kPackedV1Bytes, attn_w, attn_b,
+                                   ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, (int)T, B, Bp, (int)NC, sms,
+                                   as_stream(stream));
+    const size_t smem = sizeof(tc::Smem) + 1024;
     cudaError_t e = hs == 2 ? cudaFuncSetAttribute(tc::decoder_infer_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                             : cudaFuncSetAttribute(tc::decoder_infer_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));

@@ -1,0 +1,457 @@
+// Tensor-core tier, inference kernel v2: software-pipelined epilogue.
+//
+// Measured on B200 (scripts/time_tiles.py): a tile step of the v1 kernel (na_decoder_tc.cu) costs the same
+// 2.67 us whether one or four TMEM lane quarters are active, i.e. the bound is the MUFU pipe of ONE SM
+// sub-partition (a warp can only read the TMEM lanes of its own quarter, so the 32 windows of a quarter are
+// always processed on one scheduler: 32 x 48 units x 2 layers x 5 tanh / 4 lanes per clock = 3,840 cycles),
+// and v1 leaves that pipe idle ~26 % of the step: its layer-0 and layer-1 epilogue warps finish together,
+// then both wait for the two MMAs (commit -> mbarrier -> tcgen05.ld round trips).
+//
+// v2 removes the bubble by construction.  Each epilogue warp owns (quarter q, unit group g: 16 units) of BOTH
+// layers and alternates   layer-0 step t  ->  layer-1 step t-1  ->  layer-0 step t+1 ...
+// The MMA of a layer is issued when that layer's epilogue phase ends and has the whole other phase
+// (~1,900 cycles of MUFU work) to complete, so a warp never waits for the tensor pipe in steady state.
+//   * 12 epilogue warps (4 quarters x 3 unit groups), warp 12 = MMA issuer, warp 13 = TMA producer + TMEM
+//     allocator: 448 threads, 1 CTA / SM, persistent over 128-window tiles.
+//   * No per-step cross-warp exchange: the attention score s_t = w_a.h1_t + b_a (lstm_eeg_model.py:35) is
+//     computed BY THE TENSOR CORE as two extra accumulator columns of the next layer-1 MMA (h1_t is that
+//     MMA's recurrent A operand anyway): B1 has N = 208 rows, row 192 = fp16(w_a) (+ b_a on the ones
+//     column), row 193 = the fp16 rounding residual of w_a.  The online-softmax pooling of step t therefore
+//     runs one step late, on the h1_t the thread kept in registers; one small N = 16 "flush" MMA after the
+//     last step delivers s_{T-1}.
+//   * Fewer CUDA-core instructions per cell: the 0.5 of sigmoid(x) = 0.5 tanh(x/2) + 0.5 is folded into the
+//     packed weights (exact power-of-two scaling of the i, f, o rows), and the hidden state is carried as
+//     H = 2h (the 0.5 folded into every weight column that multiplies h):
+//         w = fma(Tf, c, c);  u = fma(Ti, Tg, Tg);  c = 0.5 (w + u);  H = fma(To, tanh c, tanh c)
+//     5 MUFU + 5 FMA-pipe ops per cell.
+//   * h_{-1} = 0 is handled by NOT issuing the recurrent MMAs of the first step (no buffer zeroing).
+#include "na_tc_common.cuh"
+
+namespace na {
+namespace tc {
+
+constexpr int kV2XStages = 4;
+constexpr int kV2K0Chunks = 8;                 // layer 0: x | ones | h0 x6
+constexpr int kV2K1Chunks = 14;                // layer 1: h0 x6 | h1 x6 | ones | zero
+constexpr int kN1 = 208;                       // layer-1 accumulator columns: 192 gates + 16 (score hi, lo, pad)
+constexpr int kB1Chunk = kN1 * 16;             // bytes of one layer-1 B K-chunk in shared memory
+constexpr int kV2Threads = 14 * 32;
+constexpr int kV2Fc = NA_FC_HIDDEN;
+constexpr uint32_t kIdescL1 = make_idesc(kN1, kFmtVal, kFmtVal);
+constexpr uint32_t kIdescFlush = make_idesc(16, kFmtVal, kFmtVal);
+
+struct HeadSmem2 {
+    float lnw[kH], lnb[kH];
+    float w0[kV2Fc * kH];
+    float b0[kV2Fc];
+    float w3[NA_MAX_CLASSES * kV2Fc];
+    float b3[NA_MAX_CLASSES];
+};
+
+struct Smem2 {
+    alignas(128) unsigned char b0[kV2K0Chunks * kBChunk];          // 24,576
+    alignas(128) unsigned char b1[kV2K1Chunks * kB1Chunk];         // 46,592
+    alignas(128) unsigned char x[kV2XStages][2 * kAChunk];         // [x chunk | ones chunk] per stage
+    alignas(128) unsigned char h0[2][6 * kAChunk];                 // double-buffered H0_t (= 2 h0_t, fp16)
+    alignas(128) unsigned char h1[6 * kAChunk];
+    alignas(128) unsigned char onez[2 * kAChunk];                  // [ones | zeros]
+    HeadSmem2 head;
+    float zx[kRows][kH + 1];                                       // pooled vector exchange, once per tile
+    alignas(8) uint64_t x_full[kV2XStages], x_empty[kV2XStages];
+    uint64_t d0_full, d1_full, h0_ready[2], h0_free[2], h1_ready;
+    uint32_t tmem_base;
+};
+
+// ---- weight packing (v2 section of `packed`) ---------------------------------------------------------
+// B0 [8 chunks][192][8] and B1 [14 chunks][192][8] fp16, row n = (j/8)*32 + gate*8 + j%8, pre-scaled:
+// rows of the i, f, o gates by 0.5 (sigmoid via tanh), columns that multiply a hidden state by 0.5 (H = 2h).
+__global__ void pack_decoder_v2_kernel(const float* __restrict__ w_ih0, const float* __restrict__ w_hh0,
+                                       const float* __restrict__ b_ih0, const float* __restrict__ b_hh0,
+                                       const float* __restrict__ w_ih1, const float* __restrict__ w_hh1,
+                                       const float* __restrict__ b_ih1, const float* __restrict__ b_hh1,
+                                       uint16_t* __restrict__ out) {
+    const int total0 = kV2K0Chunks * 8 * kN, total1 = kV2K1Chunks * 8 * kN;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total0 + total1; idx += gridDim.x * blockDim.x) {
+        const bool l1 = idx >= total0;
+        const int e = l1 ? idx - total0 : idx;
+        const int k = (e / (kN * 8)) * 8 + (e % 8);       // K index
+        const int n = (e / 8) % kN;                       // permuted gate column
+        const int j = (n / 32) * 8 + (n % 8), q = (n % 32) / 8;
+        const int col = q * kH + j;                       // row of the torch weight tensors
+        const float gs = (q == 2) ? 1.0f : 0.5f;          // gate pre-scale
+        const float hs = 0.5f * gs;                       // ... times the H = 2h column scale
+        float v = 0.f;
+        if (!l1) {
+            const float b = gs * (b_ih0[col] + b_hh0[col]);
+            const float bh = val16_to_float(val16(b));
+            if (k < 8) v = gs * w_ih0[col * 8 + k];
+            else if (k == 8) v = bh;
+            else if (k == 9) v = b - bh;
+            else if (k >= 16) v = hs * w_hh0[col * kH + (k - 16)];
+        } else {
+            const float b = gs * (b_ih1[col] + b_hh1[col]);
+            const float bh = val16_to_float(val16(b));
+            if (k < 48) v = hs * w_ih1[col * kH + k];
+            else if (k < 96) v = hs * w_hh1[col * kH + (k - 48)];
+            else if (k == 96) v = bh;
+            else if (k == 97) v = b - bh;
+        }
+        out[idx] = val16(v);
+    }
+}
+
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&v)[2]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// One cell update for the 8 units of a block; v = [i x8 | f x8 | g x8 | o x8] pre-activations (i, f, o already
+// halved by the packed weights).  Returns H = 2h packed as 4 x fp16x2.
+__device__ __forceinline__ void cell_block_v2(const uint32_t (&v)[32], float* c, uint32_t (&hp)[4]) {
+    float h[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const float ti = tanh_apx(__uint_as_float(v[u]));
+        const float tf = tanh_apx(__uint_as_float(v[8 + u]));
+        const float tg = tanh_apx(__uint_as_float(v[16 + u]));
+        const float to = tanh_apx(__uint_as_float(v[24 + u]));
+        const float w = fmaf(tf, c[u], c[u]);
+        const float uu = fmaf(ti, tg, tg);
+        c[u] = 0.5f * (w + uu);
+        const float tcell = tanh_apx(c[u]);
+        h[u] = fmaf(to, tcell, tcell);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) hp[u] = pack_val(h[2 * u], h[2 * u + 1]);
+}
+
+__global__ void __launch_bounds__(kV2Threads, 1)
+decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][Bp][8] fp16 bits
+                        const unsigned char* __restrict__ packed,   // v2 section: B0 | B1 (pack_decoder_v2_kernel)
+                        const float* __restrict__ attn_w, const float* __restrict__ attn_b,
+                        const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                        const float* __restrict__ fc0_w, const float* __restrict__ fc0_b,
+                        const float* __restrict__ fc3_w, const float* __restrict__ fc3_b,
+                        float* __restrict__ logits, float* __restrict__ probs,
+                        int T, int64_t B, int64_t Bp, int NC, int nquarters) {
+    constexpr int kMmaWarp = 12, kTmaWarp = 13;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem2& S = *reinterpret_cast<Smem2*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- one-time setup --------------------------------------------------------------------------
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(packed);
+        uint4* d0 = reinterpret_cast<uint4*>(S.b0);
+        constexpr int n0_16 = kV2K0Chunks * kBChunk / 16;
+        for (int i = tid; i < n0_16; i += kV2Threads) d0[i] = src[i];
+        // layer 1: 192 packed rows per chunk -> 208-row chunks; rows 192..207 = attention score columns
+        for (int i = tid; i < kV2K1Chunks * kN; i += kV2Threads) {
+            const int ch = i / kN, r = i % kN;
+            reinterpret_cast<uint4*>(S.b1 + ch * kB1Chunk)[r] = src[n0_16 + i];
+        }
+        for (int i = tid; i < kV2K1Chunks * 16; i += kV2Threads) {
+            const int ch = i / 16, r = i % 16;
+            uint16_t w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = ch * 8 + e;
+                float v = 0.f;
+                if (r < 2) {
+                    float full = 0.f;
+                    if (k >= 48 && k < 96) full = 0.5f * attn_w[k - 48];      // multiplies H1 = 2 h1
+                    else if (k == 96) full = attn_b[0];
+                    const float hi = val16_to_float(val16(full));
+                    v = (r == 0) ? hi : full - hi;
+                }
+                w[e] = val16(v);
+            }
+            uint4 pk;
+            pk.x = w[0] | ((uint32_t)w[1] << 16); pk.y = w[2] | ((uint32_t)w[3] << 16);
+            pk.z = w[4] | ((uint32_t)w[5] << 16); pk.w = w[6] | ((uint32_t)w[7] << 16);
+            reinterpret_cast<uint4*>(S.b1 + ch * kB1Chunk)[kN + r] = pk;
+        }
+        const uint4 ones = make_uint4(kValOnes2, 0u, 0u, 0u);     // fp16 {1,1,0,0,0,0,0,0}
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < kRows; i += kV2Threads) {
+#pragma unroll
+            for (int s = 0; s < kV2XStages; ++s) reinterpret_cast<uint4*>(S.x[s] + kAChunk)[i] = ones;
+            reinterpret_cast<uint4*>(S.onez)[i] = ones;
+            reinterpret_cast<uint4*>(S.onez + kAChunk)[i] = zero;
+        }
+        for (int i = tid; i < kH; i += kV2Threads) { S.head.lnw[i] = ln_w[i]; S.head.lnb[i] = ln_b[i]; }
+        for (int i = tid; i < kV2Fc * kH; i += kV2Threads) S.head.w0[i] = fc0_w[i];
+        for (int i = tid; i < kV2Fc; i += kV2Threads) S.head.b0[i] = fc0_b[i];
+        for (int i = tid; i < NC * kV2Fc; i += kV2Threads) S.head.w3[i] = fc3_w[i];
+        for (int i = tid; i < NC; i += kV2Threads) S.head.b3[i] = fc3_b[i];
+        if (tid == 0) {
+            for (int s = 0; s < kV2XStages; ++s) { mbar_init(&S.x_full[s], 1); mbar_init(&S.x_empty[s], 1); }
+            mbar_init(&S.d0_full, 1); mbar_init(&S.d1_full, 1);
+            mbar_init(&S.h0_ready[0], 384); mbar_init(&S.h0_ready[1], 384);
+            mbar_init(&S.h0_free[0], 1); mbar_init(&S.h0_free[1], 1);
+            mbar_init(&S.h1_ready, 384);
+            fence_mbar_init();
+        }
+        if (warp == kTmaWarp) tmem_alloc_all(&S.tmem_base);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncthreads();
+        tc_fence_after();
+    }
+    const uint32_t tmem = S.tmem_base;
+    const uint32_t tmem_d0 = tmem, tmem_d1 = tmem + kN;
+
+    // Work split as in v1: 32-window quarters, CTA i owns a contiguous range, tiles of up to 4 quarters.
+    const int q_begin = (int)(((int64_t)blockIdx.x * nquarters) / gridDim.x);
+    const int q_end = (int)(((int64_t)(blockIdx.x + 1) * nquarters) / gridDim.x);
+    int n0 = 0;                                            // running layer-0 step index across tiles
+    uint32_t k1 = 0;                                       // running d1_full phase index (T + 1 per tile)
+    for (int q0 = q_begin; q0 < q_end; q0 += 4, n0 += T) {
+        const int nq = min(4, q_end - q0);                 // active quarters of this tile
+        const uint32_t x_bytes = (uint32_t)nq * 32u * 16u;
+        const int64_t b0 = (int64_t)q0 * 32;
+
+        if (warp == kTmaWarp) {
+            // ================= TMA producer ==========================================================
+            if (lane == 0) {
+                for (int t = 0; t < T; ++t) {
+                    const int n = n0 + t, s = n % kV2XStages, u = n / kV2XStages;
+                    mbar_wait(&S.x_empty[s], (u & 1) ^ 1);
+                    mbar_arrive_expect_tx(&S.x_full[s], x_bytes);
+                    bulk_load(S.x[s], x + ((int64_t)t * Bp + b0) * 8, x_bytes, &S.x_full[s]);
+                }
+            }
+        } else if (warp == kMmaWarp) {
+            // ================= MMA issuer ============================================================
+            if (lane == 0) {
+                const uint64_t d_b0 = umma_desc(smem_u32(S.b0), kBChunk, 128), d_b1 = umma_desc(smem_u32(S.b1), kB1Chunk, 128);
+                const uint64_t d_x0 = umma_desc(smem_u32(S.x[0]), kAChunk, 128);
+                const uint64_t d_h0[2] = {umma_desc(smem_u32(S.h0[0]), kAChunk, 128), umma_desc(smem_u32(S.h0[1]), kAChunk, 128)};
+                const uint64_t d_h1 = umma_desc(smem_u32(S.h1), kAChunk, 128), d_onez = umma_desc(smem_u32(S.onez), kAChunk, 128);
+                for (int t = 0; t <= T; ++t) {
+                    const int n = n0 + t;
+                    if (t >= 1) {                                  // H0_{t-1} written, D0 drained
+                        mbar_wait(&S.h0_ready[(n - 1) & 1], ((n - 1) >> 1) & 1);
+                        tc_fence_after();
+                    }
+                    if (t < T) {                                   // layer 0, step t
+                        const int s = n % kV2XStages, u = n / kV2XStages;
+                        mbar_wait(&S.x_full[s], u & 1);
+                        tc_fence_after();
+                        umma_bf16(tmem_d0, desc_adv(d_x0, s * 2 * kAChunk), d_b0, 0u);
+                        if (t >= 1) {
+                            const uint64_t hprev = d_h0[(n - 1) & 1];
+#pragma unroll
+                            for (int i = 0; i < 3; ++i)
+                                umma_bf16(tmem_d0, desc_adv(hprev, 2 * i * kAChunk), desc_adv(d_b0, (2 + 2 * i) * kBChunk), 1u);
+                        }
+                        umma_commit(&S.x_empty[s]);
+                        umma_commit(&S.d0_full);
+                    }
+                    if (t >= 1) {                                  // layer 1, step m = t - 1
+                        const int m = n - 1;
+                        if (t >= 2) {                              // H1_{m-1} written, D1 drained
+                            mbar_wait(&S.h1_ready, (m - 1) & 1);
+                            tc_fence_after();
+                        }
+                        const uint64_t hin = d_h0[m & 1];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+                            umma_bf16_i(tmem_d1, desc_adv(hin, 2 * i * kAChunk), desc_adv(d_b1, 2 * i * kB1Chunk), kIdescL1, i == 0 ? 0u : 1u);
+                        if (t >= 2) {
+#pragma unroll
+                            for (int i = 0; i < 3; ++i)
+                                umma_bf16_i(tmem_d1, desc_adv(d_h1, 2 * i * kAChunk), desc_adv(d_b1, (6 + 2 * i) * kB1Chunk), kIdescL1, 1u);
+                        }
+                        umma_bf16_i(tmem_d1, d_onez, desc_adv(d_b1, 12 * kB1Chunk), kIdescL1, 1u);
+                        umma_commit(&S.d1_full);
+                        umma_commit(&S.h0_free[m & 1]);
+                    }
+                }
+                // flush: s_{T-1} = w_a . h1_{T-1} + b_a into the 16 score columns only
+                {
+                    const int m = n0 + T - 1;
+                    mbar_wait(&S.h1_ready, m & 1);
+                    tc_fence_after();
+                    const uint64_t d_b1s = desc_adv(d_b1, kN * 16);          // rows 192..207 of every chunk
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        umma_bf16_i(tmem_d1 + kN, desc_adv(d_h1, 2 * i * kAChunk), desc_adv(d_b1s, (6 + 2 * i) * kB1Chunk), kIdescFlush, i == 0 ? 0u : 1u);
+                    umma_bf16_i(tmem_d1 + kN, d_onez, desc_adv(d_b1s, 12 * kB1Chunk), kIdescFlush, 1u);
+                    umma_commit(&S.d1_full);
+                }
+            }
+        } else {
+            // ================= epilogue: both layers of (quarter q, unit group g) ========================
+            const int q = warp & 3, g = warp >> 2;
+            const int row = q * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+            if (q >= nq) {                                 // idle quarter: keep the barrier protocol only
+                for (int t = 0; t <= T; ++t) {
+                    const int n = n0 + t;
+                    if (t < T) { mbar_wait(&S.d0_full, n & 1); mbar_arrive(&S.h0_ready[n & 1]); }
+                    if (t >= 1) { mbar_wait(&S.d1_full, k1 & 1); ++k1; mbar_arrive(&S.h1_ready); }
+                }
+                mbar_wait(&S.d1_full, k1 & 1); ++k1;
+            } else {
+                float c0[16], c1[16], z[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { c0[j] = 0.f; c1[j] = 0.f; z[j] = 0.f; }
+                uint32_t hprev[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hprev[j] = 0u;
+                float mx = -INFINITY, l = 0.f;
+                auto pool = [&](float score) {             // online softmax over time (lstm_eeg_model.py:35-37), lazy rescale
+                    if (score > mx) {
+                        const float sc = __expf(mx - score);
+                        l *= sc;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) z[j] *= sc;
+                        mx = score;
+                    }
+                    const float e = __expf(score - mx);
+                    l += e;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        z[2 * u] = fmaf(e, val_lo(hprev[u]), z[2 * u]);
+                        z[2 * u + 1] = fmaf(e, val_hi(hprev[u]), z[2 * u + 1]);
+                    }
+                };
+                for (int t = 0; t <= T; ++t) {
+                    const int n = n0 + t;
+                    if (t < T) {                           // ---- layer 0, step t
+                        mbar_wait(&S.d0_full, n & 1);
+                        mbar_wait(&S.h0_free[n & 1], ((n >> 1) & 1) ^ 1);   // layer-1 MMA of step n-2 has read this buffer
+                        tc_fence_after();
+                        unsigned char* dst = S.h0[n & 1] + row * 16;
+#pragma unroll
+                        for (int bb = 0; bb < 2; ++bb) {
+                            const int blk = 2 * g + bb;
+                            uint32_t v[32], hp[4];
+                            tmem_ld32(tmem_d0 + lane_base + blk * 32, v);
+                            cell_block_v2(v, c0 + bb * 8, hp);
+                            st_shared_v4(dst + blk * kAChunk, hp[0], hp[1], hp[2], hp[3]);
+                        }
+                        tc_fence_before();
+                        fence_proxy_async_smem();
+                        mbar_arrive(&S.h0_ready[n & 1]);
+                    }
+                    if (t >= 1) {                          // ---- layer 1, step t-1 (+ pooling of step t-2)
+                        mbar_wait(&S.d1_full, k1 & 1); ++k1;
+                        tc_fence_after();
+                        uint32_t sc2[2];
+                        tmem_ld2(tmem_d1 + lane_base + kN, sc2);
+                        unsigned char* dst = S.h1 + row * 16;
+                        uint32_t hb[8];
+#pragma unroll
+                        for (int bb = 0; bb < 2; ++bb) {
+                            const int blk = 2 * g + bb;
+                            uint32_t v[32], hp[4];
+                            tmem_ld32(tmem_d1 + lane_base + blk * 32, v);
+                            cell_block_v2(v, c1 + bb * 8, hp);
+                            st_shared_v4(dst + blk * kAChunk, hp[0], hp[1], hp[2], hp[3]);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) hb[bb * 4 + u] = hp[u];
+                        }
+                        tc_fence_before();
+                        fence_proxy_async_smem();
+                        mbar_arrive(&S.h1_ready);
+                        if (t >= 2) pool(__uint_as_float(sc2[0]) + __uint_as_float(sc2[1]));
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) hprev[u] = hb[u];
+                    }
+                }
+                {                                          // flush: score of the last step
+                    mbar_wait(&S.d1_full, k1 & 1); ++k1;
+                    tc_fence_after();
+                    uint32_t sc2[2];
+                    tmem_ld2(tmem_d1 + lane_base + kN, sc2);
+                    tc_fence_before();
+                    pool(__uint_as_float(sc2[0]) + __uint_as_float(sc2[1]));
+                }
+                // ---- head for this window: LN -> fc0 -> RReLU(eval) -> fc3 -> softmax ----------------------
+#pragma unroll
+                for (int j = 0; j < 16; ++j) S.zx[row][g * 16 + j] = z[j];
+                named_bar_sync(1 + q, 96);
+                if (g == 0) {
+                    const int64_t b = b0 + row;
+                    float zf[kH];
+                    const float inv_l = 0.5f / l;          // z accumulated H = 2h
+                    float mean = 0.f;
+#pragma unroll
+                    for (int j = 0; j < kH; ++j) { zf[j] = S.zx[row][j] * inv_l; mean += zf[j]; }
+                    mean *= (1.0f / kH);
+                    float var = 0.f;
+#pragma unroll
+                    for (int j = 0; j < kH; ++j) { const float d = zf[j] - mean; var = fmaf(d, d, var); }
+                    const float rstd = rsqrtf(var * (1.0f / kH) + kLnEps);
+#pragma unroll
+                    for (int j = 0; j < kH; ++j) zf[j] = fmaf((zf[j] - mean) * rstd, S.head.lnw[j], S.head.lnb[j]);
+                    float lg[NA_MAX_CLASSES];
+#pragma unroll
+                    for (int k = 0; k < NA_MAX_CLASSES; ++k) lg[k] = (k < NC) ? S.head.b3[k] : -INFINITY;
+                    for (int o = 0; o < kV2Fc; ++o) {
+                        float a = S.head.b0[o];
+#pragma unroll
+                        for (int j = 0; j < kH; ++j) a = fmaf(S.head.w0[o * kH + j], zf[j], a);
+                        a = a >= 0.f ? a : a * kRReluEvalSlope;
+#pragma unroll
+                        for (int k = 0; k < NA_MAX_CLASSES; ++k)
+                            if (k < NC) lg[k] = fmaf(S.head.w3[k * kV2Fc + o], a, lg[k]);
+                    }
+                    if (b < B) {
+                        float mxl = -INFINITY;
+#pragma unroll
+                        for (int k = 0; k < NA_MAX_CLASSES; ++k) mxl = fmaxf(mxl, lg[k]);
+                        float den = 0.f, pe[NA_MAX_CLASSES];
+#pragma unroll
+                        for (int k = 0; k < NA_MAX_CLASSES; ++k) { pe[k] = (k < NC) ? __expf(lg[k] - mxl) : 0.f; den += pe[k]; }
+#pragma unroll
+                        for (int k = 0; k < NA_MAX_CLASSES; ++k)
+                            if (k < NC) {
+                                logits[b * NC + k] = lg[k];
+                                if (probs) probs[b * NC + k] = pe[k] / den;
+                            }
+                    }
+                }
+            }
+        }
+        __syncthreads();       // tile done: every MMA has completed (the epilogue saw the flush d1_full)
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kTmaWarp) {
+        tc_fence_after();
+        tmem_free_all(tmem);
+    }
+}
+
+size_t infer_v2_smem_bytes() { return sizeof(Smem2) + 1024; }
+
+int launch_pack_v2(const float* w_ih0, const float* w_hh0, const float* b_ih0, const float* b_hh0, const float* w_ih1,
+                   const float* w_hh1, const float* b_ih1, const float* b_hh1, void* out, cudaStream_t stream) {
+    pack_decoder_v2_kernel<<<64, 256, 0, stream>>>(w_ih0, w_hh0, b_ih0, b_hh0, w_ih1, w_hh1, b_ih1, b_hh1,
+                                                   reinterpret_cast<uint16_t*>(out));
+    count_launch();
+    return check_launch("na_decoder_pack_bf16 (v2 section)");
+}
+
+int launch_infer_v2(const void* x, const unsigned char* packed_v2, const float* attn_w, const float* attn_b, const float* ln_w,
+                    const float* ln_b, const float* fc0_w, const float* fc0_b, const float* fc3_w, const float* fc3_b,
+                    float* logits, float* probs, int T, int64_t B, int64_t Bp, int NC, int sms, cudaStream_t stream) {
+    const size_t smem = infer_v2_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(decoder_infer_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
+    const int nquarters = (int)((B + 31) / 32);            // padding quarters beyond B are never scheduled
+    const int ntiles = (nquarters + 3) / 4;
+    const int grid = ntiles < sms ? ntiles : sms;
+    decoder_infer_v2_kernel<<<grid, kV2Threads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), packed_v2, attn_w, attn_b,
+                                                                ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, T, B, Bp, NC,
+                                                                nquarters);
+    count_launch();
+    return check_launch("na_decoder_infer_bf16 (v2)");
+}
+
+}  // namespace tc
+}  // namespace na
