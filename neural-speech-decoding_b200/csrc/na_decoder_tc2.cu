@@ -25,6 +25,13 @@
 //         w = fma(Tf, c, c);  u = fma(Ti, Tg, Tg);  c = 0.5 (w + u);  H = fma(To, tanh c, tanh c)
 //     5 MUFU + 5 FMA-pipe ops per cell.
 //   * h_{-1} = 0 is handled by NOT issuing the recurrent MMAs of the first step (no buffer zeroing).
+//   * Row replication for short tiles (template R): a tile step costs the same MUFU time whether a lane
+//     quarter holds 32 windows or 1, so a remainder of <= 64 (<= 32) windows is laid out as R = 2 (4) copies
+//     of the same rows (TMA loads x R times, epilogue threads store H to every copy) and every copy's warps
+//     take a different 1/R of the hidden units: the tile then costs ~1/R of the MUFU work, i.e. the chain
+//     latency (~0.35 of a full step) instead of a full step.  Small batches are spread over all SMs this way.
+//     Gate columns are permuted in granules of 4 units, n = (j/4)*16 + gate*4 + j%4, so that 16 / 32
+//     accumulator columns hold i,f,g,o of 4 / 8 units.
 #include "na_tc_common.cuh"
 
 namespace na {
@@ -63,7 +70,7 @@ struct Smem2 {
 };
 
 // ---- weight packing (v2 section of `packed`) ---------------------------------------------------------
-// B0 [8 chunks][192][8] and B1 [14 chunks][192][8] fp16, row n = (j/8)*32 + gate*8 + j%8, pre-scaled:
+// B0 [8 chunks][192][8] and B1 [14 chunks][192][8] fp16, row n = (j/4)*16 + gate*4 + j%4, pre-scaled:
 // rows of the i, f, o gates by 0.5 (sigmoid via tanh), columns that multiply a hidden state by 0.5 (H = 2h).
 __global__ void pack_decoder_v2_kernel(const float* __restrict__ w_ih0, const float* __restrict__ w_hh0,
                                        const float* __restrict__ b_ih0, const float* __restrict__ b_hh0,
@@ -76,7 +83,7 @@ __global__ void pack_decoder_v2_kernel(const float* __restrict__ w_ih0, const fl
         const int e = l1 ? idx - total0 : idx;
         const int k = (e / (kN * 8)) * 8 + (e % 8);       // K index
         const int n = (e / 8) % kN;                       // permuted gate column
-        const int j = (n / 32) * 8 + (n % 8), q = (n % 32) / 8;
+        const int j = (n / 16) * 4 + (n % 4), q = (n % 16) / 4;
         const int col = q * kH + j;                       // row of the torch weight tensors
         const float gs = (q == 2) ? 1.0f : 0.5f;          // gate pre-scale
         const float hs = 0.5f * gs;                       // ... times the H = 2h column scale
@@ -104,25 +111,188 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&v)[2]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_v2(void* p, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(smem_u32(p)), "r"(a), "r"(b) : "memory");
+}
 
-// One cell update for the 8 units of a block; v = [i x8 | f x8 | g x8 | o x8] pre-activations (i, f, o already
-// halved by the packed weights).  Returns H = 2h packed as 4 x fp16x2.
-__device__ __forceinline__ void cell_block_v2(const uint32_t (&v)[32], float* c, uint32_t (&hp)[4]) {
-    float h[8];
+// One cell update for the 4 units of a granule; v = [i x4 | f x4 | g x4 | o x4] pre-activations (i, f, o already
+// halved by the packed weights).  Returns H = 2h packed as 2 x fp16x2.
+__device__ __forceinline__ void cell_granule(const uint32_t* v, float* c, uint32_t* hp) {
+    float h[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 4; ++u) {
         const float ti = tanh_apx(__uint_as_float(v[u]));
-        const float tf = tanh_apx(__uint_as_float(v[8 + u]));
-        const float tg = tanh_apx(__uint_as_float(v[16 + u]));
-        const float to = tanh_apx(__uint_as_float(v[24 + u]));
+        const float tf = tanh_apx(__uint_as_float(v[4 + u]));
+        const float tg = tanh_apx(__uint_as_float(v[8 + u]));
+        const float to = tanh_apx(__uint_as_float(v[12 + u]));
         const float w = fmaf(tf, c[u], c[u]);
         const float uu = fmaf(ti, tg, tg);
         c[u] = 0.5f * (w + uu);
         const float tcell = tanh_apx(c[u]);
         h[u] = fmaf(to, tcell, tcell);
     }
+    hp[0] = pack_val(h[0], h[1]);
+    hp[1] = pack_val(h[2], h[3]);
+}
+
+// Epilogue of one tile for one warp: both layers of (lane quarter q, unit group g).  R = row replication:
+// the tile holds 128 / R distinct windows; copy rp = q / (4 / R) of source quarter qs = q % (4 / R) takes
+// granules [4 g + rp * (4 / R), + 4 / R) of the 12 four-unit granules.
+template <int R>
+__device__ __forceinline__ void epilogue_tile(Smem2& S, const int q, const int g, const int lane, const int nq, const int T,
+                                              const int n0, uint32_t& k1, const uint32_t tmem_d0, const uint32_t tmem_d1,
+                                              const int64_t b0, const int64_t B, const int NC, float* __restrict__ logits,
+                                              float* __restrict__ probs) {
+    constexpr int kQ = 4 / R;                      // distinct source quarters = granules per warp
+    constexpr int kSlots = 4 / R, kU = 4 * kSlots; // granules / units owned by this thread
+    const int qs = q % kQ, rp = q / kQ;
+    const int wrow = qs * 32 + lane;               // window row of the tile (first copy)
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int gr0 = 4 * g + rp * kSlots;           // first granule
+    if (qs >= nq) {                                // idle quarter: keep the barrier protocol only
+        for (int t = 0; t <= T; ++t) {
+            const int n = n0 + t;
+            if (t < T) { mbar_wait(&S.d0_full, n & 1); mbar_arrive(&S.h0_ready[n & 1]); }
+            if (t >= 1) { mbar_wait(&S.d1_full, k1 & 1); ++k1; mbar_arrive(&S.h1_ready); }
+        }
+        mbar_wait(&S.d1_full, k1 & 1); ++k1;
+        return;
+    }
+    float c0[kU], c1[kU], z[kU];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) hp[u] = pack_val(h[2 * u], h[2 * u + 1]);
+    for (int j = 0; j < kU; ++j) { c0[j] = 0.f; c1[j] = 0.f; z[j] = 0.f; }
+    uint32_t hprev[2 * kSlots];
+#pragma unroll
+    for (int j = 0; j < 2 * kSlots; ++j) hprev[j] = 0u;
+    float mx = -INFINITY, l = 0.f;
+    auto pool = [&](float score) {                 // online softmax over time (lstm_eeg_model.py:35-37), lazy rescale
+        if (score > mx) {
+            const float sc = __expf(mx - score);
+            l *= sc;
+#pragma unroll
+            for (int j = 0; j < kU; ++j) z[j] *= sc;
+            mx = score;
+        }
+        const float e = __expf(score - mx);
+        l += e;
+#pragma unroll
+        for (int u = 0; u < 2 * kSlots; ++u) {
+            z[2 * u] = fmaf(e, val_lo(hprev[u]), z[2 * u]);
+            z[2 * u + 1] = fmaf(e, val_hi(hprev[u]), z[2 * u + 1]);
+        }
+    };
+    // gates of this thread's granules -> cell update -> H (fp16) stored to every row copy of the A operand `buf`
+    auto layer_phase = [&](const uint32_t tmem_d, float* c, unsigned char* buf, uint32_t* hb) {
+        if constexpr (R == 4) {
+            uint32_t v[16];
+            tmem_ld16(tmem_d + lane_base + gr0 * 16, v);
+            cell_granule(v, c, hb);
+            unsigned char* dst = buf + (gr0 >> 1) * kAChunk + wrow * 16 + (gr0 & 1) * 8;
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep) st_shared_v2(dst + rep * 32 * 16, hb[0], hb[1]);
+        } else {
+#pragma unroll
+            for (int pr = 0; pr < kSlots / 2; ++pr) {       // pairs of granules = one 8-unit K chunk
+                uint32_t v[32];
+                tmem_ld32(tmem_d + lane_base + (gr0 + 2 * pr) * 16, v);
+                cell_granule(v, c + pr * 8, hb + pr * 4);
+                cell_granule(v + 16, c + pr * 8 + 4, hb + pr * 4 + 2);
+                unsigned char* dst = buf + ((gr0 >> 1) + pr) * kAChunk + wrow * 16;
+#pragma unroll
+                for (int rep = 0; rep < R; ++rep)
+                    st_shared_v4(dst + rep * (kRows / R) * 16, hb[pr * 4], hb[pr * 4 + 1], hb[pr * 4 + 2], hb[pr * 4 + 3]);
+            }
+        }
+    };
+    for (int t = 0; t <= T; ++t) {
+        const int n = n0 + t;
+        if (t < T) {                               // ---- layer 0, step t
+            mbar_wait(&S.d0_full, n & 1);
+            mbar_wait(&S.h0_free[n & 1], ((n >> 1) & 1) ^ 1);   // layer-1 MMA of step n-2 has read this buffer
+            tc_fence_after();
+            uint32_t hb[2 * kSlots];
+            layer_phase(tmem_d0, c0, S.h0[n & 1], hb);
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive(&S.h0_ready[n & 1]);
+        }
+        if (t >= 1) {                              // ---- layer 1, step t-1 (+ pooling of step t-2)
+            mbar_wait(&S.d1_full, k1 & 1); ++k1;
+            tc_fence_after();
+            uint32_t sc2[2];
+            tmem_ld2(tmem_d1 + lane_base + kN, sc2);
+            uint32_t hb[2 * kSlots];
+            layer_phase(tmem_d1, c1, S.h1, hb);
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive(&S.h1_ready);
+            if (t >= 2) pool(__uint_as_float(sc2[0]) + __uint_as_float(sc2[1]));
+#pragma unroll
+            for (int u = 0; u < 2 * kSlots; ++u) hprev[u] = hb[u];
+        }
+    }
+    {                                              // flush: score of the last step
+        mbar_wait(&S.d1_full, k1 & 1); ++k1;
+        tc_fence_after();
+        uint32_t sc2[2];
+        tmem_ld2(tmem_d1 + lane_base + kN, sc2);
+        tc_fence_before();
+        pool(__uint_as_float(sc2[0]) + __uint_as_float(sc2[1]));
+    }
+    // ---- head for this window: LN -> fc0 -> RReLU(eval) -> fc3 -> softmax ----------------------
+#pragma unroll
+    for (int j = 0; j < kU; ++j) S.zx[wrow][gr0 * 4 + j] = z[j];
+    named_bar_sync(1 + qs, 96 * R);                // the 3 R warps that share source quarter qs
+    if (g == 0 && rp == 0) {
+        const int64_t b = b0 + wrow;
+        float zf[kH];
+        const float inv_l = 0.5f / l;              // z accumulated H = 2h
+        float mean = 0.f;
+#pragma unroll
+        for (int j = 0; j < kH; ++j) { zf[j] = S.zx[wrow][j] * inv_l; mean += zf[j]; }
+        mean *= (1.0f / kH);
+        float var = 0.f;
+#pragma unroll
+        for (int j = 0; j < kH; ++j) { const float d = zf[j] - mean; var = fmaf(d, d, var); }
+        const float rstd = rsqrtf(var * (1.0f / kH) + kLnEps);
+#pragma unroll
+        for (int j = 0; j < kH; ++j) zf[j] = fmaf((zf[j] - mean) * rstd, S.head.lnw[j], S.head.lnb[j]);
+        float lg[NA_MAX_CLASSES];
+#pragma unroll
+        for (int k = 0; k < NA_MAX_CLASSES; ++k) lg[k] = (k < NC) ? S.head.b3[k] : -INFINITY;
+        for (int o = 0; o < kV2Fc; ++o) {
+            float a = S.head.b0[o];
+#pragma unroll
+            for (int j = 0; j < kH; ++j) a = fmaf(S.head.w0[o * kH + j], zf[j], a);
+            a = a >= 0.f ? a : a * kRReluEvalSlope;
+#pragma unroll
+            for (int k = 0; k < NA_MAX_CLASSES; ++k)
+                if (k < NC) lg[k] = fmaf(S.head.w3[k * kV2Fc + o], a, lg[k]);
+        }
+        if (b < B) {
+            float mxl = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < NA_MAX_CLASSES; ++k) mxl = fmaxf(mxl, lg[k]);
+            float den = 0.f, pe[NA_MAX_CLASSES];
+#pragma unroll
+            for (int k = 0; k < NA_MAX_CLASSES; ++k) { pe[k] = (k < NC) ? __expf(lg[k] - mxl) : 0.f; den += pe[k]; }
+#pragma unroll
+            for (int k = 0; k < NA_MAX_CLASSES; ++k)
+                if (k < NC) {
+                    logits[b * NC + k] = lg[k];
+                    if (probs) probs[b * NC + k] = pe[k] / den;
+                }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kV2Threads, 1)
@@ -133,7 +303,7 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
                         const float* __restrict__ fc0_w, const float* __restrict__ fc0_b,
                         const float* __restrict__ fc3_w, const float* __restrict__ fc3_b,
                         float* __restrict__ logits, float* __restrict__ probs,
-                        int T, int64_t B, int64_t Bp, int NC, int nquarters) {
+                        int T, int64_t B, int64_t Bp, int NC, int nquarters, int allow_rep) {
     constexpr int kMmaWarp = 12, kTmaWarp = 13;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem2& S = *reinterpret_cast<Smem2*>(smem_raw);
@@ -201,13 +371,15 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
     const uint32_t tmem = S.tmem_base;
     const uint32_t tmem_d0 = tmem, tmem_d1 = tmem + kN;
 
-    // Work split as in v1: 32-window quarters, CTA i owns a contiguous range, tiles of up to 4 quarters.
+    // Work split: 32-window quarters, CTA i owns a contiguous range and walks it in tiles of up to 4 quarters; a
+    // remainder of 2 quarters runs as one R = 2 tile, a remainder of 1 as an R = 4 tile.
     const int q_begin = (int)(((int64_t)blockIdx.x * nquarters) / gridDim.x);
     const int q_end = (int)(((int64_t)(blockIdx.x + 1) * nquarters) / gridDim.x);
     int n0 = 0;                                            // running layer-0 step index across tiles
     uint32_t k1 = 0;                                       // running d1_full phase index (T + 1 per tile)
-    for (int q0 = q_begin; q0 < q_end; q0 += 4, n0 += T) {
-        const int nq = min(4, q_end - q0);                 // active quarters of this tile
+    for (int q0 = q_begin; q0 < q_end; n0 += T) {
+        const int nq = min(4, q_end - q0);                 // active source quarters of this tile
+        const int R = !allow_rep ? 1 : (nq == 1 ? 4 : (nq == 2 ? 2 : 1));
         const uint32_t x_bytes = (uint32_t)nq * 32u * 16u;
         const int64_t b0 = (int64_t)q0 * 32;
 
@@ -217,8 +389,9 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
                 for (int t = 0; t < T; ++t) {
                     const int n = n0 + t, s = n % kV2XStages, u = n / kV2XStages;
                     mbar_wait(&S.x_empty[s], (u & 1) ^ 1);
-                    mbar_arrive_expect_tx(&S.x_full[s], x_bytes);
-                    bulk_load(S.x[s], x + ((int64_t)t * Bp + b0) * 8, x_bytes, &S.x_full[s]);
+                    mbar_arrive_expect_tx(&S.x_full[s], x_bytes * (uint32_t)R);
+                    const __nv_bfloat16* src = x + ((int64_t)t * Bp + b0) * 8;
+                    for (int rep = 0; rep < R; ++rep) bulk_load(S.x[s] + rep * (kRows / R) * 16, src, x_bytes, &S.x_full[s]);
                 }
             }
         } else if (warp == kMmaWarp) {
@@ -284,139 +457,12 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
         } else {
             // ================= epilogue: both layers of (quarter q, unit group g) ========================
             const int q = warp & 3, g = warp >> 2;
-            const int row = q * 32 + lane;
-            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-            if (q >= nq) {                                 // idle quarter: keep the barrier protocol only
-                for (int t = 0; t <= T; ++t) {
-                    const int n = n0 + t;
-                    if (t < T) { mbar_wait(&S.d0_full, n & 1); mbar_arrive(&S.h0_ready[n & 1]); }
-                    if (t >= 1) { mbar_wait(&S.d1_full, k1 & 1); ++k1; mbar_arrive(&S.h1_ready); }
-                }
-                mbar_wait(&S.d1_full, k1 & 1); ++k1;
-            } else {
-                float c0[16], c1[16], z[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { c0[j] = 0.f; c1[j] = 0.f; z[j] = 0.f; }
-                uint32_t hprev[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) hprev[j] = 0u;
-                float mx = -INFINITY, l = 0.f;
-                auto pool = [&](float score) {             // online softmax over time (lstm_eeg_model.py:35-37), lazy rescale
-                    if (score > mx) {
-                        const float sc = __expf(mx - score);
-                        l *= sc;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) z[j] *= sc;
-                        mx = score;
-                    }
-                    const float e = __expf(score - mx);
-                    l += e;
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        z[2 * u] = fmaf(e, val_lo(hprev[u]), z[2 * u]);
-                        z[2 * u + 1] = fmaf(e, val_hi(hprev[u]), z[2 * u + 1]);
-                    }
-                };
-                for (int t = 0; t <= T; ++t) {
-                    const int n = n0 + t;
-                    if (t < T) {                           // ---- layer 0, step t
-                        mbar_wait(&S.d0_full, n & 1);
-                        mbar_wait(&S.h0_free[n & 1], ((n >> 1) & 1) ^ 1);   // layer-1 MMA of step n-2 has read this buffer
-                        tc_fence_after();
-                        unsigned char* dst = S.h0[n & 1] + row * 16;
-#pragma unroll
-                        for (int bb = 0; bb < 2; ++bb) {
-                            const int blk = 2 * g + bb;
-                            uint32_t v[32], hp[4];
-                            tmem_ld32(tmem_d0 + lane_base + blk * 32, v);
-                            cell_block_v2(v, c0 + bb * 8, hp);
-                            st_shared_v4(dst + blk * kAChunk, hp[0], hp[1], hp[2], hp[3]);
-                        }
-                        tc_fence_before();
-                        fence_proxy_async_smem();
-                        mbar_arrive(&S.h0_ready[n & 1]);
-                    }
-                    if (t >= 1) {                          // ---- layer 1, step t-1 (+ pooling of step t-2)
-                        mbar_wait(&S.d1_full, k1 & 1); ++k1;
-                        tc_fence_after();
-                        uint32_t sc2[2];
-                        tmem_ld2(tmem_d1 + lane_base + kN, sc2);
-                        unsigned char* dst = S.h1 + row * 16;
-                        uint32_t hb[8];
-#pragma unroll
-                        for (int bb = 0; bb < 2; ++bb) {
-                            const int blk = 2 * g + bb;
-                            uint32_t v[32], hp[4];
-                            tmem_ld32(tmem_d1 + lane_base + blk * 32, v);
-                            cell_block_v2(v, c1 + bb * 8, hp);
-                            st_shared_v4(dst + blk * kAChunk, hp[0], hp[1], hp[2], hp[3]);
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) hb[bb * 4 + u] = hp[u];
-                        }
-                        tc_fence_before();
-                        fence_proxy_async_smem();
-                        mbar_arrive(&S.h1_ready);
-                        if (t >= 2) pool(__uint_as_float(sc2[0]) + __uint_as_float(sc2[1]));
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) hprev[u] = hb[u];
-                    }
-                }
-                {                                          // flush: score of the last step
-                    mbar_wait(&S.d1_full, k1 & 1); ++k1;
-                    tc_fence_after();
-                    uint32_t sc2[2];
-                    tmem_ld2(tmem_d1 + lane_base + kN, sc2);
-                    tc_fence_before();
-                    pool(__uint_as_float(sc2[0]) + __uint_as_float(sc2[1]));
-                }
-                // ---- head for this window: LN -> fc0 -> RReLU(eval) -> fc3 -> softmax ----------------------
-#pragma unroll
-                for (int j = 0; j < 16; ++j) S.zx[row][g * 16 + j] = z[j];
-                named_bar_sync(1 + q, 96);
-                if (g == 0) {
-                    const int64_t b = b0 + row;
-                    float zf[kH];
-                    const float inv_l = 0.5f / l;          // z accumulated H = 2h
-                    float mean = 0.f;
-#pragma unroll
-                    for (int j = 0; j < kH; ++j) { zf[j] = S.zx[row][j] * inv_l; mean += zf[j]; }
-                    mean *= (1.0f / kH);
-                    float var = 0.f;
-#pragma unroll
-                    for (int j = 0; j < kH; ++j) { const float d = zf[j] - mean; var = fmaf(d, d, var); }
-                    const float rstd = rsqrtf(var * (1.0f / kH) + kLnEps);
-#pragma unroll
-                    for (int j = 0; j < kH; ++j) zf[j] = fmaf((zf[j] - mean) * rstd, S.head.lnw[j], S.head.lnb[j]);
-                    float lg[NA_MAX_CLASSES];
-#pragma unroll
-                    for (int k = 0; k < NA_MAX_CLASSES; ++k) lg[k] = (k < NC) ? S.head.b3[k] : -INFINITY;
-                    for (int o = 0; o < kV2Fc; ++o) {
-                        float a = S.head.b0[o];
-#pragma unroll
-                        for (int j = 0; j < kH; ++j) a = fmaf(S.head.w0[o * kH + j], zf[j], a);
-                        a = a >= 0.f ? a : a * kRReluEvalSlope;
-#pragma unroll
-                        for (int k = 0; k < NA_MAX_CLASSES; ++k)
-                            if (k < NC) lg[k] = fmaf(S.head.w3[k * kV2Fc + o], a, lg[k]);
-                    }
-                    if (b < B) {
-                        float mxl = -INFINITY;
-#pragma unroll
-                        for (int k = 0; k < NA_MAX_CLASSES; ++k) mxl = fmaxf(mxl, lg[k]);
-                        float den = 0.f, pe[NA_MAX_CLASSES];
-#pragma unroll
-                        for (int k = 0; k < NA_MAX_CLASSES; ++k) { pe[k] = (k < NC) ? __expf(lg[k] - mxl) : 0.f; den += pe[k]; }
-#pragma unroll
-                        for (int k = 0; k < NA_MAX_CLASSES; ++k)
-                            if (k < NC) {
-                                logits[b * NC + k] = lg[k];
-                                if (probs) probs[b * NC + k] = pe[k] / den;
-                            }
-                    }
-                }
-            }
+            if (R == 1) epilogue_tile<1>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, logits, probs);
+            else if (R == 2) epilogue_tile<2>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, logits, probs);
+            else epilogue_tile<4>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, logits, probs);
         }
         __syncthreads();       // tile done: every MMA has completed (the epilogue saw the flush d1_full)
+        q0 += nq;
     }
 
     tc_fence_before();
@@ -426,6 +472,9 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
         tmem_free_all(tmem);
     }
 }
+
+int g_infer_rep = 1;       // na_set_tuning("tc_infer_rep", 0) disables row replication (A/B timing)
+void set_infer_rep(int v) { g_infer_rep = v ? 1 : 0; }
 
 size_t infer_v2_smem_bytes() { return sizeof(Smem2) + 1024; }
 
@@ -444,11 +493,11 @@ int launch_infer_v2(const void* x, const unsigned char* packed_v2, const float* 
     cudaError_t e = cudaFuncSetAttribute(decoder_infer_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
     const int nquarters = (int)((B + 31) / 32);            // padding quarters beyond B are never scheduled
-    const int ntiles = (nquarters + 3) / 4;
-    const int grid = ntiles < sms ? ntiles : sms;
+    // one CTA per SM; fewer than 4 quarters per CTA run as row-replicated tiles (see epilogue_tile<R>)
+    const int grid = nquarters < sms ? nquarters : sms;
     decoder_infer_v2_kernel<<<grid, kV2Threads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), packed_v2, attn_w, attn_b,
                                                                 ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, T, B, Bp, NC,
-                                                                nquarters);
+                                                                nquarters, g_infer_rep);
     count_launch();
     return check_launch("na_decoder_infer_bf16 (v2)");
 }
