@@ -161,7 +161,9 @@ int na_head_bwd_f32(const float* dlogits, const float* h, const float* stats, co
  * argmax identical on the repo's windows.
  *   na_decoder_pack_bf16: the 8 nn.LSTM tensors of both layers -> `packed`
  *       (na_decoder_packed_bf16_bytes() bytes): B operands [W_ih | bias hi,lo | W_hh] in the UMMA
- *       K-major core-matrix layout, gate columns permuted to (unit/8, gate, unit%8).
+ *       K-major core-matrix layout, two sections: gate columns permuted to (unit/8, gate, unit%8) for the
+ *       training kernels, and to (unit/4, gate, unit%4) with the sigmoid / H = 2h scalings folded in for
+ *       the inference kernel (na_decoder_tc2.cu).
  *   na_decoder_infer_bf16: x TMP bf16 [T][Bp][8] (na_window_zscore with out_dtype = NA_BF16,
  *       Bp a multiple of 128) -> logits [B,NC] fp32 (+ probs [B,NC] if not NULL).
  */
@@ -174,6 +176,27 @@ int na_decoder_infer_bf16(const void* x_bf16_tmp, const void* packed,
                           const float* fc0_w, const float* fc0_b, const float* fc3_w, const float* fc3_b,
                           float* logits, float* probs,
                           int64_t T, int64_t B, int64_t Bp, int64_t NC, na_stream_t stream);
+
+/* ---- tensor-core tier, wide hidden sizes (H = 96, 144, 192; BASELINE configs[4]: H = 192, T = 2500) --------
+ * Same contract as na_decoder_infer_bf16 (lstm_eeg_model.py:32-39 + :97, eval mode; input_size 8, 2 layers),
+ * for EEG_LSTM(hidden_size = H).  [W_ih | b | W_hh] no longer fits in shared memory, so the kernel keeps
+ * the ACTIVATIONS resident (three rotating h buffers per SM) and streams the weights through a TMA ring
+ * from an L2-resident image in MMA consumption order; cell state and pooling accumulators live in
+ * `state` (na_decoder_wide_state_bytes(H) bytes, caller-allocated scratch, contents irrelevant between calls;
+ * one buffer per concurrent launch).
+ *   na_decoder_pack_wide_bf16: the 8 nn.LSTM tensors + attn.weight [1,H] + attn.bias [1] -> `packed`
+ *       (na_decoder_wide_packed_bytes(H) bytes).  Both size queries return -1 for an unsupported H.
+ *   na_decoder_infer_wide_bf16: x as for na_decoder_infer_bf16 -> logits [B,NC] (+ probs if not NULL).
+ */
+int64_t na_decoder_wide_packed_bytes(int64_t H);
+int64_t na_decoder_wide_state_bytes(int64_t H);
+int na_decoder_pack_wide_bf16(const float* w_ih0, const float* w_hh0, const float* b_ih0, const float* b_hh0,
+                              const float* w_ih1, const float* w_hh1, const float* b_ih1, const float* b_hh1,
+                              const float* attn_w, const float* attn_b, void* packed, int64_t H, na_stream_t stream);
+int na_decoder_infer_wide_bf16(const void* x_bf16_tmp, const void* packed, const float* ln_w, const float* ln_b,
+                               const float* fc0_w, const float* fc0_b, const float* fc3_w, const float* fc3_b,
+                               void* state, float* logits, float* probs,
+                               int64_t T, int64_t B, int64_t Bp, int64_t H, int64_t NC, na_stream_t stream);
 
 /* ---- tensor-core tier, training (bf16 operands; fp32 accumulate, cell state, gradients) ------------
  * Layouts: TMP fp32 [T][Bp][48]; TCL bf16 [T][Bp/128][F/8][128][8] (tile-chunk layout: a tile's

@@ -105,6 +105,21 @@ class EEG_LSTM(nn.Module):
         return (self.lstm.input_size == 8 and self.lstm.hidden_size == 48 and self.lstm.num_layers == 2
                 and self.fc[3].out_features <= 16)
 
+    def tc_wide_supported(self) -> bool:
+        """Wide shapes of the tensor-core tier (streamed weights): BASELINE configs[4] and its neighbours."""
+        return (self.lstm.input_size == 8 and self.lstm.hidden_size in ops.WIDE_HIDDEN and self.lstm.num_layers == 2
+                and self.fc[3].out_features <= 16)
+
+    def _packed_tc_wide(self):
+        ps = self.lstm.layer(0) + self.lstm.layer(1) + [self.attn.weight, self.attn.bias]
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+        hit = self._pack_cache.get("tc_wide")
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, ops.decoder_pack_wide_bf16(ps[:8], ps[8], ps[9]))
+            self._pack_cache["tc_wide"] = hit
+        return hit[1]
+
     def _packed_tc(self):
         ps = self.lstm.layer(0) + self.lstm.layer(1)
         key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
@@ -124,6 +139,9 @@ class EEG_LSTM(nn.Module):
         with torch.no_grad():
             if bf16 and self.tc_supported():
                 return ops.decoder_infer_tc(x, self._packed_tc(), self._head_params(), want_probs, self.zscore_input)
+            if bf16 and self.tc_wide_supported():
+                return ops.decoder_infer_wide(x, self._packed_tc_wide(), self._head_params(), self.lstm.hidden_size,
+                                              want_probs, self.zscore_input)
             L = self.lstm.num_layers
             return ops.decoder_infer(x, [self.lstm.layer(l) for l in range(L)],
                                      [ops._f32c(t) for t in self._head_params()], want_probs, self.zscore_input,

@@ -293,7 +293,7 @@ def decoder_pack_bf16(lstm_flat: Sequence[Tensor]) -> Tensor:
 
 @decoder_pack_bf16.register_fake
 def _(lstm_flat):
-    return lstm_flat[0].new_empty((22 * 3072,), dtype=torch.uint8)
+    return lstm_flat[0].new_empty((2 * 22 * 3072,), dtype=torch.uint8)
 
 
 @torch.library.custom_op("neuroalpha::decoder_infer_bf16", mutates_args=(), device_types="cuda")
@@ -328,6 +328,79 @@ def decoder_infer_tc(x: Tensor, packed: Tensor, head_params: Sequence[Tensor], w
     B, T, C = x.shape
     xt = window_zscore(x, T, T, zscore, True, NA_F16, TC_TILE)
     return decoder_infer_bf16(xt, packed, list(head_params), B, want_probs)
+
+
+WIDE_HIDDEN = (96, 144, 192)          # hidden sizes of the streamed-weight tensor-core kernel (na_decoder_wide.cu)
+
+
+@torch.library.custom_op("neuroalpha::decoder_pack_wide_bf16", mutates_args=(), device_types="cuda")
+def decoder_pack_wide_bf16(lstm_flat: Sequence[Tensor], attn_w: Tensor, attn_b: Tensor) -> Tensor:
+    """The 8 nn.LSTM tensors + the attention vector of a wide decoder (H in WIDE_HIDDEN, input_size 8, 2 layers)
+    -> the weight image the wide kernel streams every step (MMA consumption order) + its score operand."""
+    _require_cuda(*lstm_flat, attn_w, attn_b)
+    ts = [_f32c(t) for t in lstm_flat]
+    H = ts[1].shape[1]
+    if len(ts) != 8 or H not in WIDE_HIDDEN or tuple(ts[0].shape) != (4 * H, 8) or tuple(ts[4].shape) != (4 * H, H):
+        raise RuntimeError("decoder_pack_wide_bf16: implements input_size=8, hidden_size in (96, 144, 192), num_layers=2")
+    packed = torch.empty((_lib.query("na_decoder_wide_packed_bytes", H),), dtype=torch.uint8, device=ts[0].device)
+    _lib.call("na_decoder_pack_wide_bf16", *[t.data_ptr() for t in ts], _f32c(attn_w).data_ptr(), _f32c(attn_b).data_ptr(),
+              packed.data_ptr(), H, _stream())
+    return packed
+
+
+@decoder_pack_wide_bf16.register_fake
+def _(lstm_flat, attn_w, attn_b):
+    H = lstm_flat[1].shape[1]
+    nch = H // 48
+    return lstm_flat[0].new_empty((nch * (2 + 3 * (H // 16)) * 6144 + (1 + H // 16) * 512,), dtype=torch.uint8)
+
+
+_WIDE_STATE: dict = {}
+
+
+def _wide_state(H: int, device) -> Tensor:
+    """Per-device L2-resident workspace of the wide kernel (cell state + pooling accumulators of every CTA).
+    One buffer per (device, H, stream): launches on one stream are ordered, so it is re-used."""
+    key = (device.index, H, _stream())
+    buf = _WIDE_STATE.get(key)
+    if buf is None:
+        buf = torch.empty((_lib.query("na_decoder_wide_state_bytes", H),), dtype=torch.uint8, device=device)
+        _WIDE_STATE[key] = buf
+    return buf
+
+
+@torch.library.custom_op("neuroalpha::decoder_infer_wide_bf16", mutates_args=(), device_types="cuda")
+def decoder_infer_wide_bf16(x_tmp: Tensor, packed: Tensor, head: Sequence[Tensor], B: int, H: int,
+                            want_probs: bool) -> Tuple[Tensor, Tensor]:
+    """Whole wide-decoder forward on tcgen05 with streamed weights.  x_tmp as for decoder_infer_bf16;
+    head = [ln.w, ln.b, fc0.w, fc0.b, fc3.w, fc3.b] (the attention vector is part of `packed`)."""
+    _require_cuda(x_tmp, packed, *head)
+    T, Bp, C = x_tmp.shape
+    if x_tmp.dtype != TC_VALUE_DTYPE or C != 8 or Bp % TC_TILE:
+        raise RuntimeError("decoder_infer_wide_bf16: x_tmp must be fp16 [T, Bp % 128 == 0, 8] (the tier's value format)")
+    head = [_f32c(t) for t in head]
+    NC = head[4].shape[0]
+    logits = torch.empty((B, NC), dtype=torch.float32, device=x_tmp.device)
+    probs = torch.empty((B, NC) if want_probs else (0,), dtype=torch.float32, device=x_tmp.device)
+    state = _wide_state(H, x_tmp.device)
+    _lib.call("na_decoder_infer_wide_bf16", x_tmp.data_ptr(), packed.data_ptr(), *[t.data_ptr() for t in head],
+              state.data_ptr(), logits.data_ptr(), _ptr(probs) if want_probs else None, T, B, Bp, H, NC, _stream())
+    return logits, probs
+
+
+@decoder_infer_wide_bf16.register_fake
+def _(x_tmp, packed, head, B, H, want_probs):
+    NC = head[4].shape[0]
+    return x_tmp.new_empty((B, NC), dtype=torch.float32), x_tmp.new_empty((B, NC) if want_probs else (0,), dtype=torch.float32)
+
+
+def decoder_infer_wide(x: Tensor, packed: Tensor, head_params: Sequence[Tensor], H: int, want_probs: bool = False,
+                       zscore: bool = False) -> Tuple[Tensor, Tensor]:
+    """Eval forward of a wide decoder on the tensor-core tier.  head_params in EEG_LSTM._head_params() order."""
+    _require_cuda(x)
+    B, T, C = x.shape
+    xt = window_zscore(x, T, T, zscore, True, NA_F16, TC_TILE)
+    return decoder_infer_wide_bf16(xt, packed, list(head_params[2:]), B, H, want_probs)
 
 
 # ------------------------------------------------------------------------------------------

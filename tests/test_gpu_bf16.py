@@ -83,6 +83,42 @@ def test_bf16_synthetic_512_and_many_tiles(dev, checkpoint):
     assert (a.argmax(1) != b.argmax(1)).mean() < 2e-3
 
 
+def test_bf16_tile_modes_agree(dev, checkpoint):
+    """Every tile layout of the v2 kernel (full 128-window tiles, a 3-quarter remainder, R = 2 and R = 4 row-replicated
+    remainders, several tiles per CTA) gives bit-identical logits to the unreplicated layout, the v1 kernel agrees
+    within the tier's rounding, and all of them match the exact fp32 tier."""
+    from neural_speech_decoding_b200 import _lib, ops
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    gen = torch.Generator(device="cpu").manual_seed(3)
+    m = bf16_model(dev, checkpoint)
+    T = 40
+    try:
+        for quarters_per_cta in (1, 2, 3, 5, 6, 7):            # R=4 | R=2 | 3-quarter tile | 4+R4 | 4+R2 | 4+3
+            B = sms * 32 * quarters_per_cta - 7                    # ragged last quarter
+            x = (torch.randn(B, T, 8, generator=gen) * 2.73).to(dev)
+            with torch.inference_mode():
+                xt = ops.window_zscore(x, T, T, False, True, 2, 128)
+                packed, head = m._packed_tc(), m._head_params()
+                outs = {}
+                for name, hs, rep in (("v2", 3, 1), ("v2_norep", 3, 0), ("v1", 2, 0)):
+                    _lib.call("na_set_tuning", b"tc_infer_hs", hs)
+                    _lib.call("na_set_tuning", b"tc_infer_rep", rep)
+                    lg, pr = ops.decoder_infer_bf16(xt, packed, head, B, True)
+                    outs[name] = lg.cpu().numpy()
+                    np.testing.assert_allclose(pr.cpu().numpy(), no.softmax(outs[name]), atol=2e-6)
+                m.compute_dtype = torch.float32
+                exact = m(x).cpu().numpy()
+                m.compute_dtype = torch.bfloat16
+            assert np.array_equal(outs["v2"], outs["v2_norep"]), quarters_per_cta
+            err = np.abs(outs["v2"] - exact).max(axis=1) / np.abs(exact).max()
+            assert err.mean() < 2e-3 and np.quantile(err, 0.999) < BF16_TOL, (quarters_per_cta, err.mean(), err.max())
+            err1 = np.abs(outs["v2"] - outs["v1"]).max(axis=1) / np.abs(exact).max()
+            assert err1.mean() < 2e-3 and np.quantile(err1, 0.999) < BF16_TOL, (quarters_per_cta, err1.mean(), err1.max())
+    finally:
+        _lib.call("na_set_tuning", b"tc_infer_hs", 3)
+        _lib.call("na_set_tuning", b"tc_infer_rep", 1)
+
+
 def test_bf16_input_tensor_selects_tier_and_keeps_dtype(dev, checkpoint, windows):
     from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
     m = EEG_LSTM()
@@ -241,3 +277,47 @@ def test_edge_shapes_and_bfloat16_module(dev, checkpoint, windows):
     mb.train()
     torch.nn.functional.cross_entropy(mb(xb).float(), torch.randint(0, 3, (16,)).to(dev)).backward()
     assert all(p.grad is not None and p.grad.dtype == torch.bfloat16 for p in mb.parameters())
+
+
+# ---- wide hidden sizes (streamed-weight kernel, na_decoder_wide.cu) ------------------------------------------
+
+def test_wide_h192_matches_reference_golden(dev, golden_dir):
+    """BASELINE configs[4] architecture: the reference's own logits for EEG_LSTM(hidden_size=192) (seeded init,
+    tests/golden/ref_stress_h192.npz, generated by importing the real reference)."""
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    f = np.load(golden_dir / "ref_stress_h192.npz")
+    sd = {k[3:]: torch.from_numpy(f[k].copy()) for k in f.files if k.startswith("sd.")}
+    m = EEG_LSTM(hidden_size=192)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).eval()
+    m.compute_dtype = torch.bfloat16
+    assert m.tc_wide_supported() and not m.tc_supported()
+    with torch.inference_mode():
+        lg, pr = m.decode(torch.from_numpy(f["x"]).to(dev))
+    got = lg.cpu().numpy()
+    assert rel(got, f["logits"]) < BF16_TOL, rel(got, f["logits"])
+    assert np.array_equal(got.argmax(1), f["logits"].argmax(1))
+    np.testing.assert_allclose(pr.cpu().numpy(), no.softmax(got), atol=2e-6)
+
+
+@pytest.mark.parametrize("H,T,B", [(192, 37, 300), (144, 20, 130), (96, 50, 5), (192, 3, 148 * 128 + 77), (192, 1, 64)])
+def test_wide_matches_exact_tier(dev, H, T, B):
+    """Seeded random decoders of every wide size against the exact fp32 tier (itself pinned to the oracle):
+    ragged batches, several tiles per CTA, T = 1 (flush-only pooling)."""
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    torch.manual_seed(100 + H + T)
+    m = EEG_LSTM(hidden_size=H, num_classes=5).to(dev).eval()
+    with torch.no_grad():                                  # make the attention scores and the head non-trivial
+        m.attn.weight.mul_(4.0); m.attn.bias.fill_(0.3)
+        m.ln.weight.uniform_(0.5, 1.5); m.ln.bias.uniform_(-0.2, 0.2)
+    gen = torch.Generator(device="cpu").manual_seed(H * 7 + B)
+    x = (torch.randn(B, T, 8, generator=gen) * 2.73).to(dev)
+    with torch.inference_mode():
+        exact = m(x).cpu().numpy()
+        m.compute_dtype = torch.bfloat16
+        got = m(x).cpu().numpy()
+        again = m(x).cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.array_equal(got, again)                      # deterministic, workspace re-use is clean
+    err = np.abs(got - exact).max(axis=1) / np.abs(exact).max()
+    assert err.mean() < 2e-3 and np.quantile(err, 0.999) < BF16_TOL and err.max() < 0.1, (err.mean(), err.max())
