@@ -7,6 +7,7 @@ raised.  ``call(name, *args)`` converts a non-zero return code into
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 from pathlib import Path
 
@@ -56,7 +57,7 @@ def load(path: str | Path | None = None):
     global _LIB
     if _LIB is not None:
         return _LIB
-    p = Path(path) if path else LIB_PATH
+    p = Path(path or os.environ.get("NEUROALPHA_B200_LIB") or LIB_PATH)     # env override: A/B-timing a variant build
     if not p.exists():
         raise RuntimeError(
             f"{p} not found: the CUDA library is not built (run `python -c 'import __graft_entry__ as g; "

@@ -65,7 +65,7 @@ struct Smem2 {
     HeadSmem2 head;
     float zx[kRows][kH + 1];                                       // pooled vector exchange, once per tile
     alignas(8) uint64_t x_full[kV2XStages], x_empty[kV2XStages];
-    uint64_t d0_full, d1_full, h0_ready[2], h0_free[2], h1_ready;
+    uint64_t d0_full, d1_full, h0_ready[2], h1_ready;
     uint32_t tmem_base;
 };
 
@@ -161,7 +161,11 @@ __device__ __forceinline__ void epilogue_tile(Smem2& S, const int q, const int g
     if (qs >= nq) {                                // idle quarter: keep the barrier protocol only
         for (int t = 0; t <= T; ++t) {
             const int n = n0 + t;
-            if (t < T) { mbar_wait(&S.d0_full, n & 1); mbar_arrive(&S.h0_ready[n & 1]); }
+            if (t < T) {
+                mbar_wait(&S.d0_full, n & 1);
+                if (q == 0 && g == 0 && lane == 0) mbar_arrive(&S.x_empty[n % kV2XStages]);
+                mbar_arrive(&S.h0_ready[n & 1]);
+            }
             if (t >= 1) { mbar_wait(&S.d1_full, k1 & 1); ++k1; mbar_arrive(&S.h1_ready); }
         }
         mbar_wait(&S.d1_full, k1 & 1); ++k1;
@@ -216,8 +220,11 @@ __device__ __forceinline__ void epilogue_tile(Smem2& S, const int q, const int g
     for (int t = 0; t <= T; ++t) {
         const int n = n0 + t;
         if (t < T) {                               // ---- layer 0, step t
+            // d0_full: the layer-0 MMA of step n has completed -> its x stage is free (one thread tells the TMA producer;
+            // a plain mbarrier.arrive instead of a second tcgen05.commit per step).  The h0 buffer written below was last
+            // read by the layer-1 MMA of step n-2, whose d1_full this thread waited for in the previous iteration.
             mbar_wait(&S.d0_full, n & 1);
-            mbar_wait(&S.h0_free[n & 1], ((n >> 1) & 1) ^ 1);   // layer-1 MMA of step n-2 has read this buffer
+            if (q == 0 && g == 0 && lane == 0) mbar_arrive(&S.x_empty[n % kV2XStages]);
             tc_fence_after();
             uint32_t hb[2 * kSlots];
             layer_phase(tmem_d0, c0, S.h0[n & 1], hb);
@@ -307,7 +314,8 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
     constexpr int kMmaWarp = 12, kTmaWarp = 13;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem2& S = *reinterpret_cast<Smem2*>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: role branches are uniform control flow
 
     // ---- one-time setup --------------------------------------------------------------------------
     {
@@ -358,7 +366,6 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
             for (int s = 0; s < kV2XStages; ++s) { mbar_init(&S.x_full[s], 1); mbar_init(&S.x_empty[s], 1); }
             mbar_init(&S.d0_full, 1); mbar_init(&S.d1_full, 1);
             mbar_init(&S.h0_ready[0], 384); mbar_init(&S.h0_ready[1], 384);
-            mbar_init(&S.h0_free[0], 1); mbar_init(&S.h0_free[1], 1);
             mbar_init(&S.h1_ready, 384);
             fence_mbar_init();
         }
@@ -368,7 +375,7 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
         __syncthreads();
         tc_fence_after();
     }
-    const uint32_t tmem = S.tmem_base;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, S.tmem_base, 0);
     const uint32_t tmem_d0 = tmem, tmem_d1 = tmem + kN;
 
     // Work split: 32-window quarters, CTA i owns a contiguous range and walks it in tiles of up to 4 quarters; a
@@ -396,7 +403,9 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
             }
         } else if (warp == kMmaWarp) {
             // ================= MMA issuer ============================================================
-            if (lane == 0) {
+            {
+                // whole warp, warp-uniform control flow; one elected lane issues (descriptors stay on the uniform datapath)
+                const bool leader = elect_one();
                 const uint64_t d_b0 = umma_desc(smem_u32(S.b0), kBChunk, 128), d_b1 = umma_desc(smem_u32(S.b1), kB1Chunk, 128);
                 const uint64_t d_x0 = umma_desc(smem_u32(S.x[0]), kAChunk, 128);
                 const uint64_t d_h0[2] = {umma_desc(smem_u32(S.h0[0]), kAChunk, 128), umma_desc(smem_u32(S.h0[1]), kAChunk, 128)};
@@ -411,15 +420,14 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
                         const int s = n % kV2XStages, u = n / kV2XStages;
                         mbar_wait(&S.x_full[s], u & 1);
                         tc_fence_after();
-                        umma_bf16(tmem_d0, desc_adv(d_x0, s * 2 * kAChunk), d_b0, 0u);
+                        if (leader) umma_bf16(tmem_d0, desc_adv(d_x0, s * 2 * kAChunk), d_b0, 0u);
                         if (t >= 1) {
                             const uint64_t hprev = d_h0[(n - 1) & 1];
 #pragma unroll
                             for (int i = 0; i < 3; ++i)
-                                umma_bf16(tmem_d0, desc_adv(hprev, 2 * i * kAChunk), desc_adv(d_b0, (2 + 2 * i) * kBChunk), 1u);
+                                if (leader) umma_bf16(tmem_d0, desc_adv(hprev, 2 * i * kAChunk), desc_adv(d_b0, (2 + 2 * i) * kBChunk), 1u);
                         }
-                        umma_commit(&S.x_empty[s]);
-                        umma_commit(&S.d0_full);
+                        if (leader) umma_commit(&S.d0_full);
                     }
                     if (t >= 1) {                                  // layer 1, step m = t - 1
                         const int m = n - 1;
@@ -430,15 +438,14 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
                         const uint64_t hin = d_h0[m & 1];
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
-                            umma_bf16_i(tmem_d1, desc_adv(hin, 2 * i * kAChunk), desc_adv(d_b1, 2 * i * kB1Chunk), kIdescL1, i == 0 ? 0u : 1u);
+                            if (leader) umma_bf16_i(tmem_d1, desc_adv(hin, 2 * i * kAChunk), desc_adv(d_b1, 2 * i * kB1Chunk), kIdescL1, i == 0 ? 0u : 1u);
                         if (t >= 2) {
 #pragma unroll
                             for (int i = 0; i < 3; ++i)
-                                umma_bf16_i(tmem_d1, desc_adv(d_h1, 2 * i * kAChunk), desc_adv(d_b1, (6 + 2 * i) * kB1Chunk), kIdescL1, 1u);
+                                if (leader) umma_bf16_i(tmem_d1, desc_adv(d_h1, 2 * i * kAChunk), desc_adv(d_b1, (6 + 2 * i) * kB1Chunk), kIdescL1, 1u);
                         }
-                        umma_bf16_i(tmem_d1, d_onez, desc_adv(d_b1, 12 * kB1Chunk), kIdescL1, 1u);
-                        umma_commit(&S.d1_full);
-                        umma_commit(&S.h0_free[m & 1]);
+                        if (leader) umma_bf16_i(tmem_d1, d_onez, desc_adv(d_b1, 12 * kB1Chunk), kIdescL1, 1u);
+                        if (leader) umma_commit(&S.d1_full);
                     }
                 }
                 // flush: s_{T-1} = w_a . h1_{T-1} + b_a into the 16 score columns only
@@ -449,9 +456,9 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
                     const uint64_t d_b1s = desc_adv(d_b1, kN * 16);          // rows 192..207 of every chunk
 #pragma unroll
                     for (int i = 0; i < 3; ++i)
-                        umma_bf16_i(tmem_d1 + kN, desc_adv(d_h1, 2 * i * kAChunk), desc_adv(d_b1s, (6 + 2 * i) * kB1Chunk), kIdescFlush, i == 0 ? 0u : 1u);
-                    umma_bf16_i(tmem_d1 + kN, d_onez, desc_adv(d_b1s, 12 * kB1Chunk), kIdescFlush, 1u);
-                    umma_commit(&S.d1_full);
+                        if (leader) umma_bf16_i(tmem_d1 + kN, desc_adv(d_h1, 2 * i * kAChunk), desc_adv(d_b1s, (6 + 2 * i) * kB1Chunk), kIdescFlush, i == 0 ? 0u : 1u);
+                    if (leader) umma_bf16_i(tmem_d1 + kN, d_onez, desc_adv(d_b1s, 12 * kB1Chunk), kIdescFlush, 1u);
+                    if (leader) umma_commit(&S.d1_full);
                 }
             }
         } else {

@@ -33,9 +33,16 @@ namespace tc {
 
 constexpr int kWThreads = 14 * 32;
 constexpr int kWXStages = 2;
-constexpr int kWRing = 4;                      // weight ring stages
+#ifndef NA_WIDE_RING
+#define NA_WIDE_RING 4
+#endif
+#ifndef NA_WIDE_SPS
+#define NA_WIDE_SPS 2
+#endif
+constexpr int kWRing = NA_WIDE_RING;           // weight ring stages
+constexpr int kWSps = NA_WIDE_SPS;             // K16 slices per ring stage (one mbarrier round trip per stage)
 constexpr int kWSlice = kN * 32;               // bytes of one K16 weight slice: [2 K-chunks][192 rows][8] fp16 = 6,144
-constexpr int kWStage = 2 * kWSlice;           // a ring stage holds up to two slices
+constexpr int kWStage = kWSps * kWSlice;
 constexpr int kWD = 208;                       // TMEM columns per task accumulator (192 gates + 16 score)
 constexpr int kWFc = NA_FC_HIDDEN;
 constexpr uint32_t kIdesc16 = make_idesc(16, kFmtVal, kFmtVal);
@@ -133,6 +140,32 @@ __global__ void pack_wide_kernel(const float* __restrict__ w_ih0, const float* _
     }
 }
 
+// ---- thread-block-cluster helpers (weight-stream multicast) ---------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 1-D TMA bulk copy global -> the SAME shared-memory offset of every CTA in cta_mask; each destination CTA's
+// mbarrier (same offset) receives the complete_tx bytes.
+__device__ __forceinline__ void bulk_load_mc(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
 __device__ __forceinline__ void w_tmem_ld2(uint32_t taddr, uint32_t (&v)[2]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -172,14 +205,20 @@ decoder_infer_wide_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                           const float* __restrict__ fc3_w, const float* __restrict__ fc3_b,
                           float* __restrict__ state,                  // [grid][3][kStateFloats]: c0, c1, z
                           float* __restrict__ logits, float* __restrict__ probs,
-                          int T, int64_t B, int64_t Bp, int NC, int nquarters) {
+                          int T, int64_t B, int64_t Bp, int NC, int nquarters, int cs, int dbg) {
+    // dbg (timing experiments only, results invalid): 1 = skip the cell update, 2 = skip the gate MMAs, 4 = skip the weight loads
+    // cs = thread-block-cluster size (1, 2 or 4): the CTAs of a cluster stream the SAME weight image in lockstep, so
+    // each ring stage is fetched from L2 once per cluster -- rank r loads 1/cs of it and multicasts it to all.
     using C = WideCfg<NCH>;
     constexpr int H = C::H;
     constexpr int kMmaWarp = 12, kTmaWarp = 13;
     constexpr int kTasks = 2 * NCH;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     WideSmem<NCH>& S = *reinterpret_cast<WideSmem<NCH>*>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // warp index through a shuffle: tells the compiler it is warp-uniform, so the role branches below are uniform
+    // control flow and the MMA / TMA descriptors are computed on the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
     // ---- one-time setup --------------------------------------------------------------------------
     {
@@ -199,7 +238,7 @@ decoder_infer_wide_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
         for (int i = tid; i < NC; i += kWThreads) S.b3[i] = fc3_b[i];
         if (tid == 0) {
             for (int s = 0; s < kWXStages; ++s) { mbar_init(&S.x_full[s], 1); mbar_init(&S.x_empty[s], 1); }
-            for (int s = 0; s < kWRing; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], 1); }
+            for (int s = 0; s < kWRing; ++s) { mbar_init(&S.b_full[s], 1); mbar_init(&S.b_empty[s], cs); }     // every CTA's consumer releases it
             for (int s = 0; s < 2; ++s) { mbar_init(&S.d_full[s], 1); mbar_init(&S.d_empty[s], 384); }
             for (int l = 0; l < 2; ++l)
                 for (int j = 0; j < NCH; ++j) mbar_init(&S.a_ready[l][j], 384);
@@ -210,16 +249,23 @@ decoder_infer_wide_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
         fence_proxy_async_smem();
         __syncthreads();
         tc_fence_after();
+        if (cs > 1) cluster_sync_all();             // peers' mbarriers are initialised before anything is multicast to them
     }
-    const uint32_t tmem = S.tmem_base;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, S.tmem_base, 0);
+    const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
 
-    const int q_begin = (int)(((int64_t)blockIdx.x * nquarters) / gridDim.x);
-    const int q_end = (int)(((int64_t)(blockIdx.x + 1) * nquarters) / gridDim.x);
+    // Tiles of 4 quarters (128 windows), strided over the CTAs; EVERY CTA runs the same number of rounds (the CTAs
+    // of a cluster share the weight ring in lockstep) -- a CTA without a tile runs an idle round (nq = 0).
+    const int ntiles = (nquarters + 3) / 4;
+    const int rounds = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
     int n0 = 0;                 // running step index across tiles (A-buffer rotation, a_ready / x parities)
     uint32_t tg = 0;            // running task index (accumulator double buffer; + 1 flush round per tile)
     uint32_t gi = 0;            // running ring-stage index
-    for (int q0 = q_begin; q0 < q_end; q0 += 4, n0 += T) {
-        const int nq = min(4, q_end - q0);
+    for (int rd = 0; rd < rounds; ++rd, n0 += T) {
+        const int tile = rd * (int)gridDim.x + (int)blockIdx.x;
+        const int q0 = tile * 4;
+        const int nq = tile < ntiles ? min(4, nquarters - q0) : 0;
         const uint32_t x_bytes = (uint32_t)nq * 32u * 16u;
         const int64_t b0 = (int64_t)q0 * 32;
         // ---- h0_{-1} = h1_{-1} = 0: clear the A buffers -------------------------------------------------
@@ -236,17 +282,24 @@ decoder_infer_wide_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                 for (int t = 0; t < T; ++t) {
                     const int n = n0 + t, sx = n % kWXStages, ux = n / kWXStages;
                     mbar_wait(&S.x_empty[sx], (ux & 1) ^ 1);
-                    mbar_arrive_expect_tx(&S.x_full[sx], x_bytes);
-                    bulk_load(S.x[sx], x + ((int64_t)t * Bp + b0) * 8, x_bytes, &S.x_full[sx]);
+                    if (x_bytes) {
+                        mbar_arrive_expect_tx(&S.x_full[sx], x_bytes);
+                        bulk_load(S.x[sx], x + ((int64_t)t * Bp + b0) * 8, x_bytes, &S.x_full[sx]);
+                    } else mbar_arrive(&S.x_full[sx]);              // idle round
                     const unsigned char* src = packed;
                     for (int task = 0; task < kTasks; ++task) {
                         const int nsl = task < NCH ? C::kSl0 : C::kSl1;
-                        for (int s = 0; s < nsl; s += 2, ++gi) {
-                            const uint32_t bytes = (uint32_t)min(2, nsl - s) * kWSlice;
+                        for (int s = 0; s < nsl; s += kWSps, ++gi) {
+                            const uint32_t bytes = (uint32_t)min(kWSps, nsl - s) * kWSlice;
                             const int sb = gi % kWRing;
-                            mbar_wait(&S.b_empty[sb], ((gi / kWRing) & 1) ^ 1);
+                            mbar_wait(&S.b_empty[sb], ((gi / kWRing) & 1) ^ 1);        // released by every CTA of the cluster
                             mbar_arrive_expect_tx(&S.b_full[sb], bytes);
-                            bulk_load(S.ring[sb], src, bytes, &S.b_full[sb]);
+                            if (dbg & 4) { asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&S.b_full[sb])), "r"(bytes) : "memory"); }
+                            else if (cs == 1) bulk_load(S.ring[sb], src, bytes, &S.b_full[sb]);
+                            else {
+                                const uint32_t part = bytes / (uint32_t)cs;
+                                bulk_load_mc(S.ring[sb] + crank * part, src + crank * part, part, &S.b_full[sb], cmask);
+                            }
                             src += bytes;
                         }
                     }
@@ -254,73 +307,101 @@ decoder_infer_wide_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
             }
         } else if (warp == kMmaWarp) {
             // ================= MMA issuer ============================================================
-            if (lane == 0) {
-                const uint64_t d_p[3] = {umma_desc(smem_u32(S.p[0]), kAChunk, 128), umma_desc(smem_u32(S.p[1]), kAChunk, 128),
-                                         umma_desc(smem_u32(S.p[2]), kAChunk, 128)};
-                const uint64_t d_x0 = umma_desc(smem_u32(S.x[0]), kAChunk, 128), d_onez = umma_desc(smem_u32(S.onez), kAChunk, 128);
-                const uint64_t d_ring0 = umma_desc(smem_u32(S.ring[0]), kN * 16, 128);
-                const uint64_t d_score = umma_desc(smem_u32(S.bscore), 256, 128);
-                for (int t = 0; t <= T; ++t) {                     // t == T: flush round (scores of the last step)
-                    const int n = n0 + t;
-                    const int ia = n % 3, ib = (n + 1) % 3, ic = (n + 2) % 3;     // h0_{n-1} | h0_n | h1_{n-1};  h1_n -> ia
-                    if (t < T) {
-                        const int sx = n % kWXStages, ux = n / kWXStages;
-                        mbar_wait(&S.x_full[sx], ux & 1);
-                    }
-                    for (int task = 0; task < (t < T ? kTasks : 1); ++task, ++tg) {
-                        const bool flush = (t == T);
-                        const int layer = flush ? 1 : (task >= NCH ? 1 : 0);
-                        const int dbuf = tg & 1;
-                        mbar_wait(&S.d_empty[dbuf], ((tg >> 1) & 1) ^ 1);          // epilogue of task tg-2 has drained it
-                        tc_fence_after();
-                        const uint32_t tmem_d = tmem + dbuf * kWD;
-                        if (flush) {
-                            // h1_{T-1} lives in the buffer the next step would call ic
-                            for (int j = 0; j < NCH; ++j) mbar_wait(&S.a_ready[1][j], (n - 1) & 1);
-                            tc_fence_after();
-                            for (int s = 0; s < C::kScoreSlices; ++s)
-                                umma_bf16_i(tmem_d + kN, s == 0 ? d_onez : desc_adv(d_p[ic], (s - 1) * 2 * kAChunk),
-                                            desc_adv(d_score, s * 512), kIdesc16, s == 0 ? 0u : 1u);
-                            umma_commit(&S.d_full[dbuf]);
-                            continue;
-                        }
-                        const int nsl = layer ? C::kSl1 : C::kSl0;
-                        const bool first_l1 = (task == NCH);
-                        for (int s = 0; s < nsl; s += 2, ++gi) {
-                            const int sb = gi % kWRing;
-                            mbar_wait(&S.b_full[sb], (gi / kWRing) & 1);
-                            tc_fence_after();
+            // The WHOLE warp runs this loop with warp-uniform control flow (so descriptor arithmetic stays on the
+            // uniform datapath and feeds UTCHMMA without per-MMA R2UR moves); one fixed lane issues.  Tasks and
+            // slices are fully unrolled: every descriptor is a per-step base plus a compile-time offset.  (The first
+            // version -- one thread, runtime slice bookkeeping -- spent ~300 cycles per 96-cycle MMA and starved
+            // the tensor pipe: profiles/r1_wide_ncu_full.csv.)
+            const bool leader = elect_one();
+            const uint64_t d_p0 = umma_desc(smem_u32(S.p[0]), kAChunk, 128);
+            constexpr uint64_t kBufStep = (uint64_t)(C::kABuf >> 4);
+            const uint64_t d_x0 = umma_desc(smem_u32(S.x[0]), kAChunk, 128), d_onez = umma_desc(smem_u32(S.onez), kAChunk, 128);
+            const uint64_t d_ring0 = umma_desc(smem_u32(S.ring[0]), kN * 16, 128);
+            const uint64_t d_score = umma_desc(smem_u32(S.bscore), 256, 128);
+            constexpr uint64_t kSl16 = (uint64_t)((2 * kAChunk) >> 4);      // A descriptor step per K16 slice
+            bool ring_ready = false;                               // "b_full of ring stage gi has completed its phase"
+            for (int t = 0; t <= T; ++t) {                         // t == T: flush round (scores of the last step)
+                const int n = n0 + t;
+                const int ia = n % 3, ib = (n + 1) % 3, ic = (n + 2) % 3;         // h0_{n-1} | h0_n | h1_{n-1};  h1_n -> ia
+                const uint64_t d_ia = d_p0 + kBufStep * ia, d_ib = d_p0 + kBufStep * ib, d_ic = d_p0 + kBufStep * ic;
+                if (t == T) {
+                    const int dbuf = tg & 1;
+                    mbar_wait(&S.d_empty[dbuf], ((tg >> 1) & 1) ^ 1);
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const int ss = s + h;
-                                if (ss >= nsl) break;
-                                uint64_t da;
-                                if (layer == 0) da = ss == 0 ? desc_adv(d_x0, (n % kWXStages) * 2 * kAChunk) : desc_adv(d_p[ia], (ss - 1) * 2 * kAChunk);
-                                else if (ss == 0) da = d_onez;
-                                else if (ss <= C::kHS) {
-                                    if (first_l1 && t > 0 && (ss - 1) % 3 == 0) {           // first use of h1_{n-1} chunk
-                                        mbar_wait(&S.a_ready[1][(ss - 1) / 3], (n - 1) & 1);
-                                        tc_fence_after();
-                                    }
-                                    da = desc_adv(d_p[ic], (ss - 1) * 2 * kAChunk);
-                                } else {
-                                    if (first_l1 && (ss - 1 - C::kHS) % 3 == 0) {           // first use of h0_n chunk
-                                        mbar_wait(&S.a_ready[0][(ss - 1 - C::kHS) / 3], n & 1);
-                                        tc_fence_after();
-                                    }
-                                    da = desc_adv(d_p[ib], (ss - 1 - C::kHS) * 2 * kAChunk);
-                                }
-                                umma_bf16(tmem_d, da, desc_adv(d_ring0, sb * kWStage + h * kWSlice), ss == 0 ? 0u : 1u);
-                                if (first_l1 && ss <= C::kHS)                               // score of step n-1 (same A operand)
-                                    umma_bf16_i(tmem_d + kN, da, desc_adv(d_score, ss * 512), kIdesc16, ss == 0 ? 0u : 1u);
-                            }
-                            umma_commit(&S.b_empty[sb]);
-                        }
+                    for (int j = 0; j < NCH; ++j) mbar_wait(&S.a_ready[1][j], (n - 1) & 1);      // h1_{T-1}
+                    tc_fence_after();
+                    if (leader) {
+#pragma unroll
+                        for (int s = 0; s < C::kScoreSlices; ++s)
+                            umma_bf16_i(tmem + dbuf * kWD + kN, s == 0 ? d_onez : d_ic + kSl16 * (s - 1), d_score + 32 * s, kIdesc16,
+                                        s == 0 ? 0u : 1u);
                         umma_commit(&S.d_full[dbuf]);
-                        if (task == NCH - 1) umma_commit(&S.x_empty[n % kWXStages]);       // last reader of x_t
+                    }
+                    ++tg;
+                    break;
+                }
+                {
+                    const int sx = n % kWXStages, ux = n / kWXStages;
+                    mbar_wait(&S.x_full[sx], ux & 1);
+                }
+                const uint64_t d_xs = d_x0 + kSl16 * (n % kWXStages);
+#pragma unroll
+                for (int task = 0; task < kTasks; ++task, ++tg) {
+                    constexpr int kL0 = C::kSl0, kL1 = C::kSl1;
+                    const bool l1 = task >= NCH;                   // compile-time after unrolling
+                    const bool first_l1 = task == NCH;
+                    const int nsl = l1 ? kL1 : kL0;
+                    const int dbuf = tg & 1;
+                    mbar_wait(&S.d_empty[dbuf], ((tg >> 1) & 1) ^ 1);              // epilogue of task tg-2 has drained it
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem + dbuf * kWD;
+#pragma unroll
+                    for (int s = 0; s < kL1; s += kWSps) {
+                        if (s >= nsl) break;
+                        const int sb = gi % kWRing;
+                        // the status of this stage was probed one group ago (try_wait latency hidden behind the MMA issue)
+                        if (!ring_ready) mbar_wait(&S.b_full[sb], (gi / kWRing) & 1);
+                        ring_ready = mbar_try_wait(&S.b_full[(gi + 1) % kWRing], ((gi + 1) / kWRing) & 1);
+                        const uint64_t d_b = d_ring0 + (uint64_t)(sb * (kWStage >> 4));
+#pragma unroll
+                        for (int h = 0; h < kWSps; ++h) {
+                            const int ss = s + h;
+                            if (ss >= nsl) break;
+                            uint64_t da;
+                            if (!l1) da = ss == 0 ? d_xs : d_ia + kSl16 * (ss - 1);
+                            else if (ss == 0) da = d_onez;
+                            else if (ss <= C::kHS) {
+                                if (first_l1 && (ss - 1) % 3 == 0 && t > 0) {               // first use of an h1_{n-1} chunk
+                                    mbar_wait(&S.a_ready[1][(ss - 1) / 3], (n - 1) & 1);
+                                    tc_fence_after();
+                                }
+                                da = d_ic + kSl16 * (ss - 1);
+                            } else {
+                                if (first_l1 && (ss - 1 - C::kHS) % 3 == 0) {               // first use of an h0_n chunk
+                                    mbar_wait(&S.a_ready[0][(ss - 1 - C::kHS) / 3], n & 1);
+                                    tc_fence_after();
+                                }
+                                da = d_ib + kSl16 * (ss - 1 - C::kHS);
+                            }
+                            if (leader && !(dbg & 2)) {
+                                umma_bf16(tmem_d, da, d_b + (uint64_t)(h * (kWSlice >> 4)), ss == 0 ? 0u : 1u);
+                                if (first_l1 && ss <= C::kHS)                               // score of step n-1 (same A operand)
+                                    umma_bf16_i(tmem_d + kN, da, d_score + 32 * ss, kIdesc16, ss == 0 ? 0u : 1u);
+                            }
+                        }
+                        if (leader) {
+                            if (cs == 1) umma_commit(&S.b_empty[sb]);
+                            else umma_commit_mc(&S.b_empty[sb], cmask);
+                        }
+                        ++gi;
+                    }
+                    if (leader) {
+                        umma_commit(&S.d_full[dbuf]);
+                        if (task == NCH - 1) umma_commit(&S.x_empty[n % kWXStages]);        // last reader of x_t
                     }
                 }
             }
+            __syncwarp();
         } else {
             // ================= epilogue warps: (lane quarter q, 16-unit group g) of every task ===============
             const int q = warp & 3, g = warp >> 2;
@@ -358,11 +439,11 @@ decoder_infer_wide_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                     const float4* pz = reinterpret_cast<const float4*>(st_z);
                     if (!flush) {
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) cs[s] = t == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(pc + sidx(j, s));
+                        for (int s = 0; s < 4; ++s) cs[s] = (t == 0 || (dbg & 8)) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(pc + sidx(j, s));
                     }
                     if (layer == 1 && !flush) {
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) zs[s] = t <= 1 ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(pz + sidx(j, s));
+                        for (int s = 0; s < 4; ++s) zs[s] = (t <= 1 || (dbg & 8)) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(pz + sidx(j, s));
                     }
                     mbar_wait(&S.d_full[dbuf], (tg >> 1) & 1);
                     tc_fence_after();
@@ -413,7 +494,7 @@ decoder_infer_wide_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                             z1.z = fmaf(e, val_lo(hv.w), z1.z * scl); z1.w = fmaf(e, val_hi(hv.w), z1.w * scl);
                         }
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) __stcg(reinterpret_cast<float4*>(st_z) + sidx(j, s), zs[s]);
+                        for (int s = 0; s < 4; ++s) if (!(dbg & 8)) __stcg(reinterpret_cast<float4*>(st_z) + sidx(j, s), zs[s]);
                     }
                     // ---- gates -> cell update -> H chunk into the A buffer (layer 0: h0_n -> ib, layer 1: h1_n -> ia)
                     unsigned char* dst = S.p[layer ? ia : ib] + (j * 6 + 2 * g) * kAChunk + row * 16;
@@ -421,8 +502,11 @@ decoder_infer_wide_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                     for (int pr = 0; pr < 2; ++pr) {
                         uint32_t v[32], hb[4];
                         tmem_ld32(tmem_d + lane_base + (4 * g + 2 * pr) * 16, v);
+                        if (dbg & 1) { hb[0] = v[0]; hb[1] = v[5]; hb[2] = v[17]; hb[3] = v[30]; }
+                        else {
                         w_cell_granule(v, &cs[2 * pr].x, hb);
                         w_cell_granule(v + 16, &cs[2 * pr + 1].x, hb + 2);
+                        }
                         st_shared_v4(dst + pr * kAChunk, hb[0], hb[1], hb[2], hb[3]);
                     }
                     tc_fence_before();
@@ -431,7 +515,7 @@ decoder_infer_wide_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                     mbar_arrive(&S.d_empty[dbuf]);
                     float4* pcw = reinterpret_cast<float4*>(layer ? st_c1 : st_c0);
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) __stcg(pcw + sidx(j, s), cs[s]);
+                    for (int s = 0; s < 4; ++s) if (!(dbg & 8)) __stcg(pcw + sidx(j, s), cs[s]);
                     ++tg;
                 }
             }
@@ -490,11 +574,19 @@ decoder_infer_wide_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
 
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();                 // no peer multicasts into / arrives on this CTA's smem after it exits
     if (warp == kTmaWarp) {
         tc_fence_after();
         tmem_free_all(tmem);
     }
 }
+
+int g_wide_dbg = 0;
+void set_wide_dbg(int v) { g_wide_dbg = v; }
+// Measured (B200, H = 192): multicast halves the L2 reads but not the time -- the stream is bound by the ring round trip
+// (TMA latency + tcgen05.commit -> mbarrier), not by L2 bandwidth -- so the default stays 1.
+int g_wide_cluster = 1;      // na_set_tuning("tc_wide_cluster", 1 | 2 | 4)
+void set_wide_cluster(int v) { g_wide_cluster = (v == 1 || v == 2 || v == 4) ? v : 1; }
 
 template <int NCH>
 static int launch_wide(const void* x, const void* packed, const float* ln_w, const float* ln_b, const float* fc0_w,
@@ -505,10 +597,25 @@ static int launch_wide(const void* x, const void* packed, const float* ln_w, con
     if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_wide_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
     const int nquarters = (int)((B + 31) / 32);
     const int ntiles = (nquarters + 3) / 4;
-    const int grid = ntiles < sms ? ntiles : sms;
-    decoder_infer_wide_kernel<NCH><<<grid, kWThreads, smem, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const unsigned char*>(packed), ln_w, ln_b, fc0_w, fc0_b, fc3_w,
-        fc3_b, state, logits, probs, T, B, Bp, NC, nquarters);
+    int cs = g_wide_cluster;
+    if (ntiles < 2) cs = 1;
+    int grid = ntiles < sms ? ntiles : sms;
+    grid = (grid + cs - 1) / cs * cs;                          // whole clusters; surplus CTAs run idle rounds
+    if (grid > sms) grid = sms / cs * cs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kWThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, decoder_infer_wide_kernel<NCH>, reinterpret_cast<const __nv_bfloat16*>(x),
+                           reinterpret_cast<const unsigned char*>(packed), ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, state, logits, probs,
+                           T, B, Bp, NC, nquarters, cs, g_wide_dbg);
+    if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_wide_bf16: launch failed (%s)", cudaGetErrorString(e));
     count_launch();
     return check_launch("na_decoder_infer_wide_bf16");
 }

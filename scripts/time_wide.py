@@ -17,14 +17,17 @@ def t(fn, reps=3):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 flops = 2 * T * (4 * H * (8 + H) + 4 * H * 2 * H) + 4 * T * H
+from neural_speech_decoding_b200 import _lib
 for N in Ns:
+  for cs, dbg in ((1, 0), (1, 15)):
+    _lib.call('na_set_tuning', b'tc_wide_cluster', cs); _lib.call('na_set_tuning', b'tc_wide_dbg', dbg)
     x = torch.randn(N, T, 8, device=dev) * 2.73
     with torch.inference_mode():
         xt = ops.window_zscore(x, T, T, False, True, 2, 128)
         packed = m._packed_tc_wide(); head = m._head_params()
         ms = t(lambda: ops.decoder_infer_wide_bf16(xt, packed, head[2:], N, H, True))
         rounds = -(-N // (148 * 128))
-        print(f"H={H} T={T} N={N}: {ms:.2f} ms -> {N/ms:.1f} k windows/s, {N*flops/ms*1e-9:.1f} TFLOP/s, {ms*1e3/T/rounds:.2f} us per step-round", flush=True)
+        print(f"cluster={cs} dbg={dbg} H={H} T={T} N={N}: {ms:.2f} ms -> {N/ms:.1f} k windows/s, {N*flops/ms*1e-9:.1f} TFLOP/s, {ms*1e3/T/rounds:.2f} us per step-round", flush=True)
         if N <= 4096:
             got = ops.decoder_infer_wide_bf16(xt, packed, head[2:], N, H, True)[0].cpu().numpy()
             m.compute_dtype = torch.float32
