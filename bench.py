@@ -292,6 +292,7 @@ def run_gpu_arm(args):
     train = None
     if not args.no_train:
         train = train_leg(args, world, rank, dev)
+    stress = stress_leg(dev, peaks) if (rank == 0 and not args.no_stress) else None
 
     if rank != 0:
         return
@@ -314,19 +315,22 @@ def run_gpu_arm(args):
         "gpu_launches": bf["launches"],
         "clocks": bf["clocks"],
         "roofline": {
-            "kernel": "decoder_infer_bf16_kernel (tcgen05/TMEM/TMA: K2+K3+K4 fused, whole decoder forward)",
+            "kernel": "decoder_infer_v2_kernel (tcgen05/TMEM/TMA: K2+K3+K4 fused, whole decoder forward)",
             "bound": "tensor", "achieved": tc_tflops, "peak": peak, "unit": "TFLOP/s", "frac": tc_tflops / peak,
             "peak_source": peaks["source"] + " cuBLAS bf16 (burst: kernel timed alone)",
             # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-            # (profiles/r1_tc_infer_ncu_full.csv: 409.7 MB + 5.6 MB at 40,960 windows), scaled to this launch
-            "traffic": 415.36e6 * n_win / 40960, "traffic_source": "profiles/r1_tc_infer_ncu_full.csv",
+            # (profiles/r1_tc2_infer_ncu_full.csv: 189.65 MB + 3.51 MB at 18,944 windows), scaled to this launch
+            "traffic": 193.16e6 * n_win / 18944, "traffic_source": "profiles/r1_tc2_infer_ncu_full.csv",
             "algorithmic_bytes_per_launch": n_win * (T * C * 2 + NC * 8),
             "algorithmic_flops_per_launch": FWD_FLOPS_PER_WINDOW * n_win,
             "ms_per_launch": ms_tc,
             "per_timestep_latency_us": ms_tc * 1e3 / (T * tile_rounds),
-            "note": "latency/MUFU-bound, not tensor-bound: 1250 dependent cell updates per window; each step needs "
-                    "5 MUFU (tanh) per hidden unit -> 3840 MUFU cycles per 128-window step for both layers "
-                    "(xu pipe 72-80 % busy in ncu); 16-bit operands are fp16 (see DESIGN.md section 5)",
+            # the pipe that actually bounds the kernel: 5 tanh.approx per unit, layer and step on the 16-lane/clk/SM MUFU
+            "xu_pipe": xu_pipe(n_win, ms_tc, bf["clocks"]),
+            "note": "MUFU-bound, not tensor-bound: 1250 dependent cell updates per window, 5 tanh per hidden unit and step "
+                    "-> 3,840 MUFU cycles per 128-window step for both layers; the software-pipelined v2 kernel keeps the xu "
+                    "pipe 90.7 % busy on full rounds (ncu); the 40,960-window step is 2.16 rounds, its remainder runs as "
+                    "row-replicated short tiles; 16-bit operands are fp16 (DESIGN.md section 5)",
             "k1_window_pack": {"kernel": "window_zscore_vec_kernel (fp32 -> time-major bf16)", "bound": "hbm",
                                "achieved": n_win * T * C * 6 / (ms_pack16 * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                "unit": "GB/s", "frac": n_win * T * C * 6 / (ms_pack16 * 1e-3) / 1e9 / peaks["hbm_gbs"]},
@@ -351,7 +355,58 @@ def run_gpu_arm(args):
                                 "kind": "port", "sample": cpu["sample"]}
     if train:
         line["train"] = train
+    if stress:
+        line["stress"] = stress
     print(json.dumps(line), flush=True)
+
+
+def xu_pipe(n_win, ms_tc, clocks):
+    """The pipe that actually bounds the headline kernel: 5 tanh.approx per hidden unit, layer and step on the
+    16-results/clk/SM MUFU pipe (measured: scripts/ubench/mufu_rate.cu, 31.4 results/ns/SM at 1.965 GHz)."""
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    ops_ = n_win * T * 2 * H * 5
+    ach, peak = ops_ / (ms_tc * 1e-3) / 1e9, 16 * 148 * mhz * 1e-3
+    return {"bound": "MUFU (transcendental pipe): 16 results/clk/SM x 148 SMs x SM clock under load", "achieved": ach, "peak": peak,
+            "unit": "G tanh/s", "frac": ach / peak, "sm_mhz": mhz,
+            "ncu": "sm__inst_executed_pipe_xu 90.7 % of peak on full 148-tile rounds (profiles/r1_tc2_infer_ncu_full.csv)"}
+
+
+def stress_leg(dev, peaks):
+    """BASELINE configs[4]: EEG_LSTM(hidden_size=192), T = 2500 (4x longer windows, 4x wider LSTM), synthetic EEG,
+    one full round of 148 x 128 windows, eval forward on the streamed-weight tensor-core kernel
+    (na_decoder_wide.cu).  Seeded default init (there is no shipped checkpoint of that shape)."""
+    from neural_speech_decoding_b200 import ops
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    Hs, Ts, Bs = 192, 2500, 148 * 128
+    flops = 2 * Ts * (4 * Hs * (C + Hs) + 4 * Hs * 2 * Hs) + 4 * Ts * Hs + 2 * 32 * Hs + 2 * 32 * NC
+    torch.manual_seed(0)
+    m = EEG_LSTM(hidden_size=Hs).to(dev).eval()
+    m.compute_dtype = torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(77)
+    x = torch.empty((Bs, Ts, C), dtype=torch.float32, device=dev)
+    for i in range(0, Bs, 1024):                       # 1.5 GB of fp32 windows, generated in slabs
+        x[i:i + 1024] = (torch.randn((min(1024, Bs - i), Ts, C), generator=g) * INPUT_SIGMA).to(dev)
+    with torch.inference_mode():
+        xt = ops.window_zscore(x, Ts, Ts, False, True, ops.NA_F16, ops.TC_TILE)
+        packed, head = m._packed_tc_wide(), m._head_params()
+        ms_k = time_steps(lambda: ops.decoder_infer_wide_bf16(xt, packed, head[2:], Bs, Hs, True), 3, 2, 1, dev) / 3
+        del xt
+        ms = time_steps(lambda: m.decode(x, want_probs=True), 3, 1, 1, dev) / 3
+        # the exact-fp32 tier (generic kernels) on a bounded slice, for the ratio
+        m.compute_dtype = torch.float32
+        ms32 = time_steps(lambda: m.decode(x[:256], want_probs=True), 1, 1, 1, dev)
+    del x
+    torch.cuda.empty_cache()
+    tf = flops * Bs / (ms_k * 1e-3) / 1e12
+    return {"workload": "configs[4]: EEG_LSTM(hidden_size=192), T=2500, C=8, 18,944 synthetic windows, eval forward",
+            "value": Bs / (ms * 1e-3), "unit": "windows/s", "ms_per_pass": ms,
+            "kernel": "decoder_infer_wide_kernel<4> (tcgen05; activations resident, weights streamed by TMA from L2)",
+            "ms_per_launch": ms_k, "per_timestep_latency_us": ms_k * 1e3 / Ts,
+            "flops_per_window": flops, "achieved_tflops": tf,
+            "frac_of_bf16_sustained_peak": tf / peaks["bf16_tflops_sustained"], "frac_of_bf16_burst_peak": tf / peaks["bf16_tflops"],
+            "fp32_exact_windows_per_s": 256 / (ms32 * 1e-3),
+            "parity": "tests/test_gpu_bf16.py::test_wide_*: reference golden (H=192) and the exact tier, 2e-2 contract",
+            "note": "training at this shape runs on the exact-fp32 generic tier (no tensor-core BPTT for H > 48 yet)"}
 
 
 def train_leg(args, world, rank, dev):
@@ -407,6 +462,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-stress", action="store_true")
     ap.add_argument("--train-batch", type=int, default=65536, help="GLOBAL batch of the train leg (configs[2])")
     ap.add_argument("--train-micro", type=int, default=16384)
     args = ap.parse_args()
