@@ -84,7 +84,8 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                             int T, int64_t Bp, int ntiles) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     FwdSmem& S = *reinterpret_cast<FwdSmem*>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform (role branches = uniform control flow)
     {
         const uint4* src = reinterpret_cast<const uint4*>(packed);
         uint4* dst = reinterpret_cast<uint4*>(S.b0);
@@ -137,7 +138,8 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                     bulk_load(S.x[s], x + ((int64_t)t * Bp + b0) * 8, kAChunk, &S.x_full[s]);
                 }
         } else if (warp == 16) {
-            if (lane == 0) {
+            {   // whole warp, warp-uniform control flow; one elected lane issues (see na_decoder_wide.cu)
+                const bool leader = elect_one();
                 const uint64_t d_b0 = umma_desc(smem_u32(S.b0), kBChunk, 128), d_b1 = umma_desc(smem_u32(S.b1), kBChunk, 128);
                 const uint64_t d_x0 = umma_desc(smem_u32(S.x[0]), kAChunk, 128);
                 const uint64_t d_h0[2] = {umma_desc(smem_u32(S.h0[0]), kAChunk, 128), umma_desc(smem_u32(S.h0[1]), kAChunk, 128)};
@@ -150,12 +152,12 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                         mbar_wait(&S.h0_ready[(n + 1) & 1], ((n - 1) >> 1) & 1);
                         tc_fence_after();
                         const uint64_t hprev = d_h0[(n + 1) & 1];
-                        umma_bf16(tmem_d0, desc_adv(d_x0, s * 2 * kAChunk), d_b0, 0u);
+                        if (leader) umma_bf16(tmem_d0, desc_adv(d_x0, s * 2 * kAChunk), d_b0, 0u);
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
-                            umma_bf16(tmem_d0, desc_adv(hprev, 2 * i * kAChunk), desc_adv(d_b0, (2 + 2 * i) * kBChunk), 1u);
-                        umma_commit(&S.x_empty[s]);
-                        umma_commit(&S.d0_full);
+                            if (leader) umma_bf16(tmem_d0, desc_adv(hprev, 2 * i * kAChunk), desc_adv(d_b0, (2 + 2 * i) * kBChunk), 1u);
+                        if (leader) umma_commit(&S.x_empty[s]);
+                        if (leader) umma_commit(&S.d0_full);
                     }
                     if (t >= 1) {
                         const int m = n0 + t - 1;
@@ -165,13 +167,13 @@ lstm2_fwd_train_bf16_kernel(const __nv_bfloat16* __restrict__ x, const unsigned 
                         const uint64_t hin = drop ? d_h0d[m & 1] : d_h0[m & 1];
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
-                            umma_bf16(tmem_d1, desc_adv(hin, 2 * i * kAChunk), desc_adv(d_b1, 2 * i * kBChunk), i == 0 ? 0u : 1u);
+                            if (leader) umma_bf16(tmem_d1, desc_adv(hin, 2 * i * kAChunk), desc_adv(d_b1, 2 * i * kBChunk), i == 0 ? 0u : 1u);
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
-                            umma_bf16(tmem_d1, desc_adv(d_h1, 2 * i * kAChunk), desc_adv(d_b1, (6 + 2 * i) * kBChunk), 1u);
-                        umma_bf16(tmem_d1, d_onez, desc_adv(d_b1, 12 * kBChunk), 1u);
-                        umma_commit(&S.d1_full);
-                        umma_commit(&S.h0_free[m & 1]);
+                            if (leader) umma_bf16(tmem_d1, desc_adv(d_h1, 2 * i * kAChunk), desc_adv(d_b1, (6 + 2 * i) * kBChunk), 1u);
+                        if (leader) umma_bf16(tmem_d1, d_onez, desc_adv(d_b1, 12 * kBChunk), 1u);
+                        if (leader) umma_commit(&S.d1_full);
+                        if (leader) umma_commit(&S.h0_free[m & 1]);
                     }
                 }
             }
@@ -370,7 +372,8 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
     using C = BwdCfg<KI>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     BwdSmem<KI>& S = *reinterpret_cast<BwdSmem<KI>*>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform (role branches = uniform control flow)
     {
         const uint4* sg = reinterpret_cast<const uint4*>(packed_g);
         uint4* dgp = reinterpret_cast<uint4*>(S.bg);
@@ -435,7 +438,8 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
             // per iteration: R(prev) -> G(cur) -> commit g_full -> W(prev) -> commit act_free, w_done.
             // The epilogue only needs R and G; W (dW accumulation) trails behind and is fenced by w_done
             // before the epilogue overwrites d(gates).
-            if (lane == 0) {
+            {   // whole warp, warp-uniform control flow; one elected lane issues
+                const bool leader = elect_one();
                 // base descriptors, built once (see desc_adv)
                 const uint64_t d_bg = umma_desc(smem_u32(S.bg), kBChunk, 128);                 // forward B, K-major
                 const uint64_t d_br = umma_desc(smem_u32(S.br), C::kNR * 16, 128);             // [W_ih|W_hh]^T, K-major
@@ -453,7 +457,7 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                         tc_fence_after();
 #pragma unroll
                         for (int ks = 0; ks < 12; ++ks)
-                            umma_bf16_i(tm_r, desc_adv(d_dgk, 2 * ks * kAChunk), desc_adv(d_br, 2 * ks * C::kNR * 16), kIdescR,
+                            if (leader) umma_bf16_i(tm_r, desc_adv(d_dgk, 2 * ks * kAChunk), desc_adv(d_br, 2 * ks * C::kNR * 16), kIdescR,
                                         ks == 0 ? 0u : 1u);
                     }
                     if (i < T) {
@@ -463,21 +467,21 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                         const uint64_t da = d_actk[s];
 #pragma unroll
                         for (int ks = 0; ks < C::kStageChunks / 2; ++ks)
-                            umma_bf16(tm_g, desc_adv(da, 2 * ks * kAChunk), desc_adv(d_bg, 2 * ks * kBChunk), ks == 0 ? 0u : 1u);
+                            if (leader) umma_bf16(tm_g, desc_adv(da, 2 * ks * kAChunk), desc_adv(d_bg, 2 * ks * kBChunk), ks == 0 ? 0u : 1u);
                     }
-                    umma_commit(&S.g_full);        // R(prev) and G(cur) done; i == T: tail (R only)
+                    if (leader) umma_commit(&S.g_full);        // R(prev) and G(cur) done; i == T: tail (R only)
                     if (i >= 1) {
                         const uint64_t db = d_actm[sp];
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks) {
                             const uint32_t acc = (first_w && ks == 0) ? 0u : 1u;
                             const uint64_t bdesc = desc_adv(db, ks * 256);
-                            umma_bf16_i(tm_w1, desc_adv(d_dgm1, ks * 256), bdesc, kIdescW, acc);
-                            umma_bf16_i(tm_w2, desc_adv(d_dgm2, ks * 256), bdesc, kIdescW, acc);
+                            if (leader) umma_bf16_i(tm_w1, desc_adv(d_dgm1, ks * 256), bdesc, kIdescW, acc);
+                            if (leader) umma_bf16_i(tm_w2, desc_adv(d_dgm2, ks * 256), bdesc, kIdescW, acc);
                         }
                         first_w = false;
-                        umma_commit(&S.act_free[sp]);
-                        umma_commit(&S.w_done);
+                        if (leader) umma_commit(&S.act_free[sp]);
+                        if (leader) umma_commit(&S.w_done);
                     }
                 }
             }
