@@ -152,6 +152,18 @@ int na_head_bwd_f32(const float* dlogits, const float* h, const float* stats, co
                     float* dh, float* dparams, float* partials,
                     int64_t T, int64_t B, int64_t Bp, int64_t H, int64_t NC, na_stream_t stream);
 
+/* ---- ingestion of the collector's CSV windows ---------------------------------
+ * Replaces np.loadtxt(path, delimiter=",", dtype=np.float32) over the files np.savetxt(fmt="%.7f") wrote
+ * (Neural_decoding_data_collector.py:129-139): `text` = the raw bytes of n_files files back to back (device memory),
+ * offsets[n_files + 1] = their byte ranges (device int64), out = fp32 [n_files][fields_per_file] in file order
+ * (row-major rows x columns of each file), status[2n] = number of fields found in file n, status[2n+1] = number of
+ * fields that are not plain [sign]digits[.digits] with <= 15 significant digits (the caller must treat either
+ * mismatch as an error; the kernel never approximates).  Bit-identical to numpy: decimal -> correctly rounded
+ * double (one IEEE division of two exact operands) -> float32.  max_file_bytes = the longest file (<= 200 KB).
+ */
+int na_csv_parse_f32(const void* text, const int64_t* offsets, float* out, int* status, int64_t n_files,
+                     int64_t fields_per_file, int64_t max_file_bytes, na_stream_t stream);
+
 /* ---- tensor-core tier: whole decoder forward, bf16 operands / fp32 accumulate ----------------
  * One persistent warp-specialised tcgen05 / TMEM / TMA kernel: K2 (input-gate contraction,
  * fused as extra K-steps of the per-step MMA), K3 (2-layer recurrence, wavefronted), K4 (online

@@ -76,7 +76,8 @@ def train(X: np.ndarray, y: np.ndarray, num_classes: int, epochs: int = 30, batc
     if bf16:
         model.compute_dtype = torch.bfloat16
     tr_idx, va_idx = split_indices(len(X), val_frac, seed)
-    Xd, yd = torch.from_numpy(X).to(device), torch.from_numpy(y).to(device)
+    Xd = X.to(device) if isinstance(X, torch.Tensor) else torch.from_numpy(X).to(device)       # GPU-ingested or numpy
+    yd = y.to(device) if isinstance(y, torch.Tensor) else torch.from_numpy(y).to(device)
     trainer = DataParallelTrainer(model, torch.optim.Adam(model.parameters(), lr=lr), world_size=world)
     history = []
     for ep in range(epochs):
@@ -125,7 +126,12 @@ def main(argv=None) -> None:
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     classes = [c.strip() for c in args.classes.split(",") if c.strip()]
-    X, y = load_windows(args.data, classes)
+    if Path(args.data).is_dir():
+        # CSV directory: one H2D copy of the raw bytes + the GPU parser (ingest.py), not one np.loadtxt per file
+        from .ingest import load_labelled_dir
+        X, y, _ = load_labelled_dir(args.data, classes, torch.device("cuda", torch.cuda.current_device()))
+    else:
+        X, y = load_windows(args.data, classes)
     model, _ = train(X, y, len(classes), args.epochs, args.batch, args.lr, args.val_frac, args.seed, args.bf16)
     if int(os.environ.get("RANK", "0")) == 0:
         torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, args.out)

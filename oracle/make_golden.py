@@ -57,8 +57,22 @@ def load_windows():
     return X, names, prefix
 
 
+def csv_bytes_fixture():
+    """Raw bytes of a few of the reference's own CSV windows + what np.loadtxt (the reference's reader) makes of
+    them: the pin for the GPU CSV parser (na_csv_parse_f32)."""
+    files = sorted(p for p in (REF / "EEG_data_collection").glob("*.csv"))
+    pick = [files[i] for i in (0, 57, 133, 210, 323)]
+    raw = [p.read_bytes() for p in pick]
+    offsets = np.zeros(len(raw) + 1, dtype=np.int64)
+    np.cumsum([len(r) for r in raw], out=offsets[1:])
+    parsed = np.stack([np.loadtxt(p, delimiter=",", dtype=np.float32) for p in pick])
+    np.savez_compressed(OUT / "csv_bytes.npz", text=np.frombuffer(b"".join(raw), dtype=np.uint8), offsets=offsets,
+                        parsed=parsed, names=np.array([p.name for p in pick]))
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    csv_bytes_fixture()
     torch.set_num_threads(1)           # deterministic reduction order in the fixtures
     stub_brainflow()
     from Utilities.lstm_eeg_model import EEG_LSTM, SimplePredictor, CLASS_NAMES
