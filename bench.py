@@ -281,6 +281,23 @@ def run_gpu_arm(args):
     l1_tflops = L1_KERNEL_FLOPS_PER_WINDOW * n_win / (ms_l1 * 1e-3) / 1e12
     tile_rounds = -(-(n_win // 128) // 148)
 
+    # ---- CSV ingestion kernel: 4,096 files of the collector's format, HBM-bound byte work ------
+    import io
+    from neural_speech_decoding_b200 import ingest
+    files = []
+    for i in range(64):
+        bio = io.BytesIO()
+        np.savetxt(bio, host[0, i].numpy(), delimiter=",", fmt="%.7f")
+        files.append(bio.getvalue())
+    files = files * 64
+    off = np.zeros(len(files) + 1, dtype=np.int64)
+    np.cumsum([len(f) for f in files], out=off[1:])
+    text_dev = torch.frombuffer(bytearray(b"".join(files)), dtype=torch.uint8).to(dev)
+    off_dev = torch.from_numpy(off).to(dev)
+    ms_csv = time_steps(lambda: ingest.parse_csv_bytes(text_dev, off_dev), reps, 2, 1, dev) / reps
+    csv_bytes = int(off[-1]) + len(files) * T * C * 4
+    del text_dev
+
     # ---- measured CUDA-core fp32 peak (FFMA probe) -------------------------------------------------
     out = torch.zeros(4, device=dev)
     blocks, iters = 148 * 8, 1 << 16
@@ -334,6 +351,9 @@ def run_gpu_arm(args):
             "k1_window_pack": {"kernel": "window_zscore_vec_kernel (fp32 -> time-major bf16)", "bound": "hbm",
                                "achieved": n_win * T * C * 6 / (ms_pack16 * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                "unit": "GB/s", "frac": n_win * T * C * 6 / (ms_pack16 * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+            "csv_parse": {"kernel": "csv_parse_kernel (4,096 files of 625x8 '%.7f' text -> fp32; includes the status D2H check)",
+                          "bound": "hbm", "achieved": csv_bytes / (ms_csv * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                          "frac": csv_bytes / (ms_csv * 1e-3) / 1e9 / peaks["hbm_gbs"], "files_per_s": 4096 / (ms_csv * 1e-3)},
             "k1_zscore_f32": {"kernel": "window_zscore_vec_kernel (z-score, fp32 in/out)", "bound": "hbm",
                               "achieved": n_win * T * C * 8 / (ms_z * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                               "unit": "GB/s", "frac": n_win * T * C * 8 / (ms_z * 1e-3) / 1e9 / peaks["hbm_gbs"]},

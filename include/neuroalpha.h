@@ -160,6 +160,7 @@ int na_head_bwd_f32(const float* dlogits, const float* h, const float* stats, co
  * fields that are not plain [sign]digits[.digits] with <= 15 significant digits (the caller must treat either
  * mismatch as an error; the kernel never approximates).  Bit-identical to numpy: decimal -> correctly rounded
  * double (one IEEE division of two exact operands) -> float32.  max_file_bytes = the longest file (<= 200 KB).
+ * `text` must be 16-byte aligned and readable up to the next 16-byte boundary after its last byte.
  */
 int na_csv_parse_f32(const void* text, const int64_t* offsets, float* out, int* status, int64_t n_files,
                      int64_t fields_per_file, int64_t max_file_bytes, na_stream_t stream);
