@@ -25,7 +25,11 @@ int reduce_partials(const float* partial, float* out, int nchunks, int64_t n, cu
 namespace tc {
 
 constexpr int kTrainThreads = 576;     // forward: 8 + 8 epilogue warps (2 per TMEM quarter and layer), MMA warp, TMA warp
-constexpr int kBwdThreads = 320;       // backward: 8 epilogue warps (2 per TMEM lane quarter), MMA warp, TMA warp
+constexpr int kBwdEG = 3;               // backward: epilogue warps per TMEM lane quarter (each: 6 / kBwdEG unit blocks)
+constexpr int kBwdUB = 6 / kBwdEG;      // 8-unit blocks per epilogue thread
+constexpr int kBwdU = 8 * kBwdUB;       // units per epilogue thread
+constexpr int kBwdEW = 4 * kBwdEG;      // epilogue warps; warp kBwdEW = MMA issuer, kBwdEW + 1 = TMA producer
+constexpr int kBwdThreads = (kBwdEW + 2) * 32;
 constexpr int kXStagesT = 4;
 
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
@@ -344,9 +348,9 @@ struct BwdSmem {
     // partial (score, dz.h), the per-tile dz.z exchange, and the final d(attn) reduction
     float wa[kH];
     float ba;
-    float2 xch[2][2][kRows];
-    float xch0[2][kRows];
-    float red[8][kH / 2 + 1];
+    float2 xch[2][kBwdEG][kRows];
+    float xch0[kBwdEG][kRows];
+    float red[kBwdEW][kBwdU + 1];
 };
 
 template <int KI>
@@ -392,23 +396,23 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
             for (int s = 0; s < 2; ++s) { mbar_init(&S.act_full[s], 1); mbar_init(&S.act_free[s], 1); }
             mbar_init(&S.g_full, 1);
             mbar_init(&S.w_done, 1);
-            mbar_init(&S.dg_ready, 256);
+            mbar_init(&S.dg_ready, 32 * kBwdEW);
             fence_mbar_init();
         }
         if (dz != nullptr) {
             for (int i = tid; i < kH; i += kBwdThreads) S.wa[i] = attn_w[i];
             if (tid == 0) S.ba = attn_b[0];
         }
-        if (warp == 9) tmem_alloc_all(&S.tmem_base);
+        if (warp == kBwdEW + 1) tmem_alloc_all(&S.tmem_base);
         tc_fence_before();
         fence_proxy_async_smem();
         __syncthreads();
         tc_fence_after();
     }
     const bool head = (KI == 48) && dz != nullptr;
-    float dwa[24], dba = 0.f;                     // d attn_w (this thread's 24 units), d attn_b; epilogue warps only
+    float dwa[kBwdU], dba = 0.f;                  // d attn_w (this thread's units), d attn_b; epilogue warps only
 #pragma unroll
-    for (int j = 0; j < 24; ++j) dwa[j] = 0.f;
+    for (int j = 0; j < kBwdU; ++j) dwa[j] = 0.f;
     const uint32_t tmem = S.tmem_base;
     const uint32_t tm_g = tmem + C::kColG, tm_r = tmem + C::kColR, tm_w1 = tmem + C::kColW1, tm_w2 = tmem + C::kColW2;
     constexpr uint32_t kIdescR = make_idesc(C::kNR, kFmtGrad, kFmtVal);               // d(gates) x W^T, K-major x K-major
@@ -420,7 +424,7 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
     bool first_w = true;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t b0 = (int64_t)tile * kRows;
-        if (warp == 9) {
+        if (warp == kBwdEW + 1) {
             // ================= TMA producer: [in_t | h_{t-1}] for t = T-1 .. 0 ==========================
             if (lane == 0)
                 for (int i = 0; i < T; ++i) {
@@ -433,7 +437,7 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                     const __nv_bfloat16* hsrc = t > 0 ? h + (((int64_t)(t - 1) * ntiles + tile) * 6) * (kAChunk / 2) : zeros;
                     bulk_load(S.act[s] + C::kHprevChunk * kAChunk, hsrc, 6 * kAChunk, &S.act_full[s]);
                 }
-        } else if (warp == 8) {
+        } else if (warp == kBwdEW) {
             // ================= MMA issuer ================================================================
             // per iteration: R(prev) -> G(cur) -> commit g_full -> W(prev) -> commit act_free, w_done.
             // The epilogue only needs R and G; W (dW accumulation) trails behind and is fenced by w_done
@@ -485,83 +489,87 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                     }
                 }
             }
-        } else if (warp < 8) {
-            // ================= epilogue: thread = window x half of the units (3 blocks of 8) ================
+        } else if (warp < kBwdEW) {
+            // ================= epilogue: thread = window x 1/kBwdEG of the units (kBwdUB blocks of 8) =======
             const int q = warp & 3, hf = warp >> 2;
             const int row = q * 32 + lane;
             const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-            float dc[24], ccur[24];
+            float dc[kBwdU], ccur[kBwdU];
 #pragma unroll
-            for (int j = 0; j < 24; ++j) dc[j] = 0.f;
+            for (int j = 0; j < kBwdU; ++j) dc[j] = 0.f;
             {   // c_{T-1} of this tile (afterwards c_t is carried over from the previous iteration's c_{t-1})
 #pragma unroll
-                for (int j = 0; j < 24; j += 4) {
-                    const float4 a = *reinterpret_cast<const float4*>(cstate + tcl32_off(T - 1, ntiles, tile, hf * 6 + j / 4, row));
+                for (int j = 0; j < kBwdU; j += 4) {
+                    const float4 a = *reinterpret_cast<const float4*>(cstate + tcl32_off(T - 1, ntiles, tile, hf * (kBwdU / 4) + j / 4, row));
                     ccur[j] = a.x; ccur[j + 1] = a.y; ccur[j + 2] = a.z; ccur[j + 3] = a.w;
                 }
             }
             unsigned char* dgrow = S.dg + row * 16;
-            float dzr[24], dzz = 0.f, sm_m = 0.f, inv_l = 1.f;
+            float dzr[kBwdU], dzz = 0.f, sm_m = 0.f, inv_l = 1.f;
             if (head) {
                 const int64_t b = b0 + row;
                 float part = 0.f;
 #pragma unroll
-                for (int j = 0; j < 24; ++j) {
-                    dzr[j] = (b < B) ? dz[b * kH + hf * 24 + j] : 0.f;
-                    part = fmaf(dzr[j], (b < B) ? zpool[b * kH + hf * 24 + j] : 0.f, part);
+                for (int j = 0; j < kBwdU; ++j) {
+                    dzr[j] = (b < B) ? dz[b * kH + hf * kBwdU + j] : 0.f;
+                    part = fmaf(dzr[j], (b < B) ? zpool[b * kH + hf * kBwdU + j] : 0.f, part);
                 }
                 if (b < B) { sm_m = stats[2 * b]; inv_l = 1.0f / stats[2 * b + 1]; }
                 S.xch0[hf][row] = part;
-                named_bar_sync(1 + q, 64);
-                dzz = S.xch0[0][row] + S.xch0[1][row];              // dz . z  (both halves, fixed order)
+                named_bar_sync(1 + q, 32 * kBwdEG);
+                dzz = 0.f;
+#pragma unroll
+                for (int e = 0; e < kBwdEG; ++e) dzz += S.xch0[e][row];   // dz . z  (all unit groups, fixed order)
             }
             for (int i = 0; i <= T; ++i) {
                 const int t = T - 1 - i;                                  // step whose gates are in D_G (i < T)
                 // ---- prefetch this step's c_{t-1} and dh_out BEFORE waiting for the tensor pipe -----------
-                float cp[24], dh[24];
+                float cp[kBwdU], dh[kBwdU];
                 if (i < T && head) {
                     // head backward fused here: the loads and the exchange overlap the tensor pipe's R/G of this step
-                    uint4 hp[3];
+                    uint4 hp[kBwdUB];
 #pragma unroll
-                    for (int bb = 0; bb < 3; ++bb)
-                        hp[bb] = *reinterpret_cast<const uint4*>(h + ((((int64_t)t * ntiles + tile) * 6 + hf * 3 + bb) * kRows + row) * 8);
+                    for (int bb = 0; bb < kBwdUB; ++bb)
+                        hp[bb] = *reinterpret_cast<const uint4*>(h + ((((int64_t)t * ntiles + tile) * 6 + hf * kBwdUB + bb) * kRows + row) * 8);
 #pragma unroll
-                    for (int j = 0; j < 24; j += 4) {
+                    for (int j = 0; j < kBwdU; j += 4) {
                         float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (t > 0) c4 = *reinterpret_cast<const float4*>(cstate + tcl32_off(t - 1, ntiles, tile, hf * 6 + j / 4, row));
+                        if (t > 0) c4 = *reinterpret_cast<const float4*>(cstate + tcl32_off(t - 1, ntiles, tile, hf * (kBwdU / 4) + j / 4, row));
                         cp[j] = c4.x; cp[j + 1] = c4.y; cp[j + 2] = c4.z; cp[j + 3] = c4.w;
                     }
-                    float hv[24];
+                    float hv[kBwdU];
 #pragma unroll
-                    for (int bb = 0; bb < 3; ++bb) {
+                    for (int bb = 0; bb < kBwdUB; ++bb) {
                         const uint32_t w4[4] = {hp[bb].x, hp[bb].y, hp[bb].z, hp[bb].w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) { hv[bb * 8 + 2 * u] = val_lo(w4[u]); hv[bb * 8 + 2 * u + 1] = val_hi(w4[u]); }
                     }
                     float sp = 0.f, gp = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 24; ++j) { sp = fmaf(S.wa[hf * 24 + j], hv[j], sp); gp = fmaf(dzr[j], hv[j], gp); }
+                    for (int j = 0; j < kBwdU; ++j) { sp = fmaf(S.wa[hf * kBwdU + j], hv[j], sp); gp = fmaf(dzr[j], hv[j], gp); }
                     S.xch[i & 1][hf][row] = make_float2(sp, gp);
-                    named_bar_sync(1 + q, 64);
-                    const float2 x0 = S.xch[i & 1][0][row], x1 = S.xch[i & 1][1][row];
-                    const float alpha = __expf(x0.x + x1.x + S.ba - sm_m) * inv_l;
-                    const float ds = alpha * (x0.y + x1.y - dzz);
+                    named_bar_sync(1 + q, 32 * kBwdEG);
+                    float xs = 0.f, xg = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 24; ++j) {
-                        dh[j] = fmaf(alpha, dzr[j], ds * S.wa[hf * 24 + j]);
+                    for (int e = 0; e < kBwdEG; ++e) { const float2 xe = S.xch[i & 1][e][row]; xs += xe.x; xg += xe.y; }   // fixed order
+                    const float alpha = __expf(xs + S.ba - sm_m) * inv_l;
+                    const float ds = alpha * (xg - dzz);
+#pragma unroll
+                    for (int j = 0; j < kBwdU; ++j) {
+                        dh[j] = fmaf(alpha, dzr[j], ds * S.wa[hf * kBwdU + j]);
                         dwa[j] = fmaf(ds, hv[j], dwa[j]);
                     }
                     dba += ds;
                 } else if (i < T) {
                     const int64_t grow = (int64_t)t * Bp + b0 + row;
-                    const float* dhrow = dh_out + grow * kH + hf * 24;           // row-major TMP (head backward)
+                    const float* dhrow = dh_out + grow * kH + hf * kBwdU;           // row-major TMP (head backward)
 #pragma unroll
-                    for (int j = 0; j < 24; j += 4) {
-                        const float4 d = dh_chunked ? *reinterpret_cast<const float4*>(dh_out + tcl32_off(t, ntiles, tile, hf * 6 + j / 4, row))
+                    for (int j = 0; j < kBwdU; j += 4) {
+                        const float4 d = dh_chunked ? *reinterpret_cast<const float4*>(dh_out + tcl32_off(t, ntiles, tile, hf * (kBwdU / 4) + j / 4, row))
                                                     : *reinterpret_cast<const float4*>(dhrow + j);
                         dh[j] = d.x; dh[j + 1] = d.y; dh[j + 2] = d.z; dh[j + 3] = d.w;
                         float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (t > 0) c4 = *reinterpret_cast<const float4*>(cstate + tcl32_off(t - 1, ntiles, tile, hf * 6 + j / 4, row));
+                        if (t > 0) c4 = *reinterpret_cast<const float4*>(cstate + tcl32_off(t - 1, ntiles, tile, hf * (kBwdU / 4) + j / 4, row));
                         cp[j] = c4.x; cp[j + 1] = c4.y; cp[j + 2] = c4.z; cp[j + 3] = c4.w;
                     }
                 }
@@ -572,8 +580,8 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                     // din of step t+1 = D_R[:, 0:48] * mask * scale  -> dh_out of the layer below
                     const int64_t grow = (int64_t)(t + 1) * Bp + b0 + row;
 #pragma unroll
-                    for (int bb = 0; bb < 3; ++bb) {
-                        const int blk = hf * 3 + bb;
+                    for (int bb = 0; bb < kBwdUB; ++bb) {
+                        const int blk = hf * kBwdUB + bb;
                         uint32_t r[8];
                         tmem_ld8(tm_r + lane_base + blk * 8, r);
                         float o[8];
@@ -596,8 +604,8 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                     break;
                 }
 #pragma unroll
-                for (int bb = 0; bb < 3; ++bb) {
-                    const int blk = hf * 3 + bb;
+                for (int bb = 0; bb < kBwdUB; ++bb) {
+                    const int blk = hf * kBwdUB + bb;
                     uint32_t v[32];
                     tmem_ld32(tm_g + lane_base + blk * 32, v);
                     if (i >= 1) {
@@ -645,22 +653,22 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
 
     // ---- per-CTA partial of d attn_w / d attn_b (fused head backward) ----------------------------------------
     if (head) {
-        if (warp < 8) {
+        if (warp < kBwdEW) {
 #pragma unroll
-            for (int j = 0; j < 24; ++j) {
+            for (int j = 0; j < kBwdU; ++j) {
                 const float v = warp_sum(dwa[j]);
                 if (lane == 0) S.red[warp][j] = v;
             }
             const float vb = warp_sum(dba);
-            if (lane == 0) S.red[warp][24] = vb;
+            if (lane == 0) S.red[warp][kBwdU] = vb;
         }
         __syncthreads();
         if (tid < kH) {
-            const int hfj = tid / 24, j = tid % 24;
+            const int hfj = tid / kBwdU, j = tid % kBwdU;
             attn_partial[(size_t)blockIdx.x * (kH + 1) + tid] =
                 S.red[4 * hfj][j] + S.red[4 * hfj + 1][j] + S.red[4 * hfj + 2][j] + S.red[4 * hfj + 3][j];
         } else if (tid == kH) {
-            attn_partial[(size_t)blockIdx.x * (kH + 1) + kH] = S.red[0][24] + S.red[1][24] + S.red[2][24] + S.red[3][24];
+            attn_partial[(size_t)blockIdx.x * (kH + 1) + kH] = S.red[0][kBwdU] + S.red[1][kBwdU] + S.red[2][kBwdU] + S.red[3][kBwdU];
         }
     }
     // ---- per-CTA weight-gradient partial: D_W1 rows = gate columns 0..127, D_W2 rows 64..127 = 128..191 ----
@@ -689,7 +697,7 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) { tc_fence_after(); tmem_free_all(tmem); }
+    if (warp == kBwdEW + 1) { tc_fence_after(); tmem_free_all(tmem); }
 }
 
 // [W_ih | W_hh]^T as the B operand of R: out[chunk = n/8][o][n%8], n = permuted gate column (K index),
