@@ -298,6 +298,12 @@ def run_gpu_arm(args):
     csv_bytes = int(off[-1]) + len(files) * T * C * 4
     del text_dev
 
+    # ---- collector-side filter chain: all 40,960 windows of the step, HBM-bound -----------------
+    from neural_speech_decoding_b200 import filters
+    ms_filt = time_steps(lambda: filters.filter_windows(x_flat), 3, 1, 1, dev) / 3
+    filt_bytes = n_win * C * T * (4 + 4 + 7 * 16)
+    torch.cuda.empty_cache()
+
     # ---- measured CUDA-core fp32 peak (FFMA probe) -------------------------------------------------
     out = torch.zeros(4, device=dev)
     blocks, iters = 148 * 8, 1 << 16
@@ -354,6 +360,10 @@ def run_gpu_arm(args):
             "csv_parse": {"kernel": "csv_parse_kernel (4,096 files of 625x8 '%.7f' text -> fp32; includes the status D2H check)",
                           "bound": "hbm", "achieved": csv_bytes / (ms_csv * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                           "frac": csv_bytes / (ms_csv * 1e-3) / 1e9 / peaks["hbm_gbs"], "files_per_s": 4096 / (ms_csv * 1e-3)},
+            "filter_chain": {"kernel": "iir_chain_kernel (detrend + 4 zero-phase Butterworth band filters, float64, per (window, channel) series)",
+                             "bound": "hbm", "achieved": filt_bytes / (ms_filt * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": filt_bytes / (ms_filt * 1e-3) / 1e9 / peaks["hbm_gbs"], "windows_per_s": n_win / (ms_filt * 1e-3),
+                             "parity": "unpinned (BrainFlow absent): tests/test_filters.py vs the scipy restatement"},
             "k1_zscore_f32": {"kernel": "window_zscore_vec_kernel (z-score, fp32 in/out)", "bound": "hbm",
                               "achieved": n_win * T * C * 8 / (ms_z * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                               "unit": "GB/s", "frac": n_win * T * C * 8 / (ms_z * 1e-3) / 1e9 / peaks["hbm_gbs"]},

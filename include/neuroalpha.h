@@ -165,6 +165,18 @@ int na_head_bwd_f32(const float* dlogits, const float* h, const float* stats, co
 int na_csv_parse_f32(const void* text, const int64_t* offsets, float* out, int* status, int64_t n_files,
                      int64_t fields_per_file, int64_t max_file_bytes, na_stream_t stream);
 
+/* ---- collector-side filter chain ------------------------------------------------
+ * Replaces the per-channel BrainFlow calls of Neural_decoding_data_collector.py:109-127 on raw windows:
+ * x fp32 [B][T][C] -> y fp32 [B][T][C]; per (b, c) series: detrend(CONSTANT) if `detrend`, then for each of the
+ * nfilt filters a zero-phase application (forward DirectFormII cascade, reversal, the same cascade -- state carried
+ * over if carry_state, as BrainFlow re-uses the filter object -- reversal), then np.round(., round_decimals)
+ * (< 0: none) and -0 -> 0.  Arithmetic in float64.  coef = the sections of all filters back to back, 5 doubles each
+ * (b0 b1 b2 a1 a2, a0 = 1); nsec[f] = sections of filter f (<= 8 filters x <= 8 sections; each section count is
+ * checked by the caller); scratch = T * roundup(B*C, 128) doubles.  Parity unpinned: BrainFlow is not available in this image.
+ */
+int na_iir_chain(const float* x, float* y, double* scratch, const double* coef, const int* nsec, int64_t nfilt,
+                 int64_t B, int64_t T, int64_t C, int detrend, int round_decimals, int carry_state, na_stream_t stream);
+
 /* ---- tensor-core tier: whole decoder forward, bf16 operands / fp32 accumulate ----------------
  * One persistent warp-specialised tcgen05 / TMEM / TMA kernel: K2 (input-gate contraction,
  * fused as extra K-steps of the per-step MMA), K3 (2-layer recurrence, wavefronted), K4 (online
