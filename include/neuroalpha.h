@@ -202,6 +202,13 @@ int na_decoder_infer_bf16(const void* x_bf16_tmp, const void* packed,
                           float* logits, float* probs,
                           int64_t T, int64_t B, int64_t Bp, int64_t NC, na_stream_t stream);
 
+/* The same forward straight from the caller's batch-first fp32 windows x [B][T][8] (`forward(x)`): the
+ * fp32 -> fp16 time-major pack is fused into the kernel (no intermediate copy of the input). */
+int na_decoder_infer_bf16_x32(const float* x, const void* packed,
+                              const float* attn_w, const float* attn_b, const float* ln_w, const float* ln_b,
+                              const float* fc0_w, const float* fc0_b, const float* fc3_w, const float* fc3_b,
+                              float* logits, float* probs, int64_t T, int64_t B, int64_t NC, na_stream_t stream);
+
 /* ---- tensor-core tier, wide hidden sizes (H = 96, 144, 192; BASELINE configs[4]: H = 192, T = 2500) --------
  * Same contract as na_decoder_infer_bf16 (lstm_eeg_model.py:32-39 + :97, eval mode; input_size 8, 2 layers),
  * for EEG_LSTM(hidden_size = H).  [W_ih | b | W_hh] no longer fits in shared memory, so the kernel keeps

@@ -401,7 +401,8 @@ void set_infer_hs(int hs) { g_infer_hs = (hs >= 1 && hs <= 3) ? hs : 3; }
 int launch_pack_v2(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*,
                    void*, cudaStream_t);
 int launch_infer_v2(const void*, const unsigned char*, const float*, const float*, const float*, const float*, const float*,
-                    const float*, const float*, const float*, float*, float*, int, int64_t, int64_t, int, int, cudaStream_t);
+                    const float*, const float*, const float*, float*, float*, int, int64_t, int64_t, int, int, cudaStream_t,
+                    const float*);
 constexpr int64_t kPackedV1Bytes = (int64_t)(kK0Chunks + kK1Chunks) * kBChunk;
 
 }  // namespace tc
@@ -450,7 +451,7 @@ extern "C" int na_decoder_infer_bf16(const void* x_bf16_tmp, const void* packed,
     if (hs == 3)
         return tc::launch_infer_v2(x_bf16_tmp, reinterpret_cast<const unsigned char*>(packed) + tc::kPackedV1Bytes, attn_w, attn_b,
                                    ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, (int)T, B, Bp, (int)NC, sms,
-                                   as_stream(stream));
+                                   as_stream(stream), nullptr);
     const size_t smem = sizeof(tc::Smem) + 1024;
     cudaError_t e = hs == 2 ? cudaFuncSetAttribute(tc::decoder_infer_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                             : cudaFuncSetAttribute(tc::decoder_infer_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -468,4 +469,28 @@ extern "C" int na_decoder_infer_bf16(const void* x_bf16_tmp, const void* packed,
             ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, (int)T, B, Bp, (int)NC, nquarters);
     count_launch();
     return check_launch("na_decoder_infer_bf16");
+}
+
+// The same forward straight from the caller's batch-first fp32 windows x [B][T][8] (lstm_eeg_model.py:32: `forward(x)`):
+// the fp32 -> fp16 time-major pack of na_window_zscore is fused into the kernel's producer warp.
+extern "C" int na_decoder_infer_bf16_x32(const float* x, const void* packed, const float* attn_w, const float* attn_b,
+                                         const float* ln_w, const float* ln_b, const float* fc0_w, const float* fc0_b,
+                                         const float* fc3_w, const float* fc3_b, float* logits, float* probs, int64_t T,
+                                         int64_t B, int64_t NC, na_stream_t stream) {
+    using namespace na;
+    NA_REQUIRE(T >= 1 && T < (1 << 20) && B >= 1, NA_EINVAL, "na_decoder_infer_bf16_x32: bad shape T=%lld B=%lld", (long long)T, (long long)B);
+    NA_REQUIRE(NC >= 1 && NC <= NA_MAX_CLASSES, NA_EUNSUPPORTED, "na_decoder_infer_bf16_x32: num_classes=%lld", (long long)NC);
+    NA_REQUIRE_PTR(x); NA_REQUIRE_PTR(packed); NA_REQUIRE_PTR(logits);
+    NA_OPTIONAL_PTR(probs);
+    NA_REQUIRE(attn_w && attn_b && ln_w && ln_b && fc0_w && fc0_b && fc3_w && fc3_b, NA_EINVAL,
+               "na_decoder_infer_bf16_x32: null parameter pointer");
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return tc::launch_infer_v2(nullptr, reinterpret_cast<const unsigned char*>(packed) + tc::kPackedV1Bytes, attn_w, attn_b, ln_w, ln_b,
+                               fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, (int)T, B, 0, (int)NC, sms, as_stream(stream), x);
 }

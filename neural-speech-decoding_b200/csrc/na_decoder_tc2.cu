@@ -64,6 +64,7 @@ struct Smem2 {
     alignas(128) unsigned char onez[2 * kAChunk];                  // [ones | zeros]
     HeadSmem2 head;
     float zx[kRows][kH + 1];                                       // pooled vector exchange, once per tile
+    alignas(16) float xf32[kV2XStages][kRows][8];                  // fused input: fp32 rows staged by cp.async
     alignas(8) uint64_t x_full[kV2XStages], x_empty[kV2XStages];
     uint64_t d0_full, d1_full, h0_ready[2], h1_ready;
     uint32_t tmem_base;
@@ -310,7 +311,8 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
                         const float* __restrict__ fc0_w, const float* __restrict__ fc0_b,
                         const float* __restrict__ fc3_w, const float* __restrict__ fc3_b,
                         float* __restrict__ logits, float* __restrict__ probs,
-                        int T, int64_t B, int64_t Bp, int NC, int nquarters, int allow_rep) {
+                        int T, int64_t B, int64_t Bp, int NC, int nquarters, int allow_rep,
+                        const float* __restrict__ x32) {       // != NULL: the caller's [B][T][8] fp32 windows, read directly (x unused)
     constexpr int kMmaWarp = 12, kTmaWarp = 13;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem2& S = *reinterpret_cast<Smem2*>(smem_raw);
@@ -391,8 +393,58 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
         const int64_t b0 = (int64_t)q0 * 32;
 
         if (warp == kTmaWarp) {
-            // ================= TMA producer ==========================================================
-            if (lane == 0) {
+            // ================= producer of x_t ========================================================
+            if (x32 != nullptr) {
+                // Fused K1: the warp reads the caller's batch-first fp32 windows itself (32 B per window and step,
+                // sector-sized; the neighbouring step is served from L2), converts to fp16 and writes the A chunk --
+                // no time-major fp16 copy of the input exists.  Loads of step t+1 are in flight while step t is stored.
+                // cp.async (LDGSTS) stages the fp32 rows kPre steps ahead in shared memory (no registers held across the
+                // DRAM latency), so even a latency-bound short tile (~1 us per step) never waits for its input.
+                const int nrows = nq * 32;
+                constexpr int kPre = 3;
+                auto issue = [&](int t) {                          // fp32 rows of step t -> S.xf32[t % 4]
+                    if (t < T) {
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) {
+                            const int row = rr * 32 + lane;
+                            const int64_t b = b0 + row;
+                            if (row < nrows && b < B) {
+                                const float* src = x32 + (b * T + t) * 8;
+                                const uint32_t dst = smem_u32(&S.xf32[t % kV2XStages][row][0]);
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 4) : "memory");
+                            }
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");      // one (possibly empty) group per step
+                };
+#pragma unroll
+                for (int t = 0; t < kPre; ++t) issue(t);
+                for (int t = 0; t < T; ++t) {
+                    const int n = n0 + t, s = n % kV2XStages, u = n / kV2XStages;
+                    asm volatile("cp.async.wait_group %0;" ::"n"(kPre - 1) : "memory");   // this step's rows have landed
+                    mbar_wait(&S.x_empty[s], (u & 1) ^ 1);
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int row = rr * 32 + lane;
+                        if (row < nrows) {
+                            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                            if (b0 + row < B) {
+                                v0 = *reinterpret_cast<const float4*>(&S.xf32[t % kV2XStages][row][0]);
+                                v1 = *reinterpret_cast<const float4*>(&S.xf32[t % kV2XStages][row][4]);
+                            }
+                            const uint32_t p0 = pack_val(v0.x, v0.y), p1 = pack_val(v0.z, v0.w);
+                            const uint32_t p2 = pack_val(v1.x, v1.y), p3 = pack_val(v1.z, v1.w);
+                            for (int rep = 0; rep < R; ++rep) st_shared_v4(S.x[s] + (rep * (kRows / R) + row) * 16, p0, p1, p2, p3);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.x_full[s]);
+                    issue(t + kPre);                               // re-uses the staging slot read two steps ago (t + 3 = t - 1 mod 4)
+                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            } else if (lane == 0) {
                 for (int t = 0; t < T; ++t) {
                     const int n = n0 + t, s = n % kV2XStages, u = n / kV2XStages;
                     mbar_wait(&S.x_empty[s], (u & 1) ^ 1);
@@ -495,7 +547,8 @@ int launch_pack_v2(const float* w_ih0, const float* w_hh0, const float* b_ih0, c
 
 int launch_infer_v2(const void* x, const unsigned char* packed_v2, const float* attn_w, const float* attn_b, const float* ln_w,
                     const float* ln_b, const float* fc0_w, const float* fc0_b, const float* fc3_w, const float* fc3_b,
-                    float* logits, float* probs, int T, int64_t B, int64_t Bp, int NC, int sms, cudaStream_t stream) {
+                    float* logits, float* probs, int T, int64_t B, int64_t Bp, int NC, int sms, cudaStream_t stream,
+                    const float* x32) {
     const size_t smem = infer_v2_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(decoder_infer_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
@@ -504,7 +557,7 @@ int launch_infer_v2(const void* x, const unsigned char* packed_v2, const float* 
     const int grid = nquarters < sms ? nquarters : sms;
     decoder_infer_v2_kernel<<<grid, kV2Threads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), packed_v2, attn_w, attn_b,
                                                                 ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, T, B, Bp, NC,
-                                                                nquarters, g_infer_rep);
+                                                                nquarters, g_infer_rep, x32);
     count_launch();
     return check_launch("na_decoder_infer_bf16 (v2)");
 }

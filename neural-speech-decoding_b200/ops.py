@@ -320,12 +320,41 @@ def _(x_tmp, packed, head, B, want_probs):
     return x_tmp.new_empty((B, NC), dtype=torch.float32), x_tmp.new_empty((B, NC) if want_probs else (0,), dtype=torch.float32)
 
 
+@torch.library.custom_op("neuroalpha::decoder_infer_bf16_x32", mutates_args=(), device_types="cuda")
+def decoder_infer_bf16_x32(x: Tensor, packed: Tensor, head: Sequence[Tensor], want_probs: bool) -> Tuple[Tensor, Tensor]:
+    """Whole decoder forward on tcgen05 straight from the batch-first fp32 windows x [B,T,8] (the fp32 -> fp16
+    time-major pack is fused into the kernel's producer warp)."""
+    _require_cuda(x, packed, *head)
+    B, T, C = x.shape
+    if x.dtype != torch.float32 or C != 8 or not x.is_contiguous():
+        raise RuntimeError("decoder_infer_bf16_x32: x must be contiguous fp32 [B, T, 8]")
+    head = [_f32c(t) for t in head]
+    NC = head[6].shape[0]
+    logits = torch.empty((B, NC), dtype=torch.float32, device=x.device)
+    probs = torch.empty((B, NC) if want_probs else (0,), dtype=torch.float32, device=x.device)
+    _lib.call("na_decoder_infer_bf16_x32", x.data_ptr(), packed.data_ptr(), *[t.data_ptr() for t in head],
+              logits.data_ptr(), _ptr(probs) if want_probs else None, T, B, NC, _stream())
+    return logits, probs
+
+
+@decoder_infer_bf16_x32.register_fake
+def _(x, packed, head, want_probs):
+    NC = head[6].shape[0]
+    return x.new_empty((x.shape[0], NC), dtype=torch.float32), x.new_empty((x.shape[0], NC) if want_probs else (0,), dtype=torch.float32)
+
+
+FUSED_INPUT = True          # decoder_infer_tc: read fp32 [B,T,8] directly (False: K1 pack + time-major kernel; A/B timing)
+
+
 def decoder_infer_tc(x: Tensor, packed: Tensor, head_params: Sequence[Tensor], want_probs: bool = False,
                      zscore: bool = False) -> Tuple[Tensor, Tensor]:
     """Eval forward on the tensor-core tier.  x [B,T,8] fp32 (or bf16) -> (logits fp32, probs or empty).
-    K1 packs the windows time-major in bf16 (one read of x, one half-size write)."""
+    fp32 contiguous input without the z-score stage goes straight into the kernel; otherwise K1 packs the windows
+    time-major in fp16 first (one read of x, one half-size write)."""
     _require_cuda(x)
     B, T, C = x.shape
+    if FUSED_INPUT and not zscore and x.dtype == torch.float32 and C == 8 and B > 0:
+        return decoder_infer_bf16_x32(x.contiguous(), packed, list(head_params), want_probs)
     xt = window_zscore(x, T, T, zscore, True, NA_F16, TC_TILE)
     return decoder_infer_bf16(xt, packed, list(head_params), B, want_probs)
 
