@@ -564,3 +564,17 @@ int launch_infer_v2(const void* x, const unsigned char* packed_v2, const float* 
 
 }  // namespace tc
 }  // namespace na
+
+// ---- training forward, generation 2 (shares this translation unit's helpers) ------------------------------------
+namespace na {
+namespace tc {
+__device__ __forceinline__ void st_global_v4f(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+// TCL32 (see na_train_tc.cu): fp32 tile-chunk layout [T][Bp/128][12][128][4]
+__device__ __forceinline__ int64_t tcl32_off(int t, int ntiles, int tile, int chunk, int row) {
+    return (((((int64_t)t * ntiles + tile) * 12 + chunk) * kRows) + row) * 4;
+}
+}  // namespace tc
+}  // namespace na
+#include "na_train_fwd2.cuh"

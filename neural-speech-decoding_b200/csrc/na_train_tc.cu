@@ -787,6 +787,12 @@ static int launch_bwd(const void* act_in, const void* h, const float* c, const f
 // ---- C ABI ---------------------------------------------------------------------------------------
 extern "C" int64_t na_train_bf16_partial_floats(void) { return (int64_t)148 * 2 * na::tc::kN * 112 + 148 * 52; }
 
+namespace na { namespace tc {
+bool train_fwd_v2_enabled();
+int launch_train_fwd_v2(const void*, const unsigned char*, const unsigned char*, uint64_t, uint32_t, float, void*, void*, float*, void*,
+                        float*, const float*, const float*, float*, float*, int64_t, int, int64_t, int, cudaStream_t);
+} }
+
 extern "C" int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packed, const unsigned char* mask,
                                        uint64_t seed, int64_t thresh16, float drop_scale, void* h0, void* h0d, float* c0, void* h1, float* h1f,
                                        float* c1, const float* attn_w, const float* attn_b, float* zpool, float* stats,
@@ -803,6 +809,10 @@ extern "C" int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packe
     NA_REQUIRE(thresh16 >= 0 && thresh16 <= 65536, NA_EINVAL, "na_lstm2_fwd_train_bf16: thresh16 outside [0,65536]");
     NA_REQUIRE((mask != nullptr || thresh16 < 65536) == (h0d != nullptr), NA_EINVAL,
                "na_lstm2_fwd_train_bf16: h0d must be given exactly when dropout is on (mask tensor or thresh16 < 65536)");
+    if (tc::train_fwd_v2_enabled() && zpool != nullptr && h1f == nullptr)      // generation 2 (na_train_fwd2.cuh): fused pooling only
+        return tc::launch_train_fwd_v2(x_bf16_tmp, reinterpret_cast<const unsigned char*>(packed) + na_decoder_packed_bf16_bytes() / 2, mask,
+                                       seed, (uint32_t)thresh16, drop_scale, h0, h0d, c0, h1, c1, attn_w, attn_b, zpool, stats, B, (int)T,
+                                       Bp, tc::tc_sms(), as_stream(stream));
     const size_t smem = sizeof(tc::FwdSmem) + 1024;
     cudaError_t e = cudaFuncSetAttribute(tc::lstm2_fwd_train_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "na_lstm2_fwd_train_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
