@@ -321,3 +321,27 @@ def test_wide_matches_exact_tier(dev, H, T, B):
     assert np.array_equal(got, again)                      # deterministic, workspace re-use is clean
     err = np.abs(got - exact).max(axis=1) / np.abs(exact).max()
     assert err.mean() < 2e-3 and np.quantile(err, 0.999) < BF16_TOL and err.max() < 0.1, (err.mean(), err.max())
+
+
+def test_fused_input_entries_are_bit_identical(dev, checkpoint):
+    """na_decoder_infer_bf16_x32 / na_decoder_infer_wide_bf16_x32 (fp32 [B,T,8] read directly, pack fused into the kernel)
+    against the time-major fp16 entry points: same bits, incl. ragged batches and row-replicated short tiles."""
+    from neural_speech_decoding_b200 import ops
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    gen = torch.Generator(device="cpu").manual_seed(11)
+    m = bf16_model(dev, checkpoint)
+    for B, T in ((1, 625), (77, 50), (148 * 32 * 5 - 3, 21)):
+        x = (torch.randn(B, T, 8, generator=gen) * 2.73).to(dev)
+        with torch.inference_mode():
+            xt = ops.window_zscore(x, T, T, False, True, ops.NA_F16, ops.TC_TILE)
+            a = ops.decoder_infer_bf16(xt, m._packed_tc(), m._head_params(), B, True)
+            b = ops.decoder_infer_bf16_x32(x, m._packed_tc(), m._head_params(), True)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), (B, T)
+    torch.manual_seed(5)
+    w = EEG_LSTM(hidden_size=96).to(dev).eval()
+    x = (torch.randn(200, 30, 8, generator=gen) * 2.73).to(dev)
+    with torch.inference_mode():
+        xt = ops.window_zscore(x, 30, 30, False, True, ops.NA_F16, ops.TC_TILE)
+        a = ops.decoder_infer_wide_bf16(xt, w._packed_tc_wide(), w._head_params()[2:], 200, 96, True)
+        b = ops.decoder_infer_wide_bf16_x32(x, w._packed_tc_wide(), w._head_params()[2:], 96, True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
