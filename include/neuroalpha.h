@@ -209,6 +209,22 @@ int na_decoder_infer_bf16_x32(const float* x, const void* packed,
                               const float* fc0_w, const float* fc0_b, const float* fc3_w, const float* fc3_b,
                               float* logits, float* probs, int64_t T, int64_t B, int64_t NC, na_stream_t stream);
 
+/* ---- exact tier on the tensor cores (fp32 accuracy, 1e-5 contract) ------------------------------------
+ * The same forward as na_decoder_infer_bf16_x32 at fp32 accuracy: every operand is split into fp16 hi + lo halves and
+ * each product is three tcgen05 MMAs (hi.hi + hi.lo + lo.hi, fp32 accumulation); activations by ex2.approx + rcp.approx
+ * (~2e-7), cell state / pooling / head in fp32.  Replaces the FFMA kernels for the flagship shape (C=8, H=48, L=2) in
+ * eval mode; x = the caller's batch-first fp32 windows [B][T][8].  `packed` = na_decoder_pack_x3 output
+ * (na_decoder_packed_x3_bytes() bytes).
+ */
+int64_t na_decoder_packed_x3_bytes(void);
+int na_decoder_pack_x3(const float* w_ih0, const float* w_hh0, const float* b_ih0, const float* b_hh0,
+                       const float* w_ih1, const float* w_hh1, const float* b_ih1, const float* b_hh1,
+                       void* packed, na_stream_t stream);
+int na_decoder_infer_x3(const float* x, const void* packed,
+                        const float* attn_w, const float* attn_b, const float* ln_w, const float* ln_b,
+                        const float* fc0_w, const float* fc0_b, const float* fc3_w, const float* fc3_b,
+                        float* logits, float* probs, int64_t T, int64_t B, int64_t NC, na_stream_t stream);
+
 /* ---- tensor-core tier, wide hidden sizes (H = 96, 144, 192; BASELINE configs[4]: H = 192, T = 2500) --------
  * Same contract as na_decoder_infer_bf16 (lstm_eeg_model.py:32-39 + :97, eval mode; input_size 8, 2 layers),
  * for EEG_LSTM(hidden_size = H).  [W_ih | b | W_hh] no longer fits in shared memory, so the kernel keeps

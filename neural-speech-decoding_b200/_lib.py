@@ -36,6 +36,9 @@ SIGNATURES = {
     "na_decoder_pack_bf16": (c_int, [P] * 9 + [P]),
     "na_decoder_infer_bf16": (c_int, [P] * 12 + [I64, I64, I64, I64, P]),
     "na_decoder_infer_bf16_x32": (c_int, [P] * 12 + [I64, I64, I64, P]),
+    "na_decoder_packed_x3_bytes": (c_int64, []),
+    "na_decoder_pack_x3": (c_int, [P] * 9 + [P]),
+    "na_decoder_infer_x3": (c_int, [P] * 12 + [I64, I64, I64, P]),
     "na_decoder_wide_packed_bytes": (c_int64, [I64]),
     "na_decoder_wide_state_bytes": (c_int64, [I64]),
     "na_decoder_pack_wide_bf16": (c_int, [P] * 11 + [I64, P]),

@@ -120,6 +120,16 @@ class EEG_LSTM(nn.Module):
             self._pack_cache["tc_wide"] = hit
         return hit[1]
 
+    def _packed_x3(self):
+        ps = self.lstm.layer(0) + self.lstm.layer(1)
+        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+        hit = self._pack_cache.get("x3")
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, ops.decoder_pack_x3(ps))
+            self._pack_cache["x3"] = hit
+        return hit[1]
+
     def _packed_tc(self):
         ps = self.lstm.layer(0) + self.lstm.layer(1)
         key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
@@ -142,6 +152,10 @@ class EEG_LSTM(nn.Module):
             if bf16 and self.tc_wide_supported():
                 return ops.decoder_infer_wide(x, self._packed_tc_wide(), self._head_params(), self.lstm.hidden_size,
                                               want_probs, self.zscore_input)
+            if (ops.EXACT_TC and not bf16 and self.tc_supported() and not self.zscore_input and x.dtype == torch.float32
+                    and x.shape[0] > 0):
+                # exact tier, flagship shape: fp32-accurate tensor-core kernel (fp16 hi/lo operand split)
+                return ops.decoder_infer_x3(x.contiguous(), self._packed_x3(), self._head_params(), want_probs)
             L = self.lstm.num_layers
             return ops.decoder_infer(x, [self.lstm.layer(l) for l in range(L)],
                                      [ops._f32c(t) for t in self._head_params()], want_probs, self.zscore_input,

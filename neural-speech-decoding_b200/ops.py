@@ -360,6 +360,49 @@ def decoder_infer_tc(x: Tensor, packed: Tensor, head_params: Sequence[Tensor], w
     return decoder_infer_bf16(xt, packed, list(head_params), B, want_probs)
 
 
+EXACT_TC = True             # exact tier, flagship shape, eval: fp16-split tcgen05 kernel (False: the FFMA kernels; A/B timing)
+
+
+@torch.library.custom_op("neuroalpha::decoder_pack_x3", mutates_args=(), device_types="cuda")
+def decoder_pack_x3(lstm_flat: Sequence[Tensor]) -> Tensor:
+    """The 8 nn.LSTM tensors (layer 0 then layer 1) -> fp16 hi / lo UMMA operands of the exact tensor-core kernel."""
+    _require_cuda(*lstm_flat)
+    ts = [_f32c(t) for t in lstm_flat]
+    if len(ts) != 8 or tuple(ts[0].shape) != (192, 8) or tuple(ts[4].shape) != (192, 48):
+        raise RuntimeError("decoder_pack_x3: implements input_size=8, hidden_size=48, num_layers=2")
+    packed = torch.empty((_lib.query("na_decoder_packed_x3_bytes"),), dtype=torch.uint8, device=ts[0].device)
+    _lib.call("na_decoder_pack_x3", *[t.data_ptr() for t in ts], packed.data_ptr(), _stream())
+    return packed
+
+
+@decoder_pack_x3.register_fake
+def _(lstm_flat):
+    return lstm_flat[0].new_empty((40 * 3072,), dtype=torch.uint8)
+
+
+@torch.library.custom_op("neuroalpha::decoder_infer_x3", mutates_args=(), device_types="cuda")
+def decoder_infer_x3(x: Tensor, packed: Tensor, head: Sequence[Tensor], want_probs: bool) -> Tuple[Tensor, Tensor]:
+    """Whole decoder forward at fp32 accuracy on tcgen05 (operands split into fp16 hi + lo, three MMAs per product),
+    straight from the batch-first fp32 windows x [B,T,8]."""
+    _require_cuda(x, packed, *head)
+    B, T, C = x.shape
+    if x.dtype != torch.float32 or C != 8 or not x.is_contiguous():
+        raise RuntimeError("decoder_infer_x3: x must be contiguous fp32 [B, T, 8]")
+    head = [_f32c(t) for t in head]
+    NC = head[6].shape[0]
+    logits = torch.empty((B, NC), dtype=torch.float32, device=x.device)
+    probs = torch.empty((B, NC) if want_probs else (0,), dtype=torch.float32, device=x.device)
+    _lib.call("na_decoder_infer_x3", x.data_ptr(), packed.data_ptr(), *[t.data_ptr() for t in head],
+              logits.data_ptr(), _ptr(probs) if want_probs else None, T, B, NC, _stream())
+    return logits, probs
+
+
+@decoder_infer_x3.register_fake
+def _(x, packed, head, want_probs):
+    NC = head[6].shape[0]
+    return x.new_empty((x.shape[0], NC), dtype=torch.float32), x.new_empty((x.shape[0], NC) if want_probs else (0,), dtype=torch.float32)
+
+
 WIDE_HIDDEN = (96, 144, 192)          # hidden sizes of the streamed-weight tensor-core kernel (na_decoder_wide.cu)
 
 
