@@ -270,6 +270,8 @@ def run_gpu_arm(args):
         packed_tc, head = model._packed_tc(), model._head_params()
         ms_tc_tm = time_steps(lambda: ops.decoder_infer_bf16(xt16, packed_tc, head, n_win, True), reps, 2, 1, dev) / reps
         ms_tc = time_steps(lambda: ops.decoder_infer_bf16_x32(x_flat, packed_tc, head, True), reps, 2, 1, dev) / reps
+        packed_x3 = model._packed_x3()
+        ms_x3 = time_steps(lambda: ops.decoder_infer_x3(x_flat, packed_x3, head, True), reps, 2, 1, dev) / reps
         ms_pack16 = time_steps(lambda: ops.window_zscore(x_flat, T, T, False, True, ops.NA_F16, ops.TC_TILE), reps, 2, 1, dev) / reps
         ms_z = time_steps(lambda: ops.window_zscore(x_flat, T, T, True, False, False), reps, 2, 1, dev) / reps
         del xt16
@@ -375,6 +377,14 @@ def run_gpu_arm(args):
             "e2e": {"value": fp["e2e_value"], "unit": "windows/s", "ms_per_step": fp["e2e_ms_per_step"]},
             "gpu_launches": fp["launches"], "clocks": fp["clocks"],
             "parity": "tests/test_gpu_parity.py: logits and gradients within 1e-5, argmax identical",
+            "kernel": "decoder_infer_x3_kernel (tcgen05, every operand split into fp16 hi + lo: 3 MMAs per product, fp32 accumulate; "
+                      "ex2+rcp activations): 1.2e-6 of max|logit| vs the reference on the repo's windows",
+            "roofline_x3": {"kernel": "decoder_infer_x3_kernel", "bound": "MUFU (10 per cell update: ex2.approx + rcp.approx per activation)",
+                            "achieved": n_win * T * 2 * H * 10 / (ms_x3 * 1e-3) / 1e9,
+                            "peak": 16 * 148 * ((fp["clocks"] or {}).get("sm_mhz") or 1965.0) * 1e-3, "unit": "G MUFU results/s",
+                            "frac": n_win * T * 2 * H * 10 / (ms_x3 * 1e-3) / 1e9 / (16 * 148 * ((fp["clocks"] or {}).get("sm_mhz") or 1965.0) * 1e-3),
+                            "ms_per_launch": ms_x3, "tensor_tflops_3x": 3 * FWD_FLOPS_PER_WINDOW * n_win / (ms_x3 * 1e-3) / 1e12},
+            "ffma_kernels": "the FFMA recurrence kernels (ops.EXACT_TC = False; training forward, other shapes): roofline below",
             "roofline": {"kernel": "lstm_fwd_h48_kernel<KIN=48> (layer-1 recurrence, exact fp32 FFMA)",
                          "bound": "cuda-core fp32 (FFMA issue)", "achieved": l1_tflops, "peak": ffma_peak,
                          "unit": "TFLOP/s", "frac": l1_tflops / ffma_peak,

@@ -115,6 +115,170 @@ __device__ __forceinline__ void split_pack8(const float* h, uint32_t (&hi)[4], u
     }
 }
 
+// Epilogue of one tile for one warp: both layers of (lane quarter q, unit group g).  R = row replication as in
+// decoder_infer_v2_kernel: the tile holds 128 / R distinct windows, copy rp = q / (4 / R) of source quarter qs = q % (4 / R)
+// takes granules [4 g + rp * (4 / R), + 4 / R) of the 12 four-unit granules and stores its h (hi and lo) to every copy.
+template <int R>
+__device__ __forceinline__ void x3_epilogue_tile(SmemX3& S, const int q, const int g, const int lane, const int nq, const int T,
+                                                 const int n0, uint32_t& k1, const uint32_t tmem_d0, const uint32_t tmem_d1,
+                                                 const int64_t b0, const int64_t B, const int NC,
+                                                 const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                 const float* __restrict__ fc0_w, const float* __restrict__ fc0_b,
+                                                 const float* __restrict__ fc3_w, const float* __restrict__ fc3_b,
+                                                 float* __restrict__ logits, float* __restrict__ probs) {
+    constexpr int kQ = 4 / R, kSlots = 4 / R, kU = 4 * kSlots;
+    const int qs = q % kQ, rp = q / kQ;
+    const int wrow = qs * 32 + lane;               // window row of the tile (first copy)
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int gr0 = 4 * g + rp * kSlots;           // first granule
+    if (qs >= nq) {                                // idle quarter: keep the barrier protocol only
+        for (int t = 0; t <= T; ++t) {
+            const int n = n0 + t;
+            if (t < T) {
+                mbar_wait(&S.d0_full, n & 1);
+                if (q == 0 && g == 0 && lane == 0) mbar_arrive(&S.x_empty[n % kX3XStages]);
+                mbar_arrive(&S.h0_ready[n & 1]);
+            }
+            if (t >= 1) { mbar_wait(&S.d1_full, k1 & 1); ++k1; mbar_arrive(&S.h1_ready); }
+        }
+        mbar_wait(&S.d1_full, k1 & 1); ++k1;
+        return;
+    }
+    float c0[kU], c1[kU], z[kU], hprev[kU];
+#pragma unroll
+    for (int j = 0; j < kU; ++j) { c0[j] = 0.f; c1[j] = 0.f; z[j] = 0.f; hprev[j] = 0.f; }
+    float mx = -INFINITY, l = 0.f;
+    auto pool = [&](float score) {                 // online softmax over time (lstm_eeg_model.py:35-37), fp32
+        if (score > mx) {
+            const float sc = expf(mx - score);
+            l *= sc;
+#pragma unroll
+            for (int j = 0; j < kU; ++j) z[j] *= sc;
+            mx = score;
+        }
+        const float e = expf(score - mx);
+        l += e;
+#pragma unroll
+        for (int j = 0; j < kU; ++j) z[j] = fmaf(e, hprev[j], z[j]);
+    };
+    // gates of this thread's granules -> cell update -> h (fp32, kept in hout) -> hi / lo fp16 into every row copy of `buf`
+    auto layer_phase = [&](const uint32_t tmem_d, float* c, unsigned char* buf, float* hout) {
+        if constexpr (R == 4) {
+            uint32_t v[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(tmem_d + lane_base + gr0 * 16)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            cell_granule_exact(v, c, hout);
+            const uint32_t hi0 = pack_val(hout[0], hout[1]), hi1 = pack_val(hout[2], hout[3]);
+            const uint32_t lo0 = pack_val(hout[0] - val_lo(hi0), hout[1] - val_hi(hi0));
+            const uint32_t lo1 = pack_val(hout[2] - val_lo(hi1), hout[3] - val_hi(hi1));
+            unsigned char* dst = buf + (gr0 >> 1) * kAChunk + wrow * 16 + (gr0 & 1) * 8;
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep) {
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(smem_u32(dst + rep * 32 * 16)), "r"(hi0), "r"(hi1) : "memory");
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(smem_u32(dst + 6 * kAChunk + rep * 32 * 16)), "r"(lo0), "r"(lo1) : "memory");
+            }
+        } else {
+#pragma unroll
+            for (int pr = 0; pr < kSlots / 2; ++pr) {       // pairs of granules = one 8-unit K chunk
+                uint32_t v[32], hi[4], lo[4];
+                tmem_ld32(tmem_d + lane_base + (gr0 + 2 * pr) * 16, v);
+                cell_granule_exact(v, c + pr * 8, hout + pr * 8);
+                cell_granule_exact(v + 16, c + pr * 8 + 4, hout + pr * 8 + 4);
+                split_pack8(hout + pr * 8, hi, lo);
+                unsigned char* dst = buf + ((gr0 >> 1) + pr) * kAChunk + wrow * 16;
+#pragma unroll
+                for (int rep = 0; rep < R; ++rep) {
+                    st_shared_v4(dst + rep * (kRows / R) * 16, hi[0], hi[1], hi[2], hi[3]);
+                    st_shared_v4(dst + 6 * kAChunk + rep * (kRows / R) * 16, lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        }
+    };
+    for (int t = 0; t <= T; ++t) {
+        const int n = n0 + t;
+        if (t < T) {                               // ---- layer 0, step t
+            mbar_wait(&S.d0_full, n & 1);
+            if (q == 0 && g == 0 && lane == 0) mbar_arrive(&S.x_empty[n % kX3XStages]);
+            tc_fence_after();
+            float hdummy[kU];
+            layer_phase(tmem_d0, c0, S.h0[n & 1], hdummy);
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive(&S.h0_ready[n & 1]);
+        }
+        if (t >= 1) {                              // ---- layer 1, step t-1 (+ pooling of step t-2)
+            mbar_wait(&S.d1_full, k1 & 1); ++k1;
+            tc_fence_after();
+            uint32_t sc2[2];
+            x3_tmem_ld2(tmem_d1 + lane_base + kN, sc2);
+            if (t >= 2) pool(__uint_as_float(sc2[0]));     // pooling of step t-2 (h_{t-2} in hprev) first: frees hprev
+            layer_phase(tmem_d1, c1, S.h1, hprev);
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive(&S.h1_ready);
+        }
+    }
+    {                                              // flush: score of the last step
+        mbar_wait(&S.d1_full, k1 & 1); ++k1;
+        tc_fence_after();
+        uint32_t sc2[2];
+        x3_tmem_ld2(tmem_d1 + lane_base + kN, sc2);
+        tc_fence_before();
+        pool(__uint_as_float(sc2[0]));
+    }
+    // ---- head: LN -> fc0 -> RReLU(eval) -> fc3 -> softmax (fp32; parameters from global memory) ------
+    float* zx = reinterpret_cast<float*>(S.h0[0]);             // [128][49] floats <= the two h0 buffers
+#pragma unroll
+    for (int j = 0; j < kU; ++j) zx[wrow * (kH + 1) + gr0 * 4 + j] = z[j];
+    named_bar_sync(1 + qs, 96 * R);                // the 3 R warps that share source quarter qs
+    if (g == 0 && rp == 0) {
+        const int64_t b = b0 + wrow;
+        float zf[kH];
+        const float inv_l = 1.0f / l;
+        float mean = 0.f;
+#pragma unroll
+        for (int j = 0; j < kH; ++j) { zf[j] = zx[wrow * (kH + 1) + j] * inv_l; mean += zf[j]; }
+        mean *= (1.0f / kH);
+        float var = 0.f;
+#pragma unroll
+        for (int j = 0; j < kH; ++j) { const float d = zf[j] - mean; var = fmaf(d, d, var); }
+        const float rstd = 1.0f / sqrtf(var * (1.0f / kH) + kLnEps);
+#pragma unroll
+        for (int j = 0; j < kH; ++j) zf[j] = fmaf((zf[j] - mean) * rstd, __ldg(ln_w + j), __ldg(ln_b + j));
+        float lg[NA_MAX_CLASSES];
+#pragma unroll
+        for (int k = 0; k < NA_MAX_CLASSES; ++k) lg[k] = (k < NC) ? __ldg(fc3_b + k) : -INFINITY;
+        for (int o = 0; o < kX3Fc; ++o) {
+            float a = __ldg(fc0_b + o);
+#pragma unroll
+            for (int j = 0; j < kH; ++j) a = fmaf(__ldg(fc0_w + o * kH + j), zf[j], a);
+            a = a >= 0.f ? a : a * kRReluEvalSlope;
+#pragma unroll
+            for (int k = 0; k < NA_MAX_CLASSES; ++k)
+                if (k < NC) lg[k] = fmaf(__ldg(fc3_w + k * kX3Fc + o), a, lg[k]);
+        }
+        if (b < B) {
+            float mxl = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < NA_MAX_CLASSES; ++k) mxl = fmaxf(mxl, lg[k]);
+            float den = 0.f, pe[NA_MAX_CLASSES];
+#pragma unroll
+            for (int k = 0; k < NA_MAX_CLASSES; ++k) { pe[k] = (k < NC) ? expf(lg[k] - mxl) : 0.f; den += pe[k]; }
+#pragma unroll
+            for (int k = 0; k < NA_MAX_CLASSES; ++k)
+                if (k < NC) {
+                    logits[b * NC + k] = lg[k];
+                    if (probs) probs[b * NC + k] = pe[k] / den;
+                }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kX3Threads, 1)
 decoder_infer_x3_kernel(const float* __restrict__ x32,              // [B][T][8] fp32, batch-first
                         const unsigned char* __restrict__ packed,   // pack_decoder_x3_kernel image
@@ -189,8 +353,9 @@ decoder_infer_x3_kernel(const float* __restrict__ x32,              // [B][T][8]
     const int q_end = (int)(((int64_t)(blockIdx.x + 1) * nquarters) / gridDim.x);
     int n0 = 0;
     uint32_t k1 = 0;
-    for (int q0 = q_begin; q0 < q_end; q0 += 4, n0 += T) {
-        const int nq = min(4, q_end - q0);
+    for (int q0 = q_begin; q0 < q_end; n0 += T) {
+        const int nq = min(4, q_end - q0);                 // active source quarters of this tile
+        const int R = nq == 1 ? 4 : (nq == 2 ? 2 : 1);     // short tiles are row-replicated (see x3_epilogue_tile)
         const int64_t b0 = (int64_t)q0 * 32;
 
         if (warp == kTmaWarp) {
@@ -225,8 +390,11 @@ decoder_infer_x3_kernel(const float* __restrict__ x32,              // [B][T][8]
                                             cur[rr][1].x, cur[rr][1].y, cur[rr][1].z, cur[rr][1].w};
                         uint32_t hi[4], lo[4];
                         split_pack8(f, hi, lo);
-                        st_shared_v4(S.x[s] + row * 16, hi[0], hi[1], hi[2], hi[3]);
-                        st_shared_v4(S.x[s] + 2 * kAChunk + row * 16, lo[0], lo[1], lo[2], lo[3]);
+                        for (int rep = 0; rep < R; ++rep) {
+                            const int rr2 = rep * (kRows / R) + row;
+                            st_shared_v4(S.x[s] + rr2 * 16, hi[0], hi[1], hi[2], hi[3]);
+                            st_shared_v4(S.x[s] + 2 * kAChunk + rr2 * 16, lo[0], lo[1], lo[2], lo[3]);
+                        }
                     }
                 }
                 fence_proxy_async_smem();
@@ -320,136 +488,14 @@ decoder_infer_x3_kernel(const float* __restrict__ x32,              // [B][T][8]
                 if (leader) umma_commit(&S.d1_full);
             }
         } else {
-            // ================= epilogue: both layers of (quarter q, unit group g: K chunks 2g, 2g+1) ==================
+            // ================= epilogue: both layers of (quarter q, unit group g) ================================
             const int q = warp & 3, g = warp >> 2;
-            const int row = q * 32 + lane;
-            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-            if (q >= nq) {                                 // idle quarter: keep the barrier protocol only
-                for (int t = 0; t <= T; ++t) {
-                    const int n = n0 + t;
-                    if (t < T) { mbar_wait(&S.d0_full, n & 1); mbar_arrive(&S.h0_ready[n & 1]); }
-                    if (t >= 1) { mbar_wait(&S.d1_full, k1 & 1); ++k1; mbar_arrive(&S.h1_ready); }
-                }
-                mbar_wait(&S.d1_full, k1 & 1); ++k1;
-            } else {
-                float c0[16], c1[16], z[16], hprev[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { c0[j] = 0.f; c1[j] = 0.f; z[j] = 0.f; hprev[j] = 0.f; }
-                float mx = -INFINITY, l = 0.f;
-                auto pool = [&](float score) {             // online softmax over time (lstm_eeg_model.py:35-37), fp32
-                    if (score > mx) {
-                        const float sc = expf(mx - score);
-                        l *= sc;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) z[j] *= sc;
-                        mx = score;
-                    }
-                    const float e = expf(score - mx);
-                    l += e;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) z[j] = fmaf(e, hprev[j], z[j]);
-                };
-                for (int t = 0; t <= T; ++t) {
-                    const int n = n0 + t;
-                    if (t < T) {                           // ---- layer 0, step t
-                        mbar_wait(&S.d0_full, n & 1);
-                        if (q == 0 && g == 0 && lane == 0) mbar_arrive(&S.x_empty[n % kX3XStages]);
-                        tc_fence_after();
-#pragma unroll
-                        for (int pr = 0; pr < 2; ++pr) {
-                            const int blk = 2 * g + pr;
-                            uint32_t v[32], hi[4], lo[4];
-                            float h[8];
-                            tmem_ld32(tmem_d0 + lane_base + blk * 32, v);
-                            cell_granule_exact(v, c0 + pr * 8, h);
-                            cell_granule_exact(v + 16, c0 + pr * 8 + 4, h + 4);
-                            split_pack8(h, hi, lo);
-                            st_shared_v4(S.h0[n & 1] + blk * kAChunk + row * 16, hi[0], hi[1], hi[2], hi[3]);
-                            st_shared_v4(S.h0[n & 1] + (6 + blk) * kAChunk + row * 16, lo[0], lo[1], lo[2], lo[3]);
-                        }
-                        tc_fence_before();
-                        fence_proxy_async_smem();
-                        mbar_arrive(&S.h0_ready[n & 1]);
-                    }
-                    if (t >= 1) {                          // ---- layer 1, step t-1 (+ pooling of step t-2)
-                        mbar_wait(&S.d1_full, k1 & 1); ++k1;
-                        tc_fence_after();
-                        uint32_t sc2[2];
-                        x3_tmem_ld2(tmem_d1 + lane_base + kN, sc2);
-                        if (t >= 2) pool(__uint_as_float(sc2[0]));             // pooling of step t-2 (h_{t-2} in hprev) first: frees hprev
-#pragma unroll
-                        for (int pr = 0; pr < 2; ++pr) {
-                            const int blk = 2 * g + pr;
-                            uint32_t v[32], hi[4], lo[4];
-                            tmem_ld32(tmem_d1 + lane_base + blk * 32, v);
-                            cell_granule_exact(v, c1 + pr * 8, hprev + pr * 8);
-                            cell_granule_exact(v + 16, c1 + pr * 8 + 4, hprev + pr * 8 + 4);
-                            split_pack8(hprev + pr * 8, hi, lo);
-                            st_shared_v4(S.h1 + blk * kAChunk + row * 16, hi[0], hi[1], hi[2], hi[3]);
-                            st_shared_v4(S.h1 + (6 + blk) * kAChunk + row * 16, lo[0], lo[1], lo[2], lo[3]);
-                        }
-                        tc_fence_before();
-                        fence_proxy_async_smem();
-                        mbar_arrive(&S.h1_ready);
-                    }
-                }
-                {                                          // flush: score of the last step
-                    mbar_wait(&S.d1_full, k1 & 1); ++k1;
-                    tc_fence_after();
-                    uint32_t sc2[2];
-                    x3_tmem_ld2(tmem_d1 + lane_base + kN, sc2);
-                    tc_fence_before();
-                    pool(__uint_as_float(sc2[0]));
-                }
-                // ---- head: LN -> fc0 -> RReLU(eval) -> fc3 -> softmax (fp32; parameters from global memory) ------
-                float* zx = reinterpret_cast<float*>(S.h0[0]);             // [128][49] floats <= the two h0 buffers
-#pragma unroll
-                for (int j = 0; j < 16; ++j) zx[row * (kH + 1) + g * 16 + j] = z[j];
-                named_bar_sync(1 + q, 96);
-                if (g == 0) {
-                    const int64_t b = b0 + row;
-                    float zf[kH];
-                    const float inv_l = 1.0f / l;
-                    float mean = 0.f;
-#pragma unroll
-                    for (int j = 0; j < kH; ++j) { zf[j] = zx[row * (kH + 1) + j] * inv_l; mean += zf[j]; }
-                    mean *= (1.0f / kH);
-                    float var = 0.f;
-#pragma unroll
-                    for (int j = 0; j < kH; ++j) { const float d = zf[j] - mean; var = fmaf(d, d, var); }
-                    const float rstd = 1.0f / sqrtf(var * (1.0f / kH) + kLnEps);
-#pragma unroll
-                    for (int j = 0; j < kH; ++j) zf[j] = fmaf((zf[j] - mean) * rstd, __ldg(ln_w + j), __ldg(ln_b + j));
-                    float lg[NA_MAX_CLASSES];
-#pragma unroll
-                    for (int k = 0; k < NA_MAX_CLASSES; ++k) lg[k] = (k < NC) ? __ldg(fc3_b + k) : -INFINITY;
-                    for (int o = 0; o < kX3Fc; ++o) {
-                        float a = __ldg(fc0_b + o);
-#pragma unroll
-                        for (int j = 0; j < kH; ++j) a = fmaf(__ldg(fc0_w + o * kH + j), zf[j], a);
-                        a = a >= 0.f ? a : a * kRReluEvalSlope;
-#pragma unroll
-                        for (int k = 0; k < NA_MAX_CLASSES; ++k)
-                            if (k < NC) lg[k] = fmaf(__ldg(fc3_w + k * kX3Fc + o), a, lg[k]);
-                    }
-                    if (b < B) {
-                        float mxl = -INFINITY;
-#pragma unroll
-                        for (int k = 0; k < NA_MAX_CLASSES; ++k) mxl = fmaxf(mxl, lg[k]);
-                        float den = 0.f, pe[NA_MAX_CLASSES];
-#pragma unroll
-                        for (int k = 0; k < NA_MAX_CLASSES; ++k) { pe[k] = (k < NC) ? expf(lg[k] - mxl) : 0.f; den += pe[k]; }
-#pragma unroll
-                        for (int k = 0; k < NA_MAX_CLASSES; ++k)
-                            if (k < NC) {
-                                logits[b * NC + k] = lg[k];
-                                if (probs) probs[b * NC + k] = pe[k] / den;
-                            }
-                    }
-                }
-            }
+            if (R == 1) x3_epilogue_tile<1>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs);
+            else if (R == 2) x3_epilogue_tile<2>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs);
+            else x3_epilogue_tile<4>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs);
         }
         __syncthreads();       // tile done: every MMA has completed; the z exchange in h0 has been consumed
+        q0 += nq;
     }
 
     tc_fence_before();
@@ -502,8 +548,7 @@ extern "C" int na_decoder_infer_x3(const float* x, const void* packed, const flo
     cudaError_t e = cudaFuncSetAttribute(tc::decoder_infer_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_x3: shared memory opt-in failed (%s)", cudaGetErrorString(e));
     const int nquarters = (int)((B + 31) / 32);
-    const int ntiles = (nquarters + 3) / 4;
-    const int grid = ntiles < sms ? ntiles : sms;
+    const int grid = nquarters < sms ? nquarters : sms;    // < 4 quarters per CTA run as row-replicated tiles
     tc::decoder_infer_x3_kernel<<<grid, tc::kX3Threads, smem, as_stream(stream)>>>(
         x, reinterpret_cast<const unsigned char*>(packed), attn_w, attn_b, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs,
         (int)T, B, (int)NC, nquarters);

@@ -404,3 +404,33 @@ def test_pack16_time_major_matches_row_major(dev, windows):
             assert tm.shape == (625, 128, 8) and tm.dtype == rm.dtype
             assert torch.equal(tm[:, :77].permute(1, 0, 2), rm)
             assert tm[:, 77:].float().abs().sum().item() == 0
+
+
+def test_exact_tensor_core_kernel_vs_ffma_kernels(dev, checkpoint):
+    """The fp16-split tcgen05 kernel of the exact tier (na_decoder_x3.cu) against the FFMA kernels on every tile layout
+    (full tiles, 3-quarter remainder, R = 2 / R = 4 row-replicated remainders, several tiles per CTA, ragged last quarter),
+    T = 1..3, and 5 classes: within the 1e-5 contract of each other; both are pinned to the reference elsewhere."""
+    from neural_speech_decoding_b200 import ops
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    gen = torch.Generator(device="cpu").manual_seed(21)
+    m = EEG_LSTM()
+    m.load_state_dict(checkpoint, strict=True)
+    m = m.to(dev).eval()
+    m5 = EEG_LSTM(num_classes=5).to(dev).eval()
+    cases = [(m, 1, 1), (m, 3, 2), (m, 130, 3), (m5, 77, 40)]
+    cases += [(m, sms * 32 * k - 5, 30) for k in (1, 2, 3, 5, 6)]
+    try:
+        for model, B, T in cases:
+            x = (torch.randn(B, T, 8, generator=gen) * 2.73).to(dev)
+            with torch.inference_mode():
+                ops.EXACT_TC = True
+                a, pa = model.decode(x)
+                ops.EXACT_TC = False
+                b, pb = model.decode(x)
+            a, b = a.cpu().numpy(), b.cpu().numpy()
+            assert np.isfinite(a).all()
+            assert np.abs(a - b).max() / np.abs(b).max() < 1e-5, (B, T, np.abs(a - b).max() / np.abs(b).max())
+            np.testing.assert_allclose(pa.cpu().numpy(), pb.cpu().numpy(), atol=1e-5)
+    finally:
+        ops.EXACT_TC = True
