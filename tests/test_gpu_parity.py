@@ -431,6 +431,6 @@ def test_exact_tensor_core_kernel_vs_ffma_kernels(dev, checkpoint):
             a, b = a.cpu().numpy(), b.cpu().numpy()
             assert np.isfinite(a).all()
             assert np.abs(a - b).max() / np.abs(b).max() < 1e-5, (B, T, np.abs(a - b).max() / np.abs(b).max())
-            np.testing.assert_allclose(pa.cpu().numpy(), pb.cpu().numpy(), atol=1e-5)
+            np.testing.assert_allclose(pa.cpu().numpy(), pb.cpu().numpy(), atol=1e-4)   # softmax of logits that agree to 1e-5 of max|logit|
     finally:
         ops.EXACT_TC = True
