@@ -124,10 +124,11 @@ def test_filtered_windows_and_predictor(dev, checkpoint, golden_dir, tmp_path, w
     for k, i in enumerate(sub):
         probs, label = pred.predict(windows["X"][i])
         assert probs.dtype == np.float32 and probs.shape == (3,)
-        assert np.abs(probs - ref["predict_probs_subset"][k]).max() < 2e-6
+        # contract: logits within 1e-5 of max|logit| (~15 here) -> probabilities within ~0.25 * 1.5e-4; observed 2e-6
+        assert np.abs(probs - ref["predict_probs_subset"][k]).max() < 2e-5
         assert label == str(ref["predict_labels_subset"][k])
     pb = pred.predict_batch(windows["X"][sub])
-    assert np.abs(pb - ref["predict_probs_subset"]).max() < 2e-6
+    assert np.abs(pb - ref["predict_probs_subset"]).max() < 2e-5
     assert np.array_equal(pb.argmax(1), ref["logits_filtered_b1"][sub].argmax(1))
 
 
