@@ -378,11 +378,11 @@ def run_gpu_arm(args):
             "gpu_launches": fp["launches"], "clocks": fp["clocks"],
             "parity": "tests/test_gpu_parity.py: logits and gradients within 1e-5, argmax identical",
             "kernel": "decoder_infer_x3_kernel (tcgen05, every operand split into fp16 hi + lo: 3 MMAs per product, fp32 accumulate; "
-                      "ex2+rcp activations): 1.2e-6 of max|logit| vs the reference on the repo's windows",
-            "roofline_x3": {"kernel": "decoder_infer_x3_kernel", "bound": "MUFU (10 per cell update: ex2.approx + rcp.approx per activation)",
-                            "achieved": n_win * T * 2 * H * 10 / (ms_x3 * 1e-3) / 1e9,
+                      "ex2 / rcp activations): 1.25e-6 of max|logit| vs the reference on the repo's windows",
+            "roofline_x3": {"kernel": "decoder_infer_x3_kernel", "bound": "MUFU (7 per cell update: 5 ex2.approx + 2 rcp.approx, reciprocals combined)",
+                            "achieved": n_win * T * 2 * H * 7 / (ms_x3 * 1e-3) / 1e9,
                             "peak": 16 * 148 * ((fp["clocks"] or {}).get("sm_mhz") or 1965.0) * 1e-3, "unit": "G MUFU results/s",
-                            "frac": n_win * T * 2 * H * 10 / (ms_x3 * 1e-3) / 1e9 / (16 * 148 * ((fp["clocks"] or {}).get("sm_mhz") or 1965.0) * 1e-3),
+                            "frac": n_win * T * 2 * H * 7 / (ms_x3 * 1e-3) / 1e9 / (16 * 148 * ((fp["clocks"] or {}).get("sm_mhz") or 1965.0) * 1e-3),
                             "ms_per_launch": ms_x3, "tensor_tflops_3x": 3 * FWD_FLOPS_PER_WINDOW * n_win / (ms_x3 * 1e-3) / 1e12},
             "ffma_kernels": "the FFMA recurrence kernels (ops.EXACT_TC = False; training forward, other shapes): roofline below",
             "roofline": {"kernel": "lstm_fwd_h48_kernel<KIN=48> (layer-1 recurrence, exact fp32 FFMA)",
