@@ -30,6 +30,10 @@ constexpr int kX3B0Chunks = 15, kX3B1Chunks = 25;
 constexpr int kX3N1 = 208;
 constexpr int kX3B1Chunk = kX3N1 * 16;
 constexpr int kX3Fc = NA_FC_HIDDEN;
+// Input range: raw EEG can carry DC offsets of 1e5 uV, beyond fp16's 65,504.  The producer stores x / 16 and the packed
+// W_ih of layer 0 is multiplied by 16 (both exact powers of two): samples up to 1e6 stay finite and values as small as
+// 1e-3 keep an absolute error below 5e-7 (fp16 subnormal spacing x 16) after the hi + lo split.
+constexpr float kX3XScale = 0.0625f, kX3XScaleInv = 16.0f;
 constexpr uint32_t kX3IdescL1 = make_idesc(kX3N1, kFmtVal, kFmtVal);
 constexpr uint32_t kX3IdescFlush = make_idesc(16, kFmtVal, kFmtVal);
 
@@ -67,10 +71,10 @@ __global__ void pack_decoder_x3_kernel(const float* __restrict__ w_ih0, const fl
         float v = 0.f;
         bool want_lo = false, is_bias = false;
         if (!l1) {
-            if (ch == 0) v = w_ih0[col * 8 + kk];
+            if (ch == 0) v = kX3XScaleInv * w_ih0[col * 8 + kk];
             else if (ch == 1) { is_bias = true; v = b_ih0[col] + b_hh0[col]; }
             else if (ch <= 7) v = w_hh0[col * kH + (ch - 2) * 8 + kk];
-            else if (ch == 8) { want_lo = true; v = w_ih0[col * 8 + kk]; }
+            else if (ch == 8) { want_lo = true; v = kX3XScaleInv * w_ih0[col * 8 + kk]; }
             else { want_lo = true; v = w_hh0[col * kH + (ch - 9) * 8 + kk]; }
         } else {
             if (ch <= 5) v = w_ih1[col * kH + ch * 8 + kk];
@@ -102,19 +106,20 @@ __device__ __forceinline__ void x3_tmem_ld2(uint32_t taddr, uint32_t (&v)[2]) {
 // already saturated in fp32 (|x| <= 28 for the sigmoids, <= 14 for the tanh arguments) so the products stay below 2^127.
 __device__ __forceinline__ void cell_granule_exact(const uint32_t* v, float* c, float* h) {
     constexpr float kL2e = 1.4426950408889634f;
+    auto clampf = [](float x, float lim) { return x < -lim ? -lim : (x > lim ? lim : x); };     // NaN stays NaN (fminf would drop it)
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        const float xi = fminf(fmaxf(__uint_as_float(v[u]), -28.f), 28.f);
-        const float xf = fminf(fmaxf(__uint_as_float(v[4 + u]), -28.f), 28.f);
-        const float xg = fminf(fmaxf(__uint_as_float(v[8 + u]), -14.f), 14.f);
-        const float xo = fminf(fmaxf(__uint_as_float(v[12 + u]), -28.f), 28.f);
+        const float xi = clampf(__uint_as_float(v[u]), 28.f);
+        const float xf = clampf(__uint_as_float(v[4 + u]), 28.f);
+        const float xg = clampf(__uint_as_float(v[8 + u]), 14.f);
+        const float xo = clampf(__uint_as_float(v[12 + u]), 28.f);
         const float ei = ex2_approx(-kL2e * xi), ef = ex2_approx(-kL2e * xf), eg = ex2_approx(-2.0f * kL2e * xg);
         const float dig = (1.0f + ei) * (1.0f + eg);
         const float df = 1.0f + ef;
         const float num = fmaf(c[u], dig, (1.0f - eg) * df);
         const float cn = num * rcp_approx(df * dig);
         c[u] = cn;
-        const float xc = fminf(fmaxf(cn, -14.f), 14.f);
+        const float xc = clampf(cn, 14.f);
         const float eo = ex2_approx(-kL2e * xo), ec = ex2_approx(-2.0f * kL2e * xc);
         h[u] = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
     }
@@ -400,8 +405,8 @@ decoder_infer_x3_kernel(const float* __restrict__ x32,              // [B][T][8]
                 for (int rr = 0; rr < 4; ++rr) {
                     const int row = rr * 32 + lane;
                     if (row < nrows) {
-                        const float f[8] = {cur[rr][0].x, cur[rr][0].y, cur[rr][0].z, cur[rr][0].w,
-                                            cur[rr][1].x, cur[rr][1].y, cur[rr][1].z, cur[rr][1].w};
+                        const float f[8] = {kX3XScale * cur[rr][0].x, kX3XScale * cur[rr][0].y, kX3XScale * cur[rr][0].z, kX3XScale * cur[rr][0].w,
+                                            kX3XScale * cur[rr][1].x, kX3XScale * cur[rr][1].y, kX3XScale * cur[rr][1].z, kX3XScale * cur[rr][1].w};
                         uint32_t hi[4], lo[4];
                         split_pack8(f, hi, lo);
                         for (int rep = 0; rep < R; ++rep) {

@@ -435,3 +435,32 @@ def test_exact_tensor_core_kernel_vs_ffma_kernels(dev, checkpoint):
             np.testing.assert_allclose(pa.cpu().numpy(), pb.cpu().numpy(), atol=1e-4)   # softmax of logits that agree to 1e-5 of max|logit|
     finally:
         ops.EXACT_TC = True
+
+
+def test_exact_tier_input_range_and_nan(dev, checkpoint):
+    """The default tier must not depend on the EEG being small: windows with a 1e5 DC offset (raw ADC counts in uV), tiny
+    amplitudes, and a NaN sample behave like the reference arithmetic (FFMA kernels: any fp32 range; NaN propagates)."""
+    from neural_speech_decoding_b200 import ops
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    gen = torch.Generator(device="cpu").manual_seed(31)
+    m = EEG_LSTM()
+    m.load_state_dict(checkpoint, strict=True)
+    m = m.to(dev).eval()
+    x = torch.randn(6, 80, 8, generator=gen) * 2.73
+    x[1] += 1.0e5
+    x[2] *= 1.0e-3
+    x[3] = x[3] * 2000.0 - 3.0e4
+    x[4, 17, 3] = float("nan")
+    x = x.to(dev)
+    try:
+        with torch.inference_mode():
+            ops.EXACT_TC = True
+            a = m(x).cpu().numpy()
+            ops.EXACT_TC = False
+            b = m(x).cpu().numpy()
+    finally:
+        ops.EXACT_TC = True
+    ok = [0, 1, 2, 3, 5]
+    assert np.isfinite(a[ok]).all() and np.isfinite(b[ok]).all()
+    assert np.abs(a[ok] - b[ok]).max() / np.abs(b[ok]).max() < 1e-5
+    assert np.isnan(a[4]).all() and np.isnan(b[4]).all()
