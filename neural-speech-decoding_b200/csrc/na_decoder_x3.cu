@@ -106,7 +106,11 @@ __device__ __forceinline__ void x3_tmem_ld2(uint32_t taddr, uint32_t (&v)[2]) {
 // already saturated in fp32 (|x| <= 28 for the sigmoids, <= 14 for the tanh arguments) so the products stay below 2^127.
 __device__ __forceinline__ void cell_granule_exact(const uint32_t* v, float* c, float* h) {
     constexpr float kL2e = 1.4426950408889634f;
-    auto clampf = [](float x, float lim) { return x < -lim ? -lim : (x > lim ? lim : x); };     // NaN stays NaN (fminf would drop it)
+    auto clampf = [](float x, float lim) {                  // NaN-propagating min / max (FMNMX.NAN): NaN stays NaN, fminf would drop it
+        float r;
+        asm("{\n\t.reg .f32 t;\n\tmax.NaN.f32 t, %1, %2;\n\tmin.NaN.f32 %0, t, %3;\n\t}" : "=f"(r) : "f"(x), "f"(-lim), "f"(lim));
+        return r;
+    };
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const float xi = clampf(__uint_as_float(v[u]), 28.f);
