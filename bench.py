@@ -285,6 +285,21 @@ def run_gpu_arm(args):
     l1_tflops = L1_KERNEL_FLOPS_PER_WINDOW * n_win / (ms_l1 * 1e-3) / 1e12
     tile_rounds = -(-(n_win // 128) // 148)
 
+    # ---- single-window latency: what one `SimplePredictor.predict`-style call costs (numpy [625,8] in -> probs out) ----
+    def one_window_latency(dtype):
+        model.compute_dtype = dtype
+        w = host[0, 0].numpy()
+        lat = []
+        with torch.inference_mode():
+            for i in range(60):
+                t0 = time.perf_counter()
+                xg = torch.from_numpy(w[None]).to(dev)
+                _, p = model.decode(xg, want_probs=True)
+                p = p[0].cpu().numpy()
+                lat.append((time.perf_counter() - t0) * 1e3)
+        return statistics.median(lat[10:])
+    lat_exact, lat_bf16 = one_window_latency(torch.float32), one_window_latency(torch.bfloat16)
+
     # ---- CSV ingestion kernel: 4,096 files of the collector's format, HBM-bound byte work ------
     import io
     from neural_speech_decoding_b200 import ingest
@@ -392,6 +407,9 @@ def run_gpu_arm(args):
                          "per_timestep_latency_us": ms_l1 * 1e3 / T},
         },
     }
+    line["single_window_latency_ms"] = {"exact_fp32": lat_exact, "bf16": lat_bf16,
+                                         "what": "host numpy [625,8] -> H2D -> decoder forward + softmax -> D2H probabilities, median of 50 "
+                                                 "(reference on its CPU: ~13.5 ms per window, SURVEY 8a12)"}
     if cpu:
         line["cpu_baseline"] = {"value": cpu["windows_per_s"], "unit": "windows/s", "cores": cpu["cores"],
                                 "kind": "port", "sample": cpu["sample"]}
