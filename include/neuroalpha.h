@@ -246,12 +246,6 @@ int na_decoder_infer_wide_bf16(const void* x_bf16_tmp, const void* packed, const
                                void* state, float* logits, float* probs,
                                int64_t T, int64_t B, int64_t Bp, int64_t H, int64_t NC, na_stream_t stream);
 
-/* na_decoder_infer_wide_bf16 straight from the caller's batch-first fp32 windows x [B][T][8] (pack fused). */
-int na_decoder_infer_wide_bf16_x32(const float* x, const void* packed, const float* ln_w, const float* ln_b,
-                                   const float* fc0_w, const float* fc0_b, const float* fc3_w, const float* fc3_b,
-                                   void* state, float* logits, float* probs,
-                                   int64_t T, int64_t B, int64_t H, int64_t NC, na_stream_t stream);
-
 /* ---- tensor-core tier, training (bf16 operands; fp32 accumulate, cell state, gradients) ------------
  * Layouts: TMP fp32 [T][Bp][48]; TCL bf16 [T][Bp/128][F/8][128][8] (tile-chunk layout: a tile's
  * step-t slab is contiguous and already in the UMMA core-matrix layout); mask u8 [T][Bp][48].

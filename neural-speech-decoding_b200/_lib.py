@@ -43,7 +43,6 @@ SIGNATURES = {
     "na_decoder_wide_state_bytes": (c_int64, [I64]),
     "na_decoder_pack_wide_bf16": (c_int, [P] * 11 + [I64, P]),
     "na_decoder_infer_wide_bf16": (c_int, [P] * 11 + [I64, I64, I64, I64, I64, P]),
-    "na_decoder_infer_wide_bf16_x32": (c_int, [P] * 11 + [I64, I64, I64, I64, P]),
     "na_train_bf16_partial_floats": (c_int64, []),
     "na_dropout_mask_u8": (c_int, [ctypes.c_uint64, I64, I64, I64, P, P]),
     "na_lstm2_fwd_train_bf16": (c_int, [P, P, P, ctypes.c_uint64, I64, F32, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, P]),

@@ -205,8 +205,7 @@ decoder_infer_wide_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                           const float* __restrict__ fc3_w, const float* __restrict__ fc3_b,
                           float* __restrict__ state,                  // [grid][3][kStateFloats]: c0, c1, z
                           float* __restrict__ logits, float* __restrict__ probs,
-                          int T, int64_t B, int64_t Bp, int NC, int nquarters, int cs, int dbg,
-                          const float* __restrict__ x32) {     // != NULL: the caller's [B][T][8] fp32 windows (x unused)
+                          int T, int64_t B, int64_t Bp, int NC, int nquarters, int cs, int dbg) {
     // dbg (timing experiments only, results invalid): 1 = skip the cell update, 2 = skip the gate MMAs, 4 = skip the weight loads
     // cs = thread-block-cluster size (1, 2 or 4): the CTAs of a cluster stream the SAME weight image in lockstep, so
     // each ring stage is fetched from L2 once per cluster -- rank r loads 1/cs of it and multicasts it to all.
@@ -279,53 +278,14 @@ decoder_infer_wide_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
 
         if (warp == kTmaWarp) {
             // ================= TMA producer: x_t and the weight stream ===================================
-            // With x32 the whole warp first converts this step's fp32 rows (fetched one step ahead into registers: a
-            // step lasts > 15 us) into the fp16 A chunk -- the K1 pack fused, as in na_decoder_tc2.cu -- then lane 0
-            // streams the weights while the other lanes wait at the next step's __syncwarp.
-            const int nrows = nq * 32;
-            float4 cur[4][2], nxt[4][2];
-            auto fetch = [&](int t, float4 (&v)[4][2]) {
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                    const int row = rr * 32 + lane;
-                    const int64_t b = b0 + row;
-                    if (row < nrows && b < B) {
-                        const float4* src = reinterpret_cast<const float4*>(x32 + (b * T + t) * 8);
-                        v[rr][0] = __ldg(src);
-                        v[rr][1] = __ldg(src + 1);
-                    } else {
-                        v[rr][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        v[rr][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-            };
-            if (x32 != nullptr) fetch(0, cur);
-            for (int t = 0; t < T; ++t) {
-                const int n = n0 + t, sx = n % kWXStages, ux = n / kWXStages;
-                if (x32 != nullptr) {
-                    if (t + 1 < T) fetch(t + 1, nxt);
+            if (lane == 0) {
+                for (int t = 0; t < T; ++t) {
+                    const int n = n0 + t, sx = n % kWXStages, ux = n / kWXStages;
                     mbar_wait(&S.x_empty[sx], (ux & 1) ^ 1);
-#pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) {
-                        const int row = rr * 32 + lane;
-                        if (row < nrows)
-                            st_shared_v4(S.x[sx] + row * 16, pack_val(cur[rr][0].x, cur[rr][0].y), pack_val(cur[rr][0].z, cur[rr][0].w),
-                                         pack_val(cur[rr][1].x, cur[rr][1].y), pack_val(cur[rr][1].z, cur[rr][1].w));
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&S.x_full[sx]);
-#pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) { cur[rr][0] = nxt[rr][0]; cur[rr][1] = nxt[rr][1]; }
-                }
-                if (lane == 0) {
-                    if (x32 == nullptr) {
-                        mbar_wait(&S.x_empty[sx], (ux & 1) ^ 1);
-                        if (x_bytes) {
-                            mbar_arrive_expect_tx(&S.x_full[sx], x_bytes);
-                            bulk_load(S.x[sx], x + ((int64_t)t * Bp + b0) * 8, x_bytes, &S.x_full[sx]);
-                        } else mbar_arrive(&S.x_full[sx]);              // idle round
-                    }
+                    if (x_bytes) {
+                        mbar_arrive_expect_tx(&S.x_full[sx], x_bytes);
+                        bulk_load(S.x[sx], x + ((int64_t)t * Bp + b0) * 8, x_bytes, &S.x_full[sx]);
+                    } else mbar_arrive(&S.x_full[sx]);              // idle round
                     const unsigned char* src = packed;
                     for (int task = 0; task < kTasks; ++task) {
                         const int nsl = task < NCH ? C::kSl0 : C::kSl1;
@@ -344,7 +304,6 @@ decoder_infer_wide_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                         }
                     }
                 }
-                __syncwarp();
             }
         } else if (warp == kMmaWarp) {
             // ================= MMA issuer ============================================================
@@ -632,7 +591,7 @@ void set_wide_cluster(int v) { g_wide_cluster = (v == 1 || v == 2 || v == 4) ? v
 template <int NCH>
 static int launch_wide(const void* x, const void* packed, const float* ln_w, const float* ln_b, const float* fc0_w,
                        const float* fc0_b, const float* fc3_w, const float* fc3_b, float* state, float* logits, float* probs,
-                       int T, int64_t B, int64_t Bp, int NC, int sms, cudaStream_t stream, const float* x32) {
+                       int T, int64_t B, int64_t Bp, int NC, int sms, cudaStream_t stream) {
     const size_t smem = sizeof(WideSmem<NCH>) + 1024;
     cudaError_t e = cudaFuncSetAttribute(decoder_infer_wide_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_wide_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
@@ -655,7 +614,7 @@ static int launch_wide(const void* x, const void* packed, const float* ln_w, con
     cfg.numAttrs = 1;
     e = cudaLaunchKernelEx(&cfg, decoder_infer_wide_kernel<NCH>, reinterpret_cast<const __nv_bfloat16*>(x),
                            reinterpret_cast<const unsigned char*>(packed), ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, state, logits, probs,
-                           T, B, Bp, NC, nquarters, cs, g_wide_dbg, x32);
+                           T, B, Bp, NC, nquarters, cs, g_wide_dbg);
     if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_wide_bf16: launch failed (%s)", cudaGetErrorString(e));
     count_launch();
     return check_launch("na_decoder_infer_wide_bf16");
@@ -727,24 +686,6 @@ extern "C" int na_decoder_infer_wide_bf16(const void* x_bf16_tmp, const void* pa
     int rc = NA_EUNSUPPORTED;
     NA_WIDE_DISPATCH(H, rc = tc::launch_wide<NCH>(x_bf16_tmp, packed, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b,
                                                   reinterpret_cast<float*>(state), logits, probs, (int)T, B, Bp, (int)NC,
-                                                  tc::wide_sms(), as_stream(stream), nullptr));
-    return rc;
-}
-
-// the same forward straight from the caller's batch-first fp32 windows x [B][T][8] (fp32 -> fp16 pack fused into the kernel)
-extern "C" int na_decoder_infer_wide_bf16_x32(const float* x, const void* packed, const float* ln_w, const float* ln_b,
-                                              const float* fc0_w, const float* fc0_b, const float* fc3_w, const float* fc3_b,
-                                              void* state, float* logits, float* probs, int64_t T, int64_t B, int64_t H,
-                                              int64_t NC, na_stream_t stream) {
-    using namespace na;
-    NA_REQUIRE(H == 96 || H == 144 || H == 192, NA_EUNSUPPORTED, "na_decoder_infer_wide_bf16_x32: hidden_size=%lld (96, 144, 192)", (long long)H);
-    NA_REQUIRE(T >= 1 && T < (1 << 20) && B >= 1, NA_EINVAL, "na_decoder_infer_wide_bf16_x32: bad shape T=%lld B=%lld", (long long)T, (long long)B);
-    NA_REQUIRE(NC >= 1 && NC <= NA_MAX_CLASSES, NA_EUNSUPPORTED, "na_decoder_infer_wide_bf16_x32: num_classes=%lld", (long long)NC);
-    NA_REQUIRE_PTR(x); NA_REQUIRE_PTR(packed); NA_REQUIRE_PTR(state); NA_REQUIRE_PTR(logits);
-    NA_OPTIONAL_PTR(probs);
-    NA_REQUIRE(ln_w && ln_b && fc0_w && fc0_b && fc3_w && fc3_b, NA_EINVAL, "na_decoder_infer_wide_bf16_x32: null parameter pointer");
-    int rc = NA_EUNSUPPORTED;
-    NA_WIDE_DISPATCH(H, rc = tc::launch_wide<NCH>(nullptr, packed, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, reinterpret_cast<float*>(state),
-                                                  logits, probs, (int)T, B, 0, (int)NC, tc::wide_sms(), as_stream(stream), x));
+                                                  tc::wide_sms(), as_stream(stream)));
     return rc;
 }

@@ -64,7 +64,8 @@ def _stream() -> int:
 def all_custom_ops():
     return [window_zscore, pack_lstm_layer, lstm_layer_fwd, lstm_layer_bwd, lstm_layer_wgrad, head_fwd,
             head_bwd, trial_mean, decoder_pack_bf16, decoder_infer_bf16, lstm2_fwd_train_bf16, lstm_bwd_bf16,
-            dropout_mask_u8, head_tail_fwd, head_tail_bwd]
+            dropout_mask_u8, head_tail_fwd, head_tail_bwd, decoder_infer_bf16_x32, decoder_pack_x3, decoder_infer_x3,
+            decoder_pack_wide_bf16, decoder_infer_wide_bf16]
 
 
 def launch_count() -> int:
@@ -343,7 +344,6 @@ def _(x, packed, head, want_probs):
     return x.new_empty((x.shape[0], NC), dtype=torch.float32), x.new_empty((x.shape[0], NC) if want_probs else (0,), dtype=torch.float32)
 
 
-FUSED_INPUT_WIDE = False    # decoder_infer_wide: see the measurement note there
 FUSED_INPUT = True          # decoder_infer_tc: read fp32 [B,T,8] directly (False: K1 pack + time-major kernel; A/B timing)
 
 
@@ -467,39 +467,14 @@ def _(x_tmp, packed, head, B, H, want_probs):
     return x_tmp.new_empty((B, NC), dtype=torch.float32), x_tmp.new_empty((B, NC) if want_probs else (0,), dtype=torch.float32)
 
 
-@torch.library.custom_op("neuroalpha::decoder_infer_wide_bf16_x32", mutates_args=(), device_types="cuda")
-def decoder_infer_wide_bf16_x32(x: Tensor, packed: Tensor, head: Sequence[Tensor], H: int, want_probs: bool) -> Tuple[Tensor, Tensor]:
-    """decoder_infer_wide_bf16 straight from the batch-first fp32 windows x [B,T,8] (pack fused into the kernel)."""
-    _require_cuda(x, packed, *head)
-    B, T, C = x.shape
-    if x.dtype != torch.float32 or C != 8 or not x.is_contiguous():
-        raise RuntimeError("decoder_infer_wide_bf16_x32: x must be contiguous fp32 [B, T, 8]")
-    head = [_f32c(t) for t in head]
-    NC = head[4].shape[0]
-    logits = torch.empty((B, NC), dtype=torch.float32, device=x.device)
-    probs = torch.empty((B, NC) if want_probs else (0,), dtype=torch.float32, device=x.device)
-    state = _wide_state(H, x.device)
-    _lib.call("na_decoder_infer_wide_bf16_x32", x.data_ptr(), packed.data_ptr(), *[t.data_ptr() for t in head],
-              state.data_ptr(), logits.data_ptr(), _ptr(probs) if want_probs else None, T, B, H, NC, _stream())
-    return logits, probs
-
-
-@decoder_infer_wide_bf16_x32.register_fake
-def _(x, packed, head, H, want_probs):
-    NC = head[4].shape[0]
-    return x.new_empty((x.shape[0], NC), dtype=torch.float32), x.new_empty((x.shape[0], NC) if want_probs else (0,), dtype=torch.float32)
-
-
 def decoder_infer_wide(x: Tensor, packed: Tensor, head_params: Sequence[Tensor], H: int, want_probs: bool = False,
                        zscore: bool = False) -> Tuple[Tensor, Tensor]:
     """Eval forward of a wide decoder on the tensor-core tier.  head_params in EEG_LSTM._head_params() order."""
     _require_cuda(x)
     B, T, C = x.shape
-    # Measured on B200 (scripts/time_wide_fused.py, H = 192, T = 2500, 18,944 windows): fusing the input pack into the wide
-    # kernel is bit-identical but SLOWER (59.1 vs 56.0 ms incl. the separate pack) -- the producer warp's weight stream is
-    # that kernel's critical path and the conversion delays it at every step -- so the separate K1 pack stays the default.
-    if FUSED_INPUT_WIDE and not zscore and x.dtype == torch.float32 and C == 8 and B > 0:
-        return decoder_infer_wide_bf16_x32(x.contiguous(), packed, list(head_params[2:]), H, want_probs)
+    # (Fusing the input pack into the wide kernel, as in decoder_infer_tc, was built and measured: bit-identical but slower --
+    # 59.1 vs 56.0 ms at H = 192, T = 2500 -- because the producer warp's weight stream is that kernel's critical path; and the
+    # extra code cost the default path 7 % through the instruction cache, so it was removed again.)
     xt = window_zscore(x, T, T, zscore, True, NA_F16, TC_TILE)
     return decoder_infer_wide_bf16(xt, packed, list(head_params[2:]), B, H, want_probs)
 

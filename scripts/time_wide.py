@@ -19,7 +19,7 @@ def t(fn, reps=3):
 flops = 2 * T * (4 * H * (8 + H) + 4 * H * 2 * H) + 4 * T * H
 from neural_speech_decoding_b200 import _lib
 for N in Ns:
-  for cs, dbg in ((1, 0), (1, 15)):
+  for cs, dbg in ((1, 0),):
     _lib.call('na_set_tuning', b'tc_wide_cluster', cs); _lib.call('na_set_tuning', b'tc_wide_dbg', dbg)
     x = torch.randn(N, T, 8, device=dev) * 2.73
     with torch.inference_mode():
