@@ -165,6 +165,9 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+NUMA_BINDING = [None]
+
+
 def dist_setup(n_gpus):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -172,6 +175,9 @@ def dist_setup(n_gpus):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
+        # each rank on the CPUs (and the NUMA node) next to its GPU: the e2e leg's pinned buffers are first-touched there
+        from neural_speech_decoding_b200.dp import bind_to_gpu_numa
+        NUMA_BINDING[0] = bind_to_gpu_numa(local)
         # NCCL prints its version banner on STDOUT when the communicator is created; stdout must carry
         # exactly one JSON line, so fd 1 points at stderr until the first collective has run.
         sys.stdout.flush()
@@ -353,7 +359,8 @@ def run_gpu_arm(args):
                    "parity": "tests/test_gpu_bf16.py: logits within 2e-2 of the fp32 reference, argmax identical on the 324 repo windows"},
         "e2e": {"value": bf["e2e_value"], "unit": "windows/s", "ms_per_step": bf["e2e_ms_per_step"],
                 "h2d_bytes_per_step": n_win * T * C * 4, "d2h_bytes_per_step": B * NC * 4,
-                "api": "neural_speech_decoding_b200.tester.run_trials_batched(pinned host fp32 [R,B,T,C]) -> numpy [B,K]"},
+                "api": "neural_speech_decoding_b200.tester.run_trials_batched(pinned host fp32 [R,B,T,C]) -> numpy [B,K]",
+                "rank0_cpu_binding": (f"{len(NUMA_BINDING[0])} CPUs local to the GPU (NVML affinity)" if NUMA_BINDING[0] else "none")},
         "gpu_launches": bf["launches"],
         "clocks": bf["clocks"],
         "roofline": {

@@ -81,6 +81,38 @@ class DataParallelTrainer:
         return loss
 
 
+def bind_to_gpu_numa(device_index: int) -> Optional[list]:
+    """Pin this process to the CPUs that are local to GPU ``device_index`` (NVML's affinity mask, intersected with the
+    CPUs the container may use), so that pinned host buffers are first-touched on the GPU's NUMA node and the H2D
+    copies of N ranks do not all cross the socket interconnect.  Call it before allocating pinned memory.
+    Returns the CPU list, or None if NVML / the affinity call is unavailable (nothing changes then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        prop = torch.cuda.get_device_properties(device_index)
+        handle = None
+        if hasattr(prop, "pci_bus_id"):              # NVML enumerates every GPU of the box; CUDA only the visible ones
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByPciBusId(
+                    f"{int(getattr(prop, 'pci_domain_id', 0)):08x}:{int(prop.pci_bus_id):02x}:{int(getattr(prop, 'pci_device_id', 0)):02x}.0")
+            except Exception:
+                handle = None
+        if handle is None:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        local = {i for i in range(ncpu) if (int(mask[i // 64]) >> (i % 64)) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(local & allowed)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def shard_batch(n: int, rank: int, world_size: int) -> slice:
     """Contiguous B/N slices (keeps all trials of a session on one GPU)."""
     per = (n + world_size - 1) // world_size
