@@ -124,6 +124,8 @@ def main(argv=None) -> None:
         import torch.distributed as dist
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
+        from .dp import bind_to_gpu_numa
+        bind_to_gpu_numa(local)                     # host buffers next to this rank's GPU
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     classes = [c.strip() for c in args.classes.split(",") if c.strip()]
     if Path(args.data).is_dir():
