@@ -152,9 +152,11 @@ class EEG_LSTM(nn.Module):
             if bf16 and self.tc_wide_supported():
                 return ops.decoder_infer_wide(x, self._packed_tc_wide(), self._head_params(), self.lstm.hidden_size,
                                               want_probs, self.zscore_input)
-            if (ops.EXACT_TC and not bf16 and self.tc_supported() and not self.zscore_input and x.dtype == torch.float32
-                    and x.shape[0] > 0):
-                # exact tier, flagship shape: fp32-accurate tensor-core kernel (fp16 hi/lo operand split)
+            if (ops.EXACT_TC and not bf16 and self.tc_supported() and x.dtype == torch.float32 and x.shape[0] > 0):
+                # exact tier, flagship shape: fp32-accurate tensor-core kernel (fp16 hi/lo operand split); the optional
+                # z-score stage is one K1 pass that leaves the windows batch-first in fp32
+                if self.zscore_input:
+                    x = ops.window_zscore(x, x.shape[1], x.shape[1], True, False, ops.NA_F32)
                 return ops.decoder_infer_x3(x.contiguous(), self._packed_x3(), self._head_params(), want_probs)
             L = self.lstm.num_layers
             return ops.decoder_infer(x, [self.lstm.layer(l) for l in range(L)],

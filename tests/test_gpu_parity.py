@@ -464,3 +464,23 @@ def test_exact_tier_input_range_and_nan(dev, checkpoint):
     assert np.isfinite(a[ok]).all() and np.isfinite(b[ok]).all()
     assert np.abs(a[ok] - b[ok]).max() / np.abs(b[ok]).max() < 1e-5
     assert np.isnan(a[4]).all() and np.isnan(b[4]).all()
+
+
+def test_exact_tier_zscore_stage(dev, checkpoint, windows):
+    """zscore_input = True on the exact tier: K1 (Frontend/app.py:166-170 semantics) then the fp32-accurate decoder, against
+    the CPU oracle's z-score + the reference module restatement."""
+    from oracle import numpy_oracle as no
+    from oracle.torch_ref import RefEEGLSTM
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    m = EEG_LSTM()
+    m.load_state_dict(checkpoint, strict=True)
+    m = m.to(dev).eval()
+    m.zscore_input = True
+    refm = RefEEGLSTM().eval()
+    refm.load_state_dict(checkpoint, strict=True)
+    X = torch.from_numpy(windows["X"][:48])
+    with torch.inference_mode():
+        got = m(X.to(dev)).cpu().numpy()
+        want = refm(torch.from_numpy(no.zscore_window(X.numpy()))).numpy()
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
+    assert np.array_equal(got.argmax(1), want.argmax(1))
