@@ -24,16 +24,30 @@ gemm_tn_partial_kernel(const float* __restrict__ G, int64_t ldg, const float* __
 #pragma unroll
         for (int jn = 0; jn < 4; ++jn) acc[i][jn] = 0.f;
 
-    for (int64_t r0 = r_begin; r0 < r_end; r0 += kTnRows) {
+    // register double buffer: the global loads of the next 16 rows are in flight while the current 16 are multiplied
+    // (the first version loaded, synchronised and multiplied in sequence and was latency-bound at 16 TFLOP/s)
+    constexpr int kPer = (kTnRows * kTnTile) / kTnThreads;        // elements of each operand per thread and stage
+    float gn[kPer], an[kPer];
+    auto fetch = [&](int64_t r0) {
 #pragma unroll
-        for (int e = 0; e < (kTnRows * kTnTile) / kTnThreads; ++e) {
+        for (int e = 0; e < kPer; ++e) {
             const int idx = tid + e * kTnThreads;
             const int rr = idx / kTnTile, cc = idx % kTnTile;
             const int64_t r = r0 + rr;
-            Gs[rr][cc] = (r < r_end && m0 + cc < M) ? G[r * ldg + m0 + cc] : 0.f;
-            As[rr][cc] = (r < r_end && n0 + cc < N) ? A[r * lda + n0 + cc] : 0.f;
+            gn[e] = (r < r_end && m0 + cc < M) ? __ldg(G + r * ldg + m0 + cc) : 0.f;
+            an[e] = (r < r_end && n0 + cc < N) ? __ldg(A + r * lda + n0 + cc) : 0.f;
+        }
+    };
+    fetch(r_begin);
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += kTnRows) {
+#pragma unroll
+        for (int e = 0; e < kPer; ++e) {
+            const int idx = tid + e * kTnThreads;
+            Gs[idx / kTnTile][idx % kTnTile] = gn[e];
+            As[idx / kTnTile][idx % kTnTile] = an[e];
         }
         __syncthreads();
+        if (r0 + kTnRows < r_end) fetch(r0 + kTnRows);
 #pragma unroll
         for (int rr = 0; rr < kTnRows; ++rr) {
             const float4 g = *reinterpret_cast<const float4*>(&Gs[rr][ty * 4]);
