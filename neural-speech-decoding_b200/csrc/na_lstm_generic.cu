@@ -7,7 +7,8 @@
 
 namespace na {
 
-constexpr int kGenTile = 8;   // windows per CTA
+constexpr int kGenTile = 8;   // windows per CTA (the BPTT kernel's transposed d(gates) tile assumes 8)
+static_assert(kGenTile == 8, "lstm_bwd_generic_kernel packs the 8 windows of a gate column into two float4");
 
 __global__ void pack_lstm_layer_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh,
                                        const float* __restrict__ b_ih, const float* __restrict__ b_hh,
@@ -119,6 +120,7 @@ __global__ void lstm_bwd_generic_kernel(const float* __restrict__ dh_out, const 
     for (int t = T - 1; t >= 0; --t) {
         const int64_t row0 = (int64_t)t * Bp + b0;
         if (unit) {
+            float pi_[kGenTile], pf_[kGenTile], pg_[kGenTile], po_[kGenTile];
 #pragma unroll
             for (int b = 0; b < kGenTile; ++b) {
                 const int64_t row = row0 + b;
@@ -138,9 +140,15 @@ __global__ void lstm_bwd_generic_kernel(const float* __restrict__ dh_out, const 
                 const float po = d_o * o * (1.0f - o);
                 float* dgr = dgates + row * G + j;
                 dgr[0] = pi; dgr[H] = pf; dgr[2 * H] = pg; dgr[3 * H] = po;
-                float* ds = dg_s + b * G + j;
-                ds[0] = pi; ds[H] = pf; ds[2 * H] = pg; ds[3 * H] = po;
+                pi_[b] = pi; pf_[b] = pf; pg_[b] = pg; po_[b] = po;
             }
+            // d(gates) of this step in shared memory, TRANSPOSED: [gate column][window], so that the contraction below reads
+            // the 8 windows of a column with two 16-byte broadcast loads instead of eight 4-byte ones
+            float4* d4 = reinterpret_cast<float4*>(dg_s);
+            d4[(j) * 2] = make_float4(pi_[0], pi_[1], pi_[2], pi_[3]);             d4[(j) * 2 + 1] = make_float4(pi_[4], pi_[5], pi_[6], pi_[7]);
+            d4[(H + j) * 2] = make_float4(pf_[0], pf_[1], pf_[2], pf_[3]);         d4[(H + j) * 2 + 1] = make_float4(pf_[4], pf_[5], pf_[6], pf_[7]);
+            d4[(2 * H + j) * 2] = make_float4(pg_[0], pg_[1], pg_[2], pg_[3]);     d4[(2 * H + j) * 2 + 1] = make_float4(pg_[4], pg_[5], pg_[6], pg_[7]);
+            d4[(3 * H + j) * 2] = make_float4(po_[0], po_[1], po_[2], po_[3]);     d4[(3 * H + j) * 2 + 1] = make_float4(po_[4], po_[5], po_[6], po_[7]);
         }
         __syncthreads();
         if (colthr && (!is_in || din != nullptr)) {
@@ -149,10 +157,13 @@ __global__ void lstm_bwd_generic_kernel(const float* __restrict__ dh_out, const 
             for (int b = 0; b < kGenTile; ++b) acc[b] = 0.f;
             const float* wcol = is_in ? (w_ih + j) : (w_hh + (j - K));
             const int ld = is_in ? K : H;
+            const float4* d4 = reinterpret_cast<const float4*>(dg_s);
+#pragma unroll 4
             for (int col = 0; col < G; ++col) {
                 const float w = __ldg(wcol + (size_t)col * ld);
-#pragma unroll
-                for (int b = 0; b < kGenTile; ++b) acc[b] = fmaf(dg_s[b * G + col], w, acc[b]);
+                const float4 a = d4[col * 2], b4 = d4[col * 2 + 1];
+                acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]); acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
+                acc[4] = fmaf(b4.x, w, acc[4]); acc[5] = fmaf(b4.y, w, acc[5]); acc[6] = fmaf(b4.z, w, acc[6]); acc[7] = fmaf(b4.w, w, acc[7]);
             }
             if (is_in) {
 #pragma unroll
