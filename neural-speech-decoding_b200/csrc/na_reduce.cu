@@ -11,7 +11,10 @@ constexpr int kTnThreads = 256; // 16 x 16 threads, 4 x 4 outputs each
 
 __global__ void __launch_bounds__(kTnThreads)
 gemm_tn_partial_kernel(const float* __restrict__ G, int64_t ldg, const float* __restrict__ A, int64_t lda,
-                       int64_t R, int M, int N, float* __restrict__ partial, int64_t rows_per_chunk) {
+                       int64_t R, int M, int N, float* __restrict__ partial, int64_t rows_per_chunk,
+                       // optional second A operand: columns [N1, N) come from A2 at row r - shift (zero for r < shift);
+                       // one pass over G then yields dW_ih AND dW_hh (h_{t-1} = the h rows shifted down by Bp)
+                       int N1, const float* __restrict__ A2, int64_t lda2, int64_t shift) {
     __shared__ float Gs[kTnRows][kTnTile + 4];
     __shared__ float As[kTnRows][kTnTile + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -35,7 +38,13 @@ gemm_tn_partial_kernel(const float* __restrict__ G, int64_t ldg, const float* __
             const int rr = idx / kTnTile, cc = idx % kTnTile;
             const int64_t r = r0 + rr;
             gn[e] = (r < r_end && m0 + cc < M) ? __ldg(G + r * ldg + m0 + cc) : 0.f;
-            an[e] = (r < r_end && n0 + cc < N) ? __ldg(A + r * lda + n0 + cc) : 0.f;
+            const int n = n0 + cc;
+            float av = 0.f;
+            if (r < r_end && n < N) {
+                if (n < N1) av = __ldg(A + r * lda + n);
+                else if (r >= shift) av = __ldg(A2 + (r - shift) * lda2 + (n - N1));
+            }
+            an[e] = av;
         }
     };
     fetch(r_begin);
@@ -117,11 +126,38 @@ int gemm_tn(const float* G, int64_t ldg, const float* A, int64_t lda, int64_t R,
     int64_t rpc = (R + nch - 1) / nch;
     rpc = (rpc + kTnRows - 1) / kTnRows * kTnRows;
     const dim3 grid(nch, (unsigned)((M + kTnTile - 1) / kTnTile), (unsigned)((N + kTnTile - 1) / kTnTile));
-    gemm_tn_partial_kernel<<<grid, kTnThreads, 0, st>>>(G, ldg, A, lda, R, (int)M, (int)N, partial, rpc);
+    gemm_tn_partial_kernel<<<grid, kTnThreads, 0, st>>>(G, ldg, A, lda, R, (int)M, (int)N, partial, rpc, (int)N, nullptr, 0, 0);
     const int64_t n = M * N;
     reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, out, nch, n);
     count_launch(2);
     return check_launch("gemm_tn");
+}
+
+// out1[M][N1] = G^T A1 over rows [0, R),  out2[M][N2] = G[shift:]^T A2[:R-shift]  in ONE pass over G.
+__global__ void reduce_partials_split_kernel(const float* __restrict__ partial, float* __restrict__ out1, float* __restrict__ out2,
+                                             int nchunks, int M, int N1, int N2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = N1 + N2;
+    if (i >= (int64_t)M * N) return;
+    float s = 0.f;
+    for (int c = 0; c < nchunks; ++c) s += partial[(size_t)c * M * N + i];      // fixed order
+    const int m = (int)(i / N), n = (int)(i % N);
+    if (n < N1) out1[(size_t)m * N1 + n] = s;
+    else out2[(size_t)m * N2 + (n - N1)] = s;
+}
+
+int gemm_tn2(const float* G, int64_t ldg, const float* A1, int64_t lda1, int64_t N1, const float* A2, int64_t lda2, int64_t N2,
+             int64_t shift, int64_t R, int64_t M, float* out1, float* out2, float* partial, cudaStream_t st) {
+    const int64_t N = N1 + N2;
+    const int nch = wgrad_nchunks(M, N, R);
+    int64_t rpc = (R + nch - 1) / nch;
+    rpc = (rpc + kTnRows - 1) / kTnRows * kTnRows;
+    const dim3 grid(nch, (unsigned)((M + kTnTile - 1) / kTnTile), (unsigned)((N + kTnTile - 1) / kTnTile));
+    gemm_tn_partial_kernel<<<grid, kTnThreads, 0, st>>>(G, ldg, A1, lda1, R, (int)M, (int)N, partial, rpc, (int)N1, A2, lda2, shift);
+    const int64_t n = M * N;
+    reduce_partials_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, out1, out2, nch, (int)M, (int)N1, (int)N2);
+    count_launch(2);
+    return check_launch("gemm_tn2");
 }
 
 int reduce_partials(const float* partial, float* out, int nchunks, int64_t n, cudaStream_t st) {
@@ -145,7 +181,7 @@ int colsum(const float* G, int64_t ldg, int64_t R, int64_t M, float* out, float*
 extern "C" int64_t na_wgrad_partial_floats(int64_t K, int64_t H) {
     // worst case over the three reductions of one layer (row count unbounded)
     const int64_t M = 4 * H, big = (int64_t)1 << 40;
-    const int64_t a = (int64_t)na::wgrad_nchunks(M, K, big) * M * K;
+    const int64_t a = (int64_t)na::wgrad_nchunks(M, K + H, big) * M * (K + H);
     const int64_t b = (int64_t)na::wgrad_nchunks(M, H, big) * M * H;
     const int64_t c = (int64_t)na::wgrad_nchunks(M, 1, big) * M;
     return (a > b ? (a > c ? a : c) : (b > c ? b : c)) + 64;
@@ -160,13 +196,16 @@ extern "C" int na_lstm_layer_wgrad_f32(const float* dgates, const float* in, con
     NA_REQUIRE_PTR(dw_ih); NA_REQUIRE_PTR(dw_hh); NA_REQUIRE_PTR(db); NA_REQUIRE_PTR(partials);
     cudaStream_t st = as_stream(stream);
     const int64_t R = T * Bp, G = 4 * H;
-    int rc = gemm_tn(dgates, G, in, K, R, G, K, dw_ih, partials, st);
-    if (rc) return rc;
-    if (T > 1) {
-        // rows (t, b), t >= 1, pair with h_{t-1} = h rows shifted down by Bp
-        rc = gemm_tn(dgates + Bp * G, G, h, H, R - Bp, G, H, dw_hh, partials, st);
+    int rc;
+    if (K + H <= kTnTile) {
+        // [in | h_{t-1}] fits one 64-column tile (layer 0 of the flagship: 8 + 48): dW_ih (all rows) and dW_hh (rows t >= 1
+        // paired with h_{t-1} = the h rows shifted down by Bp) in ONE pass over dgates (10.2 -> 6.7 ms per 8,192 windows)
+        rc = gemm_tn2(dgates, G, in, K, K, h, H, H, Bp, R, G, dw_ih, dw_hh, partials, st);
     } else {
-        rc = (int)cudaMemsetAsync(dw_hh, 0, sizeof(float) * G * H, st);
+        rc = gemm_tn(dgates, G, in, K, R, G, K, dw_ih, partials, st);
+        if (rc) return rc;
+        if (T > 1) rc = gemm_tn(dgates + Bp * G, G, h, H, R - Bp, G, H, dw_hh, partials, st);
+        else rc = (int)cudaMemsetAsync(dw_hh, 0, sizeof(float) * G * H, st);
     }
     if (rc) return rc;
     return colsum(dgates, G, R, G, db, partials, st);
