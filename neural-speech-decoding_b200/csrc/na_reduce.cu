@@ -9,6 +9,7 @@ constexpr int kTnTile = 64;     // output tile 64 x 64
 constexpr int kTnRows = 16;     // rows staged per iteration
 constexpr int kTnThreads = 256; // 16 x 16 threads, 4 x 4 outputs each
 
+template <bool TWO>      // TWO: second A operand (compile-time, so the single-operand loads stay branch-free)
 __global__ void __launch_bounds__(kTnThreads)
 gemm_tn_partial_kernel(const float* __restrict__ G, int64_t ldg, const float* __restrict__ A, int64_t lda,
                        int64_t R, int M, int N, float* __restrict__ partial, int64_t rows_per_chunk,
@@ -41,7 +42,7 @@ gemm_tn_partial_kernel(const float* __restrict__ G, int64_t ldg, const float* __
             const int n = n0 + cc;
             float av = 0.f;
             if (r < r_end && n < N) {
-                if (n < N1) av = __ldg(A + r * lda + n);
+                if (!TWO || n < N1) av = __ldg(A + r * lda + n);
                 else if (r >= shift) av = __ldg(A2 + (r - shift) * lda2 + (n - N1));
             }
             an[e] = av;
@@ -126,7 +127,7 @@ int gemm_tn(const float* G, int64_t ldg, const float* A, int64_t lda, int64_t R,
     int64_t rpc = (R + nch - 1) / nch;
     rpc = (rpc + kTnRows - 1) / kTnRows * kTnRows;
     const dim3 grid(nch, (unsigned)((M + kTnTile - 1) / kTnTile), (unsigned)((N + kTnTile - 1) / kTnTile));
-    gemm_tn_partial_kernel<<<grid, kTnThreads, 0, st>>>(G, ldg, A, lda, R, (int)M, (int)N, partial, rpc, (int)N, nullptr, 0, 0);
+    gemm_tn_partial_kernel<false><<<grid, kTnThreads, 0, st>>>(G, ldg, A, lda, R, (int)M, (int)N, partial, rpc, (int)N, nullptr, 0, 0);
     const int64_t n = M * N;
     reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, out, nch, n);
     count_launch(2);
@@ -153,7 +154,7 @@ int gemm_tn2(const float* G, int64_t ldg, const float* A1, int64_t lda1, int64_t
     int64_t rpc = (R + nch - 1) / nch;
     rpc = (rpc + kTnRows - 1) / kTnRows * kTnRows;
     const dim3 grid(nch, (unsigned)((M + kTnTile - 1) / kTnTile), (unsigned)((N + kTnTile - 1) / kTnTile));
-    gemm_tn_partial_kernel<<<grid, kTnThreads, 0, st>>>(G, ldg, A1, lda1, R, (int)M, (int)N, partial, rpc, (int)N1, A2, lda2, shift);
+    gemm_tn_partial_kernel<true><<<grid, kTnThreads, 0, st>>>(G, ldg, A1, lda1, R, (int)M, (int)N, partial, rpc, (int)N1, A2, lda2, shift);
     const int64_t n = M * N;
     reduce_partials_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, out1, out2, nch, (int)M, (int)N1, (int)N2);
     count_launch(2);
