@@ -516,7 +516,7 @@ def train_leg(args, world, rank, dev):
                "allreduce": "one flat fp32 bucket (127 KB), NCCL" if world > 1 else "none (1 GPU)",
                "parity": "tests/test_gpu_bf16.py: gradients within 2e-2 of the fp64 oracle",
                "frac_of_bf16_sustained_peak": tc["achieved_tflops_per_gpu"] / measured_peaks()["bf16_tflops_sustained"]})
-    fp = run(torch.float32, min(args.train_batch, 8192 * world), 4096, min(steps, 2))
+    fp = run(torch.float32, min(args.train_batch, 8192 * world), 8192, min(steps, 2))
     tc["fp32_exact"] = {k: fp[k] for k in ("value", "unit", "ms_per_step", "global_batch", "micro_batch")}
     tc["fp32_exact"]["parity"] = "tests/test_gpu_parity.py: gradients within 1e-5"
     return tc
