@@ -32,6 +32,12 @@
 //     latency (~0.35 of a full step) instead of a full step.  Small batches are spread over all SMs this way.
 //     Gate columns are permuted in granules of 4 units, n = (j/4)*16 + gate*4 + j%4, so that 16 / 32
 //     accumulator columns hold i,f,g,o of 4 / 8 units.
+//   * Fused input (x32 != NULL, na_decoder_infer_bf16_x32): the producer warp reads the caller's batch-first fp32
+//     [B][T][8] windows itself -- 32 B per window and step, staged three steps ahead by cp.async -- converts them to
+//     fp16 and writes the x chunk, so the separate fp32 -> fp16 time-major pack (K1) and its intermediate are gone.
+//   * One tcgen05.commit per layer and step: the x ring is released by a plain mbarrier.arrive of an epilogue thread
+//     that has seen d0_full, and the h0 buffer written at step n is ordered after the layer-1 MMA of step n-2 by the
+//     d1_full the writing thread already waited for.
 #include "na_tc_common.cuh"
 
 namespace na {
