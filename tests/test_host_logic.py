@@ -124,3 +124,20 @@ def test_trial_mean_rounding(cpu_backend, golden_dir):
     t = np.load(golden_dir / "ref_run_trials.npz")
     got = ops.trial_mean(torch.from_numpy(t["per_trial_probs"])).numpy()
     assert np.array_equal(got, t["avg_probs"])
+
+
+def test_bind_to_gpu_numa_is_harmless_without_a_gpu():
+    """dp.bind_to_gpu_numa must never raise: no NVML / no GPU / restricted cpuset -> None and the affinity is untouched."""
+    import os
+    from neural_speech_decoding_b200 import dp
+    before = os.sched_getaffinity(0)
+    got = dp.bind_to_gpu_numa(0)
+    assert got is None or (isinstance(got, list) and set(got) <= before)
+    assert os.sched_getaffinity(0) == (set(got) if got else before)
+
+
+def test_shard_batch_covers_everything_once():
+    from neural_speech_decoding_b200.dp import shard_batch
+    for n, w in ((4096, 8), (10, 3), (1, 4), (0, 2)):
+        idx = [i for r in range(w) for i in range(n)[shard_batch(n, r, w)]]
+        assert idx == list(range(n))
