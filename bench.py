@@ -7,7 +7,10 @@ A "step" is one pass of the hot path over one batch of synthetic EEG: BASELINE.j
 i.e. R=10 trials x B=4096 sessions of [625,8] windows per GPU (40,960 windows), decoder forward +
 class softmax + run_trials' 10-trial probability averaging, fp32, shipped 3-class weights.
 
-  value : windows/s with the windows already resident in HBM (CUDA events, max over ranks)
+  value : windows/s with the windows already resident in HBM (CUDA events, max over ranks), measured on the
+          fp32-contract tier (decoder_infer_x3_kernel: fp32-accurate tcgen05, every operand split into fp16 hi + lo,
+          1e-5 parity) -- the reference's arithmetic is fp32, so this is the like-for-like headline; the 16-bit tier
+          (north_star's "bf16 path", IEEE fp16 operands, 2e-2 contract) is the named extra "fp16_tier"
   e2e   : the same through the public host API (run_trials_batched on PINNED HOST windows):
           H2D of every trial + D2H of the averaged probabilities inside the timed region
   roofline / cpu_baseline / clocks / gpu_launches / train : see DESIGN.md "Measurement"
@@ -46,6 +49,9 @@ L1_KERNEL_FLOPS_PER_WINDOW = 2 * (48 + 48) * 192 * T      # layer-1 recurrence k
 L0_KERNEL_FLOPS_PER_WINDOW = 2 * (8 + 48) * 192 * T
 INPUT_SIGMA = 2.73                            # matches the CSV corpus
 NCU_TRAFFIC_BYTES_40960 = 823.51e6 + 7.36e6   # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_tc2_fused_ncu_full.csv
+# the same two counters for decoder_infer_x3_kernel (one launch over 40,960 windows)
+NCU_TRAFFIC_BYTES_40960_X3 = 823.51e6 + 7.36e6
+NCU_TRAFFIC_SOURCE_X3 = "pending: profiles/r2_x3_ncu_full.csv"
 
 
 def load_checkpoint():
@@ -143,6 +149,93 @@ def cpu_arm(steps, warmup, R=10, B=256):
             f"chunks of 512, fp32, median of {steps} after {warmup} warm-up", "times": times}
 
 
+def cpu_train_arm(B=512, reps=3):
+    """the reference module's train step on the host -- B = 512, train mode (dropout, RReLU noise),
+    mean cross-entropy, Adam lr 1e-3; one warm-up, median of ``reps``."""
+    from oracle.torch_ref import RefEEGLSTM
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    m = RefEEGLSTM().train()
+    m.load_state_dict(load_checkpoint(), strict=True)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    x = synth_windows(B, seed=2000)
+    y = torch.randint(0, NC, (B,), generator=torch.Generator(device="cpu").manual_seed(1))
+    times = []
+    for i in range(reps + 1):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(m(x), y).backward()
+        opt.step()
+        if i:
+            times.append(time.perf_counter() - t0)
+    return {"value": B / statistics.median(times), "unit": "windows/s", "ms_per_step": 1e3 * statistics.median(times),
+            "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"one train step of B={B} windows [625,8] (fwd + bwd + Adam), train mode, fp32, median of {reps} after 1 warm-up"}
+
+
+def config1_labels():
+    d = np.load(ROOT / "tests" / "golden" / "eeg_windows.npz")
+    idx = {"food": 0, "water": 1, "backgroundnoise": 2}           # CLASS_NAMES order (lstm_eeg_model.py:11); yes / no excluded
+    keep = [i for i, s in enumerate(d["prefix"]) if str(s) in idx]
+    return d["X"], np.array(keep), np.array([idx[str(d["prefix"][i])] for i in keep], dtype=np.int64)
+
+
+def config1_epoch(model, X, keep, y, to_dev):
+    """BASELINE configs[0]: fp32 forward over all 324 repo windows + one training epoch (the 179 three-class windows,
+    batch 32, CE, Adam lr 1e-3 -- the recipe is ours).  Returns (forward seconds, epoch seconds, last loss)."""
+    sync = torch.cuda.synchronize if to_dev is not None else (lambda: None)
+    xa = torch.from_numpy(X)
+    model.eval()
+    sync(); t0 = time.perf_counter()
+    with torch.inference_mode():
+        xin = xa.to(to_dev) if to_dev is not None else xa
+        out = model(xin)
+        out = out.cpu() if to_dev is not None else out
+    sync(); t_fwd = time.perf_counter() - t0
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    order = np.random.default_rng(0).permutation(len(keep))
+    sync(); t0 = time.perf_counter()
+    loss = None
+    for s0 in range(0, len(order), 32):
+        ix = order[s0:s0 + 32]
+        xb, yb = torch.from_numpy(X[keep[ix]]), torch.from_numpy(y[ix])
+        if to_dev is not None:
+            xb, yb = xb.to(to_dev), yb.to(to_dev)
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(model(xb), yb)
+        loss.backward()
+        opt.step()
+    last = float(loss.item())
+    sync(); t_ep = time.perf_counter() - t0
+    return t_fwd, t_ep, last
+
+
+def config1_leg(dev):
+    """configs[0] on both sides in the same run: the CPU port and this module (exact tier) on the repo's own windows."""
+    from oracle.torch_ref import RefEEGLSTM
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    X, keep, y = config1_labels()
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    ref = RefEEGLSTM()
+    ref.load_state_dict(load_checkpoint(), strict=True)
+    cf, ce, cl = config1_epoch(ref, X, keep, y, None)
+    torch.manual_seed(0)
+    m = EEG_LSTM().to(dev)
+    m.load_state_dict(load_checkpoint(), strict=True)
+    config1_epoch(m, X, keep, y, dev)                      # warm-up (allocator, weight packs)
+    m.load_state_dict(load_checkpoint(), strict=True)
+    gf, ge, gl = config1_epoch(m, X, keep, y, dev)
+    return {"workload": "configs[0]: fp32 forward over the 324 EEG_data_collection windows + one training epoch over the 179 "
+                        "food / water / backgroundnoise windows (batch 32, CE, Adam lr 1e-3), shipped .pth weights",
+            "cpu": {"forward_ms": 1e3 * cf, "forward_windows_per_s": 324 / cf, "epoch_ms": 1e3 * ce,
+                    "epoch_windows_per_s": len(keep) / ce, "cores": torch.get_num_threads(), "kind": "port", "last_loss": cl},
+            "gpu": {"forward_ms": 1e3 * gf, "forward_windows_per_s": 324 / gf, "epoch_ms": 1e3 * ge,
+                    "epoch_windows_per_s": len(keep) / ge, "tier": "exact (fp32 contract)", "last_loss": gl,
+                    "timing": "host wall clock incl. H2D / D2H and optimizer (6 steps of <= 32 windows: launch-latency bound)"}}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -224,6 +317,19 @@ def time_steps(fn, steps, warmup, world, dev):
     return max_over_ranks(e0.elapsed_time(e1), world, dev)      # ms, max over ranks
 
 
+def h2d_ceiling(host, dev, world, reps=3):
+    """Platform ceiling of the e2e leg: every rank copies its pinned 819 MB step input with plain cudaMemcpyAsync at the
+    same time (barrier, CUDA events, max over ranks).  Aggregate GB/s = world x bytes / time."""
+    buf = torch.empty_like(host, device=dev)
+    def cp():
+        buf.copy_(host, non_blocking=True)
+    ms = time_steps(cp, reps, 1, world, dev) / reps
+    del buf
+    return {"per_gpu_gbs": host.numel() * 4 / (ms * 1e-3) / 1e9, "aggregate_gbs": world * host.numel() * 4 / (ms * 1e-3) / 1e9,
+            "ms_per_copy": ms, "bytes_per_gpu": host.numel() * 4, "concurrent_ranks": world,
+            "what": "all ranks copy their pinned step input at once (cudaMemcpyAsync, one call), max over ranks"}
+
+
 def run_gpu_arm(args):
     from neural_speech_decoding_b200 import _lib, ops
     from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
@@ -233,6 +339,7 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     peaks = measured_peaks()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
 
     model = EEG_LSTM().to(dev).eval()
     model.load_state_dict(load_checkpoint(), strict=True)
@@ -265,19 +372,26 @@ def run_gpu_arm(args):
                 "e2e_value": world * n_win * e_steps / (ms_e2e * 1e-3), "e2e_ms_per_step": ms_e2e / e_steps,
                 "launches": launches, "clocks": clocks}
 
-    bf = measure(torch.bfloat16)                    # tensor-core tier (headline)
-    fp = measure(torch.float32)                     # exact tier
+    fp = measure(torch.float32)                     # fp32-contract tier: the headline (the reference computes in fp32)
+    h16 = measure(torch.bfloat16)                   # 16-bit tensor-core tier (fp16 operands, 2e-2 contract): named extra
+    ceiling = h2d_ceiling(host, dev, world)
 
     # ---- dominant kernels alone, CUDA events on the launching stream -------------------------------
     reps = max(3, min(args.steps, 10))
+    n_full, n_short = sms * 128, sms * 32           # one full round of 128-window tiles / one round of row-replicated quarter tiles
     with torch.inference_mode():
-        model.compute_dtype = torch.bfloat16
-        xt16 = ops.window_zscore(x_flat, T, T, False, True, ops.NA_F16, ops.TC_TILE)
-        packed_tc, head = model._packed_tc(), model._head_params()
-        ms_tc_tm = time_steps(lambda: ops.decoder_infer_bf16(xt16, packed_tc, head, n_win, True), reps, 2, 1, dev) / reps
-        ms_tc = time_steps(lambda: ops.decoder_infer_bf16_x32(x_flat, packed_tc, head, True), reps, 2, 1, dev) / reps
+        head = model._head_params()
         packed_x3 = model._packed_x3()
         ms_x3 = time_steps(lambda: ops.decoder_infer_x3(x_flat, packed_x3, head, True), reps, 2, 1, dev) / reps
+        ms_x3_full = time_steps(lambda: ops.decoder_infer_x3(x_flat[:n_full], packed_x3, head, True), reps, 2, 1, dev) / reps
+        ms_x3_short = time_steps(lambda: ops.decoder_infer_x3(x_flat[:n_short], packed_x3, head, True), reps, 2, 1, dev) / reps
+        model.compute_dtype = torch.bfloat16
+        xt16 = ops.window_zscore(x_flat, T, T, False, True, ops.NA_F16, ops.TC_TILE)
+        packed_tc = model._packed_tc()
+        ms_tc_tm = time_steps(lambda: ops.decoder_infer_bf16(xt16, packed_tc, head, n_win, True), reps, 2, 1, dev) / reps
+        ms_tc = time_steps(lambda: ops.decoder_infer_bf16_x32(x_flat, packed_tc, head, True), reps, 2, 1, dev) / reps
+        ms_tc_full = time_steps(lambda: ops.decoder_infer_bf16_x32(x_flat[:n_full], packed_tc, head, True), reps, 2, 1, dev) / reps
+        ms_tc_short = time_steps(lambda: ops.decoder_infer_bf16_x32(x_flat[:n_short], packed_tc, head, True), reps, 2, 1, dev) / reps
         ms_pack16 = time_steps(lambda: ops.window_zscore(x_flat, T, T, False, True, ops.NA_F16, ops.TC_TILE), reps, 2, 1, dev) / reps
         ms_z = time_steps(lambda: ops.window_zscore(x_flat, T, T, True, False, False), reps, 2, 1, dev) / reps
         del xt16
@@ -285,11 +399,11 @@ def run_gpu_arm(args):
         xt = ops.window_zscore(x_flat, T, T, False, True, False)
         h0 = ops.lstm_layer_fwd(xt, packed[0][0], packed[0][1], None, 1.0, False)[0]
         del xt
-        ms_l1 = time_steps(lambda: ops.lstm_layer_fwd(h0, packed[1][0], packed[1][1], None, 1.0, False)[0], reps, 2, 1, dev) / reps
+        ms_l1 = time_steps(lambda: ops.lstm_layer_fwd(h0, packed[1][0], packed[1][1], None, 1.0, False)[0], 3, 1, 1, dev) / 3
         del h0
+    x3_tflops = FWD_FLOPS_PER_WINDOW * n_win / (ms_x3 * 1e-3) / 1e12
     tc_tflops = FWD_FLOPS_PER_WINDOW * n_win / (ms_tc * 1e-3) / 1e12
     l1_tflops = L1_KERNEL_FLOPS_PER_WINDOW * n_win / (ms_l1 * 1e-3) / 1e12
-    tile_rounds = -(-(n_win // 128) // 148)
 
     # ---- single-window latency: what one `SimplePredictor.predict`-style call costs (numpy [625,8] in -> probs out) ----
     def one_window_latency(dtype):
@@ -304,9 +418,9 @@ def run_gpu_arm(args):
                 p = p[0].cpu().numpy()
                 lat.append((time.perf_counter() - t0) * 1e3)
         return statistics.median(lat[10:])
-    lat_exact, lat_bf16 = one_window_latency(torch.float32), one_window_latency(torch.bfloat16)
+    lat_exact, lat_h16 = one_window_latency(torch.float32), one_window_latency(torch.bfloat16)
 
-    # ---- CSV ingestion kernel: 4,096 files of the collector's format, HBM-bound byte work ------
+    # ---- CSV ingestion kernel: 4,096 files of the collector's format, byte work ------------------
     import io
     from neural_speech_decoding_b200 import ingest
     files = []
@@ -323,15 +437,16 @@ def run_gpu_arm(args):
     csv_bytes = int(off[-1]) + len(files) * T * C * 4
     del text_dev
 
-    # ---- collector-side filter chain: all 40,960 windows of the step, HBM-bound -----------------
+    # ---- collector-side filter chain: all 40,960 windows of the step ----------------------------
     from neural_speech_decoding_b200 import filters
     ms_filt = time_steps(lambda: filters.filter_windows(x_flat), 3, 1, 1, dev) / 3
-    filt_bytes = n_win * C * T * (4 + 4 + 7 * 16)
+    filt_bytes = n_win * C * T * (4 + 4)            # algorithmic: one fp32 read + one fp32 write per sample
+    filt_flops = n_win * C * T * filters.chain_fma_per_sample() * 2
     torch.cuda.empty_cache()
 
     # ---- measured CUDA-core fp32 peak (FFMA probe) -------------------------------------------------
     out = torch.zeros(4, device=dev)
-    blocks, iters = 148 * 8, 1 << 16
+    blocks, iters = sms * 8, 1 << 16
     def probe():
         _lib.call("na_ffma_probe", out.data_ptr(), blocks, iters, torch.cuda.current_stream().cuda_stream)
     ms_probe = time_steps(probe, 3, 2, 1, dev) / 3
@@ -341,102 +456,121 @@ def run_gpu_arm(args):
     if not args.no_train:
         train = train_leg(args, world, rank, dev)
     stress = stress_leg(dev, peaks) if (rank == 0 and not args.no_stress) else None
+    config1 = config1_leg(dev) if (rank == 0 and not args.no_cpu) else None
 
     if rank != 0:
         return
-    cpu = cpu_arm(3, 1) if world == 1 and not args.no_cpu else None
+    # the CPU arm runs on rank 0 after every timed GPU region (it would perturb the other ranks' host threads otherwise)
+    cpu = cpu_arm(3, 1) if not args.no_cpu else None
+    cpu_train = cpu_train_arm() if (not args.no_cpu and not args.no_train) else None
     peak = peaks["bf16_tflops"]     # the kernel is timed alone -> burst figure
+    e2e_bytes = n_win * T * C * 4
     line = {
-        "metric": "EEG windows/sec (decoder fwd + softmax + 10-trial mean)", "value": bf["value"], "unit": "windows/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": bf["ms_per_step"],
+        "metric": "EEG windows/sec (decoder fwd + softmax + 10-trial mean)", "value": fp["value"], "unit": "windows/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": fp["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16 (tcgen05 operands; fp32 accumulate, cell state, pooling, head)", "data": "synthetic",
+        "dtype": "fp32-accurate (tcgen05: every operand split into fp16 hi + lo, 3 MMAs per product, fp32 accumulate; "
+                 "fp32 cell state / pooling / head; ex2 + rcp activations) -- 1e-5 contract vs the fp32 reference",
+        "data": "synthetic",
         "config": {"workload": "configs[1]: 3-class decoder (T=625,C=8,H=48,L=2) batched inference + run_trials "
                                "10-trial probability averaging, shipped .pth weights",
                    "trials": R, "sessions_per_gpu": B, "windows_per_step_per_gpu": n_win,
                    "l2_policy": "inputs larger than L2 (819 MB fp32 windows per step per GPU)",
                    "parallelism": f"batch-shard x{world}, no collective",
-                   "parity": "tests/test_gpu_bf16.py: logits within 2e-2 of the fp32 reference, argmax identical on the 324 repo windows"},
-        "e2e": {"value": bf["e2e_value"], "unit": "windows/s", "ms_per_step": bf["e2e_ms_per_step"],
-                "h2d_bytes_per_step": n_win * T * C * 4, "d2h_bytes_per_step": B * NC * 4,
+                   "parity": "tests/test_gpu_parity.py: logits within 1e-5 of the fp32 reference, argmax identical on the 324 repo windows"},
+        "e2e": {"value": fp["e2e_value"], "unit": "windows/s", "ms_per_step": fp["e2e_ms_per_step"],
+                "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": B * NC * 4,
                 "api": "neural_speech_decoding_b200.tester.run_trials_batched(pinned host fp32 [R,B,T,C]) -> numpy [B,K]",
+                "h2d_gbs_per_gpu": e2e_bytes / (fp["e2e_ms_per_step"] * 1e-3) / 1e9,
+                "h2d_ceiling": ceiling,
+                "frac_of_h2d_ceiling": (e2e_bytes / (fp["e2e_ms_per_step"] * 1e-3) / 1e9) / ceiling["per_gpu_gbs"],
                 "rank0_cpu_binding": (f"{len(NUMA_BINDING[0])} CPUs local to the GPU (NVML affinity)" if NUMA_BINDING[0] else "none")},
-        "gpu_launches": bf["launches"],
-        "clocks": bf["clocks"],
+        "gpu_launches": fp["launches"],
+        "clocks": fp["clocks"],
         "roofline": {
-            "kernel": "decoder_infer_v2_kernel (tcgen05/TMEM: K1 pack + K2 + K3 + K4 fused, fp32 [B,T,8] windows -> probabilities)",
-            "bound": "tensor", "achieved": tc_tflops, "peak": peak, "unit": "TFLOP/s", "frac": tc_tflops / peak,
+            "kernel": "decoder_infer_x3_kernel (tcgen05/TMEM, fp32-accurate: K1 read + K2 + K3 + K4 fused, fp32 [B,T,8] windows -> probabilities)",
+            "bound": "tensor", "achieved": x3_tflops, "peak": peak, "unit": "TFLOP/s", "frac": x3_tflops / peak,
             "peak_source": peaks["source"] + " cuBLAS bf16 (burst: kernel timed alone)",
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
-            # kernel (profiles/r1_tc2_fused_ncu_full.csv, 40,960 windows), scaled to this launch
-            "traffic": NCU_TRAFFIC_BYTES_40960 * n_win / 40960, "traffic_source": "profiles/r1_tc2_fused_ncu_full.csv",
+            "issued_tflops_3x": 3 * x3_tflops,
+            "traffic": NCU_TRAFFIC_BYTES_40960_X3 * n_win / 40960, "traffic_source": NCU_TRAFFIC_SOURCE_X3,
             "algorithmic_bytes_per_launch": n_win * (T * C * 4 + NC * 8),
             "algorithmic_flops_per_launch": FWD_FLOPS_PER_WINDOW * n_win,
-            "ms_per_launch": ms_tc, "ms_per_launch_time_major_fp16_input": ms_tc_tm,
-            "per_timestep_latency_us": ms_tc * 1e3 / (T * tile_rounds),
-            # the pipe that actually bounds the kernel: 5 tanh.approx per unit, layer and step on the 16-lane/clk/SM MUFU
-            "xu_pipe": xu_pipe(n_win, ms_tc, bf["clocks"]),
-            "note": "MUFU-bound, not tensor-bound: 1250 dependent cell updates per window, 5 tanh per hidden unit and step "
-                    "-> 3,840 MUFU cycles per 128-window step for both layers; the software-pipelined v2 kernel keeps the xu "
-                    "pipe 90.7 % busy on full rounds (ncu); the 40,960-window step is 2.16 rounds, its remainder runs as "
-                    "row-replicated short tiles; 16-bit operands are fp16 (DESIGN.md section 5)",
-            "k1_window_pack": {"kernel": "window_zscore_vec_kernel (fp32 -> time-major bf16)", "bound": "hbm",
+            "ms_per_launch": ms_x3,
+            # north_star's mandatory recurrence metric, both regimes: a full round of 128-window tiles (throughput regime,
+            # every SM sub-partition saturated) and a round of row-replicated 32-window tiles (the dependent-chain latency)
+            "per_timestep_latency_us": {"full_tile_round": ms_x3_full * 1e3 / T, "short_tile_chain": ms_x3_short * 1e3 / T,
+                                        "windows_full_round": n_full, "windows_short_round": n_short,
+                                        "what": "kernel time of one round / 625 steps (layer 0 and layer 1 of a step are software-pipelined)"},
+            # the pipe that actually bounds the kernel: 7 MUFU per cell update (5 ex2 + 2 rcp) on the 16-lane/clk/SM pipe
+            "xu_pipe": mufu_pipe(n_win, ms_x3, fp["clocks"], X3_MUFU_PER_CELL),
+            "note": "MUFU-bound, not tensor-bound: 1250 dependent cell updates per window; the accurate activations cost "
+                    "ex2 + rcp (tanh.approx is 5e-4) -- see DESIGN.md section 6a; the 40,960-window step is 2.16 rounds of 148 tiles, "
+                    "its remainder runs as row-replicated short tiles",
+            "k1_zscore_f32": {"kernel": "window_zscore_vec_kernel (z-score, fp32 in/out)", "bound": "hbm",
+                              "achieved": n_win * T * C * 8 / (ms_z * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                              "unit": "GB/s", "frac": n_win * T * C * 8 / (ms_z * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+            "k1_window_pack": {"kernel": "window_pack16_tmp_kernel (fp32 -> time-major fp16)", "bound": "hbm",
                                "achieved": n_win * T * C * 6 / (ms_pack16 * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                "unit": "GB/s", "frac": n_win * T * C * 6 / (ms_pack16 * 1e-3) / 1e9 / peaks["hbm_gbs"]},
             "csv_parse": {"kernel": "csv_parse_kernel (4,096 files of 625x8 '%.7f' text -> fp32; includes the status D2H check)",
                           "bound": "hbm", "achieved": csv_bytes / (ms_csv * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                           "frac": csv_bytes / (ms_csv * 1e-3) / 1e9 / peaks["hbm_gbs"], "files_per_s": 4096 / (ms_csv * 1e-3)},
-            "filter_chain": {"kernel": "iir_chain_kernel (detrend + 4 zero-phase Butterworth band filters, float64, per (window, channel) series)",
+            "filter_chain": {"kernel": "iir_chain_warp_kernel (detrend + 4 zero-phase Butterworth band filters, float64, one warp per "
+                                       "(window, channel) series, the series lives in registers: no scratch)",
                              "bound": "hbm", "achieved": filt_bytes / (ms_filt * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": filt_bytes / (ms_filt * 1e-3) / 1e9 / peaks["hbm_gbs"], "windows_per_s": n_win / (ms_filt * 1e-3),
+                             "algorithmic_bytes": filt_bytes, "fp64_tflops": filt_flops / (ms_filt * 1e-3) / 1e12,
+                             "note": "8 B of DRAM traffic per sample (algorithmic); the binding pipe is fp64 FMA, not HBM",
                              "parity": "unpinned (BrainFlow absent): tests/test_filters.py vs the scipy restatement"},
-            "k1_zscore_f32": {"kernel": "window_zscore_vec_kernel (z-score, fp32 in/out)", "bound": "hbm",
-                              "achieved": n_win * T * C * 8 / (ms_z * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                              "unit": "GB/s", "frac": n_win * T * C * 8 / (ms_z * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+            "ffma_kernels": {"kernel": "lstm_fwd_h48_kernel<KIN=48> (layer-1 recurrence, exact fp32 FFMA; other shapes / A-B reference)",
+                             "bound": "cuda-core fp32 (FFMA issue)", "achieved": l1_tflops, "peak": ffma_peak,
+                             "unit": "TFLOP/s", "frac": l1_tflops / ffma_peak, "peak_source": "na_ffma_probe measured in this run",
+                             "ms_per_launch": ms_l1},
         },
-        "fp32_exact": {
-            "value": fp["value"], "unit": "windows/s", "ms_per_step": fp["ms_per_step"],
-            "e2e": {"value": fp["e2e_value"], "unit": "windows/s", "ms_per_step": fp["e2e_ms_per_step"]},
-            "gpu_launches": fp["launches"], "clocks": fp["clocks"],
-            "parity": "tests/test_gpu_parity.py: logits and gradients within 1e-5, argmax identical",
-            "kernel": "decoder_infer_x3_kernel (tcgen05, every operand split into fp16 hi + lo: 3 MMAs per product, fp32 accumulate; "
-                      "ex2 / rcp activations): 1.9e-6 of max|logit| vs the reference on the repo's windows",
-            "roofline_x3": {"kernel": "decoder_infer_x3_kernel", "bound": "MUFU (7 per cell update: 5 ex2.approx + 2 rcp.approx, reciprocals combined)",
-                            "achieved": n_win * T * 2 * H * 7 / (ms_x3 * 1e-3) / 1e9,
-                            "peak": 16 * 148 * ((fp["clocks"] or {}).get("sm_mhz") or 1965.0) * 1e-3, "unit": "G MUFU results/s",
-                            "frac": n_win * T * 2 * H * 7 / (ms_x3 * 1e-3) / 1e9 / (16 * 148 * ((fp["clocks"] or {}).get("sm_mhz") or 1965.0) * 1e-3),
-                            "ms_per_launch": ms_x3, "tensor_tflops_3x": 3 * FWD_FLOPS_PER_WINDOW * n_win / (ms_x3 * 1e-3) / 1e12},
-            "ffma_kernels": "the FFMA recurrence kernels (ops.EXACT_TC = False; training forward, other shapes): roofline below",
-            "roofline": {"kernel": "lstm_fwd_h48_kernel<KIN=48> (layer-1 recurrence, exact fp32 FFMA)",
-                         "bound": "cuda-core fp32 (FFMA issue)", "achieved": l1_tflops, "peak": ffma_peak,
-                         "unit": "TFLOP/s", "frac": l1_tflops / ffma_peak,
-                         "peak_source": "na_ffma_probe measured in this run", "ms_per_launch": ms_l1,
-                         "per_timestep_latency_us": ms_l1 * 1e3 / T},
+        "fp16_tier": {
+            "what": "north_star's \"bf16 path\": 16-bit tensor-core tier, 2e-2 contract (secondary; NOT like-for-like with the fp32 reference)",
+            "dtype": "IEEE fp16 operands (x / 16, h, weights), fp32 accumulate / cell state / pooling / head; tanh.approx activations",
+            "value": h16["value"], "unit": "windows/s", "ms_per_step": h16["ms_per_step"],
+            "e2e": {"value": h16["e2e_value"], "unit": "windows/s", "ms_per_step": h16["e2e_ms_per_step"]},
+            "gpu_launches": h16["launches"], "clocks": h16["clocks"],
+            "vs_cpu": (h16["value"] / world / cpu["windows_per_s"]) if cpu else None,
+            "parity": "tests/test_gpu_bf16.py: logits within 2e-2 of the fp32 reference, argmax identical on the 324 repo windows",
+            "roofline": {"kernel": "decoder_infer_v2_kernel", "bound": "tensor", "achieved": tc_tflops, "peak": peak, "unit": "TFLOP/s",
+                         "frac": tc_tflops / peak, "ms_per_launch": ms_tc, "ms_per_launch_time_major_fp16_input": ms_tc_tm,
+                         "traffic": NCU_TRAFFIC_BYTES_40960 * n_win / 40960, "traffic_source": "profiles/r1_tc2_fused_ncu_full.csv",
+                         "per_timestep_latency_us": {"full_tile_round": ms_tc_full * 1e3 / T, "short_tile_chain": ms_tc_short * 1e3 / T},
+                         "xu_pipe": mufu_pipe(n_win, ms_tc, h16["clocks"], V2_MUFU_PER_CELL)},
         },
     }
-    line["single_window_latency_ms"] = {"exact_fp32": lat_exact, "bf16": lat_bf16,
+    line["single_window_latency_ms"] = {"exact_fp32": lat_exact, "fp16_tier": lat_h16,
                                          "what": "host numpy [625,8] -> H2D -> decoder forward + softmax -> D2H probabilities, median of 50 "
                                                  "(reference on its CPU: ~13.5 ms per window, SURVEY 8a12)"}
     if cpu:
         line["cpu_baseline"] = {"value": cpu["windows_per_s"], "unit": "windows/s", "cores": cpu["cores"],
                                 "kind": "port", "sample": cpu["sample"]}
     if train:
+        if cpu_train:
+            train["cpu_baseline"] = cpu_train
+            train["fp32_exact"]["vs_cpu"] = train["fp32_exact"]["value"] / world / cpu_train["value"]
         line["train"] = train
     if stress:
         line["stress"] = stress
+    if config1:
+        line["config1"] = config1
     print(json.dumps(line), flush=True)
 
 
-def xu_pipe(n_win, ms_tc, clocks):
-    """The pipe that actually bounds the headline kernel: 5 tanh.approx per hidden unit, layer and step on the
-    16-results/clk/SM MUFU pipe (measured: scripts/ubench/mufu_rate.cu, 31.4 results/ns/SM at 1.965 GHz)."""
+X3_MUFU_PER_CELL, V2_MUFU_PER_CELL = 7, 5
+
+
+def mufu_pipe(n_win, ms, clocks, per_cell):
+    """The pipe that actually bounds the decoder kernels: ``per_cell`` MUFU results per hidden unit, layer and step on the
+    16-results/clk/SM transcendental pipe (measured: scripts/ubench/mufu_rate.cu, 31.4 results/ns/SM at 1.965 GHz)."""
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    ops_ = n_win * T * 2 * H * 5
-    ach, peak = ops_ / (ms_tc * 1e-3) / 1e9, 16 * 148 * mhz * 1e-3
+    ops_ = n_win * T * 2 * H * per_cell
+    ach, peak = ops_ / (ms * 1e-3) / 1e9, 16 * 148 * mhz * 1e-3
     return {"bound": "MUFU (transcendental pipe): 16 results/clk/SM x 148 SMs x SM clock under load", "achieved": ach, "peak": peak,
-            "unit": "G tanh/s", "frac": ach / peak, "sm_mhz": mhz,
-            "ncu": "sm__inst_executed_pipe_xu 90.7 % of peak on full 148-tile rounds (profiles/r1_tc2_infer_ncu_full.csv), "
-                   "87.3 % over the 2.16-round benchmark launch (profiles/r1_tc2_fused_ncu_full.csv)"}
+            "unit": "G MUFU results/s", "frac": ach / peak, "sm_mhz": mhz, "mufu_per_cell": per_cell}
 
 
 def stress_leg(dev, peaks):
@@ -463,10 +597,26 @@ def stress_leg(dev, peaks):
         # the exact-fp32 tier (generic kernels) on a bounded slice, for the ratio
         m.compute_dtype = torch.float32
         ms32 = time_steps(lambda: m.decode(x[:256], want_probs=True), 1, 1, 1, dev)
+    # ---- configs[4] "... and BPTT backward": one train step (fwd + BPTT + Adam) at the stress shape -----------------
+    Bt = 256
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    yt = torch.randint(0, NC, (Bt,), generator=torch.Generator(device="cpu").manual_seed(5)).to(dev)
+    def tstep():
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(m(x[:Bt]), yt).backward()
+        opt.step()
+    ms_t = time_steps(tstep, 1, 1, 1, dev)
+    fb = 3 * flops - 2 * Ts * 4 * Hs * C                   # fwd + bwd, no dX of layer 0
+    train = {"value": Bt / (ms_t * 1e-3), "unit": "windows/s", "ms_per_step": ms_t, "batch": Bt,
+             "tier": "exact fp32 (generic FFMA forward-with-save + fused BPTT + time-parallel weight gradients)",
+             "achieved_tflops": fb * Bt / (ms_t * 1e-3) / 1e12,
+             "parity": "tests/test_gpu_parity.py::test_stress_shape_h192 (gradients within 1e-5 of the fp64 truth)"}
     del x
     torch.cuda.empty_cache()
     tf = flops * Bs / (ms_k * 1e-3) / 1e12
     return {"workload": "configs[4]: EEG_LSTM(hidden_size=192), T=2500, C=8, 18,944 synthetic windows, eval forward",
+            "train": train,
             "value": Bs / (ms * 1e-3), "unit": "windows/s", "ms_per_pass": ms,
             "kernel": "decoder_infer_wide_kernel<4> (tcgen05; activations resident, weights streamed by TMA from L2)",
             "ms_per_launch": ms_k, "per_timestep_latency_us": ms_k * 1e3 / Ts,
@@ -474,7 +624,7 @@ def stress_leg(dev, peaks):
             "frac_of_bf16_sustained_peak": tf / peaks["bf16_tflops_sustained"], "frac_of_bf16_burst_peak": tf / peaks["bf16_tflops"],
             "fp32_exact_windows_per_s": 256 / (ms32 * 1e-3),
             "parity": "tests/test_gpu_bf16.py::test_wide_*: reference golden (H=192) and the exact tier, 2e-2 contract",
-            "note": "training at this shape runs on the exact-fp32 generic tier (no tensor-core BPTT for H > 48 yet)"}
+            "note": "training at this shape runs on the exact-fp32 generic tier (no tensor-core BPTT for H > 48)"}
 
 
 def train_leg(args, world, rank, dev):
@@ -509,6 +659,30 @@ def train_leg(args, world, rank, dev):
                 "per_gpu_batch": per_gpu, "micro_batch": micro, "steps": steps,
                 "achieved_tflops_per_gpu": FWDBWD_FLOPS_PER_WINDOW * wps / world / 1e12}
 
+    def dp_equivalence(dtype):
+        """N-rank DP gradient (each rank its shard, one NCCL all-reduce) == the same global batch on ONE rank.
+        Eval-mode autograd (no noise) so both sides are deterministic; executed inside the multi-GPU bench run because
+        the driver's pytest box has one GPU."""
+        import torch.distributed as dist
+        nb = 64 * world
+        xg = synth_windows(nb, seed=4242).to(dev)                       # same global batch on every rank
+        yg = torch.randint(0, NC, (nb,), generator=torch.Generator(device="cpu").manual_seed(7)).to(dev)
+        def grads(xs, ys, ws):
+            torch.manual_seed(0)
+            m2 = EEG_LSTM().to(dev)
+            m2.load_state_dict(load_checkpoint(), strict=True)
+            m2.eval()
+            m2.compute_dtype = dtype
+            tr = DataParallelTrainer(m2, torch.optim.SGD(m2.parameters(), lr=0.0), world_size=ws)
+            tr.backward_only([(xs, ys)], global_batch=nb)
+            return tr.bucket.flat.clone()
+        sl = slice(rank * 64, rank * 64 + 64)
+        g_dp = grads(xg[sl], yg[sl], world)
+        g_one = grads(xg, yg, 1)
+        err = ((g_dp - g_one).abs().max() / g_one.abs().max()).reshape(1)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        return float(err.item())
+
     steps = max(1, min(args.steps, 3))
     tc = run(torch.bfloat16, args.train_batch, args.train_micro, steps)
     tc.update({"dtype": "fp16 tensor-core operands (tcgen05), fp32 accumulate / cell state / weight gradients",
@@ -517,8 +691,16 @@ def train_leg(args, world, rank, dev):
                "parity": "tests/test_gpu_bf16.py: gradients within 2e-2 of the fp64 oracle",
                "frac_of_bf16_sustained_peak": tc["achieved_tflops_per_gpu"] / measured_peaks()["bf16_tflops_sustained"]})
     fp = run(torch.float32, min(args.train_batch, 8192 * world), 8192, min(steps, 2))
-    tc["fp32_exact"] = {k: fp[k] for k in ("value", "unit", "ms_per_step", "global_batch", "micro_batch")}
+    tc["fp32_exact"] = {k: fp[k] for k in ("value", "unit", "ms_per_step", "global_batch", "micro_batch", "achieved_tflops_per_gpu")}
     tc["fp32_exact"]["parity"] = "tests/test_gpu_parity.py: gradients within 1e-5"
+    if world > 1:
+        e16, e32 = dp_equivalence(torch.bfloat16), dp_equivalence(torch.float32)
+        tc["dp_equivalence"] = {"what": f"max|g_DP({world} ranks, NCCL all-reduce) - g_single| / max|g| over the flat gradient bucket, "
+                                        f"global batch {64 * world}, eval-mode autograd",
+                                "fp16_tier": e16, "fp32_exact": e32, "tolerance": {"fp16_tier": 1e-4, "fp32_exact": 1e-5},
+                                "ok": bool(e16 < 1e-4 and e32 < 1e-5)}
+        if not tc["dp_equivalence"]["ok"] and rank == 0:
+            print(f"WARNING: DP equivalence outside tolerance: {tc['dp_equivalence']}", file=sys.stderr)
     return tc
 
 

@@ -69,6 +69,12 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Input range of the 16-bit formats: raw EEG can carry DC offsets of 1e5 uV, beyond fp16's 65,504.  Every fp16 copy of
+// the input (K1 with out_dtype NA_F16, the fused producers of the tensor-core kernels) stores x * 2^-4 and the packed
+// layer-0 W_ih carries the 2^4 -- both exact powers of two, so nothing changes numerically inside the normal range,
+// samples up to 1e6 stay finite, and the layer-0 weight gradient is rescaled by 2^4 where it is reduced.
+constexpr float kF16InScale = 0.0625f, kF16InScaleInv = 16.0f;
+
 // nn.RReLU eval slope: torch evaluates (lower+upper)/2 in double, then casts to the tensor dtype
 constexpr float kRReluEvalSlope = (float)((1.0 / 8.0 + 1.0 / 3.0) / 2.0);
 constexpr float kLnEps = 1e-5f;                                        // nn.LayerNorm default

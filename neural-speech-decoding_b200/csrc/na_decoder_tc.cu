@@ -81,7 +81,7 @@ __global__ void pack_decoder_bf16_kernel(const float* __restrict__ w_ih0, const 
         if (!l1) {
             const float b = b_ih0[col] + b_hh0[col];
             const float bh = val16_to_float(val16(b));
-            if (k < 8) v = w_ih0[col * 8 + k];
+            if (k < 8) v = kF16InScaleInv * w_ih0[col * 8 + k];      // x is stored as x / 16 (na_common.cuh)
             else if (k == 8) v = bh;
             else if (k == 9) v = b - bh;
             else if (k >= 16) v = w_hh0[col * kH + (k - 16)];

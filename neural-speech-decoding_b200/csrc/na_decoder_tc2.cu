@@ -98,7 +98,7 @@ __global__ void pack_decoder_v2_kernel(const float* __restrict__ w_ih0, const fl
         if (!l1) {
             const float b = gs * (b_ih0[col] + b_hh0[col]);
             const float bh = val16_to_float(val16(b));
-            if (k < 8) v = gs * w_ih0[col * 8 + k];
+            if (k < 8) v = gs * kF16InScaleInv * w_ih0[col * 8 + k];      // x is stored as x / 16
             else if (k == 8) v = bh;
             else if (k == 9) v = b - bh;
             else if (k >= 16) v = hs * w_hh0[col * kH + (k - 16)];
@@ -439,8 +439,8 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
                                 v0 = *reinterpret_cast<const float4*>(&S.xf32[t % kV2XStages][row][0]);
                                 v1 = *reinterpret_cast<const float4*>(&S.xf32[t % kV2XStages][row][4]);
                             }
-                            const uint32_t p0 = pack_val(v0.x, v0.y), p1 = pack_val(v0.z, v0.w);
-                            const uint32_t p2 = pack_val(v1.x, v1.y), p3 = pack_val(v1.z, v1.w);
+                            const uint32_t p0 = pack_val(kF16InScale * v0.x, kF16InScale * v0.y), p1 = pack_val(kF16InScale * v0.z, kF16InScale * v0.w);
+                            const uint32_t p2 = pack_val(kF16InScale * v1.x, kF16InScale * v1.y), p3 = pack_val(kF16InScale * v1.z, kF16InScale * v1.w);
                             for (int rep = 0; rep < R; ++rep) st_shared_v4(S.x[s] + (rep * (kRows / R) + row) * 16, p0, p1, p2, p3);
                         }
                     }

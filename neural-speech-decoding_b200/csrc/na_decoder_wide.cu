@@ -111,7 +111,7 @@ __global__ void pack_wide_kernel(const float* __restrict__ w_ih0, const float* _
                 if (s == 0) {
                     const float b = gs * (b_ih0[row] + b_hh0[row]);
                     const float bh = val16_to_float(val16(b));
-                    if (k < 8) v = gs * w_ih0[row * 8 + k];
+                    if (k < 8) v = gs * kF16InScaleInv * w_ih0[row * 8 + k];      // x is stored as x / 16
                     else if (k == 8) v = bh;
                     else if (k == 9) v = b - bh;
                 } else v = hs * w_hh0[row * H + (s - 1) * 16 + k];

@@ -2,11 +2,23 @@
 // Per (window, channel) series: detrend(CONSTANT), then for every filter of the chain a "zero phase" application
 // = forward DirectFormII biquad cascade, time reversal, the same cascade again (BrainFlow re-uses the filter object,
 // so by default the state of the forward pass is carried into the backward pass), reversal; finally np.round(., d).
+// float64 like BrainFlow.
 //
-// One thread per series, float64 like BrainFlow.  An IIR is serial in time, so the parallelism is the B x C series;
-// the 2 x nfilt passes read and write the series in a per-CTA tiled [T][128 series] scratch (coalesced, contiguous per CTA),
-// the first pass reads the fp32 window directly, the last one writes the fp32 result.  HBM-bound byte work:
-// algorithmic bytes per series = T x (4 + 4 + (2 nfilt - 1) x 16).
+// iir_chain_warp_kernel (T <= 2560, the default): ONE WARP per series and the series never leaves the register file.
+// Lane l owns the L = ceil(T / 32) consecutive samples [l L, l L + L).  A biquad is a linear recurrence on the state
+// s = (w[t-1], w[t-2]), s' = A s + (v, 0), so a section pass over the whole series is
+//   (1) every lane runs the recurrence over its own samples from a ZERO state (2 FMA per sample) -> its end state e_l;
+//   (2) a warp scan S_l = A^L S_{l-1} + e_l with the constant matrices A^(L 2^j) (5 shuffle rounds; the matrices are
+//       computed once per launch by repeated squaring) gives every lane its true incoming state;
+//   (3) every lane re-runs the section over its samples from that state -- the same arithmetic, in the same order, as
+//       the serial DirectFormII loop -- and overwrites its samples with the outputs.
+// The time-reversed pass is the same with the lane order reversed.  7 FMA per sample and section pass instead of 5, but
+// the dependent chain is L = 20 samples instead of 625, there is no scratch at all, and DRAM traffic is the algorithmic
+// 8 B per sample (one fp32 read, one fp32 write): the bound is the fp64 FMA pipe.  For C = 8 a CTA is one window: it is
+// loaded and stored through shared memory with fully coalesced 16-byte accesses.
+//
+// iir_chain_kernel (longer series): one thread per series, the 2 x nfilt passes go through a per-CTA tiled
+// [T][128 series] scratch.
 // PARITY UNPINNED (brainflow==5.19.0 is absent from this image): checked against oracle/filter_chain.py, a scipy
 // restatement of BrainFlow's published algorithm.
 #include "na_common.cuh"
@@ -126,6 +138,206 @@ iir_chain_kernel(const float* __restrict__ x, float* __restrict__ y, double* __r
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// warp-per-series kernel
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kIirWarps = 8;                 // series per CTA (for C == 8: the 8 channels of one window)
+
+struct Mat2 { double a, b, c, d; };          // [[a, b], [c, d]]
+__device__ __forceinline__ Mat2 mat_mul(const Mat2& x, const Mat2& y) {
+    return Mat2{x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d};
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// One section pass over the register-resident series.  dir = +1: ascending time (lane 0 first), -1: descending (lane `last`
+// first).  (w1, w2) in: the state the pass starts from (warp-uniform); out: the state after the last sample processed.
+template <int LT>
+__device__ __forceinline__ void section_pass(double (&v)[LT], const int n, const int lane, const int last, const int dir,
+                                             const double b0, const double b1, const double b2, const double a1, const double a2,
+                                             const double* __restrict__ pm,       // 5 x (a, b, c, d): A^(L 2^j)
+                                             double& w1, double& w2) {
+    const bool first = dir > 0 ? lane == 0 : lane == last;         // the block that is processed first carries the initial state
+    // (1) end state of this lane's block from a zero state (the first block: from the true initial state)
+    double e1 = first ? w1 : 0.0, e2 = first ? w2 : 0.0;
+#pragma unroll
+    for (int jj = 0; jj < LT; ++jj) {
+        const int j = dir > 0 ? jj : LT - 1 - jj;
+        if (j < n) {
+            const double w = v[j] - a1 * e1 - a2 * e2;
+            e2 = e1;
+            e1 = w;
+        }
+    }
+    if (lane > last) { e1 = 0.0; e2 = 0.0; }
+    // (2) scan over the blocks in processing order; every block that is ever multiplied through is a full block of L samples
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int d = 1 << j;
+        const int src = dir > 0 ? lane - d : lane + d;
+        const double f1 = shfl_d(e1, src & 31), f2 = shfl_d(e2, src & 31);
+        const bool take = dir > 0 ? (lane >= d && lane <= last) : (lane + d <= last);
+        if (take) {
+            e1 += pm[4 * j] * f1 + pm[4 * j + 1] * f2;
+            e2 += pm[4 * j + 2] * f1 + pm[4 * j + 3] * f2;
+        }
+    }
+    // incoming state of this lane = end state of the block processed just before it
+    const int prev = dir > 0 ? lane - 1 : lane + 1;
+    double s1 = shfl_d(e1, prev & 31), s2 = shfl_d(e2, prev & 31);
+    if (first) { s1 = w1; s2 = w2; }
+    // (3) the real pass
+#pragma unroll
+    for (int jj = 0; jj < LT; ++jj) {
+        const int j = dir > 0 ? jj : LT - 1 - jj;
+        if (j < n) {
+            const double w = v[j] - a1 * s1 - a2 * s2;
+            v[j] = b0 * w + b1 * s1 + b2 * s2;
+            s2 = s1;
+            s1 = w;
+        }
+    }
+    // state after the last processed sample: ascending -> lane `last`, descending -> lane 0
+    const int fin = dir > 0 ? last : 0;
+    w1 = shfl_d(s1, fin);
+    w2 = shfl_d(s2, fin);
+}
+
+template <int LT>
+__global__ void __launch_bounds__(kIirWarps * 32)
+iir_chain_warp_kernel(const float* __restrict__ x, float* __restrict__ y, const double* __restrict__ coef,
+                      const int* __restrict__ nsec, int nfilt, int64_t S, int T, int C, int detrend, int round_decimals,
+                      int carry_state) {
+    __shared__ double s_coef[kIirMaxF * kIirMaxS * 5];
+    __shared__ double s_pm[kIirMaxF * kIirMaxS * 20];
+    __shared__ int s_nsec[kIirMaxF];
+    extern __shared__ __align__(16) float s_io[];                  // C == 8: [8 channels][32 lanes][L + 1] staging
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = (T + 31) / 32;                                   // samples per lane (<= LT)
+    int total = 0;
+    for (int f = 0; f < nfilt; ++f) total += nsec[f];
+    for (int i = tid; i < total * 5; i += blockDim.x) s_coef[i] = coef[i];
+    if (tid < nfilt) s_nsec[tid] = nsec[tid];
+    if (tid < total) {                                             // A^(L 2^j), j = 0..4, by repeated squaring
+        const double a1 = coef[tid * 5 + 3], a2 = coef[tid * 5 + 4];
+        Mat2 base{-a1, -a2, 1.0, 0.0}, acc{1.0, 0.0, 0.0, 1.0};
+        for (int e = L; e > 0; e >>= 1) {
+            if (e & 1) acc = mat_mul(acc, base);
+            base = mat_mul(base, base);
+        }
+        for (int j = 0; j < 5; ++j) {
+            double* o = s_pm + tid * 20 + 4 * j;
+            o[0] = acc.a; o[1] = acc.b; o[2] = acc.c; o[3] = acc.d;
+            acc = mat_mul(acc, acc);
+        }
+    }
+    const int64_t s = (int64_t)blockIdx.x * kIirWarps + warp;
+    const bool coop = (C == kIirWarps);                             // CTA = one window: coalesced staging through shared memory
+    const int stride = L + 1;                                      // odd-ish padding: lanes hit distinct banks
+    if (coop) {
+        const int64_t b = blockIdx.x;
+        const float4* src = reinterpret_cast<const float4*>(x + b * T * 8);
+        for (int i = tid; i < T * 2; i += blockDim.x) {
+            const float4 q = src[i];
+            const int t = i >> 1, c0 = (i & 1) * 4;
+            const int ln = t / L, j = t - ln * L;
+            s_io[((c0 + 0) * 32 + ln) * stride + j] = q.x;
+            s_io[((c0 + 1) * 32 + ln) * stride + j] = q.y;
+            s_io[((c0 + 2) * 32 + ln) * stride + j] = q.z;
+            s_io[((c0 + 3) * 32 + ln) * stride + j] = q.w;
+        }
+    }
+    __syncthreads();
+    const bool active = s < S;
+    const int64_t b = active ? s / C : 0;
+    const int c = active ? (int)(s % C) : 0;
+    const int t0 = lane * L;
+    const int n = active ? max(0, min(L, T - t0)) : 0;
+    const int last = (T - 1) / L;                                  // last lane that owns samples
+    double v[LT];
+#pragma unroll
+    for (int j = 0; j < LT; ++j) {
+        v[j] = 0.0;
+        if (j < n) v[j] = coop ? (double)s_io[(warp * 32 + lane) * stride + j] : (double)x[(b * T + t0 + j) * C + c];
+    }
+    if (detrend) {
+        double part = 0.0;
+#pragma unroll
+        for (int j = 0; j < LT; ++j) part += v[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        const double mean = part / (double)T;
+#pragma unroll
+        for (int j = 0; j < LT; ++j) if (j < n) v[j] -= mean;
+    }
+    int cbase = 0;
+    for (int f = 0; f < nfilt; ++f) {
+        const int ns = s_nsec[f];
+        double w1[kIirMaxS], w2[kIirMaxS];
+#pragma unroll
+        for (int k = 0; k < kIirMaxS; ++k) { w1[k] = 0.0; w2[k] = 0.0; }
+        // forward: the cascade section by section over the whole series (same result as sample by sample: section k only
+        // consumes the finished output of section k-1)
+#pragma unroll
+        for (int k = 0; k < kIirMaxS; ++k)
+            if (k < ns) {
+                const double* cf = s_coef + (cbase + k) * 5;
+                section_pass<LT>(v, n, lane, last, +1, cf[0], cf[1], cf[2], cf[3], cf[4], s_pm + (cbase + k) * 20, w1[k], w2[k]);
+            }
+        if (!carry_state) {
+#pragma unroll
+            for (int k = 0; k < kIirMaxS; ++k) { w1[k] = 0.0; w2[k] = 0.0; }
+        }
+        // the reversed series through the same cascade
+#pragma unroll
+        for (int k = 0; k < kIirMaxS; ++k)
+            if (k < ns) {
+                const double* cf = s_coef + (cbase + k) * 5;
+                section_pass<LT>(v, n, lane, last, -1, cf[0], cf[1], cf[2], cf[3], cf[4], s_pm + (cbase + k) * 20, w1[k], w2[k]);
+            }
+        cbase += ns;
+    }
+    double scale = 1.0;
+    for (int k = 0; k < round_decimals; ++k) scale *= 10.0;
+    if (coop) __syncthreads();                                     // every warp has read its inputs from the staging buffer
+#pragma unroll
+    for (int j = 0; j < LT; ++j) {
+        if (j < n) {
+            double o = v[j];
+            if (round_decimals >= 0) o = rint(o * scale) / scale;  // np.round: multiply, rint, divide
+            const float of = (float)(o == 0.0 ? 0.0 : o);          // the collector also clears negative zero
+            if (coop) s_io[(warp * 32 + lane) * stride + j] = of;
+            else y[(b * T + t0 + j) * C + c] = of;
+        }
+    }
+    if (coop) {
+        __syncthreads();
+        float4* dst = reinterpret_cast<float4*>(y + (int64_t)blockIdx.x * T * 8);
+        for (int i = tid; i < T * 2; i += blockDim.x) {
+            const int t = i >> 1, c0 = (i & 1) * 4;
+            const int ln = t / L, j = t - ln * L;
+            dst[i] = make_float4(s_io[((c0 + 0) * 32 + ln) * stride + j], s_io[((c0 + 1) * 32 + ln) * stride + j],
+                                 s_io[((c0 + 2) * 32 + ln) * stride + j], s_io[((c0 + 3) * 32 + ln) * stride + j]);
+        }
+    }
+}
+
+template <int LT>
+static int launch_iir_warp(const float* x, float* y, const double* coef, const int* nsec, int nfilt, int64_t S, int T, int C,
+                           int detrend, int round_decimals, int carry_state, cudaStream_t st) {
+    const int L = (T + 31) / 32;
+    const size_t smem = C == kIirWarps ? (size_t)kIirWarps * 32 * (L + 1) * sizeof(float) : 0;
+    auto kern = iir_chain_warp_kernel<LT>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, "na_iir_chain: shared memory opt-in failed (%s)", cudaGetErrorString(e));
+    }
+    kern<<<(unsigned)((S + kIirWarps - 1) / kIirWarps), kIirWarps * 32, smem, st>>>(x, y, coef, nsec, nfilt, S, T, C, detrend,
+                                                                                  round_decimals, carry_state);
+    return 0;
+}
+
 }  // namespace na
 
 extern "C" int na_iir_chain(const float* x, float* y, double* scratch, const double* coef, const int* nsec,
@@ -137,8 +349,19 @@ extern "C" int na_iir_chain(const float* x, float* y, double* scratch, const dou
     NA_REQUIRE(nfilt >= 0 && nfilt <= kIirMaxF, NA_EUNSUPPORTED, "na_iir_chain: %lld filters (at most %d)", (long long)nfilt, kIirMaxF);
     NA_REQUIRE(round_decimals <= 22, NA_EINVAL, "na_iir_chain: round_decimals=%d", round_decimals);
     NA_REQUIRE_PTR(x); NA_REQUIRE_PTR(y);
-    NA_REQUIRE(nfilt == 0 || (scratch != nullptr && coef != nullptr && nsec != nullptr), NA_EINVAL, "na_iir_chain: null pointer");
+    NA_REQUIRE(nfilt == 0 || (coef != nullptr && nsec != nullptr), NA_EINVAL, "na_iir_chain: null pointer");
     const int64_t S = B * C;
+    if (T <= 32 * 80) {               // warp-per-series, register-resident: no scratch
+        const int L = (int)((T + 31) / 32);
+        int rc;
+        if (L <= 20) rc = launch_iir_warp<20>(x, y, coef, nsec, (int)nfilt, S, (int)T, (int)C, detrend, round_decimals, carry_state, as_stream(stream));
+        else if (L <= 40) rc = launch_iir_warp<40>(x, y, coef, nsec, (int)nfilt, S, (int)T, (int)C, detrend, round_decimals, carry_state, as_stream(stream));
+        else rc = launch_iir_warp<80>(x, y, coef, nsec, (int)nfilt, S, (int)T, (int)C, detrend, round_decimals, carry_state, as_stream(stream));
+        if (rc) return rc;
+        count_launch();
+        return check_launch("na_iir_chain");
+    }
+    NA_REQUIRE(nfilt == 0 || scratch != nullptr, NA_EINVAL, "na_iir_chain: T > 2560 needs the scratch buffer");
     iir_chain_kernel<<<(unsigned)((S + 127) / 128), 128, 0, as_stream(stream)>>>(x, y, scratch, coef, nsec, (int)nfilt, S, (int)T,
                                                                               (int)C, detrend, round_decimals, carry_state);
     count_launch();

@@ -727,7 +727,7 @@ __global__ void reduce_dw_kernel(const float* __restrict__ partial, int nparts, 
     for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * kN * NW + idx];
     const int j = (n / 32) * 8 + (n % 8), q = (n % 32) / 8, col = q * kH + j;
     if (KI == 8) {
-        if (f < 8) dw_ih[col * 8 + f] = s;
+        if (f < 8) dw_ih[col * 8 + f] = s * kF16InScaleInv;      // the stored input is x / 16
         else if (f == 8) db[col] = s;
         else if (f >= 16) dw_hh[col * kH + (f - 16)] = s;
     } else {
@@ -785,13 +785,18 @@ static int launch_bwd(const void* act_in, const void* h, const float* c, const f
 }  // namespace na
 
 // ---- C ABI ---------------------------------------------------------------------------------------
-extern "C" int64_t na_train_bf16_partial_floats(void) { return (int64_t)148 * 2 * na::tc::kN * 112 + 148 * 52; }
-
 namespace na { namespace tc {
 bool train_fwd_v2_enabled();
 int launch_train_fwd_v2(const void*, const unsigned char*, const unsigned char*, uint64_t, uint32_t, float, void*, void*, float*, void*,
                         float*, const float*, const float*, float*, float*, int64_t, int, int64_t, int, cudaStream_t);
 } }
+
+// scratch floats of na_lstm_bwd_bf16 after its 36,864-byte operand image: per-CTA attention partials [grid][52] then
+// per-CTA weight-gradient partials [grid][192][112]; grid <= the SM count of the current device
+extern "C" int64_t na_train_bf16_partial_floats(void) {
+    const int64_t sms = na::tc::tc_sms();
+    return sms * na::tc::kN * 112 + sms * 52;
+}
 
 extern "C" int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packed, const unsigned char* mask,
                                        uint64_t seed, int64_t thresh16, float drop_scale, void* h0, void* h0d, float* c0, void* h1, float* h1f,
@@ -862,8 +867,8 @@ extern "C" int na_lstm_bwd_bf16(int64_t layer, const void* act_in, const void* h
     const int KI = layer == 0 ? 8 : 48;
     // scratch: [packed_r bf16: 24*96*8*2 B = 36,864 B][partials fp32]
     __nv_bfloat16* packed_r = reinterpret_cast<__nv_bfloat16*>(scratch);
-    float* attn_partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 36864);        // [148][49]
-    float* partial = attn_partial + 148 * 52;
+    float* attn_partial = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 36864);        // [sms][49 (52)]
+    float* partial = attn_partial + (size_t)tc::tc_sms() * 52;
     tc::pack_bwd_r_kernel<<<32, 256, 0, st>>>(w_ih, w_hh, KI, packed_r);
     count_launch();
     // the forward pack holds B0 (8 chunks) then B1 (14 chunks)

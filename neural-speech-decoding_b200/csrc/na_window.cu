@@ -11,8 +11,8 @@ __device__ __forceinline__ void store_vec4(void* y, int64_t vec_idx, float4 v, i
     if (out_dtype == NA_F32) {
         reinterpret_cast<float4*>(y)[vec_idx] = v;
     } else if (out_dtype == NA_F16) {
-        __half2 lo = __floats2half2_rn(v.x, v.y);
-        __half2 hi = __floats2half2_rn(v.z, v.w);
+        __half2 lo = __floats2half2_rn(kF16InScale * v.x, kF16InScale * v.y);
+        __half2 hi = __floats2half2_rn(kF16InScale * v.z, kF16InScale * v.w);
         uint2 p;
         p.x = *reinterpret_cast<uint32_t*>(&lo);
         p.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -172,7 +172,8 @@ window_pack16_tmp_kernel(const float* __restrict__ x, void* __restrict__ y, int6
             if (i < nvec) {
                 uint2 p;
                 if (out_dtype == NA_F16) {
-                    __half2 lo = __floats2half2_rn(v[k].x, v[k].y), hi = __floats2half2_rn(v[k].z, v[k].w);
+                    __half2 lo = __floats2half2_rn(kF16InScale * v[k].x, kF16InScale * v[k].y);
+                    __half2 hi = __floats2half2_rn(kF16InScale * v[k].z, kF16InScale * v[k].w);
                     p.x = *reinterpret_cast<uint32_t*>(&lo); p.y = *reinterpret_cast<uint32_t*>(&hi);
                 } else {
                     __nv_bfloat162 lo = __floats2bfloat162_rn(v[k].x, v[k].y), hi = __floats2bfloat162_rn(v[k].z, v[k].w);
@@ -247,7 +248,7 @@ window_zscore_generic_kernel(const float* __restrict__ x, void* __restrict__ y, 
         }
         const int64_t o = out_tmp ? ((r * Bp + b) * C + c) : ((b * T + r) * C + c);
         if (out_dtype == NA_F32) reinterpret_cast<float*>(y)[o] = v;
-        else if (out_dtype == NA_F16) reinterpret_cast<__half*>(y)[o] = __float2half_rn(v);
+        else if (out_dtype == NA_F16) reinterpret_cast<__half*>(y)[o] = __float2half_rn(kF16InScale * v);
         else reinterpret_cast<__nv_bfloat16*>(y)[o] = __float2bfloat16_rn(v);
     }
 }
@@ -275,11 +276,9 @@ extern "C" int na_window_zscore(const float* x, void* y, int64_t B, int64_t T, i
     if (C == 8 && hop_ok && out_tmp && out_dtype != NA_F32 && Bp % kPackWin == 0 && nvec <= 5 * kWinThreads &&
         (size_t)T * kPackWin * 16 <= 200 * 1024) {
         const size_t smem = (size_t)T * kPackWin * 16;
-        static bool opted = false;
-        if (!opted) {
-            cudaFuncSetAttribute(window_pack16_tmp_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            opted = true;
-        }
+        // the attribute is per device: set it on every launch (cheap), like the other wrappers do
+        cudaError_t e = cudaFuncSetAttribute(window_pack16_tmp_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return fail((int)e, "na_window_zscore: shared memory opt-in failed (%s)", cudaGetErrorString(e));
         window_pack16_tmp_kernel<5><<<(unsigned)(Bp / kPackWin), block, smem, st>>>(x, y, B, T, hop, normalize, Bp, out_dtype);
     } else if (C == 8 && hop_ok && nvec <= 5 * kWinThreads) {
         window_zscore_vec_kernel<2, 5><<<grid, block, 0, st>>>(x, y, B, T, hop, normalize, out_tmp, Bp, out_dtype);

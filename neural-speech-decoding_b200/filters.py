@@ -12,8 +12,9 @@ SURVEY F8 -- so a host that wants recorded-like windows from a raw stream runs t
 
 Design: Butterworth band filters as cascades of second-order sections, computed here from first principles
 (analog prototype poles, Constantinides band transformation with exactly pre-warped band edges, bilinear map) in
-float64; the arithmetic -- 10 serial IIR passes per series -- runs in ``na_iir_chain`` (one thread per
-(window, channel) series, float64, intermediates in an L2/HBM scratch tiled ``[series/128][T][128]``).
+float64; the arithmetic -- 28 serial biquad passes per series -- runs in ``na_iir_chain`` (one WARP per
+(window, channel) series, float64, the series stays in registers: block-parallel recurrence + warp scan, no scratch;
+``csrc/na_iir.cu``).
 
 PARITY UNPINNED: BrainFlow (``brainflow==5.19.0``, C++ ``DSPFilters``) is not installed here, so the oracle
 (``oracle/filter_chain.py``) restates its published algorithm with scipy; two details cannot be confirmed
@@ -109,8 +110,16 @@ def filter_windows(x: torch.Tensor, fs: float = 125.0, chain: Sequence[Tuple[str
     coef_d = torch.from_numpy(coef).to(x.device)
     nsec_d = torch.from_numpy(nsec).to(x.device)
     y = torch.empty_like(x)
-    scratch = torch.empty((T * ((B * C + 127) // 128 * 128),), dtype=torch.float64, device=x.device)
+    # only series longer than 2,560 samples go through the scratch-tiled one-thread-per-series kernel
+    scratch = torch.empty((T * ((B * C + 127) // 128 * 128),), dtype=torch.float64, device=x.device) if T > 2560 else None
     if B * C:
-        _lib.call("na_iir_chain", x.data_ptr(), y.data_ptr(), scratch.data_ptr(), coef_d.data_ptr(), nsec_d.data_ptr(),
-                  len(sos), B, T, C, int(detrend), int(round_decimals), int(carry_state), ops._stream())
+        with torch.cuda.device(x.device):
+            _lib.call("na_iir_chain", x.data_ptr(), y.data_ptr(), ops._ptr(scratch), coef_d.data_ptr(), nsec_d.data_ptr(),
+                      len(sos), B, T, C, int(detrend), int(round_decimals), int(carry_state), ops._stream())
     return y
+
+
+def chain_fma_per_sample(chain: Sequence[Tuple[str, float, float, int]] = COLLECTOR_CHAIN) -> int:
+    """fp64 FMAs per sample of the warp-per-series kernel: every section is passed twice (zero phase), a pass costs
+    2 (zero-state run) + 5 (real run) FMAs per sample."""
+    return sum(2 * order * 7 for _, _, _, order in chain)

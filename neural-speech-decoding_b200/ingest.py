@@ -54,8 +54,9 @@ def parse_csv_bytes(text: torch.Tensor, offsets: torch.Tensor, rows: int = 625, 
         raise RuntimeError("parse_csv_bytes: offsets are not a partition of text")
     out = torch.empty((n, rows, cols), dtype=torch.float32, device=text.device)
     status = torch.empty((n, 2), dtype=torch.int32, device=text.device)
-    _lib.call("na_csv_parse_f32", text.data_ptr(), offsets.data_ptr(), out.data_ptr(), status.data_ptr(), n, rows * cols,
-              max(1, max_bytes), ops._stream())
+    with torch.cuda.device(text.device):
+        _lib.call("na_csv_parse_f32", text.data_ptr(), offsets.data_ptr(), out.data_ptr(), status.data_ptr(), n, rows * cols,
+                  max(1, max_bytes), ops._stream())
     st = status.cpu().numpy()
     bad = np.nonzero((st[:, 0] != rows * cols) | (st[:, 1] != 0))[0]
     if bad.size:

@@ -78,9 +78,10 @@ class EEG_LSTM(nn.Module):
         )
         self.dropout_p = float(dropout)
         self.zscore_input = False
-        # torch.float32: exact tier (FFMA, 1e-5 contract).  torch.bfloat16: tensor-core tier for eval
-        # forwards (tcgen05, bf16 operands / fp32 accumulate, 2e-2 contract); also selected by bf16
-        # inputs or a .bfloat16() module.  Training always runs the exact tier.
+        # torch.float32: exact tier (1e-5 contract; at the flagship shape fp32-accurate tcgen05 kernels with
+        # every operand split into fp16 hi + lo, FFMA kernels for the other shapes).  torch.bfloat16: 16-bit
+        # tensor-core tier (tcgen05, IEEE fp16 operands / fp32 accumulate, 2e-2 contract -- north_star's
+        # "bf16 path"); also selected by bf16 inputs or a .bfloat16() module.  Both tiers train.
         self.compute_dtype = torch.float32
         self._injected_noise: Optional[Dict[str, torch.Tensor]] = None
         self._pack_cache: Dict[object, tuple] = {}
@@ -90,15 +91,39 @@ class EEG_LSTM(nn.Module):
         return [self.attn.weight, self.attn.bias, self.ln.weight, self.ln.bias,
                 self.fc[0].weight, self.fc[0].bias, self.fc[3].weight, self.fc[3].bias]
 
-    def _packed(self, l: int):
-        ps = self.lstm.layer(l)
+    def invalidate_packed_weights(self) -> None:
+        """Drop the packed-weight caches.  They are keyed on (data_ptr, _version, dtype) of the parameters, which
+        in-place updates through ``p.data`` (``p.data.copy_()``, EMA, weight clipping) do NOT bump: call this after
+        such an update.  ``train()`` / ``eval()``, ``.to()`` / ``.cuda()`` / ``.half()`` and ``load_state_dict`` do it
+        themselves."""
+        self._pack_cache.clear()
+
+    def train(self, mode: bool = True):
+        self._pack_cache.clear()
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._pack_cache.clear()
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._pack_cache.clear()
+        out = super().load_state_dict(*args, **kwargs)
+        self._pack_cache.clear()
+        return out
+
+    def _cached_pack(self, slot, ps, make):
         key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
-        hit = self._pack_cache.get(l)
+        hit = self._pack_cache.get(slot)
         if hit is None or hit[0] != key:
             with torch.no_grad():
-                hit = (key, ops.pack_lstm_layer(*ps))
-            self._pack_cache[l] = hit
+                hit = (key, make())
+            self._pack_cache[slot] = hit
         return hit[1]
+
+    def _packed(self, l: int):
+        ps = self.lstm.layer(l)
+        return self._cached_pack(l, ps, lambda: ops.pack_lstm_layer(*ps))
 
     def tc_supported(self) -> bool:
         """Shape implemented by the tensor-core tier (the flagship decoder)."""
@@ -112,33 +137,15 @@ class EEG_LSTM(nn.Module):
 
     def _packed_tc_wide(self):
         ps = self.lstm.layer(0) + self.lstm.layer(1) + [self.attn.weight, self.attn.bias]
-        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
-        hit = self._pack_cache.get("tc_wide")
-        if hit is None or hit[0] != key:
-            with torch.no_grad():
-                hit = (key, ops.decoder_pack_wide_bf16(ps[:8], ps[8], ps[9]))
-            self._pack_cache["tc_wide"] = hit
-        return hit[1]
+        return self._cached_pack("tc_wide", ps, lambda: ops.decoder_pack_wide_bf16(ps[:8], ps[8], ps[9]))
 
     def _packed_x3(self):
         ps = self.lstm.layer(0) + self.lstm.layer(1)
-        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
-        hit = self._pack_cache.get("x3")
-        if hit is None or hit[0] != key:
-            with torch.no_grad():
-                hit = (key, ops.decoder_pack_x3(ps))
-            self._pack_cache["x3"] = hit
-        return hit[1]
+        return self._cached_pack("x3", ps, lambda: ops.decoder_pack_x3(ps))
 
     def _packed_tc(self):
         ps = self.lstm.layer(0) + self.lstm.layer(1)
-        key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
-        hit = self._pack_cache.get("tc")
-        if hit is None or hit[0] != key:
-            with torch.no_grad():
-                hit = (key, ops.decoder_pack_bf16(ps))
-            self._pack_cache["tc"] = hit
-        return hit[1]
+        return self._cached_pack("tc", ps, lambda: ops.decoder_pack_bf16(ps))
 
     def decode(self, x: torch.Tensor, want_probs: bool = True):
         """Eval-mode forward without autograd: x [B,T,C] on CUDA -> (logits fp32 [B,K], probs fp32 [B,K] or

@@ -10,6 +10,7 @@ rounded up to a multiple of 32 (see include/neuroalpha.h).
 """
 from __future__ import annotations
 
+import functools
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -61,6 +62,32 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _first_cuda_device(args, kwargs) -> Optional[torch.device]:
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, Tensor):
+            if a.is_cuda:
+                return a.device
+        elif isinstance(a, (list, tuple)):
+            for t in a:
+                if isinstance(t, Tensor) and t.is_cuda:
+                    return t.device
+    return None
+
+
+def _device_guard(fn):
+    """Run an op body on the device of its (first CUDA) tensor argument: the launch stream, the scratch
+    allocations and the kernel's device all follow the data, not torch's current device
+    (``SimplePredictor(device="cuda:1")`` / ``model.to("cuda:1")`` while cuda:0 is current)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = _first_cuda_device(args, kwargs)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def all_custom_ops():
     return [window_zscore, pack_lstm_layer, lstm_layer_fwd, lstm_layer_bwd, lstm_layer_wgrad, head_fwd,
             head_bwd, trial_mean, decoder_pack_bf16, decoder_infer_bf16, lstm2_fwd_train_bf16, lstm_bwd_bf16,
@@ -76,6 +103,7 @@ def launch_count() -> int:
 # custom ops (kernel granularity)
 # ------------------------------------------------------------------------------------------
 @torch.library.custom_op("neuroalpha::window_zscore", mutates_args=(), device_types="cuda")
+@_device_guard
 def window_zscore(x: Tensor, T: int, hop: int, normalize: bool, time_major: bool, out16: int,
                   pad_to: int = BATCH_ALIGN) -> Tensor:
     """K1.  x: [B,T,C] batch or [n_samples,C] stream (then windows start every ``hop`` samples).
@@ -115,6 +143,7 @@ def _(x, T, hop, normalize, time_major, out16, pad_to=BATCH_ALIGN):
 
 
 @torch.library.custom_op("neuroalpha::pack_lstm_layer", mutates_args=(), device_types="cuda")
+@_device_guard
 def pack_lstm_layer(w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh: Tensor) -> Tuple[Tensor, Tensor]:
     _require_cuda(w_ih, w_hh, b_ih, b_hh)
     w_ih, w_hh, b_ih, b_hh = map(_f32c, (w_ih, w_hh, b_ih, b_hh))
@@ -134,6 +163,7 @@ def _(w_ih, w_hh, b_ih, b_hh):
 
 
 @torch.library.custom_op("neuroalpha::lstm_layer_fwd", mutates_args=(), device_types="cuda")
+@_device_guard
 def lstm_layer_fwd(inp: Tensor, wt: Tensor, bias: Tensor, drop_mask: Optional[Tensor], drop_scale: float,
                    save: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """K3 forward of one layer.  inp TMP [T,Bp,K] -> (h, c, gates, h_drop); c/gates are empty
@@ -163,6 +193,7 @@ def _(inp, wt, bias, drop_mask, drop_scale, save):
 
 
 @torch.library.custom_op("neuroalpha::lstm_layer_bwd", mutates_args=(), device_types="cuda")
+@_device_guard
 def lstm_layer_bwd(dh: Tensor, gates: Tensor, c: Tensor, w_ih: Tensor, w_hh: Tensor,
                    in_drop_mask: Optional[Tensor], drop_scale: float, need_din: bool) -> Tuple[Tensor, Tensor]:
     """Fused BPTT of one layer: (dgates TMP [T,Bp,4H], din TMP [T,Bp,K] or empty)."""
@@ -184,6 +215,7 @@ def _(dh, gates, c, w_ih, w_hh, in_drop_mask, drop_scale, need_din):
 
 
 @torch.library.custom_op("neuroalpha::lstm_layer_wgrad", mutates_args=(), device_types="cuda")
+@_device_guard
 def lstm_layer_wgrad(dgates: Tensor, inp: Tensor, h: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     """(dW_ih [4H,K], dW_hh [4H,H], db [4H]) from dgates -- deterministic two-stage reduction."""
     _require_cuda(dgates, inp, h)
@@ -206,6 +238,7 @@ def _(dgates, inp, h):
 
 
 @torch.library.custom_op("neuroalpha::head_fwd", mutates_args=(), device_types="cuda")
+@_device_guard
 def head_fwd(h: Tensor, B: int, params: Sequence[Tensor], rrelu_slope: Optional[Tensor],
              drop_mask: Optional[Tensor], drop_scale: float, want_probs: bool,
              save: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
@@ -232,6 +265,7 @@ def _(h, B, params, rrelu_slope, drop_mask, drop_scale, want_probs, save):
 
 
 @torch.library.custom_op("neuroalpha::head_bwd", mutates_args=(), device_types="cuda")
+@_device_guard
 def head_bwd(dlogits: Tensor, h: Tensor, stats: Tensor, zpool: Tensor, params: Sequence[Tensor],
              rrelu_slope: Optional[Tensor], drop_mask: Optional[Tensor], drop_scale: float) -> Tuple[Tensor, Tensor]:
     """Backward of K4: (dh TMP [T,Bp,H], dparams packed in HEAD_KEYS order)."""
@@ -257,6 +291,7 @@ def _(dlogits, h, stats, zpool, params, rrelu_slope, drop_mask, drop_scale):
 
 
 @torch.library.custom_op("neuroalpha::trial_mean", mutates_args=(), device_types="cuda")
+@_device_guard
 def trial_mean(x: Tensor) -> Tensor:
     """K5.  x [R, ...] fp32 -> mean over the leading (trial) axis with run_trials' exact rounding
     (tester.py:54,89,97)."""
@@ -281,6 +316,7 @@ NA_F16 = 2
 
 
 @torch.library.custom_op("neuroalpha::decoder_pack_bf16", mutates_args=(), device_types="cuda")
+@_device_guard
 def decoder_pack_bf16(lstm_flat: Sequence[Tensor]) -> Tensor:
     """The 8 nn.LSTM tensors (layer 0 then layer 1) -> UMMA B operands of the tensor-core tier."""
     _require_cuda(*lstm_flat)
@@ -298,6 +334,7 @@ def _(lstm_flat):
 
 
 @torch.library.custom_op("neuroalpha::decoder_infer_bf16", mutates_args=(), device_types="cuda")
+@_device_guard
 def decoder_infer_bf16(x_tmp: Tensor, packed: Tensor, head: Sequence[Tensor], B: int,
                        want_probs: bool) -> Tuple[Tensor, Tensor]:
     """Whole decoder forward on tcgen05 (bf16 operands, fp32 accumulate).  x_tmp: TMP bf16 [T,Bp,8]
@@ -322,6 +359,7 @@ def _(x_tmp, packed, head, B, want_probs):
 
 
 @torch.library.custom_op("neuroalpha::decoder_infer_bf16_x32", mutates_args=(), device_types="cuda")
+@_device_guard
 def decoder_infer_bf16_x32(x: Tensor, packed: Tensor, head: Sequence[Tensor], want_probs: bool) -> Tuple[Tensor, Tensor]:
     """Whole decoder forward on tcgen05 straight from the batch-first fp32 windows x [B,T,8] (the fp32 -> fp16
     time-major pack is fused into the kernel's producer warp)."""
@@ -364,6 +402,7 @@ EXACT_TC = True             # exact tier, flagship shape, eval: fp16-split tcgen
 
 
 @torch.library.custom_op("neuroalpha::decoder_pack_x3", mutates_args=(), device_types="cuda")
+@_device_guard
 def decoder_pack_x3(lstm_flat: Sequence[Tensor]) -> Tensor:
     """The 8 nn.LSTM tensors (layer 0 then layer 1) -> fp16 hi / lo UMMA operands of the exact tensor-core kernel."""
     _require_cuda(*lstm_flat)
@@ -381,6 +420,7 @@ def _(lstm_flat):
 
 
 @torch.library.custom_op("neuroalpha::decoder_infer_x3", mutates_args=(), device_types="cuda")
+@_device_guard
 def decoder_infer_x3(x: Tensor, packed: Tensor, head: Sequence[Tensor], want_probs: bool) -> Tuple[Tensor, Tensor]:
     """Whole decoder forward at fp32 accuracy on tcgen05 (operands split into fp16 hi + lo, three MMAs per product),
     straight from the batch-first fp32 windows x [B,T,8]."""
@@ -407,6 +447,7 @@ WIDE_HIDDEN = (96, 144, 192)          # hidden sizes of the streamed-weight tens
 
 
 @torch.library.custom_op("neuroalpha::decoder_pack_wide_bf16", mutates_args=(), device_types="cuda")
+@_device_guard
 def decoder_pack_wide_bf16(lstm_flat: Sequence[Tensor], attn_w: Tensor, attn_b: Tensor) -> Tensor:
     """The 8 nn.LSTM tensors + the attention vector of a wide decoder (H in WIDE_HIDDEN, input_size 8, 2 layers)
     -> the weight image the wide kernel streams every step (MMA consumption order) + its score operand."""
@@ -443,6 +484,7 @@ def _wide_state(H: int, device) -> Tensor:
 
 
 @torch.library.custom_op("neuroalpha::decoder_infer_wide_bf16", mutates_args=(), device_types="cuda")
+@_device_guard
 def decoder_infer_wide_bf16(x_tmp: Tensor, packed: Tensor, head: Sequence[Tensor], B: int, H: int,
                             want_probs: bool) -> Tuple[Tensor, Tensor]:
     """Whole wide-decoder forward on tcgen05 with streamed weights.  x_tmp as for decoder_infer_bf16;
@@ -587,6 +629,7 @@ def decoder_train_forward(x: Tensor, lstm_params, head_params, p: float, zscore:
 # tensor-core tier, training
 # ------------------------------------------------------------------------------------------
 @torch.library.custom_op("neuroalpha::lstm2_fwd_train_bf16", mutates_args=(), device_types="cuda")
+@_device_guard
 def lstm2_fwd_train_bf16(x_tmp: Tensor, packed: Tensor, mask: Optional[Tensor], seed: int, thresh16: int,
                          drop_scale: float, attn_w: Tensor, attn_b: Tensor,
                          B: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
@@ -622,6 +665,7 @@ def _(x_tmp, packed, mask, seed, thresh16, drop_scale, attn_w, attn_b, B):
 
 
 @torch.library.custom_op("neuroalpha::head_tail_fwd", mutates_args=(), device_types="cuda")
+@_device_guard
 def head_tail_fwd(zpool: Tensor, params: Sequence[Tensor], rrelu_slope: Optional[Tensor], drop_mask: Optional[Tensor],
                   drop_scale: float, want_probs: bool) -> Tuple[Tensor, Tensor]:
     """LayerNorm -> fc0 -> RReLU -> dropout -> fc3 (+softmax) on an already pooled z [B,H] (lstm_eeg_model.py:38-39)."""
@@ -643,6 +687,7 @@ def _(zpool, params, rrelu_slope, drop_mask, drop_scale, want_probs):
 
 
 @torch.library.custom_op("neuroalpha::head_tail_bwd", mutates_args=(), device_types="cuda")
+@_device_guard
 def head_tail_bwd(dlogits: Tensor, zpool: Tensor, params: Sequence[Tensor], rrelu_slope: Optional[Tensor],
                   drop_mask: Optional[Tensor], drop_scale: float) -> Tuple[Tensor, Tensor]:
     """Backward of head_tail_fwd: (dz [B,H], dparams packed like head_bwd with the attn slots zeroed)."""
@@ -668,6 +713,7 @@ def _(dlogits, zpool, params, rrelu_slope, drop_mask, drop_scale):
 
 
 @torch.library.custom_op("neuroalpha::dropout_mask_u8", mutates_args=(), device_types="cuda")
+@_device_guard
 def dropout_mask_u8(like: Tensor, seed: int, thresh16: int, T: int, Bp: int) -> Tensor:
     """The keep-mask the in-kernel generator produces for (seed, thresh16): u8 [T,Bp,48] on like.device."""
     _require_cuda(like)
@@ -682,6 +728,7 @@ def _(like, seed, thresh16, T, Bp):
 
 
 @torch.library.custom_op("neuroalpha::lstm_bwd_bf16", mutates_args=(), device_types="cuda")
+@_device_guard
 def lstm_bwd_bf16(layer: int, act_in: Tensor, h: Tensor, c: Tensor, dh: Optional[Tensor], packed: Tensor, w_ih: Tensor,
                   w_hh: Tensor, in_mask: Optional[Tensor], seed: int, thresh16: int, drop_scale: float,
                   head: Sequence[Tensor], B: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:

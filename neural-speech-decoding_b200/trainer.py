@@ -75,6 +75,9 @@ def train(X: np.ndarray, y: np.ndarray, num_classes: int, epochs: int = 30, batc
     model = EEG_LSTM(input_size=X.shape[2], num_classes=num_classes, dropout=dropout).to(device)
     if bf16:
         model.compute_dtype = torch.bfloat16
+    # the init above is shared; the train-mode noise (RReLU slopes, dropout masks, the in-kernel dropout seed drawn
+    # from the CPU generator) must differ between ranks, or the batch shards would see perfectly correlated noise
+    torch.manual_seed(seed + 7919 * (rank + 1))
     tr_idx, va_idx = split_indices(len(X), val_frac, seed)
     Xd = X.to(device) if isinstance(X, torch.Tensor) else torch.from_numpy(X).to(device)       # GPU-ingested or numpy
     yd = y.to(device) if isinstance(y, torch.Tensor) else torch.from_numpy(y).to(device)

@@ -79,7 +79,7 @@ def test_bf16_synthetic_512_and_many_tiles(dev, checkpoint):
     # LayerNorm input is nearly constant amplify it), so this stress case is judged statistically
     err = np.abs(a - b).max(axis=1) / np.abs(b).max()
     assert np.isfinite(a).all()
-    assert err.mean() < 2e-3 and np.quantile(err, 0.999) < BF16_TOL and err.max() < 0.15, (err.mean(), err.max())
+    assert err.mean() < 2e-3 and err.max() < BF16_TOL, (err.mean(), err.max())      # the contract, on the worst window
     assert (a.argmax(1) != b.argmax(1)).mean() < 2e-3
 
 
@@ -157,7 +157,7 @@ def grad_rel(model, ref_grads):
     gmax = max(float(np.abs(ref_grads[k]).max()) for k, _ in model.named_parameters())
     for k, p in model.named_parameters():
         r = ref_grads[k]
-        scale = max(float(aw if k == "attn.bias" else np.abs(r).max()), 0.05 * gmax)
+        scale = float(aw if k == "attn.bias" else np.abs(r).max())        # every tensor on its own scale, no floor
         out[k] = float(np.abs(p.grad.float().cpu().numpy() - r).max() / scale)
     return out
 
@@ -320,7 +320,7 @@ def test_wide_matches_exact_tier(dev, H, T, B):
     assert np.isfinite(got).all()
     assert np.array_equal(got, again)                      # deterministic, workspace re-use is clean
     err = np.abs(got - exact).max(axis=1) / np.abs(exact).max()
-    assert err.mean() < 2e-3 and np.quantile(err, 0.999) < BF16_TOL and err.max() < 0.1, (err.mean(), err.max())
+    assert err.mean() < 2e-3 and err.max() < BF16_TOL, (err.mean(), err.max())
 
 
 def test_fused_input_entries_are_bit_identical(dev, checkpoint):
@@ -337,3 +337,29 @@ def test_fused_input_entries_are_bit_identical(dev, checkpoint):
             a = ops.decoder_infer_bf16(xt, m._packed_tc(), m._head_params(), B, True)
             b = ops.decoder_infer_bf16_x32(x, m._packed_tc(), m._head_params(), True)
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), (B, T)
+
+
+def test_fp16_tier_input_range_and_nan(dev, checkpoint):
+    """The 16-bit tier stores the input as fp16(x / 16) (the packed layer-0 W_ih carries the 16): raw ADC samples with a DC
+    offset beyond fp16's 65,504 stay finite instead of turning the logits into NaN; inside the normal range nothing changes
+    (same 2e-2 contract); a NaN sample poisons its own window only."""
+    gen = torch.Generator(device="cpu").manual_seed(9)
+    m = bf16_model(dev, checkpoint)
+    x = torch.randn(40, 625, 8, generator=gen) * 2.73
+    with torch.inference_mode():
+        big = m((x + 1.0e5).to(dev)).cpu().numpy()                # 1e5 / 16 = 6,250: representable
+        assert np.isfinite(big).all()
+        m.compute_dtype = torch.float32
+        want = m((x * 300.0).to(dev)).cpu().numpy()               # amplitudes of ~800 (max ~4,000): still the normal range
+        m.compute_dtype = torch.bfloat16
+        got = m((x * 300.0).to(dev)).cpu().numpy()
+        assert rel(got, want) < BF16_TOL, rel(got, want)
+        xn = x.clone()
+        xn[3, 100, 2] = float("nan")
+        out = m(xn.to(dev)).cpu().numpy()
+    assert np.isnan(out[3]).all() and np.isfinite(np.delete(out, 3, axis=0)).all()
+    # training forward / backward on the same tier: finite gradients for the offset input
+    m.train()
+    m.zero_grad()
+    torch.nn.functional.cross_entropy(m((x[:8] + 1.0e5).to(dev)), torch.zeros(8, dtype=torch.long, device=dev)).backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters())

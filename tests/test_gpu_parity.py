@@ -215,7 +215,11 @@ def test_synthetic_batch_parity_512(dev, checkpoint):
 # ---------------------------------------------------------------------------------------------
 # gradients
 # ---------------------------------------------------------------------------------------------
-def check_grads(model, ref_grads, tol=FP32_TOL):
+def check_grads(model, ref_grads, tol=FP32_TOL, vanishing=()):
+    """max|d| / max|g| per tensor, NO floor: every tensor is judged on its own scale.  Only the tensors whose true
+    gradient vanishes analytically are judged on the model's gradient scale instead: attn.bias always (softmax is
+    shift-invariant; scale = attn.weight's), and the ones a test names in ``vanishing`` (T = 1 makes dW_hh and
+    d attn.weight zero)."""
     worst = {}
     aw = np.abs(ref_grads["attn.weight"]).max()
     names = [k for k, _ in model.named_parameters()]
@@ -223,13 +227,21 @@ def check_grads(model, ref_grads, tol=FP32_TOL):
     for k, p in model.named_parameters():
         r = ref_grads[k]
         scale = aw if k == "attn.bias" else np.abs(r).max()     # attn.bias grad is analytically 0
-        # tensors whose true gradient (nearly) vanishes -- T=1 makes dW_hh and d attn.weight zero, two
-        # classes make d fc.3.bias a cancelling pair -- are judged on the model's gradient scale
-        scale = max(float(scale), 0.05 * gmax)
-        worst[k] = float(np.abs(p.grad.cpu().numpy() - r).max() / scale)
+        if k in vanishing or (k == "attn.bias" and "attn.weight" in vanishing):
+            scale = gmax
+        worst[k] = float(np.abs(p.grad.cpu().numpy() - r).max() / max(float(scale), 1e-30))
     bad = {k: v for k, v in worst.items() if not v < tol}
     assert not bad, f"bad={bad} all={worst}"
     return worst
+
+
+def fp64_truth_grads(kw, sd, x, y):
+    """Gradients of the oracle port evaluated in float64 (the reference's own fp32 autograd is up to 1.1e-5 away from
+    it on attn.weight, so 1e-5 parity is checked against this, as in the flagship test)."""
+    ref = RefEEGLSTM(**kw).double().eval()
+    ref.load_state_dict({k: v.double() for k, v in sd.items()}, strict=True)
+    torch.nn.functional.cross_entropy(ref(x.double()), y).backward()
+    return {k: p.grad.numpy() for k, p in ref.named_parameters()}
 
 
 def test_gradients_eval_mode_vs_reference(dev, checkpoint, windows, golden_dir):
@@ -306,7 +318,37 @@ def test_five_class_variant(dev, windows, golden_dir):
     loss = torch.nn.functional.cross_entropy(m(x[:16]), torch.from_numpy(f["y"][:16]).to(dev))
     loss.backward()
     assert abs(loss.item() - float(f["loss"])) < 1e-5
-    check_grads(m, {k[5:]: f[k] for k in f.files if k.startswith("grad.")})
+    # 1e-5 against the fp64 truth; against the reference's own fp32 autograd allow for ITS distance from the truth
+    truth = fp64_truth_grads(dict(num_classes=5), sd, x[:16].cpu(), torch.from_numpy(f["y"][:16]))
+    check_grads(m, truth)
+    for k, p in m.named_parameters():
+        scale = np.abs(truth["attn.weight"]).max() if k == "attn.bias" else np.abs(truth[k]).max()
+        ref_err = np.abs(f["grad." + k] - truth[k]).max() / scale
+        assert np.abs(p.grad.cpu().numpy() - f["grad." + k]).max() / scale < FP32_TOL + ref_err, k
+
+
+def test_five_class_few_training_steps_both_sides(dev, windows, golden_dir):
+    """"train a few steps both sides" -- 4 Adam steps (eval-mode, deterministic) on the repo's
+    windows with the 5-class labels, reference port on the CPU vs this module on the GPU: losses and final weights agree."""
+    f = np.load(golden_dir / "ref_5class.npz")
+    sd = {k[3:]: torch.from_numpy(f[k]) for k in f.files if k.startswith("sd.")}
+    x, y = torch.from_numpy(windows["X"][f["sel"]]), torch.from_numpy(f["y"])
+    ref = RefEEGLSTM(num_classes=5).eval()
+    ref.load_state_dict(sd, strict=True)
+    m = make_model(dev, sd, num_classes=5).eval()
+    opt_r, opt_m = torch.optim.Adam(ref.parameters(), lr=1e-3), torch.optim.Adam(m.parameters(), lr=1e-3)
+    xg, yg = x.to(dev), y.to(dev)
+    for step in range(4):
+        sl = slice(8 * step, 8 * step + 8)
+        opt_r.zero_grad(); opt_m.zero_grad()
+        lr_ = torch.nn.functional.cross_entropy(ref(x[sl]), y[sl]); lr_.backward(); opt_r.step()
+        lm = torch.nn.functional.cross_entropy(m(xg[sl]), yg[sl]); lm.backward(); opt_m.step()
+        assert abs(lr_.item() - lm.item()) < 2e-5 * max(1.0, abs(lr_.item())), (step, lr_.item(), lm.item())
+    # Adam normalises the update to ~lr per element, so the weights may differ by a few 1e-3 * (relative grad error)
+    for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        assert np.abs(p.detach().cpu().numpy() - q.detach().numpy()).max() < 2e-4, k
+    with torch.inference_mode():
+        assert rel(m(xg).cpu().numpy(), ref(x).numpy()) < 1e-3
 
 
 def test_stress_shape_h192(dev, golden_dir):
@@ -319,7 +361,8 @@ def test_stress_shape_h192(dev, golden_dir):
     loss = torch.nn.functional.cross_entropy(logits, torch.from_numpy(f["y"]).to(dev))
     loss.backward()
     assert abs(loss.item() - float(f["loss"])) < 1e-5
-    check_grads(m, {k[5:]: f[k] for k in f.files if k.startswith("grad.")}, tol=2e-5)
+    truth = fp64_truth_grads(dict(hidden_size=192), sd, torch.from_numpy(f["x"]), torch.from_numpy(f["y"]))
+    check_grads(m, truth)                                     # 1e-5, every tensor on its own scale
 
 
 def test_odd_sizes_against_port(dev):
@@ -335,7 +378,8 @@ def test_odd_sizes_against_port(dev):
         out = m(x.to(dev))
         torch.nn.functional.cross_entropy(out, y.to(dev)).backward()
         assert rel(out.detach().cpu().numpy(), ref(x).detach().numpy()) < FP32_TOL, kw
-        check_grads(m, {k: p.grad.numpy() for k, p in ref.named_parameters()}, tol=2e-5)
+        vanishing = [k for k, _ in ref.named_parameters() if "weight_hh" in k or k == "attn.weight"] if T == 1 else []
+        check_grads(m, fp64_truth_grads(kw, ref.state_dict(), x, y), vanishing=vanishing)
 
 
 def test_state_dict_roundtrip_on_device(dev, checkpoint, tmp_path):
