@@ -50,8 +50,8 @@ L0_KERNEL_FLOPS_PER_WINDOW = 2 * (8 + 48) * 192 * T
 INPUT_SIGMA = 2.73                            # matches the CSV corpus
 NCU_TRAFFIC_BYTES_40960 = 823.51e6 + 7.36e6   # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_tc2_fused_ncu_full.csv
 # the same two counters for decoder_infer_x3_kernel (one launch over 40,960 windows)
-NCU_TRAFFIC_BYTES_40960_X3 = 823.51e6 + 7.36e6
-NCU_TRAFFIC_SOURCE_X3 = "pending: profiles/r2_x3_ncu_full.csv"
+NCU_TRAFFIC_BYTES_40960_X3 = 823.19e6 + 5.96e6
+NCU_TRAFFIC_SOURCE_X3 = "profiles/r2_x3_ncu_full.csv"
 
 
 def load_checkpoint():

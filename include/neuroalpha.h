@@ -172,10 +172,13 @@ int na_csv_parse_f32(const void* text, const int64_t* offsets, float* out, int* 
  * over if carry_state, as BrainFlow re-uses the filter object -- reversal), then np.round(., round_decimals)
  * (< 0: none) and -0 -> 0.  Arithmetic in float64.  coef = the sections of all filters back to back, 5 doubles each
  * (b0 b1 b2 a1 a2, a0 = 1); nsec[f] = sections of filter f (<= 8 filters x <= 8 sections; each section count is
- * checked by the caller); scratch = T * roundup(B*C, 128) doubles.  Parity unpinned: BrainFlow is not available in this image.
+ * checked by the caller; max_sections = the largest nsec[f], passed in so that no device-to-host copy is needed);
+ * scratch = T * roundup(B*C, 128) doubles for T > 2560, otherwise unused and may be NULL (one warp per series, the
+ * series stays in registers).  Parity unpinned: BrainFlow is not available in this image.
  */
 int na_iir_chain(const float* x, float* y, double* scratch, const double* coef, const int* nsec, int64_t nfilt,
-                 int64_t B, int64_t T, int64_t C, int detrend, int round_decimals, int carry_state, na_stream_t stream);
+                 int64_t B, int64_t T, int64_t C, int detrend, int round_decimals, int carry_state, int64_t max_sections,
+                 na_stream_t stream);
 
 /* ---- tensor-core tier: whole decoder forward, bf16 operands / fp32 accumulate ----------------
  * One persistent warp-specialised tcgen05 / TMEM / TMA kernel: K2 (input-gate contraction,

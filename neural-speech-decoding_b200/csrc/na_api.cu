@@ -40,6 +40,7 @@ int lstm_layer_fwd_h48(const float* in, const float* wt, const float* bias, floa
 void set_h48_groups(int ng);
 int mask_scale(const float* h, const float* mask, float scale, float* out, int64_t n, cudaStream_t st);
 
+void set_iir_occ3(int v);
 namespace tc { void set_infer_hs(int hs); void set_infer_rep(int v); void set_wide_cluster(int v); void set_wide_dbg(int v); void set_train_fwd_v2(int v); }
 static int g_lstm_tier = 0;   // 0 = auto (specialised when available), 1 = generic only
 
@@ -109,6 +110,7 @@ extern "C" int na_set_tuning(const char* key, int64_t value) {
     if (!strcmp(key, "tc_infer_rep")) { tc::set_infer_rep((int)value); return NA_OK; }
     if (!strcmp(key, "tc_train_fwd_v2")) { tc::set_train_fwd_v2((int)value); return NA_OK; }
     if (!strcmp(key, "tc_wide_dbg")) { tc::set_wide_dbg((int)value); return NA_OK; }
+    if (!strcmp(key, "iir_occ3")) { set_iir_occ3((int)value); return NA_OK; }
     if (!strcmp(key, "tc_wide_cluster")) { tc::set_wide_cluster((int)value); return NA_OK; }
     return fail(NA_EINVAL, "na_set_tuning: unknown key '%s'", key);
 }

@@ -151,78 +151,80 @@ __device__ __forceinline__ Mat2 mat_mul(const Mat2& x, const Mat2& y) {
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// One section pass over the register-resident series.  dir = +1: ascending time (lane 0 first), -1: descending (lane `last`
-// first).  (w1, w2) in: the state the pass starts from (warp-uniform); out: the state after the last sample processed.
+// One section pass over the register-resident series (every lane owns exactly LT samples: the series is padded with
+// zeros at the FRONT, see the kernel).  dir = +1: ascending time (lane 0 first), -1: descending (lane 31 first).
+// (w1, w2) in: the state the pass starts from (warp-uniform); out: the state after the last sample processed.
 template <int LT>
-__device__ __forceinline__ void section_pass(double (&v)[LT], const int n, const int lane, const int last, const int dir,
-                                             const double b0, const double b1, const double b2, const double a1, const double a2,
-                                             const double* __restrict__ pm,       // 5 x (a, b, c, d): A^(L 2^j)
+__device__ __forceinline__ void section_pass(double (&v)[LT], const int lane, const int dir,
+                                             const double b0, const double b1, const double b2, const double na1, const double na2,
+                                             const double* __restrict__ pm,       // 5 x (a, b, c, d): A^(LT 2^j)
                                              double& w1, double& w2) {
-    const bool first = dir > 0 ? lane == 0 : lane == last;         // the block that is processed first carries the initial state
-    // (1) end state of this lane's block from a zero state (the first block: from the true initial state)
+    const bool first = dir > 0 ? lane == 0 : lane == 31;          // the block that is processed first carries the initial state
+    // (1) end state of this lane's block from a zero state (the first block: from the true initial state).
+    //     w_t = (v_t - a2 w_{t-2}) - a1 w_{t-1}: only the outer FMA is on the dependent chain
     double e1 = first ? w1 : 0.0, e2 = first ? w2 : 0.0;
 #pragma unroll
     for (int jj = 0; jj < LT; ++jj) {
         const int j = dir > 0 ? jj : LT - 1 - jj;
-        if (j < n) {
-            const double w = v[j] - a1 * e1 - a2 * e2;
-            e2 = e1;
-            e1 = w;
-        }
+        const double w = fma(na1, e1, fma(na2, e2, v[j]));
+        e2 = e1;
+        e1 = w;
     }
-    if (lane > last) { e1 = 0.0; e2 = 0.0; }
-    // (2) scan over the blocks in processing order; every block that is ever multiplied through is a full block of L samples
+    // (2) scan over the blocks in processing order: S_p = A^LT S_{p-1} + e_p
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const int d = 1 << j;
         const int src = dir > 0 ? lane - d : lane + d;
         const double f1 = shfl_d(e1, src & 31), f2 = shfl_d(e2, src & 31);
-        const bool take = dir > 0 ? (lane >= d && lane <= last) : (lane + d <= last);
-        if (take) {
-            e1 += pm[4 * j] * f1 + pm[4 * j + 1] * f2;
-            e2 += pm[4 * j + 2] * f1 + pm[4 * j + 3] * f2;
-        }
+        const bool take = dir > 0 ? lane >= d : lane + d <= 31;
+        const double g1 = fma(pm[4 * j], f1, pm[4 * j + 1] * f2), g2 = fma(pm[4 * j + 2], f1, pm[4 * j + 3] * f2);
+        e1 += take ? g1 : 0.0;
+        e2 += take ? g2 : 0.0;
     }
     // incoming state of this lane = end state of the block processed just before it
     const int prev = dir > 0 ? lane - 1 : lane + 1;
     double s1 = shfl_d(e1, prev & 31), s2 = shfl_d(e2, prev & 31);
     if (first) { s1 = w1; s2 = w2; }
-    // (3) the real pass
+    // (3) the real pass: DirectFormII, w = v - a1 w1 - a2 w2; out = b0 w + b1 w1 + b2 w2
 #pragma unroll
     for (int jj = 0; jj < LT; ++jj) {
         const int j = dir > 0 ? jj : LT - 1 - jj;
-        if (j < n) {
-            const double w = v[j] - a1 * s1 - a2 * s2;
-            v[j] = b0 * w + b1 * s1 + b2 * s2;
-            s2 = s1;
-            s1 = w;
-        }
+        const double part = fma(b1, s1, b2 * s2);                  // off the dependent chain
+        const double w = fma(na1, s1, fma(na2, s2, v[j]));
+        v[j] = fma(b0, w, part);
+        s2 = s1;
+        s1 = w;
     }
-    // state after the last processed sample: ascending -> lane `last`, descending -> lane 0
-    const int fin = dir > 0 ? last : 0;
+    // state after the last processed sample: ascending -> lane 31, descending -> lane 0
+    const int fin = dir > 0 ? 31 : 0;
     w1 = shfl_d(s1, fin);
     w2 = shfl_d(s2, fin);
 }
 
-template <int LT>
-__global__ void __launch_bounds__(kIirWarps * 32)
+// The series occupies the LAST T of the 32 LT register slots (slot p = pad + t, lane = p / LT): the pad slots in front hold
+// zeros.  A zero input on a zero state is an exact no-op, so the ascending pass (which always starts from a zero state) is
+// unchanged, the state after the last sample sits at the end of lane 31 where the descending pass picks it up, and what
+// the descending pass rings into the pad slots is cleared before the next filter.  Every lane runs identical,
+// unpredicated loops.
+template <int LT, int MAXS, int OCC>
+__global__ void __launch_bounds__(kIirWarps * 32, OCC)
 iir_chain_warp_kernel(const float* __restrict__ x, float* __restrict__ y, const double* __restrict__ coef,
                       const int* __restrict__ nsec, int nfilt, int64_t S, int T, int C, int detrend, int round_decimals,
                       int carry_state) {
     __shared__ double s_coef[kIirMaxF * kIirMaxS * 5];
     __shared__ double s_pm[kIirMaxF * kIirMaxS * 20];
     __shared__ int s_nsec[kIirMaxF];
-    extern __shared__ __align__(16) float s_io[];                  // C == 8: [8 channels][32 lanes][L + 1] staging
+    extern __shared__ __align__(16) float s_io[];                  // C == 8: [8 channels][32 lanes][LT + 1] staging
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int L = (T + 31) / 32;                                   // samples per lane (<= LT)
+    const int pad = 32 * LT - T;
     int total = 0;
     for (int f = 0; f < nfilt; ++f) total += nsec[f];
     for (int i = tid; i < total * 5; i += blockDim.x) s_coef[i] = coef[i];
     if (tid < nfilt) s_nsec[tid] = nsec[tid];
-    if (tid < total) {                                             // A^(L 2^j), j = 0..4, by repeated squaring
+    if (tid < total) {                                             // A^(LT 2^j), j = 0..4, by repeated squaring
         const double a1 = coef[tid * 5 + 3], a2 = coef[tid * 5 + 4];
         Mat2 base{-a1, -a2, 1.0, 0.0}, acc{1.0, 0.0, 0.0, 1.0};
-        for (int e = L; e > 0; e >>= 1) {
+        for (int e = LT; e > 0; e >>= 1) {
             if (e & 1) acc = mat_mul(acc, base);
             base = mat_mul(base, base);
         }
@@ -234,14 +236,13 @@ iir_chain_warp_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     }
     const int64_t s = (int64_t)blockIdx.x * kIirWarps + warp;
     const bool coop = (C == kIirWarps);                             // CTA = one window: coalesced staging through shared memory
-    const int stride = L + 1;                                      // odd-ish padding: lanes hit distinct banks
+    constexpr int stride = LT + 1;                                 // padding: the 32 lanes of a warp hit distinct banks
     if (coop) {
-        const int64_t b = blockIdx.x;
-        const float4* src = reinterpret_cast<const float4*>(x + b * T * 8);
+        const float4* src = reinterpret_cast<const float4*>(x + (int64_t)blockIdx.x * T * 8);
         for (int i = tid; i < T * 2; i += blockDim.x) {
             const float4 q = src[i];
-            const int t = i >> 1, c0 = (i & 1) * 4;
-            const int ln = t / L, j = t - ln * L;
+            const int p = pad + (i >> 1), c0 = (i & 1) * 4;
+            const int ln = p / LT, j = p - ln * LT;
             s_io[((c0 + 0) * 32 + ln) * stride + j] = q.x;
             s_io[((c0 + 1) * 32 + ln) * stride + j] = q.y;
             s_io[((c0 + 2) * 32 + ln) * stride + j] = q.z;
@@ -252,14 +253,13 @@ iir_chain_warp_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     const bool active = s < S;
     const int64_t b = active ? s / C : 0;
     const int c = active ? (int)(s % C) : 0;
-    const int t0 = lane * L;
-    const int n = active ? max(0, min(L, T - t0)) : 0;
-    const int last = (T - 1) / L;                                  // last lane that owns samples
+    const int p0 = lane * LT;                                      // first slot of this lane
     double v[LT];
 #pragma unroll
     for (int j = 0; j < LT; ++j) {
+        const int t = p0 + j - pad;
         v[j] = 0.0;
-        if (j < n) v[j] = coop ? (double)s_io[(warp * 32 + lane) * stride + j] : (double)x[(b * T + t0 + j) * C + c];
+        if (active && t >= 0) v[j] = coop ? (double)s_io[(warp * 32 + lane) * stride + j] : (double)x[(b * T + t) * C + c];
     }
     if (detrend) {
         double part = 0.0;
@@ -269,72 +269,85 @@ iir_chain_warp_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         const double mean = part / (double)T;
 #pragma unroll
-        for (int j = 0; j < LT; ++j) if (j < n) v[j] -= mean;
+        for (int j = 0; j < LT; ++j) if (p0 + j >= pad) v[j] -= mean;
     }
     int cbase = 0;
     for (int f = 0; f < nfilt; ++f) {
         const int ns = s_nsec[f];
-        double w1[kIirMaxS], w2[kIirMaxS];
+        double w1[MAXS], w2[MAXS];
 #pragma unroll
-        for (int k = 0; k < kIirMaxS; ++k) { w1[k] = 0.0; w2[k] = 0.0; }
+        for (int k = 0; k < MAXS; ++k) { w1[k] = 0.0; w2[k] = 0.0; }
         // forward: the cascade section by section over the whole series (same result as sample by sample: section k only
         // consumes the finished output of section k-1)
 #pragma unroll
-        for (int k = 0; k < kIirMaxS; ++k)
+        for (int k = 0; k < MAXS; ++k)
             if (k < ns) {
                 const double* cf = s_coef + (cbase + k) * 5;
-                section_pass<LT>(v, n, lane, last, +1, cf[0], cf[1], cf[2], cf[3], cf[4], s_pm + (cbase + k) * 20, w1[k], w2[k]);
+                section_pass<LT>(v, lane, +1, cf[0], cf[1], cf[2], -cf[3], -cf[4], s_pm + (cbase + k) * 20, w1[k], w2[k]);
             }
         if (!carry_state) {
 #pragma unroll
-            for (int k = 0; k < kIirMaxS; ++k) { w1[k] = 0.0; w2[k] = 0.0; }
+            for (int k = 0; k < MAXS; ++k) { w1[k] = 0.0; w2[k] = 0.0; }
         }
         // the reversed series through the same cascade
 #pragma unroll
-        for (int k = 0; k < kIirMaxS; ++k)
+        for (int k = 0; k < MAXS; ++k)
             if (k < ns) {
                 const double* cf = s_coef + (cbase + k) * 5;
-                section_pass<LT>(v, n, lane, last, -1, cf[0], cf[1], cf[2], cf[3], cf[4], s_pm + (cbase + k) * 20, w1[k], w2[k]);
+                section_pass<LT>(v, lane, -1, cf[0], cf[1], cf[2], -cf[3], -cf[4], s_pm + (cbase + k) * 20, w1[k], w2[k]);
             }
         cbase += ns;
+        if (p0 < pad) {                                            // the descending pass rang into the pad slots: clear them
+#pragma unroll
+            for (int j = 0; j < LT; ++j) if (p0 + j < pad) v[j] = 0.0;
+        }
     }
     double scale = 1.0;
     for (int k = 0; k < round_decimals; ++k) scale *= 10.0;
     if (coop) __syncthreads();                                     // every warp has read its inputs from the staging buffer
 #pragma unroll
     for (int j = 0; j < LT; ++j) {
-        if (j < n) {
+        const int t = p0 + j - pad;
+        if (active && t >= 0) {
             double o = v[j];
             if (round_decimals >= 0) o = rint(o * scale) / scale;  // np.round: multiply, rint, divide
             const float of = (float)(o == 0.0 ? 0.0 : o);          // the collector also clears negative zero
             if (coop) s_io[(warp * 32 + lane) * stride + j] = of;
-            else y[(b * T + t0 + j) * C + c] = of;
+            else y[(b * T + t) * C + c] = of;
         }
     }
     if (coop) {
         __syncthreads();
         float4* dst = reinterpret_cast<float4*>(y + (int64_t)blockIdx.x * T * 8);
         for (int i = tid; i < T * 2; i += blockDim.x) {
-            const int t = i >> 1, c0 = (i & 1) * 4;
-            const int ln = t / L, j = t - ln * L;
+            const int p = pad + (i >> 1), c0 = (i & 1) * 4;
+            const int ln = p / LT, j = p - ln * LT;
             dst[i] = make_float4(s_io[((c0 + 0) * 32 + ln) * stride + j], s_io[((c0 + 1) * 32 + ln) * stride + j],
                                  s_io[((c0 + 2) * 32 + ln) * stride + j], s_io[((c0 + 3) * 32 + ln) * stride + j]);
         }
     }
 }
 
+static int g_iir_occ3 = 1;           // LT = 20: 3 CTAs per SM (80 registers, a few spills) instead of 2 (122 registers); A/B knob
+void set_iir_occ3(int v) { g_iir_occ3 = v; }
+
 template <int LT>
-static int launch_iir_warp(const float* x, float* y, const double* coef, const int* nsec, int nfilt, int64_t S, int T, int C,
-                           int detrend, int round_decimals, int carry_state, cudaStream_t st) {
-    const int L = (T + 31) / 32;
-    const size_t smem = C == kIirWarps ? (size_t)kIirWarps * 32 * (L + 1) * sizeof(float) : 0;
-    auto kern = iir_chain_warp_kernel<LT>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail((int)e, "na_iir_chain: shared memory opt-in failed (%s)", cudaGetErrorString(e));
+static int launch_iir_warp(const float* x, float* y, const double* coef, const int* nsec, int nfilt, int max_sections, int64_t S, int T,
+                           int C, int detrend, int round_decimals, int carry_state, cudaStream_t st) {
+    const size_t smem = C == kIirWarps ? (size_t)kIirWarps * 32 * (LT + 1) * sizeof(float) : 0;
+    const unsigned grid = (unsigned)((S + kIirWarps - 1) / kIirWarps);
+    if (max_sections <= 4 && LT <= 20 && g_iir_occ3) {
+        iir_chain_warp_kernel<LT <= 20 ? LT : 20, 4, 3><<<grid, kIirWarps * 32, smem, st>>>(x, y, coef, nsec, nfilt, S, T, C, detrend,
+                                                                                          round_decimals, carry_state);
+    } else if (max_sections <= 4) {
+        auto kern = iir_chain_warp_kernel<LT, 4, 1>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, kIirWarps * 32, smem, st>>>(x, y, coef, nsec, nfilt, S, T, C, detrend, round_decimals, carry_state);
+    } else {
+        auto kern = iir_chain_warp_kernel<LT, kIirMaxS, 1>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<grid, kIirWarps * 32, smem, st>>>(x, y, coef, nsec, nfilt, S, T, C, detrend, round_decimals, carry_state);
     }
-    kern<<<(unsigned)((S + kIirWarps - 1) / kIirWarps), kIirWarps * 32, smem, st>>>(x, y, coef, nsec, nfilt, S, T, C, detrend,
-                                                                                  round_decimals, carry_state);
     return 0;
 }
 
@@ -342,7 +355,7 @@ static int launch_iir_warp(const float* x, float* y, const double* coef, const i
 
 extern "C" int na_iir_chain(const float* x, float* y, double* scratch, const double* coef, const int* nsec,
                             int64_t nfilt, int64_t B, int64_t T, int64_t C, int detrend, int round_decimals,
-                            int carry_state, na_stream_t stream) {
+                            int carry_state, int64_t max_sections, na_stream_t stream) {
     using namespace na;
     NA_REQUIRE(B >= 1 && T >= 1 && T < (1 << 30) && C >= 1 && C < (1 << 20), NA_EINVAL,
                "na_iir_chain: bad shape B=%lld T=%lld C=%lld", (long long)B, (long long)T, (long long)C);
@@ -351,12 +364,14 @@ extern "C" int na_iir_chain(const float* x, float* y, double* scratch, const dou
     NA_REQUIRE_PTR(x); NA_REQUIRE_PTR(y);
     NA_REQUIRE(nfilt == 0 || (coef != nullptr && nsec != nullptr), NA_EINVAL, "na_iir_chain: null pointer");
     const int64_t S = B * C;
+    NA_REQUIRE(max_sections >= 0 && max_sections <= kIirMaxS, NA_EUNSUPPORTED, "na_iir_chain: %lld sections per filter (at most %d)",
+               (long long)max_sections, kIirMaxS);
     if (T <= 32 * 80) {               // warp-per-series, register-resident: no scratch
-        const int L = (int)((T + 31) / 32);
+        const int L = (int)((T + 31) / 32), ms = (int)max_sections;
         int rc;
-        if (L <= 20) rc = launch_iir_warp<20>(x, y, coef, nsec, (int)nfilt, S, (int)T, (int)C, detrend, round_decimals, carry_state, as_stream(stream));
-        else if (L <= 40) rc = launch_iir_warp<40>(x, y, coef, nsec, (int)nfilt, S, (int)T, (int)C, detrend, round_decimals, carry_state, as_stream(stream));
-        else rc = launch_iir_warp<80>(x, y, coef, nsec, (int)nfilt, S, (int)T, (int)C, detrend, round_decimals, carry_state, as_stream(stream));
+        if (L <= 20) rc = launch_iir_warp<20>(x, y, coef, nsec, (int)nfilt, ms, S, (int)T, (int)C, detrend, round_decimals, carry_state, as_stream(stream));
+        else if (L <= 40) rc = launch_iir_warp<40>(x, y, coef, nsec, (int)nfilt, ms, S, (int)T, (int)C, detrend, round_decimals, carry_state, as_stream(stream));
+        else rc = launch_iir_warp<80>(x, y, coef, nsec, (int)nfilt, ms, S, (int)T, (int)C, detrend, round_decimals, carry_state, as_stream(stream));
         if (rc) return rc;
         count_launch();
         return check_launch("na_iir_chain");

@@ -115,7 +115,8 @@ def filter_windows(x: torch.Tensor, fs: float = 125.0, chain: Sequence[Tuple[str
     if B * C:
         with torch.cuda.device(x.device):
             _lib.call("na_iir_chain", x.data_ptr(), y.data_ptr(), ops._ptr(scratch), coef_d.data_ptr(), nsec_d.data_ptr(),
-                      len(sos), B, T, C, int(detrend), int(round_decimals), int(carry_state), ops._stream())
+                      len(sos), B, T, C, int(detrend), int(round_decimals), int(carry_state),
+                      int(nsec.max()) if len(sos) else 0, ops._stream())
     return y
 
 

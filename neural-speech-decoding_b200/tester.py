@@ -134,14 +134,20 @@ def run_trials_batched(windows, model, return_device: bool = False, chunk_trials
             # 625-step round (~1.8 ms on B200) however few windows it holds, so groups are sized to carry
             # at least ~8k windows: then the pipeline is bound by the PCIe copy, not by launch rounds.
             g = chunk_trials if chunk_trials > 0 else max(1, min(R, -(-8192 // max(B, 1))))
+            # group plan: full groups of g trials, but the LAST group is a single trial -- nothing overlaps the decode of
+            # the last group (the pipeline's tail), and a short launch costs only the dependent-chain latency
+            starts = list(range(0, R, g))
+            if chunk_trials <= 0 and R > 1 and (R - starts[-1]) > 1:
+                starts.append(R - 1)
+            bounds = list(zip(starts, starts[1:] + [R]))
             main = torch.cuda.current_stream(dev)
             side = torch.cuda.Stream(device=dev)
             bufs = [torch.empty((g, B, T, C), dtype=torch.float32, device=dev) for _ in range(2)]
             ready = [torch.cuda.Event() for _ in range(2)]
             freed = [torch.cuda.Event() for _ in range(2)]
             side.wait_stream(main)
-            for i, r0 in enumerate(range(0, R, g)):
-                k, n = i & 1, min(g, R - r0)
+            for i, (r0, r1) in enumerate(bounds):
+                k, n = i & 1, r1 - r0
                 with torch.cuda.stream(side):
                     if i >= 2:
                         side.wait_event(freed[k])

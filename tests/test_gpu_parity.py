@@ -216,18 +216,21 @@ def test_synthetic_batch_parity_512(dev, checkpoint):
 # gradients
 # ---------------------------------------------------------------------------------------------
 def check_grads(model, ref_grads, tol=FP32_TOL, vanishing=()):
-    """max|d| / max|g| per tensor, NO floor: every tensor is judged on its own scale.  Only the tensors whose true
-    gradient vanishes analytically are judged on the model's gradient scale instead: attn.bias always (softmax is
-    shift-invariant; scale = attn.weight's), and the ones a test names in ``vanishing`` (T = 1 makes dW_hh and
-    d attn.weight zero)."""
+    """max|d| / max|g| per tensor, NO floor: every tensor is judged on its own scale (measured on B200, round 2: every
+    tensor of the 5-class, stress and odd-size models is within 1.4e-6 of the fp64 truth on its own scale).  Only the
+    tensors whose true gradient vanishes analytically are judged on the model's gradient scale instead: attn.bias always
+    (softmax over time is shift-invariant, so d attn.bias = sum_t ds_t is EXACTLY zero and whatever fp32 leaves there --
+    the reference's own autograd included -- is rounding noise of the largest terms), and the ones a test names in
+    ``vanishing`` (T = 1 makes dW_hh and d attn.weight zero).  The flagship test additionally holds attn.bias to 1e-5 of
+    attn.weight's scale."""
     worst = {}
     aw = np.abs(ref_grads["attn.weight"]).max()
     names = [k for k, _ in model.named_parameters()]
     gmax = max(float(np.abs(ref_grads[k]).max()) for k in names)
     for k, p in model.named_parameters():
         r = ref_grads[k]
-        scale = aw if k == "attn.bias" else np.abs(r).max()     # attn.bias grad is analytically 0
-        if k in vanishing or (k == "attn.bias" and "attn.weight" in vanishing):
+        scale = np.abs(r).max()
+        if k in vanishing or k == "attn.bias":                  # analytically zero gradients
             scale = gmax
         worst[k] = float(np.abs(p.grad.cpu().numpy() - r).max() / max(float(scale), 1e-30))
     bad = {k: v for k, v in worst.items() if not v < tol}
@@ -259,6 +262,7 @@ def test_gradients_eval_mode_vs_reference(dev, checkpoint, windows, golden_dir):
     truth = np.load(golden_dir / "fp64_grads_3class_eval_b16.npz")
     check_grads(m, truth)
     aw = np.abs(truth["attn.weight"]).max()
+    assert np.abs(m.attn.bias.grad.cpu().numpy() - truth["attn.bias"]).max() / aw < FP32_TOL     # also on attn.weight's scale
     for k, p in m.named_parameters():
         scale = aw if k == "attn.bias" else np.abs(truth[k]).max()
         ref_err = np.abs(g[k] - truth[k]).max() / scale
@@ -346,6 +350,8 @@ def test_five_class_few_training_steps_both_sides(dev, windows, golden_dir):
         assert abs(lr_.item() - lm.item()) < 2e-5 * max(1.0, abs(lr_.item())), (step, lr_.item(), lm.item())
     # Adam normalises the update to ~lr per element, so the weights may differ by a few 1e-3 * (relative grad error)
     for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        if k == "attn.bias":        # a null direction (softmax shift invariance): its gradient is pure rounding noise on both
+            continue                # sides and Adam turns noise of any size into +-lr steps; the logits below cover it
         assert np.abs(p.detach().cpu().numpy() - q.detach().numpy()).max() < 2e-4, k
     with torch.inference_mode():
         assert rel(m(xg).cpu().numpy(), ref(x).numpy()) < 1e-3
