@@ -300,6 +300,39 @@ int na_head_tail_bwd_f32(const float* dlogits, const float* zpool, const float* 
                          float drop_scale, float* dz, float* dparams, float* partials,
                          int64_t B, int64_t H, int64_t NC, na_stream_t stream);
 
+/* ---- exact tier TRAINING on the tensor cores (fp32 accuracy, 1e-5 contract on logits and gradients) -----------
+ * Replaces torch autograd of lstm_eeg_model.py:32-39 at the flagship shape (C=8, H=48, 2 layers) with the
+ * operand-split scheme of na_decoder_infer_x3 (fp16 hi + lo, three tcgen05 MMAs per product, fp32 accumulate, ex2 / rcp
+ * activations).  One launch per layer and direction (csrc/na_train_x3.cu).  Layouts, all for 128-window tiles
+ * (NT = Bp / 128, chunk = [128 rows][8 fp16]):
+ *   XS    fp16 [T][NT][2][128][8]    x / 16 split into hi (chunk 0) and lo (chunk 1)       na_x3_split_input
+ *   TCLX  fp16 [T][NT][12][128][8]   h split: chunks 0-5 hi (units 8c..8c+7), 6-11 lo
+ *   TCL32 fp32 [T][NT][12][128][4]   cell state, din
+ *   DGX   fp16 [T][NT][48][128][8]   d(gates) split: chunks 0-23 hi, 24-47 lo; column n = (j/4)*16 + gate*4 + j%4
+ * `packed_x3` = na_decoder_pack_x3 output.  Inter-layer dropout as in the 16-bit tier: explicit u8 keep-mask [T][Bp][48]
+ * or (mask NULL, thresh16 < 65536) the counter-based generator keyed by `seed`; thresh16 = 65536: none.
+ *   na_lstm_fwd_train_x3  layer 0: in = XS -> h (TCLX), hd = h after dropout (TCLX, exactly when dropout is on), c;
+ *                         layer 1: in = TCLX (hd or h of layer 0) -> h, c, pooled z [B][48], softmax stats (max, sum) [B][2]
+ *   na_lstm_bwd_x3        BPTT of one layer: d(gates) -> dg (DGX); layer 1 also din (TCL32, dropout applied) and, with
+ *                         dz != NULL, the time loop of the head backward fused (dh_in must be NULL then), d_attn [52] =
+ *                         d attn_w (48) | d attn_b | pad; layer 0: dh_in = din of layer 1.  zeros: >= 24,576 zero bytes.
+ *                         scratch: na_train_x3_scratch_floats() floats.
+ *   na_lstm_wgrad_x3      time-parallel dW_ih, dW_hh, db (= both biases) from dg and the saved activations; same scratch.
+ */
+int na_x3_split_input(const float* x, void* xs, int64_t B, int64_t T, int64_t Bp, na_stream_t stream);
+int na_lstm_fwd_train_x3(int64_t layer, const void* in, const void* packed_x3, const float* attn_w, const float* attn_b,
+                         const unsigned char* mask, uint64_t seed, int64_t thresh16, float drop_scale, void* h, void* hd,
+                         float* c, float* zpool, float* stats, int64_t B, int64_t T, int64_t Bp, na_stream_t stream);
+int64_t na_train_x3_scratch_floats(void);
+int64_t na_train_x3_smem_bytes(int64_t which);
+int na_lstm_bwd_x3(int64_t layer, const void* act_in, const void* h, const float* cstate, const float* dh_in,
+                   const void* packed_x3, const void* zeros, const unsigned char* in_mask, uint64_t seed, int64_t thresh16,
+                   float drop_scale, float* din, void* dg, const float* dz, const float* stats, const float* zpool,
+                   const float* attn_w, const float* attn_b, int64_t B, float* d_attn, float* scratch,
+                   int64_t T, int64_t Bp, na_stream_t stream);
+int na_lstm_wgrad_x3(int64_t layer, const void* dg, const void* act_in, const void* h, const void* zeros,
+                     float* dw_ih, float* dw_hh, float* db, float* scratch, int64_t T, int64_t Bp, na_stream_t stream);
+
 /* ---- K5: trial averaging -----------------------------------------------------------------
  * Replaces tester.py:54,89,97 (and :90,98 for the chunk): fp32 zeros, += in trial order
  * r = 0..R-1, then one IEEE division by R.   in [R][N] -> out [N].

@@ -19,23 +19,10 @@
 //   B1 (25 chunks x 208 rows): Wih_hi x6 | Whh_hi x6 | bias(hi,lo) | Wih_lo x6 | Whh_lo x6;  rows 192.. = attention
 //   K16 MMAs pair two chunks through the descriptor's leading-byte-offset, so (x_lo | zeros), (x_hi | zeros) and
 //   (ones | zeros) pairs need no copies.  220 KB of shared memory; head parameters are read from global memory.
-#include "na_tc_common.cuh"
+#include "na_x3_common.cuh"
 
 namespace na {
 namespace tc {
-
-constexpr int kX3Threads = 14 * 32;
-constexpr int kX3XStages = 3;
-constexpr int kX3B0Chunks = 15, kX3B1Chunks = 25;
-constexpr int kX3N1 = 208;
-constexpr int kX3B1Chunk = kX3N1 * 16;
-constexpr int kX3Fc = NA_FC_HIDDEN;
-// Input range: raw EEG can carry DC offsets of 1e5 uV, beyond fp16's 65,504.  The producer stores x / 16 and the packed
-// W_ih of layer 0 is multiplied by 16 (both exact powers of two): samples up to 1e6 stay finite and values as small as
-// 1e-3 keep an absolute error below 5e-7 (fp16 subnormal spacing x 16) after the hi + lo split.
-constexpr float kX3XScale = 0.0625f, kX3XScaleInv = 16.0f;
-constexpr uint32_t kX3IdescL1 = make_idesc(kX3N1, kFmtVal, kFmtVal);
-constexpr uint32_t kX3IdescFlush = make_idesc(16, kFmtVal, kFmtVal);
 
 struct SmemX3 {
     alignas(128) unsigned char b0[kX3B0Chunks * kBChunk];          // 46,080
@@ -48,11 +35,6 @@ struct SmemX3 {
     uint64_t d0_full, d1_full, h0_ready[2], h1_ready;
     uint32_t tmem_base;
 };
-
-__device__ __forceinline__ void split16(float v, uint16_t& hi, uint16_t& lo) {
-    hi = val16(v);
-    lo = val16(v - val16_to_float(hi));
-}
 
 // ---- weight image: [B0 15 chunks][192][8] | [B1 25 chunks][192][8] fp16, row n = (j/4)*16 + gate*4 + j%4 ------------------
 __global__ void pack_decoder_x3_kernel(const float* __restrict__ w_ih0, const float* __restrict__ w_hh0,
@@ -89,52 +71,6 @@ __global__ void pack_decoder_x3_kernel(const float* __restrict__ w_ih0, const fl
         if (is_bias) r = kk == 0 ? hi : (kk == 1 ? lo : (uint16_t)0);      // the ones chunk is {1, 1, 0, ...}
         else r = want_lo ? lo : hi;
         out[idx] = r;
-    }
-}
-
-__device__ __forceinline__ void x3_tmem_ld2(uint32_t taddr, uint32_t (&v)[2]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// cell update of 4 units at fp32 accuracy; v = [i x4 | f x4 | g x4 | o x4] pre-activations.
-// The transcendental pipe bounds this kernel, so the reciprocals are combined algebraically: with E_i = e^-i, E_f = e^-f,
-// E_g = e^-2g (sigmoid(x) = 1 / (1 + e^-x), tanh(x) = (1 - e^-2x) / (1 + e^-2x))
-//     c' = f c + i g = [ c (1+E_i)(1+E_g) + (1-E_g)(1+E_f) ] / [ (1+E_f)(1+E_i)(1+E_g) ]          3 ex2 + 1 rcp
-//     h  = o tanh(c') = (1 - E_c) / [ (1+E_o)(1+E_c) ],  E_c = e^-2c'                              2 ex2 + 1 rcp
-// = 7 MUFU per cell instead of 10 (ex2 + rcp per activation).  Pre-activations are clamped where the functions are
-// already saturated in fp32 (|x| <= 28 for the sigmoids, <= 14 for the tanh arguments) so the products stay below 2^127.
-__device__ __forceinline__ void cell_granule_exact(const uint32_t* v, float* c, float* h) {
-    // an activation costs the scale (FMUL), one NaN-propagating min and one ex2: the cap keeps the products below 2^127,
-    // the lower side needs none (E -> 0).  cap 40: e^-x <= 2^40 <=> x >= -27.7, where sigmoid is 9e-13 and tanh is -1 to
-    // fp32 precision.  (Folding the scale into the packed weights saves the FMUL and 3 % of the time, but the rounding of
-    // the scaled weights pushed the worst case of 70,000 random short windows to 1.03e-5 against the FFMA kernels.)
-    constexpr float kL2e = 1.4426950408889634f;
-    auto capped_ex2 = [](float a) {
-        float r;
-        asm("min.NaN.f32 %0, %1, 0f42200000;" : "=f"(r) : "f"(a));        // min(a, 40.0f), NaN stays NaN
-        return ex2_approx(r);
-    };
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const float ei = capped_ex2(-kL2e * __uint_as_float(v[u])), ef = capped_ex2(-kL2e * __uint_as_float(v[4 + u]));
-        const float eg = capped_ex2(-2.0f * kL2e * __uint_as_float(v[8 + u])), eo = capped_ex2(-kL2e * __uint_as_float(v[12 + u]));
-        const float dig = (1.0f + ei) * (1.0f + eg);
-        const float df = 1.0f + ef;
-        const float num = fmaf(c[u], dig, (1.0f - eg) * df);
-        const float cn = num * rcp_approx(df * dig);
-        c[u] = cn;
-        const float ec = capped_ex2(-2.0f * kL2e * cn);
-        h[u] = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
-    }
-}
-
-// 8 fp32 values -> hi chunk entry and lo chunk entry (4 x fp16x2 each)
-__device__ __forceinline__ void split_pack8(const float* h, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        hi[u] = pack_val(h[2 * u], h[2 * u + 1]);
-        lo[u] = pack_val(h[2 * u] - val_lo(hi[u]), h[2 * u + 1] - val_hi(hi[u]));
     }
 }
 

@@ -1,0 +1,997 @@
+// Exact tier (fp32 contract, 1e-5 on logits AND gradients), TRAINING, on the tensor cores.
+//
+// Same idea as the exact inference kernel (na_decoder_x3.cu): every fp32 operand is split into two fp16 halves
+// (v = hi + lo + O(2^-22 |v|)) and every product is three tcgen05 MMAs (hi.hi + hi.lo + lo.hi) with fp32 accumulation in
+// TMEM; activations through ex2 / rcp (2e-7), never tanh.approx.  It replaces the FFMA recurrence / generic BPTT kernels
+// (na_lstm_h48.cu, na_lstm_generic.cu: 0.16 M windows/s per train step) at the flagship shape (C = 8, H = 48, 2 layers).
+//
+// One kernel per layer and direction, 128-window tiles (UMMA M = 128), 12 epilogue warps (TMEM lane quarter x 16-unit
+// group) + one MMA-issuing warp + one TMA producer lane, persistent over tiles:
+//
+//   lstm_fwd_x3_kernel<L>    gates_t = [in_t | 1 | h_{t-1}] . W (3-way split) -> cell update -> h_t, c_t saved
+//                            L = 0: also h0 after dropout (the input of layer 1);  L = 1: attention score as an extra
+//                            accumulator column of the NEXT step's MMA, online-softmax pooling -> z, (max, sum)
+//   lstm_bwd_x3_kernel<L>    per step, descending: G = the same gate recompute; epilogue: activations, d(gates) from
+//                            dh_t = dh_in_t + dh_rec, c_t, c_{t-1}; R: [din | dh_rec] = dG . [W_ih | W_hh] (the forward
+//                            weight image re-used as an MN-major B operand: no transposed copy); d(gates) go to shared
+//                            memory (A operand of R) and to HBM (hi / lo) for the weight-gradient kernel.
+//                            L = 1 fuses the time loop of the head backward (dh_t = alpha_t dz + ds_t w_a, centred form).
+//   lstm_wgrad_x3_kernel<L>  time-parallel dW = sum_{t, tile} [in_t | h_{t-1} | 1]^T . dG_t (3-way split, both operands
+//                            MN-major straight from the saved tile-chunk slabs), fp32 accumulation in TMEM over all the
+//                            work items of a CTA, per-CTA partials reduced in a fixed order (bit-reproducible).
+//
+// Layouts (tile = 128 consecutive windows, chunk = [128 rows][8 fp16] = 2 KB, the UMMA no-swizzle core-matrix layout):
+//   XS    fp16 [T][NT][2][128][8]     x / 16 split: chunk 0 = hi, 1 = lo                      (na_x3_split_input)
+//   TCLX  fp16 [T][NT][12][128][8]    h split: chunks 0-5 = hi (units 8c..8c+7), 6-11 = lo
+//   TCL32 fp32 [T][NT][12][128][4]    c, din (thread = window reads / writes 16 B, coalesced)
+//   DGX   fp16 [T][NT][48][128][8]    d(gates) split: chunks 0-23 = hi, 24-47 = lo; column n = (j/4)*16 + gate*4 + j%4
+#include "na_x3_common.cuh"
+
+namespace na {
+int reduce_partials(const float* partial, float* out, int nchunks, int64_t n, cudaStream_t st);   // na_reduce.cu
+namespace tc {
+
+constexpr int kTxThreads = 14 * 32;
+constexpr int kTxMmaWarp = 12, kTxTmaWarp = 13;
+constexpr int kTxStages = 3;
+
+__device__ __forceinline__ int64_t tclx_off(int t, int ntiles, int tile, int chunk, int row) {       // fp16 elements
+    return ((((int64_t)t * ntiles + tile) * 12 + chunk) * kRows + row) * 8;
+}
+__device__ __forceinline__ int64_t tcl32x_off(int t, int ntiles, int tile, int chunk, int row) {     // fp32 elements
+    return ((((int64_t)t * ntiles + tile) * 12 + chunk) * kRows + row) * 4;
+}
+__device__ __forceinline__ int64_t dgx_off(int t, int ntiles, int tile, int chunk, int row) {        // fp16 elements
+    return ((((int64_t)t * ntiles + tile) * 48 + chunk) * kRows + row) * 8;
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// input split: fp32 [B][T][8] -> XS (x / 16 as fp16 hi + lo), padding rows zero
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void x3_split_input_kernel(const float* __restrict__ x, __half* __restrict__ xs, int64_t B, int T, int64_t Bp) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one (t, padded row) per thread, t fastest
+    if (idx >= (int64_t)T * Bp) return;
+    const int64_t b = idx / T;
+    const int t = (int)(idx - b * T);
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (b < B) {
+        const float4 a0 = *reinterpret_cast<const float4*>(x + (b * T + t) * 8), a1 = *reinterpret_cast<const float4*>(x + (b * T + t) * 8 + 4);
+        f[0] = kX3XScale * a0.x; f[1] = kX3XScale * a0.y; f[2] = kX3XScale * a0.z; f[3] = kX3XScale * a0.w;
+        f[4] = kX3XScale * a1.x; f[5] = kX3XScale * a1.y; f[6] = kX3XScale * a1.z; f[7] = kX3XScale * a1.w;
+    }
+    uint32_t hi[4], lo[4];
+    split_pack8(f, hi, lo);
+    const int ntiles = (int)(Bp / kRows);
+    const int tile = (int)(b / kRows), row = (int)(b % kRows);
+    __half* dst = xs + ((((int64_t)t * ntiles + tile) * 2) * kRows + row) * 8;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst + kRows * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward of one layer with saves
+// ---------------------------------------------------------------------------------------------------------------
+template <int LAYER>
+struct TxFwdSmem {
+    static constexpr int kBBytes = LAYER == 0 ? kX3B0Chunks * kBChunk : kX3B1Chunks * kX3B1Chunk;
+    static constexpr int kInChunks = LAYER == 0 ? 2 : 12;
+    alignas(128) unsigned char b[kBBytes];
+    alignas(128) unsigned char in[kTxStages][kInChunks * kAChunk];
+    alignas(128) unsigned char h[12 * kAChunk];                     // h_{t-1}: hi x6 | lo x6
+    alignas(128) unsigned char onez[2 * kAChunk];                   // [ones | zeros]
+    alignas(8) uint64_t in_full[kTxStages], in_empty[kTxStages];
+    uint64_t d_full, h_ready;
+    uint32_t tmem_base;
+};
+
+template <int LAYER>
+__global__ void __launch_bounds__(kTxThreads, 1)
+lstm_fwd_x3_kernel(const __half* __restrict__ in,                   // L0: XS;  L1: TCLX (h0, or h0 after dropout)
+                   const unsigned char* __restrict__ packed,        // this layer's part of the pack_decoder_x3_kernel image
+                   const float* __restrict__ attn_w, const float* __restrict__ attn_b,        // L1
+                   const unsigned char* __restrict__ mask, uint64_t seed, uint32_t thresh16, float drop_scale,   // L0: dropout of h0
+                   __half* __restrict__ h_out, __half* __restrict__ hd_out, float* __restrict__ c_out,
+                   float* __restrict__ zpool, float* __restrict__ stats, int64_t B,          // L1
+                   int T, int64_t Bp, int ntiles) {
+    using SM = TxFwdSmem<LAYER>;
+    constexpr int kInChunks = SM::kInChunks;
+    constexpr int kNW = LAYER == 0 ? kN : kX3N1;                      // accumulator columns (L1: + 16 score columns)
+    constexpr int kBStride = LAYER == 0 ? kBChunk : kX3B1Chunk;
+    constexpr uint32_t kIdescG = make_idesc(kNW, kFmtVal, kFmtVal);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    // ---- one-time setup ---------------------------------------------------------------------------------------
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(packed);
+        if (LAYER == 0) {
+            uint4* d0 = reinterpret_cast<uint4*>(S.b);
+            for (int i = tid; i < kX3B0Chunks * kBChunk / 16; i += kTxThreads) d0[i] = src[i];
+        } else {
+            for (int i = tid; i < kX3B1Chunks * kN; i += kTxThreads) {
+                const int ch = i / kN, r = i % kN;
+                reinterpret_cast<uint4*>(S.b + ch * kX3B1Chunk)[r] = src[i];
+            }
+            // rows 192..207 of every chunk: row 192 = the attention vector split like the weights, the rest zero
+            for (int i = tid; i < kX3B1Chunks * 16; i += kTxThreads) {
+                const int ch = i / 16, r = i % 16;
+                uint16_t w[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    uint16_t val = 0;
+                    if (r == 0) {
+                        uint16_t hi, lo;
+                        if (ch >= 6 && ch <= 11) { split16(attn_w[(ch - 6) * 8 + e], hi, lo); val = hi; }
+                        else if (ch >= 19) { split16(attn_w[(ch - 19) * 8 + e], hi, lo); val = lo; }
+                        else if (ch == 12) { split16(attn_b[0], hi, lo); val = e == 0 ? hi : (e == 1 ? lo : (uint16_t)0); }
+                    }
+                    w[e] = val;
+                }
+                uint4 pk;
+                pk.x = w[0] | ((uint32_t)w[1] << 16); pk.y = w[2] | ((uint32_t)w[3] << 16);
+                pk.z = w[4] | ((uint32_t)w[5] << 16); pk.w = w[6] | ((uint32_t)w[7] << 16);
+                reinterpret_cast<uint4*>(S.b + ch * kX3B1Chunk)[kN + r] = pk;
+            }
+        }
+        const uint4 ones = make_uint4(kValOnes2, 0u, 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < kRows; i += kTxThreads) {
+            reinterpret_cast<uint4*>(S.onez)[i] = ones;
+            reinterpret_cast<uint4*>(S.onez + kAChunk)[i] = zero;
+        }
+        if (tid == 0) {
+            for (int s = 0; s < kTxStages; ++s) { mbar_init(&S.in_full[s], 1); mbar_init(&S.in_empty[s], 1); }
+            mbar_init(&S.d_full, 1);
+            mbar_init(&S.h_ready, 12 * 32);
+            fence_mbar_init();
+        }
+        if (warp == kTxTmaWarp) tmem_alloc_all(&S.tmem_base);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncthreads();
+        tc_fence_after();
+    }
+    const uint32_t tmem_d = __shfl_sync(0xffffffffu, S.tmem_base, 0);
+    const bool drop = LAYER == 0 && hd_out != nullptr;
+
+    uint32_t in_cnt = 0;                         // producer / MMA: input stages produced / consumed
+    uint32_t hr_cnt = 0;                         // MMA: h_ready phases consumed
+    uint32_t df_cnt = 0;                         // epilogue: d_full phases consumed
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t b0 = (int64_t)tile * kRows;
+        if (warp == kTxTmaWarp) {
+            if (lane == 0)
+                for (int t = 0; t < T; ++t, ++in_cnt) {
+                    const uint32_t s = in_cnt % kTxStages, u = in_cnt / kTxStages;
+                    mbar_wait(&S.in_empty[s], (u & 1) ^ 1);
+                    mbar_arrive_expect_tx(&S.in_full[s], kInChunks * kAChunk);
+                    bulk_load(S.in[s], in + (((int64_t)t * ntiles + tile) * kInChunks) * (kAChunk / 2), kInChunks * kAChunk, &S.in_full[s]);
+                }
+        } else if (warp == kTxMmaWarp) {
+            const bool leader = elect_one();
+            const uint32_t a_ones = smem_u32(S.onez), a_zero = a_ones + kAChunk;
+            const uint64_t d_b = umma_desc(smem_u32(S.b), kBStride, 128);
+            const uint64_t d_h = umma_desc(smem_u32(S.h), kAChunk, 128);
+            const uint64_t d_bias = umma_desc(a_ones, kAChunk, 128);                              // (ones | zeros)
+            for (int t = 0; t < T; ++t, ++in_cnt) {
+                const uint32_t s = in_cnt % kTxStages, u = in_cnt / kTxStages;
+                mbar_wait(&S.in_full[s], u & 1);
+                if (t >= 1) { mbar_wait(&S.h_ready, hr_cnt & 1); ++hr_cnt; }
+                tc_fence_after();
+                const uint32_t xs = smem_u32(S.in[s]);
+                if (LAYER == 0) {
+                    if (leader) {
+                        // (x_hi | ones) . (Wih_hi | bias);  (x_hi | zeros) . (Wih_lo | *);  (x_lo | zeros) . (Wih_hi | *)
+                        umma_bf16_i(tmem_d, umma_desc(xs, a_ones - xs, 128), d_b, kIdescG, 0u);
+                        umma_bf16_i(tmem_d, umma_desc(xs, a_zero - xs, 128), desc_adv(d_b, 8 * kBStride), kIdescG, 1u);
+                        umma_bf16_i(tmem_d, umma_desc(xs + kAChunk, a_zero - (xs + kAChunk), 128), d_b, kIdescG, 1u);
+                    }
+                    if (t >= 1) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+                            if (leader) {
+                                umma_bf16_i(tmem_d, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_b, (2 + 2 * i) * kBStride), kIdescG, 1u);
+                                umma_bf16_i(tmem_d, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_b, (9 + 2 * i) * kBStride), kIdescG, 1u);
+                                umma_bf16_i(tmem_d, desc_adv(d_h, (6 + 2 * i) * kAChunk), desc_adv(d_b, (2 + 2 * i) * kBStride), kIdescG, 1u);
+                            }
+                    }
+                } else {
+                    const uint64_t d_in = umma_desc(xs, kAChunk, 128);
+                    if (leader) umma_bf16_i(tmem_d, d_bias, desc_adv(d_b, 12 * kBStride), kIdescG, 0u);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        if (leader) {
+                            umma_bf16_i(tmem_d, desc_adv(d_in, 2 * i * kAChunk), desc_adv(d_b, 2 * i * kBStride), kIdescG, 1u);
+                            umma_bf16_i(tmem_d, desc_adv(d_in, 2 * i * kAChunk), desc_adv(d_b, (13 + 2 * i) * kBStride), kIdescG, 1u);
+                            umma_bf16_i(tmem_d, desc_adv(d_in, (6 + 2 * i) * kAChunk), desc_adv(d_b, 2 * i * kBStride), kIdescG, 1u);
+                        }
+                    if (t >= 1) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+                            if (leader) {
+                                umma_bf16_i(tmem_d, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_b, (6 + 2 * i) * kBStride), kIdescG, 1u);
+                                umma_bf16_i(tmem_d, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_b, (19 + 2 * i) * kBStride), kIdescG, 1u);
+                                umma_bf16_i(tmem_d, desc_adv(d_h, (6 + 2 * i) * kAChunk), desc_adv(d_b, (6 + 2 * i) * kBStride), kIdescG, 1u);
+                            }
+                    }
+                }
+                if (leader) umma_commit(&S.in_empty[s]);
+                if (leader) umma_commit(&S.d_full);
+            }
+            // the last h of the tile has been written (and the accumulator drained)
+            mbar_wait(&S.h_ready, hr_cnt & 1); ++hr_cnt;
+            tc_fence_after();
+            if (LAYER == 1) {   // flush: score of the last step into the 16 score columns
+                const uint64_t d_bs = desc_adv(d_b, kN * 16);
+                if (leader) umma_bf16_i(tmem_d + kN, d_bias, desc_adv(d_bs, 12 * kBStride), kX3IdescFlush, 0u);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    if (leader) {
+                        umma_bf16_i(tmem_d + kN, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_bs, (6 + 2 * i) * kBStride), kX3IdescFlush, 1u);
+                        umma_bf16_i(tmem_d + kN, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_bs, (19 + 2 * i) * kBStride), kX3IdescFlush, 1u);
+                        umma_bf16_i(tmem_d + kN, desc_adv(d_h, (6 + 2 * i) * kAChunk), desc_adv(d_bs, (6 + 2 * i) * kBStride), kX3IdescFlush, 1u);
+                    }
+                if (leader) umma_commit(&S.d_full);
+            }
+        } else {
+            // ================= epilogue: (lane quarter q, 16-unit group g) =========================================
+            const int q = warp & 3, g = warp >> 2;
+            const int row = q * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+            const int gr0 = 4 * g;                                   // first of this thread's four 4-unit granules
+            float c[16], hprev[16], z[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { c[j] = 0.f; hprev[j] = 0.f; z[j] = 0.f; }
+            float mx = -INFINITY, l = 0.f;
+            auto pool = [&](float score) {                           // online softmax over time (lstm_eeg_model.py:35-37), fp32
+                if (score > mx) {
+                    const float sc = expf(mx - score);
+                    l *= sc;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) z[j] *= sc;
+                    mx = score;
+                }
+                const float e = expf(score - mx);
+                l += e;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) z[j] = fmaf(e, hprev[j], z[j]);
+            };
+            for (int t = 0; t < T; ++t) {
+                const int64_t grow = (int64_t)t * Bp + b0 + row;
+                uint32_t keep[2] = {0xFFu, 0xFFu};
+                if (drop) {
+#pragma unroll
+                    for (int pr = 0; pr < 2; ++pr) {
+                        const int blk = 2 * g + pr;
+                        keep[pr] = mask ? mask_keep8(*reinterpret_cast<const uint2*>(mask + grow * kH + blk * 8))
+                                        : dropout_keep8(seed, grow, blk, thresh16);
+                    }
+                }
+                mbar_wait(&S.d_full, df_cnt & 1); ++df_cnt;
+                tc_fence_after();
+                if (LAYER == 1) {
+                    uint32_t sc2[2];
+                    x3_tmem_ld2(tmem_d + lane_base + kN, sc2);
+                    if (t >= 1) pool(__uint_as_float(sc2[0]));       // score of h_{t-1}, which is still in hprev
+                }
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {                      // pairs of granules = one 8-unit chunk
+                    uint32_t v[32], hi[4], lo[4];
+                    tmem_ld32(tmem_d + lane_base + (gr0 + 2 * pr) * 16, v);
+                    cell_granule_exact(v, c + pr * 8, hprev + pr * 8);
+                    cell_granule_exact(v + 16, c + pr * 8 + 4, hprev + pr * 8 + 4);
+                    split_pack8(hprev + pr * 8, hi, lo);
+                    const int chunk = 2 * g + pr;
+                    st_shared_v4(S.h + chunk * kAChunk + row * 16, hi[0], hi[1], hi[2], hi[3]);
+                    st_shared_v4(S.h + (6 + chunk) * kAChunk + row * 16, lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(h_out + tclx_off(t, ntiles, tile, chunk, row)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(h_out + tclx_off(t, ntiles, tile, 6 + chunk, row)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<float4*>(c_out + tcl32x_off(t, ntiles, tile, 2 * chunk, row)) =
+                        make_float4(c[pr * 8], c[pr * 8 + 1], c[pr * 8 + 2], c[pr * 8 + 3]);
+                    *reinterpret_cast<float4*>(c_out + tcl32x_off(t, ntiles, tile, 2 * chunk + 1, row)) =
+                        make_float4(c[pr * 8 + 4], c[pr * 8 + 5], c[pr * 8 + 6], c[pr * 8 + 7]);
+                    if (drop) {
+                        float hd[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) hd[u] = ((keep[pr] >> u) & 1u) ? hprev[pr * 8 + u] * drop_scale : 0.f;
+                        uint32_t dhi[4], dlo[4];
+                        split_pack8(hd, dhi, dlo);
+                        *reinterpret_cast<uint4*>(hd_out + tclx_off(t, ntiles, tile, chunk, row)) = make_uint4(dhi[0], dhi[1], dhi[2], dhi[3]);
+                        *reinterpret_cast<uint4*>(hd_out + tclx_off(t, ntiles, tile, 6 + chunk, row)) = make_uint4(dlo[0], dlo[1], dlo[2], dlo[3]);
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(&S.h_ready);
+            }
+            if (LAYER == 1) {
+                mbar_wait(&S.d_full, df_cnt & 1); ++df_cnt;              // flush: score of the last step
+                tc_fence_after();
+                uint32_t sc2[2];
+                x3_tmem_ld2(tmem_d + lane_base + kN, sc2);
+                tc_fence_before();
+                pool(__uint_as_float(sc2[0]));
+                const int64_t b = b0 + row;
+                if (b < B) {
+                    const float inv_l = 1.0f / l;
+                    float* zo = zpool + b * kH + 16 * g;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(zo + j) = make_float4(z[j] * inv_l, z[j + 1] * inv_l, z[j + 2] * inv_l, z[j + 3] * inv_l);
+                    if (g == 0) { stats[2 * b] = mx; stats[2 * b + 1] = l; }
+                }
+            }
+        }
+        __syncthreads();       // tile done: every MMA of the tile has completed and its accumulator has been read
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kTxTmaWarp) { tc_fence_after(); tmem_free_all(tmem_d); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward of one layer
+// ---------------------------------------------------------------------------------------------------------------
+template <int LAYER>
+struct TxBwdSmem {
+    static constexpr int kBChunks = LAYER == 0 ? kX3B0Chunks : kX3B1Chunks;
+    static constexpr int kActChunks = LAYER == 0 ? 14 : 24;          // L0: [x_hi | x_lo | hp hi x6 | hp lo x6];  L1: [in hi x6 | lo x6 | hp hi x6 | lo x6]
+    alignas(128) unsigned char b[kBChunks * kBChunk];                // forward weight image (192 rows per chunk)
+    alignas(128) unsigned char act[kActChunks * kAChunk];
+    alignas(128) unsigned char dg[48 * kAChunk];                     // d(gates): hi x24 | lo x24
+    alignas(128) unsigned char onez[2 * kAChunk];
+    alignas(8) uint64_t act_full, act_free;
+    uint64_t g_full, dg_ready;
+    uint32_t tmem_base;
+    float wa[kH];
+    float ba;
+    float2 xch[3][kRows];                                           // fused head backward: per-step exchange of the 3 unit-group warps
+};
+
+// gates of one cell at fp32 accuracy: 5 ex2 + 2 rcp (the reciprocals of each group are combined)
+__device__ __forceinline__ void gates_exact(float vi, float vf, float vg, float vo, float ct,
+                                            float& gi, float& gf, float& gg, float& go, float& tcv) {
+    constexpr float kL2e = 1.4426950408889634f;
+    auto capped_ex2 = [](float a) {
+        float r;
+        asm("min.NaN.f32 %0, %1, 0f42200000;" : "=f"(r) : "f"(a));
+        return ex2_approx(r);
+    };
+    const float ei = capped_ex2(-kL2e * vi), ef = capped_ex2(-kL2e * vf), eg = capped_ex2(-2.0f * kL2e * vg);
+    const float eo = capped_ex2(-kL2e * vo), ec = capped_ex2(-2.0f * kL2e * ct);
+    const float a = 1.0f + ei, b = 1.0f + ef, cc = 1.0f + eg;
+    const float ab = a * b;
+    const float r1 = rcp_approx(ab * cc);                            // <= 2^120: finite
+    gi = r1 * (b * cc);
+    gf = r1 * (a * cc);
+    gg = (1.0f - eg) * (r1 * ab);
+    const float d = 1.0f + eo, e = 1.0f + ec;
+    const float r2 = rcp_approx(d * e);
+    go = r2 * e;
+    tcv = (1.0f - ec) * (r2 * d);
+}
+
+template <int LAYER>
+__global__ void __launch_bounds__(kTxThreads, 1)
+lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  L1: TCLX (the layer's forward input)
+                   const __half* __restrict__ h,                    // TCLX: this layer's h
+                   const float* __restrict__ cstate,                // TCL32
+                   const float* __restrict__ dh_in,                 // TCL32 (L0: din of layer 1;  L1 without fused head)
+                   const unsigned char* __restrict__ packed,        // this layer's part of the x3 weight image
+                   const __half* __restrict__ zeros,                // >= 24 KB of zeros (h_{-1})
+                   const unsigned char* __restrict__ mask, uint64_t seed, uint32_t thresh16, float drop_scale,   // L1: dropout of its input
+                   float* __restrict__ din,                         // TCL32, L1 only
+                   __half* __restrict__ dg_out,                     // DGX
+                   const float* __restrict__ dz, const float* __restrict__ stats, const float* __restrict__ zpool,
+                   const float* __restrict__ attn_w, const float* __restrict__ attn_b, int64_t B,
+                   float* __restrict__ attn_partial,                // [grid][52]: d attn_w | d attn_b
+                   int T, int64_t Bp, int ntiles) {
+    using SM = TxBwdSmem<LAYER>;
+    constexpr int kInChunks = LAYER == 0 ? 2 : 12;
+    constexpr int kHp = LAYER == 0 ? 2 : 12;                         // first h_{t-1} chunk of the act stage
+    constexpr int kNR = LAYER == 0 ? 48 : 96;                        // columns of D_R: [din (48) |] dh_rec (48)
+    constexpr int kRecCol = LAYER == 0 ? 0 : 48;
+    constexpr uint32_t kIdescG = make_idesc(kN, kFmtVal, kFmtVal);
+    constexpr uint32_t kIdescR = make_idesc(kNR, kFmtVal, kFmtVal, false, true);      // dG (K-major) x W image (MN-major)
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(packed);
+        uint4* db = reinterpret_cast<uint4*>(S.b);
+        for (int i = tid; i < SM::kBChunks * kBChunk / 16; i += kTxThreads) db[i] = src[i];
+        const uint4 ones = make_uint4(kValOnes2, 0u, 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < kRows; i += kTxThreads) {
+            reinterpret_cast<uint4*>(S.onez)[i] = ones;
+            reinterpret_cast<uint4*>(S.onez + kAChunk)[i] = zero;
+        }
+        if (tid == 0) {
+            mbar_init(&S.act_full, 1); mbar_init(&S.act_free, 1);
+            mbar_init(&S.g_full, 1);
+            mbar_init(&S.dg_ready, 12 * 32);
+            fence_mbar_init();
+        }
+        if (dz != nullptr) {
+            for (int i = tid; i < kH; i += kTxThreads) S.wa[i] = attn_w[i];
+            if (tid == 0) S.ba = attn_b[0];
+        }
+        if (warp == kTxTmaWarp) tmem_alloc_all(&S.tmem_base);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncthreads();
+        tc_fence_after();
+    }
+    const bool head = LAYER == 1 && dz != nullptr;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, S.tmem_base, 0);
+    const uint32_t tm_g = tmem, tm_r = tmem + kN;
+    float dwa[16], dba = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dwa[j] = 0.f;
+
+    uint32_t act_cnt = 0, dgp = 0, gphase = 0;       // role-private running phase counters
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t b0 = (int64_t)tile * kRows;
+        if (warp == kTxTmaWarp) {
+            // ================= TMA producer: [in_t | h_{t-1}] for t = T-1 .. 0 (single stage) =====================
+            if (lane == 0)
+                for (int i = 0; i < T; ++i, ++act_cnt) {
+                    const int t = T - 1 - i;
+                    mbar_wait(&S.act_free, (act_cnt & 1) ^ 1);
+                    mbar_arrive_expect_tx(&S.act_full, (kInChunks + 12) * kAChunk);
+                    bulk_load(S.act, act_in + (((int64_t)t * ntiles + tile) * kInChunks) * (kAChunk / 2), kInChunks * kAChunk, &S.act_full);
+                    const __half* hsrc = t > 0 ? h + tclx_off(t - 1, ntiles, tile, 0, 0) : zeros;
+                    bulk_load(S.act + kHp * kAChunk, hsrc, 12 * kAChunk, &S.act_full);
+                }
+        } else if (warp == kTxMmaWarp) {
+            // ================= MMA issuer: per iteration  R(t+1) -> G(t) -> commit ================================
+            const bool leader = elect_one();
+            const uint32_t a_act = smem_u32(S.act), a_ones = smem_u32(S.onez), a_zero = a_ones + kAChunk;
+            const uint64_t d_b = umma_desc(smem_u32(S.b), kBChunk, 128);                    // K-major (gate recompute)
+            const uint64_t d_bm = umma_desc(smem_u32(S.b), 128, kBChunk);                   // MN-major: N = input feature, K = gate row
+            const uint64_t d_dgk = umma_desc(smem_u32(S.dg), kAChunk, 128);                 // d(gates), K-major A
+            const uint64_t d_hp = umma_desc(a_act + kHp * kAChunk, kAChunk, 128);
+            const uint64_t d_in = umma_desc(a_act, kAChunk, 128);
+            const uint64_t d_bias = umma_desc(a_ones, kAChunk, 128);
+            // first weight chunk of the R operand: L0: W_hh (chunks 2..7 hi, 9..14 lo);  L1: [W_ih | W_hh] (0..11 hi, 13..24 lo)
+            constexpr int kRHi = LAYER == 0 ? 2 : 0, kRLo = LAYER == 0 ? 9 : 13;
+            for (int i = 0; i <= T; ++i) {
+                if (i >= 1) {
+                    mbar_wait(&S.dg_ready, dgp & 1); ++dgp;
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 12; ++ks)
+                        if (leader) {
+                            const uint64_t ahi = desc_adv(d_dgk, 2 * ks * kAChunk), alo = desc_adv(d_dgk, (24 + 2 * ks) * kAChunk);
+                            umma_bf16_i(tm_r, ahi, desc_adv(d_bm, kRHi * kBChunk + ks * 256), kIdescR, ks == 0 ? 0u : 1u);
+                            umma_bf16_i(tm_r, ahi, desc_adv(d_bm, kRLo * kBChunk + ks * 256), kIdescR, 1u);
+                            umma_bf16_i(tm_r, alo, desc_adv(d_bm, kRHi * kBChunk + ks * 256), kIdescR, 1u);
+                        }
+                }
+                if (i < T) {
+                    mbar_wait(&S.act_full, act_cnt & 1); ++act_cnt;
+                    tc_fence_after();
+                    if (LAYER == 0) {
+                        if (leader) {
+                            umma_bf16_i(tm_g, umma_desc(a_act, a_ones - a_act, 128), d_b, kIdescG, 0u);
+                            umma_bf16_i(tm_g, umma_desc(a_act, a_zero - a_act, 128), desc_adv(d_b, 8 * kBChunk), kIdescG, 1u);
+                            umma_bf16_i(tm_g, umma_desc(a_act + kAChunk, a_zero - (a_act + kAChunk), 128), d_b, kIdescG, 1u);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            if (leader) {
+                                umma_bf16_i(tm_g, desc_adv(d_hp, 2 * k * kAChunk), desc_adv(d_b, (2 + 2 * k) * kBChunk), kIdescG, 1u);
+                                umma_bf16_i(tm_g, desc_adv(d_hp, 2 * k * kAChunk), desc_adv(d_b, (9 + 2 * k) * kBChunk), kIdescG, 1u);
+                                umma_bf16_i(tm_g, desc_adv(d_hp, (6 + 2 * k) * kAChunk), desc_adv(d_b, (2 + 2 * k) * kBChunk), kIdescG, 1u);
+                            }
+                    } else {
+                        if (leader) umma_bf16_i(tm_g, d_bias, desc_adv(d_b, 12 * kBChunk), kIdescG, 0u);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            if (leader) {
+                                umma_bf16_i(tm_g, desc_adv(d_in, 2 * k * kAChunk), desc_adv(d_b, 2 * k * kBChunk), kIdescG, 1u);
+                                umma_bf16_i(tm_g, desc_adv(d_in, 2 * k * kAChunk), desc_adv(d_b, (13 + 2 * k) * kBChunk), kIdescG, 1u);
+                                umma_bf16_i(tm_g, desc_adv(d_in, (6 + 2 * k) * kAChunk), desc_adv(d_b, 2 * k * kBChunk), kIdescG, 1u);
+                                umma_bf16_i(tm_g, desc_adv(d_hp, 2 * k * kAChunk), desc_adv(d_b, (6 + 2 * k) * kBChunk), kIdescG, 1u);
+                                umma_bf16_i(tm_g, desc_adv(d_hp, 2 * k * kAChunk), desc_adv(d_b, (19 + 2 * k) * kBChunk), kIdescG, 1u);
+                                umma_bf16_i(tm_g, desc_adv(d_hp, (6 + 2 * k) * kAChunk), desc_adv(d_b, (6 + 2 * k) * kBChunk), kIdescG, 1u);
+                            }
+                    }
+                    if (leader) umma_commit(&S.act_free);      // the stage may be refilled as soon as G has read it
+                }
+                if (leader) umma_commit(&S.g_full);            // R(t+1) and G(t) done; i == T: tail (R only)
+            }
+        } else {
+            // ================= epilogue: thread = window row x 16 units ===========================================
+            const int q = warp & 3, g = warp >> 2;
+            const int row = q * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+            const int gr0 = 4 * g;
+            float dc[16], ccur[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dc[j] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(cstate + tcl32x_off(T - 1, ntiles, tile, gr0 + j / 4, row));
+                ccur[j] = a.x; ccur[j + 1] = a.y; ccur[j + 2] = a.z; ccur[j + 3] = a.w;
+            }
+            float dzr[16], zr[16], sm_m = 0.f, inv_l = 1.f;
+            if (head) {
+                const int64_t b = b0 + row;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    dzr[j] = (b < B) ? dz[b * kH + 16 * g + j] : 0.f;
+                    zr[j] = (b < B) ? zpool[b * kH + 16 * g + j] : 0.f;
+                }
+                if (b < B) { sm_m = stats[2 * b]; inv_l = 1.0f / stats[2 * b + 1]; }
+            }
+            for (int i = 0; i <= T; ++i) {
+                const int t = T - 1 - i;
+                float cp[16], dh[16];
+                if (i < T) {
+                    // ---- prefetch c_{t-1} and this step's dh BEFORE waiting for the tensor pipe -------------------
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (t > 0) c4 = *reinterpret_cast<const float4*>(cstate + tcl32x_off(t - 1, ntiles, tile, gr0 + j / 4, row));
+                        cp[j] = c4.x; cp[j + 1] = c4.y; cp[j + 2] = c4.z; cp[j + 3] = c4.w;
+                    }
+                    if (head) {
+                        // head backward, time loop (lstm_eeg_model.py:35-37): alpha_t = softmax weight, centred form
+                        // ds_t = alpha_t dz . (h_t - z) (no cancellation), dh_t = alpha_t dz + ds_t w_a
+                        float hv[16];
+#pragma unroll
+                        for (int pr = 0; pr < 2; ++pr) {
+                            const uint4 ph = *reinterpret_cast<const uint4*>(h + tclx_off(t, ntiles, tile, 2 * g + pr, row));
+                            const uint4 pl = *reinterpret_cast<const uint4*>(h + tclx_off(t, ntiles, tile, 6 + 2 * g + pr, row));
+                            const uint32_t wh[4] = {ph.x, ph.y, ph.z, ph.w}, wl[4] = {pl.x, pl.y, pl.z, pl.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                hv[pr * 8 + 2 * u] = val_lo(wh[u]) + val_lo(wl[u]);
+                                hv[pr * 8 + 2 * u + 1] = val_hi(wh[u]) + val_hi(wl[u]);
+                            }
+                        }
+                        float sp = 0.f, gp = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { sp = fmaf(S.wa[16 * g + j], hv[j], sp); gp = fmaf(dzr[j], hv[j] - zr[j], gp); }
+                        S.xch[g][row] = make_float2(sp, gp);
+                        named_bar_sync(1 + q, 96);
+                        float xs = 0.f, xg = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) { const float2 xe = S.xch[e][row]; xs += xe.x; xg += xe.y; }   // fixed order
+                        named_bar_sync(1 + q, 96);                    // single exchange buffer (shared memory is full): read before rewrite
+                        const float alpha = expf(xs + S.ba - sm_m) * inv_l;
+                        const float ds = alpha * xg;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            dh[j] = fmaf(alpha, dzr[j], ds * S.wa[16 * g + j]);
+                            dwa[j] = fmaf(ds, hv[j], dwa[j]);
+                        }
+                        dba += ds;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 d4 = *reinterpret_cast<const float4*>(dh_in + tcl32x_off(t, ntiles, tile, gr0 + j / 4, row));
+                            dh[j] = d4.x; dh[j + 1] = d4.y; dh[j + 2] = d4.z; dh[j + 3] = d4.w;
+                        }
+                    }
+                }
+                mbar_wait(&S.g_full, gphase & 1); ++gphase;
+                tc_fence_after();
+                if (i >= 1) {
+                    if (LAYER == 1) {
+                        // din of step t+1 = D_R[:, 0:48] (x dropout mask x scale) -> dh_in of layer 0
+                        uint32_t r[16];
+                        tmem_ld16(tm_r + lane_base + 16 * g, r);
+                        const int64_t grow = (int64_t)(t + 1) * Bp + b0 + row;
+#pragma unroll
+                        for (int pr = 0; pr < 2; ++pr) {
+                            float o[8];
+                            if (mask || thresh16 < 65536u) {
+                                const int blk = 2 * g + pr;
+                                const uint32_t keep = mask ? mask_keep8(*reinterpret_cast<const uint2*>(mask + grow * kH + blk * 8))
+                                                           : dropout_keep8(seed, grow, blk, thresh16);
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) o[u] = ((keep >> u) & 1u) ? __uint_as_float(r[pr * 8 + u]) * drop_scale : 0.f;
+                            } else {
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) o[u] = __uint_as_float(r[pr * 8 + u]);
+                            }
+                            *reinterpret_cast<float4*>(din + tcl32x_off(t + 1, ntiles, tile, gr0 + 2 * pr, row)) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4*>(din + tcl32x_off(t + 1, ntiles, tile, gr0 + 2 * pr + 1, row)) = make_float4(o[4], o[5], o[6], o[7]);
+                        }
+                    }
+                    if (i < T) {
+                        uint32_t r[16];
+                        tmem_ld16(tm_r + lane_base + kRecCol + 16 * g, r);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) dh[j] += __uint_as_float(r[j]);
+                    }
+                }
+                if (i == T) break;
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {
+                    uint32_t v[32];
+                    tmem_ld32(tm_g + lane_base + (gr0 + 2 * pr) * 16, v);
+#pragma unroll
+                    for (int gi = 0; gi < 2; ++gi) {
+                        float pi[4], pf[4], pg[4], po[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = pr * 8 + gi * 4 + u;
+                            float a_i, a_f, a_g, a_o, tcv;
+                            gates_exact(__uint_as_float(v[gi * 16 + u]), __uint_as_float(v[gi * 16 + 4 + u]), __uint_as_float(v[gi * 16 + 8 + u]),
+                                        __uint_as_float(v[gi * 16 + 12 + u]), ccur[j], a_i, a_f, a_g, a_o, tcv);
+                            const float d_o = dh[j] * tcv;
+                            const float dct = fmaf(dh[j] * a_o, 1.0f - tcv * tcv, dc[j]);
+                            dc[j] = dct * a_f;
+                            pi[u] = dct * a_g * a_i * (1.0f - a_i);
+                            pf[u] = dct * cp[j] * a_f * (1.0f - a_f);
+                            pg[u] = dct * a_i * (1.0f - a_g * a_g);
+                            po[u] = d_o * a_o * (1.0f - a_o);
+                            ccur[j] = cp[j];                           // c_{t-1} is the next iteration's c_t
+                        }
+                        // granule G -> columns 16 G .. 16 G + 15 = chunks 2 G ([i x4 | f x4]) and 2 G + 1 ([g x4 | o x4])
+                        const int G = gr0 + 2 * pr + gi;
+                        const float e0[8] = {pi[0], pi[1], pi[2], pi[3], pf[0], pf[1], pf[2], pf[3]};
+                        const float e1[8] = {pg[0], pg[1], pg[2], pg[3], po[0], po[1], po[2], po[3]};
+                        uint32_t hi[4], lo[4];
+                        split_pack8(e0, hi, lo);
+                        st_shared_v4(S.dg + (2 * G) * kAChunk + row * 16, hi[0], hi[1], hi[2], hi[3]);
+                        st_shared_v4(S.dg + (24 + 2 * G) * kAChunk + row * 16, lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 2 * G, row)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 24 + 2 * G, row)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        split_pack8(e1, hi, lo);
+                        st_shared_v4(S.dg + (2 * G + 1) * kAChunk + row * 16, hi[0], hi[1], hi[2], hi[3]);
+                        st_shared_v4(S.dg + (24 + 2 * G + 1) * kAChunk + row * 16, lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 2 * G + 1, row)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 24 + 2 * G + 1, row)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(&S.dg_ready);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- per-CTA partial of d attn_w / d attn_b (fused head backward) ---------------------------------------------
+    if (head) {
+        float* red = reinterpret_cast<float*>(S.dg);               // [12 warps][17]; every MMA has completed (tile-end barrier)
+        if (warp < 12) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float v = warp_sum(dwa[j]);
+                if (lane == 0) red[warp * 17 + j] = v;
+            }
+            const float vb = warp_sum(dba);
+            if (lane == 0) red[warp * 17 + 16] = vb;
+        }
+        __syncthreads();
+        if (tid < kH) {
+            const int g = tid / 16, j = tid % 16;
+            attn_partial[(size_t)blockIdx.x * 52 + tid] =
+                red[(4 * g) * 17 + j] + red[(4 * g + 1) * 17 + j] + red[(4 * g + 2) * 17 + j] + red[(4 * g + 3) * 17 + j];
+        } else if (tid == kH) {
+            attn_partial[(size_t)blockIdx.x * 52 + kH] = red[16] + red[17 + 16] + red[2 * 17 + 16] + red[3 * 17 + 16];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kTxTmaWarp) { tc_fence_after(); tmem_free_all(tmem); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight gradients: dW^T[feature][gate column] = sum over (t, tile) of act^T . dG, both operands MN-major
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWgThreads = 6 * 32;            // warps 0-3: final readout, 4: MMA issuer, 5: TMA producer
+struct TxWgSmem {
+    alignas(128) unsigned char act[2][32 * kAChunk];     // hi block = chunks 0..15, lo block = chunks 16..31 (see below)
+    alignas(128) unsigned char dg[2][16 * kAChunk];      // one 64-column group: hi x8 | lo x8
+    alignas(8) uint64_t act_full[2], act_empty[2], dg_full[2], dg_empty[2];
+    uint64_t done;
+    uint32_t tmem_base;
+};
+// act stage, feature rows of the accumulator (M = 128 = 16 chunks):
+//   L1: chunks 0-5 in_hi | 6-11 hprev_hi | 12 ones | 13-15 zeros ;  16-21 in_lo | 22-27 hprev_lo | 28-31 zeros
+//   L0: chunk 0 x_hi | 1-6 hprev_hi | 7 ones | 8-15 zeros        ;  16 x_lo | 17-22 hprev_lo | 23-31 zeros
+template <int LAYER>
+__global__ void __launch_bounds__(kWgThreads, 1)
+lstm_wgrad_x3_kernel(const __half* __restrict__ dg,       // DGX
+                     const __half* __restrict__ act_in,   // L0: XS;  L1: TCLX
+                     const __half* __restrict__ h,        // TCLX (this layer's h: h_{t-1} operand)
+                     const __half* __restrict__ zeros,
+                     float* __restrict__ partial,         // [grid][128][192]
+                     int T, int ntiles) {
+    constexpr int kInC = LAYER == 0 ? 1 : 6;              // hi chunks of the input
+    constexpr int kOnesChunk = kInC + 6;
+    constexpr uint32_t kIdescW = make_idesc(64, kFmtVal, kFmtVal, true, true);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TxWgSmem& S = *reinterpret_cast<TxWgSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    {
+        const uint4 ones = make_uint4(kValOnes2 & 0xFFFFu, 0u, 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);   // {1, 0, 0, ...}: one bias row
+        for (int i = tid; i < 2 * 32 * kRows; i += kWgThreads) {
+            const int s = i / (32 * kRows), ch = (i / kRows) % 32, r = i % kRows;
+            reinterpret_cast<uint4*>(S.act[s] + ch * kAChunk)[r] = ch == kOnesChunk ? ones : zero;
+        }
+        if (tid == 0) {
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&S.act_full[s], 1); mbar_init(&S.act_empty[s], 1);
+                mbar_init(&S.dg_full[s], 1); mbar_init(&S.dg_empty[s], 1);
+            }
+            mbar_init(&S.done, 1);
+            fence_mbar_init();
+        }
+        if (warp == 5) tmem_alloc_all(&S.tmem_base);
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncthreads();
+        tc_fence_after();
+    }
+    const uint32_t tmem = __shfl_sync(0xffffffffu, S.tmem_base, 0);
+    const int64_t nitems = (int64_t)T * ntiles;
+    if (warp == 5) {
+        if (lane == 0) {
+            uint32_t k = 0, gk = 0;
+            for (int64_t w = blockIdx.x; w < nitems; w += gridDim.x, ++k) {
+                const int t = (int)(w / ntiles), tile = (int)(w % ntiles);
+                const uint32_t a = k & 1;
+                mbar_wait(&S.act_empty[a], ((k >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&S.act_full[a], (2 * kInC + 12) * kAChunk);
+                const __half* isrc = act_in + (((int64_t)t * ntiles + tile) * (2 * kInC)) * (kAChunk / 2);
+                bulk_load(S.act[a], isrc, kInC * kAChunk, &S.act_full[a]);
+                bulk_load(S.act[a] + 16 * kAChunk, isrc + kInC * (kAChunk / 2), kInC * kAChunk, &S.act_full[a]);
+                const __half* hsrc = t > 0 ? h + tclx_off(t - 1, ntiles, tile, 0, 0) : zeros;
+                bulk_load(S.act[a] + kInC * kAChunk, hsrc, 6 * kAChunk, &S.act_full[a]);
+                bulk_load(S.act[a] + (16 + kInC) * kAChunk, hsrc + 6 * (kAChunk / 2), 6 * kAChunk, &S.act_full[a]);
+                for (int g = 0; g < 3; ++g, ++gk) {
+                    const uint32_t r = gk & 1;
+                    mbar_wait(&S.dg_empty[r], ((gk >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&S.dg_full[r], 16 * kAChunk);
+                    bulk_load(S.dg[r], dg + dgx_off(t, ntiles, tile, 8 * g, 0), 8 * kAChunk, &S.dg_full[r]);
+                    bulk_load(S.dg[r] + 8 * kAChunk, dg + dgx_off(t, ntiles, tile, 24 + 8 * g, 0), 8 * kAChunk, &S.dg_full[r]);
+                }
+            }
+        }
+    } else if (warp == 4) {
+        const bool leader = elect_one();
+        const uint64_t d_act[2] = {umma_desc(smem_u32(S.act[0]), 128, kAChunk), umma_desc(smem_u32(S.act[1]), 128, kAChunk)};
+        const uint64_t d_dg[2] = {umma_desc(smem_u32(S.dg[0]), 128, kAChunk), umma_desc(smem_u32(S.dg[1]), 128, kAChunk)};
+        uint32_t k = 0, gk = 0;
+        for (int64_t w = blockIdx.x; w < nitems; w += gridDim.x, ++k) {
+            const uint32_t a = k & 1;
+            mbar_wait(&S.act_full[a], (k >> 1) & 1);
+            for (int g = 0; g < 3; ++g, ++gk) {
+                const uint32_t r = gk & 1;
+                mbar_wait(&S.dg_full[r], (gk >> 1) & 1);
+                tc_fence_after();
+                const uint32_t td = tmem + 64 * g;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    if (leader) {
+                        const uint64_t ahi = desc_adv(d_act[a], ks * 256), alo = desc_adv(d_act[a], 16 * kAChunk + ks * 256);
+                        const uint64_t bhi = desc_adv(d_dg[r], ks * 256), blo = desc_adv(d_dg[r], 8 * kAChunk + ks * 256);
+                        umma_bf16_i(td, ahi, bhi, kIdescW, (k == 0 && ks == 0) ? 0u : 1u);
+                        umma_bf16_i(td, ahi, blo, kIdescW, 1u);
+                        umma_bf16_i(td, alo, bhi, kIdescW, 1u);
+                    }
+                if (leader) umma_commit(&S.dg_empty[r]);
+            }
+            if (leader) umma_commit(&S.act_empty[a]);
+        }
+        if (leader) umma_commit(&S.done);
+    } else {
+        // ================= readout of this CTA's partial: lane = feature row, 192 gate columns =========================
+        mbar_wait(&S.done, 0);
+        tc_fence_after();
+        const int row = warp * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        float* out = partial + ((size_t)blockIdx.x * kRows + row) * kN;
+        const bool any = (int64_t)blockIdx.x < nitems;          // a CTA without work items never wrote its accumulator
+#pragma unroll 1
+        for (int cc = 0; cc < kN; cc += 8) {
+            uint32_t r[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (any) tmem_ld8(tmem + lane_base + cc, r);
+            *reinterpret_cast<float4*>(out + cc) = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+            *reinterpret_cast<float4*>(out + cc + 4) = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) { tc_fence_after(); tmem_free_all(tmem); }
+}
+
+// Sum the per-CTA partials [nparts][128 feature rows][192 permuted gate columns] in a fixed order, scatter to torch layouts.
+__global__ void reduce_dw_x3_kernel(const float* __restrict__ partial, int nparts, int layer, float* __restrict__ dw_ih,
+                                    float* __restrict__ dw_hh, float* __restrict__ db) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kRows * kN) return;
+    const int f = idx / kN, n = idx % kN;
+    const int kin = layer == 0 ? 8 : kH;
+    if (f > kin + kH) return;                                 // rows: [in (kin) | h_{t-1} (48) | bias | unused]
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * kRows * kN + idx];
+    const int j = (n / 16) * 4 + (n % 4), gate = (n % 16) / 4, col = gate * kH + j;      // torch row of the weight tensors
+    if (f < kin) dw_ih[col * kin + f] = layer == 0 ? s * kX3XScaleInv : s;             // layer 0: the stored input is x / 16
+    else if (f < kin + kH) dw_hh[col * kH + (f - kin)] = s;
+    else db[col] = s;
+}
+
+static_assert(sizeof(TxFwdSmem<0>) <= 232448 && sizeof(TxFwdSmem<1>) <= 232448, "forward: shared memory budget (227 KB)");
+static_assert(sizeof(TxBwdSmem<0>) <= 232448 && sizeof(TxBwdSmem<1>) <= 232448, "backward: shared memory budget (227 KB)");
+static_assert(sizeof(TxWgSmem) <= 232448, "weight gradients: shared memory budget (227 KB)");
+
+static int tx_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+}  // namespace tc
+}  // namespace na
+
+// ---- C ABI ---------------------------------------------------------------------------------------------------
+extern "C" int na_x3_split_input(const float* x, void* xs, int64_t B, int64_t T, int64_t Bp, na_stream_t stream) {
+    using namespace na;
+    NA_REQUIRE(B >= 1 && T >= 1 && T < (1 << 20) && Bp >= B && Bp % tc::kRows == 0, NA_EINVAL,
+               "na_x3_split_input: bad shape B=%lld T=%lld Bp=%lld (Bp must be a multiple of 128)", (long long)B, (long long)T, (long long)Bp);
+    NA_REQUIRE_PTR(x); NA_REQUIRE_PTR(xs);
+    const int64_t n = T * Bp;
+    tc::x3_split_input_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__half*>(xs), B, (int)T, Bp);
+    count_launch();
+    return check_launch("na_x3_split_input");
+}
+
+extern "C" int na_lstm_fwd_train_x3(int64_t layer, const void* in, const void* packed_x3, const float* attn_w, const float* attn_b,
+                                    const unsigned char* mask, uint64_t seed, int64_t thresh16, float drop_scale, void* h, void* hd,
+                                    float* c, float* zpool, float* stats, int64_t B, int64_t T, int64_t Bp, na_stream_t stream) {
+    using namespace na;
+    NA_REQUIRE(layer == 0 || layer == 1, NA_EINVAL, "na_lstm_fwd_train_x3: layer must be 0 or 1");
+    NA_REQUIRE(T >= 1 && T < (1 << 20) && Bp >= tc::kRows && Bp % tc::kRows == 0, NA_EINVAL,
+               "na_lstm_fwd_train_x3: bad shape T=%lld Bp=%lld (Bp must be a multiple of 128)", (long long)T, (long long)Bp);
+    NA_REQUIRE_PTR(in); NA_REQUIRE_PTR(packed_x3); NA_REQUIRE_PTR(h); NA_REQUIRE_PTR(c);
+    NA_OPTIONAL_PTR(mask); NA_OPTIONAL_PTR(hd); NA_OPTIONAL_PTR(zpool);
+    NA_REQUIRE(thresh16 >= 0 && thresh16 <= 65536, NA_EINVAL, "na_lstm_fwd_train_x3: thresh16 outside [0,65536]");
+    NA_REQUIRE(layer == 1 || (mask != nullptr || thresh16 < 65536) == (hd != nullptr), NA_EINVAL,
+               "na_lstm_fwd_train_x3: layer 0 needs hd exactly when dropout is on (mask tensor or thresh16 < 65536)");
+    NA_REQUIRE(layer == 0 || (attn_w && attn_b && zpool && stats && B >= 1 && B <= Bp), NA_EINVAL,
+               "na_lstm_fwd_train_x3: layer 1 needs attn_w, attn_b, zpool, stats and 1 <= B <= Bp");
+    const int ntiles = (int)(Bp / tc::kRows);
+    const int grid = ntiles < tc::tx_sms() ? ntiles : tc::tx_sms();
+    const unsigned char* pk = reinterpret_cast<const unsigned char*>(packed_x3) + (layer == 0 ? 0 : tc::kX3B0Chunks * tc::kBChunk);
+    cudaError_t e;
+    if (layer == 0) {
+        const size_t smem = sizeof(tc::TxFwdSmem<0>);
+        e = cudaFuncSetAttribute(tc::lstm_fwd_x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, "na_lstm_fwd_train_x3: shared memory opt-in failed (%s)", cudaGetErrorString(e));
+        tc::lstm_fwd_x3_kernel<0><<<grid, tc::kTxThreads, smem, as_stream(stream)>>>(
+            reinterpret_cast<const __half*>(in), pk, nullptr, nullptr, mask, seed, (uint32_t)thresh16, drop_scale,
+            reinterpret_cast<__half*>(h), reinterpret_cast<__half*>(hd), c, nullptr, nullptr, B, (int)T, Bp, ntiles);
+    } else {
+        const size_t smem = sizeof(tc::TxFwdSmem<1>);
+        e = cudaFuncSetAttribute(tc::lstm_fwd_x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, "na_lstm_fwd_train_x3: shared memory opt-in failed (%s)", cudaGetErrorString(e));
+        tc::lstm_fwd_x3_kernel<1><<<grid, tc::kTxThreads, smem, as_stream(stream)>>>(
+            reinterpret_cast<const __half*>(in), pk, attn_w, attn_b, nullptr, 0, 65536u, 1.0f,
+            reinterpret_cast<__half*>(h), nullptr, c, zpool, stats, B, (int)T, Bp, ntiles);
+    }
+    count_launch();
+    return check_launch("na_lstm_fwd_train_x3");
+}
+
+extern "C" int64_t na_train_x3_smem_bytes(int64_t which) {     // 0/1: forward L0/L1, 2/3: backward L0/L1, 4: weight gradients
+    switch (which) {
+        case 0: return sizeof(na::tc::TxFwdSmem<0>);
+        case 1: return sizeof(na::tc::TxFwdSmem<1>);
+        case 2: return sizeof(na::tc::TxBwdSmem<0>);
+        case 3: return sizeof(na::tc::TxBwdSmem<1>);
+        default: return sizeof(na::tc::TxWgSmem);
+    }
+}
+
+extern "C" int64_t na_train_x3_scratch_floats(void) {
+    const int64_t sms = na::tc::tx_sms();
+    return sms * 52 + sms * na::tc::kRows * na::tc::kN;      // attention partials, then weight-gradient partials
+}
+
+extern "C" int na_lstm_bwd_x3(int64_t layer, const void* act_in, const void* h, const float* cstate, const float* dh_in,
+                              const void* packed_x3, const void* zeros, const unsigned char* in_mask, uint64_t seed, int64_t thresh16,
+                              float drop_scale, float* din, void* dg, const float* dz, const float* stats, const float* zpool,
+                              const float* attn_w, const float* attn_b, int64_t B, float* d_attn, float* scratch,
+                              int64_t T, int64_t Bp, na_stream_t stream) {
+    using namespace na;
+    NA_REQUIRE(layer == 0 || layer == 1, NA_EINVAL, "na_lstm_bwd_x3: layer must be 0 or 1");
+    NA_REQUIRE(T >= 1 && T < (1 << 20) && Bp >= tc::kRows && Bp % tc::kRows == 0, NA_EINVAL,
+               "na_lstm_bwd_x3: bad shape T=%lld Bp=%lld", (long long)T, (long long)Bp);
+    NA_REQUIRE_PTR(act_in); NA_REQUIRE_PTR(h); NA_REQUIRE_PTR(cstate); NA_REQUIRE_PTR(packed_x3); NA_REQUIRE_PTR(zeros);
+    NA_REQUIRE_PTR(dg); NA_REQUIRE_PTR(scratch);
+    NA_OPTIONAL_PTR(dh_in); NA_OPTIONAL_PTR(dz); NA_OPTIONAL_PTR(in_mask); NA_OPTIONAL_PTR(din);
+    NA_REQUIRE((dz != nullptr) != (dh_in != nullptr), NA_EINVAL, "na_lstm_bwd_x3: give exactly one of dh_in and dz");
+    NA_REQUIRE(dz == nullptr || (layer == 1 && stats && zpool && attn_w && attn_b && d_attn && B >= 1 && B <= Bp), NA_EINVAL,
+               "na_lstm_bwd_x3: the fused head backward is for layer 1 and needs stats, zpool, attn_w, attn_b, d_attn, B");
+    NA_REQUIRE(layer == 0 || din != nullptr, NA_EINVAL, "na_lstm_bwd_x3: layer 1 needs din");
+    NA_REQUIRE(thresh16 >= 0 && thresh16 <= 65536, NA_EINVAL, "na_lstm_bwd_x3: thresh16 outside [0,65536]");
+    cudaStream_t st = as_stream(stream);
+    const int ntiles = (int)(Bp / tc::kRows);
+    const int grid = ntiles < tc::tx_sms() ? ntiles : tc::tx_sms();
+    const unsigned char* pk = reinterpret_cast<const unsigned char*>(packed_x3) + (layer == 0 ? 0 : tc::kX3B0Chunks * tc::kBChunk);
+    float* attn_partial = scratch;
+    cudaError_t e;
+    if (layer == 0) {
+        const size_t smem = sizeof(tc::TxBwdSmem<0>);
+        e = cudaFuncSetAttribute(tc::lstm_bwd_x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, "na_lstm_bwd_x3: shared memory opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e));
+        tc::lstm_bwd_x3_kernel<0><<<grid, tc::kTxThreads, smem, st>>>(
+            reinterpret_cast<const __half*>(act_in), reinterpret_cast<const __half*>(h), cstate, dh_in, pk,
+            reinterpret_cast<const __half*>(zeros), nullptr, 0, 65536u, 1.0f, nullptr, reinterpret_cast<__half*>(dg),
+            nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, (int)T, Bp, ntiles);
+    } else {
+        const size_t smem = sizeof(tc::TxBwdSmem<1>);
+        e = cudaFuncSetAttribute(tc::lstm_bwd_x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, "na_lstm_bwd_x3: shared memory opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e));
+        tc::lstm_bwd_x3_kernel<1><<<grid, tc::kTxThreads, smem, st>>>(
+            reinterpret_cast<const __half*>(act_in), reinterpret_cast<const __half*>(h), cstate, dh_in, pk,
+            reinterpret_cast<const __half*>(zeros), in_mask, seed, (uint32_t)thresh16, drop_scale, din, reinterpret_cast<__half*>(dg),
+            dz, stats, zpool, attn_w, attn_b, B, attn_partial, (int)T, Bp, ntiles);
+    }
+    count_launch();
+    int rc = check_launch("na_lstm_bwd_x3");
+    if (rc) return rc;
+    if (dz != nullptr) return reduce_partials(attn_partial, d_attn, grid, 52, st);
+    return NA_OK;
+}
+
+extern "C" int na_lstm_wgrad_x3(int64_t layer, const void* dg, const void* act_in, const void* h, const void* zeros,
+                                float* dw_ih, float* dw_hh, float* db, float* scratch, int64_t T, int64_t Bp, na_stream_t stream) {
+    using namespace na;
+    NA_REQUIRE(layer == 0 || layer == 1, NA_EINVAL, "na_lstm_wgrad_x3: layer must be 0 or 1");
+    NA_REQUIRE(T >= 1 && T < (1 << 20) && Bp >= tc::kRows && Bp % tc::kRows == 0, NA_EINVAL,
+               "na_lstm_wgrad_x3: bad shape T=%lld Bp=%lld", (long long)T, (long long)Bp);
+    NA_REQUIRE_PTR(dg); NA_REQUIRE_PTR(act_in); NA_REQUIRE_PTR(h); NA_REQUIRE_PTR(zeros);
+    NA_REQUIRE_PTR(dw_ih); NA_REQUIRE_PTR(dw_hh); NA_REQUIRE_PTR(db); NA_REQUIRE_PTR(scratch);
+    cudaStream_t st = as_stream(stream);
+    const int ntiles = (int)(Bp / tc::kRows);
+    const int64_t nitems = T * ntiles;
+    const int grid = (int)(nitems < tc::tx_sms() ? nitems : tc::tx_sms());
+    float* partial = scratch + (size_t)tc::tx_sms() * 52;
+    const size_t smem = sizeof(tc::TxWgSmem);
+    cudaError_t e;
+    if (layer == 0) {
+        e = cudaFuncSetAttribute(tc::lstm_wgrad_x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, "na_lstm_wgrad_x3: shared memory opt-in failed (%s)", cudaGetErrorString(e));
+        tc::lstm_wgrad_x3_kernel<0><<<grid, tc::kWgThreads, smem, st>>>(reinterpret_cast<const __half*>(dg), reinterpret_cast<const __half*>(act_in),
+                                                                       reinterpret_cast<const __half*>(h), reinterpret_cast<const __half*>(zeros),
+                                                                       partial, (int)T, ntiles);
+    } else {
+        e = cudaFuncSetAttribute(tc::lstm_wgrad_x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, "na_lstm_wgrad_x3: shared memory opt-in failed (%s)", cudaGetErrorString(e));
+        tc::lstm_wgrad_x3_kernel<1><<<grid, tc::kWgThreads, smem, st>>>(reinterpret_cast<const __half*>(dg), reinterpret_cast<const __half*>(act_in),
+                                                                       reinterpret_cast<const __half*>(h), reinterpret_cast<const __half*>(zeros),
+                                                                       partial, (int)T, ntiles);
+    }
+    count_launch();
+    int rc = check_launch("na_lstm_wgrad_x3");
+    if (rc) return rc;
+    tc::reduce_dw_x3_kernel<<<(tc::kRows * tc::kN + 255) / 256, 256, 0, st>>>(partial, grid, (int)layer, dw_ih, dw_hh, db);
+    count_launch();
+    return check_launch("na_lstm_wgrad_x3(reduce)");
+}

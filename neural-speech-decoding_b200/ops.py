@@ -92,7 +92,7 @@ def all_custom_ops():
     return [window_zscore, pack_lstm_layer, lstm_layer_fwd, lstm_layer_bwd, lstm_layer_wgrad, head_fwd,
             head_bwd, trial_mean, decoder_pack_bf16, decoder_infer_bf16, lstm2_fwd_train_bf16, lstm_bwd_bf16,
             dropout_mask_u8, head_tail_fwd, head_tail_bwd, decoder_infer_bf16_x32, decoder_pack_x3, decoder_infer_x3,
-            decoder_pack_wide_bf16, decoder_infer_wide_bf16]
+            decoder_pack_wide_bf16, decoder_infer_wide_bf16, x3_split_input, lstm_fwd_train_x3, lstm_bwd_x3, lstm_wgrad_x3]
 
 
 def launch_count() -> int:
@@ -832,3 +832,197 @@ def decoder_train_forward_tc(x: Tensor, lstm_params, head_params, p: float, zsco
                              drop1=None, rrelu_slope=None, drop2_mask=None) -> Tensor:
     flat = [t for layer in lstm_params for t in layer]
     return DecoderFunctionTC.apply(x, p, zscore, drop1, rrelu_slope, drop2_mask, *flat, *head_params)
+
+
+# ------------------------------------------------------------------------------------------
+# exact tier (fp32 contract), training on the tensor cores (csrc/na_train_x3.cu)
+# ------------------------------------------------------------------------------------------
+EXACT_TC_TRAIN = True        # flagship shape, no d/dx wanted: operand-split tcgen05 kernels (False: FFMA / generic kernels; A/B)
+
+
+def _tclx(T: int, Bp: int, dev) -> Tensor:
+    return torch.empty((T, Bp // TC_TILE, 12, TC_TILE, 8), dtype=torch.float16, device=dev)
+
+
+def _tcl32(T: int, Bp: int, dev) -> Tensor:
+    return torch.empty((T, Bp // TC_TILE, 12, TC_TILE, 4), dtype=torch.float32, device=dev)
+
+
+@torch.library.custom_op("neuroalpha::x3_split_input", mutates_args=(), device_types="cuda")
+@_device_guard
+def x3_split_input(x: Tensor, Bp: int) -> Tensor:
+    """fp32 windows [B,T,8] -> XS fp16 [T, Bp/128, 2, 128, 8]: x / 16 split into hi and lo halves (padding rows zero)."""
+    _require_cuda(x)
+    B, T, C = x.shape
+    if x.dtype != torch.float32 or C != 8 or not x.is_contiguous() or Bp % TC_TILE or Bp < B:
+        raise RuntimeError("x3_split_input: x must be contiguous fp32 [B, T, 8] and Bp a multiple of 128 >= B")
+    xs = torch.empty((T, Bp // TC_TILE, 2, TC_TILE, 8), dtype=torch.float16, device=x.device)
+    _lib.call("na_x3_split_input", x.data_ptr(), xs.data_ptr(), B, T, Bp, _stream())
+    return xs
+
+
+@x3_split_input.register_fake
+def _(x, Bp):
+    return x.new_empty((x.shape[1], Bp // TC_TILE, 2, TC_TILE, 8), dtype=torch.float16)
+
+
+@torch.library.custom_op("neuroalpha::lstm_fwd_train_x3", mutates_args=(), device_types="cuda")
+@_device_guard
+def lstm_fwd_train_x3(layer: int, inp: Tensor, packed: Tensor, attn_w: Tensor, attn_b: Tensor, mask: Optional[Tensor], seed: int,
+                      thresh16: int, drop_scale: float, B: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Training forward of one layer at fp32 accuracy -> (h TCLX, hd TCLX or empty, c TCL32, zpool [B,48] or empty,
+    stats [B,2] or empty).  Layer 0: ``inp`` = XS, ``hd`` = h after inter-layer dropout (when on); layer 1: ``inp`` = TCLX."""
+    _require_cuda(inp, packed, attn_w, attn_b, mask)
+    T, NT = inp.shape[0], inp.shape[1]
+    Bp, dev = NT * TC_TILE, inp.device
+    has_drop = layer == 0 and (mask is not None or thresh16 < 65536)
+    h, c = _tclx(T, Bp, dev), _tcl32(T, Bp, dev)
+    hd = _tclx(T, Bp, dev) if has_drop else torch.empty((0,), dtype=torch.float16, device=dev)
+    zpool = torch.empty((B, 48) if layer == 1 else (0,), dtype=torch.float32, device=dev)
+    stats = torch.empty((B, 2) if layer == 1 else (0,), dtype=torch.float32, device=dev)
+    aw, ab = _f32c(attn_w), _f32c(attn_b)
+    _lib.call("na_lstm_fwd_train_x3", int(layer), inp.data_ptr(), packed.data_ptr(), aw.data_ptr(), ab.data_ptr(),
+              _ptr(mask) if layer == 0 else None, int(seed), int(thresh16) if layer == 0 else 65536, float(drop_scale),
+              h.data_ptr(), _ptr(hd) if has_drop else None, c.data_ptr(), _ptr(zpool) if layer == 1 else None,
+              _ptr(stats) if layer == 1 else None, int(B), T, Bp, _stream())
+    return h, hd, c, zpool, stats
+
+
+@lstm_fwd_train_x3.register_fake
+def _(layer, inp, packed, attn_w, attn_b, mask, seed, thresh16, drop_scale, B):
+    T, NT = inp.shape[0], inp.shape[1]
+    has_drop = layer == 0 and (mask is not None or thresh16 < 65536)
+    f32 = lambda *s: inp.new_empty(s, dtype=torch.float32)
+    return (inp.new_empty((T, NT, 12, TC_TILE, 8)), inp.new_empty((T, NT, 12, TC_TILE, 8) if has_drop else (0,)),
+            f32(T, NT, 12, TC_TILE, 4), f32(B, 48) if layer == 1 else f32(0), f32(B, 2) if layer == 1 else f32(0))
+
+
+@torch.library.custom_op("neuroalpha::lstm_bwd_x3", mutates_args=(), device_types="cuda")
+@_device_guard
+def lstm_bwd_x3(layer: int, act_in: Tensor, h: Tensor, c: Tensor, dh_in: Optional[Tensor], packed: Tensor,
+                in_mask: Optional[Tensor], seed: int, thresh16: int, drop_scale: float, head: Sequence[Tensor],
+                B: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """BPTT of one layer at fp32 accuracy -> (din TCL32 (layer 1) or empty, dg DGX, d_attn [49] or empty).
+    ``head`` = [] (dh_in given) or [dz, stats, zpool, attn_w, attn_b]: layer 1 with the head backward's time loop fused."""
+    _require_cuda(act_in, h, c, dh_in, packed, in_mask, *head)
+    T, NT = c.shape[0], c.shape[1]
+    Bp, dev = NT * TC_TILE, c.device
+    din = _tcl32(T, Bp, dev) if layer == 1 else torch.empty((0,), dtype=torch.float32, device=dev)
+    dg = torch.empty((T, NT, 48, TC_TILE, 8), dtype=torch.float16, device=dev)
+    fused = len(head) > 0
+    d_attn = torch.empty((52,) if fused else (0,), dtype=torch.float32, device=dev)
+    hp = [_f32c(t) for t in head]
+    zeros = torch.zeros((24576,), dtype=torch.uint8, device=dev)
+    scratch = torch.empty((_lib.query("na_train_x3_scratch_floats"),), dtype=torch.float32, device=dev)
+    _lib.call("na_lstm_bwd_x3", int(layer), act_in.data_ptr(), h.data_ptr(), c.data_ptr(), None if fused else dh_in.data_ptr(),
+              packed.data_ptr(), zeros.data_ptr(), _ptr(in_mask), int(seed), int(thresh16), float(drop_scale),
+              _ptr(din) if layer == 1 else None, dg.data_ptr(), *([t.data_ptr() for t in hp] if fused else [None] * 5), int(B),
+              _ptr(d_attn) if fused else None, scratch.data_ptr(), T, Bp, _stream())
+    return din, dg, d_attn[:49] if fused else d_attn
+
+
+@lstm_bwd_x3.register_fake
+def _(layer, act_in, h, c, dh_in, packed, in_mask, seed, thresh16, drop_scale, head, B):
+    T, NT = c.shape[0], c.shape[1]
+    return (c.new_empty(c.shape if layer == 1 else (0,)), h.new_empty((T, NT, 48, TC_TILE, 8)),
+            c.new_empty((49,) if len(head) else (0,)))
+
+
+@torch.library.custom_op("neuroalpha::lstm_wgrad_x3", mutates_args=(), device_types="cuda")
+@_device_guard
+def lstm_wgrad_x3(layer: int, dg: Tensor, act_in: Tensor, h: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """Time-parallel weight gradients of one layer from d(gates) (DGX) and the saved activations:
+    (dW_ih [192, 8 | 48], dW_hh [192, 48], db [192])."""
+    _require_cuda(dg, act_in, h)
+    T, NT = dg.shape[0], dg.shape[1]
+    dev = dg.device
+    dw_ih = torch.empty((192, 8 if layer == 0 else 48), dtype=torch.float32, device=dev)
+    dw_hh = torch.empty((192, 48), dtype=torch.float32, device=dev)
+    db = torch.empty((192,), dtype=torch.float32, device=dev)
+    zeros = torch.zeros((24576,), dtype=torch.uint8, device=dev)
+    scratch = torch.empty((_lib.query("na_train_x3_scratch_floats"),), dtype=torch.float32, device=dev)
+    _lib.call("na_lstm_wgrad_x3", int(layer), dg.data_ptr(), act_in.data_ptr(), h.data_ptr(), zeros.data_ptr(), dw_ih.data_ptr(),
+              dw_hh.data_ptr(), db.data_ptr(), scratch.data_ptr(), T, NT * TC_TILE, _stream())
+    return dw_ih, dw_hh, db
+
+
+@lstm_wgrad_x3.register_fake
+def _(layer, dg, act_in, h):
+    f32 = lambda *s: dg.new_empty(s, dtype=torch.float32)
+    return f32(192, 8 if layer == 0 else 48), f32(192, 48), f32(192)
+
+
+class DecoderFunctionX3(torch.autograd.Function):
+    """Training step of the flagship decoder at fp32 accuracy on the tensor cores (1e-5 contract on logits and
+    gradients): operand-split tcgen05 forward with saves, fp32 head kernels, operand-split BPTT, time-parallel
+    weight-gradient GEMMs.  No d/dx (the FFMA tier provides it)."""
+
+    @staticmethod
+    def forward(ctx, x, p, zscore, drop1, rrelu_slope, drop2_mask, *params):
+        _require_cuda(x, *params)
+        ctx.param_dtypes = [t.dtype for t in params]
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("the tensor-core exact training tier does not produce d/dx")
+        B, T, C = x.shape
+        lstm_flat, head = [t.detach() for t in params[:8]], [_f32c(t.detach()) for t in params[8:]]
+        scale = 1.0 / (1.0 - p) if p < 1.0 else 0.0          # head dropout (and mask-tensor mode)
+        mask, seed, thresh16, scale1 = None, 0, 65536, 1.0
+        if isinstance(drop1, tuple):
+            seed, thresh16 = int(drop1[0]), int(drop1[1])
+            scale1 = 65536.0 / thresh16 if thresh16 > 0 else 0.0
+        elif drop1 is not None:
+            mask, scale1 = drop1, scale
+        xin = x.detach()
+        if xin.dtype != torch.float32:
+            xin = xin.float()
+        if zscore:
+            xin = window_zscore(xin, T, T, True, False, NA_F32)
+        Bp = padded_batch(B, TC_TILE)
+        xs = x3_split_input(xin.contiguous(), Bp)
+        packed = decoder_pack_x3(lstm_flat)
+        h0, h0d, c0, _, _ = lstm_fwd_train_x3(0, xs, packed, head[0], head[1], mask, seed, thresh16, scale1, B)
+        has_drop = mask is not None or thresh16 < 65536
+        h1, _, c1, zpool, stats = lstm_fwd_train_x3(1, h0d if has_drop else h0, packed, head[0], head[1], None, 0, 65536, 1.0, B)
+        logits, _ = head_tail_fwd(zpool, head, rrelu_slope, drop2_mask, scale, False)
+        opt = [t for t in (mask, rrelu_slope, drop2_mask) if t is not None]
+        ctx.save_for_backward(xs, h0, h0d, c0, h1, c1, packed, stats, zpool, *head, *opt)
+        ctx.meta = (scale, B, mask is not None, rrelu_slope is not None, drop2_mask is not None, seed, thresh16, scale1)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        scale, B, has_d1, has_rr, has_d2, seed, thresh16, scale1 = ctx.meta
+        has_drop = has_d1 or thresh16 < 65536
+        sv = list(ctx.saved_tensors)
+        xs, h0, h0d, c0, h1, c1, packed, stats, zpool = sv[:9]
+        head = sv[9:17]
+        rest = sv[17:]
+        d1 = rest.pop(0) if has_d1 else None
+        rr = rest.pop(0) if has_rr else None
+        d2 = rest.pop(0) if has_d2 else None
+        H, NC = 48, dlogits.shape[1]
+        # d(gates) cross the tensor pipe as fp16 hi + lo pairs: the incoming gradient is scaled by an exact power of two
+        # that puts max|dlogits| at 2^11 (fp16's range; the split keeps 22 bits), every gradient is unscaled at the end
+        amax = dlogits.detach().abs().max().clamp_min(1e-30)
+        s = torch.pow(2.0, 11.0 - torch.ceil(torch.log2(amax)))
+        inv_s = 1.0 / s
+        dz, dparams = head_tail_bwd((dlogits * s).contiguous(), zpool, head, rr, d2, scale)
+        in1 = h0d if has_drop else h0
+        din1, dg1, d_attn = lstm_bwd_x3(1, in1, h1, c1, None, packed, d1, seed, thresh16, scale1, [dz, stats, zpool, head[0], head[1]], B)
+        dw_ih1, dw_hh1, db1 = lstm_wgrad_x3(1, dg1, in1, h1)
+        del dg1
+        _, dg0, _ = lstm_bwd_x3(0, xs, h0, c0, din1, packed, None, 0, 65536, 1.0, [], B)
+        dw_ih0, dw_hh0, db0 = lstm_wgrad_x3(0, dg0, xs, h0)
+        del dg0
+        dparams = torch.cat([d_attn, dparams[H + 1:]])
+        head_grads = split_head_grads(dparams * inv_s, H, NC)
+        db0, db1 = db0 * inv_s, db1 * inv_s
+        grads = [dw_ih0 * inv_s, dw_hh0 * inv_s, db0, db0.clone(), dw_ih1 * inv_s, dw_hh1 * inv_s, db1, db1.clone(), *head_grads]
+        grads = [g.to(dt) if g.dtype != dt else g for g, dt in zip(grads, ctx.param_dtypes)]
+        return (None, None, None, None, None, None, *grads)
+
+
+def decoder_train_forward_x3(x: Tensor, lstm_params, head_params, p: float, zscore: bool = False,
+                             drop1=None, rrelu_slope=None, drop2_mask=None) -> Tensor:
+    flat = [t for layer in lstm_params for t in layer]
+    return DecoderFunctionX3.apply(x, p, zscore, drop1, rrelu_slope, drop2_mask, *flat, *head_params)

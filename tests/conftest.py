@@ -59,6 +59,7 @@ def cpu_backend(monkeypatch):
     monkeypatch.setattr(ops, "_stream", lambda: None)
     monkeypatch.setattr(ops, "compute_device", lambda d: torch.device("cpu"))
     monkeypatch.setattr(ops, "EXACT_TC", False)      # the fake implements the granular fp32 entry points (host-logic path)
+    monkeypatch.setattr(ops, "EXACT_TC_TRAIN", False)
     if not _CPU_KERNELS_REGISTERED:
         for op in ops.all_custom_ops():
             op.register_kernel("cpu")(op._init_fn)

@@ -273,6 +273,8 @@ def install():
     ops._require_cuda = lambda *t: None
     ops._stream = lambda: None
     ops.compute_device = lambda d: torch.device("cpu")
+    ops.EXACT_TC = False             # the fake implements the granular fp32 entry points (host-logic path)
+    ops.EXACT_TC_TRAIN = False
     for op in ops.all_custom_ops():
         op.register_kernel("cpu")(op._init_fn)
     return fake
