@@ -690,9 +690,12 @@ def train_leg(args, world, rank, dev):
                "allreduce": "one flat fp32 bucket (127 KB), NCCL" if world > 1 else "none (1 GPU)",
                "parity": "tests/test_gpu_bf16.py: gradients within 2e-2 of the fp64 oracle",
                "frac_of_bf16_sustained_peak": tc["achieved_tflops_per_gpu"] / measured_peaks()["bf16_tflops_sustained"]})
-    fp = run(torch.float32, min(args.train_batch, 8192 * world), 8192, min(steps, 2))
+    fp = run(torch.float32, args.train_batch, args.train_micro, min(steps, 2))      # the same configs[2] step on the fp32-contract tier
     tc["fp32_exact"] = {k: fp[k] for k in ("value", "unit", "ms_per_step", "global_batch", "micro_batch", "achieved_tflops_per_gpu")}
-    tc["fp32_exact"]["parity"] = "tests/test_gpu_parity.py: gradients within 1e-5"
+    tc["fp32_exact"]["parity"] = "tests/test_gpu_parity.py: logits and gradients within 1e-5 of the fp64 truth / the reference's autograd"
+    tc["fp32_exact"]["kernels"] = ("lstm_fwd_x3_kernel<0/1>, lstm_bwd_x3_kernel<1/0>, lstm_wgrad_x3_kernel<1/0> (tcgen05, operands split into "
+                                   "fp16 hi + lo: 3 MMAs per product, fp32 accumulate; ex2 / rcp activations)")
+    tc["fp32_exact"]["frac_of_bf16_sustained_peak_issued_3x"] = 3 * fp["achieved_tflops_per_gpu"] / measured_peaks()["bf16_tflops_sustained"]
     if world > 1:
         e16, e32 = dp_equivalence(torch.bfloat16), dp_equivalence(torch.float32)
         tc["dp_equivalence"] = {"what": f"max|g_DP({world} ranks, NCCL all-reduce) - g_single| / max|g| over the flat gradient bucket, "
