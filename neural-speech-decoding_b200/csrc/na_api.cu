@@ -41,7 +41,7 @@ void set_h48_groups(int ng);
 int mask_scale(const float* h, const float* mask, float scale, float* out, int64_t n, cudaStream_t st);
 
 void set_iir_occ3(int v);
-namespace tc { void set_infer_hs(int hs); void set_infer_rep(int v); void set_wide_cluster(int v); void set_wide_dbg(int v); void set_train_fwd_v2(int v); }
+namespace tc { void set_infer_tanh_fma(int v); void set_x3_rcp_fma(int v); void set_infer_hs(int hs); void set_infer_rep(int v); void set_wide_cluster(int v); void set_wide_dbg(int v); void set_train_fwd_v2(int v); }
 static int g_lstm_tier = 0;   // 0 = auto (specialised when available), 1 = generic only
 
 // K5.  fp32 zeros, += in trial order, one IEEE division: bit-identical to tester.py:54,89,97.
@@ -110,6 +110,8 @@ extern "C" int na_set_tuning(const char* key, int64_t value) {
     if (!strcmp(key, "tc_infer_rep")) { tc::set_infer_rep((int)value); return NA_OK; }
     if (!strcmp(key, "tc_train_fwd_v2")) { tc::set_train_fwd_v2((int)value); return NA_OK; }
     if (!strcmp(key, "tc_wide_dbg")) { tc::set_wide_dbg((int)value); return NA_OK; }
+    if (!strcmp(key, "tc_infer_tanh_fma")) { tc::set_infer_tanh_fma((int)value); return NA_OK; }
+    if (!strcmp(key, "x3_rcp_fma")) { tc::set_x3_rcp_fma((int)value); return NA_OK; }
     if (!strcmp(key, "iir_occ3")) { set_iir_occ3((int)value); return NA_OK; }
     if (!strcmp(key, "tc_wide_cluster")) { tc::set_wide_cluster((int)value); return NA_OK; }
     return fail(NA_EINVAL, "na_set_tuning: unknown key '%s'", key);

@@ -131,8 +131,32 @@ __device__ __forceinline__ void st_shared_v2(void* p, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(smem_u32(p)), "r"(a), "r"(b) : "memory");
 }
 
+// tanh on the FMA pipe.  The MUFU pipe (16 results / clk / SM) bounds this kernel at 5 tanh.approx per cell while the FMA
+// pipe is 15 % busy and two thirds of the issue slots are free (ncu, profiles/r1_tc2_infer_ncu_full.csv), so one of the five
+// is evaluated as the [7/6] Pade approximant of tanh (Lambert's continued fraction)
+//     tanh y ~ y (135135 + 17325 y^2 + 378 y^4 + y^6) / (135135 + 62370 y^2 + 3150 y^4 + 28 y^6),   |y| clamped to 5,
+// absolute error < 1.1e-4 (tanh.approx: 5e-4); the reciprocal is an exponent-trick seed + one cubic + one quadratic
+// Newton step (4e-6).  17 FMA-pipe / ALU instructions for one MUFU result.
+// MEASURED (B200, round 2, scripts/time_offload.py): full round of 18,944 windows 1.575 ms without, 1.612 ms with the
+// offload; short (row-replicated) round 0.701 -> 0.668 ms; 40,960 windows 3.79 -> 3.88 ms.  The xu pipe is 90 % busy but the
+// three epilogue warps of a sub-partition are bound by their own dependent chains, so trading one MUFU for 17 dependent
+// FMA-pipe instructions does not pay on full tiles.  Default: off (knob "tc_infer_tanh_fma").
+__device__ __forceinline__ float tanh_fma(float y) {
+    const float yc = fminf(fmaxf(y, -5.0f), 5.0f);
+    const float y2 = yc * yc;
+    const float num = yc * fmaf(fmaf(y2 + 378.0f, y2, 17325.0f), y2, 135135.0f);
+    const float den = fmaf(fmaf(fmaf(28.0f, y2, 3150.0f), y2, 62370.0f), y2, 135135.0f);
+    float r = __int_as_float(0x7EF311C7 - __float_as_int(den));
+    float e = fmaf(-den, r, 1.0f);
+    r = fmaf(r, fmaf(e, e, e), r);
+    e = fmaf(-den, r, 1.0f);
+    r = fmaf(r, e, r);
+    return num * r;
+}
+
 // One cell update for the 4 units of a granule; v = [i x4 | f x4 | g x4 | o x4] pre-activations (i, f, o already
-// halved by the packed weights).  Returns H = 2h packed as 2 x fp16x2.
+// halved by the packed weights).  Returns H = 2h packed as 2 x fp16x2.  NT = activations per cell on the FMA pipe (0 / 1).
+template <int NT>
 __device__ __forceinline__ void cell_granule(const uint32_t* v, float* c, uint32_t* hp) {
     float h[4];
 #pragma unroll
@@ -140,7 +164,7 @@ __device__ __forceinline__ void cell_granule(const uint32_t* v, float* c, uint32
         const float ti = tanh_apx(__uint_as_float(v[u]));
         const float tf = tanh_apx(__uint_as_float(v[4 + u]));
         const float tg = tanh_apx(__uint_as_float(v[8 + u]));
-        const float to = tanh_apx(__uint_as_float(v[12 + u]));
+        const float to = NT >= 1 ? tanh_fma(__uint_as_float(v[12 + u])) : tanh_apx(__uint_as_float(v[12 + u]));
         const float w = fmaf(tf, c[u], c[u]);
         const float uu = fmaf(ti, tg, tg);
         c[u] = 0.5f * (w + uu);
@@ -154,7 +178,7 @@ __device__ __forceinline__ void cell_granule(const uint32_t* v, float* c, uint32
 // Epilogue of one tile for one warp: both layers of (lane quarter q, unit group g).  R = row replication:
 // the tile holds 128 / R distinct windows; copy rp = q / (4 / R) of source quarter qs = q % (4 / R) takes
 // granules [4 g + rp * (4 / R), + 4 / R) of the 12 four-unit granules.
-template <int R>
+template <int R, int NT>
 __device__ __forceinline__ void epilogue_tile(Smem2& S, const int q, const int g, const int lane, const int nq, const int T,
                                               const int n0, uint32_t& k1, const uint32_t tmem_d0, const uint32_t tmem_d1,
                                               const int64_t b0, const int64_t B, const int NC, float* __restrict__ logits,
@@ -206,7 +230,7 @@ __device__ __forceinline__ void epilogue_tile(Smem2& S, const int q, const int g
         if constexpr (R == 4) {
             uint32_t v[16];
             tmem_ld16(tmem_d + lane_base + gr0 * 16, v);
-            cell_granule(v, c, hb);
+            cell_granule<NT>(v, c, hb);
             unsigned char* dst = buf + (gr0 >> 1) * kAChunk + wrow * 16 + (gr0 & 1) * 8;
 #pragma unroll
             for (int rep = 0; rep < 4; ++rep) st_shared_v2(dst + rep * 32 * 16, hb[0], hb[1]);
@@ -215,8 +239,8 @@ __device__ __forceinline__ void epilogue_tile(Smem2& S, const int q, const int g
             for (int pr = 0; pr < kSlots / 2; ++pr) {       // pairs of granules = one 8-unit K chunk
                 uint32_t v[32];
                 tmem_ld32(tmem_d + lane_base + (gr0 + 2 * pr) * 16, v);
-                cell_granule(v, c + pr * 8, hb + pr * 4);
-                cell_granule(v + 16, c + pr * 8 + 4, hb + pr * 4 + 2);
+                cell_granule<NT>(v, c + pr * 8, hb + pr * 4);
+                cell_granule<NT>(v + 16, c + pr * 8 + 4, hb + pr * 4 + 2);
                 unsigned char* dst = buf + ((gr0 >> 1) + pr) * kAChunk + wrow * 16;
 #pragma unroll
                 for (int rep = 0; rep < R; ++rep)
@@ -309,6 +333,7 @@ __device__ __forceinline__ void epilogue_tile(Smem2& S, const int q, const int g
     }
 }
 
+template <int NT>
 __global__ void __launch_bounds__(kV2Threads, 1)
 decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][Bp][8] fp16 bits
                         const unsigned char* __restrict__ packed,   // v2 section: B0 | B1 (pack_decoder_v2_kernel)
@@ -522,9 +547,9 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
         } else {
             // ================= epilogue: both layers of (quarter q, unit group g) ========================
             const int q = warp & 3, g = warp >> 2;
-            if (R == 1) epilogue_tile<1>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, logits, probs);
-            else if (R == 2) epilogue_tile<2>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, logits, probs);
-            else epilogue_tile<4>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, logits, probs);
+            if (R == 1) epilogue_tile<1, NT>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, logits, probs);
+            else if (R == 2) epilogue_tile<2, NT>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, logits, probs);
+            else epilogue_tile<4, NT>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, logits, probs);
         }
         __syncthreads();       // tile done: every MMA has completed (the epilogue saw the flush d1_full)
         q0 += nq;
@@ -538,6 +563,8 @@ decoder_infer_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][B
     }
 }
 
+int g_infer_tanh_fma = 0;  // na_set_tuning("tc_infer_tanh_fma", 0 / 1): activations per cell on the FMA pipe (A/B timing)
+void set_infer_tanh_fma(int v) { g_infer_tanh_fma = v ? 1 : 0; }
 int g_infer_rep = 1;       // na_set_tuning("tc_infer_rep", 0) disables row replication (A/B timing)
 void set_infer_rep(int v) { g_infer_rep = v ? 1 : 0; }
 
@@ -556,14 +583,15 @@ int launch_infer_v2(const void* x, const unsigned char* packed_v2, const float* 
                     float* logits, float* probs, int T, int64_t B, int64_t Bp, int NC, int sms, cudaStream_t stream,
                     const float* x32) {
     const size_t smem = infer_v2_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(decoder_infer_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = g_infer_tanh_fma ? decoder_infer_v2_kernel<1> : decoder_infer_v2_kernel<0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
     const int nquarters = (int)((B + 31) / 32);            // padding quarters beyond B are never scheduled
     // one CTA per SM; fewer than 4 quarters per CTA run as row-replicated tiles (see epilogue_tile<R>)
     const int grid = nquarters < sms ? nquarters : sms;
-    decoder_infer_v2_kernel<<<grid, kV2Threads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), packed_v2, attn_w, attn_b,
-                                                                ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, T, B, Bp, NC,
-                                                                nquarters, g_infer_rep, x32);
+    kern<<<grid, kV2Threads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), packed_v2, attn_w, attn_b,
+                                             ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, T, B, Bp, NC,
+                                             nquarters, g_infer_rep, x32);
     count_launch();
     return check_launch("na_decoder_infer_bf16 (v2)");
 }

@@ -77,7 +77,7 @@ __global__ void pack_decoder_x3_kernel(const float* __restrict__ w_ih0, const fl
 // Epilogue of one tile for one warp: both layers of (lane quarter q, unit group g).  R = row replication as in
 // decoder_infer_v2_kernel: the tile holds 128 / R distinct windows, copy rp = q / (4 / R) of source quarter qs = q % (4 / R)
 // takes granules [4 g + rp * (4 / R), + 4 / R) of the 12 four-unit granules and stores its h (hi and lo) to every copy.
-template <int R>
+template <int R, int NR>
 __device__ __forceinline__ void x3_epilogue_tile(SmemX3& S, const int q, const int g, const int lane, const int nq, const int T,
                                                  const int n0, uint32_t& k1, const uint32_t tmem_d0, const uint32_t tmem_d1,
                                                  const int64_t b0, const int64_t B, const int NC,
@@ -131,7 +131,7 @@ __device__ __forceinline__ void x3_epilogue_tile(SmemX3& S, const int q, const i
                 : "r"(tmem_d + lane_base + gr0 * 16)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            cell_granule_exact(v, c, hout);
+            cell_granule_exact<NR>(v, c, hout);
             const uint32_t hi0 = pack_val(hout[0], hout[1]), hi1 = pack_val(hout[2], hout[3]);
             const uint32_t lo0 = pack_val(hout[0] - val_lo(hi0), hout[1] - val_hi(hi0));
             const uint32_t lo1 = pack_val(hout[2] - val_lo(hi1), hout[3] - val_hi(hi1));
@@ -146,8 +146,8 @@ __device__ __forceinline__ void x3_epilogue_tile(SmemX3& S, const int q, const i
             for (int pr = 0; pr < kSlots / 2; ++pr) {       // pairs of granules = one 8-unit K chunk
                 uint32_t v[32], hi[4], lo[4];
                 tmem_ld32(tmem_d + lane_base + (gr0 + 2 * pr) * 16, v);
-                cell_granule_exact(v, c + pr * 8, hout + pr * 8);
-                cell_granule_exact(v + 16, c + pr * 8 + 4, hout + pr * 8 + 4);
+                cell_granule_exact<NR>(v, c + pr * 8, hout + pr * 8);
+                cell_granule_exact<NR>(v + 16, c + pr * 8 + 4, hout + pr * 8 + 4);
                 split_pack8(hout + pr * 8, hi, lo);
                 unsigned char* dst = buf + ((gr0 >> 1) + pr) * kAChunk + wrow * 16;
 #pragma unroll
@@ -238,6 +238,7 @@ __device__ __forceinline__ void x3_epilogue_tile(SmemX3& S, const int q, const i
     }
 }
 
+template <int NR>
 __global__ void __launch_bounds__(kX3Threads, 1)
 decoder_infer_x3_kernel(const float* __restrict__ x32,              // [B][T][8] fp32, batch-first
                         const unsigned char* __restrict__ packed,   // pack_decoder_x3_kernel image
@@ -449,9 +450,9 @@ decoder_infer_x3_kernel(const float* __restrict__ x32,              // [B][T][8]
         } else {
             // ================= epilogue: both layers of (quarter q, unit group g) ================================
             const int q = warp & 3, g = warp >> 2;
-            if (R == 1) x3_epilogue_tile<1>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs);
-            else if (R == 2) x3_epilogue_tile<2>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs);
-            else x3_epilogue_tile<4>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs);
+            if (R == 1) x3_epilogue_tile<1, NR>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs);
+            else if (R == 2) x3_epilogue_tile<2, NR>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs);
+            else x3_epilogue_tile<4, NR>(S, q, g, lane, nq, T, n0, k1, tmem_d0, tmem_d1, b0, B, NC, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs);
         }
         __syncthreads();       // tile done: every MMA has completed; the z exchange in h0 has been consumed
         q0 += nq;
@@ -467,6 +468,11 @@ decoder_infer_x3_kernel(const float* __restrict__ x32,              // [B][T][8]
 
 }  // namespace tc
 }  // namespace na
+
+namespace na { namespace tc {
+int g_x3_rcp_fma = kX3DefaultNR;
+void set_x3_rcp_fma(int v) { g_x3_rcp_fma = v; }
+} }
 
 extern "C" int64_t na_decoder_packed_x3_bytes(void) {
     return (int64_t)(na::tc::kX3B0Chunks + na::tc::kX3B1Chunks) * na::tc::kBChunk;
@@ -504,13 +510,23 @@ extern "C" int na_decoder_infer_x3(const float* x, const void* packed, const flo
         if (sms <= 0) sms = 148;
     }
     const size_t smem = sizeof(tc::SmemX3) + 1024;
-    cudaError_t e = cudaFuncSetAttribute(tc::decoder_infer_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_x3: shared memory opt-in failed (%s)", cudaGetErrorString(e));
     const int nquarters = (int)((B + 31) / 32);
     const int grid = nquarters < sms ? nquarters : sms;    // < 4 quarters per CTA run as row-replicated tiles
-    tc::decoder_infer_x3_kernel<<<grid, tc::kX3Threads, smem, as_stream(stream)>>>(
-        x, reinterpret_cast<const unsigned char*>(packed), attn_w, attn_b, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs,
-        (int)T, B, (int)NC, nquarters);
+#define NA_X3_LAUNCH(NRV)                                                                                                            \
+    {                                                                                                                                \
+        cudaError_t e = cudaFuncSetAttribute(tc::decoder_infer_x3_kernel<NRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return fail((int)e, "na_decoder_infer_x3: shared memory opt-in failed (%s)", cudaGetErrorString(e));    \
+        tc::decoder_infer_x3_kernel<NRV><<<grid, tc::kX3Threads, smem, as_stream(stream)>>>(                                         \
+            x, reinterpret_cast<const unsigned char*>(packed), attn_w, attn_b, ln_w, ln_b, fc0_w, fc0_b, fc3_w, fc3_b, logits, probs, \
+            (int)T, B, (int)NC, nquarters);                                                                                          \
+    }
+    switch (tc::g_x3_rcp_fma) {
+        case 0: NA_X3_LAUNCH(0) break;
+        case 2: NA_X3_LAUNCH(2) break;
+        case 3: NA_X3_LAUNCH(3) break;
+        default: NA_X3_LAUNCH(1) break;
+    }
+#undef NA_X3_LAUNCH
     count_launch();
     return check_launch("na_decoder_infer_x3");
 }

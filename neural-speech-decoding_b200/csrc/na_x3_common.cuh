@@ -36,6 +36,27 @@ __device__ __forceinline__ void x3_tmem_ld2(uint32_t taddr, uint32_t (&v)[2]) {
 //     h  = o tanh(c') = (1 - E_c) / [ (1+E_o)(1+E_c) ],  E_c = e^-2c'                              2 ex2 + 1 rcp
 // = 7 MUFU per cell instead of 10 (ex2 + rcp per activation).  Pre-activations are clamped where the functions are
 // already saturated in fp32 (|x| <= 28 for the sigmoids, <= 14 for the tanh arguments) so the products stay below 2^127.
+// The MUFU pipe (16 results / clk / SM) bounds these kernels while the FMA pipe idles, so a reciprocal can be taken off it:
+// rcp_fma = an exponent-trick seed (12 % off) refined by two cubically convergent steps r <- r (1 + e + e^2), e = 1 - d r
+// (0.125^9 = 7e-9, then fp32 rounding: as accurate as rcp.approx) -- 1 integer op + 6 FFMA instead of 1 MUFU.
+// The denominators here are products of (1 + E) terms: positive, normal, <= 2^120; a NaN stays a NaN.
+__device__ __forceinline__ float rcp_fma(float d) {
+    float r = __int_as_float(0x7EF311C7 - __float_as_int(d));
+    float e = fmaf(-d, r, 1.0f);
+    r = fmaf(r, fmaf(e, e, e), r);
+    e = fmaf(-d, r, 1.0f);
+    r = fmaf(r, fmaf(e, e, e), r);
+    return r;
+}
+// NR = how many of the two reciprocals of a cell update run on the FMA pipe: 0 = none (7 MUFU per cell), 1 = the one of h
+// (6 MUFU), 2 = both (5 MUFU), 3 = alternate 1 / 2 over the units (5.5 MUFU).  Runtime knob "x3_rcp_fma" (A/B timing).
+// MEASURED (B200, round 2, scripts/time_offload.py, 18,944 windows = one full round): NR = 0: 2.359 ms, 1: 2.599, 2: 2.664,
+// 3: 2.708 -- the offload LOSES 10-15 %: with 3 epilogue warps per SM sub-partition the step is bound by the dependent chain
+// of each warp (ex2 -> products -> rcp -> ex2 -> rcp), not by MUFU issue, and the 7 serially dependent instructions of the
+// FMA-pipe reciprocal lengthen exactly that chain.  Same accuracy (8.9e-7 vs 9.2e-7 against the FFMA kernels).  Default: off.
+constexpr int kX3DefaultNR = 0;
+
+template <int NR = kX3DefaultNR>
 __device__ __forceinline__ void cell_granule_exact(const uint32_t* v, float* c, float* h) {
     // an activation costs the scale (FMUL), one NaN-propagating min and one ex2: the cap keeps the products below 2^127,
     // the lower side needs none (E -> 0).  cap 40: e^-x <= 2^40 <=> x >= -27.7, where sigmoid is 9e-13 and tanh is -1 to
@@ -54,10 +75,12 @@ __device__ __forceinline__ void cell_granule_exact(const uint32_t* v, float* c, 
         const float dig = (1.0f + ei) * (1.0f + eg);
         const float df = 1.0f + ef;
         const float num = fmaf(c[u], dig, (1.0f - eg) * df);
-        const float cn = num * rcp_approx(df * dig);
+        const bool c_on_fma = NR == 2 || (NR == 3 && (u & 1));
+        const float cn = num * (c_on_fma ? rcp_fma(df * dig) : rcp_approx(df * dig));
         c[u] = cn;
         const float ec = capped_ex2(-2.0f * kL2e * cn);
-        h[u] = (1.0f - ec) * rcp_approx((1.0f + eo) * (1.0f + ec));
+        const float dh = (1.0f + eo) * (1.0f + ec);
+        h[u] = (1.0f - ec) * (NR >= 1 ? rcp_fma(dh) : rcp_approx(dh));
     }
 }
 
