@@ -442,6 +442,18 @@ def run_gpu_arm(args):
     ms_filt = time_steps(lambda: filters.filter_windows(x_flat), 3, 1, 1, dev) / 3
     filt_bytes = n_win * C * T * (4 + 4)            # algorithmic: one fp32 read + one fp32 write per sample
     filt_flops = n_win * C * T * filters.chain_fma_per_sample() * 2
+    # ---- preprocessing front stage (opt-in): the step in front of the decoder on every live window ----
+    from neural_speech_decoding_b200.preprocess_gpu import PhaseCouplingFilterGPU
+    pre = PhaseCouplingFilterGPU(device=dev, accept_noncommercial_terms=True)      # benchmark of the opt-in stage
+    ms_pre = time_steps(lambda: pre.transform_batch(x_flat), 3, 1, 1, dev) / 3
+    pre_cpu = None
+    if rank == 0 and not args.no_cpu:
+        from oracle.phase_filter import phase_coupling_filter
+        wins = host[0, :24].numpy()
+        t0 = time.perf_counter()
+        for wv in wins:
+            phase_coupling_filter(wv)
+        pre_cpu = len(wins) / (time.perf_counter() - t0)
     torch.cuda.empty_cache()
 
     # ---- measured CUDA-core fp32 peak (FFMA probe) -------------------------------------------------
@@ -522,6 +534,15 @@ def run_gpu_arm(args):
                              "algorithmic_bytes": filt_bytes, "fp64_tflops": filt_flops / (ms_filt * 1e-3) / 1e12,
                              "note": "8 B of DRAM traffic per sample (algorithmic); the binding pipe is fp64 FMA, not HBM",
                              "parity": "unpinned (BrainFlow absent): tests/test_filters.py vs the scipy restatement"},
+            "phase_filter": {"kernel": "phase_coupling_filter_kernel (opt-in front stage: radix-5 FFT Hilbert transform, 28 pairwise phase sums, "
+                                       "8x8 fp64 solve, mix; one CTA per window, float64)",
+                             "bound": "hbm", "achieved": n_win * T * C * 8 / (ms_pre * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": n_win * T * C * 8 / (ms_pre * 1e-3) / 1e9 / peaks["hbm_gbs"], "windows_per_s": n_win / (ms_pre * 1e-3),
+                             "ms_per_40960_windows": ms_pre,
+                             "cpu_windows_per_s_per_core": pre_cpu, "cpu_kind": "port (oracle/phase_filter.py, numpy float64, one core)",
+                             "note": "nominally HBM-bound byte work (40 KB per window); actually bound by fp64 arithmetic and shared-memory "
+                                     "latency of the 8 FFTs per window",
+                             "parity": "tests/test_phase_filter.py: the reference's own filtered windows (1e-5) and filtered-path logits"},
             "ffma_kernels": {"kernel": "lstm_fwd_h48_kernel<KIN=48> (layer-1 recurrence, exact fp32 FFMA; other shapes / A-B reference)",
                              "bound": "cuda-core fp32 (FFMA issue)", "achieved": l1_tflops, "peak": ffma_peak,
                              "unit": "TFLOP/s", "frac": l1_tflops / ffma_peak, "peak_source": "na_ffma_probe measured in this run",

@@ -333,6 +333,18 @@ int na_lstm_bwd_x3(int64_t layer, const void* act_in, const void* h, const float
 int na_lstm_wgrad_x3(int64_t layer, const void* dg, const void* act_in, const void* h, const void* zeros,
                      float* dw_ih, float* dw_hh, float* db, float* scratch, int64_t T, int64_t Bp, na_stream_t stream);
 
+/* ---- phase-coupling preprocessing filter, OPT-IN ---------------------------------------------
+ * Replaces, for batches of windows, Utilities/preprocessor.py:21-36 -> MindsAI/mindsai_filter_python/core.py:14-48 (the
+ * step in front of the decoder on every live window): analytic signal per channel (Hilbert transform), pairwise
+ * sum_t sin^2(phase_i - phase_j), diagonal renormalisation (EPS = 1e-12), M = (I + lambd P^T P)^-1, y = M x.
+ * x, y fp32 [B][625][8] (batch-first windows as the reference stores them: samples x channels); arithmetic in float64.
+ * twiddle = exp(-2 pi i k / 625), k = 0..624, as 1250 doubles (re, im); status: one int, set to 1 if a matrix was singular.
+ * The method is third-party (MindsApplied, patent pending; the reference implementation is Polyform-Noncommercial):
+ * written from the published mathematics, never enabled by default (preprocess_gpu.PhaseCouplingFilterGPU).
+ */
+int na_phase_coupling_filter(const float* x, float* y, const double* twiddle, double lambd, int* status,
+                             int64_t B, int64_t T, int64_t C, na_stream_t stream);
+
 /* ---- K5: trial averaging -----------------------------------------------------------------
  * Replaces tester.py:54,89,97 (and :90,98 for the chunk): fp32 zeros, += in trial order
  * r = 0..R-1, then one IEEE division by R.   in [R][N] -> out [N].

@@ -318,8 +318,13 @@ class SimplePredictor:
 
     def predict_batch(self, chunks_BxTxC: np.ndarray, preprocess: bool = True) -> np.ndarray:
         """Batched sibling of ``predict``: [B,T,C] -> probs [B,K] (one H2D, one launch sequence, one D2H)."""
-        x = np.stack([self.pre.transform(c) for c in chunks_BxTxC]) if preprocess else np.asarray(chunks_BxTxC)
-        x_t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.compute_device)
+        if preprocess and hasattr(self.pre, "transform_batch"):
+            # a batched GPU front stage (preprocess_gpu.PhaseCouplingFilterGPU, opt-in): one H2D, filter + decode on the device
+            x_t = torch.from_numpy(np.ascontiguousarray(chunks_BxTxC, dtype=np.float32)).to(self.compute_device)
+            x_t = self.pre.transform_batch(x_t)
+        else:
+            x = np.stack([self.pre.transform(c) for c in chunks_BxTxC]) if preprocess else np.asarray(chunks_BxTxC)
+            x_t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.compute_device)
         with self._no_grad():
             _, probs = self.model.decode(x_t, want_probs=True)
         return probs.cpu().numpy().astype(np.float32)

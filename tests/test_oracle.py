@@ -105,3 +105,13 @@ def test_reference_fp32_autograd_distance_from_fp64_truth(golden_dir):
         worst[k] = float(np.abs(ref[k] - tru[k]).max() / scale)
     assert 5e-6 < worst["attn.weight"] < 2e-5, worst
     assert all(v < 7e-6 for k, v in worst.items() if k != "attn.weight"), worst
+
+
+def test_phase_filter_oracle_matches_reference_outputs(windows, golden_dir):
+    """The restatement of the preprocessing filter (oracle/phase_filter.py) against the reference's own filtered
+    windows (make_golden.py ran the real PreProcessor): this pins the oracle the GPU front stage is checked with."""
+    from oracle.phase_filter import phase_coupling_filter
+    f = np.load(golden_dir / "ref_outputs_3class.npz")
+    for i, want in zip(f["filtered_subset_idx"][:12], f["filtered_subset"][:12]):
+        got = phase_coupling_filter(windows["X"][int(i)])
+        assert np.abs(got - want).max() / np.abs(want).max() < 2e-6, int(i)
