@@ -272,20 +272,25 @@ int na_decoder_infer_wide_bf16(const void* x_bf16_tmp, const void* packed, const
  * thresh16 < 65536, a counter-based in-kernel generator: unit block (t*Bp + b, blk) keeps a unit with
  * probability thresh16/65536 as a pure function of (seed, row, blk) -- the backward regenerates the
  * forward's mask, no mask tensor exists.  thresh16 == 65536 and mask == NULL: no dropout.
- * na_dropout_mask_u8 materialises that mask ([T][Bp][48] u8) for tests. */
+ * na_dropout_mask_u8 materialises that mask ([T][Bp][48] u8) for tests.  * HALF TILES (half_stride > 0; strong scaling at small batches): a tile holds 64 distinct windows, rows 64..127 of the
+ * input (the caller replicates them), of h0 / h0d / h1 (the kernels write both copies) mirror rows 0..63, and the two
+ * copies of a window split its hidden units, so a tile costs about half a step and B windows occupy B / 64 SMs.  Window b
+ * lives in rows (b / 64) * 128 + b % 64 (+ 64); B <= Bp / 2; half_stride = the row stride of the counter-based dropout
+ * generator's key (the full-tile padded batch, so that both layouts draw the same mask).  Pass 0 for full tiles.
+ */
 int na_dropout_mask_u8(uint64_t seed, int64_t thresh16, int64_t T, int64_t Bp, unsigned char* out, na_stream_t stream);
 int64_t na_train_bf16_partial_floats(void);
 int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packed, const unsigned char* mask,
                             uint64_t seed, int64_t thresh16, float drop_scale, void* h0, void* h0d, float* c0, void* h1, float* h1f,
                             float* c1, const float* attn_w, const float* attn_b, float* zpool, float* stats,
-                            int64_t B, int64_t T, int64_t Bp, na_stream_t stream);
+                            int64_t B, int64_t T, int64_t Bp, int64_t half_stride, na_stream_t stream);
 int na_lstm_bwd_bf16(int64_t layer, const void* act_in, const void* h, const float* cstate,
                      const float* dh_out, const void* packed_fwd, const float* w_ih, const float* w_hh,
                      const void* zeros, const unsigned char* in_mask, uint64_t seed, int64_t thresh16,
                      float drop_scale, float* din, float* dw_ih, float* dw_hh, float* db, void* scratch,
                      const float* dz, const float* stats, const float* zpool, const float* attn_w,
                      const float* attn_b, int64_t B, float* d_attn,
-                     int64_t T, int64_t Bp, na_stream_t stream);
+                     int64_t T, int64_t Bp, int64_t half_stride, na_stream_t stream);
 
 /* Tail-only forms of K4 for the fused tier: na_lstm2_fwd_train_bf16 already pooled (zpool, stats), and
  * na_lstm_bwd_bf16(layer 1, dz != NULL) rebuilds dh_t = alpha_t dz + ds_t w_a per step and owns d attn_w /

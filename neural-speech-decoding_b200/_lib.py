@@ -45,9 +45,9 @@ SIGNATURES = {
     "na_decoder_infer_wide_bf16": (c_int, [P] * 11 + [I64, I64, I64, I64, I64, P]),
     "na_train_bf16_partial_floats": (c_int64, []),
     "na_dropout_mask_u8": (c_int, [ctypes.c_uint64, I64, I64, I64, P, P]),
-    "na_lstm2_fwd_train_bf16": (c_int, [P, P, P, ctypes.c_uint64, I64, F32, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, P]),
+    "na_lstm2_fwd_train_bf16": (c_int, [P, P, P, ctypes.c_uint64, I64, F32, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, P]),
     "na_lstm_bwd_bf16": (c_int, [I64, P, P, P, P, P, P, P, P, P, ctypes.c_uint64, I64, F32, P, P, P, P, P,
-                                 P, P, P, P, P, I64, P, I64, I64, P]),
+                                 P, P, P, P, P, I64, P, I64, I64, I64, P]),
     "na_x3_split_input": (c_int, [P, P, I64, I64, I64, P]),
     "na_lstm_fwd_train_x3": (c_int, [I64, P, P, P, P, P, ctypes.c_uint64, I64, F32, P, P, P, P, P, I64, I64, I64, P]),
     "na_train_x3_scratch_floats": (c_int64, []),

@@ -44,6 +44,11 @@ __device__ __forceinline__ uint32_t half2_halve(uint32_t p) {        // exact: f
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// HALF = half tiles (strong scaling at small batches): a tile holds 64 distinct windows and rows 64..127 of every operand
+// mirror rows 0..63 (the host replicates the input rows, this kernel stores h to both copies, in shared memory and in
+// HBM).  The MMAs are unchanged; the two copies split the hidden units -- copy rp = q / 2 takes K chunk 2 g + rp (8 units
+// per thread instead of 16) -- so a tile costs roughly half a step and a batch of B windows occupies B / 64 SMs.
+template <bool HALF>
 __global__ void __launch_bounds__(kV2Threads, 1)
 lstm2_fwd_train_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T][Bp][8] fp16 bits
                           const unsigned char* __restrict__ packed,   // v2 section (pack_decoder_v2_kernel)
@@ -52,7 +57,7 @@ lstm2_fwd_train_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                           __nv_bfloat16* __restrict__ h1_out, float* __restrict__ c1_out,
                           const float* __restrict__ attn_w, const float* __restrict__ attn_b,
                           float* __restrict__ zpool_out, float* __restrict__ stats_out, int64_t B,
-                          int T, int64_t Bp, int ntiles) {
+                          int T, int64_t Bp, int ntiles, int64_t drop_stride) {
     constexpr int kMmaWarp = 12, kTmaWarp = 13;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SmemT2& S = *reinterpret_cast<SmemT2*>(smem_raw);
@@ -185,25 +190,30 @@ lstm2_fwd_train_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
             const int q = warp & 3, g = warp >> 2;
             const int row = q * 32 + lane;
             const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-            float c0[16], c1[16], z[16];
+            constexpr int kNB = HALF ? 1 : 2;              // 8-unit blocks per thread
+            const int rp = HALF ? (q >> 1) : 0;            // row copy of this warp
+            const int crow = HALF ? (row & 63) : row;      // canonical row (first copy)
+            const int blk0 = HALF ? 2 * g + rp : 2 * g;    // first K chunk of this thread
+            const int64_t bwin = HALF ? (int64_t)tile * 64 + crow : b0 + row;       // window index
+            float c0[8 * kNB], c1[8 * kNB], z[8 * kNB];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { c0[j] = 0.f; c1[j] = 0.f; z[j] = 0.f; }
-            uint32_t hprev[8];
+            for (int j = 0; j < 8 * kNB; ++j) { c0[j] = 0.f; c1[j] = 0.f; z[j] = 0.f; }
+            uint32_t hprev[4 * kNB];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) hprev[j] = 0u;
+            for (int j = 0; j < 4 * kNB; ++j) hprev[j] = 0u;
             float mx = -INFINITY, l = 0.f;
             auto pool = [&](float score) {                 // online softmax over time (lstm_eeg_model.py:35-37)
                 if (score > mx) {
                     const float sc = __expf(mx - score);
                     l *= sc;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) z[j] *= sc;
+                    for (int j = 0; j < 8 * kNB; ++j) z[j] *= sc;
                     mx = score;
                 }
                 const float e = __expf(score - mx);
                 l += e;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < 4 * kNB; ++u) {
                     z[2 * u] = fmaf(e, val_lo(hprev[u]), z[2 * u]);
                     z[2 * u + 1] = fmaf(e, val_hi(hprev[u]), z[2 * u + 1]);
                 }
@@ -211,23 +221,26 @@ lstm2_fwd_train_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
             for (int t = 0; t <= T; ++t) {
                 const int n = n0 + t;
                 if (t < T) {                               // ---- layer 0, step t
-                    const int64_t grow = (int64_t)t * Bp + b0 + row;
+                    const int64_t grow = (int64_t)t * Bp + b0 + crow;                      // mask-tensor row
+                    const int64_t gkey = HALF ? (int64_t)t * drop_stride + bwin : grow;   // counter-based generator: layout-independent
                     const int64_t tcl = ((int64_t)t * ntiles + tile) * 6 * (kAChunk / 2) + row * 8;
-                    uint32_t keep[2] = {0xFFu, 0xFFu};
+                    uint32_t keep[kNB];
+#pragma unroll
+                    for (int pr = 0; pr < kNB; ++pr) keep[pr] = 0xFFu;
                     if (drop) {
 #pragma unroll
-                        for (int pr = 0; pr < 2; ++pr) {
-                            const int blk = 2 * g + pr;
+                        for (int pr = 0; pr < kNB; ++pr) {
+                            const int blk = blk0 + pr;
                             keep[pr] = mask ? mask_keep8(*reinterpret_cast<const uint2*>(mask + grow * kH + blk * 8))
-                                            : dropout_keep8(seed, grow, blk, thresh16);
+                                            : dropout_keep8(seed, gkey, blk, thresh16);
                         }
                     }
                     mbar_wait(&S.d0_full, n & 1);
                     if (q == 0 && g == 0 && lane == 0) mbar_arrive(&S.x_empty[n % kV2XStages]);
                     tc_fence_after();
 #pragma unroll
-                    for (int pr = 0; pr < 2; ++pr) {
-                        const int blk = 2 * g + pr;
+                    for (int pr = 0; pr < kNB; ++pr) {
+                        const int blk = blk0 + pr;
                         uint32_t v[32];
                         float H[8];
                         tmem_ld32(tmem_d0 + lane_base + blk * 32, v);
@@ -235,9 +248,13 @@ lstm2_fwd_train_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                         cell_granule_f(v + 16, c0 + pr * 8 + 4, H + 4);
                         const uint32_t p0 = pack_val(H[0], H[1]), p1 = pack_val(H[2], H[3]);
                         const uint32_t p2 = pack_val(H[4], H[5]), p3 = pack_val(H[6], H[7]);
+                        const uint4 hs = make_uint4(half2_halve(p0), half2_halve(p1), half2_halve(p2), half2_halve(p3));
                         st_shared_v4(S.h0[n & 1] + blk * kAChunk + row * 16, p0, p1, p2, p3);
-                        *reinterpret_cast<uint4*>(h0_out + tcl + blk * (kAChunk / 2)) =
-                            make_uint4(half2_halve(p0), half2_halve(p1), half2_halve(p2), half2_halve(p3));
+                        *reinterpret_cast<uint4*>(h0_out + tcl + blk * (kAChunk / 2)) = hs;
+                        if (HALF) {                        // the other row copy
+                            st_shared_v4(S.h0[n & 1] + blk * kAChunk + (row ^ 64) * 16, p0, p1, p2, p3);
+                            *reinterpret_cast<uint4*>(h0_out + tcl + blk * (kAChunk / 2) + ((row ^ 64) - row) * 8) = hs;
+                        }
                         st_global_v4f(c0_out + tcl32_off(t, ntiles, tile, 2 * blk, row), c0[pr * 8], c0[pr * 8 + 1], c0[pr * 8 + 2], c0[pr * 8 + 3]);
                         st_global_v4f(c0_out + tcl32_off(t, ntiles, tile, 2 * blk + 1, row), c0[pr * 8 + 4], c0[pr * 8 + 5], c0[pr * 8 + 6], c0[pr * 8 + 7]);
                         if (drop) {
@@ -246,9 +263,13 @@ lstm2_fwd_train_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                             for (int u = 0; u < 8; ++u) Hd[u] = ((keep[pr] >> u) & 1u) ? H[u] * drop_scale : 0.f;
                             const uint32_t q0 = pack_val(Hd[0], Hd[1]), q1 = pack_val(Hd[2], Hd[3]);
                             const uint32_t q2 = pack_val(Hd[4], Hd[5]), q3 = pack_val(Hd[6], Hd[7]);
+                            const uint4 ds = make_uint4(half2_halve(q0), half2_halve(q1), half2_halve(q2), half2_halve(q3));
                             st_shared_v4(S.h0d[n & 1] + blk * kAChunk + row * 16, q0, q1, q2, q3);
-                            *reinterpret_cast<uint4*>(h0d_out + tcl + blk * (kAChunk / 2)) =
-                                make_uint4(half2_halve(q0), half2_halve(q1), half2_halve(q2), half2_halve(q3));
+                            *reinterpret_cast<uint4*>(h0d_out + tcl + blk * (kAChunk / 2)) = ds;
+                            if (HALF) {
+                                st_shared_v4(S.h0d[n & 1] + blk * kAChunk + (row ^ 64) * 16, q0, q1, q2, q3);
+                                *reinterpret_cast<uint4*>(h0d_out + tcl + blk * (kAChunk / 2) + ((row ^ 64) - row) * 8) = ds;
+                            }
                         }
                     }
                     tc_fence_before();
@@ -262,10 +283,10 @@ lstm2_fwd_train_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                     tc_fence_after();
                     uint32_t sc2[2];
                     tmem_ld2(tmem_d1 + lane_base + kN, sc2);
-                    uint32_t hb[8];
+                    uint32_t hb[4 * kNB];
 #pragma unroll
-                    for (int pr = 0; pr < 2; ++pr) {
-                        const int blk = 2 * g + pr;
+                    for (int pr = 0; pr < kNB; ++pr) {
+                        const int blk = blk0 + pr;
                         uint32_t v[32];
                         float H[8];
                         tmem_ld32(tmem_d1 + lane_base + blk * 32, v);
@@ -273,9 +294,13 @@ lstm2_fwd_train_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                         cell_granule_f(v + 16, c1 + pr * 8 + 4, H + 4);
                         hb[pr * 4] = pack_val(H[0], H[1]); hb[pr * 4 + 1] = pack_val(H[2], H[3]);
                         hb[pr * 4 + 2] = pack_val(H[4], H[5]); hb[pr * 4 + 3] = pack_val(H[6], H[7]);
+                        const uint4 hs = make_uint4(half2_halve(hb[pr * 4]), half2_halve(hb[pr * 4 + 1]), half2_halve(hb[pr * 4 + 2]), half2_halve(hb[pr * 4 + 3]));
                         st_shared_v4(S.h1 + blk * kAChunk + row * 16, hb[pr * 4], hb[pr * 4 + 1], hb[pr * 4 + 2], hb[pr * 4 + 3]);
-                        *reinterpret_cast<uint4*>(h1_out + tcl + blk * (kAChunk / 2)) =
-                            make_uint4(half2_halve(hb[pr * 4]), half2_halve(hb[pr * 4 + 1]), half2_halve(hb[pr * 4 + 2]), half2_halve(hb[pr * 4 + 3]));
+                        *reinterpret_cast<uint4*>(h1_out + tcl + blk * (kAChunk / 2)) = hs;
+                        if (HALF) {
+                            st_shared_v4(S.h1 + blk * kAChunk + (row ^ 64) * 16, hb[pr * 4], hb[pr * 4 + 1], hb[pr * 4 + 2], hb[pr * 4 + 3]);
+                            *reinterpret_cast<uint4*>(h1_out + tcl + blk * (kAChunk / 2) + ((row ^ 64) - row) * 8) = hs;
+                        }
                         st_global_v4f(c1_out + tcl32_off(tt, ntiles, tile, 2 * blk, row), c1[pr * 8], c1[pr * 8 + 1], c1[pr * 8 + 2], c1[pr * 8 + 3]);
                         st_global_v4f(c1_out + tcl32_off(tt, ntiles, tile, 2 * blk + 1, row), c1[pr * 8 + 4], c1[pr * 8 + 5], c1[pr * 8 + 6], c1[pr * 8 + 7]);
                     }
@@ -284,7 +309,7 @@ lstm2_fwd_train_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                     mbar_arrive(&S.h1_ready);
                     if (t >= 2) pool(__uint_as_float(sc2[0]) + __uint_as_float(sc2[1]));
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) hprev[u] = hb[u];
+                    for (int u = 0; u < 4 * kNB; ++u) hprev[u] = hb[u];
                 }
             }
             {                                              // flush: score of the last step
@@ -295,12 +320,12 @@ lstm2_fwd_train_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                 tc_fence_before();
                 pool(__uint_as_float(sc2[0]) + __uint_as_float(sc2[1]));
             }
-            if (b0 + row < B) {                            // pooled vector (H = 2h accumulated) and the softmax stats
+            if (bwin < B) {                                // pooled vector (H = 2h accumulated) and the softmax stats
                 const float inv_l = 0.5f / l;
-                float* zo = zpool_out + (b0 + row) * kH + g * 16;
+                float* zo = zpool_out + bwin * kH + blk0 * 8;
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) st_global_v4f(zo + j, z[j] * inv_l, z[j + 1] * inv_l, z[j + 2] * inv_l, z[j + 3] * inv_l);
-                if (g == 0) { stats_out[2 * (b0 + row)] = mx; stats_out[2 * (b0 + row) + 1] = l; }
+                for (int j = 0; j < 8 * kNB; j += 4) st_global_v4f(zo + j, z[j] * inv_l, z[j + 1] * inv_l, z[j + 2] * inv_l, z[j + 3] * inv_l);
+                if (g == 0 && rp == 0) { stats_out[2 * bwin] = mx; stats_out[2 * bwin + 1] = l; }
             }
         }
         __syncthreads();
@@ -316,15 +341,17 @@ bool train_fwd_v2_enabled() { return g_train_fwd_v2 != 0; }
 
 int launch_train_fwd_v2(const void* x, const unsigned char* packed_v2, const unsigned char* mask, uint64_t seed, uint32_t thresh16,
                         float drop_scale, void* h0, void* h0d, float* c0, void* h1, float* c1, const float* attn_w, const float* attn_b,
-                        float* zpool, float* stats, int64_t B, int T, int64_t Bp, int sms, cudaStream_t stream) {
+                        float* zpool, float* stats, int64_t B, int T, int64_t Bp, int sms, cudaStream_t stream, int64_t half_stride) {
     const size_t smem = sizeof(SmemT2) + 1024;
-    cudaError_t e = cudaFuncSetAttribute(lstm2_fwd_train_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = half_stride > 0 ? lstm2_fwd_train_v2_kernel<true> : lstm2_fwd_train_v2_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "na_lstm2_fwd_train_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
     const int ntiles = (int)(Bp / kRows);
     const int grid = ntiles < sms ? ntiles : sms;
-    lstm2_fwd_train_v2_kernel<<<grid, kV2Threads, smem, stream>>>(
+    kern<<<grid, kV2Threads, smem, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), packed_v2, mask, seed, thresh16, drop_scale, reinterpret_cast<__nv_bfloat16*>(h0),
-        reinterpret_cast<__nv_bfloat16*>(h0d), c0, reinterpret_cast<__nv_bfloat16*>(h1), c1, attn_w, attn_b, zpool, stats, B, T, Bp, ntiles);
+        reinterpret_cast<__nv_bfloat16*>(h0d), c0, reinterpret_cast<__nv_bfloat16*>(h1), c1, attn_w, attn_b, zpool, stats, B, T, Bp, ntiles,
+        half_stride > 0 ? half_stride : Bp);
     count_launch();
     return check_launch("na_lstm2_fwd_train_bf16 (v2)");
 }

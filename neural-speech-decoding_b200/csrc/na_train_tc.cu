@@ -353,7 +353,10 @@ struct BwdSmem {
     float red[kBwdEW][kBwdU + 1];
 };
 
-template <int KI>
+// HALF = half tiles (see lstm2_fwd_train_v2_kernel): 64 distinct windows per tile, rows 64..127 mirror rows 0..63.  Copy
+// rp = q / 2 of a window takes unit block 2 hf + rp (8 units per thread instead of 16) and writes its d(gates) to BOTH row
+// copies, so D_R is complete on every row; the weight-gradient MMAs then run over 64 window rows (K = 4 x 16).
+template <int KI, bool HALF>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT][KI/8][128][8]
                      const __nv_bfloat16* __restrict__ h,          // TCL [T][NT][6][128][8]  (this layer's raw h)
@@ -372,7 +375,7 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                      const float* __restrict__ dz, const float* __restrict__ stats, const float* __restrict__ zpool,
                      const float* __restrict__ attn_w, const float* __restrict__ attn_b, int64_t B,
                      float* __restrict__ attn_partial,             // [grid][49]: d attn_w | d attn_b
-                     int T, int64_t Bp, int ntiles) {
+                     int T, int64_t Bp, int ntiles, int64_t drop_stride) {
     using C = BwdCfg<KI>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     BwdSmem<KI>& S = *reinterpret_cast<BwdSmem<KI>*>(smem_raw);
@@ -477,7 +480,7 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                     if (i >= 1) {
                         const uint64_t db = d_actm[sp];
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {
+                        for (int ks = 0; ks < (HALF ? 4 : 8); ++ks) {          // half tiles: rows 64..127 are copies
                             const uint32_t acc = (first_w && ks == 0) ? 0u : 1u;
                             const uint64_t bdesc = desc_adv(db, ks * 256);
                             if (leader) umma_bf16_i(tm_w1, desc_adv(d_dgm1, ks * 256), bdesc, kIdescW, acc);
@@ -494,82 +497,97 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
             const int q = warp & 3, hf = warp >> 2;
             const int row = q * 32 + lane;
             const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-            float dc[kBwdU], ccur[kBwdU];
+            constexpr int kNB = HALF ? 1 : kBwdUB, kU = 8 * kNB;            // unit blocks / units of this thread
+            const int rp = HALF ? (q >> 1) : 0;
+            const int crow = HALF ? (row & 63) : row;                       // canonical row (first copy)
+            const int blk0 = HALF ? hf * kBwdUB + rp : hf * kBwdUB;         // first 8-unit block
+            const int u0 = 8 * blk0;                                        // first hidden unit
+            const int64_t bwin = HALF ? (int64_t)tile * 64 + crow : b0 + row;
+            const uint32_t xbar = HALF ? 1 + (q & 1) : 1 + q;               // the warps that share a window
+            const uint32_t xcnt = HALF ? 64 * kBwdEG : 32 * kBwdEG;
+            float dc[kU], ccur[kU];
 #pragma unroll
-            for (int j = 0; j < kBwdU; ++j) dc[j] = 0.f;
+            for (int j = 0; j < kU; ++j) dc[j] = 0.f;
             {   // c_{T-1} of this tile (afterwards c_t is carried over from the previous iteration's c_{t-1})
 #pragma unroll
-                for (int j = 0; j < kBwdU; j += 4) {
-                    const float4 a = *reinterpret_cast<const float4*>(cstate + tcl32_off(T - 1, ntiles, tile, hf * (kBwdU / 4) + j / 4, row));
+                for (int j = 0; j < kU; j += 4) {
+                    const float4 a = *reinterpret_cast<const float4*>(cstate + tcl32_off(T - 1, ntiles, tile, 2 * blk0 + j / 4, row));
                     ccur[j] = a.x; ccur[j + 1] = a.y; ccur[j + 2] = a.z; ccur[j + 3] = a.w;
                 }
             }
             unsigned char* dgrow = S.dg + row * 16;
-            float dzr[kBwdU], dzz = 0.f, sm_m = 0.f, inv_l = 1.f;
+            float dzr[kU], dzz = 0.f, sm_m = 0.f, inv_l = 1.f;
             if (head) {
-                const int64_t b = b0 + row;
+                const int64_t b = bwin;
                 float part = 0.f;
 #pragma unroll
-                for (int j = 0; j < kBwdU; ++j) {
-                    dzr[j] = (b < B) ? dz[b * kH + hf * kBwdU + j] : 0.f;
-                    part = fmaf(dzr[j], (b < B) ? zpool[b * kH + hf * kBwdU + j] : 0.f, part);
+                for (int j = 0; j < kU; ++j) {
+                    dzr[j] = (b < B) ? dz[b * kH + u0 + j] : 0.f;
+                    part = fmaf(dzr[j], (b < B) ? zpool[b * kH + u0 + j] : 0.f, part);
                 }
                 if (b < B) { sm_m = stats[2 * b]; inv_l = 1.0f / stats[2 * b + 1]; }
                 S.xch0[hf][row] = part;
-                named_bar_sync(1 + q, 32 * kBwdEG);
+                named_bar_sync(xbar, xcnt);
                 dzz = 0.f;
 #pragma unroll
-                for (int e = 0; e < kBwdEG; ++e) dzz += S.xch0[e][row];   // dz . z  (all unit groups, fixed order)
+                for (int e = 0; e < kBwdEG; ++e) {                          // dz . z  (all unit groups, fixed order)
+                    dzz += S.xch0[e][crow];
+                    if (HALF) dzz += S.xch0[e][crow + 64];
+                }
             }
             for (int i = 0; i <= T; ++i) {
                 const int t = T - 1 - i;                                  // step whose gates are in D_G (i < T)
                 // ---- prefetch this step's c_{t-1} and dh_out BEFORE waiting for the tensor pipe -----------
-                float cp[kBwdU], dh[kBwdU];
+                float cp[kU], dh[kU];
                 if (i < T && head) {
                     // head backward fused here: the loads and the exchange overlap the tensor pipe's R/G of this step
-                    uint4 hp[kBwdUB];
+                    uint4 hp[kNB];
 #pragma unroll
-                    for (int bb = 0; bb < kBwdUB; ++bb)
-                        hp[bb] = *reinterpret_cast<const uint4*>(h + ((((int64_t)t * ntiles + tile) * 6 + hf * kBwdUB + bb) * kRows + row) * 8);
+                    for (int bb = 0; bb < kNB; ++bb)
+                        hp[bb] = *reinterpret_cast<const uint4*>(h + ((((int64_t)t * ntiles + tile) * 6 + blk0 + bb) * kRows + row) * 8);
 #pragma unroll
-                    for (int j = 0; j < kBwdU; j += 4) {
+                    for (int j = 0; j < kU; j += 4) {
                         float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (t > 0) c4 = *reinterpret_cast<const float4*>(cstate + tcl32_off(t - 1, ntiles, tile, hf * (kBwdU / 4) + j / 4, row));
+                        if (t > 0) c4 = *reinterpret_cast<const float4*>(cstate + tcl32_off(t - 1, ntiles, tile, 2 * blk0 + j / 4, row));
                         cp[j] = c4.x; cp[j + 1] = c4.y; cp[j + 2] = c4.z; cp[j + 3] = c4.w;
                     }
-                    float hv[kBwdU];
+                    float hv[kU];
 #pragma unroll
-                    for (int bb = 0; bb < kBwdUB; ++bb) {
+                    for (int bb = 0; bb < kNB; ++bb) {
                         const uint32_t w4[4] = {hp[bb].x, hp[bb].y, hp[bb].z, hp[bb].w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) { hv[bb * 8 + 2 * u] = val_lo(w4[u]); hv[bb * 8 + 2 * u + 1] = val_hi(w4[u]); }
                     }
                     float sp = 0.f, gp = 0.f;
 #pragma unroll
-                    for (int j = 0; j < kBwdU; ++j) { sp = fmaf(S.wa[hf * kBwdU + j], hv[j], sp); gp = fmaf(dzr[j], hv[j], gp); }
+                    for (int j = 0; j < kU; ++j) { sp = fmaf(S.wa[u0 + j], hv[j], sp); gp = fmaf(dzr[j], hv[j], gp); }
                     S.xch[i & 1][hf][row] = make_float2(sp, gp);
-                    named_bar_sync(1 + q, 32 * kBwdEG);
+                    named_bar_sync(xbar, xcnt);
                     float xs = 0.f, xg = 0.f;
 #pragma unroll
-                    for (int e = 0; e < kBwdEG; ++e) { const float2 xe = S.xch[i & 1][e][row]; xs += xe.x; xg += xe.y; }   // fixed order
+                    for (int e = 0; e < kBwdEG; ++e) {                      // fixed order
+                        const float2 xe = S.xch[i & 1][e][crow];
+                        xs += xe.x; xg += xe.y;
+                        if (HALF) { const float2 xf = S.xch[i & 1][e][crow + 64]; xs += xf.x; xg += xf.y; }
+                    }
                     const float alpha = __expf(xs + S.ba - sm_m) * inv_l;
                     const float ds = alpha * (xg - dzz);
 #pragma unroll
-                    for (int j = 0; j < kBwdU; ++j) {
-                        dh[j] = fmaf(alpha, dzr[j], ds * S.wa[hf * kBwdU + j]);
+                    for (int j = 0; j < kU; ++j) {
+                        dh[j] = fmaf(alpha, dzr[j], ds * S.wa[u0 + j]);
                         dwa[j] = fmaf(ds, hv[j], dwa[j]);
                     }
                     dba += ds;
                 } else if (i < T) {
                     const int64_t grow = (int64_t)t * Bp + b0 + row;
-                    const float* dhrow = dh_out + grow * kH + hf * kBwdU;           // row-major TMP (head backward)
+                    const float* dhrow = dh_out + grow * kH + u0;                   // row-major TMP (separate head backward; full tiles only)
 #pragma unroll
-                    for (int j = 0; j < kBwdU; j += 4) {
-                        const float4 d = dh_chunked ? *reinterpret_cast<const float4*>(dh_out + tcl32_off(t, ntiles, tile, hf * (kBwdU / 4) + j / 4, row))
+                    for (int j = 0; j < kU; j += 4) {
+                        const float4 d = dh_chunked ? *reinterpret_cast<const float4*>(dh_out + tcl32_off(t, ntiles, tile, 2 * blk0 + j / 4, row))
                                                     : *reinterpret_cast<const float4*>(dhrow + j);
                         dh[j] = d.x; dh[j + 1] = d.y; dh[j + 2] = d.z; dh[j + 3] = d.w;
                         float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (t > 0) c4 = *reinterpret_cast<const float4*>(cstate + tcl32_off(t - 1, ntiles, tile, hf * (kBwdU / 4) + j / 4, row));
+                        if (t > 0) c4 = *reinterpret_cast<const float4*>(cstate + tcl32_off(t - 1, ntiles, tile, 2 * blk0 + j / 4, row));
                         cp[j] = c4.x; cp[j + 1] = c4.y; cp[j + 2] = c4.z; cp[j + 3] = c4.w;
                     }
                 }
@@ -578,16 +596,17 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                 tc_fence_after();
                 if (KI == 48 && i >= 1) {
                     // din of step t+1 = D_R[:, 0:48] * mask * scale  -> dh_out of the layer below
-                    const int64_t grow = (int64_t)(t + 1) * Bp + b0 + row;
+                    const int64_t grow = (int64_t)(t + 1) * Bp + b0 + crow;                               // mask-tensor row
+                    const int64_t gkey = HALF ? (int64_t)(t + 1) * drop_stride + bwin : grow;             // counter-based generator
 #pragma unroll
-                    for (int bb = 0; bb < kBwdUB; ++bb) {
-                        const int blk = hf * kBwdUB + bb;
+                    for (int bb = 0; bb < kNB; ++bb) {
+                        const int blk = blk0 + bb;
                         uint32_t r[8];
                         tmem_ld8(tm_r + lane_base + blk * 8, r);
                         float o[8];
                         if (mask || thresh16 < 65536u) {
                             const uint32_t keep = mask ? mask_keep8(*reinterpret_cast<const uint2*>(mask + grow * kH + blk * 8))
-                                                       : dropout_keep8(seed, grow, blk, thresh16);
+                                                       : dropout_keep8(seed, gkey, blk, thresh16);
 #pragma unroll
                             for (int u = 0; u < 8; ++u) o[u] = ((keep >> u) & 1u) ? __uint_as_float(r[u]) * drop_scale : 0.f;
                         } else {
@@ -604,8 +623,8 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                     break;
                 }
 #pragma unroll
-                for (int bb = 0; bb < kBwdUB; ++bb) {
-                    const int blk = hf * kBwdUB + bb;
+                for (int bb = 0; bb < kNB; ++bb) {
+                    const int blk = blk0 + bb;
                     uint32_t v[32];
                     tmem_ld32(tm_g + lane_base + blk * 32, v);
                     if (i >= 1) {
@@ -641,6 +660,13 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                     st_shared_v4(d4 + kAChunk, pack_val(pf[0], pf[1]), pack_val(pf[2], pf[3]), pack_val(pf[4], pf[5]), pack_val(pf[6], pf[7]));
                     st_shared_v4(d4 + 2 * kAChunk, pack_val(pg[0], pg[1]), pack_val(pg[2], pg[3]), pack_val(pg[4], pg[5]), pack_val(pg[6], pg[7]));
                     st_shared_v4(d4 + 3 * kAChunk, pack_val(po[0], po[1]), pack_val(po[2], po[3]), pack_val(po[4], po[5]), pack_val(po[6], po[7]));
+                    if (HALF) {                                           // the other row copy: D_R must be complete on every row
+                        unsigned char* e4 = S.dg + (row ^ 64) * 16 + (blk * 4) * kAChunk;
+                        st_shared_v4(e4, pack_val(pi[0], pi[1]), pack_val(pi[2], pi[3]), pack_val(pi[4], pi[5]), pack_val(pi[6], pi[7]));
+                        st_shared_v4(e4 + kAChunk, pack_val(pf[0], pf[1]), pack_val(pf[2], pf[3]), pack_val(pf[4], pf[5]), pack_val(pf[6], pf[7]));
+                        st_shared_v4(e4 + 2 * kAChunk, pack_val(pg[0], pg[1]), pack_val(pg[2], pg[3]), pack_val(pg[4], pg[5]), pack_val(pg[6], pg[7]));
+                        st_shared_v4(e4 + 3 * kAChunk, pack_val(po[0], po[1]), pack_val(po[2], po[3]), pack_val(po[4], po[5]), pack_val(po[6], po[7]));
+                    }
                 }
                 tc_fence_before();
                 fence_proxy_async_smem();
@@ -656,19 +682,30 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
         if (warp < kBwdEW) {
 #pragma unroll
             for (int j = 0; j < kBwdU; ++j) {
-                const float v = warp_sum(dwa[j]);
+                const float v = warp_sum(j < (HALF ? 8 : kBwdU) ? dwa[j] : 0.f);
                 if (lane == 0) S.red[warp][j] = v;
             }
             const float vb = warp_sum(dba);
             if (lane == 0) S.red[warp][kBwdU] = vb;
         }
         __syncthreads();
-        if (tid < kH) {
-            const int hfj = tid / kBwdU, j = tid % kBwdU;
-            attn_partial[(size_t)blockIdx.x * (kH + 1) + tid] =
-                S.red[4 * hfj][j] + S.red[4 * hfj + 1][j] + S.red[4 * hfj + 2][j] + S.red[4 * hfj + 3][j];
-        } else if (tid == kH) {
-            attn_partial[(size_t)blockIdx.x * (kH + 1) + kH] = S.red[0][kBwdU] + S.red[1][kBwdU] + S.red[2][kBwdU] + S.red[3][kBwdU];
+        if (!HALF) {
+            if (tid < kH) {
+                const int hfj = tid / kBwdU, j = tid % kBwdU;
+                attn_partial[(size_t)blockIdx.x * (kH + 1) + tid] =
+                    S.red[4 * hfj][j] + S.red[4 * hfj + 1][j] + S.red[4 * hfj + 2][j] + S.red[4 * hfj + 3][j];
+            } else if (tid == kH) {
+                attn_partial[(size_t)blockIdx.x * (kH + 1) + kH] = S.red[0][kBwdU] + S.red[1][kBwdU] + S.red[2][kBwdU] + S.red[3][kBwdU];
+            }
+        } else {
+            // unit u = 8 blk + j belongs to the warps (q, hf) with hf = blk / 2 and q / 2 = blk % 2 (both quarters of that copy);
+            // ds is identical in every warp of a window: count it once (hf = 0, copy 0)
+            if (tid < kH) {
+                const int blk = tid / 8, j = tid % 8, w0 = 4 * (blk / kBwdUB) + 2 * (blk % kBwdUB);
+                attn_partial[(size_t)blockIdx.x * (kH + 1) + tid] = S.red[w0][j] + S.red[w0 + 1][j];
+            } else if (tid == kH) {
+                attn_partial[(size_t)blockIdx.x * (kH + 1) + kH] = S.red[0][kBwdU] + S.red[1][kBwdU];
+            }
         }
     }
     // ---- per-CTA weight-gradient partial: D_W1 rows = gate columns 0..127, D_W2 rows 64..127 = 128..191 ----
@@ -764,9 +801,9 @@ static int launch_bwd(const void* act_in, const void* h, const float* c, const f
                       const void* packed_r, const void* zeros, const unsigned char* mask, uint64_t seed, uint32_t thresh16,
                       float scale, float* din, float* partial, const float* dz, const float* stats, const float* zpool,
                       const float* attn_w, const float* attn_b, int64_t B, float* attn_partial, int64_t T, int64_t Bp,
-                      cudaStream_t st, int* grid_out) {
+                      cudaStream_t st, int* grid_out, int64_t half_stride) {
     const size_t smem = sizeof(BwdSmem<KI>) + 1024;
-    auto kern = lstm_bwd_bf16_kernel<KI>;
+    auto kern = half_stride > 0 ? lstm_bwd_bf16_kernel<KI, true> : lstm_bwd_bf16_kernel<KI, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "lstm_bwd_bf16: shared memory opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e));
     const int ntiles = (int)(Bp / kRows);
@@ -776,7 +813,8 @@ static int launch_bwd(const void* act_in, const void* h, const float* c, const f
                                           c, dh_out, reinterpret_cast<const unsigned char*>(packed_g),
                                           reinterpret_cast<const unsigned char*>(packed_r),
                                           reinterpret_cast<const __nv_bfloat16*>(zeros), mask, seed, thresh16, scale, din, partial,
-                                          KI == 8 ? 1 : 0, dz, stats, zpool, attn_w, attn_b, B, attn_partial, (int)T, Bp, ntiles);
+                                          KI == 8 ? 1 : 0, dz, stats, zpool, attn_w, attn_b, B, attn_partial, (int)T, Bp, ntiles,
+                                          half_stride > 0 ? half_stride : Bp);
     count_launch();
     return check_launch("na_lstm_bwd_bf16");
 }
@@ -788,7 +826,7 @@ static int launch_bwd(const void* act_in, const void* h, const float* c, const f
 namespace na { namespace tc {
 bool train_fwd_v2_enabled();
 int launch_train_fwd_v2(const void*, const unsigned char*, const unsigned char*, uint64_t, uint32_t, float, void*, void*, float*, void*,
-                        float*, const float*, const float*, float*, float*, int64_t, int, int64_t, int, cudaStream_t);
+                        float*, const float*, const float*, float*, float*, int64_t, int, int64_t, int, cudaStream_t, int64_t);
 } }
 
 // scratch floats of na_lstm_bwd_bf16 after its 36,864-byte operand image: per-CTA attention partials [grid][52] then
@@ -801,13 +839,16 @@ extern "C" int64_t na_train_bf16_partial_floats(void) {
 extern "C" int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packed, const unsigned char* mask,
                                        uint64_t seed, int64_t thresh16, float drop_scale, void* h0, void* h0d, float* c0, void* h1, float* h1f,
                                        float* c1, const float* attn_w, const float* attn_b, float* zpool, float* stats,
-                                       int64_t B, int64_t T, int64_t Bp, na_stream_t stream) {
+                                       int64_t B, int64_t T, int64_t Bp, int64_t half_stride, na_stream_t stream) {
     using namespace na;
     NA_REQUIRE(T >= 1 && T < (1 << 20) && Bp >= tc::kRows && Bp % tc::kRows == 0, NA_EINVAL,
                "na_lstm2_fwd_train_bf16: bad shape T=%lld Bp=%lld (Bp must be a multiple of 128)", (long long)T, (long long)Bp);
     NA_REQUIRE_PTR(x_bf16_tmp); NA_REQUIRE_PTR(packed); NA_REQUIRE_PTR(h0); NA_REQUIRE_PTR(c0);
     NA_REQUIRE_PTR(h1); NA_REQUIRE_PTR(c1);
     NA_OPTIONAL_PTR(mask); NA_OPTIONAL_PTR(h0d); NA_OPTIONAL_PTR(h1f); NA_OPTIONAL_PTR(zpool);
+    NA_REQUIRE(half_stride >= 0, NA_EINVAL, "na_lstm2_fwd_train_bf16: half_stride < 0");
+    NA_REQUIRE(half_stride == 0 || (tc::train_fwd_v2_enabled() && zpool != nullptr && h1f == nullptr && B <= Bp / 2), NA_EUNSUPPORTED,
+               "na_lstm2_fwd_train_bf16: half tiles need the generation-2 kernel with fused pooling and B <= Bp / 2");
     NA_REQUIRE(zpool == nullptr || (attn_w && attn_b && stats && B >= 1 && B <= Bp), NA_EINVAL,
                "na_lstm2_fwd_train_bf16: fused pooling needs attn_w, attn_b, stats and 1 <= B <= Bp");
     NA_REQUIRE(zpool != nullptr || h1f != nullptr, NA_EINVAL, "na_lstm2_fwd_train_bf16: give h1f (separate head) or zpool (fused pooling)");
@@ -817,7 +858,7 @@ extern "C" int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packe
     if (tc::train_fwd_v2_enabled() && zpool != nullptr && h1f == nullptr)      // generation 2 (na_train_fwd2.cuh): fused pooling only
         return tc::launch_train_fwd_v2(x_bf16_tmp, reinterpret_cast<const unsigned char*>(packed) + na_decoder_packed_bf16_bytes() / 2, mask,
                                        seed, (uint32_t)thresh16, drop_scale, h0, h0d, c0, h1, c1, attn_w, attn_b, zpool, stats, B, (int)T,
-                                       Bp, tc::tc_sms(), as_stream(stream));
+                                       Bp, tc::tc_sms(), as_stream(stream), half_stride);
     const size_t smem = sizeof(tc::FwdSmem) + 1024;
     cudaError_t e = cudaFuncSetAttribute(tc::lstm2_fwd_train_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "na_lstm2_fwd_train_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
@@ -848,9 +889,11 @@ extern "C" int na_lstm_bwd_bf16(int64_t layer, const void* act_in, const void* h
                                 float* din, float* dw_ih, float* dw_hh,
                                 float* db, void* scratch, const float* dz, const float* stats, const float* zpool,
                                 const float* attn_w, const float* attn_b, int64_t B, float* d_attn,
-                                int64_t T, int64_t Bp, na_stream_t stream) {
+                                int64_t T, int64_t Bp, int64_t half_stride, na_stream_t stream) {
     using namespace na;
     NA_REQUIRE(layer == 0 || layer == 1, NA_EINVAL, "na_lstm_bwd_bf16: layer must be 0 or 1");
+    NA_REQUIRE(half_stride >= 0 && (half_stride == 0 || layer == 0 || dz != nullptr), NA_EUNSUPPORTED,
+               "na_lstm_bwd_bf16: half tiles need the fused head backward on layer 1");
     NA_REQUIRE(T >= 1 && T < (1 << 20) && Bp >= tc::kRows && Bp % tc::kRows == 0, NA_EINVAL,
                "na_lstm_bwd_bf16: bad shape T=%lld Bp=%lld", (long long)T, (long long)Bp);
     NA_REQUIRE_PTR(act_in); NA_REQUIRE_PTR(h); NA_REQUIRE_PTR(cstate); NA_REQUIRE_PTR(packed_fwd);
@@ -876,10 +919,10 @@ extern "C" int na_lstm_bwd_bf16(int64_t layer, const void* act_in, const void* h
     int grid = 0, rc;
     if (layer == 0)
         rc = tc::launch_bwd<8>(act_in, h, cstate, dh_out, pg, packed_r, zeros, nullptr, 0, 65536u, 1.0f, nullptr, partial,
-                               nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, T, Bp, st, &grid);
+                               nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, T, Bp, st, &grid, half_stride);
     else
         rc = tc::launch_bwd<48>(act_in, h, cstate, dh_out, pg, packed_r, zeros, in_mask, seed, (uint32_t)thresh16, drop_scale, din,
-                                partial, dz, stats, zpool, attn_w, attn_b, B, attn_partial, T, Bp, st, &grid);
+                                partial, dz, stats, zpool, attn_w, attn_b, B, attn_partial, T, Bp, st, &grid, half_stride);
     if (rc) return rc;
     if (dz != nullptr)
         if ((rc = reduce_partials(attn_partial, d_attn, grid, tc::kH + 1, st))) return rc;

@@ -632,7 +632,7 @@ def decoder_train_forward(x: Tensor, lstm_params, head_params, p: float, zscore:
 @_device_guard
 def lstm2_fwd_train_bf16(x_tmp: Tensor, packed: Tensor, mask: Optional[Tensor], seed: int, thresh16: int,
                          drop_scale: float, attn_w: Tensor, attn_b: Tensor,
-                         B: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+                         B: int, half_stride: int = 0) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """Training forward of the 2-layer LSTM on tcgen05 with the attention pool fused.  x_tmp fp16 TMP
     [T,Bp,8] (Bp % 128 == 0).  Inter-layer dropout: explicit ``mask`` u8 [T,Bp,48], or (mask None, thresh16 <
     65536) the in-kernel counter-based generator keyed by ``seed``, or none (thresh16 = 65536).
@@ -650,12 +650,12 @@ def lstm2_fwd_train_bf16(x_tmp: Tensor, packed: Tensor, mask: Optional[Tensor], 
     aw, ab = _f32c(attn_w), _f32c(attn_b)
     _lib.call("na_lstm2_fwd_train_bf16", x_tmp.data_ptr(), packed.data_ptr(), _ptr(mask), int(seed), int(thresh16),
               float(drop_scale), h0.data_ptr(), _ptr(h0d) if has_drop else None, c0.data_ptr(), h1.data_ptr(), None,
-              c1.data_ptr(), aw.data_ptr(), ab.data_ptr(), zpool.data_ptr(), stats.data_ptr(), B, T, Bp, _stream())
+              c1.data_ptr(), aw.data_ptr(), ab.data_ptr(), zpool.data_ptr(), stats.data_ptr(), B, T, Bp, int(half_stride), _stream())
     return h0, h0d, c0, h1, c1, zpool, stats
 
 
 @lstm2_fwd_train_bf16.register_fake
-def _(x_tmp, packed, mask, seed, thresh16, drop_scale, attn_w, attn_b, B):
+def _(x_tmp, packed, mask, seed, thresh16, drop_scale, attn_w, attn_b, B, half_stride=0):
     T, Bp, _ = x_tmp.shape
     tcl = lambda: x_tmp.new_empty((T, Bp // TC_TILE, 6, TC_TILE, 8))
     tcl32 = lambda: x_tmp.new_empty((T, Bp // TC_TILE, 12, TC_TILE, 4), dtype=torch.float32)
@@ -731,7 +731,7 @@ def _(like, seed, thresh16, T, Bp):
 @_device_guard
 def lstm_bwd_bf16(layer: int, act_in: Tensor, h: Tensor, c: Tensor, dh: Optional[Tensor], packed: Tensor, w_ih: Tensor,
                   w_hh: Tensor, in_mask: Optional[Tensor], seed: int, thresh16: int, drop_scale: float,
-                  head: Sequence[Tensor], B: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+                  head: Sequence[Tensor], B: int, half_stride: int = 0) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """Fused BPTT + weight gradients of one layer on tcgen05 -> (din TCL32 or empty, dW_ih, dW_hh, db, d_attn).
     ``head`` = [] (dh given) or [dz, stats, zpool, attn_w, attn_b] for layer 1 with the head backward fused:
     dh_t is rebuilt per step inside the kernel and d_attn [49] = (d attn_w | d attn_b) is returned."""
@@ -753,12 +753,12 @@ def lstm_bwd_bf16(layer: int, act_in: Tensor, h: Tensor, c: Tensor, dh: Optional
               zeros.data_ptr(), _ptr(in_mask), int(seed), int(thresh16), float(drop_scale),
               _ptr(din) if layer == 1 else None, dw_ih.data_ptr(), dw_hh.data_ptr(), db.data_ptr(), scratch.data_ptr(),
               *([t.data_ptr() for t in hp] if fused else [None] * 5), int(B), _ptr(d_attn) if fused else None,
-              T, Bp, _stream())
+              T, Bp, int(half_stride), _stream())
     return din, dw_ih, dw_hh, db, d_attn
 
 
 @lstm_bwd_bf16.register_fake
-def _(layer, act_in, h, c, dh, packed, w_ih, w_hh, in_mask, seed, thresh16, drop_scale, head, B):
+def _(layer, act_in, h, c, dh, packed, w_ih, w_hh, in_mask, seed, thresh16, drop_scale, head, B, half_stride=0):
     return (c.new_empty(c.shape if layer == 1 else (0,)), w_ih.new_empty(w_ih.shape, dtype=torch.float32),
             w_hh.new_empty(w_hh.shape, dtype=torch.float32), c.new_empty((192,)),
             c.new_empty((49,) if len(head) else (0,)))
@@ -774,6 +774,17 @@ def _scale_dz(dz: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     amax = dz.detach().abs().max().clamp_min(1e-30)
     s = torch.pow(2.0, 6.0 - torch.ceil(torch.log2(amax)))          # (torch.exp2 would JIT-compile via nvrtc)
     return dz * s, s, 1.0 / s
+
+
+TC_HALF_TILES = True          # 16-bit training tier: half tiles for batches that leave more than half of the SMs idle (A/B knob)
+_SM_COUNT: dict = {}
+
+
+def _sm_count(device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
 
 
 class DecoderFunctionTC(torch.autograd.Function):
@@ -798,19 +809,34 @@ class DecoderFunctionTC(torch.autograd.Function):
             scale1 = 65536.0 / thresh16 if thresh16 > 0 else 0.0   # exactly unbiased for the quantised keep-rate
         elif drop1 is not None:
             mask, scale1 = drop1, scale
-        xt = window_zscore(x.detach(), T, T, zscore, True, NA_F16, TC_TILE)
+        # half tiles (64 windows per 128-row tile, the two row copies split the hidden units) when the batch would leave
+        # more than half of the SMs without a tile: a tile then costs about half a step (strong scaling at small batches)
+        half = TC_HALF_TILES and 2 * ((B + TC_TILE - 1) // TC_TILE) <= _sm_count(x.device)
+        half_stride = padded_batch(B, TC_TILE) if half else 0
+        xin = x.detach()
+        if half:
+            nt = (B + 63) // 64
+            if nt * 64 != B:
+                xin = torch.cat([xin, xin.new_zeros((nt * 64 - B, T, C))])
+            xin = xin.reshape(nt, 64, T, C).repeat(1, 2, 1, 1).reshape(nt * TC_TILE, T, C)       # rows 64..127 mirror rows 0..63
+            if mask is not None:                                                                 # window b -> row (b // 64) * 128 + b % 64
+                b_idx = torch.arange(B, device=x.device)
+                remapped = mask.new_zeros((T, nt * TC_TILE, mask.shape[2]))
+                remapped[:, (b_idx // 64) * TC_TILE + b_idx % 64] = mask[:, :B]
+                mask = remapped
+        xt = window_zscore(xin, T, T, zscore, True, NA_F16, TC_TILE)
         packed = decoder_pack_bf16(lstm_flat)
-        h0, h0d, c0, h1, c1, zpool, stats = lstm2_fwd_train_bf16(xt, packed, mask, seed, thresh16, scale1, head[0], head[1], B)
+        h0, h0d, c0, h1, c1, zpool, stats = lstm2_fwd_train_bf16(xt, packed, mask, seed, thresh16, scale1, head[0], head[1], B, half_stride)
         logits, _ = head_tail_fwd(zpool, head, rrelu_slope, drop2_mask, scale, False)
         w = [_f32c(t) for t in lstm_flat]
         opt = [t for t in (mask, rrelu_slope, drop2_mask) if t is not None]
         ctx.save_for_backward(xt, h0, h0d, c0, h1, c1, packed, stats, zpool, w[0], w[1], w[4], w[5], *head, *opt)
-        ctx.meta = (scale, B, mask is not None, rrelu_slope is not None, drop2_mask is not None, seed, thresh16, scale1)
+        ctx.meta = (scale, B, mask is not None, rrelu_slope is not None, drop2_mask is not None, seed, thresh16, scale1, half_stride)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        scale, B, has_d1, has_rr, has_d2, seed, thresh16, scale1 = ctx.meta
+        scale, B, has_d1, has_rr, has_d2, seed, thresh16, scale1, half_stride = ctx.meta
         has_drop = has_d1 or thresh16 < 65536
         sv = list(ctx.saved_tensors)
         xt, h0, h0d, c0, h1, c1, packed, stats, zpool, w_ih0, w_hh0, w_ih1, w_hh1 = sv[:13]
@@ -825,10 +851,10 @@ class DecoderFunctionTC(torch.autograd.Function):
         dz, dparams = head_tail_bwd(dlogits.contiguous(), zpool, head, rr, d2, scale)
         dz, s, inv_s = _scale_dz(dz)
         din1, dw_ih1, dw_hh1, db1, d_attn = lstm_bwd_bf16(1, h0d if has_drop else h0, h1, c1, None, packed, w_ih1, w_hh1,
-                                                          d1, seed, thresh16, scale1, [dz, stats, zpool, head[0], head[1]], B)
+                                                          d1, seed, thresh16, scale1, [dz, stats, zpool, head[0], head[1]], B, half_stride)
         dparams = torch.cat([d_attn * inv_s, dparams[H + 1:]])
         head_grads = split_head_grads(dparams, H, NC)
-        _, dw_ih0, dw_hh0, db0, _ = lstm_bwd_bf16(0, xt, h0, c0, din1, packed, w_ih0, w_hh0, None, 0, 65536, 1.0, [], B)
+        _, dw_ih0, dw_hh0, db0, _ = lstm_bwd_bf16(0, xt, h0, c0, din1, packed, w_ih0, w_hh0, None, 0, 65536, 1.0, [], B, half_stride)
         db0, db1 = db0 * inv_s, db1 * inv_s
         grads = [dw_ih0 * inv_s, dw_hh0 * inv_s, db0, db0.clone(), dw_ih1 * inv_s, dw_hh1 * inv_s, db1, db1.clone(),
                  *head_grads]

@@ -1,0 +1,24 @@
+import sys, numpy as np, torch
+sys.path.insert(0, '.')
+from neural_speech_decoding_b200 import ops
+from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+ck = np.load('tests/golden/checkpoint_3class.npz')
+sd = {str(k): torch.from_numpy(ck[str(k)].copy()) for k in ck['__order__']}
+dev = torch.device('cuda:0')
+m = EEG_LSTM(); m.load_state_dict(sd); m = m.to(dev).train()
+m.compute_dtype = torch.bfloat16
+for B in [int(a) for a in sys.argv[1:]] or [8192]:
+    x = torch.randn(B, 625, 8, device=dev) * 2.73
+    y = torch.randint(0, 3, (B,), device=dev)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    def step():
+        opt.zero_grad(); torch.nn.functional.cross_entropy(m(x), y).backward(); opt.step()
+    for half in (False, True):
+        ops.TC_HALF_TILES = half
+        step(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3): step()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print(f"16-bit train step B={B} half_tiles={half}: {ms:.2f} ms -> {B/ms*1e3:.0f} windows/s")

@@ -363,3 +363,33 @@ def test_fp16_tier_input_range_and_nan(dev, checkpoint):
     m.zero_grad()
     torch.nn.functional.cross_entropy(m((x[:8] + 1.0e5).to(dev)), torch.zeros(8, dtype=torch.long, device=dev)).backward()
     assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+@pytest.mark.parametrize("B,T", [(300, 30), (64, 7), (1, 3), (65, 12)])
+def test_bf16_training_half_tiles_match_full_tiles(dev, checkpoint, B, T):
+    """Half tiles (64 windows per tile, the two row copies split the hidden units -- used when a batch would leave more than
+    half of the SMs idle) against full tiles: bit-identical logits, gradients equal up to the order of the fp32 weight-gradient
+    accumulation, in eval mode and in train mode with the counter-based in-kernel dropout (same mask in both layouts)."""
+    from neural_speech_decoding_b200 import ops
+    gen = torch.Generator(device="cpu").manual_seed(B + T)
+    x = (torch.randn(B, T, 8, generator=gen) * 2.73).to(dev)
+    y = torch.randint(0, 3, (B,), generator=gen).to(dev)
+    m = bf16_model(dev, checkpoint)
+    def run(half, train):
+        ops.TC_HALF_TILES = half
+        m.train(train)
+        m.zero_grad()
+        torch.manual_seed(77)                      # same dropout seed / RReLU slopes / head dropout in both runs
+        out = m(x)
+        torch.nn.functional.cross_entropy(out, y).backward()
+        return out.detach().clone(), [p.grad.clone() for p in m.parameters()]
+    try:
+        for train in (False, True):
+            a, ga = run(True, train)
+            b, gb = run(False, train)
+            assert torch.isfinite(a).all() and torch.equal(a, b), (train, (a - b).abs().max().item())
+            gmax = max(float(q.abs().max()) for q in gb)
+            for (k, _), p, q in zip(m.named_parameters(), ga, gb):
+                assert (p - q).abs().max().item() <= 2e-5 * gmax, (train, k, (p - q).abs().max().item(), gmax)
+    finally:
+        ops.TC_HALF_TILES = True
