@@ -338,6 +338,24 @@ int na_lstm_bwd_x3(int64_t layer, const void* act_in, const void* h, const float
 int na_lstm_wgrad_x3(int64_t layer, const void* dg, const void* act_in, const void* h, const void* zeros,
                      float* dw_ih, float* dw_hh, float* db, float* scratch, int64_t T, int64_t Bp, na_stream_t stream);
 
+/* ---- wide decoders (H = 96 / 144 / 192, BASELINE configs[4]): TRAINING on the tensor cores, 16-bit tier -----------
+ * Replaces torch autograd of lstm_eeg_model.py:32-39 with hidden_size > 48 for the serial part of a
+ * layer; everything parallel over time (input projection, din, weight gradients) is a plain GEMM done by the caller.
+ * Per-thread vectors use the wide tile layout WTL [T][NT][H/48][3][128][E] (NT = Bp / 128; thread = window row x 16-unit
+ * group g of 48-unit task k; gates / d(gates): E = 64 fp16 in accumulator column order (u/4)*16 + gate*4 + u%4;
+ * h: 16 fp16; c, dh: 16 fp32).
+ *   na_lstm_wide_fwd_train  gx = in . W_ih^T + b (WTL, fp16) -> activated gates, h, c for every step.
+ *                           w_image: [H/48][H/16][2][192][8] fp16 = W_hh rows of a task (accumulator column order) x K16 slices.
+ *   na_lstm_wide_bwd        gates, c, dh_in (WTL) -> dg (WTL) with dh_rec = dG . W_hh carried through the steps.
+ *                           w_image: [H/48][12][2][H][8] fp16 = W_hh^T, K = the task's 192 gate columns.
+ *                           workspace: na_wide_train_ws_floats(H) floats (running d(cell), L2-resident).
+ */
+int64_t na_wide_train_ws_floats(int64_t H);
+int na_lstm_wide_fwd_train(const void* gx, const void* w_image, void* gates, void* h, float* c, int64_t T, int64_t Bp,
+                           int64_t H, na_stream_t stream);
+int na_lstm_wide_bwd(const void* gates, const float* c, const float* dh_in, const void* w_image, void* dg, float* workspace,
+                     int64_t T, int64_t Bp, int64_t H, na_stream_t stream);
+
 /* ---- phase-coupling preprocessing filter, OPT-IN ---------------------------------------------
  * Replaces, for batches of windows, Utilities/preprocessor.py:21-36 -> MindsAI/mindsai_filter_python/core.py:14-48 (the
  * step in front of the decoder on every live window): analytic signal per channel (Hilbert transform), pairwise

@@ -57,6 +57,9 @@ SIGNATURES = {
     "na_head_tail_fwd_f32": (c_int, [P] * 9 + [P, P, F32, P, P, I64, I64, I64, P]),
     "na_head_tail_bwd_f32": (c_int, [P] * 10 + [P, P, F32, P, P, P, I64, I64, I64, P]),
     "na_iir_chain": (c_int, [P, P, P, P, P, I64, I64, I64, I64, I32, I32, I32, I64, P]),
+    "na_wide_train_ws_floats": (c_int64, [I64]),
+    "na_lstm_wide_fwd_train": (c_int, [P, P, P, P, P, I64, I64, I64, P]),
+    "na_lstm_wide_bwd": (c_int, [P, P, P, P, P, P, I64, I64, I64, P]),
     "na_phase_coupling_filter": (c_int, [P, P, P, ctypes.c_double, P, I64, I64, I64, P]),
     "na_csv_parse_f32": (c_int, [P, P, P, P, I64, I64, I64, P]),
     "na_trial_mean_f32": (c_int, [P, P, I64, I64, P]),

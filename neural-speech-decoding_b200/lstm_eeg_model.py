@@ -245,6 +245,14 @@ class EEG_LSTM(nn.Module):
                         drop1 = (int(torch.randint(0, 2 ** 62, (1,)).item()), int(round((1.0 - self.dropout_p) * 65536)))
                 logits = ops.decoder_train_forward_tc(x, lstm_params, head, self.dropout_p, self.zscore_input,
                                                       drop1, rr, d2)
+            elif bf16 and self.tc_wide_supported() and not x.requires_grad:
+                # wide shapes (BASELINE configs[4]) on the 16-bit tier: streamed-weight recurrence kernels + cuBLAS for the
+                # time-parallel GEMMs; dropout / RReLU noise as tensors (time-major padded to 128)
+                drop1 = None
+                if self.training:
+                    d1, rr, d2 = self._draw_noise(B, T, x.device, ops.TC_TILE)
+                    drop1 = d1[0] if d1 is not None else None
+                logits = ops.decoder_train_forward_wide_tc(x, lstm_params, head, self.dropout_p, self.zscore_input, drop1, rr, d2)
             elif (ops.EXACT_TC_TRAIN and not bf16 and self.tc_supported() and not x.requires_grad
                   and x.dtype in (torch.float32, torch.float16, torch.bfloat16)):
                 # exact tier, flagship shape: fp32-accurate tensor-core training (operands split into fp16 hi + lo)

@@ -92,7 +92,8 @@ def all_custom_ops():
     return [window_zscore, pack_lstm_layer, lstm_layer_fwd, lstm_layer_bwd, lstm_layer_wgrad, head_fwd,
             head_bwd, trial_mean, decoder_pack_bf16, decoder_infer_bf16, lstm2_fwd_train_bf16, lstm_bwd_bf16,
             dropout_mask_u8, head_tail_fwd, head_tail_bwd, decoder_infer_bf16_x32, decoder_pack_x3, decoder_infer_x3,
-            decoder_pack_wide_bf16, decoder_infer_wide_bf16, x3_split_input, lstm_fwd_train_x3, lstm_bwd_x3, lstm_wgrad_x3]
+            decoder_pack_wide_bf16, decoder_infer_wide_bf16, x3_split_input, lstm_fwd_train_x3, lstm_bwd_x3, lstm_wgrad_x3,
+            lstm_wide_fwd_train, lstm_wide_bwd]
 
 
 def launch_count() -> int:
@@ -1056,3 +1057,202 @@ def decoder_train_forward_x3(x: Tensor, lstm_params, head_params, p: float, zsco
                              drop1=None, rrelu_slope=None, drop2_mask=None) -> Tensor:
     flat = [t for layer in lstm_params for t in layer]
     return DecoderFunctionX3.apply(x, p, zscore, drop1, rrelu_slope, drop2_mask, *flat, *head_params)
+
+
+# ------------------------------------------------------------------------------------------
+# wide decoders (H = 96 / 144 / 192): training on the tensor cores, 16-bit tier (csrc/na_wide_train.cu)
+# ------------------------------------------------------------------------------------------
+def _wtl_perm(H: int, device):
+    """Index tensors between torch's gate-major row layout (gate * H + unit) and the WTL element order."""
+    nch = H // 48
+    k, g, q, gate, ur = torch.meshgrid(torch.arange(nch), torch.arange(3), torch.arange(4), torch.arange(4), torch.arange(4), indexing="ij")
+    unit = 48 * k + 16 * g + 4 * q + ur
+    return (gate * H + unit).reshape(-1).to(device)             # WTL position (k, g, q*16 + gate*4 + ur) -> torch column
+
+
+def _to_wtl(x2d: Tensor, T: int, Bp: int, cols: Tensor, E: int) -> Tensor:
+    """row-major [T*Bp, F] -> WTL [T, NT, nch, 3, 128, E] (gather of the columns, then the tile transpose)."""
+    nt = Bp // TC_TILE
+    nch3 = cols.numel() // E
+    return x2d.index_select(1, cols).reshape(T, nt, TC_TILE, nch3, E).permute(0, 1, 3, 2, 4).contiguous()
+
+
+def _from_wtl(w: Tensor, T: int, Bp: int, cols: Tensor, F: int) -> Tensor:
+    """WTL -> row-major [T*Bp, F] in torch column order."""
+    nt = Bp // TC_TILE
+    flat = w.reshape(T, nt, -1, TC_TILE, w.shape[-1]).permute(0, 1, 3, 2, 4).reshape(T * Bp, -1)
+    out = torch.empty((T * Bp, F), dtype=w.dtype, device=w.device)
+    out[:, cols] = flat
+    return out
+
+
+def _wide_images(w_hh: Tensor, H: int):
+    """The two streamed weight images of a layer (see include/neuroalpha.h): forward [nch][H/16][2][192][8] and
+    backward [nch][12][2][H][8], fp16."""
+    nch = H // 48
+    n = torch.arange(192, device=w_hh.device)
+    j, gate = (n // 16) * 4 + n % 4, (n % 16) // 4
+    rows = (gate[None, :] * H + 48 * torch.arange(nch, device=w_hh.device)[:, None] + j[None, :])        # [nch, 192] torch rows
+    wt = w_hh.detach().float()[rows]                                                                    # [nch, 192 (n), H (k)]
+    fwd = wt.reshape(nch, 192, H // 16, 2, 8).permute(0, 2, 3, 1, 4).contiguous().to(torch.float16)     # [nch][ks][c2][n][e]
+    bwd = wt.permute(0, 2, 1).reshape(nch, H, 12, 2, 8).permute(0, 2, 3, 1, 4).contiguous().to(torch.float16)   # [nch][ks][c2][n_out][e]
+    return fwd, bwd
+
+
+@torch.library.custom_op("neuroalpha::lstm_wide_fwd_train", mutates_args=(), device_types="cuda")
+@_device_guard
+def lstm_wide_fwd_train(gx: Tensor, w_image: Tensor, H: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Serial part of one wide layer's training forward.  gx: WTL fp16 [T, NT, H/48, 3, 128, 64] -> (gates WTL, h WTL fp16
+    [.., 16], c WTL fp32 [.., 16])."""
+    _require_cuda(gx, w_image)
+    T, NT = gx.shape[0], gx.shape[1]
+    gates = torch.empty_like(gx)
+    h = torch.empty(gx.shape[:-1] + (16,), dtype=torch.float16, device=gx.device)
+    c = torch.empty(gx.shape[:-1] + (16,), dtype=torch.float32, device=gx.device)
+    _lib.call("na_lstm_wide_fwd_train", gx.data_ptr(), w_image.data_ptr(), gates.data_ptr(), h.data_ptr(), c.data_ptr(), T, NT * TC_TILE,
+              int(H), _stream())
+    return gates, h, c
+
+
+@lstm_wide_fwd_train.register_fake
+def _(gx, w_image, H):
+    return gx.new_empty(gx.shape), gx.new_empty(gx.shape[:-1] + (16,)), gx.new_empty(gx.shape[:-1] + (16,), dtype=torch.float32)
+
+
+@torch.library.custom_op("neuroalpha::lstm_wide_bwd", mutates_args=(), device_types="cuda")
+@_device_guard
+def lstm_wide_bwd(gates: Tensor, c: Tensor, dh_in: Tensor, w_image: Tensor, H: int) -> Tensor:
+    """Serial part of one wide layer's BPTT: (gates, c, dh_in) WTL -> d(gates) WTL fp16."""
+    _require_cuda(gates, c, dh_in, w_image)
+    T, NT = gates.shape[0], gates.shape[1]
+    dg = torch.empty_like(gates)
+    ws = torch.empty((_lib.query("na_wide_train_ws_floats", int(H)),), dtype=torch.float32, device=gates.device)
+    _lib.call("na_lstm_wide_bwd", gates.data_ptr(), c.data_ptr(), dh_in.data_ptr(), w_image.data_ptr(), dg.data_ptr(), ws.data_ptr(),
+              T, NT * TC_TILE, int(H), _stream())
+    return dg
+
+
+@lstm_wide_bwd.register_fake
+def _(gates, c, dh_in, w_image, H):
+    return gates.new_empty(gates.shape)
+
+
+def _mm_f32(a: Tensor, b: Tensor) -> Tensor:
+    """fp16 x fp16 -> fp32 GEMM (cuBLAS, fp32 accumulate AND fp32 output: sums over millions of rows must not round to fp16)."""
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except TypeError:                                  # older torch: chunk the reduction dimension and accumulate in fp32
+        out = torch.zeros((a.shape[0], b.shape[1]), dtype=torch.float32, device=a.device)
+        step = 1 << 18
+        for i in range(0, a.shape[1], step):
+            out += a[:, i:i + step].float() @ b[i:i + step].float()
+        return out
+
+
+class DecoderFunctionWideTC(torch.autograd.Function):
+    """Training step of a wide decoder (hidden_size 96 / 144 / 192, 2 layers) on the 16-bit tensor-core tier: cuBLAS for
+    everything that is parallel over time, the streamed-weight recurrence kernels for the serial part of every layer and
+    direction, the fp32 head kernels.  2e-2 contract."""
+
+    @staticmethod
+    def forward(ctx, x, p, zscore, drop1, rrelu_slope, drop2_mask, *params):
+        _require_cuda(x, *params)
+        ctx.param_dtypes = [t.dtype for t in params]
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("the tensor-core training tier does not produce d/dx; use compute_dtype=float32")
+        B, T, C = x.shape
+        lstm, head = [t.detach() for t in params[:8]], [_f32c(t.detach()) for t in params[8:]]
+        H = lstm[1].shape[1]
+        scale = 1.0 / (1.0 - p) if p < 1.0 else 0.0
+        Bp = padded_batch(B, TC_TILE)
+        dev = x.device
+        cols64, cols16 = _wtl_perm(H, dev), None
+        unit_cols = torch.arange(H, device=dev)                                  # WTL h / c / dh order == unit order (k, g, u)
+        xin = x.detach().float()
+        if zscore:
+            xin = window_zscore(xin, T, T, True, False, NA_F32)
+        xt = torch.zeros((T, Bp, C), dtype=torch.float32, device=dev)
+        xt[:, :B] = xin.permute(1, 0, 2)
+        layer_in = xt.reshape(T * Bp, C)
+        saved, h_rows = [], []
+        mask = None
+        for l in range(2):
+            w_ih, w_hh, b_ih, b_hh = lstm[4 * l:4 * l + 4]
+            fimg, bimg = _wide_images(w_hh, H)
+            if l == 0:          # K = 8: fp32 GEMM (raw EEG can exceed fp16's range), rounded to fp16 afterwards
+                gx2d = torch.addmm((b_ih + b_hh).float(), layer_in, w_ih.float().t()).to(torch.float16)
+            else:
+                gx2d = torch.addmm((b_ih + b_hh).to(torch.float16), layer_in, w_ih.to(torch.float16).t())
+            gates, h, c = lstm_wide_fwd_train(_to_wtl(gx2d, T, Bp, cols64, 64), fimg, H)
+            del gx2d
+            h2d = _from_wtl(h, T, Bp, unit_cols, H)                              # [T*Bp, H] fp16, unit order
+            saved += [gates, c, bimg, layer_in if l == 0 else None]
+            h_rows.append(h2d)
+            if l == 0:
+                if drop1 is not None:                                            # inter-layer dropout (lstm_eeg_model.py:21)
+                    mask = drop1.reshape(T * Bp, H).to(torch.float16)
+                    layer_in = h2d * mask * scale
+                else:
+                    layer_in = h2d
+        h1 = h_rows[1].float().reshape(T, Bp, H)
+        logits, _, stats, zpool = head_fwd(h1, B, head, rrelu_slope, drop2_mask, scale, False, True)
+        opt = [t for t in (mask, rrelu_slope, drop2_mask) if t is not None]
+        ctx.save_for_backward(saved[0], saved[1], saved[2], saved[3], saved[4], saved[5], saved[6], h_rows[0], h_rows[1],
+                              layer_in if mask is not None else h_rows[0], stats, zpool, *lstm, *head, *opt)
+        ctx.meta = (scale, B, T, Bp, H, mask is not None, rrelu_slope is not None, drop2_mask is not None)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        scale, B, T, Bp, H, has_d1, has_rr, has_d2 = ctx.meta
+        sv = list(ctx.saved_tensors)
+        gates0, c0, bimg0, x2d, gates1, c1, bimg1, h0_2d, h1_2d, in1_2d, stats, zpool = sv[:12]
+        lstm, head = sv[12:20], sv[20:28]
+        rest = sv[28:]
+        mask = rest.pop(0) if has_d1 else None
+        rr = rest.pop(0) if has_rr else None
+        d2 = rest.pop(0) if has_d2 else None
+        dev = dlogits.device
+        NC = dlogits.shape[1]
+        cols64, unit_cols = _wtl_perm(H, dev), torch.arange(H, device=dev)
+        h1 = h1_2d.float().reshape(T, Bp, H)
+        dh1, dparams = head_bwd(dlogits.contiguous(), h1, stats, zpool, head, rr, d2, scale)
+        del h1
+        # d(gates) are fp16: scale the gradient entering the recurrence by an exact power of two (max|dh| -> 2^6)
+        amax = dh1.detach().abs().max().clamp_min(1e-30)
+        s = torch.pow(2.0, 6.0 - torch.ceil(torch.log2(amax)))
+        inv_s = 1.0 / s
+        zeros_h = torch.zeros((Bp, H), dtype=torch.float16, device=dev)
+        def layer_bwd(gates, c, bimg, dh2d, in2d, h2d, w_ih):
+            dg = lstm_wide_bwd(gates, c, _to_wtl(dh2d, T, Bp, unit_cols, 16), bimg, H)
+            dg2d = _from_wtl(dg, T, Bp, cols64, 4 * H)                            # [T*Bp, 4H] fp16, torch gate order
+            del dg
+            dgt = dg2d.t()
+            in16 = in2d if in2d.dtype == torch.float16 else in2d.to(torch.float16)
+            dw_ih = _mm_f32(dgt, in16)
+            hprev = torch.cat([zeros_h, h2d[:-Bp]])                               # h_{t-1}
+            dw_hh = _mm_f32(dgt, hprev)
+            db = _mm_f32(dgt, torch.ones((dg2d.shape[0], 8), dtype=torch.float16, device=dev))[:, 0].contiguous()
+            return dg2d, dw_ih, dw_hh, db
+        dg1, dw_ih1, dw_hh1, db1 = layer_bwd(gates1, c1, bimg1, (dh1 * s).reshape(T * Bp, H), in1_2d, h1_2d, lstm[4])
+        del dh1
+        din1 = _mm_f32(dg1, lstm[4].to(torch.float16))                            # [T*Bp, H] fp32 (still scaled by s)
+        del dg1
+        if mask is not None:
+            din1 = din1 * mask * scale
+        # layer 0: its input is the raw fp32 window; x can exceed fp16's range, so the weight gradient uses x / 16 (exact) and is rescaled
+        x16 = (x2d * 0.0625).to(torch.float16)
+        dg0, dw_ih0, dw_hh0, db0 = layer_bwd(gates0, c0, bimg0, din1, x16, h0_2d, lstm[0])
+        dw_ih0 = dw_ih0 * 16.0
+        del dg0, din1
+        head_grads = split_head_grads(dparams, H, NC)
+        db0, db1 = db0 * inv_s, db1 * inv_s
+        grads = [dw_ih0 * inv_s, dw_hh0 * inv_s, db0, db0.clone(), dw_ih1 * inv_s, dw_hh1 * inv_s, db1, db1.clone(), *head_grads]
+        grads = [g.to(dt) if g.dtype != dt else g for g, dt in zip(grads, ctx.param_dtypes)]
+        return (None, None, None, None, None, None, *grads)
+
+
+def decoder_train_forward_wide_tc(x: Tensor, lstm_params, head_params, p: float, zscore: bool = False,
+                                  drop1=None, rrelu_slope=None, drop2_mask=None) -> Tensor:
+    flat = [t for layer in lstm_params for t in layer]
+    return DecoderFunctionWideTC.apply(x, p, zscore, drop1, rrelu_slope, drop2_mask, *flat, *head_params)

@@ -393,3 +393,62 @@ def test_bf16_training_half_tiles_match_full_tiles(dev, checkpoint, B, T):
                 assert (p - q).abs().max().item() <= 2e-5 * gmax, (train, k, (p - q).abs().max().item(), gmax)
     finally:
         ops.TC_HALF_TILES = True
+
+
+# ---------------------------------------------------------------------------------------------
+# wide decoders: training on the tensor cores (streamed-weight recurrence kernels + cuBLAS, csrc/na_wide_train.cu)
+# ---------------------------------------------------------------------------------------------
+def test_wide_training_stress_shape_vs_reference(dev, golden_dir):
+    """BASELINE configs[4] (hidden_size = 192): logits, loss and every gradient of the 16-bit tensor-core training tier against
+    float64 autograd of the reference module on the reference's own H = 192 fixture (2e-2 contract)."""
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    f = np.load(golden_dir / "ref_stress_h192.npz")
+    sd = {k[3:]: torch.from_numpy(f[k]) for k in f.files if k.startswith("sd.")}
+    m = EEG_LSTM(hidden_size=192)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).eval()
+    m.compute_dtype = torch.bfloat16
+    x, y = torch.from_numpy(f["x"]), torch.from_numpy(f["y"])
+    logits = m(x.to(dev))
+    assert rel(logits.detach().cpu().numpy(), f["logits"]) < BF16_TOL
+    loss = torch.nn.functional.cross_entropy(logits, y.to(dev))
+    loss.backward()
+    assert abs(loss.item() - float(f["loss"])) < 2e-2
+    ref = RefEEGLSTM(hidden_size=192).double().eval()
+    ref.load_state_dict({k: v.double() for k, v in sd.items()}, strict=True)
+    torch.nn.functional.cross_entropy(ref(x.double()), y).backward()
+    truth = {k: p.grad.numpy() for k, p in ref.named_parameters()}
+    worst = grad_rel(m, truth)
+    worst.pop("attn.bias")                                  # analytically zero (softmax shift invariance): rounding noise on both sides
+    assert max(worst.values()) < BF16_TOL, worst
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+@pytest.mark.parametrize("H,B,T", [(96, 150, 23), (144, 300, 9), (192, 5, 1)])
+def test_wide_training_matches_exact_tier_with_noise(dev, H, B, T):
+    """Seeded wide decoders in TRAIN mode with injected noise (inter-layer dropout mask, RReLU slopes, head dropout): the
+    tensor-core tier against the exact fp32 tier (pinned to the oracle in test_gpu_parity.py), several tiles, ragged batch, T = 1."""
+    from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
+    torch.manual_seed(7 * H + B)
+    m = EEG_LSTM(hidden_size=H, num_classes=5).to(dev).train()
+    x = (torch.randn(B, T, 8) * 2.73).to(dev)
+    y = torch.randint(0, 5, (B,)).to(dev)
+    d1 = (torch.rand(1, B, T, H) >= 0.6).float()
+    rr = torch.empty(B, 32).uniform_(1 / 8, 1 / 3)
+    d2 = (torch.rand(B, 32) >= 0.6).float()
+    m.inject_noise(drop1=d1, rrelu_slope=rr, drop2=d2)
+    def run(dtype):
+        m.compute_dtype = dtype
+        m.zero_grad()
+        out = m(x)
+        torch.nn.functional.cross_entropy(out, y).backward()
+        return out.detach().cpu().numpy(), {k: p.grad.detach().cpu().numpy().copy() for k, p in m.named_parameters()}
+    lb, gb = run(torch.float32)
+    la, ga = run(torch.bfloat16)
+    assert np.isfinite(la).all() and rel(la, lb) < BF16_TOL, rel(la, lb)
+    gmax = max(float(np.abs(v).max()) for v in gb.values())
+    for k in ga:
+        scale = np.abs(gb[k]).max()
+        if k == "attn.bias" or (T == 1 and ("weight_hh" in k or k == "attn.weight")):
+            scale = gmax
+        assert np.abs(ga[k] - gb[k]).max() / scale < BF16_TOL, (k, np.abs(ga[k] - gb[k]).max() / scale)
