@@ -619,20 +619,34 @@ def stress_leg(dev, peaks):
         m.compute_dtype = torch.float32
         ms32 = time_steps(lambda: m.decode(x[:256], want_probs=True), 1, 1, 1, dev)
     # ---- configs[4] "... and BPTT backward": one train step (fwd + BPTT + Adam) at the stress shape -----------------
-    Bt = 256
-    m.train()
-    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
-    yt = torch.randint(0, NC, (Bt,), generator=torch.Generator(device="cpu").manual_seed(5)).to(dev)
-    def tstep():
-        opt.zero_grad()
-        torch.nn.functional.cross_entropy(m(x[:Bt]), yt).backward()
-        opt.step()
-    ms_t = time_steps(tstep, 1, 1, 1, dev)
     fb = 3 * flops - 2 * Ts * 4 * Hs * C                   # fwd + bwd, no dX of layer 0
-    train = {"value": Bt / (ms_t * 1e-3), "unit": "windows/s", "ms_per_step": ms_t, "batch": Bt,
-             "tier": "exact fp32 (generic FFMA forward-with-save + fused BPTT + time-parallel weight gradients)",
-             "achieved_tflops": fb * Bt / (ms_t * 1e-3) / 1e12,
-             "parity": "tests/test_gpu_parity.py::test_stress_shape_h192 (gradients within 1e-5 of the fp64 truth)"}
+    def train_step_time(dtype, Bt):
+        torch.manual_seed(0)
+        mt = EEG_LSTM(hidden_size=Hs).to(dev).train()
+        mt.compute_dtype = dtype
+        opt = torch.optim.Adam(mt.parameters(), lr=1e-3)
+        yt = torch.randint(0, NC, (Bt,), generator=torch.Generator(device="cpu").manual_seed(5)).to(dev)
+        def tstep():
+            opt.zero_grad()
+            torch.nn.functional.cross_entropy(mt(x[:Bt]), yt).backward()
+            opt.step()
+        ms_t = time_steps(tstep, 1, 1, 1, dev)
+        del mt, opt
+        torch.cuda.empty_cache()
+        return ms_t
+    Bt16, Bt32 = 2048, 256
+    ms_t16 = train_step_time(torch.bfloat16, Bt16)
+    ms_t32 = train_step_time(torch.float32, Bt32)
+    train = {"value": Bt16 / (ms_t16 * 1e-3), "unit": "windows/s", "ms_per_step": ms_t16, "batch": Bt16,
+             "tier": "16-bit tensor-core tier: lstm_wide_fwd_kernel<4> / lstm_wide_bwd_kernel<4> (tcgen05, weights streamed by TMA, the "
+                     "recurrent state resident) for the serial part of every layer and direction + cuBLAS for the time-parallel GEMMs",
+             "achieved_tflops": fb * Bt16 / (ms_t16 * 1e-3) / 1e12,
+             "parity": "tests/test_gpu_bf16.py::test_wide_training_* (the reference's H=192 fixture vs float64 autograd, 2e-2; train-mode noise vs the exact tier)",
+             "fp32_exact": {"value": Bt32 / (ms_t32 * 1e-3), "unit": "windows/s", "ms_per_step": ms_t32, "batch": Bt32,
+                            "tier": "generic FFMA forward-with-save + fused BPTT + time-parallel weight gradients",
+                            "parity": "tests/test_gpu_parity.py::test_stress_shape_h192 (gradients within 1e-5 of the fp64 truth)"},
+             "note": "2,048 windows = 16 tiles: the serial kernels occupy 16 of 148 SMs (the saves are 27 MB per window; memory, not "
+                     "SMs, bounds the batch)"}
     del x
     torch.cuda.empty_cache()
     tf = flops * Bs / (ms_k * 1e-3) / 1e12
@@ -645,7 +659,7 @@ def stress_leg(dev, peaks):
             "frac_of_bf16_sustained_peak": tf / peaks["bf16_tflops_sustained"], "frac_of_bf16_burst_peak": tf / peaks["bf16_tflops"],
             "fp32_exact_windows_per_s": 256 / (ms32 * 1e-3),
             "parity": "tests/test_gpu_bf16.py::test_wide_*: reference golden (H=192) and the exact tier, 2e-2 contract",
-            "note": "training at this shape runs on the exact-fp32 generic tier (no tensor-core BPTT for H > 48)"}
+            "note": "stress.train: the 16-bit tier trains at this shape on the tensor cores since round 2"}
 
 
 def train_leg(args, world, rank, dev):

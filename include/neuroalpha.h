@@ -341,7 +341,7 @@ int na_lstm_wgrad_x3(int64_t layer, const void* dg, const void* act_in, const vo
 /* ---- wide decoders (H = 96 / 144 / 192, BASELINE configs[4]): TRAINING on the tensor cores, 16-bit tier -----------
  * Replaces torch autograd of lstm_eeg_model.py:32-39 with hidden_size > 48 for the serial part of a
  * layer; everything parallel over time (input projection, din, weight gradients) is a plain GEMM done by the caller.
- * Per-thread vectors use the wide tile layout WTL [T][NT][H/48][3][128][E] (NT = Bp / 128; thread = window row x 16-unit
+ * Per-thread vectors use the wide tile layout WTL [T][NT][H/48][3][P][128][16 B] (NT = Bp / 128; thread = window row x 16-unit
  * group g of 48-unit task k; gates / d(gates): E = 64 fp16 in accumulator column order (u/4)*16 + gate*4 + u%4;
  * h: 16 fp16; c, dh: 16 fp32).
  *   na_lstm_wide_fwd_train  gx = in . W_ih^T + b (WTL, fp16) -> activated gates, h, c for every step.

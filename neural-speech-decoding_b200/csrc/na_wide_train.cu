@@ -16,9 +16,11 @@
 //                               D_R += dG[task] . W_hh[task] (K = 192 gate columns, N = H); two D_R accumulators alternate
 //                               between steps.  The running d(cell) lives in an L2-resident per-CTA workspace.
 //
-// Per-thread vectors live in the "wide tile layout" WTL [T][NT][NCH][3][128][E]: thread (row, 16-unit group g) of task k
-// owns E contiguous elements (gates / d(gates): E = 64 fp16 in TMEM column order q*16 + gate*4 + u%4, q = u/4; h: 16 fp16;
-// c, dh: 16 fp32), so a warp touches 32 E contiguous elements.  ops.py converts to / from row-major for the GEMMs.
+// Per-thread vectors live in the "wide tile layout" WTL [T][NT][NCH][3][P][128][16 bytes]: thread (row, 16-unit group g) of
+// task k owns P 16-byte pieces (gates / d(gates): 64 fp16 = 8 pieces, in TMEM column order q*16 + gate*4 + u%4, q = u/4;
+// h: 16 fp16 = 2 pieces; c, dh: 16 fp32 = 4 pieces), and the 32 lanes of a warp touch 512 CONSECUTIVE bytes per piece.
+// (First version: [..][128][E], each thread's vector contiguous -- every 16-byte load of a warp hit 32 different cache lines:
+// 30 us per step, long-scoreboard stall 15 per issue, tensor pipe 8 % busy.)  ops.py converts to / from row-major for the GEMMs.
 #include "na_tc_common.cuh"
 
 namespace na {
@@ -26,10 +28,14 @@ namespace tc {
 
 constexpr int kWtThreads = 14 * 32;
 constexpr int kWtMmaWarp = 12, kWtTmaWarp = 13;
-constexpr int kWtStages = 20;          // 120 KB in flight: the ring must cover the L2 round trip (6 stages: 24 us per step, latency-bound)
+// The weight ring moves GROUPS of K16 slices: one TMA bulk copy and one tcgen05.commit per group.  A commit after every
+// MMA (first version: 6 KB stages) serialises the tensor pipe -- 0.56 us per slice, 27 us per step, however deep the ring;
+// with half a task per group a step issues 8 commits instead of 48.
+constexpr int kWtRingBytes = 108 * 1024;
 
-__device__ __forceinline__ int64_t wtl_off(int t, int ntiles, int tile, int nch, int k, int g, int row, int E) {
-    return ((((((int64_t)t * ntiles + tile) * nch + k) * 3 + g) * kRows) + row) * E;
+// element offset of piece `piece` (of `np` pieces of `epp` elements = 16 bytes) of thread (row, g) of task k
+__device__ __forceinline__ int64_t wtl_off(int t, int ntiles, int tile, int nch, int k, int g, int np, int piece, int row, int epp) {
+    return (((((((int64_t)t * ntiles + tile) * nch + k) * 3 + g) * np + piece) * kRows) + row) * epp;
 }
 
 __device__ __forceinline__ void wt_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -49,9 +55,13 @@ template <int NCH>
 struct WfSmem {
     static constexpr int kKC = 6 * NCH;                  // 8-unit K chunks of h
     static constexpr int kSlice = 2 * kN * 16;           // one K16 slice of a task's B operand: [2][192 rows][8] fp16
+    static constexpr int kKS = 3 * NCH;                  // K16 slices per task (K = H)
+    static constexpr int kGroup = (kKS % 2 == 0) ? kKS / 2 : kKS;       // slices per ring stage
+    static constexpr int kStageBytes = kGroup * kSlice;
+    static constexpr int kStages = kWtRingBytes / kStageBytes;
     alignas(128) unsigned char h[2][kKC * kAChunk];
-    alignas(128) unsigned char ring[kWtStages][kSlice];
-    alignas(8) uint64_t ring_full[kWtStages], ring_empty[kWtStages];
+    alignas(128) unsigned char ring[kStages][kStageBytes];
+    alignas(8) uint64_t ring_full[kStages], ring_empty[kStages];
     uint64_t d_full[2], d_empty[2], h_ready;
     uint32_t tmem_base;
 };
@@ -65,14 +75,14 @@ lstm_wide_fwd_kernel(const __half* __restrict__ gx,                // WTL E=64: 
                      float* __restrict__ c_out,                    // WTL E=16
                      int T, int ntiles) {
     using SM = WfSmem<NCH>;
-    constexpr int kH = 48 * NCH, kKS = kH / 16;                     // hidden size, K16 slices per task
+    constexpr int kKS = SM::kKS, kGroup = SM::kGroup, kStages = SM::kStages, kGroupsPerStep = NCH * kKS / kGroup;
     constexpr uint32_t kIdesc = make_idesc(kN, kFmtVal, kFmtVal);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SM& S = *reinterpret_cast<SM*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) {
-        for (int s = 0; s < kWtStages; ++s) { mbar_init(&S.ring_full[s], 1); mbar_init(&S.ring_empty[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&S.ring_full[s], 1); mbar_init(&S.ring_empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&S.d_full[b], 1); mbar_init(&S.d_empty[b], 12 * 32); }
         mbar_init(&S.h_ready, 12 * 32 * NCH);
         fence_mbar_init();
@@ -96,11 +106,11 @@ lstm_wide_fwd_kernel(const __half* __restrict__ gx,                // WTL E=64: 
         if (warp == kWtTmaWarp) {
             if (lane == 0)
                 for (int t = 0; t < T; ++t)
-                    for (int i = 0; i < NCH * kKS; ++i, ++sc) {
-                        const uint32_t s = sc % kWtStages, u = sc / kWtStages;
+                    for (int i = 0; i < kGroupsPerStep; ++i, ++sc) {
+                        const uint32_t s = sc % kStages, u = sc / kStages;
                         mbar_wait(&S.ring_empty[s], (u & 1) ^ 1);
-                        mbar_arrive_expect_tx(&S.ring_full[s], SM::kSlice);
-                        bulk_load(S.ring[s], wimg + (size_t)i * SM::kSlice, SM::kSlice, &S.ring_full[s]);
+                        mbar_arrive_expect_tx(&S.ring_full[s], SM::kStageBytes);
+                        bulk_load(S.ring[s], wimg + (size_t)i * SM::kStageBytes, SM::kStageBytes, &S.ring_full[s]);
                     }
         } else if (warp == kWtMmaWarp) {
             const bool leader = elect_one();
@@ -112,15 +122,17 @@ lstm_wide_fwd_kernel(const __half* __restrict__ gx,                // WTL E=64: 
                     const uint32_t b = cnt & 1;
                     mbar_wait(&S.d_empty[b], ((cnt >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    for (int ks = 0; ks < kKS; ++ks, ++sc) {
-                        const uint32_t s = sc % kWtStages, u = sc / kWtStages;
+                    for (int gr = 0; gr < kKS / kGroup; ++gr, ++sc) {
+                        const uint32_t s = sc % kStages, u = sc / kStages;
                         mbar_wait(&S.ring_full[s], u & 1);
                         tc_fence_after();
-                        if (leader) {
-                            umma_bf16_i(tmem + b * kN, desc_adv(hp, 2 * ks * kAChunk), umma_desc(smem_u32(S.ring[s]), kBChunk, 128), kIdesc,
-                                        ks == 0 ? 0u : 1u);
-                            umma_commit(&S.ring_empty[s]);
+                        const uint64_t d_w = umma_desc(smem_u32(S.ring[s]), kBChunk, 128);
+#pragma unroll
+                        for (int j = 0; j < kGroup; ++j) {
+                            const int ks = gr * kGroup + j;
+                            if (leader) umma_bf16_i(tmem + b * kN, desc_adv(hp, 2 * ks * kAChunk), desc_adv(d_w, j * SM::kSlice), kIdesc, ks == 0 ? 0u : 1u);
                         }
+                        if (leader) umma_commit(&S.ring_empty[s]);
                     }
                     if (leader) umma_commit(&S.d_full[b]);
                 }
@@ -133,17 +145,16 @@ lstm_wide_fwd_kernel(const __half* __restrict__ gx,                // WTL E=64: 
             for (int t = 0; t < T; ++t) {
                 for (int k = 0; k < NCH; ++k, ++cnt) {
                     const uint32_t b = cnt & 1;
-                    const __half* gxp = gx + wtl_off(t, ntiles, tile, NCH, k, g, row, 64);
                     float cprev[16];
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (t > 0) c4 = *reinterpret_cast<const float4*>(c_out + wtl_off(t - 1, ntiles, tile, NCH, k, g, row, 16) + j);
+                        if (t > 0) c4 = *reinterpret_cast<const float4*>(c_out + wtl_off(t - 1, ntiles, tile, NCH, k, g, 4, j / 4, row, 4));
                         cprev[j] = c4.x; cprev[j + 1] = c4.y; cprev[j + 2] = c4.z; cprev[j + 3] = c4.w;
                     }
                     uint4 gxv[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) gxv[i] = *reinterpret_cast<const uint4*>(gxp + 8 * i);
+                    for (int i = 0; i < 8; ++i) gxv[i] = *reinterpret_cast<const uint4*>(gx + wtl_off(t, ntiles, tile, NCH, k, g, 8, i, row, 8));
                     mbar_wait(&S.d_full[b], (cnt >> 1) & 1);
                     tc_fence_after();
                     float cn[16], hn[16];
@@ -175,21 +186,21 @@ lstm_wide_fwd_kernel(const __half* __restrict__ gx,                // WTL E=64: 
 #pragma unroll
                             for (int e = 0; e < 8; ++e) act[gi * 8 + e] = pack_val(a[2 * e], a[2 * e + 1]);
                         }
-                        __half* go_ = gates_out + wtl_off(t, ntiles, tile, NCH, k, g, row, 64) + pr * 32;
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            *reinterpret_cast<uint4*>(go_ + 8 * i) = make_uint4(act[4 * i], act[4 * i + 1], act[4 * i + 2], act[4 * i + 3]);
+                            *reinterpret_cast<uint4*>(gates_out + wtl_off(t, ntiles, tile, NCH, k, g, 8, pr * 4 + i, row, 8)) =
+                                make_uint4(act[4 * i], act[4 * i + 1], act[4 * i + 2], act[4 * i + 3]);
                         // h of these 8 units: HBM (WTL) + the operand buffer of step t + 1 (K chunk 6 k + 2 g + pr)
                         const uint32_t p0 = pack_val(hn[pr * 8], hn[pr * 8 + 1]), p1 = pack_val(hn[pr * 8 + 2], hn[pr * 8 + 3]);
                         const uint32_t p2 = pack_val(hn[pr * 8 + 4], hn[pr * 8 + 5]), p3 = pack_val(hn[pr * 8 + 6], hn[pr * 8 + 7]);
                         st_shared_v4(S.h[t & 1] + (6 * k + 2 * g + pr) * kAChunk + row * 16, p0, p1, p2, p3);
-                        *reinterpret_cast<uint4*>(h_out + wtl_off(t, ntiles, tile, NCH, k, g, row, 16) + pr * 8) = make_uint4(p0, p1, p2, p3);
+                        *reinterpret_cast<uint4*>(h_out + wtl_off(t, ntiles, tile, NCH, k, g, 2, pr, row, 8)) = make_uint4(p0, p1, p2, p3);
                     }
                     tc_fence_before();
                     mbar_arrive(&S.d_empty[b]);
-                    float* co = c_out + wtl_off(t, ntiles, tile, NCH, k, g, row, 16);
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(co + j) = make_float4(cn[j], cn[j + 1], cn[j + 2], cn[j + 3]);
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(c_out + wtl_off(t, ntiles, tile, NCH, k, g, 4, j / 4, row, 4)) = make_float4(cn[j], cn[j + 1], cn[j + 2], cn[j + 3]);
                     fence_proxy_async_smem();
                     mbar_arrive(&S.h_ready);
                 }
@@ -208,9 +219,12 @@ lstm_wide_fwd_kernel(const __half* __restrict__ gx,                // WTL E=64: 
 template <int NCH>
 struct WbSmem {
     static constexpr int kSlice = 2 * 48 * NCH * 16;     // one K16 slice of W_hh^T for a task: [2][H rows][8] fp16
+    static constexpr int kGroup = 6;                     // slices per ring stage (12 per task: K = 192 gate columns)
+    static constexpr int kStageBytes = kGroup * kSlice;
+    static constexpr int kStages = kWtRingBytes / kStageBytes;
     alignas(128) unsigned char dg[2][24 * kAChunk];      // d(gates) of one task (192 columns), double-buffered
-    alignas(128) unsigned char ring[kWtStages][kSlice];
-    alignas(8) uint64_t ring_full[kWtStages], ring_empty[kWtStages];
+    alignas(128) unsigned char ring[kStages][kStageBytes];
+    alignas(8) uint64_t ring_full[kStages], ring_empty[kStages];
     uint64_t dg_ready[2], dg_free[2], r_full;
     uint32_t tmem_base;
 };
@@ -225,14 +239,14 @@ lstm_wide_bwd_kernel(const __half* __restrict__ gates,             // WTL E=64 (
                      float* __restrict__ dc_ws,                    // [grid][NCH][3][128][16] running d(cell)
                      int T, int ntiles) {
     using SM = WbSmem<NCH>;
-    constexpr int kH = 48 * NCH;
+    constexpr int kH = 48 * NCH, kGroup = SM::kGroup, kStages = SM::kStages;
     constexpr uint32_t kIdescR = make_idesc(kH, kFmtVal, kFmtVal);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SM& S = *reinterpret_cast<SM*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) {
-        for (int s = 0; s < kWtStages; ++s) { mbar_init(&S.ring_full[s], 1); mbar_init(&S.ring_empty[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&S.ring_full[s], 1); mbar_init(&S.ring_empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&S.dg_ready[b], 12 * 32); mbar_init(&S.dg_free[b], 1); }
         mbar_init(&S.r_full, 1);
         fence_mbar_init();
@@ -248,11 +262,11 @@ lstm_wide_bwd_kernel(const __half* __restrict__ gates,             // WTL E=64 (
         if (warp == kWtTmaWarp) {
             if (lane == 0)
                 for (int i = 0; i < T; ++i)
-                    for (int j = 0; j < NCH * 12; ++j, ++sc) {
-                        const uint32_t s = sc % kWtStages, u = sc / kWtStages;
+                    for (int j = 0; j < NCH * 12 / kGroup; ++j, ++sc) {
+                        const uint32_t s = sc % kStages, u = sc / kStages;
                         mbar_wait(&S.ring_empty[s], (u & 1) ^ 1);
-                        mbar_arrive_expect_tx(&S.ring_full[s], SM::kSlice);
-                        bulk_load(S.ring[s], wimg + (size_t)j * SM::kSlice, SM::kSlice, &S.ring_full[s]);
+                        mbar_arrive_expect_tx(&S.ring_full[s], SM::kStageBytes);
+                        bulk_load(S.ring[s], wimg + (size_t)j * SM::kStageBytes, SM::kStageBytes, &S.ring_full[s]);
                     }
         } else if (warp == kWtMmaWarp) {
             const bool leader = elect_one();
@@ -263,15 +277,18 @@ lstm_wide_bwd_kernel(const __half* __restrict__ gates,             // WTL E=64 (
                     const uint32_t b = cnt & 1;
                     mbar_wait(&S.dg_ready[b], (cnt >> 1) & 1);
                     tc_fence_after();
-                    for (int ks = 0; ks < 12; ++ks, ++sc) {
-                        const uint32_t s = sc % kWtStages, u = sc / kWtStages;
+                    for (int gr = 0; gr < 12 / kGroup; ++gr, ++sc) {
+                        const uint32_t s = sc % kStages, u = sc / kStages;
                         mbar_wait(&S.ring_full[s], u & 1);
                         tc_fence_after();
-                        if (leader) {
-                            umma_bf16_i(tr, desc_adv(d_dg[b], 2 * ks * kAChunk), umma_desc(smem_u32(S.ring[s]), kH * 16, 128), kIdescR,
-                                        (k == 0 && ks == 0) ? 0u : 1u);
-                            umma_commit(&S.ring_empty[s]);
+                        const uint64_t d_w = umma_desc(smem_u32(S.ring[s]), kH * 16, 128);
+#pragma unroll
+                        for (int j = 0; j < kGroup; ++j) {
+                            const int ks = gr * kGroup + j;
+                            if (leader) umma_bf16_i(tr, desc_adv(d_dg[b], 2 * ks * kAChunk), desc_adv(d_w, j * SM::kSlice), kIdescR,
+                                                    (k == 0 && ks == 0) ? 0u : 1u);
                         }
+                        if (leader) umma_commit(&S.ring_empty[s]);
                     }
                     if (leader) umma_commit(&S.dg_free[b]);
                 }
@@ -281,29 +298,28 @@ lstm_wide_bwd_kernel(const __half* __restrict__ gates,             // WTL E=64 (
             const int q = warp & 3, g = warp >> 2;
             const int row = q * 32 + lane;
             const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-            float* dcw = dc_ws + (((size_t)blockIdx.x * NCH * 3) * kRows) * 16;
+            float* dcw = dc_ws + (((size_t)blockIdx.x * NCH * 3) * kRows) * 16;      // [k][g][4 pieces][128][4]
             for (int i = 0; i < T; ++i) {
                 const int t = T - 1 - i;
                 for (int k = 0; k < NCH; ++k, ++cnt) {
                     const uint32_t b = cnt & 1;
-                    float* dcp = dcw + (((size_t)k * 3 + g) * kRows + row) * 16;
+                    float* dcp = dcw + (((size_t)k * 3 + g) * 4 * kRows + row) * 4;     // piece p at dcp + p * 128 * 4
                     // ---- loads that do not depend on the tensor pipe -------------------------------------------------
-                    uint4 gv[8];
-                    const __half* gp = gates + wtl_off(t, ntiles, tile, NCH, k, g, row, 64);
+                    uint4 gv[8];      // (fetching these one task ahead, as the forward does with gx, costs 230 B of spills here and is slower)
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) gv[e] = *reinterpret_cast<const uint4*>(gp + 8 * e);
+                    for (int e = 0; e < 8; ++e) gv[e] = *reinterpret_cast<const uint4*>(gates + wtl_off(t, ntiles, tile, NCH, k, g, 8, e, row, 8));
                     float ct[16], cp[16], dh[16], dc[16];
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
-                        const float4 a = *reinterpret_cast<const float4*>(cstate + wtl_off(t, ntiles, tile, NCH, k, g, row, 16) + j);
+                        const float4 a = *reinterpret_cast<const float4*>(cstate + wtl_off(t, ntiles, tile, NCH, k, g, 4, j / 4, row, 4));
                         ct[j] = a.x; ct[j + 1] = a.y; ct[j + 2] = a.z; ct[j + 3] = a.w;
                         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (t > 0) p = *reinterpret_cast<const float4*>(cstate + wtl_off(t - 1, ntiles, tile, NCH, k, g, row, 16) + j);
+                        if (t > 0) p = *reinterpret_cast<const float4*>(cstate + wtl_off(t - 1, ntiles, tile, NCH, k, g, 4, j / 4, row, 4));
                         cp[j] = p.x; cp[j + 1] = p.y; cp[j + 2] = p.z; cp[j + 3] = p.w;
-                        const float4 d = *reinterpret_cast<const float4*>(dh_in + wtl_off(t, ntiles, tile, NCH, k, g, row, 16) + j);
+                        const float4 d = *reinterpret_cast<const float4*>(dh_in + wtl_off(t, ntiles, tile, NCH, k, g, 4, j / 4, row, 4));
                         dh[j] = d.x; dh[j + 1] = d.y; dh[j + 2] = d.z; dh[j + 3] = d.w;
                         float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (i > 0) c4 = *reinterpret_cast<const float4*>(dcp + j);
+                        if (i > 0) c4 = *reinterpret_cast<const float4*>(dcp + (j / 4) * kRows * 4);
                         dc[j] = c4.x; dc[j + 1] = c4.y; dc[j + 2] = c4.z; dc[j + 3] = c4.w;
                     }
                     // ---- dh_rec of this step = D_R of the previous iteration (complete when its last task has committed) ----
@@ -338,10 +354,12 @@ lstm_wide_bwd_kernel(const __half* __restrict__ gates,             // WTL E=64 (
                         for (int e = 0; e < 8; ++e) out[qq * 8 + e] = pack_val(pg_[2 * e], pg_[2 * e + 1]);
                     }
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dcp + j) = make_float4(dc[j], dc[j + 1], dc[j + 2], dc[j + 3]);
-                    __half* dgo = dg_out + wtl_off(t, ntiles, tile, NCH, k, g, row, 64);
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(dcp + (j / 4) * kRows * 4) = make_float4(dc[j], dc[j + 1], dc[j + 2], dc[j + 3]);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) *reinterpret_cast<uint4*>(dgo + 8 * e) = make_uint4(out[4 * e], out[4 * e + 1], out[4 * e + 2], out[4 * e + 3]);
+                    for (int e = 0; e < 8; ++e)
+                        *reinterpret_cast<uint4*>(dg_out + wtl_off(t, ntiles, tile, NCH, k, g, 8, e, row, 8)) =
+                            make_uint4(out[4 * e], out[4 * e + 1], out[4 * e + 2], out[4 * e + 3]);
                     // A operand of R: columns n = (4 g + qq) * 16 + e -> K chunks (4 g + qq) * 2 and + 1 of the task's 24
                     mbar_wait(&S.dg_free[b], ((cnt >> 1) & 1) ^ 1);     // the MMAs that read this buffer two tasks ago are done
 #pragma unroll

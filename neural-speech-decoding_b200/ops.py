@@ -1062,28 +1062,27 @@ def decoder_train_forward_x3(x: Tensor, lstm_params, head_params, p: float, zsco
 # ------------------------------------------------------------------------------------------
 # wide decoders (H = 96 / 144 / 192): training on the tensor cores, 16-bit tier (csrc/na_wide_train.cu)
 # ------------------------------------------------------------------------------------------
-def _wtl_perm(H: int, device):
-    """Index tensors between torch's gate-major row layout (gate * H + unit) and the WTL element order."""
-    nch = H // 48
-    k, g, q, gate, ur = torch.meshgrid(torch.arange(nch), torch.arange(3), torch.arange(4), torch.arange(4), torch.arange(4), indexing="ij")
-    unit = 48 * k + 16 * g + 4 * q + ur
-    return (gate * H + unit).reshape(-1).to(device)             # WTL position (k, g, q*16 + gate*4 + ur) -> torch column
+def _to_wtl(x2d: Tensor, T: int, Bp: int, H: int) -> Tensor:
+    """row-major [T*Bp, F] -> WTL [T, NT, H/48 * 3, P, 128, 16 bytes]: thread = (row, 16-unit group g of task k) owns P
+    16-byte pieces, the lanes of a warp are contiguous within a piece.  F = 4H (gates, torch order gate * H + unit ->
+    accumulator column order (u/4)*16 + gate*4 + u%4 within the group) or F = H (h, c, dh: unit order).  One transpose copy."""
+    nt, nch = Bp // TC_TILE, H // 48
+    if x2d.shape[1] == 4 * H:
+        v = x2d.view(T, nt, TC_TILE, 2, 2, nch, 3, 4, 4)                  # t, tile, row, gate/2, gate%2, k, g, q, ur
+        return v.permute(0, 1, 5, 6, 7, 3, 2, 4, 8).reshape(T, nt, nch * 3, 8, TC_TILE, 8).contiguous()
+    epp = 16 // x2d.element_size()                                       # elements per 16-byte piece
+    v = x2d.view(T, nt, TC_TILE, nch, 3, 16 // epp, epp)                  # t, tile, row, k, g, piece, e
+    return v.permute(0, 1, 3, 4, 5, 2, 6).reshape(T, nt, nch * 3, 16 // epp, TC_TILE, epp).contiguous()   # (reshape alone may return a view)
 
 
-def _to_wtl(x2d: Tensor, T: int, Bp: int, cols: Tensor, E: int) -> Tensor:
-    """row-major [T*Bp, F] -> WTL [T, NT, nch, 3, 128, E] (gather of the columns, then the tile transpose)."""
-    nt = Bp // TC_TILE
-    nch3 = cols.numel() // E
-    return x2d.index_select(1, cols).reshape(T, nt, TC_TILE, nch3, E).permute(0, 1, 3, 2, 4).contiguous()
-
-
-def _from_wtl(w: Tensor, T: int, Bp: int, cols: Tensor, F: int) -> Tensor:
-    """WTL -> row-major [T*Bp, F] in torch column order."""
-    nt = Bp // TC_TILE
-    flat = w.reshape(T, nt, -1, TC_TILE, w.shape[-1]).permute(0, 1, 3, 2, 4).reshape(T * Bp, -1)
-    out = torch.empty((T * Bp, F), dtype=w.dtype, device=w.device)
-    out[:, cols] = flat
-    return out
+def _from_wtl(w: Tensor, T: int, Bp: int, H: int) -> Tensor:
+    """WTL -> row-major [T*Bp, F] (the inverse of _to_wtl)."""
+    nt, nch = Bp // TC_TILE, H // 48
+    if w.shape[3] == 8 and w.dtype == torch.float16 and w.shape[5] == 8:  # gates / d(gates)
+        v = w.view(T, nt, nch, 3, 4, 2, TC_TILE, 2, 4)                    # t, tile, k, g, q, gate/2, row, gate%2, ur
+        return v.permute(0, 1, 6, 5, 7, 2, 3, 4, 8).reshape(T * Bp, 4 * H).contiguous()
+    v = w.view(T, nt, nch, 3, w.shape[3], TC_TILE, w.shape[5])           # t, tile, k, g, piece, row, e
+    return v.permute(0, 1, 5, 2, 3, 4, 6).reshape(T * Bp, H).contiguous()
 
 
 def _wide_images(w_hh: Tensor, H: int):
@@ -1102,13 +1101,13 @@ def _wide_images(w_hh: Tensor, H: int):
 @torch.library.custom_op("neuroalpha::lstm_wide_fwd_train", mutates_args=(), device_types="cuda")
 @_device_guard
 def lstm_wide_fwd_train(gx: Tensor, w_image: Tensor, H: int) -> Tuple[Tensor, Tensor, Tensor]:
-    """Serial part of one wide layer's training forward.  gx: WTL fp16 [T, NT, H/48, 3, 128, 64] -> (gates WTL, h WTL fp16
-    [.., 16], c WTL fp32 [.., 16])."""
+    """Serial part of one wide layer's training forward.  gx: WTL fp16 [T, NT, H/48 * 3, 8, 128, 8] -> (gates WTL, h WTL fp16
+    [.., 2, 128, 8], c WTL fp32 [.., 4, 128, 4])."""
     _require_cuda(gx, w_image)
     T, NT = gx.shape[0], gx.shape[1]
-    gates = torch.empty_like(gx)
-    h = torch.empty(gx.shape[:-1] + (16,), dtype=torch.float16, device=gx.device)
-    c = torch.empty(gx.shape[:-1] + (16,), dtype=torch.float32, device=gx.device)
+    gates = torch.empty_like(gx)                                        # [T, NT, nch * 3, 8, 128, 8]
+    h = torch.empty(gx.shape[:3] + (2, TC_TILE, 8), dtype=torch.float16, device=gx.device)
+    c = torch.empty(gx.shape[:3] + (4, TC_TILE, 4), dtype=torch.float32, device=gx.device)
     _lib.call("na_lstm_wide_fwd_train", gx.data_ptr(), w_image.data_ptr(), gates.data_ptr(), h.data_ptr(), c.data_ptr(), T, NT * TC_TILE,
               int(H), _stream())
     return gates, h, c
@@ -1116,7 +1115,8 @@ def lstm_wide_fwd_train(gx: Tensor, w_image: Tensor, H: int) -> Tuple[Tensor, Te
 
 @lstm_wide_fwd_train.register_fake
 def _(gx, w_image, H):
-    return gx.new_empty(gx.shape), gx.new_empty(gx.shape[:-1] + (16,)), gx.new_empty(gx.shape[:-1] + (16,), dtype=torch.float32)
+    return (gx.new_empty(gx.shape), gx.new_empty(gx.shape[:3] + (2, TC_TILE, 8)),
+            gx.new_empty(gx.shape[:3] + (4, TC_TILE, 4), dtype=torch.float32))
 
 
 @torch.library.custom_op("neuroalpha::lstm_wide_bwd", mutates_args=(), device_types="cuda")
@@ -1166,8 +1166,6 @@ class DecoderFunctionWideTC(torch.autograd.Function):
         scale = 1.0 / (1.0 - p) if p < 1.0 else 0.0
         Bp = padded_batch(B, TC_TILE)
         dev = x.device
-        cols64, cols16 = _wtl_perm(H, dev), None
-        unit_cols = torch.arange(H, device=dev)                                  # WTL h / c / dh order == unit order (k, g, u)
         xin = x.detach().float()
         if zscore:
             xin = window_zscore(xin, T, T, True, False, NA_F32)
@@ -1183,9 +1181,9 @@ class DecoderFunctionWideTC(torch.autograd.Function):
                 gx2d = torch.addmm((b_ih + b_hh).float(), layer_in, w_ih.float().t()).to(torch.float16)
             else:
                 gx2d = torch.addmm((b_ih + b_hh).to(torch.float16), layer_in, w_ih.to(torch.float16).t())
-            gates, h, c = lstm_wide_fwd_train(_to_wtl(gx2d, T, Bp, cols64, 64), fimg, H)
+            gates, h, c = lstm_wide_fwd_train(_to_wtl(gx2d, T, Bp, H), fimg, H)
             del gx2d
-            h2d = _from_wtl(h, T, Bp, unit_cols, H)                              # [T*Bp, H] fp16, unit order
+            h2d = _from_wtl(h, T, Bp, H)                                         # [T*Bp, H] fp16, unit order
             saved += [gates, c, bimg, layer_in if l == 0 else None]
             h_rows.append(h2d)
             if l == 0:
@@ -1214,7 +1212,6 @@ class DecoderFunctionWideTC(torch.autograd.Function):
         d2 = rest.pop(0) if has_d2 else None
         dev = dlogits.device
         NC = dlogits.shape[1]
-        cols64, unit_cols = _wtl_perm(H, dev), torch.arange(H, device=dev)
         h1 = h1_2d.float().reshape(T, Bp, H)
         dh1, dparams = head_bwd(dlogits.contiguous(), h1, stats, zpool, head, rr, d2, scale)
         del h1
@@ -1224,8 +1221,8 @@ class DecoderFunctionWideTC(torch.autograd.Function):
         inv_s = 1.0 / s
         zeros_h = torch.zeros((Bp, H), dtype=torch.float16, device=dev)
         def layer_bwd(gates, c, bimg, dh2d, in2d, h2d, w_ih):
-            dg = lstm_wide_bwd(gates, c, _to_wtl(dh2d, T, Bp, unit_cols, 16), bimg, H)
-            dg2d = _from_wtl(dg, T, Bp, cols64, 4 * H)                            # [T*Bp, 4H] fp16, torch gate order
+            dg = lstm_wide_bwd(gates, c, _to_wtl(dh2d, T, Bp, H), bimg, H)
+            dg2d = _from_wtl(dg, T, Bp, H)                                       # [T*Bp, 4H] fp16, torch gate order
             del dg
             dgt = dg2d.t()
             in16 = in2d if in2d.dtype == torch.float16 else in2d.to(torch.float16)
