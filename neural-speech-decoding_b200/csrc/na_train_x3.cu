@@ -352,7 +352,7 @@ struct TxBwdSmem {
     alignas(128) unsigned char dg[48 * kAChunk];                     // d(gates): hi x24 | lo x24
     alignas(128) unsigned char onez[2 * kAChunk];
     alignas(8) uint64_t act_full, act_free;
-    uint64_t g_full, dg_ready;
+    uint64_t g_full, r_full, dg_ready;
     uint32_t tmem_base;
     float wa[kH];
     float ba;
@@ -419,7 +419,7 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
         }
         if (tid == 0) {
             mbar_init(&S.act_full, 1); mbar_init(&S.act_free, 1);
-            mbar_init(&S.g_full, 1);
+            mbar_init(&S.g_full, 1); mbar_init(&S.r_full, 1);
             mbar_init(&S.dg_ready, 12 * 32);
             fence_mbar_init();
         }
@@ -435,12 +435,13 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
     }
     const bool head = LAYER == 1 && dz != nullptr;
     const uint32_t tmem = __shfl_sync(0xffffffffu, S.tmem_base, 0);
-    const uint32_t tm_g = tmem, tm_r = tmem + kN;
+    // two gate accumulators (the recompute of step t-1 runs under the epilogue of step t) + D_R: 2 x 192 + 96 = 480 columns
+    const uint32_t tm_r = tmem + 2 * kN;
     float dwa[16], dba = 0.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) dwa[j] = 0.f;
 
-    uint32_t act_cnt = 0, dgp = 0, gphase = 0;       // role-private running phase counters
+    uint32_t act_cnt = 0, dgp = 0, gphase = 0, rphase = 0;       // role-private running phase counters
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t b0 = (int64_t)tile * kRows;
         if (warp == kTxTmaWarp) {
@@ -466,6 +467,43 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
             const uint64_t d_bias = umma_desc(a_ones, kAChunk, 128);
             // first weight chunk of the R operand: L0: W_hh (chunks 2..7 hi, 9..14 lo);  L1: [W_ih | W_hh] (0..11 hi, 13..24 lo)
             constexpr int kRHi = LAYER == 0 ? 2 : 0, kRLo = LAYER == 0 ? 9 : 13;
+            // gate recompute of step `t` into accumulator `buf`
+            auto issue_g = [&](const uint32_t tm_g) {
+                mbar_wait(&S.act_full, act_cnt & 1); ++act_cnt;
+                tc_fence_after();
+                if (LAYER == 0) {
+                    if (leader) {
+                        umma_bf16_i(tm_g, umma_desc(a_act, a_ones - a_act, 128), d_b, kIdescG, 0u);
+                        umma_bf16_i(tm_g, umma_desc(a_act, a_zero - a_act, 128), desc_adv(d_b, 8 * kBChunk), kIdescG, 1u);
+                        umma_bf16_i(tm_g, umma_desc(a_act + kAChunk, a_zero - (a_act + kAChunk), 128), d_b, kIdescG, 1u);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (leader) {
+                            umma_bf16_i(tm_g, desc_adv(d_hp, 2 * k * kAChunk), desc_adv(d_b, (2 + 2 * k) * kBChunk), kIdescG, 1u);
+                            umma_bf16_i(tm_g, desc_adv(d_hp, 2 * k * kAChunk), desc_adv(d_b, (9 + 2 * k) * kBChunk), kIdescG, 1u);
+                            umma_bf16_i(tm_g, desc_adv(d_hp, (6 + 2 * k) * kAChunk), desc_adv(d_b, (2 + 2 * k) * kBChunk), kIdescG, 1u);
+                        }
+                } else {
+                    if (leader) umma_bf16_i(tm_g, d_bias, desc_adv(d_b, 12 * kBChunk), kIdescG, 0u);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (leader) {
+                            umma_bf16_i(tm_g, desc_adv(d_in, 2 * k * kAChunk), desc_adv(d_b, 2 * k * kBChunk), kIdescG, 1u);
+                            umma_bf16_i(tm_g, desc_adv(d_in, 2 * k * kAChunk), desc_adv(d_b, (13 + 2 * k) * kBChunk), kIdescG, 1u);
+                            umma_bf16_i(tm_g, desc_adv(d_in, (6 + 2 * k) * kAChunk), desc_adv(d_b, 2 * k * kBChunk), kIdescG, 1u);
+                            umma_bf16_i(tm_g, desc_adv(d_hp, 2 * k * kAChunk), desc_adv(d_b, (6 + 2 * k) * kBChunk), kIdescG, 1u);
+                            umma_bf16_i(tm_g, desc_adv(d_hp, 2 * k * kAChunk), desc_adv(d_b, (19 + 2 * k) * kBChunk), kIdescG, 1u);
+                            umma_bf16_i(tm_g, desc_adv(d_hp, (6 + 2 * k) * kAChunk), desc_adv(d_b, (6 + 2 * k) * kBChunk), kIdescG, 1u);
+                        }
+                }
+                if (leader) umma_commit(&S.act_free);          // the stage may be refilled as soon as G has read it
+                if (leader) umma_commit(&S.g_full);
+            };
+            // Per iteration i (step t = T-1-i): R(t+1) first -- it is the only MMA on the step's critical path (d(gates) ->
+            // dh_rec -> d(gates)) --, then the gate recompute of the NEXT step into the other accumulator, where it runs
+            // under this step's epilogue.
+            issue_g(tmem);                                          // G(T-1)
             for (int i = 0; i <= T; ++i) {
                 if (i >= 1) {
                     mbar_wait(&S.dg_ready, dgp & 1); ++dgp;
@@ -479,38 +517,8 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
                             umma_bf16_i(tm_r, alo, desc_adv(d_bm, kRHi * kBChunk + ks * 256), kIdescR, 1u);
                         }
                 }
-                if (i < T) {
-                    mbar_wait(&S.act_full, act_cnt & 1); ++act_cnt;
-                    tc_fence_after();
-                    if (LAYER == 0) {
-                        if (leader) {
-                            umma_bf16_i(tm_g, umma_desc(a_act, a_ones - a_act, 128), d_b, kIdescG, 0u);
-                            umma_bf16_i(tm_g, umma_desc(a_act, a_zero - a_act, 128), desc_adv(d_b, 8 * kBChunk), kIdescG, 1u);
-                            umma_bf16_i(tm_g, umma_desc(a_act + kAChunk, a_zero - (a_act + kAChunk), 128), d_b, kIdescG, 1u);
-                        }
-#pragma unroll
-                        for (int k = 0; k < 3; ++k)
-                            if (leader) {
-                                umma_bf16_i(tm_g, desc_adv(d_hp, 2 * k * kAChunk), desc_adv(d_b, (2 + 2 * k) * kBChunk), kIdescG, 1u);
-                                umma_bf16_i(tm_g, desc_adv(d_hp, 2 * k * kAChunk), desc_adv(d_b, (9 + 2 * k) * kBChunk), kIdescG, 1u);
-                                umma_bf16_i(tm_g, desc_adv(d_hp, (6 + 2 * k) * kAChunk), desc_adv(d_b, (2 + 2 * k) * kBChunk), kIdescG, 1u);
-                            }
-                    } else {
-                        if (leader) umma_bf16_i(tm_g, d_bias, desc_adv(d_b, 12 * kBChunk), kIdescG, 0u);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k)
-                            if (leader) {
-                                umma_bf16_i(tm_g, desc_adv(d_in, 2 * k * kAChunk), desc_adv(d_b, 2 * k * kBChunk), kIdescG, 1u);
-                                umma_bf16_i(tm_g, desc_adv(d_in, 2 * k * kAChunk), desc_adv(d_b, (13 + 2 * k) * kBChunk), kIdescG, 1u);
-                                umma_bf16_i(tm_g, desc_adv(d_in, (6 + 2 * k) * kAChunk), desc_adv(d_b, 2 * k * kBChunk), kIdescG, 1u);
-                                umma_bf16_i(tm_g, desc_adv(d_hp, 2 * k * kAChunk), desc_adv(d_b, (6 + 2 * k) * kBChunk), kIdescG, 1u);
-                                umma_bf16_i(tm_g, desc_adv(d_hp, 2 * k * kAChunk), desc_adv(d_b, (19 + 2 * k) * kBChunk), kIdescG, 1u);
-                                umma_bf16_i(tm_g, desc_adv(d_hp, (6 + 2 * k) * kAChunk), desc_adv(d_b, (6 + 2 * k) * kBChunk), kIdescG, 1u);
-                            }
-                    }
-                    if (leader) umma_commit(&S.act_free);      // the stage may be refilled as soon as G has read it
-                }
-                if (leader) umma_commit(&S.g_full);            // R(t+1) and G(t) done; i == T: tail (R only)
+                if (leader) umma_commit(&S.r_full);            // R(t+1) done (i == 0: nothing pending)
+                if (i + 1 < T) issue_g(tmem + ((i + 1) & 1) * kN);      // G(t-1): accumulator (i+1)&1 was drained in iteration i-1
             }
         } else {
             // ================= epilogue: thread = window row x 16 units ===========================================
@@ -587,8 +595,10 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
                         }
                     }
                 }
-                mbar_wait(&S.g_full, gphase & 1); ++gphase;
+                mbar_wait(&S.r_full, rphase & 1); ++rphase;
+                if (i < T) { mbar_wait(&S.g_full, gphase & 1); ++gphase; }
                 tc_fence_after();
+                const uint32_t tm_g = tmem + (i & 1) * kN;
                 if (i >= 1) {
                     if (LAYER == 1) {
                         // din of step t+1 = D_R[:, 0:48] (x dropout mask x scale) -> dh_in of layer 0
