@@ -157,19 +157,25 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 template <int LT>
 __device__ __forceinline__ void section_pass(double (&v)[LT], const int lane, const int dir,
                                              const double b0, const double b1, const double b2, const double na1, const double na2,
-                                             const double* __restrict__ pm,       // 5 x (a, b, c, d): A^(LT 2^j)
+                                             const double* __restrict__ pm,       // 5 x (a, b, c, d): A^(LT 2^j), then A^(LT/2)
                                              double& w1, double& w2) {
+    static_assert(LT % 2 == 0, "the lane block is processed as two half blocks");
+    constexpr int HB = LT / 2;
     const bool first = dir > 0 ? lane == 0 : lane == 31;          // the block that is processed first carries the initial state
-    // (1) end state of this lane's block from a zero state (the first block: from the true initial state).
-    //     w_t = (v_t - a2 w_{t-2}) - a1 w_{t-1}: only the outer FMA is on the dependent chain
-    double e1 = first ? w1 : 0.0, e2 = first ? w2 : 0.0;
+    const double h00 = pm[20], h01 = pm[21], h10 = pm[22], h11 = pm[23];     // A^HB
+    // (1) end state of this lane's block from a zero state (the first block: from the true initial state).  The block is
+    //     run as TWO independent half-block chains (instruction-level parallelism: the recurrence is latency-bound),
+    //     joined by A^HB.  w_t = (v_t - a2 w_{t-2}) - a1 w_{t-1}: only the outer FMA is on a dependent chain.
+    double p1 = first ? w1 : 0.0, p2 = first ? w2 : 0.0, q1 = 0.0, q2 = 0.0;
 #pragma unroll
-    for (int jj = 0; jj < LT; ++jj) {
-        const int j = dir > 0 ? jj : LT - 1 - jj;
-        const double w = fma(na1, e1, fma(na2, e2, v[j]));
-        e2 = e1;
-        e1 = w;
+    for (int jj = 0; jj < HB; ++jj) {
+        const int ja = dir > 0 ? jj : LT - 1 - jj, jb = dir > 0 ? jj + HB : HB - 1 - jj;
+        const double wa = fma(na1, p1, fma(na2, p2, v[ja]));
+        const double wb = fma(na1, q1, fma(na2, q2, v[jb]));
+        p2 = p1; p1 = wa;
+        q2 = q1; q1 = wb;
     }
+    double e1 = fma(h00, p1, fma(h01, p2, q1)), e2 = fma(h10, p1, fma(h11, p2, q2));
     // (2) scan over the blocks in processing order: S_p = A^LT S_{p-1} + e_p
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -185,20 +191,25 @@ __device__ __forceinline__ void section_pass(double (&v)[LT], const int lane, co
     const int prev = dir > 0 ? lane - 1 : lane + 1;
     double s1 = shfl_d(e1, prev & 31), s2 = shfl_d(e2, prev & 31);
     if (first) { s1 = w1; s2 = w2; }
-    // (3) the real pass: DirectFormII, w = v - a1 w1 - a2 w2; out = b0 w + b1 w1 + b2 w2
+    // incoming state of the second half block = A^HB s_in + (zero-state end of the first half); in the first block the
+    // first half already ran from the true initial state
+    double t1 = first ? p1 : fma(h00, s1, fma(h01, s2, p1)), t2 = first ? p2 : fma(h10, s1, fma(h11, s2, p2));
+    // (3) the real pass: DirectFormII, w = v - a1 w1 - a2 w2; out = b0 w + b1 w1 + b2 w2 (two half-block chains again)
 #pragma unroll
-    for (int jj = 0; jj < LT; ++jj) {
-        const int j = dir > 0 ? jj : LT - 1 - jj;
-        const double part = fma(b1, s1, b2 * s2);                  // off the dependent chain
-        const double w = fma(na1, s1, fma(na2, s2, v[j]));
-        v[j] = fma(b0, w, part);
-        s2 = s1;
-        s1 = w;
+    for (int jj = 0; jj < HB; ++jj) {
+        const int ja = dir > 0 ? jj : LT - 1 - jj, jb = dir > 0 ? jj + HB : HB - 1 - jj;
+        const double parta = fma(b1, s1, b2 * s2), partb = fma(b1, t1, b2 * t2);       // off the dependent chains
+        const double wa = fma(na1, s1, fma(na2, s2, v[ja]));
+        const double wb = fma(na1, t1, fma(na2, t2, v[jb]));
+        v[ja] = fma(b0, wa, parta);
+        v[jb] = fma(b0, wb, partb);
+        s2 = s1; s1 = wa;
+        t2 = t1; t1 = wb;
     }
-    // state after the last processed sample: ascending -> lane 31, descending -> lane 0
+    // state after the last processed sample (end of the second half): ascending -> lane 31, descending -> lane 0
     const int fin = dir > 0 ? 31 : 0;
-    w1 = shfl_d(s1, fin);
-    w2 = shfl_d(s2, fin);
+    w1 = shfl_d(t1, fin);
+    w2 = shfl_d(t2, fin);
 }
 
 // The series occupies the LAST T of the 32 LT register slots (slot p = pad + t, lane = p / LT): the pad slots in front hold
@@ -212,7 +223,7 @@ iir_chain_warp_kernel(const float* __restrict__ x, float* __restrict__ y, const 
                       const int* __restrict__ nsec, int nfilt, int64_t S, int T, int C, int detrend, int round_decimals,
                       int carry_state) {
     __shared__ double s_coef[kIirMaxF * kIirMaxS * 5];
-    __shared__ double s_pm[kIirMaxF * kIirMaxS * 20];
+    __shared__ double s_pm[kIirMaxF * kIirMaxS * 24];
     __shared__ int s_nsec[kIirMaxF];
     extern __shared__ __align__(16) float s_io[];                  // C == 8: [8 channels][32 lanes][LT + 1] staging
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -221,15 +232,18 @@ iir_chain_warp_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     for (int f = 0; f < nfilt; ++f) total += nsec[f];
     for (int i = tid; i < total * 5; i += blockDim.x) s_coef[i] = coef[i];
     if (tid < nfilt) s_nsec[tid] = nsec[tid];
-    if (tid < total) {                                             // A^(LT 2^j), j = 0..4, by repeated squaring
+    if (tid < total) {                                             // A^(LT/2), then A^(LT 2^j), j = 0..4, by repeated squaring
         const double a1 = coef[tid * 5 + 3], a2 = coef[tid * 5 + 4];
         Mat2 base{-a1, -a2, 1.0, 0.0}, acc{1.0, 0.0, 0.0, 1.0};
-        for (int e = LT; e > 0; e >>= 1) {
+        for (int e = LT / 2; e > 0; e >>= 1) {
             if (e & 1) acc = mat_mul(acc, base);
             base = mat_mul(base, base);
         }
+        double* oh = s_pm + tid * 24 + 20;
+        oh[0] = acc.a; oh[1] = acc.b; oh[2] = acc.c; oh[3] = acc.d;
+        acc = mat_mul(acc, acc);
         for (int j = 0; j < 5; ++j) {
-            double* o = s_pm + tid * 20 + 4 * j;
+            double* o = s_pm + tid * 24 + 4 * j;
             o[0] = acc.a; o[1] = acc.b; o[2] = acc.c; o[3] = acc.d;
             acc = mat_mul(acc, acc);
         }
@@ -283,7 +297,7 @@ iir_chain_warp_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         for (int k = 0; k < MAXS; ++k)
             if (k < ns) {
                 const double* cf = s_coef + (cbase + k) * 5;
-                section_pass<LT>(v, lane, +1, cf[0], cf[1], cf[2], -cf[3], -cf[4], s_pm + (cbase + k) * 20, w1[k], w2[k]);
+                section_pass<LT>(v, lane, +1, cf[0], cf[1], cf[2], -cf[3], -cf[4], s_pm + (cbase + k) * 24, w1[k], w2[k]);
             }
         if (!carry_state) {
 #pragma unroll
@@ -294,7 +308,7 @@ iir_chain_warp_kernel(const float* __restrict__ x, float* __restrict__ y, const 
         for (int k = 0; k < MAXS; ++k)
             if (k < ns) {
                 const double* cf = s_coef + (cbase + k) * 5;
-                section_pass<LT>(v, lane, -1, cf[0], cf[1], cf[2], -cf[3], -cf[4], s_pm + (cbase + k) * 20, w1[k], w2[k]);
+                section_pass<LT>(v, lane, -1, cf[0], cf[1], cf[2], -cf[3], -cf[4], s_pm + (cbase + k) * 24, w1[k], w2[k]);
             }
         cbase += ns;
         if (p0 < pad) {                                            // the descending pass rang into the pad slots: clear them
@@ -328,7 +342,7 @@ iir_chain_warp_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     }
 }
 
-static int g_iir_occ3 = 1;           // LT = 20: 3 CTAs per SM (80 registers, a few spills) instead of 2 (122 registers); A/B knob
+static int g_iir_occ3 = 2;           // LT = 20: CTAs per SM the register allocation aims at (1: 152 registers, 2: <= 128, 3: <= 80 with spills); A/B knob
 void set_iir_occ3(int v) { g_iir_occ3 = v; }
 
 template <int LT>
@@ -336,8 +350,11 @@ static int launch_iir_warp(const float* x, float* y, const double* coef, const i
                            int C, int detrend, int round_decimals, int carry_state, cudaStream_t st) {
     const size_t smem = C == kIirWarps ? (size_t)kIirWarps * 32 * (LT + 1) * sizeof(float) : 0;
     const unsigned grid = (unsigned)((S + kIirWarps - 1) / kIirWarps);
-    if (max_sections <= 4 && LT <= 20 && g_iir_occ3) {
+    if (max_sections <= 4 && LT <= 20 && g_iir_occ3 >= 3) {
         iir_chain_warp_kernel<LT <= 20 ? LT : 20, 4, 3><<<grid, kIirWarps * 32, smem, st>>>(x, y, coef, nsec, nfilt, S, T, C, detrend,
+                                                                                          round_decimals, carry_state);
+    } else if (max_sections <= 4 && LT <= 20 && g_iir_occ3 == 2) {
+        iir_chain_warp_kernel<LT <= 20 ? LT : 20, 4, 2><<<grid, kIirWarps * 32, smem, st>>>(x, y, coef, nsec, nfilt, S, T, C, detrend,
                                                                                           round_decimals, carry_state);
     } else if (max_sections <= 4) {
         auto kern = iir_chain_warp_kernel<LT, 4, 1>;

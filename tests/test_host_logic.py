@@ -141,3 +141,30 @@ def test_shard_batch_covers_everything_once():
     for n, w in ((4096, 8), (10, 3), (1, 4), (0, 2)):
         idx = [i for r in range(w) for i in range(n)[shard_batch(n, r, w)]]
         assert idx == list(range(n))
+
+
+def test_wide_tile_layout_transposes_are_inverse_and_contiguous():
+    """ops._to_wtl / _from_wtl (host side of the wide training tier): the per-thread layout the recurrence kernels read is a
+    contiguous tensor (a reshape of a permuted view may silently stay a view), the element order is the accumulator column
+    order, and the two transposes are inverses."""
+    from neural_speech_decoding_b200 import ops
+    T, Bp = 3, 256
+    for H in (96, 144, 192):
+        nch = H // 48
+        g = torch.arange(T * Bp * 4 * H, dtype=torch.float32).reshape(T * Bp, 4 * H).to(torch.float16)
+        w = ops._to_wtl(g, T, Bp, H)
+        assert w.is_contiguous() and tuple(w.shape) == (T, Bp // 128, nch * 3, 8, 128, 8)
+        for (t, tile, k, grp, p, row, e) in [(0, 0, 0, 0, 0, 0, 0), (1, 1, nch - 1, 2, 5, 77, 3), (2, 0, 1, 1, 7, 127, 7)]:
+            e64 = p * 8 + e
+            q, gate, ur = e64 // 16, (e64 % 16) // 4, e64 % 4
+            unit = 48 * k + 16 * grp + 4 * q + ur
+            assert w[t, tile, k * 3 + grp, p, row, e] == g[t * Bp + tile * 128 + row, gate * H + unit]
+        back = ops._from_wtl(w, T, Bp, H)
+        assert back.is_contiguous() and torch.equal(back, g)
+        for dt in (torch.float32, torch.float16):
+            c = torch.randn(T * Bp, H).to(dt)
+            wc = ops._to_wtl(c, T, Bp, H)
+            epp = 16 // c.element_size()
+            assert wc.is_contiguous() and tuple(wc.shape) == (T, Bp // 128, nch * 3, 16 // epp, 128, epp)
+            assert wc[1, 1, 2, 1, 9, 2] == c[Bp + 128 + 9, 48 * 0 + 16 * 2 + epp * 1 + 2]
+            assert torch.equal(ops._from_wtl(wc, T, Bp, H), c)
