@@ -323,20 +323,24 @@ int na_head_tail_bwd_f32(const float* dlogits, const float* zpool, const float* 
  *                         d attn_w (48) | d attn_b | pad; layer 0: dh_in = din of layer 1.  zeros: >= 24,576 zero bytes.
  *                         scratch: na_train_x3_scratch_floats() floats.
  *   na_lstm_wgrad_x3      time-parallel dW_ih, dW_hh, db (= both biases) from dg and the saved activations; same scratch.
+ * half_stride > 0 selects HALF TILES exactly as in na_lstm2_fwd_train_bf16 (64 windows per tile, rows 64..127 mirror rows
+ * 0..63, B <= Bp / 2, half_stride = the dropout generator's row stride); 0 = full tiles.
  */
-int na_x3_split_input(const float* x, void* xs, int64_t B, int64_t T, int64_t Bp, na_stream_t stream);
+int na_x3_split_input(const float* x, void* xs, int64_t B, int64_t T, int64_t Bp, int64_t half_stride, na_stream_t stream);
 int na_lstm_fwd_train_x3(int64_t layer, const void* in, const void* packed_x3, const float* attn_w, const float* attn_b,
                          const unsigned char* mask, uint64_t seed, int64_t thresh16, float drop_scale, void* h, void* hd,
-                         float* c, float* zpool, float* stats, int64_t B, int64_t T, int64_t Bp, na_stream_t stream);
+                         float* c, float* zpool, float* stats, int64_t B, int64_t T, int64_t Bp, int64_t half_stride,
+                         na_stream_t stream);
 int64_t na_train_x3_scratch_floats(void);
 int64_t na_train_x3_smem_bytes(int64_t which);
 int na_lstm_bwd_x3(int64_t layer, const void* act_in, const void* h, const float* cstate, const float* dh_in,
                    const void* packed_x3, const void* zeros, const unsigned char* in_mask, uint64_t seed, int64_t thresh16,
                    float drop_scale, float* din, void* dg, const float* dz, const float* stats, const float* zpool,
                    const float* attn_w, const float* attn_b, int64_t B, float* d_attn, float* scratch,
-                   int64_t T, int64_t Bp, na_stream_t stream);
+                   int64_t T, int64_t Bp, int64_t half_stride, na_stream_t stream);
 int na_lstm_wgrad_x3(int64_t layer, const void* dg, const void* act_in, const void* h, const void* zeros,
-                     float* dw_ih, float* dw_hh, float* db, float* scratch, int64_t T, int64_t Bp, na_stream_t stream);
+                     float* dw_ih, float* dw_hh, float* db, float* scratch, int64_t T, int64_t Bp, int64_t half_stride,
+                     na_stream_t stream);
 
 /* ---- wide decoders (H = 96 / 144 / 192, BASELINE configs[4]): TRAINING on the tensor cores, 16-bit tier -----------
  * Replaces torch autograd of lstm_eeg_model.py:32-39 with hidden_size > 48 for the serial part of a

@@ -58,9 +58,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 // ---------------------------------------------------------------------------------------------------------------
 // input split: fp32 [B][T][8] -> XS (x / 16 as fp16 hi + lo), padding rows zero
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void x3_split_input_kernel(const float* __restrict__ x, __half* __restrict__ xs, int64_t B, int T, int64_t Bp) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one (t, padded row) per thread, t fastest
-    if (idx >= (int64_t)T * Bp) return;
+// half != 0 (half tiles): window b lives in row (b / 64) * 128 + b % 64 AND in the mirror row + 64 (see lstm_fwd_x3_kernel)
+__global__ void x3_split_input_kernel(const float* __restrict__ x, __half* __restrict__ xs, int64_t B, int T, int64_t Bp, int half) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one (t, window slot) per thread, t fastest
+    const int64_t nslots = half ? Bp / 2 : Bp;
+    if (idx >= (int64_t)T * nslots) return;
     const int64_t b = idx / T;
     const int t = (int)(idx - b * T);
     float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -72,10 +74,15 @@ __global__ void x3_split_input_kernel(const float* __restrict__ x, __half* __res
     uint32_t hi[4], lo[4];
     split_pack8(f, hi, lo);
     const int ntiles = (int)(Bp / kRows);
-    const int tile = (int)(b / kRows), row = (int)(b % kRows);
+    const int per = half ? 64 : kRows;
+    const int tile = (int)(b / per), row = (int)(b % per);
     __half* dst = xs + ((((int64_t)t * ntiles + tile) * 2) * kRows + row) * 8;
     *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(dst + kRows * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (half) {
+        *reinterpret_cast<uint4*>(dst + 64 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + kRows * 8 + 64 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -94,7 +101,10 @@ struct TxFwdSmem {
     uint32_t tmem_base;
 };
 
-template <int LAYER>
+// HALF = half tiles (strong scaling / small batches, as in the 16-bit tier): 64 distinct windows per tile, rows 64..127 of
+// every operand mirror rows 0..63; copy rp = q / 2 of a window takes K chunk 2 g + rp (8 units per thread instead of 16)
+// and stores h to both row copies (shared memory and HBM), so every MMA row stays complete.
+template <int LAYER, bool HALF>
 __global__ void __launch_bounds__(kTxThreads, 1)
 lstm_fwd_x3_kernel(const __half* __restrict__ in,                   // L0: XS;  L1: TCLX (h0, or h0 after dropout)
                    const unsigned char* __restrict__ packed,        // this layer's part of the pack_decoder_x3_kernel image
@@ -102,7 +112,7 @@ lstm_fwd_x3_kernel(const __half* __restrict__ in,                   // L0: XS;  
                    const unsigned char* __restrict__ mask, uint64_t seed, uint32_t thresh16, float drop_scale,   // L0: dropout of h0
                    __half* __restrict__ h_out, __half* __restrict__ hd_out, float* __restrict__ c_out,
                    float* __restrict__ zpool, float* __restrict__ stats, int64_t B,          // L1
-                   int T, int64_t Bp, int ntiles) {
+                   int T, int64_t Bp, int ntiles, int64_t drop_stride) {
     using SM = TxFwdSmem<LAYER>;
     constexpr int kInChunks = SM::kInChunks;
     constexpr int kNW = LAYER == 0 ? kN : kX3N1;                      // accumulator columns (L1: + 16 score columns)
@@ -249,33 +259,40 @@ lstm_fwd_x3_kernel(const __half* __restrict__ in,                   // L0: XS;  
             const int q = warp & 3, g = warp >> 2;
             const int row = q * 32 + lane;
             const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-            const int gr0 = 4 * g;                                   // first of this thread's four 4-unit granules
-            float c[16], hprev[16], z[16];
+            constexpr int kNB = HALF ? 1 : 2;                        // 8-unit chunks per thread
+            const int rp = HALF ? (q >> 1) : 0;
+            const int crow = HALF ? (row & 63) : row;                // canonical row (first copy)
+            const int chunk0 = HALF ? 2 * g + rp : 2 * g;            // first K chunk of this thread
+            const int64_t bwin = HALF ? (int64_t)tile * 64 + crow : b0 + row;
+            float c[8 * kNB], hprev[8 * kNB], z[8 * kNB];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { c[j] = 0.f; hprev[j] = 0.f; z[j] = 0.f; }
+            for (int j = 0; j < 8 * kNB; ++j) { c[j] = 0.f; hprev[j] = 0.f; z[j] = 0.f; }
             float mx = -INFINITY, l = 0.f;
             auto pool = [&](float score) {                           // online softmax over time (lstm_eeg_model.py:35-37), fp32
                 if (score > mx) {
                     const float sc = expf(mx - score);
                     l *= sc;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) z[j] *= sc;
+                    for (int j = 0; j < 8 * kNB; ++j) z[j] *= sc;
                     mx = score;
                 }
                 const float e = expf(score - mx);
                 l += e;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) z[j] = fmaf(e, hprev[j], z[j]);
+                for (int j = 0; j < 8 * kNB; ++j) z[j] = fmaf(e, hprev[j], z[j]);
             };
             for (int t = 0; t < T; ++t) {
-                const int64_t grow = (int64_t)t * Bp + b0 + row;
-                uint32_t keep[2] = {0xFFu, 0xFFu};
+                const int64_t grow = (int64_t)t * Bp + b0 + crow;                        // mask-tensor row
+                const int64_t gkey = HALF ? (int64_t)t * drop_stride + bwin : grow;     // counter-based generator: layout-independent
+                uint32_t keep[kNB];
+#pragma unroll
+                for (int pr = 0; pr < kNB; ++pr) keep[pr] = 0xFFu;
                 if (drop) {
 #pragma unroll
-                    for (int pr = 0; pr < 2; ++pr) {
-                        const int blk = 2 * g + pr;
+                    for (int pr = 0; pr < kNB; ++pr) {
+                        const int blk = chunk0 + pr;
                         keep[pr] = mask ? mask_keep8(*reinterpret_cast<const uint2*>(mask + grow * kH + blk * 8))
-                                        : dropout_keep8(seed, grow, blk, thresh16);
+                                        : dropout_keep8(seed, gkey, blk, thresh16);
                     }
                 }
                 mbar_wait(&S.d_full, df_cnt & 1); ++df_cnt;
@@ -286,17 +303,24 @@ lstm_fwd_x3_kernel(const __half* __restrict__ in,                   // L0: XS;  
                     if (t >= 1) pool(__uint_as_float(sc2[0]));       // score of h_{t-1}, which is still in hprev
                 }
 #pragma unroll
-                for (int pr = 0; pr < 2; ++pr) {                      // pairs of granules = one 8-unit chunk
+                for (int pr = 0; pr < kNB; ++pr) {                    // pairs of granules = one 8-unit chunk
                     uint32_t v[32], hi[4], lo[4];
-                    tmem_ld32(tmem_d + lane_base + (gr0 + 2 * pr) * 16, v);
+                    const int chunk = chunk0 + pr;
+                    tmem_ld32(tmem_d + lane_base + chunk * 32, v);
                     cell_granule_exact(v, c + pr * 8, hprev + pr * 8);
                     cell_granule_exact(v + 16, c + pr * 8 + 4, hprev + pr * 8 + 4);
                     split_pack8(hprev + pr * 8, hi, lo);
-                    const int chunk = 2 * g + pr;
+                    const uint4 vhi = make_uint4(hi[0], hi[1], hi[2], hi[3]), vlo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     st_shared_v4(S.h + chunk * kAChunk + row * 16, hi[0], hi[1], hi[2], hi[3]);
                     st_shared_v4(S.h + (6 + chunk) * kAChunk + row * 16, lo[0], lo[1], lo[2], lo[3]);
-                    *reinterpret_cast<uint4*>(h_out + tclx_off(t, ntiles, tile, chunk, row)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(h_out + tclx_off(t, ntiles, tile, 6 + chunk, row)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(h_out + tclx_off(t, ntiles, tile, chunk, row)) = vhi;
+                    *reinterpret_cast<uint4*>(h_out + tclx_off(t, ntiles, tile, 6 + chunk, row)) = vlo;
+                    if (HALF) {                                       // the other row copy
+                        st_shared_v4(S.h + chunk * kAChunk + (row ^ 64) * 16, hi[0], hi[1], hi[2], hi[3]);
+                        st_shared_v4(S.h + (6 + chunk) * kAChunk + (row ^ 64) * 16, lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4*>(h_out + tclx_off(t, ntiles, tile, chunk, row ^ 64)) = vhi;
+                        *reinterpret_cast<uint4*>(h_out + tclx_off(t, ntiles, tile, 6 + chunk, row ^ 64)) = vlo;
+                    }
                     *reinterpret_cast<float4*>(c_out + tcl32x_off(t, ntiles, tile, 2 * chunk, row)) =
                         make_float4(c[pr * 8], c[pr * 8 + 1], c[pr * 8 + 2], c[pr * 8 + 3]);
                     *reinterpret_cast<float4*>(c_out + tcl32x_off(t, ntiles, tile, 2 * chunk + 1, row)) =
@@ -307,8 +331,13 @@ lstm_fwd_x3_kernel(const __half* __restrict__ in,                   // L0: XS;  
                         for (int u = 0; u < 8; ++u) hd[u] = ((keep[pr] >> u) & 1u) ? hprev[pr * 8 + u] * drop_scale : 0.f;
                         uint32_t dhi[4], dlo[4];
                         split_pack8(hd, dhi, dlo);
-                        *reinterpret_cast<uint4*>(hd_out + tclx_off(t, ntiles, tile, chunk, row)) = make_uint4(dhi[0], dhi[1], dhi[2], dhi[3]);
-                        *reinterpret_cast<uint4*>(hd_out + tclx_off(t, ntiles, tile, 6 + chunk, row)) = make_uint4(dlo[0], dlo[1], dlo[2], dlo[3]);
+                        const uint4 whi = make_uint4(dhi[0], dhi[1], dhi[2], dhi[3]), wlo = make_uint4(dlo[0], dlo[1], dlo[2], dlo[3]);
+                        *reinterpret_cast<uint4*>(hd_out + tclx_off(t, ntiles, tile, chunk, row)) = whi;
+                        *reinterpret_cast<uint4*>(hd_out + tclx_off(t, ntiles, tile, 6 + chunk, row)) = wlo;
+                        if (HALF) {
+                            *reinterpret_cast<uint4*>(hd_out + tclx_off(t, ntiles, tile, chunk, row ^ 64)) = whi;
+                            *reinterpret_cast<uint4*>(hd_out + tclx_off(t, ntiles, tile, 6 + chunk, row ^ 64)) = wlo;
+                        }
                     }
                 }
                 tc_fence_before();
@@ -322,14 +351,13 @@ lstm_fwd_x3_kernel(const __half* __restrict__ in,                   // L0: XS;  
                 x3_tmem_ld2(tmem_d + lane_base + kN, sc2);
                 tc_fence_before();
                 pool(__uint_as_float(sc2[0]));
-                const int64_t b = b0 + row;
-                if (b < B) {
+                if (bwin < B) {
                     const float inv_l = 1.0f / l;
-                    float* zo = zpool + b * kH + 16 * g;
+                    float* zo = zpool + bwin * kH + chunk0 * 8;
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
+                    for (int j = 0; j < 8 * kNB; j += 4)
                         *reinterpret_cast<float4*>(zo + j) = make_float4(z[j] * inv_l, z[j + 1] * inv_l, z[j + 2] * inv_l, z[j + 3] * inv_l);
-                    if (g == 0) { stats[2 * b] = mx; stats[2 * b + 1] = l; }
+                    if (g == 0 && rp == 0) { stats[2 * bwin] = mx; stats[2 * bwin + 1] = l; }
                 }
             }
         }
@@ -352,7 +380,7 @@ struct TxBwdSmem {
     alignas(128) unsigned char dg[48 * kAChunk];                     // d(gates): hi x24 | lo x24
     alignas(128) unsigned char onez[2 * kAChunk];
     alignas(8) uint64_t act_full, act_free;
-    uint64_t g_full, r_full, dg_ready;
+    uint64_t g_full[2], r_full, dg_ready;     // g_full per gate accumulator: a barrier must never run two phases ahead of its waiter
     uint32_t tmem_base;
     float wa[kH];
     float ba;
@@ -382,7 +410,10 @@ __device__ __forceinline__ void gates_exact(float vi, float vf, float vg, float 
     tcv = (1.0f - ec) * (r2 * d);
 }
 
-template <int LAYER>
+// HALF: half tiles as in lstm_fwd_x3_kernel -- copy rp = q / 2 takes K chunk 2 g + rp (8 units per thread), writes its
+// d(gates) to BOTH row copies in shared memory (so D_R is complete on every row) and to the canonical row in HBM (the
+// weight-gradient kernel then reads rows 0..63 only).
+template <int LAYER, bool HALF>
 __global__ void __launch_bounds__(kTxThreads, 1)
 lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  L1: TCLX (the layer's forward input)
                    const __half* __restrict__ h,                    // TCLX: this layer's h
@@ -396,7 +427,7 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
                    const float* __restrict__ dz, const float* __restrict__ stats, const float* __restrict__ zpool,
                    const float* __restrict__ attn_w, const float* __restrict__ attn_b, int64_t B,
                    float* __restrict__ attn_partial,                // [grid][52]: d attn_w | d attn_b
-                   int T, int64_t Bp, int ntiles) {
+                   int T, int64_t Bp, int ntiles, int64_t drop_stride) {
     using SM = TxBwdSmem<LAYER>;
     constexpr int kInChunks = LAYER == 0 ? 2 : 12;
     constexpr int kHp = LAYER == 0 ? 2 : 12;                         // first h_{t-1} chunk of the act stage
@@ -419,7 +450,7 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
         }
         if (tid == 0) {
             mbar_init(&S.act_full, 1); mbar_init(&S.act_free, 1);
-            mbar_init(&S.g_full, 1); mbar_init(&S.r_full, 1);
+            mbar_init(&S.g_full[0], 1); mbar_init(&S.g_full[1], 1); mbar_init(&S.r_full, 1);
             mbar_init(&S.dg_ready, 12 * 32);
             fence_mbar_init();
         }
@@ -441,7 +472,8 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
 #pragma unroll
     for (int j = 0; j < 16; ++j) dwa[j] = 0.f;
 
-    uint32_t act_cnt = 0, dgp = 0, gphase = 0, rphase = 0;       // role-private running phase counters
+    uint32_t act_cnt = 0, dgp = 0, rphase = 0;       // role-private running phase counters
+    uint32_t gph[2] = {0, 0};                         // epilogue: g_full phases consumed, per accumulator
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t b0 = (int64_t)tile * kRows;
         if (warp == kTxTmaWarp) {
@@ -468,7 +500,8 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
             // first weight chunk of the R operand: L0: W_hh (chunks 2..7 hi, 9..14 lo);  L1: [W_ih | W_hh] (0..11 hi, 13..24 lo)
             constexpr int kRHi = LAYER == 0 ? 2 : 0, kRLo = LAYER == 0 ? 9 : 13;
             // gate recompute of step `t` into accumulator `buf`
-            auto issue_g = [&](const uint32_t tm_g) {
+            auto issue_g = [&](const int buf) {
+                const uint32_t tm_g = tmem + buf * kN;
                 mbar_wait(&S.act_full, act_cnt & 1); ++act_cnt;
                 tc_fence_after();
                 if (LAYER == 0) {
@@ -498,12 +531,12 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
                         }
                 }
                 if (leader) umma_commit(&S.act_free);          // the stage may be refilled as soon as G has read it
-                if (leader) umma_commit(&S.g_full);
+                if (leader) umma_commit(&S.g_full[buf]);
             };
             // Per iteration i (step t = T-1-i): R(t+1) first -- it is the only MMA on the step's critical path (d(gates) ->
             // dh_rec -> d(gates)) --, then the gate recompute of the NEXT step into the other accumulator, where it runs
             // under this step's epilogue.
-            issue_g(tmem);                                          // G(T-1)
+            issue_g(0);                                             // G(T-1)
             for (int i = 0; i <= T; ++i) {
                 if (i >= 1) {
                     mbar_wait(&S.dg_ready, dgp & 1); ++dgp;
@@ -518,39 +551,46 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
                         }
                 }
                 if (leader) umma_commit(&S.r_full);            // R(t+1) done (i == 0: nothing pending)
-                if (i + 1 < T) issue_g(tmem + ((i + 1) & 1) * kN);      // G(t-1): accumulator (i+1)&1 was drained in iteration i-1
+                if (i + 1 < T) issue_g((i + 1) & 1);           // G(t-1): accumulator (i+1)&1 was drained (and its barrier consumed) in iteration i-1
             }
         } else {
             // ================= epilogue: thread = window row x 16 units ===========================================
             const int q = warp & 3, g = warp >> 2;
             const int row = q * 32 + lane;
             const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-            const int gr0 = 4 * g;
-            float dc[16], ccur[16];
+            constexpr int kNB = HALF ? 1 : 2, kU = 8 * kNB;          // 8-unit chunks / units per thread
+            const int rp = HALF ? (q >> 1) : 0;
+            const int crow = HALF ? (row & 63) : row;                // canonical row (first copy)
+            const int chunk0 = HALF ? 2 * g + rp : 2 * g;            // first K chunk (8 units) of this thread
+            const int gr0 = 2 * chunk0;                              // its first 4-unit granule
+            const int u0 = 8 * chunk0;                               // its first hidden unit
+            const int64_t bwin = HALF ? (int64_t)tile * 64 + crow : b0 + row;
+            const uint32_t xbar = HALF ? 1 + (q & 1) : 1 + q, xcnt = HALF ? 192 : 96;      // the warps that share a window
+            float dc[kU], ccur[kU];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dc[j] = 0.f;
+            for (int j = 0; j < kU; ++j) dc[j] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
+            for (int j = 0; j < kU; j += 4) {
                 const float4 a = *reinterpret_cast<const float4*>(cstate + tcl32x_off(T - 1, ntiles, tile, gr0 + j / 4, row));
                 ccur[j] = a.x; ccur[j + 1] = a.y; ccur[j + 2] = a.z; ccur[j + 3] = a.w;
             }
-            float dzr[16], zr[16], sm_m = 0.f, inv_l = 1.f;
+            float dzr[kU], zr[kU], sm_m = 0.f, inv_l = 1.f;
             if (head) {
-                const int64_t b = b0 + row;
+                const int64_t b = bwin;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    dzr[j] = (b < B) ? dz[b * kH + 16 * g + j] : 0.f;
-                    zr[j] = (b < B) ? zpool[b * kH + 16 * g + j] : 0.f;
+                for (int j = 0; j < kU; ++j) {
+                    dzr[j] = (b < B) ? dz[b * kH + u0 + j] : 0.f;
+                    zr[j] = (b < B) ? zpool[b * kH + u0 + j] : 0.f;
                 }
                 if (b < B) { sm_m = stats[2 * b]; inv_l = 1.0f / stats[2 * b + 1]; }
             }
             for (int i = 0; i <= T; ++i) {
                 const int t = T - 1 - i;
-                float cp[16], dh[16];
+                float cp[kU], dh[kU];
                 if (i < T) {
                     // ---- prefetch c_{t-1} and this step's dh BEFORE waiting for the tensor pipe -------------------
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
+                    for (int j = 0; j < kU; j += 4) {
                         float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (t > 0) c4 = *reinterpret_cast<const float4*>(cstate + tcl32x_off(t - 1, ntiles, tile, gr0 + j / 4, row));
                         cp[j] = c4.x; cp[j + 1] = c4.y; cp[j + 2] = c4.z; cp[j + 3] = c4.w;
@@ -558,11 +598,11 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
                     if (head) {
                         // head backward, time loop (lstm_eeg_model.py:35-37): alpha_t = softmax weight, centred form
                         // ds_t = alpha_t dz . (h_t - z) (no cancellation), dh_t = alpha_t dz + ds_t w_a
-                        float hv[16];
+                        float hv[kU];
 #pragma unroll
-                        for (int pr = 0; pr < 2; ++pr) {
-                            const uint4 ph = *reinterpret_cast<const uint4*>(h + tclx_off(t, ntiles, tile, 2 * g + pr, row));
-                            const uint4 pl = *reinterpret_cast<const uint4*>(h + tclx_off(t, ntiles, tile, 6 + 2 * g + pr, row));
+                        for (int pr = 0; pr < kNB; ++pr) {
+                            const uint4 ph = *reinterpret_cast<const uint4*>(h + tclx_off(t, ntiles, tile, chunk0 + pr, row));
+                            const uint4 pl = *reinterpret_cast<const uint4*>(h + tclx_off(t, ntiles, tile, 6 + chunk0 + pr, row));
                             const uint32_t wh[4] = {ph.x, ph.y, ph.z, ph.w}, wl[4] = {pl.x, pl.y, pl.z, pl.w};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
@@ -572,46 +612,52 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
                         }
                         float sp = 0.f, gp = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) { sp = fmaf(S.wa[16 * g + j], hv[j], sp); gp = fmaf(dzr[j], hv[j] - zr[j], gp); }
+                        for (int j = 0; j < kU; ++j) { sp = fmaf(S.wa[u0 + j], hv[j], sp); gp = fmaf(dzr[j], hv[j] - zr[j], gp); }
                         S.xch[g][row] = make_float2(sp, gp);
-                        named_bar_sync(1 + q, 96);
+                        named_bar_sync(xbar, xcnt);
                         float xs = 0.f, xg = 0.f;
 #pragma unroll
-                        for (int e = 0; e < 3; ++e) { const float2 xe = S.xch[e][row]; xs += xe.x; xg += xe.y; }   // fixed order
-                        named_bar_sync(1 + q, 96);                    // single exchange buffer (shared memory is full): read before rewrite
+                        for (int e = 0; e < 3; ++e) {                 // fixed order
+                            const float2 xe = S.xch[e][crow];
+                            xs += xe.x; xg += xe.y;
+                            if (HALF) { const float2 xf = S.xch[e][crow + 64]; xs += xf.x; xg += xf.y; }
+                        }
+                        named_bar_sync(xbar, xcnt);                   // single exchange buffer (shared memory is full): read before rewrite
                         const float alpha = expf(xs + S.ba - sm_m) * inv_l;
                         const float ds = alpha * xg;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            dh[j] = fmaf(alpha, dzr[j], ds * S.wa[16 * g + j]);
+                        for (int j = 0; j < kU; ++j) {
+                            dh[j] = fmaf(alpha, dzr[j], ds * S.wa[u0 + j]);
                             dwa[j] = fmaf(ds, hv[j], dwa[j]);
                         }
                         dba += ds;
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
+                        for (int j = 0; j < kU; j += 4) {
                             const float4 d4 = *reinterpret_cast<const float4*>(dh_in + tcl32x_off(t, ntiles, tile, gr0 + j / 4, row));
                             dh[j] = d4.x; dh[j + 1] = d4.y; dh[j + 2] = d4.z; dh[j + 3] = d4.w;
                         }
                     }
                 }
                 mbar_wait(&S.r_full, rphase & 1); ++rphase;
-                if (i < T) { mbar_wait(&S.g_full, gphase & 1); ++gphase; }
+                if (i < T) { mbar_wait(&S.g_full[i & 1], gph[i & 1] & 1); ++gph[i & 1]; }
                 tc_fence_after();
                 const uint32_t tm_g = tmem + (i & 1) * kN;
                 if (i >= 1) {
                     if (LAYER == 1) {
                         // din of step t+1 = D_R[:, 0:48] (x dropout mask x scale) -> dh_in of layer 0
-                        uint32_t r[16];
-                        tmem_ld16(tm_r + lane_base + 16 * g, r);
-                        const int64_t grow = (int64_t)(t + 1) * Bp + b0 + row;
+                        uint32_t r[kU];
+                        if constexpr (HALF) tmem_ld8(tm_r + lane_base + u0, reinterpret_cast<uint32_t(&)[8]>(r));
+                        else tmem_ld16(tm_r + lane_base + u0, reinterpret_cast<uint32_t(&)[16]>(r));
+                        const int64_t grow = (int64_t)(t + 1) * Bp + b0 + crow;                          // mask-tensor row
+                        const int64_t gkey = HALF ? (int64_t)(t + 1) * drop_stride + bwin : grow;        // counter-based generator
 #pragma unroll
-                        for (int pr = 0; pr < 2; ++pr) {
+                        for (int pr = 0; pr < kNB; ++pr) {
                             float o[8];
                             if (mask || thresh16 < 65536u) {
-                                const int blk = 2 * g + pr;
+                                const int blk = chunk0 + pr;
                                 const uint32_t keep = mask ? mask_keep8(*reinterpret_cast<const uint2*>(mask + grow * kH + blk * 8))
-                                                           : dropout_keep8(seed, grow, blk, thresh16);
+                                                           : dropout_keep8(seed, gkey, blk, thresh16);
 #pragma unroll
                                 for (int u = 0; u < 8; ++u) o[u] = ((keep >> u) & 1u) ? __uint_as_float(r[pr * 8 + u]) * drop_scale : 0.f;
                             } else {
@@ -623,15 +669,16 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
                         }
                     }
                     if (i < T) {
-                        uint32_t r[16];
-                        tmem_ld16(tm_r + lane_base + kRecCol + 16 * g, r);
+                        uint32_t r[kU];
+                        if constexpr (HALF) tmem_ld8(tm_r + lane_base + kRecCol + u0, reinterpret_cast<uint32_t(&)[8]>(r));
+                        else tmem_ld16(tm_r + lane_base + kRecCol + u0, reinterpret_cast<uint32_t(&)[16]>(r));
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) dh[j] += __uint_as_float(r[j]);
+                        for (int j = 0; j < kU; ++j) dh[j] += __uint_as_float(r[j]);
                     }
                 }
                 if (i == T) break;
 #pragma unroll
-                for (int pr = 0; pr < 2; ++pr) {
+                for (int pr = 0; pr < kNB; ++pr) {
                     uint32_t v[32];
                     tmem_ld32(tm_g + lane_base + (gr0 + 2 * pr) * 16, v);
 #pragma unroll
@@ -660,13 +707,21 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
                         split_pack8(e0, hi, lo);
                         st_shared_v4(S.dg + (2 * G) * kAChunk + row * 16, hi[0], hi[1], hi[2], hi[3]);
                         st_shared_v4(S.dg + (24 + 2 * G) * kAChunk + row * 16, lo[0], lo[1], lo[2], lo[3]);
-                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 2 * G, row)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 24 + 2 * G, row)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        if (HALF) {
+                            st_shared_v4(S.dg + (2 * G) * kAChunk + (row ^ 64) * 16, hi[0], hi[1], hi[2], hi[3]);
+                            st_shared_v4(S.dg + (24 + 2 * G) * kAChunk + (row ^ 64) * 16, lo[0], lo[1], lo[2], lo[3]);
+                        }
+                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 2 * G, crow)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 24 + 2 * G, crow)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         split_pack8(e1, hi, lo);
                         st_shared_v4(S.dg + (2 * G + 1) * kAChunk + row * 16, hi[0], hi[1], hi[2], hi[3]);
                         st_shared_v4(S.dg + (24 + 2 * G + 1) * kAChunk + row * 16, lo[0], lo[1], lo[2], lo[3]);
-                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 2 * G + 1, row)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 24 + 2 * G + 1, row)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        if (HALF) {
+                            st_shared_v4(S.dg + (2 * G + 1) * kAChunk + (row ^ 64) * 16, hi[0], hi[1], hi[2], hi[3]);
+                            st_shared_v4(S.dg + (24 + 2 * G + 1) * kAChunk + (row ^ 64) * 16, lo[0], lo[1], lo[2], lo[3]);
+                        }
+                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 2 * G + 1, crow)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 24 + 2 * G + 1, crow)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
                 tc_fence_before();
@@ -683,19 +738,30 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
         if (warp < 12) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float v = warp_sum(dwa[j]);
+                const float v = warp_sum(j < (HALF ? 8 : 16) ? dwa[j] : 0.f);
                 if (lane == 0) red[warp * 17 + j] = v;
             }
             const float vb = warp_sum(dba);
             if (lane == 0) red[warp * 17 + 16] = vb;
         }
         __syncthreads();
-        if (tid < kH) {
-            const int g = tid / 16, j = tid % 16;
-            attn_partial[(size_t)blockIdx.x * 52 + tid] =
-                red[(4 * g) * 17 + j] + red[(4 * g + 1) * 17 + j] + red[(4 * g + 2) * 17 + j] + red[(4 * g + 3) * 17 + j];
-        } else if (tid == kH) {
-            attn_partial[(size_t)blockIdx.x * 52 + kH] = red[16] + red[17 + 16] + red[2 * 17 + 16] + red[3 * 17 + 16];
+        if (!HALF) {
+            if (tid < kH) {
+                const int g = tid / 16, j = tid % 16;
+                attn_partial[(size_t)blockIdx.x * 52 + tid] =
+                    red[(4 * g) * 17 + j] + red[(4 * g + 1) * 17 + j] + red[(4 * g + 2) * 17 + j] + red[(4 * g + 3) * 17 + j];
+            } else if (tid == kH) {
+                attn_partial[(size_t)blockIdx.x * 52 + kH] = red[16] + red[17 + 16] + red[2 * 17 + 16] + red[3 * 17 + 16];
+            }
+        } else {
+            // unit 8 chunk + j belongs to the warps (q, g) with g = chunk / 2 and q / 2 = chunk % 2; ds is the same in every
+            // warp of a window: count it once (g = 0, copy 0 = quarters 0 and 1)
+            if (tid < kH) {
+                const int chunk = tid / 8, j = tid % 8, w0 = 4 * (chunk / 2) + 2 * (chunk % 2);
+                attn_partial[(size_t)blockIdx.x * 52 + tid] = red[w0 * 17 + j] + red[(w0 + 1) * 17 + j];
+            } else if (tid == kH) {
+                attn_partial[(size_t)blockIdx.x * 52 + kH] = red[16] + red[17 + 16];
+            }
         }
     }
     tc_fence_before();
@@ -717,7 +783,7 @@ struct TxWgSmem {
 // act stage, feature rows of the accumulator (M = 128 = 16 chunks):
 //   L1: chunks 0-5 in_hi | 6-11 hprev_hi | 12 ones | 13-15 zeros ;  16-21 in_lo | 22-27 hprev_lo | 28-31 zeros
 //   L0: chunk 0 x_hi | 1-6 hprev_hi | 7 ones | 8-15 zeros        ;  16 x_lo | 17-22 hprev_lo | 23-31 zeros
-template <int LAYER>
+template <int LAYER, bool HALF>          // HALF: rows 64..127 of the slabs are copies (or unwritten): K = 64 window rows
 __global__ void __launch_bounds__(kWgThreads, 1)
 lstm_wgrad_x3_kernel(const __half* __restrict__ dg,       // DGX
                      const __half* __restrict__ act_in,   // L0: XS;  L1: TCLX
@@ -791,7 +857,7 @@ lstm_wgrad_x3_kernel(const __half* __restrict__ dg,       // DGX
                 tc_fence_after();
                 const uint32_t td = tmem + 64 * g;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
+                for (int ks = 0; ks < (HALF ? 4 : 8); ++ks)
                     if (leader) {
                         const uint64_t ahi = desc_adv(d_act[a], ks * 256), alo = desc_adv(d_act[a], 16 * kAChunk + ks * 256);
                         const uint64_t bhi = desc_adv(d_dg[r], ks * 256), blo = desc_adv(d_dg[r], 8 * kAChunk + ks * 256);
@@ -860,22 +926,26 @@ static int tx_sms() {
 }  // namespace na
 
 // ---- C ABI ---------------------------------------------------------------------------------------------------
-extern "C" int na_x3_split_input(const float* x, void* xs, int64_t B, int64_t T, int64_t Bp, na_stream_t stream) {
+extern "C" int na_x3_split_input(const float* x, void* xs, int64_t B, int64_t T, int64_t Bp, int64_t half_stride, na_stream_t stream) {
     using namespace na;
     NA_REQUIRE(B >= 1 && T >= 1 && T < (1 << 20) && Bp >= B && Bp % tc::kRows == 0, NA_EINVAL,
                "na_x3_split_input: bad shape B=%lld T=%lld Bp=%lld (Bp must be a multiple of 128)", (long long)B, (long long)T, (long long)Bp);
+    NA_REQUIRE(half_stride == 0 || B <= Bp / 2, NA_EINVAL, "na_x3_split_input: half tiles need B <= Bp / 2");
     NA_REQUIRE_PTR(x); NA_REQUIRE_PTR(xs);
-    const int64_t n = T * Bp;
-    tc::x3_split_input_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__half*>(xs), B, (int)T, Bp);
+    const int64_t n = T * (half_stride ? Bp / 2 : Bp);
+    tc::x3_split_input_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__half*>(xs), B, (int)T, Bp,
+                                                                                          half_stride ? 1 : 0);
     count_launch();
     return check_launch("na_x3_split_input");
 }
 
 extern "C" int na_lstm_fwd_train_x3(int64_t layer, const void* in, const void* packed_x3, const float* attn_w, const float* attn_b,
                                     const unsigned char* mask, uint64_t seed, int64_t thresh16, float drop_scale, void* h, void* hd,
-                                    float* c, float* zpool, float* stats, int64_t B, int64_t T, int64_t Bp, na_stream_t stream) {
+                                    float* c, float* zpool, float* stats, int64_t B, int64_t T, int64_t Bp, int64_t half_stride,
+                                    na_stream_t stream) {
     using namespace na;
     NA_REQUIRE(layer == 0 || layer == 1, NA_EINVAL, "na_lstm_fwd_train_x3: layer must be 0 or 1");
+    NA_REQUIRE(half_stride >= 0 && (half_stride == 0 || B <= Bp / 2), NA_EINVAL, "na_lstm_fwd_train_x3: half tiles need B <= Bp / 2");
     NA_REQUIRE(T >= 1 && T < (1 << 20) && Bp >= tc::kRows && Bp % tc::kRows == 0, NA_EINVAL,
                "na_lstm_fwd_train_x3: bad shape T=%lld Bp=%lld (Bp must be a multiple of 128)", (long long)T, (long long)Bp);
     NA_REQUIRE_PTR(in); NA_REQUIRE_PTR(packed_x3); NA_REQUIRE_PTR(h); NA_REQUIRE_PTR(c);
@@ -888,22 +958,21 @@ extern "C" int na_lstm_fwd_train_x3(int64_t layer, const void* in, const void* p
     const int ntiles = (int)(Bp / tc::kRows);
     const int grid = ntiles < tc::tx_sms() ? ntiles : tc::tx_sms();
     const unsigned char* pk = reinterpret_cast<const unsigned char*>(packed_x3) + (layer == 0 ? 0 : tc::kX3B0Chunks * tc::kBChunk);
-    cudaError_t e;
-    if (layer == 0) {
-        const size_t smem = sizeof(tc::TxFwdSmem<0>);
-        e = cudaFuncSetAttribute(tc::lstm_fwd_x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail((int)e, "na_lstm_fwd_train_x3: shared memory opt-in failed (%s)", cudaGetErrorString(e));
-        tc::lstm_fwd_x3_kernel<0><<<grid, tc::kTxThreads, smem, as_stream(stream)>>>(
-            reinterpret_cast<const __half*>(in), pk, nullptr, nullptr, mask, seed, (uint32_t)thresh16, drop_scale,
-            reinterpret_cast<__half*>(h), reinterpret_cast<__half*>(hd), c, nullptr, nullptr, B, (int)T, Bp, ntiles);
-    } else {
-        const size_t smem = sizeof(tc::TxFwdSmem<1>);
-        e = cudaFuncSetAttribute(tc::lstm_fwd_x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail((int)e, "na_lstm_fwd_train_x3: shared memory opt-in failed (%s)", cudaGetErrorString(e));
-        tc::lstm_fwd_x3_kernel<1><<<grid, tc::kTxThreads, smem, as_stream(stream)>>>(
-            reinterpret_cast<const __half*>(in), pk, attn_w, attn_b, nullptr, 0, 65536u, 1.0f,
-            reinterpret_cast<__half*>(h), nullptr, c, zpool, stats, B, (int)T, Bp, ntiles);
+    const int64_t dstride = half_stride > 0 ? half_stride : Bp;
+#define NA_X3_FWD(L, HF)                                                                                                              \
+    {                                                                                                                                \
+        const size_t smem = sizeof(tc::TxFwdSmem<L>);                                                                                \
+        cudaError_t e = cudaFuncSetAttribute(tc::lstm_fwd_x3_kernel<L, HF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return fail((int)e, "na_lstm_fwd_train_x3: shared memory opt-in failed (%s)", cudaGetErrorString(e));   \
+        tc::lstm_fwd_x3_kernel<L, HF><<<grid, tc::kTxThreads, smem, as_stream(stream)>>>(                                           \
+            reinterpret_cast<const __half*>(in), pk, L == 0 ? nullptr : attn_w, L == 0 ? nullptr : attn_b, L == 0 ? mask : nullptr,   \
+            L == 0 ? seed : 0, L == 0 ? (uint32_t)thresh16 : 65536u, L == 0 ? drop_scale : 1.0f, reinterpret_cast<__half*>(h),        \
+            L == 0 ? reinterpret_cast<__half*>(hd) : nullptr, c, L == 0 ? nullptr : zpool, L == 0 ? nullptr : stats, B, (int)T, Bp,   \
+            ntiles, dstride);                                                                                                        \
     }
+    if (layer == 0) { if (half_stride > 0) NA_X3_FWD(0, true) else NA_X3_FWD(0, false) }
+    else { if (half_stride > 0) NA_X3_FWD(1, true) else NA_X3_FWD(1, false) }
+#undef NA_X3_FWD
     count_launch();
     return check_launch("na_lstm_fwd_train_x3");
 }
@@ -927,9 +996,11 @@ extern "C" int na_lstm_bwd_x3(int64_t layer, const void* act_in, const void* h, 
                               const void* packed_x3, const void* zeros, const unsigned char* in_mask, uint64_t seed, int64_t thresh16,
                               float drop_scale, float* din, void* dg, const float* dz, const float* stats, const float* zpool,
                               const float* attn_w, const float* attn_b, int64_t B, float* d_attn, float* scratch,
-                              int64_t T, int64_t Bp, na_stream_t stream) {
+                              int64_t T, int64_t Bp, int64_t half_stride, na_stream_t stream) {
     using namespace na;
     NA_REQUIRE(layer == 0 || layer == 1, NA_EINVAL, "na_lstm_bwd_x3: layer must be 0 or 1");
+    NA_REQUIRE(half_stride >= 0 && (half_stride == 0 || layer == 0 || dz != nullptr), NA_EUNSUPPORTED,
+               "na_lstm_bwd_x3: half tiles need the fused head backward on layer 1");
     NA_REQUIRE(T >= 1 && T < (1 << 20) && Bp >= tc::kRows && Bp % tc::kRows == 0, NA_EINVAL,
                "na_lstm_bwd_x3: bad shape T=%lld Bp=%lld", (long long)T, (long long)Bp);
     NA_REQUIRE_PTR(act_in); NA_REQUIRE_PTR(h); NA_REQUIRE_PTR(cstate); NA_REQUIRE_PTR(packed_x3); NA_REQUIRE_PTR(zeros);
@@ -945,24 +1016,22 @@ extern "C" int na_lstm_bwd_x3(int64_t layer, const void* act_in, const void* h, 
     const int grid = ntiles < tc::tx_sms() ? ntiles : tc::tx_sms();
     const unsigned char* pk = reinterpret_cast<const unsigned char*>(packed_x3) + (layer == 0 ? 0 : tc::kX3B0Chunks * tc::kBChunk);
     float* attn_partial = scratch;
-    cudaError_t e;
-    if (layer == 0) {
-        const size_t smem = sizeof(tc::TxBwdSmem<0>);
-        e = cudaFuncSetAttribute(tc::lstm_bwd_x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail((int)e, "na_lstm_bwd_x3: shared memory opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e));
-        tc::lstm_bwd_x3_kernel<0><<<grid, tc::kTxThreads, smem, st>>>(
-            reinterpret_cast<const __half*>(act_in), reinterpret_cast<const __half*>(h), cstate, dh_in, pk,
-            reinterpret_cast<const __half*>(zeros), nullptr, 0, 65536u, 1.0f, nullptr, reinterpret_cast<__half*>(dg),
-            nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, (int)T, Bp, ntiles);
-    } else {
-        const size_t smem = sizeof(tc::TxBwdSmem<1>);
-        e = cudaFuncSetAttribute(tc::lstm_bwd_x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail((int)e, "na_lstm_bwd_x3: shared memory opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e));
-        tc::lstm_bwd_x3_kernel<1><<<grid, tc::kTxThreads, smem, st>>>(
-            reinterpret_cast<const __half*>(act_in), reinterpret_cast<const __half*>(h), cstate, dh_in, pk,
-            reinterpret_cast<const __half*>(zeros), in_mask, seed, (uint32_t)thresh16, drop_scale, din, reinterpret_cast<__half*>(dg),
-            dz, stats, zpool, attn_w, attn_b, B, attn_partial, (int)T, Bp, ntiles);
+    const int64_t dstride = half_stride > 0 ? half_stride : Bp;
+#define NA_X3_BWD(L, HF)                                                                                                              \
+    {                                                                                                                                \
+        const size_t smem = sizeof(tc::TxBwdSmem<L>);                                                                                \
+        cudaError_t e = cudaFuncSetAttribute(tc::lstm_bwd_x3_kernel<L, HF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return fail((int)e, "na_lstm_bwd_x3: shared memory opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e)); \
+        tc::lstm_bwd_x3_kernel<L, HF><<<grid, tc::kTxThreads, smem, st>>>(                                                           \
+            reinterpret_cast<const __half*>(act_in), reinterpret_cast<const __half*>(h), cstate, dh_in, pk,                           \
+            reinterpret_cast<const __half*>(zeros), L == 0 ? nullptr : in_mask, L == 0 ? 0 : seed, L == 0 ? 65536u : (uint32_t)thresh16, \
+            L == 0 ? 1.0f : drop_scale, L == 0 ? nullptr : din, reinterpret_cast<__half*>(dg), L == 0 ? nullptr : dz,                 \
+            L == 0 ? nullptr : stats, L == 0 ? nullptr : zpool, L == 0 ? nullptr : attn_w, L == 0 ? nullptr : attn_b, B,              \
+            L == 0 ? nullptr : attn_partial, (int)T, Bp, ntiles, dstride);                                                           \
     }
+    if (layer == 0) { if (half_stride > 0) NA_X3_BWD(0, true) else NA_X3_BWD(0, false) }
+    else { if (half_stride > 0) NA_X3_BWD(1, true) else NA_X3_BWD(1, false) }
+#undef NA_X3_BWD
     count_launch();
     int rc = check_launch("na_lstm_bwd_x3");
     if (rc) return rc;
@@ -971,7 +1040,8 @@ extern "C" int na_lstm_bwd_x3(int64_t layer, const void* act_in, const void* h, 
 }
 
 extern "C" int na_lstm_wgrad_x3(int64_t layer, const void* dg, const void* act_in, const void* h, const void* zeros,
-                                float* dw_ih, float* dw_hh, float* db, float* scratch, int64_t T, int64_t Bp, na_stream_t stream) {
+                                float* dw_ih, float* dw_hh, float* db, float* scratch, int64_t T, int64_t Bp, int64_t half_stride,
+                                na_stream_t stream) {
     using namespace na;
     NA_REQUIRE(layer == 0 || layer == 1, NA_EINVAL, "na_lstm_wgrad_x3: layer must be 0 or 1");
     NA_REQUIRE(T >= 1 && T < (1 << 20) && Bp >= tc::kRows && Bp % tc::kRows == 0, NA_EINVAL,
@@ -984,20 +1054,17 @@ extern "C" int na_lstm_wgrad_x3(int64_t layer, const void* dg, const void* act_i
     const int grid = (int)(nitems < tc::tx_sms() ? nitems : tc::tx_sms());
     float* partial = scratch + (size_t)tc::tx_sms() * 52;
     const size_t smem = sizeof(tc::TxWgSmem);
-    cudaError_t e;
-    if (layer == 0) {
-        e = cudaFuncSetAttribute(tc::lstm_wgrad_x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail((int)e, "na_lstm_wgrad_x3: shared memory opt-in failed (%s)", cudaGetErrorString(e));
-        tc::lstm_wgrad_x3_kernel<0><<<grid, tc::kWgThreads, smem, st>>>(reinterpret_cast<const __half*>(dg), reinterpret_cast<const __half*>(act_in),
-                                                                       reinterpret_cast<const __half*>(h), reinterpret_cast<const __half*>(zeros),
-                                                                       partial, (int)T, ntiles);
-    } else {
-        e = cudaFuncSetAttribute(tc::lstm_wgrad_x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail((int)e, "na_lstm_wgrad_x3: shared memory opt-in failed (%s)", cudaGetErrorString(e));
-        tc::lstm_wgrad_x3_kernel<1><<<grid, tc::kWgThreads, smem, st>>>(reinterpret_cast<const __half*>(dg), reinterpret_cast<const __half*>(act_in),
-                                                                       reinterpret_cast<const __half*>(h), reinterpret_cast<const __half*>(zeros),
-                                                                       partial, (int)T, ntiles);
+#define NA_X3_WG(L, HF)                                                                                                               \
+    {                                                                                                                                \
+        cudaError_t e = cudaFuncSetAttribute(tc::lstm_wgrad_x3_kernel<L, HF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return fail((int)e, "na_lstm_wgrad_x3: shared memory opt-in failed (%s)", cudaGetErrorString(e));       \
+        tc::lstm_wgrad_x3_kernel<L, HF><<<grid, tc::kWgThreads, smem, st>>>(                                                          \
+            reinterpret_cast<const __half*>(dg), reinterpret_cast<const __half*>(act_in), reinterpret_cast<const __half*>(h),         \
+            reinterpret_cast<const __half*>(zeros), partial, (int)T, ntiles);                                                         \
     }
+    if (layer == 0) { if (half_stride > 0) NA_X3_WG(0, true) else NA_X3_WG(0, false) }
+    else { if (half_stride > 0) NA_X3_WG(1, true) else NA_X3_WG(1, false) }
+#undef NA_X3_WG
     count_launch();
     int rc = check_launch("na_lstm_wgrad_x3");
     if (rc) return rc;

@@ -873,6 +873,7 @@ def decoder_train_forward_tc(x: Tensor, lstm_params, head_params, p: float, zsco
 # exact tier (fp32 contract), training on the tensor cores (csrc/na_train_x3.cu)
 # ------------------------------------------------------------------------------------------
 EXACT_TC_TRAIN = True        # flagship shape, no d/dx wanted: operand-split tcgen05 kernels (False: FFMA / generic kernels; A/B)
+X3_HALF_TILES = False        # half tiles for the exact training tier (A/B knob; enabled once validated on the GPU)
 
 
 def _tclx(T: int, Bp: int, dev) -> Tensor:
@@ -885,26 +886,27 @@ def _tcl32(T: int, Bp: int, dev) -> Tensor:
 
 @torch.library.custom_op("neuroalpha::x3_split_input", mutates_args=(), device_types="cuda")
 @_device_guard
-def x3_split_input(x: Tensor, Bp: int) -> Tensor:
-    """fp32 windows [B,T,8] -> XS fp16 [T, Bp/128, 2, 128, 8]: x / 16 split into hi and lo halves (padding rows zero)."""
+def x3_split_input(x: Tensor, Bp: int, half_stride: int = 0) -> Tensor:
+    """fp32 windows [B,T,8] -> XS fp16 [T, Bp/128, 2, 128, 8]: x / 16 split into hi and lo halves (padding rows zero).
+    ``half_stride`` > 0: half tiles (window b in rows (b // 64) * 128 + b % 64 and + 64)."""
     _require_cuda(x)
     B, T, C = x.shape
     if x.dtype != torch.float32 or C != 8 or not x.is_contiguous() or Bp % TC_TILE or Bp < B:
         raise RuntimeError("x3_split_input: x must be contiguous fp32 [B, T, 8] and Bp a multiple of 128 >= B")
     xs = torch.empty((T, Bp // TC_TILE, 2, TC_TILE, 8), dtype=torch.float16, device=x.device)
-    _lib.call("na_x3_split_input", x.data_ptr(), xs.data_ptr(), B, T, Bp, _stream())
+    _lib.call("na_x3_split_input", x.data_ptr(), xs.data_ptr(), B, T, Bp, int(half_stride), _stream())
     return xs
 
 
 @x3_split_input.register_fake
-def _(x, Bp):
+def _(x, Bp, half_stride=0):
     return x.new_empty((x.shape[1], Bp // TC_TILE, 2, TC_TILE, 8), dtype=torch.float16)
 
 
 @torch.library.custom_op("neuroalpha::lstm_fwd_train_x3", mutates_args=(), device_types="cuda")
 @_device_guard
 def lstm_fwd_train_x3(layer: int, inp: Tensor, packed: Tensor, attn_w: Tensor, attn_b: Tensor, mask: Optional[Tensor], seed: int,
-                      thresh16: int, drop_scale: float, B: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+                      thresh16: int, drop_scale: float, B: int, half_stride: int = 0) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """Training forward of one layer at fp32 accuracy -> (h TCLX, hd TCLX or empty, c TCL32, zpool [B,48] or empty,
     stats [B,2] or empty).  Layer 0: ``inp`` = XS, ``hd`` = h after inter-layer dropout (when on); layer 1: ``inp`` = TCLX."""
     _require_cuda(inp, packed, attn_w, attn_b, mask)
@@ -919,12 +921,12 @@ def lstm_fwd_train_x3(layer: int, inp: Tensor, packed: Tensor, attn_w: Tensor, a
     _lib.call("na_lstm_fwd_train_x3", int(layer), inp.data_ptr(), packed.data_ptr(), aw.data_ptr(), ab.data_ptr(),
               _ptr(mask) if layer == 0 else None, int(seed), int(thresh16) if layer == 0 else 65536, float(drop_scale),
               h.data_ptr(), _ptr(hd) if has_drop else None, c.data_ptr(), _ptr(zpool) if layer == 1 else None,
-              _ptr(stats) if layer == 1 else None, int(B), T, Bp, _stream())
+              _ptr(stats) if layer == 1 else None, int(B), T, Bp, int(half_stride), _stream())
     return h, hd, c, zpool, stats
 
 
 @lstm_fwd_train_x3.register_fake
-def _(layer, inp, packed, attn_w, attn_b, mask, seed, thresh16, drop_scale, B):
+def _(layer, inp, packed, attn_w, attn_b, mask, seed, thresh16, drop_scale, B, half_stride=0):
     T, NT = inp.shape[0], inp.shape[1]
     has_drop = layer == 0 and (mask is not None or thresh16 < 65536)
     f32 = lambda *s: inp.new_empty(s, dtype=torch.float32)
@@ -936,7 +938,7 @@ def _(layer, inp, packed, attn_w, attn_b, mask, seed, thresh16, drop_scale, B):
 @_device_guard
 def lstm_bwd_x3(layer: int, act_in: Tensor, h: Tensor, c: Tensor, dh_in: Optional[Tensor], packed: Tensor,
                 in_mask: Optional[Tensor], seed: int, thresh16: int, drop_scale: float, head: Sequence[Tensor],
-                B: int) -> Tuple[Tensor, Tensor, Tensor]:
+                B: int, half_stride: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
     """BPTT of one layer at fp32 accuracy -> (din TCL32 (layer 1) or empty, dg DGX, d_attn [49] or empty).
     ``head`` = [] (dh_in given) or [dz, stats, zpool, attn_w, attn_b]: layer 1 with the head backward's time loop fused."""
     _require_cuda(act_in, h, c, dh_in, packed, in_mask, *head)
@@ -952,12 +954,12 @@ def lstm_bwd_x3(layer: int, act_in: Tensor, h: Tensor, c: Tensor, dh_in: Optiona
     _lib.call("na_lstm_bwd_x3", int(layer), act_in.data_ptr(), h.data_ptr(), c.data_ptr(), None if fused else dh_in.data_ptr(),
               packed.data_ptr(), zeros.data_ptr(), _ptr(in_mask), int(seed), int(thresh16), float(drop_scale),
               _ptr(din) if layer == 1 else None, dg.data_ptr(), *([t.data_ptr() for t in hp] if fused else [None] * 5), int(B),
-              _ptr(d_attn) if fused else None, scratch.data_ptr(), T, Bp, _stream())
+              _ptr(d_attn) if fused else None, scratch.data_ptr(), T, Bp, int(half_stride), _stream())
     return din, dg, d_attn[:49] if fused else d_attn
 
 
 @lstm_bwd_x3.register_fake
-def _(layer, act_in, h, c, dh_in, packed, in_mask, seed, thresh16, drop_scale, head, B):
+def _(layer, act_in, h, c, dh_in, packed, in_mask, seed, thresh16, drop_scale, head, B, half_stride=0):
     T, NT = c.shape[0], c.shape[1]
     return (c.new_empty(c.shape if layer == 1 else (0,)), h.new_empty((T, NT, 48, TC_TILE, 8)),
             c.new_empty((49,) if len(head) else (0,)))
@@ -965,7 +967,7 @@ def _(layer, act_in, h, c, dh_in, packed, in_mask, seed, thresh16, drop_scale, h
 
 @torch.library.custom_op("neuroalpha::lstm_wgrad_x3", mutates_args=(), device_types="cuda")
 @_device_guard
-def lstm_wgrad_x3(layer: int, dg: Tensor, act_in: Tensor, h: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+def lstm_wgrad_x3(layer: int, dg: Tensor, act_in: Tensor, h: Tensor, half_stride: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
     """Time-parallel weight gradients of one layer from d(gates) (DGX) and the saved activations:
     (dW_ih [192, 8 | 48], dW_hh [192, 48], db [192])."""
     _require_cuda(dg, act_in, h)
@@ -977,12 +979,12 @@ def lstm_wgrad_x3(layer: int, dg: Tensor, act_in: Tensor, h: Tensor) -> Tuple[Te
     zeros = torch.zeros((24576,), dtype=torch.uint8, device=dev)
     scratch = torch.empty((_lib.query("na_train_x3_scratch_floats"),), dtype=torch.float32, device=dev)
     _lib.call("na_lstm_wgrad_x3", int(layer), dg.data_ptr(), act_in.data_ptr(), h.data_ptr(), zeros.data_ptr(), dw_ih.data_ptr(),
-              dw_hh.data_ptr(), db.data_ptr(), scratch.data_ptr(), T, NT * TC_TILE, _stream())
+              dw_hh.data_ptr(), db.data_ptr(), scratch.data_ptr(), T, NT * TC_TILE, int(half_stride), _stream())
     return dw_ih, dw_hh, db
 
 
 @lstm_wgrad_x3.register_fake
-def _(layer, dg, act_in, h):
+def _(layer, dg, act_in, h, half_stride=0):
     f32 = lambda *s: dg.new_empty(s, dtype=torch.float32)
     return f32(192, 8 if layer == 0 else 48), f32(192, 48), f32(192)
 
@@ -1012,21 +1014,29 @@ class DecoderFunctionX3(torch.autograd.Function):
             xin = xin.float()
         if zscore:
             xin = window_zscore(xin, T, T, True, False, NA_F32)
-        Bp = padded_batch(B, TC_TILE)
-        xs = x3_split_input(xin.contiguous(), Bp)
+        # half tiles (see DecoderFunctionTC) when the batch would leave more than half of the SMs without a tile
+        half = X3_HALF_TILES and 2 * ((B + TC_TILE - 1) // TC_TILE) <= _sm_count(x.device)
+        half_stride = padded_batch(B, TC_TILE) if half else 0
+        Bp = ((B + 63) // 64) * TC_TILE if half else padded_batch(B, TC_TILE)
+        if half and mask is not None:                                    # window b -> row (b // 64) * 128 + b % 64
+            b_idx = torch.arange(B, device=x.device)
+            remapped = mask.new_zeros((T, Bp, mask.shape[2]))
+            remapped[:, (b_idx // 64) * TC_TILE + b_idx % 64] = mask[:, :B]
+            mask = remapped
+        xs = x3_split_input(xin.contiguous(), Bp, half_stride)
         packed = decoder_pack_x3(lstm_flat)
-        h0, h0d, c0, _, _ = lstm_fwd_train_x3(0, xs, packed, head[0], head[1], mask, seed, thresh16, scale1, B)
+        h0, h0d, c0, _, _ = lstm_fwd_train_x3(0, xs, packed, head[0], head[1], mask, seed, thresh16, scale1, B, half_stride)
         has_drop = mask is not None or thresh16 < 65536
-        h1, _, c1, zpool, stats = lstm_fwd_train_x3(1, h0d if has_drop else h0, packed, head[0], head[1], None, 0, 65536, 1.0, B)
+        h1, _, c1, zpool, stats = lstm_fwd_train_x3(1, h0d if has_drop else h0, packed, head[0], head[1], None, 0, 65536, 1.0, B, half_stride)
         logits, _ = head_tail_fwd(zpool, head, rrelu_slope, drop2_mask, scale, False)
         opt = [t for t in (mask, rrelu_slope, drop2_mask) if t is not None]
         ctx.save_for_backward(xs, h0, h0d, c0, h1, c1, packed, stats, zpool, *head, *opt)
-        ctx.meta = (scale, B, mask is not None, rrelu_slope is not None, drop2_mask is not None, seed, thresh16, scale1)
+        ctx.meta = (scale, B, mask is not None, rrelu_slope is not None, drop2_mask is not None, seed, thresh16, scale1, half_stride)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        scale, B, has_d1, has_rr, has_d2, seed, thresh16, scale1 = ctx.meta
+        scale, B, has_d1, has_rr, has_d2, seed, thresh16, scale1, hs = ctx.meta
         has_drop = has_d1 or thresh16 < 65536
         sv = list(ctx.saved_tensors)
         xs, h0, h0d, c0, h1, c1, packed, stats, zpool = sv[:9]
@@ -1039,11 +1049,11 @@ class DecoderFunctionX3(torch.autograd.Function):
         dz, dparams = head_tail_bwd(dlogits.contiguous(), zpool, head, rr, d2, scale)      # fp32, unscaled
         dz, s, inv_s = _scale_dz(dz)
         in1 = h0d if has_drop else h0
-        din1, dg1, d_attn = lstm_bwd_x3(1, in1, h1, c1, None, packed, d1, seed, thresh16, scale1, [dz, stats, zpool, head[0], head[1]], B)
-        dw_ih1, dw_hh1, db1 = lstm_wgrad_x3(1, dg1, in1, h1)
+        din1, dg1, d_attn = lstm_bwd_x3(1, in1, h1, c1, None, packed, d1, seed, thresh16, scale1, [dz, stats, zpool, head[0], head[1]], B, hs)
+        dw_ih1, dw_hh1, db1 = lstm_wgrad_x3(1, dg1, in1, h1, hs)
         del dg1
-        _, dg0, _ = lstm_bwd_x3(0, xs, h0, c0, din1, packed, None, 0, 65536, 1.0, [], B)
-        dw_ih0, dw_hh0, db0 = lstm_wgrad_x3(0, dg0, xs, h0)
+        _, dg0, _ = lstm_bwd_x3(0, xs, h0, c0, din1, packed, None, 0, 65536, 1.0, [], B, hs)
+        dw_ih0, dw_hh0, db0 = lstm_wgrad_x3(0, dg0, xs, h0, hs)
         del dg0
         dparams = torch.cat([d_attn * inv_s, dparams[H + 1:]])
         head_grads = split_head_grads(dparams, H, NC)

@@ -621,3 +621,34 @@ def test_exact_tc_training_in_kernel_dropout_equals_mask_mode(dev, checkpoint):
     b, gb = run((seed, th))
     assert torch.equal(a, b) and all(torch.equal(p, q) for p, q in zip(ga, gb))          # run-to-run reproducible
     assert abs(mask[:, :B].float().mean().item() - 0.4) < 0.01
+
+
+@pytest.mark.parametrize("B,T", [(300, 30), (64, 7), (1, 3), (65, 12)])
+def test_exact_tc_training_half_tiles_match_full_tiles(dev, checkpoint, B, T):
+    """Half tiles of the exact tensor-core training tier (64 windows per tile, the two row copies split the hidden units)
+    against full tiles: bit-identical logits, gradients equal up to the order of the fp32 weight-gradient accumulation, in eval
+    mode and in train mode with the counter-based in-kernel dropout (the generator's key is layout-independent)."""
+    from neural_speech_decoding_b200 import ops
+    gen = torch.Generator(device="cpu").manual_seed(B + T)
+    x = (torch.randn(B, T, 8, generator=gen) * 2.73).to(dev)
+    y = torch.randint(0, 3, (B,), generator=gen).to(dev)
+    m = make_model(dev, checkpoint)
+    saved = ops.X3_HALF_TILES
+    def run(half, train):
+        ops.X3_HALF_TILES = half
+        m.train(train)
+        m.zero_grad()
+        torch.manual_seed(77)
+        out = m(x)
+        torch.nn.functional.cross_entropy(out, y).backward()
+        return out.detach().clone(), [p.grad.clone() for p in m.parameters()]
+    try:
+        for train in (False, True):
+            a, ga = run(True, train)
+            b, gb = run(False, train)
+            assert torch.isfinite(a).all() and torch.equal(a, b), (train, (a - b).abs().max().item())
+            gmax = max(float(q.abs().max()) for q in gb)
+            for (k, _), p, q in zip(m.named_parameters(), ga, gb):
+                assert (p - q).abs().max().item() <= 1e-5 * gmax, (train, k, (p - q).abs().max().item(), gmax)
+    finally:
+        ops.X3_HALF_TILES = saved
