@@ -873,7 +873,7 @@ def decoder_train_forward_tc(x: Tensor, lstm_params, head_params, p: float, zsco
 # exact tier (fp32 contract), training on the tensor cores (csrc/na_train_x3.cu)
 # ------------------------------------------------------------------------------------------
 EXACT_TC_TRAIN = True        # flagship shape, no d/dx wanted: operand-split tcgen05 kernels (False: FFMA / generic kernels; A/B)
-X3_HALF_TILES = False        # half tiles for the exact training tier (A/B knob; enabled once validated on the GPU)
+X3_HALF_TILES = True         # half tiles for the exact training tier when a batch fills less than half of the SMs (A/B knob)
 
 
 def _tclx(T: int, Bp: int, dev) -> Tensor:
