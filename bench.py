@@ -677,21 +677,23 @@ def train_leg(args, world, rank, dev):
         model.train()
         model.compute_dtype = dtype
         per_gpu = global_batch // world
+        # micro-batches of `micro` windows (default 148 x 128 = one tile per SM) + one ragged remainder: the per-GPU batch is
+        # exactly global_batch / world, whatever the SM count
         micro = min(per_gpu, micro)
-        n_micro = max(1, per_gpu // micro)
-        per_gpu = n_micro * micro
+        micros = [micro] * (per_gpu // micro) + ([per_gpu % micro] if per_gpu % micro else [])
         x = synth_windows(micro, seed=2000 + rank).to(dev)
         g = torch.Generator(device="cpu").manual_seed(1 + rank)
         y = torch.randint(0, NC, (micro,), generator=g).to(dev)
         trainer = DataParallelTrainer(model, torch.optim.Adam(model.parameters(), lr=1e-3), world_size=world)
+        batches = [(x[:m], y[:m]) for m in micros]
 
         def step():
-            trainer.step([(x, y)] * n_micro, global_batch=per_gpu * world)
+            trainer.step(batches, global_batch=per_gpu * world)
 
         ms = time_steps(step, steps, 1, world, dev)
         wps = world * per_gpu * steps / (ms * 1e-3)
         return {"value": wps, "unit": "windows/s", "ms_per_step": ms / steps, "global_batch": per_gpu * world,
-                "per_gpu_batch": per_gpu, "micro_batch": micro, "steps": steps,
+                "per_gpu_batch": per_gpu, "micro_batch": micro, "micro_batches": micros, "steps": steps,
                 "achieved_tflops_per_gpu": FWDBWD_FLOPS_PER_WINDOW * wps / world / 1e12}
 
     def dp_equivalence(dtype):
@@ -752,7 +754,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stress", action="store_true")
     ap.add_argument("--train-batch", type=int, default=65536, help="GLOBAL batch of the train leg (configs[2])")
-    ap.add_argument("--train-micro", type=int, default=16384)
+    ap.add_argument("--train-micro", type=int, default=148 * 128, help="windows per micro-batch (default: one 128-window tile per SM)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
