@@ -372,6 +372,15 @@ int na_lstm_wide_bwd(const void* gates, const float* c, const float* dh_in, cons
 int na_phase_coupling_filter(const float* x, float* y, const double* twiddle, double lambd, int* status,
                              int64_t B, int64_t T, int64_t C, na_stream_t stream);
 
+/* ---- optimizer step (train step of SURVEY 8(d): "Adam lr 1e-3 in torch") --------------------------------------------
+ * torch.optim.Adam's update (no amsgrad) for a whole list of fp32 tensors in ONE launch.  table (device): n_tensors x
+ * {param ptr, grad ptr, exp_avg ptr, exp_avg_sq ptr, numel} as int64; grad_scale: optional device scalar multiplied into every
+ * gradient (NULL = 1); bias_correction{1,2} = 1 - beta^step, computed by the caller.
+ */
+int na_adam_multi(const int64_t* table, int64_t n_tensors, int64_t max_numel, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, float bias_correction1, float bias_correction2, const float* grad_scale,
+                  na_stream_t stream);
+
 /* ---- K5: trial averaging -----------------------------------------------------------------
  * Replaces tester.py:54,89,97 (and :90,98 for the chunk): fp32 zeros, += in trial order
  * r = 0..R-1, then one IEEE division by R.   in [R][N] -> out [N].

@@ -62,6 +62,7 @@ SIGNATURES = {
     "na_lstm_wide_bwd": (c_int, [P, P, P, P, P, P, I64, I64, I64, P]),
     "na_phase_coupling_filter": (c_int, [P, P, P, ctypes.c_double, P, I64, I64, I64, P]),
     "na_csv_parse_f32": (c_int, [P, P, P, P, I64, I64, I64, P]),
+    "na_adam_multi": (c_int, [P, I64, I64, F32, F32, F32, F32, F32, F32, F32, P, P]),
     "na_trial_mean_f32": (c_int, [P, P, I64, I64, P]),
 }
 

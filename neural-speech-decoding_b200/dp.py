@@ -59,6 +59,8 @@ class DataParallelTrainer:
             world_size = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.world_size = world_size
         self.bucket = FlatGradBucket(list(model.parameters()))
+        if hasattr(optimizer, "attach"):            # optim.FusedAdam updates in place: it must drop the model's packed-weight caches
+            optimizer.attach(model)
 
     def backward_only(self, micro_batches: Iterable[Tuple[torch.Tensor, torch.Tensor]], global_batch: int) -> torch.Tensor:
         self.bucket.check_views()

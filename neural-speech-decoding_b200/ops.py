@@ -747,8 +747,7 @@ def lstm_bwd_bf16(layer: int, act_in: Tensor, h: Tensor, c: Tensor, dh: Optional
     fused = len(head) > 0
     d_attn = torch.empty((H + 1,) if fused else (0,), dtype=torch.float32, device=dev)
     hp = [_f32c(t) for t in head]
-    zeros = torch.zeros((12288,), dtype=torch.uint8, device=dev)
-    scratch = torch.empty((36864 + 4 * _lib.query("na_train_bf16_partial_floats"),), dtype=torch.uint8, device=dev)
+    zeros, scratch = _train_buffers(dev, "bf16", 12288, 36864 + 4 * _lib.query("na_train_bf16_partial_floats"))
     _lib.call("na_lstm_bwd_bf16", int(layer), act_in.data_ptr(), h.data_ptr(), c.data_ptr(),
               None if fused else _f32c(dh).data_ptr(), packed.data_ptr(), w_ih.data_ptr(), w_hh.data_ptr(),
               zeros.data_ptr(), _ptr(in_mask), int(seed), int(thresh16), float(drop_scale),
@@ -775,6 +774,20 @@ def _scale_dz(dz: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     amax = dz.detach().abs().max().clamp_min(1e-30)
     s = torch.pow(2.0, 6.0 - torch.ceil(torch.log2(amax)))          # (torch.exp2 would JIT-compile via nvrtc)
     return dz * s, s, 1.0 / s
+
+
+_TRAIN_BUFFERS: dict = {}
+
+
+def _train_buffers(device, tag: str, zero_bytes: int, scratch_bytes: int):
+    """Per (device, stream) zero block and scratch area of the training kernels (they used to be allocated -- and the zeros
+    memset -- on every call).  Launches on one stream are ordered, so consecutive kernels may share the scratch."""
+    key = (device.index, tag, _stream())
+    hit = _TRAIN_BUFFERS.get(key)
+    if hit is None or hit[1].numel() < scratch_bytes:
+        hit = (torch.zeros((zero_bytes,), dtype=torch.uint8, device=device), torch.empty((scratch_bytes,), dtype=torch.uint8, device=device))
+        _TRAIN_BUFFERS[key] = hit
+    return hit
 
 
 TC_HALF_TILES = True          # 16-bit training tier: half tiles for batches that leave more than half of the SMs idle (A/B knob)
@@ -853,12 +866,11 @@ class DecoderFunctionTC(torch.autograd.Function):
         dz, s, inv_s = _scale_dz(dz)
         din1, dw_ih1, dw_hh1, db1, d_attn = lstm_bwd_bf16(1, h0d if has_drop else h0, h1, c1, None, packed, w_ih1, w_hh1,
                                                           d1, seed, thresh16, scale1, [dz, stats, zpool, head[0], head[1]], B, half_stride)
-        dparams = torch.cat([d_attn * inv_s, dparams[H + 1:]])
-        head_grads = split_head_grads(dparams, H, NC)
         _, dw_ih0, dw_hh0, db0, _ = lstm_bwd_bf16(0, xt, h0, c0, din1, packed, w_ih0, w_hh0, None, 0, 65536, 1.0, [], B, half_stride)
-        db0, db1 = db0 * inv_s, db1 * inv_s
-        grads = [dw_ih0 * inv_s, dw_hh0 * inv_s, db0, db0.clone(), dw_ih1 * inv_s, dw_hh1 * inv_s, db1, db1.clone(),
-                 *head_grads]
+        torch._foreach_mul_([dw_ih0, dw_hh0, db0, dw_ih1, dw_hh1, db1, d_attn], inv_s)      # ONE launch unscales every scaled gradient
+        dparams = torch.cat([d_attn, dparams[H + 1:]])
+        head_grads = split_head_grads(dparams, H, NC)
+        grads = [dw_ih0, dw_hh0, db0, db0.clone(), dw_ih1, dw_hh1, db1, db1.clone(), *head_grads]
         grads = [g.to(dt) if g.dtype != dt else g for g, dt in zip(grads, ctx.param_dtypes)]   # .bfloat16() modules
         return (None, None, None, None, None, None, *grads)
 
@@ -949,8 +961,7 @@ def lstm_bwd_x3(layer: int, act_in: Tensor, h: Tensor, c: Tensor, dh_in: Optiona
     fused = len(head) > 0
     d_attn = torch.empty((52,) if fused else (0,), dtype=torch.float32, device=dev)
     hp = [_f32c(t) for t in head]
-    zeros = torch.zeros((24576,), dtype=torch.uint8, device=dev)
-    scratch = torch.empty((_lib.query("na_train_x3_scratch_floats"),), dtype=torch.float32, device=dev)
+    zeros, scratch = _train_buffers(dev, "x3", 24576, 4 * _lib.query("na_train_x3_scratch_floats"))
     _lib.call("na_lstm_bwd_x3", int(layer), act_in.data_ptr(), h.data_ptr(), c.data_ptr(), None if fused else dh_in.data_ptr(),
               packed.data_ptr(), zeros.data_ptr(), _ptr(in_mask), int(seed), int(thresh16), float(drop_scale),
               _ptr(din) if layer == 1 else None, dg.data_ptr(), *([t.data_ptr() for t in hp] if fused else [None] * 5), int(B),
@@ -976,8 +987,7 @@ def lstm_wgrad_x3(layer: int, dg: Tensor, act_in: Tensor, h: Tensor, half_stride
     dw_ih = torch.empty((192, 8 if layer == 0 else 48), dtype=torch.float32, device=dev)
     dw_hh = torch.empty((192, 48), dtype=torch.float32, device=dev)
     db = torch.empty((192,), dtype=torch.float32, device=dev)
-    zeros = torch.zeros((24576,), dtype=torch.uint8, device=dev)
-    scratch = torch.empty((_lib.query("na_train_x3_scratch_floats"),), dtype=torch.float32, device=dev)
+    zeros, scratch = _train_buffers(dev, "x3", 24576, 4 * _lib.query("na_train_x3_scratch_floats"))
     _lib.call("na_lstm_wgrad_x3", int(layer), dg.data_ptr(), act_in.data_ptr(), h.data_ptr(), zeros.data_ptr(), dw_ih.data_ptr(),
               dw_hh.data_ptr(), db.data_ptr(), scratch.data_ptr(), T, NT * TC_TILE, int(half_stride), _stream())
     return dw_ih, dw_hh, db
@@ -1055,10 +1065,11 @@ class DecoderFunctionX3(torch.autograd.Function):
         _, dg0, _ = lstm_bwd_x3(0, xs, h0, c0, din1, packed, None, 0, 65536, 1.0, [], B, hs)
         dw_ih0, dw_hh0, db0 = lstm_wgrad_x3(0, dg0, xs, h0, hs)
         del dg0
-        dparams = torch.cat([d_attn * inv_s, dparams[H + 1:]])
+        d_attn = d_attn.clone()                        # (a slice of the kernel's 52-float output)
+        torch._foreach_mul_([dw_ih0, dw_hh0, db0, dw_ih1, dw_hh1, db1, d_attn], inv_s)      # ONE launch unscales every scaled gradient
+        dparams = torch.cat([d_attn, dparams[H + 1:]])
         head_grads = split_head_grads(dparams, H, NC)
-        db0, db1 = db0 * inv_s, db1 * inv_s
-        grads = [dw_ih0 * inv_s, dw_hh0 * inv_s, db0, db0.clone(), dw_ih1 * inv_s, dw_hh1 * inv_s, db1, db1.clone(), *head_grads]
+        grads = [dw_ih0, dw_hh0, db0, db0.clone(), dw_ih1, dw_hh1, db1, db1.clone(), *head_grads]
         grads = [g.to(dt) if g.dtype != dt else g for g, dt in zip(grads, ctx.param_dtypes)]
         return (None, None, None, None, None, None, *grads)
 

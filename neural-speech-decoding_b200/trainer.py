@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from .dp import DataParallelTrainer, shard_batch
+from .optim import FusedAdam
 from .lstm_eeg_model import EEG_LSTM
 
 DEFAULT_CLASSES = ("food", "water", "backgroundnoise")      # CLASS_NAMES order, lstm_eeg_model.py:11
@@ -81,7 +82,9 @@ def train(X: np.ndarray, y: np.ndarray, num_classes: int, epochs: int = 30, batc
     tr_idx, va_idx = split_indices(len(X), val_frac, seed)
     Xd = X.to(device) if isinstance(X, torch.Tensor) else torch.from_numpy(X).to(device)       # GPU-ingested or numpy
     yd = y.to(device) if isinstance(y, torch.Tensor) else torch.from_numpy(y).to(device)
-    trainer = DataParallelTrainer(model, torch.optim.Adam(model.parameters(), lr=lr), world_size=world)
+    # one-launch Adam on the GPU; plain torch Adam only where the parameters are not on a CUDA device (host-logic tests)
+    opt = FusedAdam(model.parameters(), lr=lr) if torch.device(device).type == "cuda" else torch.optim.Adam(model.parameters(), lr=lr)
+    trainer = DataParallelTrainer(model, opt, world_size=world)
     history = []
     for ep in range(epochs):
         model.train()
