@@ -238,6 +238,9 @@ lstm2_fwd_train_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                     mbar_wait(&S.d0_full, n & 1);
                     if (q == 0 && g == 0 && lane == 0) mbar_arrive(&S.x_empty[n % kV2XStages]);
                     tc_fence_after();
+                    // the saves go to HBM only AFTER the fence + arrive that release h0_t to the tensor pipe: the fence
+                    // (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) otherwise waits for the global stores, on the step's critical path
+                    uint32_t ph[4 * kNB], pd[4 * kNB];
 #pragma unroll
                     for (int pr = 0; pr < kNB; ++pr) {
                         const int blk = blk0 + pr;
@@ -246,35 +249,39 @@ lstm2_fwd_train_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                         tmem_ld32(tmem_d0 + lane_base + blk * 32, v);
                         cell_granule_f(v, c0 + pr * 8, H);
                         cell_granule_f(v + 16, c0 + pr * 8 + 4, H + 4);
-                        const uint32_t p0 = pack_val(H[0], H[1]), p1 = pack_val(H[2], H[3]);
-                        const uint32_t p2 = pack_val(H[4], H[5]), p3 = pack_val(H[6], H[7]);
-                        const uint4 hs = make_uint4(half2_halve(p0), half2_halve(p1), half2_halve(p2), half2_halve(p3));
-                        st_shared_v4(S.h0[n & 1] + blk * kAChunk + row * 16, p0, p1, p2, p3);
-                        *reinterpret_cast<uint4*>(h0_out + tcl + blk * (kAChunk / 2)) = hs;
-                        if (HALF) {                        // the other row copy
-                            st_shared_v4(S.h0[n & 1] + blk * kAChunk + (row ^ 64) * 16, p0, p1, p2, p3);
-                            *reinterpret_cast<uint4*>(h0_out + tcl + blk * (kAChunk / 2) + ((row ^ 64) - row) * 8) = hs;
-                        }
-                        st_global_v4f(c0_out + tcl32_off(t, ntiles, tile, 2 * blk, row), c0[pr * 8], c0[pr * 8 + 1], c0[pr * 8 + 2], c0[pr * 8 + 3]);
-                        st_global_v4f(c0_out + tcl32_off(t, ntiles, tile, 2 * blk + 1, row), c0[pr * 8 + 4], c0[pr * 8 + 5], c0[pr * 8 + 6], c0[pr * 8 + 7]);
+                        ph[pr * 4] = pack_val(H[0], H[1]); ph[pr * 4 + 1] = pack_val(H[2], H[3]);
+                        ph[pr * 4 + 2] = pack_val(H[4], H[5]); ph[pr * 4 + 3] = pack_val(H[6], H[7]);
+                        st_shared_v4(S.h0[n & 1] + blk * kAChunk + row * 16, ph[pr * 4], ph[pr * 4 + 1], ph[pr * 4 + 2], ph[pr * 4 + 3]);
+                        if (HALF)                          // the other row copy
+                            st_shared_v4(S.h0[n & 1] + blk * kAChunk + (row ^ 64) * 16, ph[pr * 4], ph[pr * 4 + 1], ph[pr * 4 + 2], ph[pr * 4 + 3]);
                         if (drop) {
                             float Hd[8];
 #pragma unroll
                             for (int u = 0; u < 8; ++u) Hd[u] = ((keep[pr] >> u) & 1u) ? H[u] * drop_scale : 0.f;
-                            const uint32_t q0 = pack_val(Hd[0], Hd[1]), q1 = pack_val(Hd[2], Hd[3]);
-                            const uint32_t q2 = pack_val(Hd[4], Hd[5]), q3 = pack_val(Hd[6], Hd[7]);
-                            const uint4 ds = make_uint4(half2_halve(q0), half2_halve(q1), half2_halve(q2), half2_halve(q3));
-                            st_shared_v4(S.h0d[n & 1] + blk * kAChunk + row * 16, q0, q1, q2, q3);
-                            *reinterpret_cast<uint4*>(h0d_out + tcl + blk * (kAChunk / 2)) = ds;
-                            if (HALF) {
-                                st_shared_v4(S.h0d[n & 1] + blk * kAChunk + (row ^ 64) * 16, q0, q1, q2, q3);
-                                *reinterpret_cast<uint4*>(h0d_out + tcl + blk * (kAChunk / 2) + ((row ^ 64) - row) * 8) = ds;
-                            }
+                            pd[pr * 4] = pack_val(Hd[0], Hd[1]); pd[pr * 4 + 1] = pack_val(Hd[2], Hd[3]);
+                            pd[pr * 4 + 2] = pack_val(Hd[4], Hd[5]); pd[pr * 4 + 3] = pack_val(Hd[6], Hd[7]);
+                            st_shared_v4(S.h0d[n & 1] + blk * kAChunk + row * 16, pd[pr * 4], pd[pr * 4 + 1], pd[pr * 4 + 2], pd[pr * 4 + 3]);
+                            if (HALF)
+                                st_shared_v4(S.h0d[n & 1] + blk * kAChunk + (row ^ 64) * 16, pd[pr * 4], pd[pr * 4 + 1], pd[pr * 4 + 2], pd[pr * 4 + 3]);
                         }
                     }
                     tc_fence_before();
                     fence_proxy_async_smem();
                     mbar_arrive(&S.h0_ready[n & 1]);
+#pragma unroll
+                    for (int pr = 0; pr < kNB; ++pr) {
+                        const int blk = blk0 + pr;
+                        const uint4 hs = make_uint4(half2_halve(ph[pr * 4]), half2_halve(ph[pr * 4 + 1]), half2_halve(ph[pr * 4 + 2]), half2_halve(ph[pr * 4 + 3]));
+                        *reinterpret_cast<uint4*>(h0_out + tcl + blk * (kAChunk / 2)) = hs;
+                        if (HALF) *reinterpret_cast<uint4*>(h0_out + tcl + blk * (kAChunk / 2) + ((row ^ 64) - row) * 8) = hs;
+                        st_global_v4f(c0_out + tcl32_off(t, ntiles, tile, 2 * blk, row), c0[pr * 8], c0[pr * 8 + 1], c0[pr * 8 + 2], c0[pr * 8 + 3]);
+                        st_global_v4f(c0_out + tcl32_off(t, ntiles, tile, 2 * blk + 1, row), c0[pr * 8 + 4], c0[pr * 8 + 5], c0[pr * 8 + 6], c0[pr * 8 + 7]);
+                        if (drop) {
+                            const uint4 ds = make_uint4(half2_halve(pd[pr * 4]), half2_halve(pd[pr * 4 + 1]), half2_halve(pd[pr * 4 + 2]), half2_halve(pd[pr * 4 + 3]));
+                            *reinterpret_cast<uint4*>(h0d_out + tcl + blk * (kAChunk / 2)) = ds;
+                            if (HALF) *reinterpret_cast<uint4*>(h0d_out + tcl + blk * (kAChunk / 2) + ((row ^ 64) - row) * 8) = ds;
+                        }
+                    }
                 }
                 if (t >= 1) {                              // ---- layer 1, step t-1 (+ pooling of step t-2)
                     const int tt = t - 1;
@@ -294,19 +301,21 @@ lstm2_fwd_train_v2_kernel(const __nv_bfloat16* __restrict__ x,        // TMP [T]
                         cell_granule_f(v + 16, c1 + pr * 8 + 4, H + 4);
                         hb[pr * 4] = pack_val(H[0], H[1]); hb[pr * 4 + 1] = pack_val(H[2], H[3]);
                         hb[pr * 4 + 2] = pack_val(H[4], H[5]); hb[pr * 4 + 3] = pack_val(H[6], H[7]);
-                        const uint4 hs = make_uint4(half2_halve(hb[pr * 4]), half2_halve(hb[pr * 4 + 1]), half2_halve(hb[pr * 4 + 2]), half2_halve(hb[pr * 4 + 3]));
                         st_shared_v4(S.h1 + blk * kAChunk + row * 16, hb[pr * 4], hb[pr * 4 + 1], hb[pr * 4 + 2], hb[pr * 4 + 3]);
-                        *reinterpret_cast<uint4*>(h1_out + tcl + blk * (kAChunk / 2)) = hs;
-                        if (HALF) {
-                            st_shared_v4(S.h1 + blk * kAChunk + (row ^ 64) * 16, hb[pr * 4], hb[pr * 4 + 1], hb[pr * 4 + 2], hb[pr * 4 + 3]);
-                            *reinterpret_cast<uint4*>(h1_out + tcl + blk * (kAChunk / 2) + ((row ^ 64) - row) * 8) = hs;
-                        }
-                        st_global_v4f(c1_out + tcl32_off(tt, ntiles, tile, 2 * blk, row), c1[pr * 8], c1[pr * 8 + 1], c1[pr * 8 + 2], c1[pr * 8 + 3]);
-                        st_global_v4f(c1_out + tcl32_off(tt, ntiles, tile, 2 * blk + 1, row), c1[pr * 8 + 4], c1[pr * 8 + 5], c1[pr * 8 + 6], c1[pr * 8 + 7]);
+                        if (HALF) st_shared_v4(S.h1 + blk * kAChunk + (row ^ 64) * 16, hb[pr * 4], hb[pr * 4 + 1], hb[pr * 4 + 2], hb[pr * 4 + 3]);
                     }
                     tc_fence_before();
                     fence_proxy_async_smem();
                     mbar_arrive(&S.h1_ready);
+#pragma unroll
+                    for (int pr = 0; pr < kNB; ++pr) {             // saves: after the release (see layer 0)
+                        const int blk = blk0 + pr;
+                        const uint4 hs = make_uint4(half2_halve(hb[pr * 4]), half2_halve(hb[pr * 4 + 1]), half2_halve(hb[pr * 4 + 2]), half2_halve(hb[pr * 4 + 3]));
+                        *reinterpret_cast<uint4*>(h1_out + tcl + blk * (kAChunk / 2)) = hs;
+                        if (HALF) *reinterpret_cast<uint4*>(h1_out + tcl + blk * (kAChunk / 2) + ((row ^ 64) - row) * 8) = hs;
+                        st_global_v4f(c1_out + tcl32_off(tt, ntiles, tile, 2 * blk, row), c1[pr * 8], c1[pr * 8 + 1], c1[pr * 8 + 2], c1[pr * 8 + 3]);
+                        st_global_v4f(c1_out + tcl32_off(tt, ntiles, tile, 2 * blk + 1, row), c1[pr * 8 + 4], c1[pr * 8 + 5], c1[pr * 8 + 6], c1[pr * 8 + 7]);
+                    }
                     if (t >= 2) pool(__uint_as_float(sc2[0]) + __uint_as_float(sc2[1]));
 #pragma unroll
                     for (int u = 0; u < 4 * kNB; ++u) hprev[u] = hb[u];

@@ -31,6 +31,10 @@ constexpr int kBwdU = 8 * kBwdUB;       // units per epilogue thread
 constexpr int kBwdEW = 4 * kBwdEG;      // epilogue warps; warp kBwdEW = MMA issuer, kBwdEW + 1 = TMA producer
 constexpr int kBwdThreads = (kBwdEW + 2) * 32;
 constexpr int kXStagesT = 4;
+// backward: [in_t | 1 | h_{t-1}] stages in flight.  The gate recompute of step t-1 is issued early in step t; with two stages its
+// TMA load, which has to wait for W(t+1), was 35 % of the MMA warp's time in half-tile mode (three stages: -15 % / -21 %
+// kernel time).  Full tiles of layer 1 are bound by instruction issue instead and lose L1 capacity to a third stage.
+constexpr int bwd_stages(int KI, bool half) { return (KI == 48 && !half) ? 2 : 3; }
 
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 
@@ -334,15 +338,15 @@ struct BwdCfg {
     static_assert(kColW2 + kNW <= 512, "TMEM budget");
 };
 
-template <int KI>
+template <int KI, int kBwdStages>
 struct BwdSmem {
     using C = BwdCfg<KI>;
     alignas(128) unsigned char bg[C::kStageChunks * kBChunk];          // forward B operand (recompute)
     alignas(128) unsigned char br[24 * C::kNR * 16];                   // [W_ih | W_hh]^T, K = 192 gate columns
-    alignas(128) unsigned char act[2][C::kStageChunks * kAChunk];      // [in_t | 1 | h_{t-1}] stages
+    alignas(128) unsigned char act[kBwdStages][C::kStageChunks * kAChunk];      // [in_t | 1 | h_{t-1}] stages
     alignas(128) unsigned char dg[24 * kAChunk];                       // d(gates) bf16, A operand of R and W
-    alignas(8) uint64_t act_full[2], act_free[2];
-    uint64_t g_full, dg_ready, w_done;
+    alignas(8) uint64_t act_full[kBwdStages], act_free[kBwdStages];
+    uint64_t g_full, g_free, r_full, dg_ready, w_done;
     uint32_t tmem_base;
     // fused head backward (layer 1): attention weights, per-step exchange of the two half-row warps'
     // partial (score, dz.h), the per-tile dz.z exchange, and the final d(attn) reduction
@@ -352,6 +356,8 @@ struct BwdSmem {
     float xch0[kBwdEG][kRows];
     float red[kBwdEW][kBwdU + 1];
 };
+
+static_assert(sizeof(BwdSmem<48, 3>) + 1024 <= 232448 && sizeof(BwdSmem<8, 3>) + 1024 <= 232448, "shared-memory budget (227 KB)");
 
 // HALF = half tiles (see lstm2_fwd_train_v2_kernel): 64 distinct windows per tile, rows 64..127 mirror rows 0..63.  Copy
 // rp = q / 2 of a window takes unit block 2 hf + rp (8 units per thread instead of 16) and writes its d(gates) to BOTH row
@@ -378,7 +384,8 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                      int T, int64_t Bp, int ntiles, int64_t drop_stride) {
     using C = BwdCfg<KI>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    BwdSmem<KI>& S = *reinterpret_cast<BwdSmem<KI>*>(smem_raw);
+    constexpr int kBwdStages = bwd_stages(KI, HALF);
+    BwdSmem<KI, kBwdStages>& S = *reinterpret_cast<BwdSmem<KI, kBwdStages>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform (role branches = uniform control flow)
     {
@@ -391,13 +398,18 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
         const uint4 ones = make_uint4(kValOnes2, 0u, 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);
         for (int i = tid; i < kRows; i += kBwdThreads)
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < kBwdStages; ++s) {
                 reinterpret_cast<uint4*>(S.act[s] + C::kOnesChunk * kAChunk)[i] = ones;
                 if (KI == 48) reinterpret_cast<uint4*>(S.act[s] + 13 * kAChunk)[i] = zero;
             }
         if (tid == 0) {
-            for (int s = 0; s < 2; ++s) { mbar_init(&S.act_full[s], 1); mbar_init(&S.act_free[s], 1); }
+            // fused head backward: the epilogue threads read h_t out of the stage of step t+1, so a stage is free once the W
+            // MMAs (one commit) AND every epilogue thread have finished with it
+            const uint32_t free_cnt = (KI == 48 && dz != nullptr) ? 1 + 32 * kBwdEW : 1;
+            for (int s = 0; s < kBwdStages; ++s) { mbar_init(&S.act_full[s], 1); mbar_init(&S.act_free[s], free_cnt); }
             mbar_init(&S.g_full, 1);
+            mbar_init(&S.r_full, 1);
+            mbar_init(&S.g_free, 32 * kBwdEW);
             mbar_init(&S.w_done, 1);
             mbar_init(&S.dg_ready, 32 * kBwdEW);
             fence_mbar_init();
@@ -423,7 +435,7 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
     constexpr uint32_t kStageBytes = (C::kInChunks + 6) * kAChunk;
 
     uint32_t k0 = 0;                              // running step counter (stage / phase bookkeeping)
-    uint32_t gphase = 0, wphase = 0;              // phases of g_full / w_done consumed so far (epilogue warps)
+    uint32_t gphase = 0, rphase = 0, wphase = 0;  // phases of g_full / r_full / w_done consumed so far (epilogue warps)
     bool first_w = true;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t b0 = (int64_t)tile * kRows;
@@ -432,7 +444,7 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
             if (lane == 0)
                 for (int i = 0; i < T; ++i) {
                     const int t = T - 1 - i;
-                    const uint32_t k = k0 + i, s = k & 1, u = k >> 1;
+                    const uint32_t k = k0 + i, s = k % kBwdStages, u = k / kBwdStages;
                     mbar_wait(&S.act_free[s], (u & 1) ^ 1);
                     mbar_arrive_expect_tx(&S.act_full[s], kStageBytes);
                     bulk_load(S.act[s], act_in + (((int64_t)t * ntiles + tile) * C::kInChunks) * (kAChunk / 2),
@@ -442,9 +454,10 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                 }
         } else if (warp == kBwdEW) {
             // ================= MMA issuer ================================================================
-            // per iteration: R(prev) -> G(cur) -> commit g_full -> W(prev) -> commit act_free, w_done.
-            // The epilogue only needs R and G; W (dW accumulation) trails behind and is fenced by w_done
-            // before the epilogue overwrites d(gates).
+            // per iteration i (step t = T-1-i):  R(t+1) -> commit r_full -> W(t+1) -> commit act_free, w_done -> G(t-1) -> commit
+            // g_full.  Only R is on the step's critical path (d(gates) -> dh_rec -> d(gates)): the gate recompute of the NEXT
+            // step is issued as soon as the epilogue has drained this step's gates out of TMEM (g_free) and runs, like the
+            // dW accumulation, under the epilogue.
             {   // whole warp, warp-uniform control flow; one elected lane issues
                 const bool leader = elect_one();
                 // base descriptors, built once (see desc_adv)
@@ -453,11 +466,23 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                 const uint64_t d_dgk = umma_desc(smem_u32(S.dg), kAChunk, 128);                // d(gates) as K-major A (R)
                 const uint64_t d_dgm1 = umma_desc(smem_u32(S.dg), 128, kAChunk);               // d(gates)^T, MN-major A (W, rows 0..127)
                 const uint64_t d_dgm2 = umma_desc(smem_u32(S.dg) + 8 * kAChunk, 128, kAChunk); // rows 64..191
-                const uint64_t d_actk[2] = {umma_desc(smem_u32(S.act[0]), kAChunk, 128), umma_desc(smem_u32(S.act[1]), kAChunk, 128)};
-                const uint64_t d_actm[2] = {umma_desc(smem_u32(S.act[0]), 128, kAChunk), umma_desc(smem_u32(S.act[1]), 128, kAChunk)};
-                uint32_t dgp = k0;                // dg_ready phases consumed
+                const uint64_t d_actk0 = umma_desc(smem_u32(S.act[0]), kAChunk, 128);          // stage s: desc_adv(.., s * stage bytes)
+                const uint64_t d_actm0 = umma_desc(smem_u32(S.act[0]), 128, kAChunk);
+                constexpr uint32_t kStageSmem = C::kStageChunks * kAChunk;
+                uint32_t dgp = k0, gfp = k0;      // dg_ready / g_free phases consumed (T of each per tile)
+                auto issue_g = [&](const uint32_t k) {
+                    const uint32_t s = k % kBwdStages, u = k / kBwdStages;
+                    mbar_wait(&S.act_full[s], u & 1);
+                    tc_fence_after();
+                    const uint64_t da = desc_adv(d_actk0, s * kStageSmem);
+#pragma unroll
+                    for (int ks = 0; ks < C::kStageChunks / 2; ++ks)
+                        if (leader) umma_bf16(tm_g, desc_adv(da, 2 * ks * kAChunk), desc_adv(d_bg, 2 * ks * kBChunk), ks == 0 ? 0u : 1u);
+                    if (leader) umma_commit(&S.g_full);
+                };
+                issue_g(k0);                      // G(T-1)
                 for (int i = 0; i <= T; ++i) {
-                    const uint32_t sp = (k0 + i - 1) & 1;
+                    const uint32_t sp = (k0 + i - 1) % kBwdStages;
                     if (i >= 1) {
                         mbar_wait(&S.dg_ready, dgp & 1);
                         ++dgp;
@@ -467,18 +492,9 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                             if (leader) umma_bf16_i(tm_r, desc_adv(d_dgk, 2 * ks * kAChunk), desc_adv(d_br, 2 * ks * C::kNR * 16), kIdescR,
                                         ks == 0 ? 0u : 1u);
                     }
-                    if (i < T) {
-                        const uint32_t k = k0 + i, s = k & 1, u = k >> 1;
-                        mbar_wait(&S.act_full[s], u & 1);
-                        tc_fence_after();
-                        const uint64_t da = d_actk[s];
-#pragma unroll
-                        for (int ks = 0; ks < C::kStageChunks / 2; ++ks)
-                            if (leader) umma_bf16(tm_g, desc_adv(da, 2 * ks * kAChunk), desc_adv(d_bg, 2 * ks * kBChunk), ks == 0 ? 0u : 1u);
-                    }
-                    if (leader) umma_commit(&S.g_full);        // R(prev) and G(cur) done; i == T: tail (R only)
+                    if (leader) umma_commit(&S.r_full);        // R(t+1) done (i == 0: nothing pending)
                     if (i >= 1) {
-                        const uint64_t db = d_actm[sp];
+                        const uint64_t db = desc_adv(d_actm0, sp * kStageSmem);
 #pragma unroll
                         for (int ks = 0; ks < (HALF ? 4 : 8); ++ks) {          // half tiles: rows 64..127 are copies
                             const uint32_t acc = (first_w && ks == 0) ? 0u : 1u;
@@ -489,6 +505,12 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                         first_w = false;
                         if (leader) umma_commit(&S.act_free[sp]);
                         if (leader) umma_commit(&S.w_done);
+                    }
+                    if (i < T) {
+                        mbar_wait(&S.g_free, gfp & 1);         // the epilogue has read G(t) out of TMEM
+                        ++gfp;
+                        tc_fence_after();
+                        if (i + 1 < T) issue_g(k0 + i + 1);    // G(t-1)
                     }
                 }
             }
@@ -541,10 +563,20 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                 float cp[kU], dh[kU];
                 if (i < T && head) {
                     // head backward fused here: the loads and the exchange overlap the tensor pipe's R/G of this step
+                    // h_t: step t+1's stage holds it as h_{(t+1)-1} (already in shared memory: no global-load latency at the
+                    // top of the step); only the first step of a tile reads it from HBM
                     uint4 hp[kNB];
+                    if (i == 0) {
 #pragma unroll
-                    for (int bb = 0; bb < kNB; ++bb)
-                        hp[bb] = *reinterpret_cast<const uint4*>(h + ((((int64_t)t * ntiles + tile) * 6 + blk0 + bb) * kRows + row) * 8);
+                        for (int bb = 0; bb < kNB; ++bb)
+                            hp[bb] = *reinterpret_cast<const uint4*>(h + ((((int64_t)t * ntiles + tile) * 6 + blk0 + bb) * kRows + row) * 8);
+                    } else {
+                        const uint32_t kp = k0 + i - 1, sp = kp % kBwdStages;
+                        mbar_wait(&S.act_full[sp], (kp / kBwdStages) & 1);          // completed long ago: acquires the TMA's writes
+#pragma unroll
+                        for (int bb = 0; bb < kNB; ++bb)
+                            hp[bb] = *reinterpret_cast<const uint4*>(S.act[sp] + (C::kHprevChunk + blk0 + bb) * kAChunk + row * 16);
+                    }
 #pragma unroll
                     for (int j = 0; j < kU; j += 4) {
                         float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -561,6 +593,7 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                     float sp = 0.f, gp = 0.f;
 #pragma unroll
                     for (int j = 0; j < kU; ++j) { sp = fmaf(S.wa[u0 + j], hv[j], sp); gp = fmaf(dzr[j], hv[j], gp); }
+                    if (i >= 1) mbar_arrive(&S.act_free[(k0 + i - 1) % kBwdStages]);          // this thread is done with the stage
                     S.xch[i & 1][hf][row] = make_float2(sp, gp);
                     named_bar_sync(xbar, xcnt);
                     float xs = 0.f, xg = 0.f;
@@ -591,8 +624,44 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
                         cp[j] = c4.x; cp[j + 1] = c4.y; cp[j + 2] = c4.z; cp[j + 3] = c4.w;
                     }
                 }
-                mbar_wait(&S.g_full, gphase & 1);
-                ++gphase;
+                // ---- phase A (does not need dh_rec): the gates of step t have been in TMEM since the previous epilogue; everything
+                // of the first unit block that does not depend on dh -- the five activations and the products around them --
+                // is evaluated while the tensor pipe runs R(t+1).  po = dh A,  dct = dh Bc + dc,  (pi, pf, pg) = dct (Ci, Cf, Cg)
+                // (half tiles only: with 16 cells per thread the 48 coefficients do not fit the 128-register budget)
+                constexpr bool kPre = HALF;
+                float cA[8], cB[8], cI[8], cF[8], cG[8], cGf[8];
+                if (kPre && i < T) {
+                    mbar_wait(&S.g_full, gphase & 1);
+                    ++gphase;
+                    tc_fence_after();
+                    uint32_t v[32];
+                    tmem_ld32(tm_g + lane_base + blk0 * 32, v);
+                    if (kNB == 1) {                                       // this thread's gates are in registers: G(t-1) may overwrite
+                        tc_fence_before();
+                        mbar_arrive(&S.g_free);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float gi = sigmoid_apx(__uint_as_float(v[u]));
+                        const float gf = sigmoid_apx(__uint_as_float(v[8 + u]));
+                        const float gg = tanh_apx(__uint_as_float(v[16 + u]));
+                        const float go = sigmoid_apx(__uint_as_float(v[24 + u]));
+                        const float tcv = tanh_apx(ccur[u]);
+                        cA[u] = tcv * (go * (1.0f - go));
+                        cB[u] = go * (1.0f - tcv * tcv);
+                        cI[u] = gg * (gi * (1.0f - gi));
+                        cF[u] = cp[u] * (gf * (1.0f - gf));
+                        cG[u] = gi * (1.0f - gg * gg);
+                        cGf[u] = gf;
+                        ccur[u] = cp[u];                                  // c_{t-1} is next iteration's c_t
+                    }
+                }
+                mbar_wait(&S.r_full, rphase & 1);
+                ++rphase;
+                if (!kPre && i < T) {
+                    mbar_wait(&S.g_full, gphase & 1);
+                    ++gphase;
+                }
                 tc_fence_after();
                 if (KI == 48 && i >= 1) {
                     // din of step t+1 = D_R[:, 0:48] * mask * scale  -> dh_out of the layer below
@@ -613,11 +682,13 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
 #pragma unroll
                             for (int u = 0; u < 8; ++u) o[u] = __uint_as_float(r[u]);
                         }
+                        // (deferring these stores until after the fence + arrive below costs registers: 1.31 -> 1.80 ms, measured)
                         st_global_v4f(din + tcl32_off(t + 1, ntiles, tile, 2 * blk, row), o[0], o[1], o[2], o[3]);
                         st_global_v4f(din + tcl32_off(t + 1, ntiles, tile, 2 * blk + 1, row), o[4], o[5], o[6], o[7]);
                     }
                 }
                 if (i == T) {                                             // tail: all W of this tile must be done
+                    if (head) mbar_arrive(&S.act_free[(k0 + T - 1) % kBwdStages]);  // keeps the stage's arrival count (no h to read)
                     mbar_wait(&S.w_done, wphase & 1);
                     ++wphase;
                     break;
@@ -625,35 +696,62 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
 #pragma unroll
                 for (int bb = 0; bb < kNB; ++bb) {
                     const int blk = blk0 + bb;
-                    uint32_t v[32];
-                    tmem_ld32(tm_g + lane_base + blk * 32, v);
-                    if (i >= 1) {
-                        uint32_t r[8];
-                        tmem_ld8(tm_r + lane_base + C::kRecCol + blk * 8, r);
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) dh[bb * 8 + u] += __uint_as_float(r[u]);
-                    }
                     float pi[8], pf[8], pg[8], po[8];
+                    if (kPre && bb == 0) {
+                        // ---- phase B of the first block: only the products with dh_t = dh_out_t + dh_rec are left ----
+                        if (i >= 1) {
+                            uint32_t r[8];
+                            tmem_ld8(tm_r + lane_base + C::kRecCol + blk * 8, r);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int j = bb * 8 + u;
-                        const float gi = sigmoid_apx(__uint_as_float(v[u]));
-                        const float gf = sigmoid_apx(__uint_as_float(v[8 + u]));
-                        const float gg = tanh_apx(__uint_as_float(v[16 + u]));
-                        const float go = sigmoid_apx(__uint_as_float(v[24 + u]));
-                        const float tcv = tanh_apx(ccur[j]);
-                        const float d_o = dh[j] * tcv;
-                        const float dct = fmaf(dh[j] * go, 1.0f - tcv * tcv, dc[j]);
-                        dc[j] = dct * gf;
-                        pi[u] = dct * gg * gi * (1.0f - gi);
-                        pf[u] = dct * cp[j] * gf * (1.0f - gf);
-                        pg[u] = dct * gi * (1.0f - gg * gg);
-                        po[u] = d_o * go * (1.0f - go);
-                        ccur[j] = cp[j];                                  // c_{t-1} is next iteration's c_t
-                    }
-                    if (bb == 0 && i >= 1) {                              // W of the previous step still reads d(gates)
-                        mbar_wait(&S.w_done, wphase & 1);
-                        ++wphase;
+                            for (int u = 0; u < 8; ++u) dh[u] += __uint_as_float(r[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float dct = fmaf(dh[u], cB[u], dc[u]);
+                            po[u] = dh[u] * cA[u];
+                            dc[u] = dct * cGf[u];
+                            pi[u] = dct * cI[u];
+                            pf[u] = dct * cF[u];
+                            pg[u] = dct * cG[u];
+                        }
+                        if (i >= 1) {                                     // W of the previous step still reads d(gates)
+                            mbar_wait(&S.w_done, wphase & 1);
+                            ++wphase;
+                        }
+                    } else {
+                        uint32_t v[32];
+                        tmem_ld32(tm_g + lane_base + blk * 32, v);
+                        if (i >= 1) {
+                            uint32_t r[8];
+                            tmem_ld8(tm_r + lane_base + C::kRecCol + blk * 8, r);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) dh[bb * 8 + u] += __uint_as_float(r[u]);
+                        }
+                        if (bb == kNB - 1) {                              // this thread's gates are in registers: G(t-1) may overwrite
+                            tc_fence_before();
+                            mbar_arrive(&S.g_free);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int j = bb * 8 + u;
+                            const float gi = sigmoid_apx(__uint_as_float(v[u]));
+                            const float gf = sigmoid_apx(__uint_as_float(v[8 + u]));
+                            const float gg = tanh_apx(__uint_as_float(v[16 + u]));
+                            const float go = sigmoid_apx(__uint_as_float(v[24 + u]));
+                            const float tcv = tanh_apx(ccur[j]);
+                            const float d_o = dh[j] * tcv;
+                            const float dct = fmaf(dh[j] * go, 1.0f - tcv * tcv, dc[j]);
+                            dc[j] = dct * gf;
+                            pi[u] = dct * gg * gi * (1.0f - gi);
+                            pf[u] = dct * cp[j] * gf * (1.0f - gf);
+                            pg[u] = dct * gi * (1.0f - gg * gg);
+                            po[u] = d_o * go * (1.0f - go);
+                            ccur[j] = cp[j];                              // c_{t-1} is next iteration's c_t
+                        }
+                        if (bb == 0 && i >= 1) {                          // W of the previous step still reads d(gates)
+                            mbar_wait(&S.w_done, wphase & 1);
+                            ++wphase;
+                        }
                     }
                     unsigned char* d4 = dgrow + (blk * 4) * kAChunk;
                     st_shared_v4(d4, pack_val(pi[0], pi[1]), pack_val(pi[2], pi[3]), pack_val(pi[4], pi[5]), pack_val(pi[6], pi[7]));
@@ -802,7 +900,7 @@ static int launch_bwd(const void* act_in, const void* h, const float* c, const f
                       float scale, float* din, float* partial, const float* dz, const float* stats, const float* zpool,
                       const float* attn_w, const float* attn_b, int64_t B, float* attn_partial, int64_t T, int64_t Bp,
                       cudaStream_t st, int* grid_out, int64_t half_stride) {
-    const size_t smem = sizeof(BwdSmem<KI>) + 1024;
+    const size_t smem = (half_stride > 0 ? sizeof(BwdSmem<KI, bwd_stages(KI, true)>) : sizeof(BwdSmem<KI, bwd_stages(KI, false)>)) + 1024;
     auto kern = half_stride > 0 ? lstm_bwd_bf16_kernel<KI, true> : lstm_bwd_bf16_kernel<KI, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "lstm_bwd_bf16: shared memory opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e));
