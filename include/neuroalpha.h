@@ -314,6 +314,7 @@ int na_head_tail_bwd_f32(const float* dlogits, const float* zpool, const float* 
  *   TCLX  fp16 [T][NT][12][128][8]   h split: chunks 0-5 hi (units 8c..8c+7), 6-11 lo
  *   TCL32 fp32 [T][NT][12][128][4]   cell state, din
  *   DGX   fp16 [T][NT][48][128][8]   d(gates) split: chunks 0-23 hi, 24-47 lo; column n = (j/4)*16 + gate*4 + j%4
+ *         (half tiles, half_stride > 0: [T][NT][48][64][8] -- only the 64 real window rows of a tile are stored)
  * `packed_x3` = na_decoder_pack_x3 output.  Inter-layer dropout as in the 16-bit tier: explicit u8 keep-mask [T][Bp][48]
  * or (mask NULL, thresh16 < 65536) the counter-based generator keyed by `seed`; thresh16 = 65536: none.
  *   na_lstm_fwd_train_x3  layer 0: in = XS -> h (TCLX), hd = h after dropout (TCLX, exactly when dropout is on), c;

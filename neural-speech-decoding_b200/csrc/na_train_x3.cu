@@ -25,6 +25,7 @@
 //   TCLX  fp16 [T][NT][12][128][8]    h split: chunks 0-5 = hi (units 8c..8c+7), 6-11 = lo
 //   TCL32 fp32 [T][NT][12][128][4]    c, din (thread = window reads / writes 16 B, coalesced)
 //   DGX   fp16 [T][NT][48][128][8]    d(gates) split: chunks 0-23 = hi, 24-47 = lo; column n = (j/4)*16 + gate*4 + j%4
+//         (half tiles: [T][NT][48][64][8] -- only the 64 real window rows of a tile are stored)
 #include "na_x3_common.cuh"
 
 namespace na {
@@ -43,6 +44,15 @@ __device__ __forceinline__ int64_t tcl32x_off(int t, int ntiles, int tile, int c
 }
 __device__ __forceinline__ int64_t dgx_off(int t, int ntiles, int tile, int chunk, int row) {        // fp16 elements
     return ((((int64_t)t * ntiles + tile) * 48 + chunk) * kRows + row) * 8;
+}
+// half tiles: only the 64 real window rows are stored ([T][NT][48][64][8]), so the weight-gradient kernel fetches a whole
+// column group with one bulk copy
+__device__ __forceinline__ int64_t dgx_half_off(int t, int ntiles, int tile, int chunk, int row) {   // fp16 elements
+    return ((((int64_t)t * ntiles + tile) * 48 + chunk) * 64 + row) * 8;
+}
+template <bool HALF>
+__device__ __forceinline__ int64_t dgx_any(int t, int ntiles, int tile, int chunk, int row) {
+    return HALF ? dgx_half_off(t, ntiles, tile, chunk, row) : dgx_off(t, ntiles, tile, chunk, row);
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -601,6 +611,7 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
                         float hv[kU];
 #pragma unroll
                         for (int pr = 0; pr < kNB; ++pr) {
+                            // (fetching h one step ahead into registers was measured: no gain, the step is bound by instruction issue)
                             const uint4 ph = *reinterpret_cast<const uint4*>(h + tclx_off(t, ntiles, tile, chunk0 + pr, row));
                             const uint4 pl = *reinterpret_cast<const uint4*>(h + tclx_off(t, ntiles, tile, 6 + chunk0 + pr, row));
                             const uint32_t wh[4] = {ph.x, ph.y, ph.z, ph.w}, wl[4] = {pl.x, pl.y, pl.z, pl.w};
@@ -639,10 +650,37 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
                         }
                     }
                 }
-                mbar_wait(&S.r_full, rphase & 1); ++rphase;
-                if (i < T) { mbar_wait(&S.g_full[i & 1], gph[i & 1] & 1); ++gph[i & 1]; }
-                tc_fence_after();
+                // ---- phase A (half tiles: registers to spare): the gates of step t have been in TMEM since the previous epilogue, so
+                // everything that does not depend on dh_rec -- the 5 ex2 + 2 rcp per cell and the products around them -- is
+                // evaluated while the tensor pipe runs R(t+1) (36 small MMAs: the epilogue warps were idle a third of the step).
+                //   po = dh cA,  dct = dh cB + dc,  dc' = dct cGf,  (pi, pf, pg) = dct (cI, cF c_{t-1}, cG)
+                constexpr bool kPre = HALF;
                 const uint32_t tm_g = tmem + (i & 1) * kN;
+                float cA[8], cB[8], cI[8], cF[8], cG[8], cGf[8];
+                if (kPre && i < T) {
+                    mbar_wait(&S.g_full[i & 1], gph[i & 1] & 1); ++gph[i & 1];
+                    tc_fence_after();
+                    uint32_t v[32];
+                    tmem_ld32(tm_g + lane_base + gr0 * 16, v);
+#pragma unroll
+                    for (int gi = 0; gi < 2; ++gi)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = gi * 4 + u;
+                            float a_i, a_f, a_g, a_o, tcv;
+                            gates_exact(__uint_as_float(v[gi * 16 + u]), __uint_as_float(v[gi * 16 + 4 + u]), __uint_as_float(v[gi * 16 + 8 + u]),
+                                        __uint_as_float(v[gi * 16 + 12 + u]), ccur[j], a_i, a_f, a_g, a_o, tcv);
+                            cA[j] = tcv * (a_o * (1.0f - a_o));
+                            cB[j] = a_o * (1.0f - tcv * tcv);
+                            cI[j] = a_g * (a_i * (1.0f - a_i));
+                            cF[j] = a_f * (1.0f - a_f);
+                            cG[j] = a_i * (1.0f - a_g * a_g);
+                            cGf[j] = a_f;
+                        }
+                }
+                mbar_wait(&S.r_full, rphase & 1); ++rphase;
+                if (!kPre && i < T) { mbar_wait(&S.g_full[i & 1], gph[i & 1] & 1); ++gph[i & 1]; }
+                tc_fence_after();
                 if (i >= 1) {
                     if (LAYER == 1) {
                         // din of step t+1 = D_R[:, 0:48] (x dropout mask x scale) -> dh_in of layer 0
@@ -680,23 +718,33 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
 #pragma unroll
                 for (int pr = 0; pr < kNB; ++pr) {
                     uint32_t v[32];
-                    tmem_ld32(tm_g + lane_base + (gr0 + 2 * pr) * 16, v);
+                    if (!kPre) tmem_ld32(tm_g + lane_base + (gr0 + 2 * pr) * 16, v);
 #pragma unroll
                     for (int gi = 0; gi < 2; ++gi) {
                         float pi[4], pf[4], pg[4], po[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int j = pr * 8 + gi * 4 + u;
-                            float a_i, a_f, a_g, a_o, tcv;
-                            gates_exact(__uint_as_float(v[gi * 16 + u]), __uint_as_float(v[gi * 16 + 4 + u]), __uint_as_float(v[gi * 16 + 8 + u]),
-                                        __uint_as_float(v[gi * 16 + 12 + u]), ccur[j], a_i, a_f, a_g, a_o, tcv);
-                            const float d_o = dh[j] * tcv;
-                            const float dct = fmaf(dh[j] * a_o, 1.0f - tcv * tcv, dc[j]);
-                            dc[j] = dct * a_f;
-                            pi[u] = dct * a_g * a_i * (1.0f - a_i);
-                            pf[u] = dct * cp[j] * a_f * (1.0f - a_f);
-                            pg[u] = dct * a_i * (1.0f - a_g * a_g);
-                            po[u] = d_o * a_o * (1.0f - a_o);
+                            if (kPre) {                                // phase B: only the products with dh_t are left
+                                const int jj = gi * 4 + u;             // (kNB == 1)
+                                const float dct = fmaf(dh[j], cB[jj], dc[j]);
+                                po[u] = dh[j] * cA[jj];
+                                dc[j] = dct * cGf[jj];
+                                pi[u] = dct * cI[jj];
+                                pf[u] = dct * (cp[j] * cF[jj]);
+                                pg[u] = dct * cG[jj];
+                            } else {
+                                float a_i, a_f, a_g, a_o, tcv;
+                                gates_exact(__uint_as_float(v[gi * 16 + u]), __uint_as_float(v[gi * 16 + 4 + u]), __uint_as_float(v[gi * 16 + 8 + u]),
+                                            __uint_as_float(v[gi * 16 + 12 + u]), ccur[j], a_i, a_f, a_g, a_o, tcv);
+                                const float d_o = dh[j] * tcv;
+                                const float dct = fmaf(dh[j] * a_o, 1.0f - tcv * tcv, dc[j]);
+                                dc[j] = dct * a_f;
+                                pi[u] = dct * a_g * a_i * (1.0f - a_i);
+                                pf[u] = dct * cp[j] * a_f * (1.0f - a_f);
+                                pg[u] = dct * a_i * (1.0f - a_g * a_g);
+                                po[u] = d_o * a_o * (1.0f - a_o);
+                            }
                             ccur[j] = cp[j];                           // c_{t-1} is the next iteration's c_t
                         }
                         // granule G -> columns 16 G .. 16 G + 15 = chunks 2 G ([i x4 | f x4]) and 2 G + 1 ([g x4 | o x4])
@@ -711,8 +759,8 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
                             st_shared_v4(S.dg + (2 * G) * kAChunk + (row ^ 64) * 16, hi[0], hi[1], hi[2], hi[3]);
                             st_shared_v4(S.dg + (24 + 2 * G) * kAChunk + (row ^ 64) * 16, lo[0], lo[1], lo[2], lo[3]);
                         }
-                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 2 * G, crow)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 24 + 2 * G, crow)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4*>(dg_out + dgx_any<HALF>(t, ntiles, tile, 2 * G, crow)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(dg_out + dgx_any<HALF>(t, ntiles, tile, 24 + 2 * G, crow)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         split_pack8(e1, hi, lo);
                         st_shared_v4(S.dg + (2 * G + 1) * kAChunk + row * 16, hi[0], hi[1], hi[2], hi[3]);
                         st_shared_v4(S.dg + (24 + 2 * G + 1) * kAChunk + row * 16, lo[0], lo[1], lo[2], lo[3]);
@@ -720,8 +768,8 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
                             st_shared_v4(S.dg + (2 * G + 1) * kAChunk + (row ^ 64) * 16, hi[0], hi[1], hi[2], hi[3]);
                             st_shared_v4(S.dg + (24 + 2 * G + 1) * kAChunk + (row ^ 64) * 16, lo[0], lo[1], lo[2], lo[3]);
                         }
-                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 2 * G + 1, crow)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4*>(dg_out + dgx_off(t, ntiles, tile, 24 + 2 * G + 1, crow)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4*>(dg_out + dgx_any<HALF>(t, ntiles, tile, 2 * G + 1, crow)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(dg_out + dgx_any<HALF>(t, ntiles, tile, 24 + 2 * G + 1, crow)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
                 tc_fence_before();
@@ -773,10 +821,16 @@ lstm_bwd_x3_kernel(const __half* __restrict__ act_in,               // L0: XS;  
 // weight gradients: dW^T[feature][gate column] = sum over (t, tile) of act^T . dG, both operands MN-major
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kWgThreads = 6 * 32;            // warps 0-3: final readout, 4: MMA issuer, 5: TMA producer
+// Stages of [128 feature rows x K window rows] (act) and [64 gate columns x K] (one d(gates) column group).  Half tiles keep only
+// the 64 real window rows of every chunk (1 KB instead of 2 KB), which buys twice the stages: with half-size stages and the same
+// depth the kernel was latency-bound (bytes in flight), not HBM-bound.
+template <bool HALF>
 struct TxWgSmem {
-    alignas(128) unsigned char act[2][32 * kAChunk];     // hi block = chunks 0..15, lo block = chunks 16..31 (see below)
-    alignas(128) unsigned char dg[2][16 * kAChunk];      // one 64-column group: hi x8 | lo x8
-    alignas(8) uint64_t act_full[2], act_empty[2], dg_full[2], dg_empty[2];
+    static constexpr int kChunkB = HALF ? kAChunk / 2 : kAChunk;
+    static constexpr int kSt = HALF ? 4 : 2;
+    alignas(128) unsigned char act[kSt][32 * kChunkB];   // hi block = chunks 0..15, lo block = chunks 16..31 (see below)
+    alignas(128) unsigned char dg[kSt][16 * kChunkB];    // one 64-column group: hi x8 | lo x8
+    alignas(8) uint64_t act_full[kSt], act_empty[kSt], dg_full[kSt], dg_empty[kSt];
     uint64_t done;
     uint32_t tmem_base;
 };
@@ -791,21 +845,23 @@ lstm_wgrad_x3_kernel(const __half* __restrict__ dg,       // DGX
                      const __half* __restrict__ zeros,
                      float* __restrict__ partial,         // [grid][128][192]
                      int T, int ntiles) {
+    using SM = TxWgSmem<HALF>;
+    constexpr int kCB = SM::kChunkB, kSt = SM::kSt, kKRows = HALF ? 64 : kRows;
     constexpr int kInC = LAYER == 0 ? 1 : 6;              // hi chunks of the input
     constexpr int kOnesChunk = kInC + 6;
     constexpr uint32_t kIdescW = make_idesc(64, kFmtVal, kFmtVal, true, true);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    TxWgSmem& S = *reinterpret_cast<TxWgSmem*>(smem_raw);
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     {
         const uint4 ones = make_uint4(kValOnes2 & 0xFFFFu, 0u, 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);   // {1, 0, 0, ...}: one bias row
-        for (int i = tid; i < 2 * 32 * kRows; i += kWgThreads) {
-            const int s = i / (32 * kRows), ch = (i / kRows) % 32, r = i % kRows;
-            reinterpret_cast<uint4*>(S.act[s] + ch * kAChunk)[r] = ch == kOnesChunk ? ones : zero;
+        for (int i = tid; i < kSt * 32 * kKRows; i += kWgThreads) {
+            const int s = i / (32 * kKRows), ch = (i / kKRows) % 32, r = i % kKRows;
+            reinterpret_cast<uint4*>(S.act[s] + ch * kCB)[r] = ch == kOnesChunk ? ones : zero;
         }
         if (tid == 0) {
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < kSt; ++s) {
                 mbar_init(&S.act_full[s], 1); mbar_init(&S.act_empty[s], 1);
                 mbar_init(&S.dg_full[s], 1); mbar_init(&S.dg_empty[s], 1);
             }
@@ -821,12 +877,45 @@ lstm_wgrad_x3_kernel(const __half* __restrict__ dg,       // DGX
     const uint32_t tmem = __shfl_sync(0xffffffffu, S.tmem_base, 0);
     const int64_t nitems = (int64_t)T * ntiles;
     if (warp == 5) {
-        if (lane == 0) {
+        if constexpr (HALF) {
+            // half tiles: only rows 0..63 of every chunk carry windows (and only those were written by the backward kernel), so
+            // the first 1 KB of each 2 KB chunk is fetched -- one bulk copy per chunk, spread over the lanes of this warp
+            uint32_t k = 0, gk = 0;
+            constexpr int kNAct = 2 * kInC + 12;
+            for (int64_t w = blockIdx.x; w < nitems; w += gridDim.x, ++k) {
+                const int t = (int)(w / ntiles), tile = (int)(w % ntiles);
+                const uint32_t a = k % kSt;
+                if (lane == 0) {
+                    mbar_wait(&S.act_empty[a], ((k / kSt) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&S.act_full[a], kNAct * kCB);
+                }
+                __syncwarp();
+                const __half* isrc = act_in + (((int64_t)t * ntiles + tile) * (2 * kInC)) * (kAChunk / 2);
+                const __half* hsrc = t > 0 ? h + tclx_off(t - 1, ntiles, tile, 0, 0) : zeros;
+                if (lane < kNAct) {
+                    const int c = lane;                                    // source chunk: [in hi | in lo | h hi x6 | h lo x6]
+                    const bool is_in = c < 2 * kInC;
+                    const int cc = is_in ? c : c - 2 * kInC;               // chunk inside its slab
+                    const bool lo = is_in ? cc >= kInC : cc >= 6;
+                    const int dst = (lo ? 16 : 0) + (is_in ? (lo ? cc - kInC : cc) : kInC + (lo ? cc - 6 : cc));
+                    bulk_load(S.act[a] + dst * kCB, (is_in ? isrc : hsrc) + cc * (kAChunk / 2), kCB, &S.act_full[a]);
+                }
+                for (int g = 0; g < 3; ++g, ++gk) {
+                    const uint32_t r = gk % kSt;
+                    if (lane == 0) {
+                        mbar_wait(&S.dg_empty[r], ((gk / kSt) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&S.dg_full[r], 16 * kCB);
+                        bulk_load(S.dg[r], dg + dgx_half_off(t, ntiles, tile, 8 * g, 0), 8 * kCB, &S.dg_full[r]);
+                        bulk_load(S.dg[r] + 8 * kCB, dg + dgx_half_off(t, ntiles, tile, 24 + 8 * g, 0), 8 * kCB, &S.dg_full[r]);
+                    }
+                }
+            }
+        } else if (lane == 0) {   // (if constexpr: the full-size stage offsets below do not exist in the half-tile layout)
             uint32_t k = 0, gk = 0;
             for (int64_t w = blockIdx.x; w < nitems; w += gridDim.x, ++k) {
                 const int t = (int)(w / ntiles), tile = (int)(w % ntiles);
-                const uint32_t a = k & 1;
-                mbar_wait(&S.act_empty[a], ((k >> 1) & 1) ^ 1);
+                const uint32_t a = k % kSt;
+                mbar_wait(&S.act_empty[a], ((k / kSt) & 1) ^ 1);
                 mbar_arrive_expect_tx(&S.act_full[a], (2 * kInC + 12) * kAChunk);
                 const __half* isrc = act_in + (((int64_t)t * ntiles + tile) * (2 * kInC)) * (kAChunk / 2);
                 bulk_load(S.act[a], isrc, kInC * kAChunk, &S.act_full[a]);
@@ -835,8 +924,8 @@ lstm_wgrad_x3_kernel(const __half* __restrict__ dg,       // DGX
                 bulk_load(S.act[a] + kInC * kAChunk, hsrc, 6 * kAChunk, &S.act_full[a]);
                 bulk_load(S.act[a] + (16 + kInC) * kAChunk, hsrc + 6 * (kAChunk / 2), 6 * kAChunk, &S.act_full[a]);
                 for (int g = 0; g < 3; ++g, ++gk) {
-                    const uint32_t r = gk & 1;
-                    mbar_wait(&S.dg_empty[r], ((gk >> 1) & 1) ^ 1);
+                    const uint32_t r = gk % kSt;
+                    mbar_wait(&S.dg_empty[r], ((gk / kSt) & 1) ^ 1);
                     mbar_arrive_expect_tx(&S.dg_full[r], 16 * kAChunk);
                     bulk_load(S.dg[r], dg + dgx_off(t, ntiles, tile, 8 * g, 0), 8 * kAChunk, &S.dg_full[r]);
                     bulk_load(S.dg[r] + 8 * kAChunk, dg + dgx_off(t, ntiles, tile, 24 + 8 * g, 0), 8 * kAChunk, &S.dg_full[r]);
@@ -845,22 +934,24 @@ lstm_wgrad_x3_kernel(const __half* __restrict__ dg,       // DGX
         }
     } else if (warp == 4) {
         const bool leader = elect_one();
-        const uint64_t d_act[2] = {umma_desc(smem_u32(S.act[0]), 128, kAChunk), umma_desc(smem_u32(S.act[1]), 128, kAChunk)};
-        const uint64_t d_dg[2] = {umma_desc(smem_u32(S.dg[0]), 128, kAChunk), umma_desc(smem_u32(S.dg[1]), 128, kAChunk)};
+        const uint64_t d_act0 = umma_desc(smem_u32(S.act[0]), 128, kCB);      // MN-major: chunk (8 feature rows) stride = kCB
+        const uint64_t d_dg0 = umma_desc(smem_u32(S.dg[0]), 128, kCB);
         uint32_t k = 0, gk = 0;
         for (int64_t w = blockIdx.x; w < nitems; w += gridDim.x, ++k) {
-            const uint32_t a = k & 1;
-            mbar_wait(&S.act_full[a], (k >> 1) & 1);
+            const uint32_t a = k % kSt;
+            mbar_wait(&S.act_full[a], (k / kSt) & 1);
+            const uint64_t d_act = desc_adv(d_act0, a * 32 * kCB);
             for (int g = 0; g < 3; ++g, ++gk) {
-                const uint32_t r = gk & 1;
-                mbar_wait(&S.dg_full[r], (gk >> 1) & 1);
+                const uint32_t r = gk % kSt;
+                mbar_wait(&S.dg_full[r], (gk / kSt) & 1);
                 tc_fence_after();
                 const uint32_t td = tmem + 64 * g;
+                const uint64_t d_dg = desc_adv(d_dg0, r * 16 * kCB);
 #pragma unroll
                 for (int ks = 0; ks < (HALF ? 4 : 8); ++ks)
                     if (leader) {
-                        const uint64_t ahi = desc_adv(d_act[a], ks * 256), alo = desc_adv(d_act[a], 16 * kAChunk + ks * 256);
-                        const uint64_t bhi = desc_adv(d_dg[r], ks * 256), blo = desc_adv(d_dg[r], 8 * kAChunk + ks * 256);
+                        const uint64_t ahi = desc_adv(d_act, ks * 256), alo = desc_adv(d_act, 16 * kCB + ks * 256);
+                        const uint64_t bhi = desc_adv(d_dg, ks * 256), blo = desc_adv(d_dg, 8 * kCB + ks * 256);
                         umma_bf16_i(td, ahi, bhi, kIdescW, (k == 0 && ks == 0) ? 0u : 1u);
                         umma_bf16_i(td, ahi, blo, kIdescW, 1u);
                         umma_bf16_i(td, alo, bhi, kIdescW, 1u);
@@ -909,7 +1000,7 @@ __global__ void reduce_dw_x3_kernel(const float* __restrict__ partial, int npart
 
 static_assert(sizeof(TxFwdSmem<0>) <= 232448 && sizeof(TxFwdSmem<1>) <= 232448, "forward: shared memory budget (227 KB)");
 static_assert(sizeof(TxBwdSmem<0>) <= 232448 && sizeof(TxBwdSmem<1>) <= 232448, "backward: shared memory budget (227 KB)");
-static_assert(sizeof(TxWgSmem) <= 232448, "weight gradients: shared memory budget (227 KB)");
+static_assert(sizeof(TxWgSmem<false>) <= 232448 && sizeof(TxWgSmem<true>) <= 232448, "weight gradients: shared memory budget (227 KB)");
 
 static int tx_sms() {
     static int sms = 0;
@@ -983,7 +1074,7 @@ extern "C" int64_t na_train_x3_smem_bytes(int64_t which) {     // 0/1: forward L
         case 1: return sizeof(na::tc::TxFwdSmem<1>);
         case 2: return sizeof(na::tc::TxBwdSmem<0>);
         case 3: return sizeof(na::tc::TxBwdSmem<1>);
-        default: return sizeof(na::tc::TxWgSmem);
+        default: return sizeof(na::tc::TxWgSmem<true>) > sizeof(na::tc::TxWgSmem<false>) ? sizeof(na::tc::TxWgSmem<true>) : sizeof(na::tc::TxWgSmem<false>);
     }
 }
 
@@ -1053,7 +1144,7 @@ extern "C" int na_lstm_wgrad_x3(int64_t layer, const void* dg, const void* act_i
     const int64_t nitems = T * ntiles;
     const int grid = (int)(nitems < tc::tx_sms() ? nitems : tc::tx_sms());
     float* partial = scratch + (size_t)tc::tx_sms() * 52;
-    const size_t smem = sizeof(tc::TxWgSmem);
+    const size_t smem = half_stride > 0 ? sizeof(tc::TxWgSmem<true>) : sizeof(tc::TxWgSmem<false>);
 #define NA_X3_WG(L, HF)                                                                                                               \
     {                                                                                                                                \
         cudaError_t e = cudaFuncSetAttribute(tc::lstm_wgrad_x3_kernel<L, HF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
