@@ -58,6 +58,11 @@ int64_t na_launch_count(void);
 /* Tuning / test knobs (process-global, not thread-safe; set before launching work):
  *   "lstm_tier"  0 = auto (specialised H=48 kernels when the shape allows), 1 = generic tier only
  *   "h48_groups" 0 = auto, 1..4 = groups (32-window tiles) resident per CTA in the H=48 kernels
+ *   "tc_infer_hs" / "tc_infer_rep" / "tc_train_fwd_v2" / "tc_wide_dbg" / "tc_wide_cluster"   A/B switches of the 16-bit tier
+ *   "tc_infer_tanh_fma", "x3_rcp_fma"   MUFU -> FMA-pipe offloads (default 0: measured slower)
+ *   "iir_occ3"        1 = three CTAs per SM in na_iir_chain (default 0 = two)
+ *   "train_max_ctas"  test knob: caps the grid of the persistent tensor-core training kernels (0 = one CTA per SM), so that
+ *                     small batches exercise the several-tiles-per-CTA paths; scratch sizes ignore it
  */
 int na_set_tuning(const char* key, int64_t value);
 

@@ -19,6 +19,8 @@ int fail(int code, const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static int g_train_max_ctas = 0;
+int train_grid_cap(int grid) { return (g_train_max_ctas > 0 && g_train_max_ctas < grid) ? g_train_max_ctas : grid; }
 
 int check_launch(const char* what) {
     const cudaError_t e = cudaGetLastError();
@@ -113,6 +115,7 @@ extern "C" int na_set_tuning(const char* key, int64_t value) {
     if (!strcmp(key, "tc_infer_tanh_fma")) { tc::set_infer_tanh_fma((int)value); return NA_OK; }
     if (!strcmp(key, "x3_rcp_fma")) { tc::set_x3_rcp_fma((int)value); return NA_OK; }
     if (!strcmp(key, "iir_occ3")) { set_iir_occ3((int)value); return NA_OK; }
+    if (!strcmp(key, "train_max_ctas")) { g_train_max_ctas = (int)value; return NA_OK; }
     if (!strcmp(key, "tc_wide_cluster")) { tc::set_wide_cluster((int)value); return NA_OK; }
     return fail(NA_EINVAL, "na_set_tuning: unknown key '%s'", key);
 }

@@ -14,6 +14,9 @@ namespace na {
 char* err_buf();
 int fail(int code, const char* fmt, ...);
 void count_launch(int n = 1);
+// test knob (na_set_tuning "train_max_ctas"): caps the grid of the persistent training kernels so that small batches exercise
+// the several-tiles-per-CTA paths (running mbarrier phases across tiles); 0 = one CTA per SM.  Scratch sizes ignore it.
+int train_grid_cap(int grid);
 int check_launch(const char* what);   // cudaGetLastError -> code + message
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

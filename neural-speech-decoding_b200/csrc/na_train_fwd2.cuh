@@ -356,7 +356,7 @@ int launch_train_fwd_v2(const void* x, const unsigned char* packed_v2, const uns
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "na_lstm2_fwd_train_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
     const int ntiles = (int)(Bp / kRows);
-    const int grid = ntiles < sms ? ntiles : sms;
+    const int grid = train_grid_cap(ntiles < sms ? ntiles : sms);
     kern<<<grid, kV2Threads, smem, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), packed_v2, mask, seed, thresh16, drop_scale, reinterpret_cast<__nv_bfloat16*>(h0),
         reinterpret_cast<__nv_bfloat16*>(h0d), c0, reinterpret_cast<__nv_bfloat16*>(h1), c1, attn_w, attn_b, zpool, stats, B, T, Bp, ntiles,

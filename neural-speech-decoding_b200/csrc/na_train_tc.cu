@@ -905,7 +905,7 @@ static int launch_bwd(const void* act_in, const void* h, const float* c, const f
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "lstm_bwd_bf16: shared memory opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e));
     const int ntiles = (int)(Bp / kRows);
-    const int grid = ntiles < tc_sms() ? ntiles : tc_sms();
+    const int grid = train_grid_cap(ntiles < tc_sms() ? ntiles : tc_sms());
     *grid_out = grid;
     kern<<<grid, kBwdThreads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(act_in), reinterpret_cast<const __nv_bfloat16*>(h),
                                           c, dh_out, reinterpret_cast<const unsigned char*>(packed_g),
@@ -961,7 +961,7 @@ extern "C" int na_lstm2_fwd_train_bf16(const void* x_bf16_tmp, const void* packe
     cudaError_t e = cudaFuncSetAttribute(tc::lstm2_fwd_train_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "na_lstm2_fwd_train_bf16: shared memory opt-in failed (%s)", cudaGetErrorString(e));
     const int ntiles = (int)(Bp / tc::kRows);
-    const int grid = ntiles < tc::tc_sms() ? ntiles : tc::tc_sms();
+    const int grid = train_grid_cap(ntiles < tc::tc_sms() ? ntiles : tc::tc_sms());
     tc::lstm2_fwd_train_bf16_kernel<<<grid, tc::kTrainThreads, smem, as_stream(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(x_bf16_tmp), reinterpret_cast<const unsigned char*>(packed), mask, seed,
         (uint32_t)thresh16, drop_scale,

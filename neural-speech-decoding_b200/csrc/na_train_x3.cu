@@ -1047,7 +1047,7 @@ extern "C" int na_lstm_fwd_train_x3(int64_t layer, const void* in, const void* p
     NA_REQUIRE(layer == 0 || (attn_w && attn_b && zpool && stats && B >= 1 && B <= Bp), NA_EINVAL,
                "na_lstm_fwd_train_x3: layer 1 needs attn_w, attn_b, zpool, stats and 1 <= B <= Bp");
     const int ntiles = (int)(Bp / tc::kRows);
-    const int grid = ntiles < tc::tx_sms() ? ntiles : tc::tx_sms();
+    const int grid = train_grid_cap(ntiles < tc::tx_sms() ? ntiles : tc::tx_sms());
     const unsigned char* pk = reinterpret_cast<const unsigned char*>(packed_x3) + (layer == 0 ? 0 : tc::kX3B0Chunks * tc::kBChunk);
     const int64_t dstride = half_stride > 0 ? half_stride : Bp;
 #define NA_X3_FWD(L, HF)                                                                                                              \
@@ -1104,7 +1104,7 @@ extern "C" int na_lstm_bwd_x3(int64_t layer, const void* act_in, const void* h, 
     NA_REQUIRE(thresh16 >= 0 && thresh16 <= 65536, NA_EINVAL, "na_lstm_bwd_x3: thresh16 outside [0,65536]");
     cudaStream_t st = as_stream(stream);
     const int ntiles = (int)(Bp / tc::kRows);
-    const int grid = ntiles < tc::tx_sms() ? ntiles : tc::tx_sms();
+    const int grid = train_grid_cap(ntiles < tc::tx_sms() ? ntiles : tc::tx_sms());
     const unsigned char* pk = reinterpret_cast<const unsigned char*>(packed_x3) + (layer == 0 ? 0 : tc::kX3B0Chunks * tc::kBChunk);
     float* attn_partial = scratch;
     const int64_t dstride = half_stride > 0 ? half_stride : Bp;
@@ -1142,7 +1142,7 @@ extern "C" int na_lstm_wgrad_x3(int64_t layer, const void* dg, const void* act_i
     cudaStream_t st = as_stream(stream);
     const int ntiles = (int)(Bp / tc::kRows);
     const int64_t nitems = T * ntiles;
-    const int grid = (int)(nitems < tc::tx_sms() ? nitems : tc::tx_sms());
+    const int grid = train_grid_cap((int)(nitems < tc::tx_sms() ? nitems : tc::tx_sms()));
     float* partial = scratch + (size_t)tc::tx_sms() * 52;
     const size_t smem = half_stride > 0 ? sizeof(tc::TxWgSmem<true>) : sizeof(tc::TxWgSmem<false>);
 #define NA_X3_WG(L, HF)                                                                                                               \

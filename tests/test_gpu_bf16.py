@@ -395,6 +395,41 @@ def test_bf16_training_half_tiles_match_full_tiles(dev, checkpoint, B, T):
         ops.TC_HALF_TILES = True
 
 
+@pytest.mark.parametrize("half", [True, False])
+@pytest.mark.parametrize("B,T", [(700, 34), (390, 41)])
+def test_bf16_training_several_tiles_per_cta(dev, checkpoint, B, T, half):
+    """The persistent training kernels with SEVERAL tiles per CTA (grid capped to 2 CTAs by the `train_max_ctas` test knob: the
+    running mbarrier phases, the 2- / 3-stage TMA ring and the dW accumulators carry over from tile to tile) against one tile
+    per CTA: bit-identical logits, gradients equal up to the order of the fp32 weight-gradient accumulation; eval and train
+    mode (in-kernel dropout), full and half tiles, T not a multiple of the stage count."""
+    from neural_speech_decoding_b200 import _lib, ops
+    gen = torch.Generator(device="cpu").manual_seed(B + T)
+    x = (torch.randn(B, T, 8, generator=gen) * 2.73).to(dev)
+    y = torch.randint(0, 3, (B,), generator=gen).to(dev)
+    m = bf16_model(dev, checkpoint)
+    def run(cap, train):
+        _lib.call("na_set_tuning", b"train_max_ctas", cap)
+        m.train(train)
+        m.zero_grad()
+        torch.manual_seed(77)
+        out = m(x)
+        torch.nn.functional.cross_entropy(out, y).backward()
+        return out.detach().clone(), [p.grad.clone() for p in m.parameters()]
+    saved = ops.TC_HALF_TILES
+    try:
+        ops.TC_HALF_TILES = half
+        for train in (False, True):
+            a, ga = run(2, train)
+            b, gb = run(0, train)
+            assert torch.isfinite(a).all() and torch.equal(a, b), (train, (a - b).abs().max().item())
+            gmax = max(float(q.abs().max()) for q in gb)
+            for (k, _), p, q in zip(m.named_parameters(), ga, gb):
+                assert (p - q).abs().max().item() <= 2e-5 * gmax, (train, k, (p - q).abs().max().item(), gmax)
+    finally:
+        _lib.call("na_set_tuning", b"train_max_ctas", 0)
+        ops.TC_HALF_TILES = saved
+
+
 # ---------------------------------------------------------------------------------------------
 # wide decoders: training on the tensor cores (streamed-weight recurrence kernels + cuBLAS, csrc/na_wide_train.cu)
 # ---------------------------------------------------------------------------------------------

@@ -652,3 +652,39 @@ def test_exact_tc_training_half_tiles_match_full_tiles(dev, checkpoint, B, T):
                 assert (p - q).abs().max().item() <= 1e-5 * gmax, (train, k, (p - q).abs().max().item(), gmax)
     finally:
         ops.X3_HALF_TILES = saved
+
+
+@pytest.mark.parametrize("half", [True, False])
+@pytest.mark.parametrize("B,T", [(700, 19), (390, 26)])
+def test_exact_tc_training_several_tiles_per_cta(dev, checkpoint, B, T, half):
+    """Exact tensor-core training tier with SEVERAL tiles / work items per CTA (grid capped to 2 CTAs by the `train_max_ctas`
+    test knob: running mbarrier phases and both gate accumulators carry over from tile to tile) against one tile per CTA:
+    bit-identical logits, gradients equal up to the order of the fp32 weight-gradient accumulation."""
+    from neural_speech_decoding_b200 import _lib, ops
+    gen = torch.Generator(device="cpu").manual_seed(B + T)
+    x = (torch.randn(B, T, 8, generator=gen) * 2.73).to(dev)
+    y = torch.randint(0, 3, (B,), generator=gen).to(dev)
+    m = make_model(dev, checkpoint)
+    saved = ops.X3_HALF_TILES
+    def run(cap, train):
+        _lib.call("na_set_tuning", b"train_max_ctas", cap)
+        m.train(train)
+        m.zero_grad()
+        torch.manual_seed(77)
+        out = m(x)
+        torch.nn.functional.cross_entropy(out, y).backward()
+        return out.detach().clone(), [p.grad.clone() for p in m.parameters()]
+    try:
+        ops.X3_HALF_TILES = half
+        for train in (False, True):
+            a, ga = run(2, train)
+            b, gb = run(0, train)
+            assert torch.isfinite(a).all() and torch.equal(a, b), (train, (a - b).abs().max().item())
+            gmax = max(float(q.abs().max()) for q in gb)
+            for (k, _), p, q in zip(m.named_parameters(), ga, gb):
+                # 2 CTAs accumulate ~6,500 window-steps each in TMEM before the fixed-order reduction, 148 CTAs ~90: a different
+                # fp32 summation order (measured: 1.7e-5 of the largest gradient on lstm.weight_ih_l0, whose input is x / 16)
+                assert (p - q).abs().max().item() <= 5e-5 * gmax, (train, k, (p - q).abs().max().item(), gmax)
+    finally:
+        _lib.call("na_set_tuning", b"train_max_ctas", 0)
+        ops.X3_HALF_TILES = saved
