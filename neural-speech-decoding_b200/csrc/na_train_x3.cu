@@ -35,6 +35,7 @@ namespace tc {
 constexpr int kTxThreads = 14 * 32;
 constexpr int kTxMmaWarp = 12, kTxTmaWarp = 13;
 constexpr int kTxStages = 3;
+constexpr uint32_t kTxAccCols = 256;      // forward: TMEM column stride of the two gate accumulators (192 gates + 16 score columns)
 
 __device__ __forceinline__ int64_t tclx_off(int t, int ntiles, int tile, int chunk, int row) {       // fp16 elements
     return ((((int64_t)t * ntiles + tile) * 12 + chunk) * kRows + row) * 8;
@@ -204,63 +205,68 @@ lstm_fwd_x3_kernel(const __half* __restrict__ in,                   // L0: XS;  
             const uint64_t d_b = umma_desc(smem_u32(S.b), kBStride, 128);
             const uint64_t d_h = umma_desc(smem_u32(S.h), kAChunk, 128);
             const uint64_t d_bias = umma_desc(a_ones, kAChunk, 128);                              // (ones | zeros)
-            for (int t = 0; t < T; ++t, ++in_cnt) {
+            // Two accumulators (2 x 256 TMEM columns): the input + bias part of step t+1 does not depend on h_t, so it is issued
+            // right after the recurrent part of step t and runs under the epilogue of step t; only the 9 recurrent MMAs of a step
+            // (of 12 / 19) stay on the critical path h_t -> gates -> h_{t+1}.  Accumulator (t+1) & 1 was last read by the epilogue of
+            // step t-1, whose h_ready this warp has already consumed.
+            auto issue_in = [&](const int t) {
                 const uint32_t s = in_cnt % kTxStages, u = in_cnt / kTxStages;
+                ++in_cnt;
                 mbar_wait(&S.in_full[s], u & 1);
-                if (t >= 1) { mbar_wait(&S.h_ready, hr_cnt & 1); ++hr_cnt; }
                 tc_fence_after();
+                const uint32_t acc = tmem_d + (uint32_t)(t & 1) * kTxAccCols;
                 const uint32_t xs = smem_u32(S.in[s]);
                 if (LAYER == 0) {
                     if (leader) {
                         // (x_hi | ones) . (Wih_hi | bias);  (x_hi | zeros) . (Wih_lo | *);  (x_lo | zeros) . (Wih_hi | *)
-                        umma_bf16_i(tmem_d, umma_desc(xs, a_ones - xs, 128), d_b, kIdescG, 0u);
-                        umma_bf16_i(tmem_d, umma_desc(xs, a_zero - xs, 128), desc_adv(d_b, 8 * kBStride), kIdescG, 1u);
-                        umma_bf16_i(tmem_d, umma_desc(xs + kAChunk, a_zero - (xs + kAChunk), 128), d_b, kIdescG, 1u);
-                    }
-                    if (t >= 1) {
-#pragma unroll
-                        for (int i = 0; i < 3; ++i)
-                            if (leader) {
-                                umma_bf16_i(tmem_d, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_b, (2 + 2 * i) * kBStride), kIdescG, 1u);
-                                umma_bf16_i(tmem_d, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_b, (9 + 2 * i) * kBStride), kIdescG, 1u);
-                                umma_bf16_i(tmem_d, desc_adv(d_h, (6 + 2 * i) * kAChunk), desc_adv(d_b, (2 + 2 * i) * kBStride), kIdescG, 1u);
-                            }
+                        umma_bf16_i(acc, umma_desc(xs, a_ones - xs, 128), d_b, kIdescG, 0u);
+                        umma_bf16_i(acc, umma_desc(xs, a_zero - xs, 128), desc_adv(d_b, 8 * kBStride), kIdescG, 1u);
+                        umma_bf16_i(acc, umma_desc(xs + kAChunk, a_zero - (xs + kAChunk), 128), d_b, kIdescG, 1u);
                     }
                 } else {
                     const uint64_t d_in = umma_desc(xs, kAChunk, 128);
-                    if (leader) umma_bf16_i(tmem_d, d_bias, desc_adv(d_b, 12 * kBStride), kIdescG, 0u);
+                    if (leader) umma_bf16_i(acc, d_bias, desc_adv(d_b, 12 * kBStride), kIdescG, 0u);
 #pragma unroll
                     for (int i = 0; i < 3; ++i)
                         if (leader) {
-                            umma_bf16_i(tmem_d, desc_adv(d_in, 2 * i * kAChunk), desc_adv(d_b, 2 * i * kBStride), kIdescG, 1u);
-                            umma_bf16_i(tmem_d, desc_adv(d_in, 2 * i * kAChunk), desc_adv(d_b, (13 + 2 * i) * kBStride), kIdescG, 1u);
-                            umma_bf16_i(tmem_d, desc_adv(d_in, (6 + 2 * i) * kAChunk), desc_adv(d_b, 2 * i * kBStride), kIdescG, 1u);
+                            umma_bf16_i(acc, desc_adv(d_in, 2 * i * kAChunk), desc_adv(d_b, 2 * i * kBStride), kIdescG, 1u);
+                            umma_bf16_i(acc, desc_adv(d_in, 2 * i * kAChunk), desc_adv(d_b, (13 + 2 * i) * kBStride), kIdescG, 1u);
+                            umma_bf16_i(acc, desc_adv(d_in, (6 + 2 * i) * kAChunk), desc_adv(d_b, 2 * i * kBStride), kIdescG, 1u);
                         }
-                    if (t >= 1) {
-#pragma unroll
-                        for (int i = 0; i < 3; ++i)
-                            if (leader) {
-                                umma_bf16_i(tmem_d, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_b, (6 + 2 * i) * kBStride), kIdescG, 1u);
-                                umma_bf16_i(tmem_d, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_b, (19 + 2 * i) * kBStride), kIdescG, 1u);
-                                umma_bf16_i(tmem_d, desc_adv(d_h, (6 + 2 * i) * kAChunk), desc_adv(d_b, (6 + 2 * i) * kBStride), kIdescG, 1u);
-                            }
-                    }
                 }
                 if (leader) umma_commit(&S.in_empty[s]);
+            };
+            issue_in(0);
+            for (int t = 0; t < T; ++t) {
+                const uint32_t acc = tmem_d + (uint32_t)(t & 1) * kTxAccCols;
+                if (t >= 1) {
+                    mbar_wait(&S.h_ready, hr_cnt & 1); ++hr_cnt;
+                    tc_fence_after();
+                    constexpr int kRecHi = LAYER == 0 ? 2 : 6, kRecLo = LAYER == 0 ? 9 : 19;      // first W_hh chunk (hi / lo) of the image
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        if (leader) {
+                            umma_bf16_i(acc, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_b, (kRecHi + 2 * i) * kBStride), kIdescG, 1u);
+                            umma_bf16_i(acc, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_b, (kRecLo + 2 * i) * kBStride), kIdescG, 1u);
+                            umma_bf16_i(acc, desc_adv(d_h, (6 + 2 * i) * kAChunk), desc_adv(d_b, (kRecHi + 2 * i) * kBStride), kIdescG, 1u);
+                        }
+                }
                 if (leader) umma_commit(&S.d_full);
+                if (t + 1 < T) issue_in(t + 1);
             }
             // the last h of the tile has been written (and the accumulator drained)
             mbar_wait(&S.h_ready, hr_cnt & 1); ++hr_cnt;
             tc_fence_after();
             if (LAYER == 1) {   // flush: score of the last step into the 16 score columns
                 const uint64_t d_bs = desc_adv(d_b, kN * 16);
-                if (leader) umma_bf16_i(tmem_d + kN, d_bias, desc_adv(d_bs, 12 * kBStride), kX3IdescFlush, 0u);
+                const uint32_t accf = tmem_d + (uint32_t)(T & 1) * kTxAccCols + kN;        // the "next" accumulator's score columns
+                if (leader) umma_bf16_i(accf, d_bias, desc_adv(d_bs, 12 * kBStride), kX3IdescFlush, 0u);
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
                     if (leader) {
-                        umma_bf16_i(tmem_d + kN, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_bs, (6 + 2 * i) * kBStride), kX3IdescFlush, 1u);
-                        umma_bf16_i(tmem_d + kN, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_bs, (19 + 2 * i) * kBStride), kX3IdescFlush, 1u);
-                        umma_bf16_i(tmem_d + kN, desc_adv(d_h, (6 + 2 * i) * kAChunk), desc_adv(d_bs, (6 + 2 * i) * kBStride), kX3IdescFlush, 1u);
+                        umma_bf16_i(accf, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_bs, (6 + 2 * i) * kBStride), kX3IdescFlush, 1u);
+                        umma_bf16_i(accf, desc_adv(d_h, 2 * i * kAChunk), desc_adv(d_bs, (19 + 2 * i) * kBStride), kX3IdescFlush, 1u);
+                        umma_bf16_i(accf, desc_adv(d_h, (6 + 2 * i) * kAChunk), desc_adv(d_bs, (6 + 2 * i) * kBStride), kX3IdescFlush, 1u);
                     }
                 if (leader) umma_commit(&S.d_full);
             }
@@ -307,27 +313,41 @@ lstm_fwd_x3_kernel(const __half* __restrict__ in,                   // L0: XS;  
                 }
                 mbar_wait(&S.d_full, df_cnt & 1); ++df_cnt;
                 tc_fence_after();
+                const uint32_t acc = tmem_d + (uint32_t)(t & 1) * kTxAccCols;
                 if (LAYER == 1) {
                     uint32_t sc2[2];
-                    x3_tmem_ld2(tmem_d + lane_base + kN, sc2);
+                    x3_tmem_ld2(acc + lane_base + kN, sc2);
                     if (t >= 1) pool(__uint_as_float(sc2[0]));       // score of h_{t-1}, which is still in hprev
                 }
+                // h_t goes to shared memory first; the saves go to HBM only AFTER the fence + arrive that release h_t to the tensor
+                // pipe (the fence otherwise waits for the global stores, on the step's critical path)
+                uint32_t hi[4 * kNB], lo[4 * kNB];
 #pragma unroll
                 for (int pr = 0; pr < kNB; ++pr) {                    // pairs of granules = one 8-unit chunk
-                    uint32_t v[32], hi[4], lo[4];
+                    uint32_t v[32];
                     const int chunk = chunk0 + pr;
-                    tmem_ld32(tmem_d + lane_base + chunk * 32, v);
+                    tmem_ld32(acc + lane_base + chunk * 32, v);
                     cell_granule_exact(v, c + pr * 8, hprev + pr * 8);
                     cell_granule_exact(v + 16, c + pr * 8 + 4, hprev + pr * 8 + 4);
-                    split_pack8(hprev + pr * 8, hi, lo);
-                    const uint4 vhi = make_uint4(hi[0], hi[1], hi[2], hi[3]), vlo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    st_shared_v4(S.h + chunk * kAChunk + row * 16, hi[0], hi[1], hi[2], hi[3]);
-                    st_shared_v4(S.h + (6 + chunk) * kAChunk + row * 16, lo[0], lo[1], lo[2], lo[3]);
+                    split_pack8(hprev + pr * 8, reinterpret_cast<uint32_t(&)[4]>(hi[pr * 4]), reinterpret_cast<uint32_t(&)[4]>(lo[pr * 4]));
+                    st_shared_v4(S.h + chunk * kAChunk + row * 16, hi[pr * 4], hi[pr * 4 + 1], hi[pr * 4 + 2], hi[pr * 4 + 3]);
+                    st_shared_v4(S.h + (6 + chunk) * kAChunk + row * 16, lo[pr * 4], lo[pr * 4 + 1], lo[pr * 4 + 2], lo[pr * 4 + 3]);
+                    if (HALF) {                                       // the other row copy
+                        st_shared_v4(S.h + chunk * kAChunk + (row ^ 64) * 16, hi[pr * 4], hi[pr * 4 + 1], hi[pr * 4 + 2], hi[pr * 4 + 3]);
+                        st_shared_v4(S.h + (6 + chunk) * kAChunk + (row ^ 64) * 16, lo[pr * 4], lo[pr * 4 + 1], lo[pr * 4 + 2], lo[pr * 4 + 3]);
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(&S.h_ready);
+#pragma unroll
+                for (int pr = 0; pr < kNB; ++pr) {
+                    const int chunk = chunk0 + pr;
+                    const uint4 vhi = make_uint4(hi[pr * 4], hi[pr * 4 + 1], hi[pr * 4 + 2], hi[pr * 4 + 3]);
+                    const uint4 vlo = make_uint4(lo[pr * 4], lo[pr * 4 + 1], lo[pr * 4 + 2], lo[pr * 4 + 3]);
                     *reinterpret_cast<uint4*>(h_out + tclx_off(t, ntiles, tile, chunk, row)) = vhi;
                     *reinterpret_cast<uint4*>(h_out + tclx_off(t, ntiles, tile, 6 + chunk, row)) = vlo;
-                    if (HALF) {                                       // the other row copy
-                        st_shared_v4(S.h + chunk * kAChunk + (row ^ 64) * 16, hi[0], hi[1], hi[2], hi[3]);
-                        st_shared_v4(S.h + (6 + chunk) * kAChunk + (row ^ 64) * 16, lo[0], lo[1], lo[2], lo[3]);
+                    if (HALF) {
                         *reinterpret_cast<uint4*>(h_out + tclx_off(t, ntiles, tile, chunk, row ^ 64)) = vhi;
                         *reinterpret_cast<uint4*>(h_out + tclx_off(t, ntiles, tile, 6 + chunk, row ^ 64)) = vlo;
                     }
@@ -350,15 +370,12 @@ lstm_fwd_x3_kernel(const __half* __restrict__ in,                   // L0: XS;  
                         }
                     }
                 }
-                tc_fence_before();
-                fence_proxy_async_smem();
-                mbar_arrive(&S.h_ready);
             }
             if (LAYER == 1) {
                 mbar_wait(&S.d_full, df_cnt & 1); ++df_cnt;              // flush: score of the last step
                 tc_fence_after();
                 uint32_t sc2[2];
-                x3_tmem_ld2(tmem_d + lane_base + kN, sc2);
+                x3_tmem_ld2(tmem_d + (uint32_t)(T & 1) * kTxAccCols + lane_base + kN, sc2);
                 tc_fence_before();
                 pool(__uint_as_float(sc2[0]));
                 if (bwin < B) {
