@@ -691,7 +691,7 @@ def train_leg(args, world, rank, dev):
         def step():
             trainer.step(batches, global_batch=per_gpu * world)
 
-        ms = time_steps(step, steps, 1, world, dev)
+        ms = time_steps(step, steps, 3, world, dev)      # 3 warm-up steps (1 left NCCL / allocator warm-up inside the timed region at N = 8)
         wps = world * per_gpu * steps / (ms * 1e-3)
         return {"value": wps, "unit": "windows/s", "ms_per_step": ms / steps, "global_batch": per_gpu * world,
                 "per_gpu_batch": per_gpu, "micro_batch": micro, "micro_batches": micros, "steps": steps,
@@ -721,7 +721,7 @@ def train_leg(args, world, rank, dev):
         dist.all_reduce(err, op=dist.ReduceOp.MAX)
         return float(err.item())
 
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 5))
     tc = run(torch.bfloat16, args.train_batch, args.train_micro, steps)
     tc.update({"dtype": "fp16 tensor-core operands (tcgen05), fp32 accumulate / cell state / weight gradients",
                "optimizer": "Adam lr=1e-3 (optim.FusedAdam: torch.optim.Adam's update, one launch for all 16 tensors)",
@@ -729,7 +729,7 @@ def train_leg(args, world, rank, dev):
                "allreduce": "one flat fp32 bucket (127 KB), NCCL" if world > 1 else "none (1 GPU)",
                "parity": "tests/test_gpu_bf16.py: gradients within 2e-2 of the fp64 oracle",
                "frac_of_bf16_sustained_peak": tc["achieved_tflops_per_gpu"] / measured_peaks()["bf16_tflops_sustained"]})
-    fp = run(torch.float32, args.train_batch, args.train_micro, min(steps, 2))      # the same configs[2] step on the fp32-contract tier
+    fp = run(torch.float32, args.train_batch, args.train_micro, min(steps, 3))      # the same configs[2] step on the fp32-contract tier
     tc["fp32_exact"] = {k: fp[k] for k in ("value", "unit", "ms_per_step", "global_batch", "micro_batch", "achieved_tflops_per_gpu")}
     tc["fp32_exact"]["parity"] = "tests/test_gpu_parity.py: logits and gradients within 1e-5 of the fp64 truth / the reference's autograd"
     tc["fp32_exact"]["kernels"] = ("lstm_fwd_x3_kernel<0/1>, lstm_bwd_x3_kernel<1/0>, lstm_wgrad_x3_kernel<1/0> (tcgen05, operands split into "

@@ -3,7 +3,8 @@ exchange step per optimizer step -- a single flat fp32 gradient bucket all-reduc
 (NVLink 5 / NVSwitch), then an identical optimizer step on every rank.  SURVEY 8(e).
 
 The model has 31,764 parameters (127 KB of gradients): the all-reduce is latency-bound, so there is
-nothing to overlap or bucket -- every parameter's ``.grad`` is a VIEW into one contiguous buffer, the
+nothing to overlap or bucket -- every parameter's ``.grad`` is a VIEW into one contiguous buffer (the scalar loss rides in one
+extra slot behind the gradients, so a step issues a single collective), the
 backward kernels' results are accumulated straight into it and the collective runs on that buffer
 in place (no flatten / unflatten copies).
 
@@ -24,14 +25,17 @@ class FlatGradBucket:
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        # one extra slot behind the gradients carries the scalar loss through the SAME collective (one launch instead of two)
+        self.store = torch.zeros(n + 1, dtype=torch.float32, device=dev)
+        self.flat = self.store[:n]
+        self.loss_slot = self.store[n:]
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
 
     def zero_(self) -> None:
-        self.flat.zero_()
+        self.store.zero_()
 
     def check_views(self) -> None:
         """Autograd accumulates in place into an existing .grad; if someone replaced it
@@ -72,9 +76,10 @@ class DataParallelTrainer:
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
         if self.world_size > 1:
-            # one exchange step: gradients and the scalar loss (for logging) in two tiny collectives
-            dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=self.group)
-            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.group)
+            # one exchange step: the gradients and, in the slot behind them, the scalar loss (for logging) -- ONE collective
+            self.bucket.loss_slot.copy_(total.reshape(1))
+            dist.all_reduce(self.bucket.store, op=dist.ReduceOp.SUM, group=self.group)
+            total = self.bucket.loss_slot[0].clone()
         return total
 
     def step(self, micro_batches: Iterable[Tuple[torch.Tensor, torch.Tensor]], global_batch: int) -> torch.Tensor:
