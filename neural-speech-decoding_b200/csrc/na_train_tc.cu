@@ -400,7 +400,7 @@ lstm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ act_in,     // TCL [T][NT
 #pragma unroll
             for (int s = 0; s < kBwdStages; ++s) {
                 reinterpret_cast<uint4*>(S.act[s] + C::kOnesChunk * kAChunk)[i] = ones;
-                if (KI == 48) reinterpret_cast<uint4*>(S.act[s] + 13 * kAChunk)[i] = zero;
+                if constexpr (KI == 48) reinterpret_cast<uint4*>(S.act[s] + 13 * kAChunk)[i] = zero;
             }
         if (tid == 0) {
             // fused head backward: the epilogue threads read h_t out of the stage of step t+1, so a stage is free once the W
