@@ -832,13 +832,19 @@ class DecoderFunctionTC(torch.autograd.Function):
             nt = (B + 63) // 64
             if nt * 64 != B:
                 xin = torch.cat([xin, xin.new_zeros((nt * 64 - B, T, C))])
-            xin = xin.reshape(nt, 64, T, C).repeat(1, 2, 1, 1).reshape(nt * TC_TILE, T, C)       # rows 64..127 mirror rows 0..63
             if mask is not None:                                                                 # window b -> row (b // 64) * 128 + b % 64
                 b_idx = torch.arange(B, device=x.device)
                 remapped = mask.new_zeros((T, nt * TC_TILE, mask.shape[2]))
                 remapped[:, (b_idx // 64) * TC_TILE + b_idx % 64] = mask[:, :B]
                 mask = remapped
-        xt = window_zscore(xin, T, T, zscore, True, NA_F16, TC_TILE)
+        if half:
+            # pack first (fp16, time-major, 64 windows per tile), then mirror: rows 64..127 of every tile repeat rows 0..63 -- on
+            # the 16-byte packed rows this copies a quarter of the bytes that mirroring the fp32 windows did
+            xt = window_zscore(xin, T, T, zscore, True, NA_F16, 64)
+            xt = xt.reshape(T, nt, 64, C)
+            xt = torch.stack((xt, xt), dim=2).reshape(T, nt * TC_TILE, C)       # (the batched cat kernel: 1 KB contiguous runs)
+        else:
+            xt = window_zscore(xin, T, T, zscore, True, NA_F16, TC_TILE)
         packed = decoder_pack_bf16(lstm_flat)
         h0, h0d, c0, h1, c1, zpool, stats = lstm2_fwd_train_bf16(xt, packed, mask, seed, thresh16, scale1, head[0], head[1], B, half_stride)
         logits, _ = head_tail_fwd(zpool, head, rrelu_slope, drop2_mask, scale, False)
