@@ -18,6 +18,12 @@
 //      re-used as MN-major operands -- no transposes, no dgates round trip through HBM)          D_W
 //   dW (+ db via the ones column) accumulates in TMEM in fp32 over ALL steps and tiles of the CTA;
 //   per-CTA partials are reduced in a fixed order by a second tiny kernel (deterministic).
+// Pipeline of a step (round 2, second pass): only R is on the critical path d(gates) -> dh_rec -> d(gates).  The MMA warp issues
+// R(t+1) as soon as d(gates) of step t+1 are in shared memory (dg_ready) and commits r_full; W(t+1) follows and releases the
+// stage (act_free) and d(gates) (w_done); G(t-1) is issued once the epilogue has drained G(t) out of TMEM (g_free) and runs
+// under the epilogue of step t.  The [in | 1 | h] stages form a 2- or 3-deep TMA ring (bwd_stages); with the fused head
+// backward the epilogue threads read h_t out of the stage of step t+1, which is therefore freed by the W commit AND 384 thread
+// arrivals.  Half tiles additionally evaluate the activations before waiting for R.
 #include "na_tc_common.cuh"
 
 namespace na {
