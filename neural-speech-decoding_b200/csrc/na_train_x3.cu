@@ -20,6 +20,12 @@
 //                            MN-major straight from the saved tile-chunk slabs), fp32 accumulation in TMEM over all the
 //                            work items of a CTA, per-CTA partials reduced in a fixed order (bit-reproducible).
 //
+// Step pipelines (round 2, second pass).  Forward: two gate accumulators; the input + bias MMAs of step t+1 are issued right
+// behind the recurrent MMAs of step t (only 9 of a step's 12 / 19 MMAs wait for h_t), saves go to HBM after the release fence.
+// BPTT: two gate accumulators as well (the recompute of step t-1 runs under the epilogue of step t); half tiles evaluate the
+// activations under R.  Weight gradients, half tiles: d(gates) are stored compactly (64 rows per chunk) and the kernel runs
+// four half-size stages.
+//
 // Layouts (tile = 128 consecutive windows, chunk = [128 rows][8 fp16] = 2 KB, the UMMA no-swizzle core-matrix layout):
 //   XS    fp16 [T][NT][2][128][8]     x / 16 split: chunk 0 = hi, 1 = lo                      (na_x3_split_input)
 //   TCLX  fp16 [T][NT][12][128][8]    h split: chunks 0-5 = hi (units 8c..8c+7), 6-11 = lo
