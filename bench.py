@@ -665,7 +665,7 @@ def stress_leg(dev, peaks):
 def train_leg(args, world, rank, dev):
     """BASELINE configs[2]: data-parallel training of the 3-class decoder on synthetic EEG, GLOBAL batch
     65,536 (fixed as N grows: per-GPU batch 65,536/N, micro-batched), train mode (inter-layer dropout,
-    RReLU noise, dropout), mean CE over the global batch, one flat NCCL all-reduce, Adam (torch).
+    RReLU noise, dropout), mean CE over the global batch, one flat NCCL all-reduce, Adam (optim.FusedAdam: one launch).
     Headline: tensor-core tier; the exact-fp32 tier is timed beside it on a bounded global batch."""
     from neural_speech_decoding_b200.lstm_eeg_model import EEG_LSTM
     from neural_speech_decoding_b200.dp import DataParallelTrainer
