@@ -22,5 +22,7 @@ for B in [int(a) for a in sys.argv[1:] if a.isdigit()] or [8192]:
         from torch.profiler import profile, ProfilerActivity
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             step(); torch.cuda.synchronize()
-        rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:12]
+        rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:26]
+        allk = [r for r in prof.key_averages() if r.device_time_total > 0]
+        print(f"   device total {sum(r.device_time_total for r in allk)/1e3:.3f} ms in {sum(r.count for r in allk)} launches")
         for r in rows: print(f"   {r.device_time_total/1e3:8.3f} ms  x{r.count:3d}  {r.key[:100]}")
