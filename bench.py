@@ -400,7 +400,13 @@ def run_gpu_arm(args):
         h0 = ops.lstm_layer_fwd(xt, packed[0][0], packed[0][1], None, 1.0, False)[0]
         del xt
         ms_l1 = time_steps(lambda: ops.lstm_layer_fwd(h0, packed[1][0], packed[1][1], None, 1.0, False)[0], 3, 1, 1, dev) / 3
+        # K4 / K5 alone: the standalone pooling head over a [T, Bp, 48] fp32 tensor (fused into the inference
+        # kernels; standalone in the FFMA tier), and the 10-trial mean
+        ms_k4 = time_steps(lambda: ops.head_fwd(h0, n_win, head, None, None, 1.0, True, False), 3, 1, 1, dev) / 3
+        k4_bytes = h0.numel() * 4
         del h0
+        pr = torch.rand(R, B, NC, device=dev)
+        ms_k5 = time_steps(lambda: ops.trial_mean(pr), reps, 2, 1, dev) / reps
     x3_tflops = FWD_FLOPS_PER_WINDOW * n_win / (ms_x3 * 1e-3) / 1e12
     tc_tflops = FWD_FLOPS_PER_WINDOW * n_win / (ms_tc * 1e-3) / 1e12
     l1_tflops = L1_KERNEL_FLOPS_PER_WINDOW * n_win / (ms_l1 * 1e-3) / 1e12
@@ -524,6 +530,15 @@ def run_gpu_arm(args):
             "k1_window_pack": {"kernel": "window_pack16_tmp_kernel (fp32 -> time-major fp16)", "bound": "hbm",
                                "achieved": n_win * T * C * 6 / (ms_pack16 * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                "unit": "GB/s", "frac": n_win * T * C * 6 / (ms_pack16 * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+            "k4_head": {"kernel": "head_fwd_kernel (attention score, online softmax over time, pooling, LayerNorm, MLP, softmax; standalone)",
+                        "bound": "hbm", "achieved": k4_bytes / (ms_k4 * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": k4_bytes / (ms_k4 * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms_per_launch": ms_k4,
+                        "note": "h [625, Bp, 48] fp32 read once (120,000 B per window); in the tensor-core inference kernels K4 is fused and "
+                                "this traffic does not exist"},
+            "k5_trial_mean": {"kernel": "trial_mean_kernel (ordered fp32 sum of 10 trials, one division: tester.py:54,89,97)", "bound": "hbm",
+                              "achieved": (R + 1) * B * NC * 4 / (ms_k5 * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                              "frac": (R + 1) * B * NC * 4 / (ms_k5 * 1e-3) / 1e9 / peaks["hbm_gbs"], "us_per_launch": ms_k5 * 1e3,
+                              "note": "540 KB per launch: launch-latency-bound, not HBM-bound"},
             "csv_parse": {"kernel": "csv_parse_kernel (4,096 files of 625x8 '%.7f' text -> fp32; includes the status D2H check)",
                           "bound": "hbm", "achieved": csv_bytes / (ms_csv * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                           "frac": csv_bytes / (ms_csv * 1e-3) / 1e9 / peaks["hbm_gbs"], "files_per_s": 4096 / (ms_csv * 1e-3)},
